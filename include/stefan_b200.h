@@ -1,0 +1,112 @@
+/* stefan_b200.h -- C ABI of the B200-native StefanProblem hot path.
+ *
+ * One shared library (libstefan_b200.so, CUDA kernels built for sm_100a) behind
+ * plain-C entry points: pointers and sizes only, int status returns (0 = ok, never
+ * throws across the boundary; stefan_last_error() gives the message), opaque
+ * handles, caller-owned DEVICE buffers unless the name ends in _host, an explicit
+ * cudaStream_t passed as void*.  No hidden global state; one handle per (GPU,
+ * host thread).  There is NO CPU fallback: every compute entry point needs a
+ * CUDA device.
+ *
+ * The reference (ArjunNarayanan/StefanProblem) has no FFI of its own; the seam
+ * these entry points replace is its Julia call surface, cited per entry as
+ * file:line under /root/reference.  The Julia `ccall` module that keeps that
+ * call surface is julia/StefanB200.jl; its Python twin (used by all tests,
+ * because no Julia runtime exists in the build image) is stefanproblem_b200/.
+ *
+ * Dof order is the reference's: cells y-fastest (cell = i*ny + j), nodes
+ * consecutive per cell, eta-node fastest (a = ix*(p+1) + iy), dof = node*dpn + c.
+ * All reals are fp64.
+ */
+#ifndef STEFAN_B200_H
+#define STEFAN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  STEFAN_OK = 0,
+  STEFAN_BAD_ARGUMENT = 1,
+  STEFAN_CUDA_ERROR = 2,
+  STEFAN_UNSUPPORTED = 3,
+  STEFAN_OUT_OF_RANGE = 4,
+  STEFAN_CAPACITY = 5
+};
+
+const char* stefan_last_error(void);
+int stefan_version(void);
+
+/* ------------------------------------------------------------------ tables
+ * 1-D reference-element matrices the uniform-mesh operators factor into
+ * (host only, no GPU needed): mass sum_q w N N', stiffness sum_q w N' N'',
+ * advection sum_q w N' N', and N'(-1), N'(+1).  Row-major (order+1)^2 / (order+1).
+ * Restates PolynomialBasis.LagrangeTensorProductBasis + tensor_product_quadrature
+ * as used by IP_gradient_operator.jl:1-9 and LDG_div_operator.jl:1-11. */
+int stefan_reference_tables(int32_t order, int32_t numqp, double* mass, double* stiff,
+                            double* adv, double* dleft, double* dright,
+                            double* qpoints, double* qweights);
+
+/* ------------------------------------------------------------------- IP-DG
+ * Symmetric interior-penalty operator for -div(k grad T) on an uncut uniform
+ * nx x ny mesh of Q_order cells, two phases (phase +1 -> k1, -1 -> k2).
+ *
+ * `terms` selects which of the reference's assemble_* passes are present
+ * (STEFAN_IP_* below, OR-ed); STEFAN_IP_REFERENCE_SYSTEM is what
+ * assemble_interior_penalty_linear_system! (IP_assembly.jl:1-80) assembles on an
+ * uncut mesh, where faces between unlike phases are NOT coupled
+ * (IP_flux_operator.jl:181).  The INTERFACE_* and ROBIN bits add the reference's
+ * face-level interface terms (assemble_face_flux_operator! IP_flux_operator.jl:35-118,
+ * assemble_face_penalty_operator! IP_penalty_operator.jl:21-65,
+ * assemble_face_robin_operator! IP_robin_interface_operator.jl:1-45) on the
+ * mesh faces between unlike phases, side 1 = the +1 cell.
+ * variant 1 = the legacy boundary form that reproduces the stored
+ * uncut_mesh_tests/IP_convergence.csv (boundary operator -M', rhs penalty only). */
+enum {
+  STEFAN_IP_VOLUME = 1,               /* assemble_gradient_operator!            IP_gradient_operator.jl:29-57 */
+  STEFAN_IP_INTERELEMENT_FLUX = 2,    /* assemble_interelement_flux_operator!   IP_flux_operator.jl:202-256 */
+  STEFAN_IP_INTERELEMENT_PENALTY = 4, /* assemble_interelement_penalty_operator! IP_penalty_operator.jl:134-181 */
+  STEFAN_IP_INTERFACE_FLUX = 8,
+  STEFAN_IP_INTERFACE_PENALTY = 16,
+  STEFAN_IP_BOUNDARY_FLUX = 32,       /* assemble_boundary_flux_operator!       IP_flux_operator.jl:393-444 */
+  STEFAN_IP_BOUNDARY_PENALTY = 64,    /* assemble_boundary_penalty_operator!    IP_penalty_operator.jl:286-329 */
+  STEFAN_IP_ROBIN = 128,              /* assemble_robin_operator!               IP_robin_interface_operator.jl:76-99 */
+  STEFAN_IP_REFERENCE_SYSTEM = 1 | 2 | 4 | 32 | 64,
+  STEFAN_IP_ALL_TERMS = 255
+};
+
+typedef struct {
+  int32_t nx, ny;      /* cells of the local slab */
+  double hx, hy;       /* cell widths */
+  int32_t order;       /* 1..3 */
+  int32_t numqp;       /* Gauss points per direction (reference: order+1) */
+  double k1, k2;       /* conductivities of phase +1 / -1 */
+  double penalty;      /* penaltyfactor / min element size (set by the caller, as in the reference) */
+  double lambda, Tm;   /* Robin coefficient and melting temperature */
+  int32_t variant;     /* 0 current, 1 legacy_boundary */
+  int32_t terms;       /* STEFAN_IP_* */
+} stefan_ipdg_params;
+
+typedef struct stefan_ipdg stefan_ipdg;
+
+/* phase: host int8[nx*ny] (+1/-1; NULL = all +1).  phase_lo / phase_hi: host
+ * int8[ny], the phases of the neighbouring slab's adjacent cell column when the
+ * mesh is partitioned by cell columns across GPUs (NULL = domain boundary). */
+int stefan_ipdg_create(const stefan_ipdg_params* params, const int8_t* phase,
+                       const int8_t* phase_lo, const int8_t* phase_hi, stefan_ipdg** out);
+int stefan_ipdg_destroy(stefan_ipdg* h);
+int64_t stefan_ipdg_ndofs(const stefan_ipdg* h);
+
+/* y = A x (replaces sparse_operator(sysmatrix, mesh, 1) * x).  x_lo / x_hi: the
+ * neighbouring slabs' adjacent cell columns (ny*NF doubles each; local or peer
+ * device memory), required iff the handle has phase_lo / phase_hi.
+ * algo 0 = streaming kernel (production), 1 = simple one-thread-per-cell kernel. */
+int stefan_ipdg_apply(stefan_ipdg* h, const double* x, double* y, const double* x_lo,
+                      const double* x_hi, int32_t algo, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STEFAN_B200_H */

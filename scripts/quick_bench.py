@@ -1,0 +1,46 @@
+"""Development timing of the IP-DG apply kernels (CUDA events, inputs > L2)."""
+import sys
+import numpy as np
+import torch
+sys.path.insert(0, ".")
+from stefanproblem_b200 import cutcelldg as cc
+
+def run(order, nx, ny, two_phase, algo, reps=20):
+    basis = cc.LagrangeTensorProductBasis(2, order)
+    phase = None
+    if two_phase:
+        i, j = np.divmod(np.arange(nx * ny), ny)
+        cx, cy = (i + 0.5) / nx, (j + 0.5) / ny
+        phase = np.where((cx - 0.5) ** 2 + (cy - 0.5) ** 2 < 0.16, -1, 1).astype(np.int8)
+    mesh = cc.UniformMesh([0, 0], [1, 1], [nx, ny], basis, phase=phase)
+    op = cc.IPOperator(mesh, order, order + 1, 1.0, 2.0, 1e3 * nx, 1.0, 0.5, "current", 255)
+    x = torch.rand(op.ndofs, dtype=torch.float64, device="cuda") * 2 - 1
+    y = torch.empty_like(x)
+    for _ in range(3):
+        op.apply(x, out=y, algo=algo)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        op.apply(x, out=y, algo=algo)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    gdofs = op.ndofs / ms / 1e6
+    print(f"p={order} {nx}x{ny} two_phase={two_phase} algo={algo}: {ms:.3f} ms  {gdofs:.1f} GDOF/s  "
+          f"{16 * gdofs:.0f} GB/s  ({16 * gdofs / 6551 * 100:.1f}% of 6551)", flush=True)
+
+if __name__ == "__main__":
+    a = torch.empty(1 << 28, dtype=torch.float64, device="cuda"); b = torch.empty_like(a)
+    for _ in range(3): b.copy_(a)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10): b.copy_(a)
+    e1.record(); torch.cuda.synchronize()
+    print("copy GB/s:", 2 * a.numel() * 8 * 10 / e0.elapsed_time(e1) / 1e6, flush=True)
+    del a, b
+    for order, n in ((1, 5000), (2, 3334), (3, 2500)):
+        for tp in (False, True):
+            for algo in (0, 1):
+                run(order, n, n, tp, algo)

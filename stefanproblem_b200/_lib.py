@@ -1,0 +1,75 @@
+"""ctypes binding of libstefan_b200.so (the C ABI declared in include/stefan_b200.h).
+
+The library is built in-tree by `stefanproblem_b200.build` (nvcc, sm_100a).  There
+is no fallback of any kind: if the shared library is missing or a CUDA device is
+not available the compute entry points raise.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libstefan_b200.so")
+
+c_double_p = ctypes.POINTER(ctypes.c_double)
+c_int8_p = ctypes.POINTER(ctypes.c_int8)
+c_int64_p = ctypes.POINTER(ctypes.c_int64)
+
+
+class StefanError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(f"libstefan_b200 status {status}: {message}")
+        self.status = status
+
+
+class IpdgParams(ctypes.Structure):
+    """`stefan_ipdg_params` (include/stefan_b200.h)."""
+    _fields_ = [
+        ("nx", ctypes.c_int32), ("ny", ctypes.c_int32),
+        ("hx", ctypes.c_double), ("hy", ctypes.c_double),
+        ("order", ctypes.c_int32), ("numqp", ctypes.c_int32),
+        ("k1", ctypes.c_double), ("k2", ctypes.c_double),
+        ("penalty", ctypes.c_double),
+        ("lam", ctypes.c_double), ("Tm", ctypes.c_double),
+        ("variant", ctypes.c_int32), ("terms", ctypes.c_int32),
+    ]
+
+
+_SIGNATURES = {
+    "stefan_last_error": (ctypes.c_char_p, []),
+    "stefan_version": (ctypes.c_int, []),
+    "stefan_reference_tables": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32] + [c_double_p] * 7),
+    "stefan_ipdg_create": (ctypes.c_int, [ctypes.POINTER(IpdgParams), c_int8_p, c_int8_p, c_int8_p,
+                                          ctypes.POINTER(ctypes.c_void_p)]),
+    "stefan_ipdg_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "stefan_ipdg_ndofs": (ctypes.c_int64, [ctypes.c_void_p]),
+    "stefan_ipdg_apply": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
+                                         ctypes.c_void_p]),
+}
+
+_lib = None
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def lib():
+    """The loaded library; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise StefanError(-1, f"{LIB_PATH} not found: run `python -m stefanproblem_b200.build` "
+                                  "(there is no CPU fallback)")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(status):
+    if status != 0:
+        raise StefanError(status, lib().stefan_last_error().decode())

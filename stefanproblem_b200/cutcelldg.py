@@ -1,0 +1,208 @@
+"""Host-side stand-ins for the `CutCellDG` / `PolynomialBasis` objects the hot path
+is called with (uncut uniform meshes only), and the two consumers of the COO seam:
+`sparse_operator` and `rhs_vector`.
+
+In the reference, `SystemMatrix` is a growable COO triplet list that the
+`assemble_*!` functions append to, and `sparse_operator(sysmatrix, mesh, dpn)`
+turns it into a `SparseMatrixCSC`.  Here `SystemMatrix` records WHICH assemble
+passes were requested (and with what coefficients); `sparse_operator` hands that
+description to libstefan_b200.so and returns a matrix-free device operator whose
+`@` is the CUDA apply kernel.  Nothing is computed on the host.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+
+class LagrangeTensorProductBasis:
+    """`PolynomialBasis.LagrangeTensorProductBasis(dim, order)` descriptor."""
+
+    def __init__(self, dim, order):
+        if dim not in (1, 2):
+            raise ValueError("dim must be 1 or 2")
+        if order not in (1, 2, 3):
+            raise ValueError("order must be 1, 2 or 3")
+        self.dim, self.order = dim, order
+        self.nf = (order + 1) ** dim
+
+
+def number_of_basis_functions(basis):
+    return basis.nf
+
+
+def interpolation_points(basis):
+    nodes = np.linspace(-1.0, 1.0, basis.order + 1)
+    if basis.dim == 1:
+        return nodes.reshape(1, -1)
+    return np.stack([np.repeat(nodes, basis.order + 1), np.tile(nodes, basis.order + 1)])
+
+
+def reference_tables(order, numqp):
+    """1-D reference matrices from the library (host call, no GPU needed)."""
+    n = order + 1
+    M, K, C = (np.zeros((n, n)) for _ in range(3))
+    dL, dR = np.zeros(n), np.zeros(n)
+    qx, qw = np.zeros(numqp), np.zeros(numqp)
+    p = lambda a: a.ctypes.data_as(_lib.c_double_p)  # noqa: E731
+    _lib.check(_lib.lib().stefan_reference_tables(order, numqp, p(M), p(K), p(C), p(dL), p(dR),
+                                                  p(qx), p(qw)))
+    return dict(mass=M, stiff=K, adv=C, dleft=dL, dright=dR, qpoints=qx, qweights=qw)
+
+
+class UniformMesh:
+    """Uncut Cartesian DG mesh: what `DGMesh` + `CutMesh` + `MergedMesh!` give when no
+    cell is cut.  Cells y-fastest; `phase` (+1 / -1 per cell) plays `cell_sign`."""
+
+    def __init__(self, x0, widths, nelements, basis, phase=None):
+        self.x0 = np.asarray(x0, dtype=float)
+        self.widths = np.asarray(widths, dtype=float)
+        self.nx, self.ny = int(nelements[0]), int(nelements[1])
+        self.basis = basis
+        self.nf = basis.nf
+        self.ncells = self.nx * self.ny
+        self.h = self.widths / np.array([self.nx, self.ny], dtype=float)
+        if phase is None:
+            phase = np.ones(self.ncells, dtype=np.int8)
+        phase = np.ascontiguousarray(phase, dtype=np.int8).reshape(-1)
+        if phase.size != self.ncells:
+            raise ValueError("phase must have one entry per cell")
+        if not np.all(np.abs(phase) == 1):
+            raise ValueError("cell_sign must be +1 or -1 (cut cells are not supported)")
+        self.phase = phase
+
+    def number_of_cells(self):
+        return self.ncells
+
+    def number_of_nodes(self):
+        return self.ncells * self.nf
+
+    def element_size(self):
+        return self.h
+
+    def jacobian(self):
+        return 0.5 * self.h
+
+    def cell_centres(self):
+        i, j = np.divmod(np.arange(self.ncells), self.ny)
+        return (self.x0[0] + (i + 0.5) * self.h[0], self.x0[1] + (j + 0.5) * self.h[1])
+
+
+def element_size(mesh):
+    return mesh.element_size()
+
+
+def number_of_cells(mesh):
+    return mesh.number_of_cells()
+
+
+class CellQuadratures:
+    def __init__(self, mesh, numqp):
+        self.numqp = int(numqp)
+
+
+class FaceQuadratures:
+    def __init__(self, mesh, numqp):
+        self.numqp = int(numqp)
+
+
+class InterfaceQuadratures:
+    """Empty on an uncut mesh (no cell has sign 0)."""
+
+    def __init__(self, mesh=None, numqp=0):
+        self.numqp = int(numqp)
+
+
+class SystemMatrix:
+    """Description of the operator being assembled (see module docstring)."""
+
+    def __init__(self):
+        self.kind = None
+        self.spec = {}
+
+    def _merge(self, kind, **kw):
+        if self.kind is None:
+            self.kind = kind
+        elif self.kind != kind:
+            raise ValueError(f"SystemMatrix already holds a {self.kind} operator, not {kind}")
+        for key, val in kw.items():
+            if key == "terms":
+                self.spec["terms"] = self.spec.get("terms", 0) | int(val)
+            elif key in self.spec and self.spec[key] != val and val is not None:
+                raise ValueError(f"inconsistent {key}: {self.spec[key]} vs {val}")
+            elif val is not None:
+                self.spec[key] = val
+
+
+class SystemRHS:
+    def __init__(self):
+        self.kind = None
+        self.terms = []  # recorded rhs passes, evaluated by rhs_vector
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream_ptr(stream=None):
+    import torch
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return ctypes.c_void_p(s.cuda_stream)
+
+
+class IPOperator:
+    """Matrix-free `sparse_operator` of an interior-penalty system on one GPU."""
+
+    STREAM, SIMPLE = 0, 1
+
+    def __init__(self, mesh, order, numqp, k1, k2, penalty, lam=0.0, Tm=0.0,
+                 variant="current", terms=None, phase_lo=None, phase_hi=None):
+        import torch
+        if not torch.cuda.is_available():
+            raise _lib.StefanError(-1, "no CUDA device: stefanproblem_b200 has no CPU fallback")
+        if terms is None:
+            terms = 255
+        self.mesh, self.order, self.nf = mesh, order, (order + 1) ** 2
+        self.params = _lib.IpdgParams(
+            nx=mesh.nx, ny=mesh.ny, hx=float(mesh.h[0]), hy=float(mesh.h[1]), order=order,
+            numqp=numqp, k1=float(k1), k2=float(k2), penalty=float(penalty), lam=float(lam),
+            Tm=float(Tm), variant={"current": 0, "legacy_boundary": 1}[variant], terms=int(terms))
+        i8 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.int8)  # noqa: E731
+        self._plo, self._phi = i8(phase_lo), i8(phase_hi)
+        p8 = lambda a: None if a is None else a.ctypes.data_as(_lib.c_int8_p)  # noqa: E731
+        h = ctypes.c_void_p()
+        _lib.check(_lib.lib().stefan_ipdg_create(ctypes.byref(self.params), p8(mesh.phase),
+                                                 p8(self._plo), p8(self._phi), ctypes.byref(h)))
+        self._h = h
+        self.ndofs = int(_lib.lib().stefan_ipdg_ndofs(h))
+        self.shape = (self.ndofs, self.ndofs)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            _lib.lib().stefan_ipdg_destroy(h)
+            self._h = None
+
+    def apply(self, x, out=None, x_lo=None, x_hi=None, algo=STREAM, stream=None):
+        import torch
+        assert x.is_cuda and x.dtype == torch.float64 and x.is_contiguous() and x.numel() == self.ndofs
+        if out is None:
+            out = torch.empty_like(x)
+        _lib.check(_lib.lib().stefan_ipdg_apply(self._h, _ptr(x), _ptr(out), _ptr(x_lo), _ptr(x_hi),
+                                                algo, _stream_ptr(stream)))
+        return out
+
+    def __matmul__(self, x):
+        return self.apply(x)
+
+
+def sparse_operator(sysmatrix, mesh, dofspernode):
+    """`CutCellDG.sparse_operator(sysmatrix, mesh, dofspernode)`: device operator."""
+    if sysmatrix.kind == "ip":
+        if dofspernode != 1:
+            raise ValueError("interior penalty has 1 dof per node")
+        s = sysmatrix.spec
+        return IPOperator(mesh, s["order"], s["numqp"], s["k1"], s["k2"], s.get("penalty", 0.0),
+                          s.get("lam", 0.0), 0.0, s.get("variant", "current"), s["terms"])
+    raise ValueError(f"nothing assembled (kind={sysmatrix.kind})")

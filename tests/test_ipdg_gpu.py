@@ -1,0 +1,67 @@
+"""GPU parity of the IP-DG apply kernels against the oracle (`A_assembled @ x`).
+
+Tolerance: north star <= 1e-12 relative per operator application; asserted here at
+1e-13 (observed ~5e-16)."""
+import numpy as np
+import pytest
+
+from oracle import fast
+from oracle.mesh import UniformMesh2D
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-13
+ALL, REFSYS = 255, 1 | 2 | 4 | 32 | 64
+
+
+def _case(order, nx, ny, two_phase, terms, variant, lam=1.5):
+    import torch
+    from stefanproblem_b200 import cutcelldg as cc
+    omesh = UniformMesh2D([0, 0], [1.0, 0.8], [nx, ny], (order + 1) ** 2)
+    if two_phase:
+        omesh.cellsign[:] = fast.circle_phase(omesh, (0.5, 0.4), 0.3)
+    k1, k2, pen = 1.0, 2.0, 1e3 * nx
+    coupled = bool(terms & 8)
+    A = fast.ip_matrix(omesh, order, order + 1, k1, k2, pen, lam if (terms & 128) else 0.0,
+                       variant, aligned_interface=coupled)
+    basis = cc.LagrangeTensorProductBasis(2, order)
+    mesh = cc.UniformMesh([0, 0], [1.0, 0.8], [nx, ny], basis, phase=omesh.cellsign)
+    op = cc.IPOperator(mesh, order, order + 1, k1, k2, pen, lam, 0.5, variant, terms)
+    x = np.random.default_rng(0).uniform(-1, 1, A.shape[0])
+    return A, op, x, torch.from_numpy(x).cuda()
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
+@pytest.mark.parametrize("algo", [0, 1])
+@pytest.mark.parametrize("nx,ny", [(3, 3), (7, 6), (17, 33), (40, 95)])
+@pytest.mark.parametrize("two_phase,terms,variant", [
+    (False, REFSYS, "current"), (False, REFSYS, "legacy_boundary"),
+    (True, ALL, "current"), (True, REFSYS, "current")])
+def test_apply_matches_oracle(cuda, order, algo, nx, ny, two_phase, terms, variant):
+    A, op, x, xd = _case(order, nx, ny, two_phase, terms, variant)
+    y = op.apply(xd, algo=algo).cpu().numpy()
+    yr = A @ x
+    assert np.linalg.norm(y - yr) / np.linalg.norm(yr) < TOL
+    assert np.max(np.abs(y - yr)) / np.max(np.abs(yr)) < TOL
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_stream_equals_simple_large(cuda, order):
+    """Two independent kernels agree on a mesh with many strips / segments."""
+    import torch
+    from stefanproblem_b200 import cutcelldg as cc
+    nx, ny = 700, 611
+    basis = cc.LagrangeTensorProductBasis(2, order)
+    omesh = UniformMesh2D([0, 0], [1, 1], [nx, ny], basis.nf)
+    phase = fast.circle_phase(omesh)
+    mesh = cc.UniformMesh([0, 0], [1, 1], [nx, ny], basis, phase=phase)
+    op = cc.IPOperator(mesh, order, order + 1, 1.0, 2.0, 1e3 * nx, 1.0, 0.5, "current", ALL)
+    x = torch.from_numpy(np.random.default_rng(1).uniform(-1, 1, op.ndofs)).cuda()
+    y0 = op.apply(x, algo=0)
+    y1 = op.apply(x, algo=1)
+    assert torch.equal(y0, y1) or (y0 - y1).norm() / y1.norm() < 1e-15
+    # symmetry of the operator: x' A z == z' A x
+    z = torch.from_numpy(np.random.default_rng(2).uniform(-1, 1, op.ndofs)).cuda()
+    a = torch.dot(z, y0)
+    b = torch.dot(x, op.apply(z))
+    assert abs(a - b) / abs(a) < 1e-11
