@@ -10,8 +10,8 @@ LIB = os.path.join(LIBDIR, "libstefan_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "--use_fast_math=false" if False else "-Xptxas=-v",
-]
+    "-Xcompiler", "-fPIC", "-Xptxas=-v",
+] + os.environ.get("STEFAN_NVCC_EXTRA", "").split()
 
 
 def sources():

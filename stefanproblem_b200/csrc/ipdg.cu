@@ -8,7 +8,8 @@
 //
 // Data layout in HBM (the reference's dof order):
 //   x[(i*ny + j)*NF + ix*(P+1) + iy], fp64; cells y-fastest, eta-node fastest.
-//   phase: int8 per cell, padded to (nx+2) x (ny+2) with 0 = "no cell".
+//   phase: one byte per cell (1: sign +1, 2: sign -1), padded to (nx+2) x (ny+2)
+//          with 0 = "no cell".
 //
 // Kernels
 //   ipdg_apply_simple<P>: one thread per cell, neighbours straight from global
@@ -38,16 +39,25 @@ struct IpdgHandle {
   double Tm;
   bool has_lo, has_hi;
   int8_t* phase_dev;  // (nx+2)*(ny+2), padded
+  uint8_t* flags_dev;  // [nstrips][nxpad]
+  int32_t* fix_dev;    // cells recomputed by the fix-up kernel
+  int nfix;
   void* tab_host;     // IpTab<P>
   RefElem1D ref;
   int64_t ndofs;
 };
 
+#ifndef P1_MINB
+#define P1_MINB 2
+#endif
+#ifndef P1_NST
+#define P1_NST 6
+#endif
 template <int P>
 struct StreamCfg;
 template <>
 struct StreamCfg<1> {
-  static constexpr int PIECE = 16, CELLB = 32, STRIDE = 48, NST = 6, WARPS = 8, MINB = 2;
+  static constexpr int PIECE = 16, CELLB = 32, STRIDE = 48, NST = P1_NST, WARPS = 8, MINB = P1_MINB;
 };
 template <>
 struct StreamCfg<2> {
@@ -66,6 +76,8 @@ struct ApplyArgs {
   const double* x_hi;  // neighbour slab's first column or nullptr
   double* y;
   const int8_t* phase;  // padded
+  const uint8_t* flags;  // [nstrips][nxpad] strip classification (stream kernel)
+  int nxpad;             // nx rounded up to 16 (flag rows are 16-byte aligned)
   int nx, ny;
   int nseg;  // x segments (stream kernel)
 };
@@ -100,13 +112,47 @@ ipdg_apply_simple(const __grid_constant__ IpTab<P> tab, const ApplyArgs a) {
       XD[k] = sD ? xc[k - NF] : 0.0;
       XU[k] = sU ? xc[k + NF] : 0.0;
     }
-    ip_cell_rows<P>(tab, s > 0 ? 0 : 1, ip_face_type(s, sL),
+    ip_cell_rows<P>(tab, s == 1 ? 0 : 1, ip_face_type(s, sL),
                     ip_face_type(s, sR), ip_face_type(s, sD),
                     ip_face_type(s, sU), X, XL, XR, XD, XU, out);
     double* yc = a.y + cell * NF;
 #pragma unroll
     for (int k = 0; k < NF; ++k) yc[k] = out[k];
   }
+}
+
+// Cells the stream kernel does not (or not correctly) produce: boundary cells, cells
+// next to the other phase, and every cell of a (strip, column) that mixes phases.
+// One thread per listed cell, general tables, neighbours straight from global memory.
+template <int P>
+__global__ void __launch_bounds__(128)
+ipdg_apply_fixup(const __grid_constant__ IpTab<P> tab, const ApplyArgs a,
+                 const int32_t* __restrict__ cells, int ncell) {
+  constexpr int NF = (P + 1) * (P + 1);
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ncell) return;
+  const int64_t cell = cells[t];
+  const int i = (int)(cell / a.ny), j = (int)(cell % a.ny);
+  const int s = phase_at(a.phase, a.ny, i, j);
+  const int sL = phase_at(a.phase, a.ny, i - 1, j), sR = phase_at(a.phase, a.ny, i + 1, j);
+  const int sD = phase_at(a.phase, a.ny, i, j - 1), sU = phase_at(a.phase, a.ny, i, j + 1);
+  double X[NF], XL[NF], XR[NF], XD[NF], XU[NF], out[NF];
+  const double* xc = a.x + cell * NF;
+  const double* pl = (i > 0) ? xc - (size_t)a.ny * NF : a.x_lo + (size_t)j * NF;
+  const double* pr = (i < a.nx - 1) ? xc + (size_t)a.ny * NF : a.x_hi + (size_t)j * NF;
+#pragma unroll
+  for (int k = 0; k < NF; ++k) {
+    X[k] = xc[k];
+    XL[k] = sL ? pl[k] : 0.0;
+    XR[k] = sR ? pr[k] : 0.0;
+    XD[k] = sD ? xc[k - NF] : 0.0;
+    XU[k] = sU ? xc[k + NF] : 0.0;
+  }
+  ip_cell_rows<P>(tab, s == 1 ? 0 : 1, ip_face_type(s, sL), ip_face_type(s, sR),
+                  ip_face_type(s, sD), ip_face_type(s, sU), X, XL, XR, XD, XU, out);
+  double* yc = a.y + cell * NF;
+#pragma unroll
+  for (int k = 0; k < NF; ++k) yc[k] = out[k];
 }
 
 // --------------------------------------------------------------------------
@@ -143,13 +189,23 @@ __device__ __forceinline__ void store_cell(double* dst, const double* v) {
   }
 }
 
+// phase byte, zero-extended by the load itself (no conversion instruction that
+// would wait on the load right after it is issued)
+__device__ __forceinline__ unsigned ld_phase(const uint8_t* p) {
+  unsigned v;
+  asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
 template <int P>
 __global__ void __launch_bounds__(StreamCfg<P>::WARPS * 32, StreamCfg<P>::MINB)
 ipdg_apply_stream(const __grid_constant__ IpTab<P> tab, const ApplyArgs a) {
   using C = StreamCfg<P>;
   constexpr int NF = (P + 1) * (P + 1);
   constexpr int NST = C::NST;
-  constexpr int STAGE_BYTES = 32 * C::STRIDE;
+  constexpr int FLAG_OFF = 32 * C::STRIDE;        // the column's strip flag rides with its data
+  constexpr int STAGE_BYTES = 32 * C::STRIDE + 16;
+  constexpr int NPIECE = C::CELLB / C::PIECE;     // pieces per lane per column
   extern __shared__ __align__(16) char smem[];
 
   const int lane = threadIdx.x & 31;
@@ -160,140 +216,147 @@ ipdg_apply_stream(const __grid_constant__ IpTab<P> tab, const ApplyArgs a) {
   const int seg = blockIdx.x / ngroups;
   const int strip = group * C::WARPS + warp;
   if (strip >= nstrips) return;
+  const int c0 = (int)((int64_t)a.nx * seg / a.nseg);
+  const int c1 = (int)((int64_t)a.nx * (seg + 1) / a.nseg);
+  if (c0 >= c1) return;
 
   char* ring = smem + (size_t)warp * NST * STAGE_BYTES;
   const int j0 = strip * kStripCells;  // first output cell of the strip
   const int j = j0 - 1 + lane;         // this lane's cell
   const bool outlane = lane >= 1 && lane <= kStripCells && j < a.ny;
   const int jlo = max(j0 - 1, 0), jhi = min(j0 + kStripCells + 1, a.ny);
-  const int nchunk = (jhi - jlo) * C::CELLB / C::PIECE;  // pieces in one column chunk
-  const int rel0 = jlo - (j0 - 1);                        // first staged cell, lane units
+  const int nchunk = (jhi - jlo) * NPIECE;  // 16- or 8-byte pieces in one column chunk
+  const int rel0 = jlo - (j0 - 1);          // first staged cell, in lane units
+  const size_t colbytes = (size_t)a.ny * NF * sizeof(double);
 
-  // column range of this segment
-  const int c0 = (int)((int64_t)a.nx * seg / a.nseg);
-  const int c1 = (int)((int64_t)a.nx * (seg + 1) / a.nseg);
-  if (c0 >= c1) return;
+  // per-lane constants: ring offsets of the pieces this lane copies, of its own
+  // cell and of its y-neighbours
+  int dsto[NPIECE];
+#pragma unroll
+  for (int q = 0; q < NPIECE; ++q) {
+    const int byte = (lane + 32 * q) * C::PIECE;
+    dsto[q] = (rel0 + byte / C::CELLB) * C::STRIDE + byte % C::CELLB;
+  }
+  const int own = lane * C::STRIDE;
+  const int dn = max(lane - 1, 0) * C::STRIDE;
+  const int up = min(lane + 1, 31) * C::STRIDE;
 
-  auto column_ptr = [&](int c) -> const double* {
-    if (c < 0) return a.x_lo;
-    if (c >= a.nx) return a.x_hi;
-    return a.x + (size_t)c * a.ny * NF;
+  // cells of this strip that lie outside the mesh are never staged: zero them once
+  if (j < 0 || j >= a.ny) {
+#pragma unroll
+    for (int st = 0; st < NST; ++st)
+      for (int k = 0; k < C::STRIDE; k += 8)
+        *reinterpret_cast<double*>(ring + st * STAGE_BYTES + own + k) = 0.0;
+  }
+  __syncwarp();
+
+  // source of this lane's first piece in column c (valid for 0 <= c < nx)
+  const char* const src0 =
+      reinterpret_cast<const char*>(a.x) + (size_t)jlo * (NF * sizeof(double)) + lane * C::PIECE;
+  // per (strip, column) classification computed at handle creation:
+  // 1 / 2 = every output cell of the strip is an interior cell of that phase code
+  // whose four neighbours have the same phase; 0 = anything else.  The flag rides
+  // with the column data: the 16-byte block holding the flags of columns
+  // [16 floor(c/16), +16) is staged by a .cg cp.async like the data (measured: a
+  // 4-byte .ca cp.async per column costs 35% of the kernel, an LDG in the loop waits
+  // behind every cp.async in flight because L1TEX returns in order).
+  const uint8_t* const flag0 = a.flags + (size_t)strip * a.nxpad;
+  auto stage = [&](const char* src, char* dst, const uint8_t* flag) {
+#pragma unroll
+    for (int q = 0; q < NPIECE; ++q) {
+      if (lane + 32 * q < nchunk) {
+        if constexpr (C::PIECE == 16)
+          cp_async16(dst + dsto[q], src + q * 32 * C::PIECE);
+        else
+          cp_async8(dst + dsto[q], src + q * 32 * C::PIECE);
+      }
+    }
+    if (lane == 0 && flag != nullptr) cp_async16(dst + FLAG_OFF, flag);
   };
-  auto issue = [&](int c) {
-    // stage column c (if it exists and lies in [c0-1, c1]) into ring slot c mod NST
-    if (c <= c1 && c >= -1 && c <= a.nx) {
-      const double* col = column_ptr(c);
-      if (col != nullptr) {
-        const char* src = reinterpret_cast<const char*>(col + (size_t)jlo * NF);
-        char* dst = ring + ((c + NST) % NST) * STAGE_BYTES;
-        for (int k = lane; k < nchunk; k += 32) {
-          const int byte = k * C::PIECE;
-          const int cellrel = rel0 + byte / C::CELLB;
-          const int within = byte % C::CELLB;
-          if constexpr (C::PIECE == 16)
-            cp_async16(dst + cellrel * C::STRIDE + within, src + byte);
-          else
-            cp_async8(dst + cellrel * C::STRIDE + within, src + byte);
-        }
+  auto issue_general = [&](int c, int slot) {
+    // stage column c into ring slot `slot`; columns beyond c1 are not needed
+    if (c <= c1) {
+      char* dst = ring + slot * STAGE_BYTES;
+      const char* halo = reinterpret_cast<const char*>(c < 0 ? a.x_lo : a.x_hi);
+      if (c >= 0 && c < a.nx) {
+        stage(src0 + (size_t)c * colbytes, dst, flag0 + (c & ~15));
+      } else if (halo != nullptr) {
+        stage(halo + (size_t)jlo * (NF * sizeof(double)) + lane * C::PIECE, dst, nullptr);
+      } else {
+        // no such column (domain boundary): the slot must read as zeros
+        for (int k = 0; k < C::STRIDE; k += 8) *reinterpret_cast<double*>(dst + own + k) = 0.0;
       }
     }
     cp_async_commit();
   };
-  auto col_exists = [&](int c) -> bool {
-    return (c >= 0 && c < a.nx) || (c == -1 && a.x_lo != nullptr) ||
-           (c == a.nx && a.x_hi != nullptr);
-  };
-  auto lane_phase = [&](int c) -> int {
-    // phase of this lane's cell in column c (0 outside the mesh)
-    const int jj = min(max(j, -1), a.ny);
-    const int cc = min(max(c, -1), a.nx);
-    return phase_at(a.phase, a.ny, cc, jj);
-  };
 
-  // prologue: fill the ring with columns c0-1 .. c0+NST-2
+  // prologue: fill the ring with columns c0-1 .. c0+NST-2 (column c0-1+k -> slot k)
 #pragma unroll
-  for (int k = 0; k < NST; ++k) issue(c0 - 1 + k);
-
-  int sL = lane_phase(c0 - 1), s = lane_phase(c0), sR = lane_phase(c0 + 1);
-  int sRR = lane_phase(c0 + 2);
-  if (a.x_lo == nullptr && c0 == 0) sL = 0;
+  for (int k = 0; k < NST; ++k) issue_general(c0 - 1 + k, k);
 
   double X[NF], XL[NF];
   cp_async_wait<NST - 2>();
   __syncwarp();
-  {
-    const char* st = ring + ((c0 - 1 + NST) % NST) * STAGE_BYTES + lane * C::STRIDE;
-    if (col_exists(c0 - 1) && sL != 0) {
-      load_cell<P>(st, XL);
-    } else {
-#pragma unroll
-      for (int k = 0; k < NF; ++k) XL[k] = 0.0;
-    }
-    st = ring + ((c0 + NST) % NST) * STAGE_BYTES + lane * C::STRIDE;
-    if (s != 0) {
-      load_cell<P>(st, X);
-    } else {
-#pragma unroll
-      for (int k = 0; k < NF; ++k) X[k] = 0.0;
-    }
-  }
+  load_cell<P>(ring + 0 * STAGE_BYTES + own, XL);
+  load_cell<P>(ring + 1 * STAGE_BYTES + own, X);
   __syncwarp();
 
+  const int csteady = min(c1, a.nx - 1) - (NST - 1);  // last c whose prefetch column is a plain one
+  const char* srcn = src0 + (size_t)(c0 + NST - 1) * colbytes;  // column c + NST - 1
+  double* yp = a.y + ((size_t)c0 * a.ny + j) * NF;
+  int slot_c = 1;  // ring slot of column c
+  P1Coef coef;
+  unsigned coef_phase = 0;
+  if constexpr (P == 1) {
+    p1_load_coef(tab, 0, coef);
+    coef_phase = 1;
+  }
   for (int c = c0; c < c1; ++c) {
-    issue(c + NST - 1);  // reuses the slot of column c-1, which nobody reads any more
-    cp_async_wait<NST - 2>();
+    const int slot_l = slot_c == 0 ? NST - 1 : slot_c - 1;
+    const int slot_r = slot_c == NST - 1 ? 0 : slot_c + 1;
+    // prefetch column c+NST-1 into the slot of column c-1, which nobody reads any more
+    if (c <= csteady) {
+      stage(srcn, ring + slot_l * STAGE_BYTES, flag0 + ((c + NST - 1) & ~15));
+      cp_async_commit();
+    } else {
+      issue_general(c + NST - 1, slot_l);
+    }
+    srcn += colbytes;
+    cp_async_wait<NST - 2>();  // column c+1 has landed
     __syncwarp();
-    const int sNext = lane_phase(c + 3);  // prefetched two iterations ahead
 
     double XR[NF], XD[NF], XU[NF], out[NF];
-    const char* stc = ring + ((c + NST) % NST) * STAGE_BYTES;
-    const char* str = ring + ((c + 1 + NST) % NST) * STAGE_BYTES;
-    const int sD = __shfl_up_sync(0xffffffffu, s, 1);
-    const int sU = __shfl_down_sync(0xffffffffu, s, 1);
-    if (sR != 0 && col_exists(c + 1)) {
-      load_cell<P>(str + lane * C::STRIDE, XR);
-    } else {
-#pragma unroll
-      for (int k = 0; k < NF; ++k) XR[k] = 0.0;
+    const char* stc = ring + slot_c * STAGE_BYTES;
+    const unsigned f0 = *reinterpret_cast<const uint8_t*>(stc + FLAG_OFF + (c & 15));
+    load_cell<P>(ring + slot_r * STAGE_BYTES + own, XR);
+    load_cell<P>(stc + dn, XD);
+    load_cell<P>(stc + up, XU);
+    // f0 = phase code all 30 cells are treated as (their exceptions -- boundary,
+    // interface or other-phase cells -- are recomputed by ipdg_apply_fixup), or 0 =
+    // the strip mixes phases in this column and is left to the fix-up kernel entirely
+    if (f0 != 0) {
+      if constexpr (P == 1) {
+        if (f0 != coef_phase) {  // rare: the strip crossed into the other phase
+          p1_load_coef(tab, f0 == 1 ? 0 : 1, coef);
+          coef_phase = f0;
+        }
+        p1_uniform_rows(coef, X, XL, XR, XD, XU, out);
+      } else {
+        if (f0 == 1)
+          ip_cell_rows<P>(tab, 0, T_SAME, T_SAME, T_SAME, T_SAME, X, XL, XR, XD, XU, out);
+        else
+          ip_cell_rows<P>(tab, 1, T_SAME, T_SAME, T_SAME, T_SAME, X, XL, XR, XD, XU, out);
+      }
     }
-    if (outlane && sD != 0) {
-      load_cell<P>(stc + (lane - 1) * C::STRIDE, XD);
-    } else {
-#pragma unroll
-      for (int k = 0; k < NF; ++k) XD[k] = 0.0;
-    }
-    if (outlane && sU != 0) {
-      load_cell<P>(stc + (lane + 1) * C::STRIDE, XU);
-    } else {
-#pragma unroll
-      for (int k = 0; k < NF; ++k) XU[k] = 0.0;
-    }
-    const int sRe = col_exists(c + 1) ? sR : 0;
-    const int sLe = col_exists(c - 1) ? sL : 0;
-    const int tL = ip_face_type(s, sLe), tR = ip_face_type(s, sRe);
-    const int tD = ip_face_type(s, sD), tU = ip_face_type(s, sU);
-    const bool plain = !outlane || (tL == T_SAME && tR == T_SAME && tD == T_SAME && tU == T_SAME);
-    const int sref = __shfl_sync(0xffffffffu, s, 1);
-    const bool uniform = __all_sync(0xffffffffu, plain && (!outlane || s == sref));
-    if (uniform) {
-      if (sref > 0)
-        ip_cell_rows<P>(tab, 0, T_SAME, T_SAME, T_SAME, T_SAME, X, XL, XR, XD, XU, out);
-      else
-        ip_cell_rows<P>(tab, 1, T_SAME, T_SAME, T_SAME, T_SAME, X, XL, XR, XD, XU, out);
-    } else if (outlane) {
-      ip_cell_rows<P>(tab, s > 0 ? 0 : 1, tL, tR, tD, tU, X, XL, XR, XD, XU, out);
-    }
-    if (outlane) store_cell<P>(a.y + ((size_t)c * a.ny + j) * NF, out);
+    if (outlane && f0 != 0) store_cell<P>(yp, out);
+    yp += (size_t)a.ny * NF;
 #pragma unroll
     for (int k = 0; k < NF; ++k) {
       XL[k] = X[k];
       X[k] = XR[k];
     }
-    sL = s;
-    s = sR;
-    sR = sRR;
-    sRR = sNext;
-    __syncwarp();
+    slot_c = slot_r;
+    __syncwarp();  // everyone is done with column c's slot before it is refilled
   }
   cp_async_wait<0>();
 }
@@ -317,7 +380,7 @@ static int launch_apply(const IpdgHandle* h, const ApplyArgs& args0, int algo, c
     int nseg = std::max(1, (sm_count() * C::MINB) / ngroups);
     nseg = std::min(nseg, std::max(1, h->nx / 16));
     args.nseg = nseg;
-    const size_t smem = (size_t)C::WARPS * C::NST * 32 * C::STRIDE;
+        const size_t smem = (size_t)C::WARPS * C::NST * (32 * C::STRIDE + 16);
     static bool attr_set = false;
     if (!attr_set) {
       STEFAN_CUDA(cudaFuncSetAttribute(ipdg_apply_stream<P>,
@@ -325,6 +388,8 @@ static int launch_apply(const IpdgHandle* h, const ApplyArgs& args0, int algo, c
       attr_set = true;
     }
     ipdg_apply_stream<P><<<ngroups * nseg, C::WARPS * 32, smem, st>>>(tab, args);
+    if (h->nfix > 0)
+      ipdg_apply_fixup<P><<<(h->nfix + 127) / 128, 128, 0, st>>>(tab, args, h->fix_dev, h->nfix);
   }
   STEFAN_CUDA(cudaGetLastError());
   return ST_OK;
@@ -356,6 +421,9 @@ int stefan_ipdg_create(const stefan_ipdg_params* p, const int8_t* phase, const i
   h->has_lo = phase_lo != nullptr;
   h->has_hi = phase_hi != nullptr;
   h->phase_dev = nullptr;
+  h->flags_dev = nullptr;
+  h->fix_dev = nullptr;
+  h->nfix = 0;
   h->tab_host = nullptr;
   const int NF = (p->order + 1) * (p->order + 1);
   h->ndofs = (int64_t)p->nx * p->ny * NF;
@@ -375,14 +443,49 @@ int stefan_ipdg_create(const stefan_ipdg_params* p, const int8_t* phase, const i
     for (int j = 0; j < p->ny; ++j) {
       int8_t s = phase ? phase[(size_t)i * p->ny + j] : 1;
       if (s != 1 && s != -1) { delete h; return fail(ST_BAD_ARGUMENT, "stefan_ipdg_create: phase[%d,%d] = %d (expected +1/-1; cut cells are not supported)", i, j, (int)s); }
-      ph[(size_t)(i + 1) * (p->ny + 2) + (j + 1)] = s;
+      ph[(size_t)(i + 1) * (p->ny + 2) + (j + 1)] = (s == 1) ? 1 : 2;
     }
   for (int j = 0; j < p->ny; ++j) {
-    if (phase_lo) ph[(size_t)0 * (p->ny + 2) + (j + 1)] = phase_lo[j];
-    if (phase_hi) ph[(size_t)(p->nx + 1) * (p->ny + 2) + (j + 1)] = phase_hi[j];
+    if (phase_lo) ph[(size_t)0 * (p->ny + 2) + (j + 1)] = (phase_lo[j] == 1) ? 1 : 2;
+    if (phase_hi) ph[(size_t)(p->nx + 1) * (p->ny + 2) + (j + 1)] = (phase_hi[j] == 1) ? 1 : 2;
   }
+  // strip classification for the stream kernel: flag = the phase code shared by
+  // the (up to) 30 cells of the strip in that column, or 0 if they differ; and the
+  // list of cells the fix-up kernel recomputes
+  const int nstrips = (p->ny + kStripCells - 1) / kStripCells;
+  const int nxpad = (p->nx + 15) / 16 * 16;
+  std::vector<uint8_t> flags((size_t)nstrips * nxpad, 0);
+  std::vector<int32_t> fix;
+  if ((int64_t)p->nx * p->ny >= (int64_t)INT32_MAX) {
+    delete h;
+    return fail(ST_UNSUPPORTED, "stefan_ipdg_create: more than 2^31 cells per slab");
+  }
+  {
+    const int ld = p->ny + 2;
+    for (int i = 0; i < p->nx; ++i) {
+      const int8_t* col = ph.data() + (size_t)(i + 1) * ld + 1;
+      for (int sidx = 0; sidx < nstrips; ++sidx) {
+        const int ja = sidx * kStripCells, jb = std::min(ja + kStripCells, (int)p->ny);
+        const int8_t ref = col[ja];
+        bool same = true;
+        for (int j = ja; j < jb && same; ++j) same = col[j] == ref;
+        flags[(size_t)sidx * nxpad + i] = same ? (uint8_t)ref : 0;
+        for (int j = ja; j < jb; ++j) {
+          const int8_t s = col[j];
+          const bool plain = col[j - 1] == s && col[j + 1] == s && col[j - ld] == s && col[j + ld] == s;
+          if (!same || !plain) fix.push_back((int32_t)((int64_t)i * p->ny + j));
+        }
+      }
+    }
+  }
+  h->nfix = (int)fix.size();
   cudaError_t e = cudaMalloc(&h->phase_dev, pn);
   if (e == cudaSuccess) e = cudaMemcpy(h->phase_dev, ph.data(), pn, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&h->flags_dev, flags.size());
+  if (e == cudaSuccess) e = cudaMemcpy(h->flags_dev, flags.data(), flags.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && h->nfix > 0) e = cudaMalloc(&h->fix_dev, fix.size() * sizeof(int32_t));
+  if (e == cudaSuccess && h->nfix > 0)
+    e = cudaMemcpy(h->fix_dev, fix.data(), fix.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) { delete h; return fail(ST_CUDA_ERROR, "stefan_ipdg_create: %s", cudaGetErrorString(e)); }
   *out = reinterpret_cast<stefan_ipdg*>(h);
   return ST_OK;
@@ -392,6 +495,8 @@ int stefan_ipdg_destroy(stefan_ipdg* hv) {
   IpdgHandle* h = reinterpret_cast<IpdgHandle*>(hv);
   if (!h) return ST_OK;
   if (h->phase_dev) cudaFree(h->phase_dev);
+  if (h->flags_dev) cudaFree(h->flags_dev);
+  if (h->fix_dev) cudaFree(h->fix_dev);
   switch (h->order) {
     case 1: delete static_cast<IpTab<1>*>(h->tab_host); break;
     case 2: delete static_cast<IpTab<2>*>(h->tab_host); break;
@@ -419,7 +524,7 @@ int stefan_ipdg_apply(stefan_ipdg* hv, const double* x, double* y, const double*
                  (reinterpret_cast<uintptr_t>(x_lo) & 15) == 0 && (reinterpret_cast<uintptr_t>(x_hi) & 15) == 0,
                  "stefan_ipdg_apply: device pointers must be 16-byte aligned");
   STEFAN_REQUIRE(algo == 0 || algo == 1, "stefan_ipdg_apply: unknown algo %d", algo);
-  ApplyArgs a{x, x_lo, x_hi, y, h->phase_dev, h->nx, h->ny, 1};
+  ApplyArgs a{x, x_lo, x_hi, y, h->phase_dev, h->flags_dev, (h->nx + 15) / 16 * 16, h->nx, h->ny, 1};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (h->order) {
     case 1: return launch_apply<1>(h, a, algo, st);

@@ -153,7 +153,90 @@ int build_ip_tables(const RefElem1D& r, double jx, double jy, const IpPhys& ph, 
       t->Mx[a * N1 + b] = jx * r.M[a][b];
       t->My[a * N1 + b] = jy * r.M[a][b];
     }
+  // The interior (same-phase neighbours on both sides) blocks are persymmetric and
+  // the high-side blocks mirror the low-side ones; make that exact in floating point
+  // so that kernels that exploit it agree bitwise with those that do not.
+  for (int ax = 0; ax < 2; ++ax)
+    for (int s = 0; s < 2; ++s) {
+      double* D = t->D[ax][s][T_SAME][T_SAME];
+      for (int a = 0; a < N1; ++a)
+        for (int b = 0; b < N1; ++b) {
+          const int m = (P - a) * N1 + (P - b);
+          if (m > a * N1 + b) D[m] = D[a * N1 + b];
+        }
+      for (int b = 0; b < N1; ++b) {
+        t->Rp[ax][s][T_SAME][b] = t->L0[ax][s][T_SAME][P - b];
+        t->Rc[ax][s][T_SAME][b] = t->Lc[ax][s][T_SAME][P - b];
+      }
+    }
+  for (int a = 0; a < N1; ++a)
+    for (int b = 0; b < N1; ++b) {
+      const int m = (P - a) * N1 + (P - b);
+      if (m > a * N1 + b) {
+        t->Mx[m] = t->Mx[a * N1 + b];
+        t->My[m] = t->My[a * N1 + b];
+      }
+    }
   return 0;
+}
+
+// Order-1 interior cell of one phase with same-phase neighbours: the 14 distinct
+// coefficients of the two 1-D stencils and mass matrices, held in registers by the
+// stream kernel (the uniform datapath cannot hold two phases' worth of them).
+struct P1Coef {
+  double dx0, dx1, lx0, lx1, lcx, mx0, mx1;
+  double dy0, dy1, ly0, ly1, lcy, my0, my1;
+};
+
+#if defined(__CUDACC__)
+__host__ __device__ __forceinline__
+#else
+inline
+#endif
+void p1_load_coef(const IpTab<1>& tab, int s, P1Coef& c) {
+  c.dx0 = tab.D[0][s][T_SAME][T_SAME][0];
+  c.dx1 = tab.D[0][s][T_SAME][T_SAME][1];
+  c.lx0 = tab.L0[0][s][T_SAME][0];
+  c.lx1 = tab.L0[0][s][T_SAME][1];
+  c.lcx = tab.Lc[0][s][T_SAME][1];
+  c.mx0 = tab.Mx[0];
+  c.mx1 = tab.Mx[1];
+  c.dy0 = tab.D[1][s][T_SAME][T_SAME][0];
+  c.dy1 = tab.D[1][s][T_SAME][T_SAME][1];
+  c.ly0 = tab.L0[1][s][T_SAME][0];
+  c.ly1 = tab.L0[1][s][T_SAME][1];
+  c.lcy = tab.Lc[1][s][T_SAME][1];
+  c.my0 = tab.My[0];
+  c.my1 = tab.My[1];
+}
+
+#if defined(__CUDACC__)
+__host__ __device__ __forceinline__
+#else
+inline
+#endif
+void p1_uniform_rows(const P1Coef& c, const double* __restrict__ X, const double* __restrict__ XL,
+                     const double* __restrict__ XR, const double* __restrict__ XD,
+                     const double* __restrict__ XU, double* __restrict__ out) {
+  double ax[4], ay[4];
+#pragma unroll
+  for (int iy = 0; iy < 2; ++iy) {
+    ax[0 + iy] = c.dx0 * X[0 + iy] + c.dx1 * X[2 + iy] + c.lx0 * XL[0 + iy] + c.lx1 * XL[2 + iy] +
+                 c.lcx * XR[0 + iy];
+    ax[2 + iy] = c.dx1 * X[0 + iy] + c.dx0 * X[2 + iy] + c.lcx * XL[2 + iy] + c.lx1 * XR[0 + iy] +
+                 c.lx0 * XR[2 + iy];
+  }
+#pragma unroll
+  for (int ix = 0; ix < 2; ++ix) {
+    ay[2 * ix + 0] = c.dy0 * X[2 * ix] + c.dy1 * X[2 * ix + 1] + c.ly0 * XD[2 * ix] +
+                     c.ly1 * XD[2 * ix + 1] + c.lcy * XU[2 * ix];
+    ay[2 * ix + 1] = c.dy1 * X[2 * ix] + c.dy0 * X[2 * ix + 1] + c.lcy * XD[2 * ix + 1] +
+                     c.ly1 * XU[2 * ix] + c.ly0 * XU[2 * ix + 1];
+  }
+  out[0] = c.my0 * ax[0] + c.my1 * ax[1] + c.mx0 * ay[0] + c.mx1 * ay[2];
+  out[1] = c.my1 * ax[0] + c.my0 * ax[1] + c.mx0 * ay[1] + c.mx1 * ay[3];
+  out[2] = c.my0 * ax[2] + c.my1 * ax[3] + c.mx1 * ay[0] + c.mx0 * ay[2];
+  out[3] = c.my1 * ax[2] + c.my0 * ax[3] + c.mx1 * ay[1] + c.mx0 * ay[3];
 }
 
 // Face type seen from a cell of sign s towards a neighbour of sign sn (0 = no cell).
