@@ -102,7 +102,9 @@ int64_t stefan_ipdg_ndofs(const stefan_ipdg* h);
 /* y = A x (replaces sparse_operator(sysmatrix, mesh, 1) * x).  x_lo / x_hi: the
  * neighbouring slabs' adjacent cell columns (ny*NF doubles each; local or peer
  * device memory), required iff the handle has phase_lo / phase_hi.
- * algo 0 = streaming kernel (production), 1 = simple one-thread-per-cell kernel. */
+ * algo 0 = production kernel (order 1: register-streaming LDG.256 kernel; orders 2, 3:
+ * cp.async streaming kernel), 1 = simple one-thread-per-cell kernel, 2 = cp.async
+ * streaming kernel for every order. */
 int stefan_ipdg_apply(stefan_ipdg* h, const double* x, double* y, const double* x_lo,
                       const double* x_hi, int32_t algo, void* stream);
 

@@ -35,13 +35,15 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--order", type=int, default=0)
     ap.add_argument("--n", type=int, default=0)
+    ap.add_argument("--nx", type=int, default=0)
+    ap.add_argument("--ny", type=int, default=0)
     ap.add_argument("--algo", type=int, default=0)
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--two-phase", type=int, default=1)
     args = ap.parse_args()
     if args.order:
         n = args.n or {1: 5000, 2: 3334, 3: 2500}[args.order]
-        run(args.order, n, n, bool(args.two_phase), args.algo, args.reps)
+        run(args.order, args.nx or n, args.ny or n, bool(args.two_phase), args.algo, args.reps)
         sys.exit(0)
     a = torch.empty(1 << 28, dtype=torch.float64, device="cuda"); b = torch.empty_like(a)
     for _ in range(3): b.copy_(a)

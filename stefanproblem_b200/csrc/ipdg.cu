@@ -42,6 +42,8 @@ struct IpdgHandle {
   uint8_t* flags_dev;  // [nstrips][nxpad]
   int32_t* fix_dev;    // cells recomputed by the fix-up kernel
   int nfix;
+  int2* runs_dev;      // per-strip run lists (order-1 kernel)
+  int* run_ofs_dev;
   void* tab_host;     // IpTab<P>
   RefElem1D ref;
   int64_t ndofs;
@@ -176,13 +178,20 @@ __device__ __forceinline__ void load_cell(const char* base, double* v) {
   }
 }
 
+// 32 bytes per lane in one instruction (STG.256, sm_100): a warp writes whole
+// 32-byte sectors; two STG.128 per lane would send every sector to L2 twice, half
+// filled (measured: L1->XBAR request path 66% busy, 43% of it stores).
+__device__ __forceinline__ void st_global_v4(double* p, double a, double b, double c, double d) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d)
+               : "memory");
+}
+
 template <int P>
 __device__ __forceinline__ void store_cell(double* dst, const double* v) {
   constexpr int NF = (P + 1) * (P + 1);
-  if constexpr (StreamCfg<P>::PIECE == 16) {
-    double2* p = reinterpret_cast<double2*>(dst);
+  if constexpr (NF % 4 == 0) {
 #pragma unroll
-    for (int k = 0; k < NF / 2; ++k) p[k] = make_double2(v[2 * k], v[2 * k + 1]);
+    for (int k = 0; k < NF; k += 4) st_global_v4(dst + k, v[k], v[k + 1], v[k + 2], v[k + 3]);
   } else {
 #pragma unroll
     for (int k = 0; k < NF; ++k) dst[k] = v[k];
@@ -206,7 +215,7 @@ ipdg_apply_stream(const __grid_constant__ IpTab<P> tab, const ApplyArgs a) {
   constexpr int FLAG_OFF = 32 * C::STRIDE;        // the column's strip flag rides with its data
   constexpr int STAGE_BYTES = 32 * C::STRIDE + 16;
   constexpr int NPIECE = C::CELLB / C::PIECE;     // pieces per lane per column
-  extern __shared__ __align__(16) char smem[];
+  extern __shared__ __align__(128) char smem[];
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -264,7 +273,11 @@ ipdg_apply_stream(const __grid_constant__ IpTab<P> tab, const ApplyArgs a) {
   auto stage = [&](const char* src, char* dst, const uint8_t* flag) {
 #pragma unroll
     for (int q = 0; q < NPIECE; ++q) {
+#ifdef EXP_NOLOAD
+      if (lane + 32 * q < nchunk && a.nseg < 0) {
+#else
       if (lane + 32 * q < nchunk) {
+#endif
         if constexpr (C::PIECE == 16)
           cp_async16(dst + dsto[q], src + q * 32 * C::PIECE);
         else
@@ -340,7 +353,12 @@ ipdg_apply_stream(const __grid_constant__ IpTab<P> tab, const ApplyArgs a) {
           p1_load_coef(tab, f0 == 1 ? 0 : 1, coef);
           coef_phase = f0;
         }
+#ifdef EXP_NOCOMPUTE
+#pragma unroll
+        for (int k = 0; k < NF; ++k) out[k] = X[k] + XL[k] + XR[k] + XD[k] + XU[k] * coef.dx0;
+#else
         p1_uniform_rows(coef, X, XL, XR, XD, XU, out);
+#endif
       } else {
         if (f0 == 1)
           ip_cell_rows<P>(tab, 0, T_SAME, T_SAME, T_SAME, T_SAME, X, XL, XR, XD, XU, out);
@@ -348,7 +366,11 @@ ipdg_apply_stream(const __grid_constant__ IpTab<P> tab, const ApplyArgs a) {
           ip_cell_rows<P>(tab, 1, T_SAME, T_SAME, T_SAME, T_SAME, X, XL, XR, XD, XU, out);
       }
     }
+#ifdef EXP_NOSTORE
+    if (outlane && f0 != 0 && out[0] == 1.2345e300) store_cell<P>(yp, out);
+#else
     if (outlane && f0 != 0) store_cell<P>(yp, out);
+#endif
     yp += (size_t)a.ny * NF;
 #pragma unroll
     for (int k = 0; k < NF; ++k) {
@@ -359,6 +381,331 @@ ipdg_apply_stream(const __grid_constant__ IpTab<P> tab, const ApplyArgs a) {
     __syncwarp();  // everyone is done with column c's slot before it is refilled
   }
   cp_async_wait<0>();
+}
+
+// --------------------------------------------------------------------------
+// order-1 register-streaming kernel (production path for P = 1)
+// --------------------------------------------------------------------------
+// Same decomposition as the cp.async kernel (one warp = a strip of 30 cells + 1 halo
+// cell each side, marching along x), but each lane loads its own cell -- 32
+// contiguous bytes -- with one LDG.256 straight into registers, kP1R - 3 columns
+// ahead, so a warp-wide load is one 1 KiB contiguous request made of whole 32-byte
+// sectors.  (Measured on the cp.async version: LDGSTS does not merge the two
+// 16-byte halves of a sector that two lanes ask for, so L2 served every sector
+// twice and the kernel sat at 70% of the copy bandwidth with the arithmetic removed.)
+// The x-neighbours are the previous / next register columns; the y-neighbours are
+// exchanged through a 3-deep per-warp shared-memory buffer (one __syncwarp per
+// column).  Which coefficient set a column uses comes from a per-strip run list
+// built at handle creation, so the loop carries no flag loads at all.
+constexpr int kP1R = 6;       // register columns: c-1, c, c+1 and three in flight
+constexpr int kP1Warps = 8;
+constexpr int kP1Stride = 48; // bytes per cell in the exchange buffer (conflict-free LDS.128)
+
+__device__ __forceinline__ void ld_global_v4(const double* p, double* v) {
+  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3])
+               : "l"(p));
+}
+
+__global__ void __launch_bounds__(kP1Warps * 32, 2)
+ipdg_apply_p1(const __grid_constant__ IpTab<1> tab, const ApplyArgs a,
+              const int2* __restrict__ runs, const int* __restrict__ run_ofs) {
+  __shared__ __align__(16) char xbuf[kP1Warps][3][32 * kP1Stride];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nstrips = (a.ny + kStripCells - 1) / kStripCells;
+  const int ngroups = (nstrips + kP1Warps - 1) / kP1Warps;
+  const int group = blockIdx.x % ngroups;
+  const int seg = blockIdx.x / ngroups;
+  const int strip = group * kP1Warps + warp;
+  if (strip >= nstrips) return;
+  const int c0 = (int)((int64_t)a.nx * seg / a.nseg);
+  const int c1 = (int)((int64_t)a.nx * (seg + 1) / a.nseg);
+  if (c0 >= c1) return;
+
+  const int j0 = strip * kStripCells;
+  const int j = j0 - 1 + lane;
+  const bool valid = j >= 0 && j < a.ny;
+  const bool outlane = lane >= 1 && lane <= kStripCells && j < a.ny;
+  const size_t colstride = (size_t)a.ny * 4;  // doubles per column
+  char* const mybuf = &xbuf[warp][0][0];
+  const int own = lane * kP1Stride;
+  const int dn = max(lane - 1, 0) * kP1Stride;
+  const int up = min(lane + 1, 31) * kP1Stride;
+
+  auto load_col = [&](int c, double* v) {
+    // column c of this lane's cell; zeros where there is no such cell
+    const double* p = nullptr;
+    if (c >= 0 && c < a.nx)
+      p = a.x + (size_t)c * colstride;
+    else if (c == -1)
+      p = a.x_lo;
+    else if (c == a.nx)
+      p = a.x_hi;
+    if (valid && p != nullptr && c <= c1) {
+      ld_global_v4(p + (size_t)j * 4, v);
+    } else {
+      v[0] = v[1] = v[2] = v[3] = 0.0;
+    }
+  };
+
+  // run list of this strip: (end column, phase code or 0) with increasing end
+  const int2* rp = runs + run_ofs[strip];
+  int2 cur = rp[0];
+  while (cur.x <= c0) cur = *++rp;
+  int2 nxt = rp[1];  // the list ends with a sentinel run, so rp[1] always exists
+  P1Coef coef;
+  p1_load_coef(tab, cur.y == 2 ? 1 : 0, coef);
+
+  double A[kP1R][4];
+#pragma unroll
+  for (int k = 0; k < kP1R; ++k) load_col(c0 - 1 + k, A[k]);
+  // column c0 goes to exchange buffer 0 (buffers are indexed by (c - c0) mod 3)
+  *reinterpret_cast<double2*>(mybuf + own) = make_double2(A[1][0], A[1][1]);
+  *reinterpret_cast<double2*>(mybuf + own + 16) = make_double2(A[1][2], A[1][3]);
+
+  const double* pn = a.x + (size_t)(c0 + kP1R - 1) * colstride + (size_t)j * 4;  // column c + R - 1
+  double* yp = a.y + (size_t)c0 * colstride + (size_t)j * 4;
+  const int cplain = min(c1, a.nx - 1) - (kP1R - 1);  // last c whose prefetch column is an ordinary one
+
+  for (int cb = c0; cb < c1; cb += kP1R) {
+#pragma unroll
+    for (int k = 0; k < kP1R; ++k) {
+      const int c = cb + k;
+      if (c < c1) {
+        double* XL = A[k];
+        double* X = A[(k + 1) % kP1R];
+        double* XR = A[(k + 2) % kP1R];
+        // publish column c+1 for the next step, then read the y-neighbours of column c
+        char* bnext = mybuf + ((k + 1) % 3) * (32 * kP1Stride);
+        const char* bcur = mybuf + (k % 3) * (32 * kP1Stride);
+        *reinterpret_cast<double2*>(bnext + own) = make_double2(XR[0], XR[1]);
+        *reinterpret_cast<double2*>(bnext + own + 16) = make_double2(XR[2], XR[3]);
+        __syncwarp();
+        double XD[4], XU[4], out[4];
+        {
+          const double2 d0 = *reinterpret_cast<const double2*>(bcur + dn);
+          const double2 d1 = *reinterpret_cast<const double2*>(bcur + dn + 16);
+          const double2 u0 = *reinterpret_cast<const double2*>(bcur + up);
+          const double2 u1 = *reinterpret_cast<const double2*>(bcur + up + 16);
+          XD[0] = d0.x; XD[1] = d0.y; XD[2] = d1.x; XD[3] = d1.y;
+          XU[0] = u0.x; XU[1] = u0.y; XU[2] = u1.x; XU[3] = u1.y;
+        }
+        if (c >= cur.x) {  // rare: next run of this strip
+          cur = nxt;
+          nxt = *(++rp + 1);
+          if (cur.y != 0) p1_load_coef(tab, cur.y == 2 ? 1 : 0, coef);
+        }
+        if (cur.y != 0) {
+          p1_uniform_rows(coef, X, XL, XR, XD, XU, out);
+          if (outlane) st_global_v4(yp, out[0], out[1], out[2], out[3]);
+        }
+        yp += colstride;
+        // column c-1 is dead: reuse its registers for column c + R - 1
+        if (c <= cplain) {
+          if (valid) {
+            ld_global_v4(pn, XL);
+          } else {
+            XL[0] = XL[1] = XL[2] = XL[3] = 0.0;
+          }
+        } else {
+          load_col(c + kP1R - 1, XL);
+        }
+        pn += colstride;
+      }
+    }
+  }
+}
+
+// --------------------------------------------------------------------------
+// order-1 TMA kernel (production path for P = 1)
+// --------------------------------------------------------------------------
+// Same decomposition again (warp = strip of 30 cells + 1 halo cell each side,
+// marching along x), but every column chunk -- 32 cells = 1 KiB, contiguous in
+// memory -- is fetched by ONE bulk asynchronous copy (cp.async.bulk, the TMA unit;
+// SASS UBLKCP) issued by lane 0 into a per-warp ring of kTmaStages stages, each
+// guarded by an mbarrier.  Why TMA: measured with the arithmetic removed
+// (scripts/micro/stream_pattern.cu), 16 warps/SM moving 1 KiB per warp per column
+// reach 5.0 TB/s with LDG.256 into registers (the six scoreboards per warp cap the
+// loads a warp can keep in flight), 4.5 TB/s with 16-byte cp.async (LDGSTS does not
+// merge the two halves of a sector, so L2 serves every sector twice), and 5.9 TB/s
+// with bulk copies, against 6.5 TB/s for a plain copy.
+constexpr int kTmaStages = 6;
+constexpr int kTmaWarps = 8;
+constexpr int kTmaStageBytes = 32 * 32;  // 32 cells x 32 B, dense (bulk copies cannot pad)
+constexpr int kTmaWarpSmem = kTmaStages * kTmaStageBytes + 128;  // ring + mbarriers
+
+__device__ __forceinline__ unsigned smem_addr(const void* p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(void* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(void* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(void* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_load(void* dst, const void* src, unsigned bytes, void* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_addr(dst)),
+      "l"(src), "r"(bytes), "r"(smem_addr(bar))
+      : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(void* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok)
+      : "r"(smem_addr(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(kTmaWarps * 32, 2)
+ipdg_apply_p1_tma(const __grid_constant__ IpTab<1> tab, const ApplyArgs a,
+                  const int2* __restrict__ runs, const int* __restrict__ run_ofs) {
+  constexpr int NST = kTmaStages;
+  extern __shared__ __align__(128) char smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  char* const ring = smem + (size_t)warp * kTmaWarpSmem;
+  unsigned long long* const bars = reinterpret_cast<unsigned long long*>(ring + NST * kTmaStageBytes);
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < NST; ++s) mbar_init(&bars[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+
+  const int nstrips = (a.ny + kStripCells - 1) / kStripCells;
+  const int ngroups = (nstrips + kTmaWarps - 1) / kTmaWarps;
+  const int group = blockIdx.x % ngroups;
+  const int seg = blockIdx.x / ngroups;
+  const int strip = group * kTmaWarps + warp;
+  if (strip >= nstrips) return;
+  const int c0 = (int)((int64_t)a.nx * seg / a.nseg);
+  const int c1 = (int)((int64_t)a.nx * (seg + 1) / a.nseg);
+  if (c0 >= c1) return;
+
+  const int j0 = strip * kStripCells;
+  const int j = j0 - 1 + lane;
+  const bool outlane = lane >= 1 && lane <= kStripCells && j < a.ny;
+  const int jlo = max(j0 - 1, 0), jhi = min(j0 + kStripCells + 1, a.ny);
+  const unsigned bytes = (unsigned)(jhi - jlo) * 32u;  // one column chunk
+  const int dst0 = (jlo - (j0 - 1)) * 32;              // where the chunk starts inside a stage
+  const size_t colstride = (size_t)a.ny * 4;           // doubles per column
+  const int own = lane * 32;
+  const int dn = max(lane - 1, 0) * 32;
+  const int up = min(lane + 1, 31) * 32;
+
+  // cells of the strip outside the mesh are never written by a copy: zero them once
+  if (j < 0 || j >= a.ny) {
+#pragma unroll
+    for (int s = 0; s < NST; ++s) {
+      *reinterpret_cast<double2*>(ring + s * kTmaStageBytes + own) = make_double2(0.0, 0.0);
+      *reinterpret_cast<double2*>(ring + s * kTmaStageBytes + own + 16) = make_double2(0.0, 0.0);
+    }
+  }
+  fence_proxy_async();
+  __syncwarp();
+
+  const double* const src0 = a.x + (size_t)jlo * 4;
+  auto issue = [&](int c, int slot) {
+    // column c into ring slot `slot` (columns beyond c1 are not needed)
+    if (c > c1) return;
+    char* dst = ring + slot * kTmaStageBytes;
+    const double* col = nullptr;
+    if (c >= 0 && c < a.nx)
+      col = src0 + (size_t)c * colstride;
+    else if (c < 0 && a.x_lo != nullptr)
+      col = a.x_lo + (size_t)jlo * 4;
+    else if (c >= a.nx && a.x_hi != nullptr)
+      col = a.x_hi + (size_t)jlo * 4;
+    if (col != nullptr) {
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&bars[slot], bytes);
+        tma_bulk_load(dst + dst0, col, bytes, &bars[slot]);
+      }
+    } else {
+      // no such column (domain boundary): the slot reads as zeros
+      *reinterpret_cast<double2*>(dst + own) = make_double2(0.0, 0.0);
+      *reinterpret_cast<double2*>(dst + own + 16) = make_double2(0.0, 0.0);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[slot]);
+    }
+  };
+  auto wait_slot = [&](int slot, unsigned parity) {
+    while (!mbar_try_wait(&bars[slot], parity)) {
+    }
+  };
+  auto lds4 = [&](const char* p, double* v) {
+    const double2 t0 = *reinterpret_cast<const double2*>(p);
+    const double2 t1 = *reinterpret_cast<const double2*>(p + 16);
+    v[0] = t0.x; v[1] = t0.y; v[2] = t1.x; v[3] = t1.y;
+  };
+
+  // run list of this strip: (end column, phase code or 0) with increasing end
+  const int2* rp = runs + run_ofs[strip];
+  int2 cur = rp[0];
+  while (cur.x <= c0) cur = *++rp;
+  int2 nxt = rp[1];  // the list ends with sentinel runs, so rp[1] always exists
+  P1Coef coef;
+  p1_load_coef(tab, cur.y == 2 ? 1 : 0, coef);
+
+  // prologue: columns c0-1 .. c0+NST-2 into slots 0 .. NST-1
+#pragma unroll
+  for (int k = 0; k < NST; ++k) issue(c0 - 1 + k, k);
+  double X[4], XL[4];
+  wait_slot(0, 0);
+  wait_slot(1, 0);
+  lds4(ring + 0 * kTmaStageBytes + own, XL);
+  lds4(ring + 1 * kTmaStageBytes + own, X);
+  __syncwarp();
+
+  double* yp = a.y + (size_t)c0 * colstride + (size_t)j * 4;
+  int slot_c = 1;              // ring slot of column c
+  unsigned par_r = 0;          // phase parity of the slot of column c+1
+  for (int c = c0; c < c1; ++c) {
+    const int slot_l = slot_c == 0 ? NST - 1 : slot_c - 1;
+    const int slot_r = slot_c == NST - 1 ? 0 : slot_c + 1;
+    // refill the slot of column c-1 (nobody reads it any more) with column c+NST-1
+    issue(c + NST - 1, slot_l);
+    // wait for column c+1
+    if (slot_r == 0) par_r ^= 1;  // the ring wrapped: slot 0 is in its next phase
+    wait_slot(slot_r, par_r);
+
+    double XR[4], XD[4], XU[4], out[4];
+    const char* stc = ring + slot_c * kTmaStageBytes;
+    lds4(ring + slot_r * kTmaStageBytes + own, XR);
+    lds4(stc + dn, XD);
+    lds4(stc + up, XU);
+    if (c >= cur.x) {  // rare: next run of this strip
+      cur = nxt;
+      nxt = *(++rp + 1);
+      if (cur.y != 0) p1_load_coef(tab, cur.y == 2 ? 1 : 0, coef);
+    }
+    if (cur.y != 0) {
+      p1_uniform_rows(coef, X, XL, XR, XD, XU, out);
+      if (outlane) st_global_v4(yp, out[0], out[1], out[2], out[3]);
+    }
+    yp += colstride;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      XL[k] = X[k];
+      X[k] = XR[k];
+    }
+    slot_c = slot_r;
+    __syncwarp();  // everyone is done with column c's slot before it is refilled
+  }
 }
 
 // --------------------------------------------------------------------------
@@ -373,6 +720,35 @@ static int launch_apply(const IpdgHandle* h, const ApplyArgs& args0, int algo, c
     const int64_t ncells = (int64_t)h->nx * h->ny;
     int blocks = (int)std::min<int64_t>((ncells + 127) / 128, (int64_t)sm_count() * 32);
     ipdg_apply_simple<P><<<blocks, 128, 0, st>>>(tab, args);
+  } else if (P == 1 && algo == 3) {
+    const int nstrips = (h->ny + kStripCells - 1) / kStripCells;
+    const int ngroups = (nstrips + kP1Warps - 1) / kP1Warps;
+    int nseg = std::max(1, (sm_count() * 2) / ngroups);
+    nseg = std::min(nseg, std::max(1, h->nx / 16));
+    args.nseg = nseg;
+    if constexpr (P == 1)
+      ipdg_apply_p1<<<ngroups * nseg, kP1Warps * 32, 0, st>>>(tab, args, h->runs_dev, h->run_ofs_dev);
+    if (h->nfix > 0)
+      ipdg_apply_fixup<P><<<(h->nfix + 127) / 128, 128, 0, st>>>(tab, args, h->fix_dev, h->nfix);
+  } else if (P == 1 && algo == 0) {
+    const int nstrips = (h->ny + kStripCells - 1) / kStripCells;
+    const int ngroups = (nstrips + kP1Warps - 1) / kP1Warps;
+    int nseg = std::max(1, (sm_count() * 2) / ngroups);
+    nseg = std::min(nseg, std::max(1, h->nx / 16));
+    args.nseg = nseg;
+    if constexpr (P == 1) {
+      const size_t smem = (size_t)kTmaWarps * kTmaWarpSmem;
+      static bool attr_set = false;
+      if (!attr_set) {
+        STEFAN_CUDA(cudaFuncSetAttribute(ipdg_apply_p1_tma, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem));
+        attr_set = true;
+      }
+      ipdg_apply_p1_tma<<<ngroups * nseg, kTmaWarps * 32, smem, st>>>(tab, args, h->runs_dev,
+                                                                      h->run_ofs_dev);
+    }
+    if (h->nfix > 0)
+      ipdg_apply_fixup<P><<<(h->nfix + 127) / 128, 128, 0, st>>>(tab, args, h->fix_dev, h->nfix);
   } else {
     const int nstrips = (h->ny + kStripCells - 1) / kStripCells;
     const int ngroups = (nstrips + C::WARPS - 1) / C::WARPS;
@@ -424,6 +800,8 @@ int stefan_ipdg_create(const stefan_ipdg_params* p, const int8_t* phase, const i
   h->flags_dev = nullptr;
   h->fix_dev = nullptr;
   h->nfix = 0;
+  h->runs_dev = nullptr;
+  h->run_ofs_dev = nullptr;
   h->tab_host = nullptr;
   const int NF = (p->order + 1) * (p->order + 1);
   h->ndofs = (int64_t)p->nx * p->ny * NF;
@@ -479,10 +857,32 @@ int stefan_ipdg_create(const stefan_ipdg_params* p, const int8_t* phase, const i
     }
   }
   h->nfix = (int)fix.size();
+  // run lists: maximal column ranges over which a strip keeps the same flag, as
+  // (end column, flag); each list ends with a sentinel that is never reached
+  std::vector<int2> runs;
+  std::vector<int> run_ofs(nstrips);
+  for (int sidx = 0; sidx < nstrips; ++sidx) {
+    run_ofs[sidx] = (int)runs.size();
+    const uint8_t* f = flags.data() + (size_t)sidx * nxpad;
+    for (int i = 0; i < p->nx;) {
+      int e = i + 1;
+      while (e < p->nx && f[e] == f[i]) ++e;
+      runs.push_back(make_int2(e, (int)f[i]));
+      i = e;
+    }
+    runs.push_back(make_int2(INT32_MAX, 0));
+    runs.push_back(make_int2(INT32_MAX, 0));
+  }
   cudaError_t e = cudaMalloc(&h->phase_dev, pn);
   if (e == cudaSuccess) e = cudaMemcpy(h->phase_dev, ph.data(), pn, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMalloc(&h->flags_dev, flags.size());
   if (e == cudaSuccess) e = cudaMemcpy(h->flags_dev, flags.data(), flags.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&h->runs_dev, runs.size() * sizeof(int2));
+  if (e == cudaSuccess)
+    e = cudaMemcpy(h->runs_dev, runs.data(), runs.size() * sizeof(int2), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&h->run_ofs_dev, run_ofs.size() * sizeof(int));
+  if (e == cudaSuccess)
+    e = cudaMemcpy(h->run_ofs_dev, run_ofs.data(), run_ofs.size() * sizeof(int), cudaMemcpyHostToDevice);
   if (e == cudaSuccess && h->nfix > 0) e = cudaMalloc(&h->fix_dev, fix.size() * sizeof(int32_t));
   if (e == cudaSuccess && h->nfix > 0)
     e = cudaMemcpy(h->fix_dev, fix.data(), fix.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
@@ -497,6 +897,8 @@ int stefan_ipdg_destroy(stefan_ipdg* hv) {
   if (h->phase_dev) cudaFree(h->phase_dev);
   if (h->flags_dev) cudaFree(h->flags_dev);
   if (h->fix_dev) cudaFree(h->fix_dev);
+  if (h->runs_dev) cudaFree(h->runs_dev);
+  if (h->run_ofs_dev) cudaFree(h->run_ofs_dev);
   switch (h->order) {
     case 1: delete static_cast<IpTab<1>*>(h->tab_host); break;
     case 2: delete static_cast<IpTab<2>*>(h->tab_host); break;
@@ -523,7 +925,8 @@ int stefan_ipdg_apply(stefan_ipdg* hv, const double* x, double* y, const double*
   STEFAN_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
                  (reinterpret_cast<uintptr_t>(x_lo) & 15) == 0 && (reinterpret_cast<uintptr_t>(x_hi) & 15) == 0,
                  "stefan_ipdg_apply: device pointers must be 16-byte aligned");
-  STEFAN_REQUIRE(algo == 0 || algo == 1, "stefan_ipdg_apply: unknown algo %d", algo);
+  STEFAN_REQUIRE(algo >= 0 && algo <= 3, "stefan_ipdg_apply: unknown algo %d", algo);
+  STEFAN_REQUIRE(algo != 3 || h->order == 1, "stefan_ipdg_apply: algo 3 exists for order 1 only");
   ApplyArgs a{x, x_lo, x_hi, y, h->phase_dev, h->flags_dev, (h->nx + 15) / 16 * 16, h->nx, h->ny, 1};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (h->order) {
