@@ -108,6 +108,11 @@ int64_t stefan_ipdg_ndofs(const stefan_ipdg* h);
 int stefan_ipdg_apply(stefan_ipdg* h, const double* x, double* y, const double* x_lo,
                       const double* x_hi, int32_t algo, void* stream);
 
+/* Same operation with HOST buffers (pinned memory recommended): host->device
+ * copies, kernels and device->host copies of `nslabs` column slabs are pipelined
+ * on three streams inside the call (nslabs <= 0: default).  Synchronous. */
+int stefan_ipdg_apply_host(stefan_ipdg* h, const double* x_host, double* y_host, int32_t nslabs);
+
 #ifdef __cplusplus
 }
 #endif

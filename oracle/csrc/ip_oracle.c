@@ -24,9 +24,9 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
-#ifdef _OPENMP
-#include <omp.h>
-#endif
+#include <pthread.h>
+#include <time.h>
+#include <unistd.h>
 
 #define MAXN1 4
 #define MAXNF 16
@@ -48,11 +48,44 @@ typedef struct {
 } csr_t;
 
 static double now_s(void) {
-#ifdef _OPENMP
-  return omp_get_wtime();
-#else
-  return 0.0;
-#endif
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+/* minimal parallel-for over row ranges (this image's gcc has no libgomp) */
+typedef void (*range_fn)(int64_t lo, int64_t hi, void* ctx);
+typedef struct {
+  range_fn fn;
+  int64_t lo, hi;
+  void* ctx;
+} task_t;
+static void* run_task(void* p) {
+  task_t* t = (task_t*)p;
+  t->fn(t->lo, t->hi, t->ctx);
+  return NULL;
+}
+static int hw_threads(void) {
+  long n = sysconf(_SC_NPROCESSORS_ONLN);
+  return n > 0 ? (int)n : 1;
+}
+static void parallel_for(int64_t n, int nthreads, range_fn fn, void* ctx) {
+  if (nthreads <= 0) nthreads = hw_threads();
+  if (nthreads > 256) nthreads = 256;
+  if (nthreads == 1 || n < 1024) {
+    fn(0, n, ctx);
+    return;
+  }
+  pthread_t th[256];
+  task_t tk[256];
+  for (int t = 0; t < nthreads; ++t) {
+    tk[t].fn = fn;
+    tk[t].lo = n * t / nthreads;
+    tk[t].hi = n * (t + 1) / nthreads;
+    tk[t].ctx = ctx;
+    pthread_create(&th[t], NULL, run_task, &tk[t]);
+  }
+  for (int t = 0; t < nthreads; ++t) pthread_join(th[t], NULL);
 }
 
 static void coo_reserve(coo_t* c, int64_t extra) {
@@ -132,9 +165,9 @@ typedef struct {
   int n;
   double p[MAXQ * MAXQ][2];
   double w[MAXQ * MAXQ];
-} quad_t;
+} quadrule_t;
 
-static void cell_quadrature(int nq, quad_t* q) {
+static void cell_quadrature(int nq, quadrule_t* q) {
   double x[MAXQ], w[MAXQ];
   gauss_legendre(nq, x, w);
   q->n = nq * nq;
@@ -146,7 +179,7 @@ static void cell_quadrature(int nq, quad_t* q) {
     }
 }
 
-static void face_quadrature(int faceid, int nq, quad_t* q) {
+static void face_quadrature(int faceid, int nq, quadrule_t* q) {
   double x[MAXQ], w[MAXQ];
   gauss_legendre(nq, x, w);
   q->n = nq;
@@ -166,7 +199,7 @@ static const int kOpposite[4] = {2, 3, 0, 1};
 
 /* ------------------------------------------------------ element matrices */
 /* IP_gradient_operator.jl:1-9 */
-static void gradient_operator(int order, const quad_t* quad, double k, const double* jac,
+static void gradient_operator(int order, const quadrule_t* quad, double k, const double* jac,
                               double detjac, double* M) {
   int nf = (order + 1) * (order + 1);
   double G[MAXNF * 2];
@@ -180,7 +213,7 @@ static void gradient_operator(int order, const quad_t* quad, double k, const dou
 }
 
 /* IP_flux_operator.jl:1-33 (constant normal and scale area on mesh faces) */
-static void flux_operator(int order, const quad_t* q1, const quad_t* q2, const double* normal,
+static void flux_operator(int order, const quadrule_t* q1, const quadrule_t* q2, const double* normal,
                           double k, const double* jac, double sa, double* M) {
   int nf = (order + 1) * (order + 1);
   double G[MAXNF * 2], V[MAXNF];
@@ -196,7 +229,7 @@ static void flux_operator(int order, const quad_t* q1, const quad_t* q2, const d
 }
 
 /* IP_penalty_operator.jl:1-18 */
-static void mass_operator(int order, const quad_t* q1, const quad_t* q2, double sa, double* M) {
+static void mass_operator(int order, const quadrule_t* q1, const quadrule_t* q2, double sa, double* M) {
   int nf = (order + 1) * (order + 1);
   double V1[MAXNF], V2[MAXNF];
   memset(M, 0, sizeof(double) * nf * nf);
@@ -229,12 +262,13 @@ static void add_t(int nf, double sa, const double* A, double sb, const double* B
 }
 
 /* IP_flux_operator.jl:35-118 */
-static void assemble_face_flux_operator(coo_t* c, int order, const quad_t* q1, const quad_t* q2,
+static void assemble_face_flux_operator(coo_t* c, int order, const quadrule_t* q1, const quadrule_t* q2,
                                         const double* normal, double k1, double k2,
                                         const double* jac, double sa, int64_t cell1, int64_t cell2) {
   int nf = (order + 1) * (order + 1);
   double M11[MAXNF * MAXNF], M12[MAXNF * MAXNF], M21[MAXNF * MAXNF], M22[MAXNF * MAXNF];
   double T[MAXNF * MAXNF];
+  memset(T, 0, sizeof(T));
   flux_operator(order, q1, q1, normal, k1, jac, sa, M11);
   flux_operator(order, q1, q2, normal, k1, jac, sa, M12);
   flux_operator(order, q2, q1, normal, k2, jac, sa, M21);
@@ -256,7 +290,7 @@ static void assemble_face_flux_operator(coo_t* c, int order, const quad_t* q1, c
 }
 
 /* IP_penalty_operator.jl:21-65 and IP_robin_interface_operator.jl:1-45 */
-static void assemble_face_mass_blocks(coo_t* c, int order, const quad_t* q1, const quad_t* q2,
+static void assemble_face_mass_blocks(coo_t* c, int order, const quadrule_t* q1, const quadrule_t* q2,
                                       double coef, double offsign, double sa, int64_t cell1,
                                       int64_t cell2) {
   int nf = (order + 1) * (order + 1);
@@ -284,7 +318,7 @@ static int64_t neighbour(int nx, int ny, int f, int64_t cell) {
   }
 }
 
-static int cmp_entry(const void* a, const void* b);
+
 
 typedef struct {
   int64_t col;
@@ -297,6 +331,40 @@ static int cmp_entry(const void* a, const void* b) {
 }
 
 /* dropzeros!(sparse(rows, cols, vals, N, N)) */
+typedef struct {
+  entry_t* ent;
+  int64_t *cnt, *rownnz;
+  csr_t* A;
+} compress_ctx;
+
+static void compress_rows(int64_t lo, int64_t hi, void* p) {
+  compress_ctx* c = (compress_ctx*)p;
+  for (int64_t r = lo; r < hi; ++r) {
+    int64_t b = c->cnt[r], e = c->cnt[r + 1], k = b;
+    qsort(c->ent + b, e - b, sizeof(entry_t), cmp_entry);
+    for (int64_t i = b; i < e;) {
+      int64_t col = c->ent[i].col;
+      double v = 0.0;
+      while (i < e && c->ent[i].col == col) v += c->ent[i++].val;
+      if (v != 0.0) {
+        c->ent[k].col = col;
+        c->ent[k].val = v;
+        k++;
+      }
+    }
+    c->rownnz[r] = k - b;
+  }
+}
+
+static void compress_copy(int64_t lo, int64_t hi, void* p) {
+  compress_ctx* c = (compress_ctx*)p;
+  for (int64_t r = lo; r < hi; ++r)
+    for (int64_t i = 0; i < c->rownnz[r]; ++i) {
+      c->A->indices[c->A->indptr[r] + i] = (int32_t)c->ent[c->cnt[r] + i].col;
+      c->A->data[c->A->indptr[r] + i] = c->ent[c->cnt[r] + i].val;
+    }
+}
+
 static void compress(const coo_t* c, int64_t nrows, csr_t* A) {
   int64_t* cnt = (int64_t*)calloc(nrows + 1, sizeof(int64_t));
   for (int64_t e = 0; e < c->n; ++e) cnt[c->rows[e] + 1]++;
@@ -313,33 +381,14 @@ static void compress(const coo_t* c, int64_t nrows, csr_t* A) {
   A->nrows = nrows;
   A->indptr = (int64_t*)malloc(sizeof(int64_t) * (nrows + 1));
   int64_t* rownnz = (int64_t*)calloc(nrows, sizeof(int64_t));
-#pragma omp parallel for schedule(static)
-  for (int64_t r = 0; r < nrows; ++r) {
-    int64_t b = cnt[r], e = cnt[r + 1], k = b;
-    qsort(ent + b, e - b, sizeof(entry_t), cmp_entry);
-    for (int64_t i = b; i < e;) {
-      int64_t col = ent[i].col;
-      double v = 0.0;
-      while (i < e && ent[i].col == col) v += ent[i++].val;
-      if (v != 0.0) {
-        ent[k].col = col;
-        ent[k].val = v;
-        k++;
-      }
-    }
-    rownnz[r] = k - b;
-  }
+  compress_ctx ctx = {ent, cnt, rownnz, A};
+  parallel_for(nrows, 0, compress_rows, &ctx);
   A->indptr[0] = 0;
   for (int64_t r = 0; r < nrows; ++r) A->indptr[r + 1] = A->indptr[r] + rownnz[r];
   A->nnz = A->indptr[nrows];
   A->indices = (int32_t*)malloc(sizeof(int32_t) * (A->nnz ? A->nnz : 1));
   A->data = (double*)malloc(sizeof(double) * (A->nnz ? A->nnz : 1));
-#pragma omp parallel for schedule(static)
-  for (int64_t r = 0; r < nrows; ++r)
-    for (int64_t i = 0; i < rownnz[r]; ++i) {
-      A->indices[A->indptr[r] + i] = (int32_t)ent[cnt[r] + i].col;
-      A->data[A->indptr[r] + i] = ent[cnt[r] + i].val;
-    }
+  parallel_for(nrows, 0, compress_copy, &ctx);
   free(cnt);
   free(ent);
   free(pos);
@@ -357,11 +406,12 @@ csr_t* ip_oracle_assemble(int order, int numqp, int nx, int ny, double hx, doubl
   const double jac[2] = {0.5 * hx, 0.5 * hy};
   const double detjac = jac[0] * jac[1];
   const double facedetjac[4] = {jac[0], jac[1], jac[0], jac[1]};
-  quad_t cq, fq[4];
+  quadrule_t cq, fq[4];
   cell_quadrature(numqp, &cq);
   for (int f = 0; f < 4; ++f) face_quadrature(f, numqp, &fq[f]);
   coo_t c = {0, 0, NULL, NULL, NULL};
   double M[MAXNF * MAXNF], T[MAXNF * MAXNF];
+  memset(T, 0, sizeof(T));
   double t0 = now_s();
 #define SIGN(cell) (phase ? (int)phase[cell] : 1)
 #define COND(s) ((s) > 0 ? k1 : k2)
@@ -460,26 +510,29 @@ void ip_oracle_csr(const csr_t* A, int64_t* indptr, int32_t* indices, double* da
   memcpy(data, A->data, sizeof(double) * A->nnz);
 }
 
-/* y = A x; nthreads <= 0: all available (Julia's SparseArrays `*` is serial: 1) */
-void ip_oracle_spmv(const csr_t* A, const double* x, double* y, int nthreads) {
-#ifdef _OPENMP
-  if (nthreads <= 0) nthreads = omp_get_max_threads();
-#endif
-#pragma omp parallel for schedule(static) num_threads(nthreads)
-  for (int64_t r = 0; r < A->nrows; ++r) {
+/* y = A x; nthreads <= 0: all hardware threads (Julia's SparseArrays `*` is serial: 1) */
+typedef struct {
+  const csr_t* A;
+  const double* x;
+  double* y;
+} spmv_ctx;
+
+static void spmv_rows(int64_t lo, int64_t hi, void* p) {
+  spmv_ctx* c = (spmv_ctx*)p;
+  const csr_t* A = c->A;
+  for (int64_t r = lo; r < hi; ++r) {
     double v = 0.0;
-    for (int64_t i = A->indptr[r]; i < A->indptr[r + 1]; ++i) v += A->data[i] * x[A->indices[i]];
-    y[r] = v;
+    for (int64_t i = A->indptr[r]; i < A->indptr[r + 1]; ++i) v += A->data[i] * c->x[A->indices[i]];
+    c->y[r] = v;
   }
 }
 
-int ip_oracle_max_threads(void) {
-#ifdef _OPENMP
-  return omp_get_max_threads();
-#else
-  return 1;
-#endif
+void ip_oracle_spmv(const csr_t* A, const double* x, double* y, int nthreads) {
+  spmv_ctx ctx = {A, x, y};
+  parallel_for(A->nrows, nthreads, spmv_rows, &ctx);
 }
+
+int ip_oracle_max_threads(void) { return hw_threads(); }
 
 void ip_oracle_free(csr_t* A) {
   if (!A) return;

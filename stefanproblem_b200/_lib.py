@@ -42,6 +42,8 @@ _SIGNATURES = {
                                           ctypes.POINTER(ctypes.c_void_p)]),
     "stefan_ipdg_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "stefan_ipdg_ndofs": (ctypes.c_int64, [ctypes.c_void_p]),
+    "stefan_ipdg_apply_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                              ctypes.c_int32]),
     "stefan_ipdg_apply": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
                                          ctypes.c_void_p]),

@@ -42,6 +42,11 @@ struct IpdgHandle {
   uint8_t* flags_dev;  // [nstrips][nxpad]
   int32_t* fix_dev;    // cells recomputed by the fix-up kernel
   int nfix;
+  std::vector<int> fix_col_ofs;  // fix cells are sorted by column: [nx+1] offsets
+  double *xh_dev, *yh_dev;       // device staging of the host path
+  cudaStream_t hs[3];
+  cudaEvent_t hev[64];
+  bool host_ready;
   int2* runs_dev;      // per-strip run lists (order-1 kernel)
   int* run_ofs_dev;
   void* tab_host;     // IpTab<P>
@@ -81,7 +86,8 @@ struct ApplyArgs {
   const uint8_t* flags;  // [nstrips][nxpad] strip classification (stream kernel)
   int nxpad;             // nx rounded up to 16 (flag rows are 16-byte aligned)
   int nx, ny;
-  int nseg;  // x segments (stream kernel)
+  int nseg;  // x segments (stream kernels)
+  int cbeg, cend;  // columns to produce (a sub-range when the host path pipelines slabs)
 };
 
 __device__ __forceinline__ int phase_at(const int8_t* __restrict__ ph, int ny, int i, int j) {
@@ -95,9 +101,9 @@ template <int P>
 __global__ void __launch_bounds__(128)
 ipdg_apply_simple(const __grid_constant__ IpTab<P> tab, const ApplyArgs a) {
   constexpr int NF = (P + 1) * (P + 1);
-  const int64_t ncells = (int64_t)a.nx * a.ny;
-  for (int64_t cell = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; cell < ncells;
-       cell += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t cell_end = (int64_t)a.cend * a.ny;
+  for (int64_t cell = (int64_t)a.cbeg * a.ny + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+       cell < cell_end; cell += (int64_t)gridDim.x * blockDim.x) {
     const int i = (int)(cell / a.ny), j = (int)(cell % a.ny);
     const int s = phase_at(a.phase, a.ny, i, j);
     const int sL = phase_at(a.phase, a.ny, i - 1, j), sR = phase_at(a.phase, a.ny, i + 1, j);
@@ -225,8 +231,8 @@ ipdg_apply_stream(const __grid_constant__ IpTab<P> tab, const ApplyArgs a) {
   const int seg = blockIdx.x / ngroups;
   const int strip = group * C::WARPS + warp;
   if (strip >= nstrips) return;
-  const int c0 = (int)((int64_t)a.nx * seg / a.nseg);
-  const int c1 = (int)((int64_t)a.nx * (seg + 1) / a.nseg);
+  const int c0 = a.cbeg + (int)((int64_t)(a.cend - a.cbeg) * seg / a.nseg);
+  const int c1 = a.cbeg + (int)((int64_t)(a.cend - a.cbeg) * (seg + 1) / a.nseg);
   if (c0 >= c1) return;
 
   char* ring = smem + (size_t)warp * NST * STAGE_BYTES;
@@ -419,8 +425,8 @@ ipdg_apply_p1(const __grid_constant__ IpTab<1> tab, const ApplyArgs a,
   const int seg = blockIdx.x / ngroups;
   const int strip = group * kP1Warps + warp;
   if (strip >= nstrips) return;
-  const int c0 = (int)((int64_t)a.nx * seg / a.nseg);
-  const int c1 = (int)((int64_t)a.nx * (seg + 1) / a.nseg);
+  const int c0 = a.cbeg + (int)((int64_t)(a.cend - a.cbeg) * seg / a.nseg);
+  const int c1 = a.cbeg + (int)((int64_t)(a.cend - a.cbeg) * (seg + 1) / a.nseg);
   if (c0 >= c1) return;
 
   const int j0 = strip * kStripCells;
@@ -591,8 +597,8 @@ ipdg_apply_p1_tma(const __grid_constant__ IpTab<1> tab, const ApplyArgs a,
   const int seg = blockIdx.x / ngroups;
   const int strip = group * kTmaWarps + warp;
   if (strip >= nstrips) return;
-  const int c0 = (int)((int64_t)a.nx * seg / a.nseg);
-  const int c1 = (int)((int64_t)a.nx * (seg + 1) / a.nseg);
+  const int c0 = a.cbeg + (int)((int64_t)(a.cend - a.cbeg) * seg / a.nseg);
+  const int c1 = a.cbeg + (int)((int64_t)(a.cend - a.cbeg) * (seg + 1) / a.nseg);
   if (c0 >= c1) return;
 
   const int j0 = strip * kStripCells;
@@ -716,26 +722,31 @@ static int launch_apply(const IpdgHandle* h, const ApplyArgs& args0, int algo, c
   using C = StreamCfg<P>;
   const IpTab<P>& tab = *static_cast<const IpTab<P>*>(h->tab_host);
   ApplyArgs args = args0;
+  const int ncol = args.cend - args.cbeg;
+  if (ncol <= 0) return ST_OK;
   if (algo == 1) {
-    const int64_t ncells = (int64_t)h->nx * h->ny;
+    const int64_t ncells = (int64_t)ncol * h->ny;
     int blocks = (int)std::min<int64_t>((ncells + 127) / 128, (int64_t)sm_count() * 32);
     ipdg_apply_simple<P><<<blocks, 128, 0, st>>>(tab, args);
-  } else if (P == 1 && algo == 3) {
-    const int nstrips = (h->ny + kStripCells - 1) / kStripCells;
-    const int ngroups = (nstrips + kP1Warps - 1) / kP1Warps;
-    int nseg = std::max(1, (sm_count() * 2) / ngroups);
-    nseg = std::min(nseg, std::max(1, h->nx / 16));
+    STEFAN_CUDA(cudaGetLastError());
+    return ST_OK;
+  }
+  // stream kernels: CTA = (group of adjacent strips, x segment); one wave of
+  // 2 CTAs per SM, segments no shorter than 16 columns
+  const int nstrips = (h->ny + kStripCells - 1) / kStripCells;
+  auto grid_for = [&](int warps, int ctas_per_sm) {
+    const int ngroups = (nstrips + warps - 1) / warps;
+    int nseg = std::max(1, (sm_count() * ctas_per_sm) / ngroups);
+    nseg = std::min(nseg, std::max(1, ncol / 16));
     args.nseg = nseg;
+    return ngroups * nseg;
+  };
+  if (P == 1 && algo == 3) {
+    const int grid = grid_for(kP1Warps, 2);
     if constexpr (P == 1)
-      ipdg_apply_p1<<<ngroups * nseg, kP1Warps * 32, 0, st>>>(tab, args, h->runs_dev, h->run_ofs_dev);
-    if (h->nfix > 0)
-      ipdg_apply_fixup<P><<<(h->nfix + 127) / 128, 128, 0, st>>>(tab, args, h->fix_dev, h->nfix);
+      ipdg_apply_p1<<<grid, kP1Warps * 32, 0, st>>>(tab, args, h->runs_dev, h->run_ofs_dev);
   } else if (P == 1 && algo == 0) {
-    const int nstrips = (h->ny + kStripCells - 1) / kStripCells;
-    const int ngroups = (nstrips + kP1Warps - 1) / kP1Warps;
-    int nseg = std::max(1, (sm_count() * 2) / ngroups);
-    nseg = std::min(nseg, std::max(1, h->nx / 16));
-    args.nseg = nseg;
+    const int grid = grid_for(kTmaWarps, 2);
     if constexpr (P == 1) {
       const size_t smem = (size_t)kTmaWarps * kTmaWarpSmem;
       static bool attr_set = false;
@@ -744,31 +755,34 @@ static int launch_apply(const IpdgHandle* h, const ApplyArgs& args0, int algo, c
                                          (int)smem));
         attr_set = true;
       }
-      ipdg_apply_p1_tma<<<ngroups * nseg, kTmaWarps * 32, smem, st>>>(tab, args, h->runs_dev,
-                                                                      h->run_ofs_dev);
+      ipdg_apply_p1_tma<<<grid, kTmaWarps * 32, smem, st>>>(tab, args, h->runs_dev, h->run_ofs_dev);
     }
-    if (h->nfix > 0)
-      ipdg_apply_fixup<P><<<(h->nfix + 127) / 128, 128, 0, st>>>(tab, args, h->fix_dev, h->nfix);
   } else {
-    const int nstrips = (h->ny + kStripCells - 1) / kStripCells;
-    const int ngroups = (nstrips + C::WARPS - 1) / C::WARPS;
-    // aim at MINB resident CTAs per SM in one wave; segments no shorter than 16 columns
-    int nseg = std::max(1, (sm_count() * C::MINB) / ngroups);
-    nseg = std::min(nseg, std::max(1, h->nx / 16));
-    args.nseg = nseg;
-        const size_t smem = (size_t)C::WARPS * C::NST * (32 * C::STRIDE + 16);
+    const int grid = grid_for(C::WARPS, C::MINB);
+    const size_t smem = (size_t)C::WARPS * C::NST * (32 * C::STRIDE + 16);
     static bool attr_set = false;
     if (!attr_set) {
       STEFAN_CUDA(cudaFuncSetAttribute(ipdg_apply_stream<P>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr_set = true;
     }
-    ipdg_apply_stream<P><<<ngroups * nseg, C::WARPS * 32, smem, st>>>(tab, args);
-    if (h->nfix > 0)
-      ipdg_apply_fixup<P><<<(h->nfix + 127) / 128, 128, 0, st>>>(tab, args, h->fix_dev, h->nfix);
+    ipdg_apply_stream<P><<<grid, C::WARPS * 32, smem, st>>>(tab, args);
   }
+  // exception cells of the produced columns (the list is sorted by column)
+  const int f0 = h->fix_col_ofs[args.cbeg], f1 = h->fix_col_ofs[args.cend];
+  if (f1 > f0)
+    ipdg_apply_fixup<P><<<(f1 - f0 + 127) / 128, 128, 0, st>>>(tab, args, h->fix_dev + f0, f1 - f0);
   STEFAN_CUDA(cudaGetLastError());
   return ST_OK;
+}
+
+static int dispatch_apply(const IpdgHandle* h, const ApplyArgs& a, int algo, cudaStream_t st) {
+  switch (h->order) {
+    case 1: return launch_apply<1>(h, a, algo, st);
+    case 2: return launch_apply<2>(h, a, algo, st);
+    case 3: return launch_apply<3>(h, a, algo, st);
+  }
+  return fail(ST_UNSUPPORTED, "order %d", h->order);
 }
 
 }  // namespace stefan
@@ -801,6 +815,8 @@ int stefan_ipdg_create(const stefan_ipdg_params* p, const int8_t* phase, const i
   h->fix_dev = nullptr;
   h->nfix = 0;
   h->runs_dev = nullptr;
+  h->xh_dev = h->yh_dev = nullptr;
+  h->host_ready = false;
   h->run_ofs_dev = nullptr;
   h->tab_host = nullptr;
   const int NF = (p->order + 1) * (p->order + 1);
@@ -857,6 +873,9 @@ int stefan_ipdg_create(const stefan_ipdg_params* p, const int8_t* phase, const i
     }
   }
   h->nfix = (int)fix.size();
+  h->fix_col_ofs.assign(p->nx + 1, 0);
+  for (int32_t cell : fix) h->fix_col_ofs[cell / p->ny + 1]++;
+  for (int i = 0; i < p->nx; ++i) h->fix_col_ofs[i + 1] += h->fix_col_ofs[i];
   // run lists: maximal column ranges over which a strip keeps the same flag, as
   // (end column, flag); each list ends with a sentinel that is never reached
   std::vector<int2> runs;
@@ -898,6 +917,12 @@ int stefan_ipdg_destroy(stefan_ipdg* hv) {
   if (h->flags_dev) cudaFree(h->flags_dev);
   if (h->fix_dev) cudaFree(h->fix_dev);
   if (h->runs_dev) cudaFree(h->runs_dev);
+  if (h->xh_dev) cudaFree(h->xh_dev);
+  if (h->yh_dev) cudaFree(h->yh_dev);
+  if (h->host_ready) {
+    for (auto& s : h->hs) cudaStreamDestroy(s);
+    for (auto& e : h->hev) cudaEventDestroy(e);
+  }
   if (h->run_ofs_dev) cudaFree(h->run_ofs_dev);
   switch (h->order) {
     case 1: delete static_cast<IpTab<1>*>(h->tab_host); break;
@@ -927,14 +952,54 @@ int stefan_ipdg_apply(stefan_ipdg* hv, const double* x, double* y, const double*
                  "stefan_ipdg_apply: device pointers must be 16-byte aligned");
   STEFAN_REQUIRE(algo >= 0 && algo <= 3, "stefan_ipdg_apply: unknown algo %d", algo);
   STEFAN_REQUIRE(algo != 3 || h->order == 1, "stefan_ipdg_apply: algo 3 exists for order 1 only");
-  ApplyArgs a{x, x_lo, x_hi, y, h->phase_dev, h->flags_dev, (h->nx + 15) / 16 * 16, h->nx, h->ny, 1};
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  switch (h->order) {
-    case 1: return launch_apply<1>(h, a, algo, st);
-    case 2: return launch_apply<2>(h, a, algo, st);
-    case 3: return launch_apply<3>(h, a, algo, st);
+  ApplyArgs a{x, x_lo, x_hi, y, h->phase_dev, h->flags_dev, (h->nx + 15) / 16 * 16, h->nx, h->ny, 1, 0, h->nx};
+  return dispatch_apply(h, a, algo, static_cast<cudaStream_t>(stream));
+}
+
+// y = A x with HOST buffers (pinned memory recommended): the mesh is cut into
+// `nslabs` column slabs that are pipelined on three streams -- host->device copy
+// of slab s+1, kernel on slab s, device->host copy of slab s-1 run concurrently --
+// so the call is bounded by max(H2D, D2H) over PCIe, not their sum.
+int stefan_ipdg_apply_host(stefan_ipdg* hv, const double* x_host, double* y_host, int32_t nslabs) {
+  IpdgHandle* h = reinterpret_cast<IpdgHandle*>(hv);
+  STEFAN_REQUIRE(h && x_host && y_host, "stefan_ipdg_apply_host: null argument");
+  STEFAN_REQUIRE(!h->has_lo && !h->has_hi,
+                 "stefan_ipdg_apply_host: handles with halo columns take device buffers");
+  if (nslabs <= 0) nslabs = 16;
+  nslabs = std::min<int>(std::min<int>(nslabs, 32), h->nx);
+  if (!h->host_ready) {
+    STEFAN_CUDA(cudaMalloc(&h->xh_dev, h->ndofs * sizeof(double)));
+    STEFAN_CUDA(cudaMalloc(&h->yh_dev, h->ndofs * sizeof(double)));
+    for (auto& s : h->hs) STEFAN_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    for (auto& e : h->hev) STEFAN_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->host_ready = true;
   }
-  return fail(ST_UNSUPPORTED, "stefan_ipdg_apply: order %d", h->order);
+  const int NF = (h->order + 1) * (h->order + 1);
+  const size_t col = (size_t)h->ny * NF;  // doubles per column
+  auto slab_begin = [&](int s) { return (int)((int64_t)h->nx * s / nslabs); };
+  for (int s = 0; s <= nslabs; ++s) {
+    if (s < nslabs) {  // upload slab s
+      const int b = slab_begin(s), e = slab_begin(s + 1);
+      STEFAN_CUDA(cudaMemcpyAsync(h->xh_dev + b * col, x_host + b * col, (size_t)(e - b) * col * sizeof(double),
+                                  cudaMemcpyHostToDevice, h->hs[0]));
+      STEFAN_CUDA(cudaEventRecord(h->hev[s], h->hs[0]));
+    }
+    if (s >= 1) {  // slab s-1 needs the first column of slab s: wait for that upload
+      const int k = s - 1;
+      STEFAN_CUDA(cudaStreamWaitEvent(h->hs[1], h->hev[std::min(s, nslabs - 1)], 0));
+      ApplyArgs a{h->xh_dev, nullptr, nullptr, h->yh_dev, h->phase_dev, h->flags_dev, (h->nx + 15) / 16 * 16,
+                  h->nx, h->ny, 1, slab_begin(k), slab_begin(k + 1)};
+      int rc = dispatch_apply(h, a, 0, h->hs[1]);
+      if (rc) return rc;
+      STEFAN_CUDA(cudaEventRecord(h->hev[32 + k], h->hs[1]));
+      STEFAN_CUDA(cudaStreamWaitEvent(h->hs[2], h->hev[32 + k], 0));
+      const int b = slab_begin(k), e = slab_begin(k + 1);
+      STEFAN_CUDA(cudaMemcpyAsync(y_host + b * col, h->yh_dev + b * col, (size_t)(e - b) * col * sizeof(double),
+                                  cudaMemcpyDeviceToHost, h->hs[2]));
+    }
+  }
+  STEFAN_CUDA(cudaStreamSynchronize(h->hs[2]));
+  return ST_OK;
 }
 
 }  // extern "C"

@@ -193,6 +193,18 @@ class IPOperator:
                                                 algo, _stream_ptr(stream)))
         return out
 
+    def apply_host(self, x_host, out_host=None, nslabs=0):
+        """y = A x for HOST tensors / arrays (pinned torch tensors are fastest);
+        copies and kernels are pipelined inside the C call."""
+        import torch
+        if isinstance(x_host, np.ndarray):
+            x_host = torch.from_numpy(np.ascontiguousarray(x_host, dtype=np.float64))
+        assert not x_host.is_cuda and x_host.dtype == torch.float64 and x_host.numel() == self.ndofs
+        if out_host is None:
+            out_host = torch.empty_like(x_host)
+        _lib.check(_lib.lib().stefan_ipdg_apply_host(self._h, _ptr(x_host), _ptr(out_host), nslabs))
+        return out_host
+
     def __matmul__(self, x):
         return self.apply(x)
 
