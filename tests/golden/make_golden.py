@@ -1,0 +1,37 @@
+"""Copies the reference's golden CSV numbers into tests/golden/reference_csv.json.
+Run in the build container (reads /root/reference, which does not exist on the GPU box)."""
+import csv
+import json
+import os
+
+REF = "/root/reference"
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_csv.json")
+
+
+def rows(path):
+    with open(os.path.join(REF, path)) as f:
+        return [[float(v) for v in r] for r in list(csv.reader(f))[1:]]
+
+
+def main():
+    ip_rows = rows("StefanDG/InteriorPenalty/uncut_mesh_tests/IP_convergence.csv")
+    ldg_rows = rows("StefanDG/LocalDG/uncut_mesh_tests/MD-LDG_convergence.csv")
+    robin = rows("StefanRobinIC/DG1D/robin-interface-tests/robin-convergence.csv")
+    gold = {
+        "ip_uncut": [[int(r[0]), r[1], r[2]] for r in ip_rows],
+        "ldg_uncut": [[int(r[0])] + r[1:] for r in ldg_rows],
+        "dg1d_robin_linear": [r[1] for r in robin],
+        "dg1d_robin_quadratic": [r[2] for r in robin],
+        "sources": {
+            "ip_uncut": "StefanDG/InteriorPenalty/uncut_mesh_tests/IP_convergence.csv",
+            "ldg_uncut": "StefanDG/LocalDG/uncut_mesh_tests/MD-LDG_convergence.csv",
+            "dg1d_robin": "StefanRobinIC/DG1D/robin-interface-tests/robin-convergence.csv",
+        },
+    }
+    with open(OUT, "w") as f:
+        json.dump(gold, f, indent=1)
+    print("wrote", OUT)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,136 @@
+"""CPU-side checks of the product's host logic (no GPU, no compute entry points):
+the C-ABI library loads and exports every symbol include/stefan_b200.h declares; the
+reference-element tables; the per-cell row functions run on the host (test harness
+tests/hostcheck) against the oracle; the C oracle against the NumPy oracle."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import fast
+from oracle.basis import gauss_1d, lagrange_1d
+from oracle.mesh import UniformMesh2D
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    header = open(os.path.join(ROOT, "include", "stefan_b200.h")).read()
+    declared = set(re.findall(r"\b(stefan_[a-z0-9_]+)\s*\(", header))
+    L = ctypes.CDLL(built_lib)
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in stefan_b200.h but not exported"
+    from stefanproblem_b200 import _lib
+    assert declared == set(_lib.exported_symbols()), "ctypes binding and header disagree"
+
+
+def test_missing_gpu_fails_loudly(built_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from stefanproblem_b200 import StefanError, cutcelldg as cc
+    basis = cc.LagrangeTensorProductBasis(2, 1)
+    mesh = cc.UniformMesh([0, 0], [1, 1], [4, 4], basis)
+    with pytest.raises(StefanError):
+        cc.IPOperator(mesh, 1, 2, 1.0, 1.0, 1e3)
+
+
+@pytest.mark.parametrize("order,numqp", [(1, 2), (2, 3), (3, 4), (2, 5)])
+def test_reference_tables(built_lib, order, numqp):
+    from stefanproblem_b200 import cutcelldg as cc
+    t = cc.reference_tables(order, numqp)
+    x, w = gauss_1d(numqp)
+    assert np.allclose(t["qpoints"], x, atol=1e-15) and np.allclose(t["qweights"], w, atol=1e-15)
+    n = order + 1
+    M, K, C = np.zeros((n, n)), np.zeros((n, n)), np.zeros((n, n))
+    for xq, wq in zip(x, w):
+        N, dN = lagrange_1d(order, xq)
+        M += wq * np.outer(N, N)
+        K += wq * np.outer(dN, dN)
+        C += wq * np.outer(dN, N)
+    assert np.allclose(t["mass"], M, atol=1e-15)
+    assert np.allclose(t["stiff"], K, atol=1e-14)
+    assert np.allclose(t["adv"], C, atol=1e-15)
+    assert np.allclose(t["dleft"], lagrange_1d(order, -1.0)[1], atol=1e-14)
+    assert np.allclose(t["dright"], lagrange_1d(order, 1.0)[1], atol=1e-14)
+
+
+@pytest.fixture(scope="module")
+def hostcheck():
+    hc = os.path.join(ROOT, "tests", "hostcheck")
+    so = os.path.join(hc, "_hostcheck.so")
+    subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-o", so, os.path.join(hc, "hostcheck.cpp")], check=True)
+    return ctypes.CDLL(so)
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
+@pytest.mark.parametrize("variant", ["current", "legacy_boundary"])
+@pytest.mark.parametrize("terms", [255, 1 | 2 | 4 | 32 | 64, 1, 2 | 4, 32 | 64, 8 | 16 | 128])
+def test_cell_row_functions_match_oracle(hostcheck, order, variant, terms):
+    """The __host__ __device__ row functions the kernels call, looped over the cells on
+    the CPU, reproduce `A_oracle @ x` for every combination of assemble passes."""
+    nx, ny = 7, 6
+    mesh = UniformMesh2D([0, 0], [1.0, 0.8], [nx, ny], (order + 1) ** 2)
+    mesh.cellsign[:] = fast.circle_phase(mesh, (0.5, 0.4), 0.3)
+    k1, k2, pen, lam = 1.0, 2.0, 1e3 * nx, 1.5
+    A = ip_matrix_terms(mesh, order, k1, k2, pen, lam, variant, terms)
+    x = np.random.default_rng(0).uniform(-1, 1, A.shape[0])
+    y = np.zeros_like(x)
+    ph = np.ascontiguousarray(mesh.cellsign, dtype=np.int8)
+    jx, jy = mesh.jacobian()
+    dp = ctypes.POINTER(ctypes.c_double)
+    d = ctypes.c_double
+    rc = hostcheck.hostcheck_ipdg_apply(order, nx, ny, order + 1, d(jx), d(jy), d(k1), d(k2), d(pen), d(lam),
+                                        {"current": 0, "legacy_boundary": 1}[variant], terms,
+                                        ph.ctypes.data_as(ctypes.POINTER(ctypes.c_int8)),
+                                        x.ctypes.data_as(dp), y.ctypes.data_as(dp))
+    assert rc == 0
+    yr = A @ x
+    scale = np.linalg.norm(yr) if np.linalg.norm(yr) > 0 else 1.0
+    assert np.linalg.norm(y - yr) / scale < 1e-13
+
+
+def ip_matrix_terms(mesh, order, k1, k2, pen, lam, variant, terms):
+    """Oracle matrix for a subset of the reference's assemble passes (literal loops)."""
+    from oracle import ip
+    from oracle.basis import LagrangeTensorProductBasis
+    from oracle.mesh import CellQuadratures, FaceQuadratures, SystemMatrix, sparse_operator
+    basis = LagrangeTensorProductBasis(2, order)
+    cq, fq = CellQuadratures(order + 1), FaceQuadratures(order + 1)
+    A = SystemMatrix()
+    if terms & 1:
+        ip.assemble_gradient_operator(A, basis, cq, k1, k2, mesh)
+    if terms & 2:
+        ip.assemble_interelement_flux_operator(A, basis, fq, k1, k2, mesh)
+    if terms & 4:
+        ip.assemble_interelement_penalty_operator(A, basis, fq, pen, mesh)
+    if terms & 8:
+        ip.assemble_aligned_interface_flux_operator(A, basis, fq, k1, k2, mesh)
+    if terms & 16:
+        ip.assemble_aligned_interface_penalty_operator(A, basis, fq, pen, mesh)
+    if terms & 32:
+        ip.assemble_boundary_flux_operator(A, basis, fq, k1, k2, mesh, variant)
+    if terms & 64:
+        ip.assemble_boundary_penalty_operator(A, basis, fq, pen, mesh)
+    if terms & 128:
+        ip.assemble_aligned_robin_operator(A, basis, fq, lam, mesh)
+    return sparse_operator(A, mesh.number_of_nodes())
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_c_oracle_matches_numpy_oracle(order):
+    from oracle.cport import CIPOracle
+    nx, ny = 9, 7
+    mesh = UniformMesh2D([0, 0], [1.0, 0.7], [nx, ny], (order + 1) ** 2)
+    mesh.cellsign[:] = fast.circle_phase(mesh, (0.5, 0.35), 0.3)
+    for variant in ("current", "legacy_boundary"):
+        A = fast.ip_matrix(mesh, order, order + 1, 1.0, 2.0, 1e3 * nx, 1.5, variant)
+        C = CIPOracle(order, order + 1, nx, ny, mesh.h[0], mesh.h[1], 1.0, 2.0, 1e3 * nx, 1.5, variant,
+                      255, mesh.cellsign)
+        assert abs(A - C.csr()).max() < 1e-14 * abs(A).max()
+        x = np.random.default_rng(0).uniform(-1, 1, A.shape[0])
+        for threads in (1, 0):
+            assert np.linalg.norm(C.spmv(x, nthreads=threads) - A @ x) < 1e-13 * np.linalg.norm(A @ x)
