@@ -102,7 +102,7 @@ int64_t stefan_ipdg_ndofs(const stefan_ipdg* h);
 /* y = A x (replaces sparse_operator(sysmatrix, mesh, 1) * x).  x_lo / x_hi: the
  * neighbouring slabs' adjacent cell columns (ny*NF doubles each; local or peer
  * device memory), required iff the handle has phase_lo / phase_hi.
- * algo 0 = production kernel (order 1: register-streaming LDG.256 kernel; orders 2, 3:
+ * algo 0 = production kernel (order 1: TMA bulk-copy streaming kernel; orders 2, 3:
  * cp.async streaming kernel), 1 = simple one-thread-per-cell kernel, 2 = cp.async
  * streaming kernel for every order. */
 int stefan_ipdg_apply(stefan_ipdg* h, const double* x, double* y, const double* x_lo,
@@ -112,6 +112,35 @@ int stefan_ipdg_apply(stefan_ipdg* h, const double* x, double* y, const double* 
  * copies, kernels and device->host copies of `nslabs` column slabs are pipelined
  * on three streams inside the call (nslabs <= 0: default).  Synchronous. */
 int stefan_ipdg_apply_host(stefan_ipdg* h, const double* x_host, double* y_host, int32_t nslabs);
+
+/* --------------------------------------------------------------------- FD
+ * Two-phase 1-D finite-difference Laplace operator of module FiniteDifference
+ * (StefanFD/finite-difference.jl).  phaseid: host int8[numnodes] as produced by
+ * phase_id (:92-103; 1 where phi < 0, else 2).  stefan_fd_create classifies every
+ * row once, following assemble_laplace_operator! (:71-85) -- central / backward /
+ * forward second derivative, or no row -- and, if `dirichlet`, the identity rows
+ * of assemble_dirichlet_boundary_condition! (:87-90).  Where the reference would
+ * index phaseid out of bounds (interface within 3 nodes of an end) it returns
+ * STEFAN_OUT_OF_RANGE.  phase_lo / phase_hi: host int8[3], the neighbouring slab's
+ * three adjacent nodes when the line is partitioned across GPUs (else NULL). */
+typedef struct stefan_fd stefan_fd;
+int stefan_fd_create(int64_t numnodes, double stepsize, const int8_t* phaseid, int32_t dirichlet,
+                     const int8_t* phase_lo, const int8_t* phase_hi, stefan_fd** out);
+int stefan_fd_destroy(stefan_fd* h);
+/* assemble_interface_continuity!(matrix, r, s, nodeid) (:111-116); nodeid 0-based. */
+int stefan_fd_add_interface_continuity(stefan_fd* h, double r, double s, int64_t nodeid);
+/* y = K u (replaces sparse_operator(matrix, ndofs) * u, :105-109).  u_lo / u_hi: the
+ * neighbouring slabs' 3 adjacent nodes (device), iff phase_lo / phase_hi were given. */
+int stefan_fd_apply(stefan_fd* h, const double* u, double* y, const double* u_lo,
+                    const double* u_hi, void* stream);
+/* Fused explicit heat step (no reference implementation; defined in oracle/timeloop.py):
+ * unew = u + dt * kappa(phase) * (K u) on the Laplace rows, unew = u on all other rows. */
+int stefan_fd_step(stefan_fd* h, const double* u, double* unew, const double* u_lo,
+                   const double* u_hi, double dt, double kappa1, double kappa2, void* stream);
+/* The COO triplets the reference appends (0-based, ordered by row), on the device. */
+int64_t stefan_fd_nnz(stefan_fd* h);
+int stefan_fd_assemble_coo(stefan_fd* h, int64_t* rows, int64_t* cols, double* vals,
+                           int64_t capacity, int64_t* nnz_out, void* stream);
 
 #ifdef __cplusplus
 }

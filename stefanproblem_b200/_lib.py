@@ -42,6 +42,15 @@ _SIGNATURES = {
                                           ctypes.POINTER(ctypes.c_void_p)]),
     "stefan_ipdg_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "stefan_ipdg_ndofs": (ctypes.c_int64, [ctypes.c_void_p]),
+    "stefan_fd_create": (ctypes.c_int, [ctypes.c_int64, ctypes.c_double, c_int8_p, ctypes.c_int32, c_int8_p,
+                                        c_int8_p, ctypes.POINTER(ctypes.c_void_p)]),
+    "stefan_fd_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "stefan_fd_add_interface_continuity": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, ctypes.c_double,
+                                                          ctypes.c_int64]),
+    "stefan_fd_apply": (ctypes.c_int, [ctypes.c_void_p] * 6),
+    "stefan_fd_step": (ctypes.c_int, [ctypes.c_void_p] * 5 + [ctypes.c_double] * 3 + [ctypes.c_void_p]),
+    "stefan_fd_nnz": (ctypes.c_int64, [ctypes.c_void_p]),
+    "stefan_fd_assemble_coo": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int64, c_int64_p, ctypes.c_void_p]),
     "stefan_ipdg_apply_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                               ctypes.c_int32]),
     "stefan_ipdg_apply": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,

@@ -88,6 +88,8 @@ struct ApplyArgs {
   int nx, ny;
   int nseg;  // x segments (stream kernels)
   int cbeg, cend;  // columns to produce (a sub-range when the host path pipelines slabs)
+  const int32_t* fix;  // cells the stream kernels leave to their tail (see fixup_tail)
+  int nfix;
 };
 
 __device__ __forceinline__ int phase_at(const int8_t* __restrict__ ph, int ny, int i, int j) {
@@ -129,38 +131,38 @@ ipdg_apply_simple(const __grid_constant__ IpTab<P> tab, const ApplyArgs a) {
   }
 }
 
-// Cells the stream kernel does not (or not correctly) produce: boundary cells, cells
-// next to the other phase, and every cell of a (strip, column) that mixes phases.
-// One thread per listed cell, general tables, neighbours straight from global memory.
+// Cells the streaming loops do not produce (they skip the store): boundary cells,
+// cells next to the other phase, and every cell of a (strip, column) that mixes
+// phases or has such a column next to it.  They are disjoint from what the loops
+// write, so each CTA simply works through its share of the list after its strips:
+// one thread per cell, general tables, neighbours straight from global memory.
 template <int P>
-__global__ void __launch_bounds__(128)
-ipdg_apply_fixup(const __grid_constant__ IpTab<P> tab, const ApplyArgs a,
-                 const int32_t* __restrict__ cells, int ncell) {
+__device__ __forceinline__ void fixup_tail(const IpTab<P>& tab, const ApplyArgs& a) {
   constexpr int NF = (P + 1) * (P + 1);
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= ncell) return;
-  const int64_t cell = cells[t];
-  const int i = (int)(cell / a.ny), j = (int)(cell % a.ny);
-  const int s = phase_at(a.phase, a.ny, i, j);
-  const int sL = phase_at(a.phase, a.ny, i - 1, j), sR = phase_at(a.phase, a.ny, i + 1, j);
-  const int sD = phase_at(a.phase, a.ny, i, j - 1), sU = phase_at(a.phase, a.ny, i, j + 1);
-  double X[NF], XL[NF], XR[NF], XD[NF], XU[NF], out[NF];
-  const double* xc = a.x + cell * NF;
-  const double* pl = (i > 0) ? xc - (size_t)a.ny * NF : a.x_lo + (size_t)j * NF;
-  const double* pr = (i < a.nx - 1) ? xc + (size_t)a.ny * NF : a.x_hi + (size_t)j * NF;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < a.nfix; t += gridDim.x * blockDim.x) {
+    const int64_t cell = a.fix[t];
+    const int i = (int)(cell / a.ny), j = (int)(cell % a.ny);
+    const int s = phase_at(a.phase, a.ny, i, j);
+    const int sL = phase_at(a.phase, a.ny, i - 1, j), sR = phase_at(a.phase, a.ny, i + 1, j);
+    const int sD = phase_at(a.phase, a.ny, i, j - 1), sU = phase_at(a.phase, a.ny, i, j + 1);
+    double X[NF], XL[NF], XR[NF], XD[NF], XU[NF], out[NF];
+    const double* xc = a.x + cell * NF;
+    const double* pl = (i > 0) ? xc - (size_t)a.ny * NF : a.x_lo + (size_t)j * NF;
+    const double* pr = (i < a.nx - 1) ? xc + (size_t)a.ny * NF : a.x_hi + (size_t)j * NF;
 #pragma unroll
-  for (int k = 0; k < NF; ++k) {
-    X[k] = xc[k];
-    XL[k] = sL ? pl[k] : 0.0;
-    XR[k] = sR ? pr[k] : 0.0;
-    XD[k] = sD ? xc[k - NF] : 0.0;
-    XU[k] = sU ? xc[k + NF] : 0.0;
+    for (int k = 0; k < NF; ++k) {
+      X[k] = xc[k];
+      XL[k] = sL ? pl[k] : 0.0;
+      XR[k] = sR ? pr[k] : 0.0;
+      XD[k] = sD ? xc[k - NF] : 0.0;
+      XU[k] = sU ? xc[k + NF] : 0.0;
+    }
+    ip_cell_rows<P>(tab, s == 1 ? 0 : 1, ip_face_type(s, sL), ip_face_type(s, sR),
+                    ip_face_type(s, sD), ip_face_type(s, sU), X, XL, XR, XD, XU, out);
+    double* yc = a.y + cell * NF;
+#pragma unroll
+    for (int k = 0; k < NF; ++k) yc[k] = out[k];
   }
-  ip_cell_rows<P>(tab, s == 1 ? 0 : 1, ip_face_type(s, sL), ip_face_type(s, sR),
-                  ip_face_type(s, sD), ip_face_type(s, sU), X, XL, XR, XD, XU, out);
-  double* yc = a.y + cell * NF;
-#pragma unroll
-  for (int k = 0; k < NF; ++k) yc[k] = out[k];
 }
 
 // --------------------------------------------------------------------------
@@ -230,15 +232,14 @@ ipdg_apply_stream(const __grid_constant__ IpTab<P> tab, const ApplyArgs a) {
   const int group = blockIdx.x % ngroups;
   const int seg = blockIdx.x / ngroups;
   const int strip = group * C::WARPS + warp;
-  if (strip >= nstrips) return;
   const int c0 = a.cbeg + (int)((int64_t)(a.cend - a.cbeg) * seg / a.nseg);
   const int c1 = a.cbeg + (int)((int64_t)(a.cend - a.cbeg) * (seg + 1) / a.nseg);
-  if (c0 >= c1) return;
-
+  if (strip < nstrips && c0 < c1) {
   char* ring = smem + (size_t)warp * NST * STAGE_BYTES;
   const int j0 = strip * kStripCells;  // first output cell of the strip
   const int j = j0 - 1 + lane;         // this lane's cell
   const bool outlane = lane >= 1 && lane <= kStripCells && j < a.ny;
+  const int jhi_out = min(j0 + kStripCells, a.ny);  // one past the strip's top output cell
   const int jlo = max(j0 - 1, 0), jhi = min(j0 + kStripCells + 1, a.ny);
   const int nchunk = (jhi - jlo) * NPIECE;  // 16- or 8-byte pieces in one column chunk
   const int rel0 = jlo - (j0 - 1);          // first staged cell, in lane units
@@ -346,7 +347,8 @@ ipdg_apply_stream(const __grid_constant__ IpTab<P> tab, const ApplyArgs a) {
 
     double XR[NF], XD[NF], XU[NF], out[NF];
     const char* stc = ring + slot_c * STAGE_BYTES;
-    const unsigned f0 = *reinterpret_cast<const uint8_t*>(stc + FLAG_OFF + (c & 15));
+    const unsigned fb = *reinterpret_cast<const uint8_t*>(stc + FLAG_OFF + (c & 15));
+    const unsigned f0 = fb & 3u;  // phase code; bits 2 / 3: do not store the bottom / top cell
     load_cell<P>(ring + slot_r * STAGE_BYTES + own, XR);
     load_cell<P>(stc + dn, XD);
     load_cell<P>(stc + up, XU);
@@ -375,7 +377,8 @@ ipdg_apply_stream(const __grid_constant__ IpTab<P> tab, const ApplyArgs a) {
 #ifdef EXP_NOSTORE
     if (outlane && f0 != 0 && out[0] == 1.2345e300) store_cell<P>(yp, out);
 #else
-    if (outlane && f0 != 0) store_cell<P>(yp, out);
+    if (outlane && f0 != 0 && !((fb & 4u) && lane == 1) && !((fb & 8u) && j == jhi_out - 1))
+      store_cell<P>(yp, out);
 #endif
     yp += (size_t)a.ny * NF;
 #pragma unroll
@@ -387,140 +390,8 @@ ipdg_apply_stream(const __grid_constant__ IpTab<P> tab, const ApplyArgs a) {
     __syncwarp();  // everyone is done with column c's slot before it is refilled
   }
   cp_async_wait<0>();
-}
-
-// --------------------------------------------------------------------------
-// order-1 register-streaming kernel (production path for P = 1)
-// --------------------------------------------------------------------------
-// Same decomposition as the cp.async kernel (one warp = a strip of 30 cells + 1 halo
-// cell each side, marching along x), but each lane loads its own cell -- 32
-// contiguous bytes -- with one LDG.256 straight into registers, kP1R - 3 columns
-// ahead, so a warp-wide load is one 1 KiB contiguous request made of whole 32-byte
-// sectors.  (Measured on the cp.async version: LDGSTS does not merge the two
-// 16-byte halves of a sector that two lanes ask for, so L2 served every sector
-// twice and the kernel sat at 70% of the copy bandwidth with the arithmetic removed.)
-// The x-neighbours are the previous / next register columns; the y-neighbours are
-// exchanged through a 3-deep per-warp shared-memory buffer (one __syncwarp per
-// column).  Which coefficient set a column uses comes from a per-strip run list
-// built at handle creation, so the loop carries no flag loads at all.
-constexpr int kP1R = 6;       // register columns: c-1, c, c+1 and three in flight
-constexpr int kP1Warps = 8;
-constexpr int kP1Stride = 48; // bytes per cell in the exchange buffer (conflict-free LDS.128)
-
-__device__ __forceinline__ void ld_global_v4(const double* p, double* v) {
-  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];"
-               : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3])
-               : "l"(p));
-}
-
-__global__ void __launch_bounds__(kP1Warps * 32, 2)
-ipdg_apply_p1(const __grid_constant__ IpTab<1> tab, const ApplyArgs a,
-              const int2* __restrict__ runs, const int* __restrict__ run_ofs) {
-  __shared__ __align__(16) char xbuf[kP1Warps][3][32 * kP1Stride];
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const int nstrips = (a.ny + kStripCells - 1) / kStripCells;
-  const int ngroups = (nstrips + kP1Warps - 1) / kP1Warps;
-  const int group = blockIdx.x % ngroups;
-  const int seg = blockIdx.x / ngroups;
-  const int strip = group * kP1Warps + warp;
-  if (strip >= nstrips) return;
-  const int c0 = a.cbeg + (int)((int64_t)(a.cend - a.cbeg) * seg / a.nseg);
-  const int c1 = a.cbeg + (int)((int64_t)(a.cend - a.cbeg) * (seg + 1) / a.nseg);
-  if (c0 >= c1) return;
-
-  const int j0 = strip * kStripCells;
-  const int j = j0 - 1 + lane;
-  const bool valid = j >= 0 && j < a.ny;
-  const bool outlane = lane >= 1 && lane <= kStripCells && j < a.ny;
-  const size_t colstride = (size_t)a.ny * 4;  // doubles per column
-  char* const mybuf = &xbuf[warp][0][0];
-  const int own = lane * kP1Stride;
-  const int dn = max(lane - 1, 0) * kP1Stride;
-  const int up = min(lane + 1, 31) * kP1Stride;
-
-  auto load_col = [&](int c, double* v) {
-    // column c of this lane's cell; zeros where there is no such cell
-    const double* p = nullptr;
-    if (c >= 0 && c < a.nx)
-      p = a.x + (size_t)c * colstride;
-    else if (c == -1)
-      p = a.x_lo;
-    else if (c == a.nx)
-      p = a.x_hi;
-    if (valid && p != nullptr && c <= c1) {
-      ld_global_v4(p + (size_t)j * 4, v);
-    } else {
-      v[0] = v[1] = v[2] = v[3] = 0.0;
-    }
-  };
-
-  // run list of this strip: (end column, phase code or 0) with increasing end
-  const int2* rp = runs + run_ofs[strip];
-  int2 cur = rp[0];
-  while (cur.x <= c0) cur = *++rp;
-  int2 nxt = rp[1];  // the list ends with a sentinel run, so rp[1] always exists
-  P1Coef coef;
-  p1_load_coef(tab, cur.y == 2 ? 1 : 0, coef);
-
-  double A[kP1R][4];
-#pragma unroll
-  for (int k = 0; k < kP1R; ++k) load_col(c0 - 1 + k, A[k]);
-  // column c0 goes to exchange buffer 0 (buffers are indexed by (c - c0) mod 3)
-  *reinterpret_cast<double2*>(mybuf + own) = make_double2(A[1][0], A[1][1]);
-  *reinterpret_cast<double2*>(mybuf + own + 16) = make_double2(A[1][2], A[1][3]);
-
-  const double* pn = a.x + (size_t)(c0 + kP1R - 1) * colstride + (size_t)j * 4;  // column c + R - 1
-  double* yp = a.y + (size_t)c0 * colstride + (size_t)j * 4;
-  const int cplain = min(c1, a.nx - 1) - (kP1R - 1);  // last c whose prefetch column is an ordinary one
-
-  for (int cb = c0; cb < c1; cb += kP1R) {
-#pragma unroll
-    for (int k = 0; k < kP1R; ++k) {
-      const int c = cb + k;
-      if (c < c1) {
-        double* XL = A[k];
-        double* X = A[(k + 1) % kP1R];
-        double* XR = A[(k + 2) % kP1R];
-        // publish column c+1 for the next step, then read the y-neighbours of column c
-        char* bnext = mybuf + ((k + 1) % 3) * (32 * kP1Stride);
-        const char* bcur = mybuf + (k % 3) * (32 * kP1Stride);
-        *reinterpret_cast<double2*>(bnext + own) = make_double2(XR[0], XR[1]);
-        *reinterpret_cast<double2*>(bnext + own + 16) = make_double2(XR[2], XR[3]);
-        __syncwarp();
-        double XD[4], XU[4], out[4];
-        {
-          const double2 d0 = *reinterpret_cast<const double2*>(bcur + dn);
-          const double2 d1 = *reinterpret_cast<const double2*>(bcur + dn + 16);
-          const double2 u0 = *reinterpret_cast<const double2*>(bcur + up);
-          const double2 u1 = *reinterpret_cast<const double2*>(bcur + up + 16);
-          XD[0] = d0.x; XD[1] = d0.y; XD[2] = d1.x; XD[3] = d1.y;
-          XU[0] = u0.x; XU[1] = u0.y; XU[2] = u1.x; XU[3] = u1.y;
-        }
-        if (c >= cur.x) {  // rare: next run of this strip
-          cur = nxt;
-          nxt = *(++rp + 1);
-          if (cur.y != 0) p1_load_coef(tab, cur.y == 2 ? 1 : 0, coef);
-        }
-        if (cur.y != 0) {
-          p1_uniform_rows(coef, X, XL, XR, XD, XU, out);
-          if (outlane) st_global_v4(yp, out[0], out[1], out[2], out[3]);
-        }
-        yp += colstride;
-        // column c-1 is dead: reuse its registers for column c + R - 1
-        if (c <= cplain) {
-          if (valid) {
-            ld_global_v4(pn, XL);
-          } else {
-            XL[0] = XL[1] = XL[2] = XL[3] = 0.0;
-          }
-        } else {
-          load_col(c + kP1R - 1, XL);
-        }
-        pn += colstride;
-      }
-    }
   }
+  fixup_tail<P>(tab, a);
 }
 
 // --------------------------------------------------------------------------
@@ -596,12 +467,11 @@ ipdg_apply_p1_tma(const __grid_constant__ IpTab<1> tab, const ApplyArgs a,
   const int group = blockIdx.x % ngroups;
   const int seg = blockIdx.x / ngroups;
   const int strip = group * kTmaWarps + warp;
-  if (strip >= nstrips) return;
   const int c0 = a.cbeg + (int)((int64_t)(a.cend - a.cbeg) * seg / a.nseg);
   const int c1 = a.cbeg + (int)((int64_t)(a.cend - a.cbeg) * (seg + 1) / a.nseg);
-  if (c0 >= c1) return;
-
+  if (strip < nstrips && c0 < c1) {
   const int j0 = strip * kStripCells;
+  const int jhi_out = min(j0 + kStripCells, a.ny);  // one past the strip's top output cell
   const int j = j0 - 1 + lane;
   const bool outlane = lane >= 1 && lane <= kStripCells && j < a.ny;
   const int jlo = max(j0 - 1, 0), jhi = min(j0 + kStripCells + 1, a.ny);
@@ -659,13 +529,17 @@ ipdg_apply_p1_tma(const __grid_constant__ IpTab<1> tab, const ApplyArgs a,
     v[0] = t0.x; v[1] = t0.y; v[2] = t1.x; v[3] = t1.y;
   };
 
-  // run list of this strip: (end column, phase code or 0) with increasing end
+  // run list of this strip: (end column, flag) with increasing end; flag & 3 = phase
+  // code all cells are treated as (0: none, the column is left to the tail), bit 2 /
+  // bit 3 = the bottom / top cell of the strip is an exception and is not stored
   const int2* rp = runs + run_ofs[strip];
   int2 cur = rp[0];
   while (cur.x <= c0) cur = *++rp;
   int2 nxt = rp[1];  // the list ends with sentinel runs, so rp[1] always exists
   P1Coef coef;
-  p1_load_coef(tab, cur.y == 2 ? 1 : 0, coef);
+  p1_load_coef(tab, (cur.y & 3) == 2 ? 1 : 0, coef);
+  bool store = outlane && (cur.y & 3) != 0 && !((cur.y & 4) && lane == 1) &&
+               !((cur.y & 8) && j == jhi_out - 1);
 
   // prologue: columns c0-1 .. c0+NST-2 into slots 0 .. NST-1
 #pragma unroll
@@ -697,11 +571,13 @@ ipdg_apply_p1_tma(const __grid_constant__ IpTab<1> tab, const ApplyArgs a,
     if (c >= cur.x) {  // rare: next run of this strip
       cur = nxt;
       nxt = *(++rp + 1);
-      if (cur.y != 0) p1_load_coef(tab, cur.y == 2 ? 1 : 0, coef);
+      if ((cur.y & 3) != 0) p1_load_coef(tab, (cur.y & 3) == 2 ? 1 : 0, coef);
+      store = outlane && (cur.y & 3) != 0 && !((cur.y & 4) && lane == 1) &&
+              !((cur.y & 8) && j == jhi_out - 1);
     }
-    if (cur.y != 0) {
+    if ((cur.y & 3) != 0) {
       p1_uniform_rows(coef, X, XL, XR, XD, XU, out);
-      if (outlane) st_global_v4(yp, out[0], out[1], out[2], out[3]);
+      if (store) st_global_v4(yp, out[0], out[1], out[2], out[3]);
     }
     yp += colstride;
 #pragma unroll
@@ -712,6 +588,8 @@ ipdg_apply_p1_tma(const __grid_constant__ IpTab<1> tab, const ApplyArgs a,
     slot_c = slot_r;
     __syncwarp();  // everyone is done with column c's slot before it is refilled
   }
+  }
+  fixup_tail<1>(tab, a);
 }
 
 // --------------------------------------------------------------------------
@@ -731,6 +609,9 @@ static int launch_apply(const IpdgHandle* h, const ApplyArgs& args0, int algo, c
     STEFAN_CUDA(cudaGetLastError());
     return ST_OK;
   }
+  // exception cells of the produced columns (the list is sorted by column)
+  args.fix = h->fix_dev + h->fix_col_ofs[args.cbeg];
+  args.nfix = h->fix_col_ofs[args.cend] - h->fix_col_ofs[args.cbeg];
   // stream kernels: CTA = (group of adjacent strips, x segment); one wave of
   // 2 CTAs per SM, segments no shorter than 16 columns
   const int nstrips = (h->ny + kStripCells - 1) / kStripCells;
@@ -741,11 +622,7 @@ static int launch_apply(const IpdgHandle* h, const ApplyArgs& args0, int algo, c
     args.nseg = nseg;
     return ngroups * nseg;
   };
-  if (P == 1 && algo == 3) {
-    const int grid = grid_for(kP1Warps, 2);
-    if constexpr (P == 1)
-      ipdg_apply_p1<<<grid, kP1Warps * 32, 0, st>>>(tab, args, h->runs_dev, h->run_ofs_dev);
-  } else if (P == 1 && algo == 0) {
+  if (P == 1 && algo == 0) {
     const int grid = grid_for(kTmaWarps, 2);
     if constexpr (P == 1) {
       const size_t smem = (size_t)kTmaWarps * kTmaWarpSmem;
@@ -768,10 +645,6 @@ static int launch_apply(const IpdgHandle* h, const ApplyArgs& args0, int algo, c
     }
     ipdg_apply_stream<P><<<grid, C::WARPS * 32, smem, st>>>(tab, args);
   }
-  // exception cells of the produced columns (the list is sorted by column)
-  const int f0 = h->fix_col_ofs[args.cbeg], f1 = h->fix_col_ofs[args.cend];
-  if (f1 > f0)
-    ipdg_apply_fixup<P><<<(f1 - f0 + 127) / 128, 128, 0, st>>>(tab, args, h->fix_dev + f0, f1 - f0);
   STEFAN_CUDA(cudaGetLastError());
   return ST_OK;
 }
@@ -861,14 +734,22 @@ int stefan_ipdg_create(const stefan_ipdg_params* p, const int8_t* phase, const i
       for (int sidx = 0; sidx < nstrips; ++sidx) {
         const int ja = sidx * kStripCells, jb = std::min(ja + kStripCells, (int)p->ny);
         const int8_t ref = col[ja];
+        // the loop produces the strip in this column iff all its cells, and all their
+        // x-neighbours, have one phase; the bottom / top cell additionally need the
+        // cell below / above them to have it (else: skip bit, and the cell is listed)
         bool same = true;
-        for (int j = ja; j < jb && same; ++j) same = col[j] == ref;
-        flags[(size_t)sidx * nxpad + i] = same ? (uint8_t)ref : 0;
-        for (int j = ja; j < jb; ++j) {
-          const int8_t s = col[j];
-          const bool plain = col[j - 1] == s && col[j + 1] == s && col[j - ld] == s && col[j + ld] == s;
-          if (!same || !plain) fix.push_back((int32_t)((int64_t)i * p->ny + j));
+        for (int j = ja; j < jb && same; ++j)
+          same = col[j] == ref && col[j - ld] == ref && col[j + ld] == ref;
+        uint8_t flag = 0;
+        if (same) {
+          flag = (uint8_t)ref;
+          if (col[ja - 1] != ref) flag |= 4;
+          if (col[jb] != ref) flag |= 8;
         }
+        flags[(size_t)sidx * nxpad + i] = flag;
+        for (int j = ja; j < jb; ++j)
+          if (!same || ((flag & 4) && j == ja) || ((flag & 8) && j == jb - 1))
+            fix.push_back((int32_t)((int64_t)i * p->ny + j));
       }
     }
   }
@@ -950,9 +831,8 @@ int stefan_ipdg_apply(stefan_ipdg* hv, const double* x, double* y, const double*
   STEFAN_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
                  (reinterpret_cast<uintptr_t>(x_lo) & 15) == 0 && (reinterpret_cast<uintptr_t>(x_hi) & 15) == 0,
                  "stefan_ipdg_apply: device pointers must be 16-byte aligned");
-  STEFAN_REQUIRE(algo >= 0 && algo <= 3, "stefan_ipdg_apply: unknown algo %d", algo);
-  STEFAN_REQUIRE(algo != 3 || h->order == 1, "stefan_ipdg_apply: algo 3 exists for order 1 only");
-  ApplyArgs a{x, x_lo, x_hi, y, h->phase_dev, h->flags_dev, (h->nx + 15) / 16 * 16, h->nx, h->ny, 1, 0, h->nx};
+  STEFAN_REQUIRE(algo >= 0 && algo <= 2, "stefan_ipdg_apply: unknown algo %d", algo);
+  ApplyArgs a{x, x_lo, x_hi, y, h->phase_dev, h->flags_dev, (h->nx + 15) / 16 * 16, h->nx, h->ny, 1, 0, h->nx, nullptr, 0};
   return dispatch_apply(h, a, algo, static_cast<cudaStream_t>(stream));
 }
 
@@ -988,7 +868,7 @@ int stefan_ipdg_apply_host(stefan_ipdg* hv, const double* x_host, double* y_host
       const int k = s - 1;
       STEFAN_CUDA(cudaStreamWaitEvent(h->hs[1], h->hev[std::min(s, nslabs - 1)], 0));
       ApplyArgs a{h->xh_dev, nullptr, nullptr, h->yh_dev, h->phase_dev, h->flags_dev, (h->nx + 15) / 16 * 16,
-                  h->nx, h->ny, 1, slab_begin(k), slab_begin(k + 1)};
+                  h->nx, h->ny, 1, slab_begin(k), slab_begin(k + 1), nullptr, 0};
       int rc = dispatch_apply(h, a, 0, h->hs[1]);
       if (rc) return rc;
       STEFAN_CUDA(cudaEventRecord(h->hev[32 + k], h->hs[1]));
