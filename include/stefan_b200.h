@@ -113,6 +113,33 @@ int stefan_ipdg_apply(stefan_ipdg* h, const double* x, double* y, const double* 
  * on three streams inside the call (nslabs <= 0: default).  Synchronous. */
 int stefan_ipdg_apply_host(stefan_ipdg* h, const double* x_host, double* y_host, int32_t nslabs);
 
+/* -------------------------------------------------------------------- LDG
+ * Local-DG mixed form, 3 dofs per node (T, q_x, q_y), of
+ * assemble_LDG_linear_system! (StefanDG/LocalDG/LDG_assembly.jl:1-91) on an uncut
+ * uniform mesh: divergence + mass + gradient cell operators, inter-element scalar and
+ * vector fluxes with the directional switch V0, boundary vector flux.  As in the
+ * reference, V0 itself is used as `beta` in the vector flux (LDG_assembly.jl:44-53) and
+ * faces between unlike phases are not coupled.  interfacepenalty has no effect on an
+ * uncut mesh and is not part of the parameters. */
+typedef struct {
+  int32_t nx, ny;
+  double hx, hy;
+  int32_t order, numqp;
+  double k1, k2;
+  double interiorpenalty, negboundarypenalty, posboundarypenalty;
+  double V0x, V0y;
+} stefan_ldg_params;
+
+typedef struct stefan_ldg stefan_ldg;
+int stefan_ldg_create(const stefan_ldg_params* params, const int8_t* phase, const int8_t* phase_lo,
+                      const int8_t* phase_hi, stefan_ldg** out);
+int stefan_ldg_destroy(stefan_ldg* h);
+int64_t stefan_ldg_ndofs(const stefan_ldg* h);
+/* y = A x (replaces sparse_operator(sysmatrix, mesh, 3) * x); dof = 3*node + component.
+ * x_lo / x_hi: the neighbouring slabs' adjacent cell columns (3*ny*NF doubles each). */
+int stefan_ldg_apply(stefan_ldg* h, const double* x, double* y, const double* x_lo,
+                     const double* x_hi, void* stream);
+
 /* --------------------------------------------------------------------- FD
  * Two-phase 1-D finite-difference Laplace operator of module FiniteDifference
  * (StefanFD/finite-difference.jl).  phaseid: host int8[numnodes] as produced by

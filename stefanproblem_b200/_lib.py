@@ -34,6 +34,19 @@ class IpdgParams(ctypes.Structure):
     ]
 
 
+class LdgParams(ctypes.Structure):
+    """`stefan_ldg_params` (include/stefan_b200.h)."""
+    _fields_ = [
+        ("nx", ctypes.c_int32), ("ny", ctypes.c_int32),
+        ("hx", ctypes.c_double), ("hy", ctypes.c_double),
+        ("order", ctypes.c_int32), ("numqp", ctypes.c_int32),
+        ("k1", ctypes.c_double), ("k2", ctypes.c_double),
+        ("interiorpenalty", ctypes.c_double), ("negboundarypenalty", ctypes.c_double),
+        ("posboundarypenalty", ctypes.c_double),
+        ("V0x", ctypes.c_double), ("V0y", ctypes.c_double),
+    ]
+
+
 _SIGNATURES = {
     "stefan_last_error": (ctypes.c_char_p, []),
     "stefan_version": (ctypes.c_int, []),
@@ -42,6 +55,11 @@ _SIGNATURES = {
                                           ctypes.POINTER(ctypes.c_void_p)]),
     "stefan_ipdg_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "stefan_ipdg_ndofs": (ctypes.c_int64, [ctypes.c_void_p]),
+    "stefan_ldg_create": (ctypes.c_int, [ctypes.POINTER(LdgParams), c_int8_p, c_int8_p, c_int8_p,
+                                         ctypes.POINTER(ctypes.c_void_p)]),
+    "stefan_ldg_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "stefan_ldg_ndofs": (ctypes.c_int64, [ctypes.c_void_p]),
+    "stefan_ldg_apply": (ctypes.c_int, [ctypes.c_void_p] * 6),
     "stefan_fd_create": (ctypes.c_int, [ctypes.c_int64, ctypes.c_double, c_int8_p, ctypes.c_int32, c_int8_p,
                                         c_int8_p, ctypes.POINTER(ctypes.c_void_p)]),
     "stefan_fd_destroy": (ctypes.c_int, [ctypes.c_void_p]),

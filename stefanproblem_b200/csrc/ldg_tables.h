@@ -1,0 +1,167 @@
+// Local DG (3 dofs per node: T, q_x, q_y) on an uncut uniform Cartesian mesh: tables
+// and the per-cell row function the matrix-free kernels apply.
+//
+// Reference passes (StefanDG/LocalDG/), all Kronecker products on a uniform mesh:
+//   divergence_operator   LDG_div_operator.jl:1-11      rows q_d, cols T:  int d_d(phi_a) phi_b
+//   mass_matrix           LDG_mass_operator.jl:1-25     rows q_d, cols q_d: int phi_a phi_b
+//   gradient_operator     LDG_gradient_operator.jl:1-11 rows T, cols q_d:  k int d_d(phi_a) phi_b
+//   scalar flux           LDG_scalar_flux_operator.jl:25-107   rows q_d of the cell itself:
+//        n_d e [(-1/2 - bp) tr T_K + (-1/2 + bp) tr T_N],  bp = 1/2 sign(V0 . n)
+//   vector flux           LDG_vector_flux_operator.jl:47-154   rows T of the cell itself:
+//        n_d e k [(-1/2 + bn) tr q_d,K + (-1/2 - bn) tr q_d,N] + alpha e (tr T_K - tr T_N),
+//        bn = n . V0   (the raw unit vector: LDG_assembly.jl:44-53 passes V0 as `beta`)
+//   boundary vector flux  LDG_vector_flux_operator.jl:391-439
+//        e [-k n_d tr q_d,K + alpha_b tr T_K],  alpha_b = (V0 . n < 0) ? negpen : pospen
+// Every cell assembles its own rows for every face with a same-phase neighbour
+// (LDG_scalar_flux_operator.jl:159); faces between unlike phases get nothing.
+// With M = sum_q w N N', C = sum_q w N' N' (1-D, reference cell):
+//   y_qx = jy (I (x) M) [ jx (M (x) I) q_x + (Cx (x) I) T ]      Cx = C + face terms along x
+//   y_qy = jx (M (x) I) [ jy (I (x) M) q_y + (I (x) Cy) T ]
+//   y_T  = jy (I (x) M) Gx(q_x, T) + jx (M (x) I) Gy(q_y, T),   G = k C q + face terms
+#pragma once
+#include "ipdg_tables.h"
+
+namespace stefan {
+
+struct LdgPhys {
+  double k1, k2;
+  double interiorpenalty, negboundarypenalty, posboundarypenalty;
+  double V0x, V0y;
+};
+
+template <int P>
+struct LdgTab {
+  static constexpr int N1 = P + 1;
+  double Mx[N1 * N1], My[N1 * N1];  // jx Mh, jy Mh
+  double C[N1 * N1];                // sum_q w N'_a N_b
+  double kk[2];                     // conductivity per phase index
+  // face coefficients [axis][side 0 = low / 1 = high][face type]
+  double sqK[2][2][T_NTYPES], sqN[2][2][T_NTYPES];      // q-rows <- tr T (own / neighbour)
+  double tqK[2][2][2][T_NTYPES], tqN[2][2][2][T_NTYPES];  // [phase] T-rows <- tr q_d
+  double tpK[2][2][T_NTYPES], tpN[2][2][T_NTYPES];      // T-rows <- tr T (penalty)
+};
+
+inline double sign0(double v) { return v > 0 ? 1.0 : (v < 0 ? -1.0 : 0.0); }
+
+template <int P>
+int build_ldg_tables(const RefElem1D& r, double jx, double jy, const LdgPhys& ph, LdgTab<P>* t) {
+  constexpr int N1 = P + 1;
+  if (r.order != P) return 1;
+  std::memset(t, 0, sizeof(*t));
+  for (int a = 0; a < N1; ++a)
+    if (r.NL[a] != (a == 0 ? 1.0 : 0.0) || r.NR[a] != (a == P ? 1.0 : 0.0)) return 2;
+  for (int a = 0; a < N1; ++a)
+    for (int b = 0; b < N1; ++b) {
+      t->Mx[a * N1 + b] = jx * r.M[a][b];
+      t->My[a * N1 + b] = jy * r.M[a][b];
+      t->C[a * N1 + b] = r.C[a][b];
+    }
+  t->kk[0] = ph.k1;
+  t->kk[1] = ph.k2;
+  const double V0[2] = {ph.V0x, ph.V0y};
+  for (int ax = 0; ax < 2; ++ax)
+    for (int side = 0; side < 2; ++side) {
+      const double n = side == 0 ? -1.0 : 1.0;
+      const double v0n = V0[ax] * n;
+      const double bp = 0.5 * sign0(v0n);  // edge_switch, LDG_utilities.jl:1-4
+      const double bn = v0n;               // posnormals' * beta with beta = V0
+      const double alpha_b = v0n < 0 ? ph.negboundarypenalty : ph.posboundarypenalty;
+      t->sqK[ax][side][T_SAME] = n * (-0.5 - bp);
+      t->sqN[ax][side][T_SAME] = n * (-0.5 + bp);
+      t->tpK[ax][side][T_SAME] = ph.interiorpenalty;
+      t->tpN[ax][side][T_SAME] = -ph.interiorpenalty;
+      t->tpK[ax][side][T_BDRY] = alpha_b;
+      for (int s = 0; s < 2; ++s) {
+        const double k = t->kk[s];
+        t->tqK[s][ax][side][T_SAME] = n * k * (-0.5 + bn);
+        t->tqN[s][ax][side][T_SAME] = n * k * (-0.5 - bn);
+        t->tqK[s][ax][side][T_BDRY] = -k * n;
+      }
+    }
+  return 0;
+}
+
+// Rows of one cell.  U* hold the 3 NF dofs of a cell interleaved per node (T, q_x,
+// q_y); of the neighbours only the face nodes' T and normal q component are read.
+template <int P>
+#if defined(__CUDACC__)
+__host__ __device__ __forceinline__
+#else
+inline
+#endif
+void ldg_cell_rows(const LdgTab<P>& tab, int s, int tL, int tR, int tD, int tU,
+                   const double* __restrict__ U, const double* __restrict__ UL,
+                   const double* __restrict__ UR, const double* __restrict__ UD,
+                   const double* __restrict__ UU, double* __restrict__ out) {
+  constexpr int N1 = P + 1;
+  constexpr int NF = N1 * N1;
+  const double k = tab.kk[s];
+  double aqx[NF], aqy[NF], gx[NF], gy[NF];
+#define T_(W, ix, iy) W[3 * ((ix)*N1 + (iy)) + 0]
+#define QX_(W, ix, iy) W[3 * ((ix)*N1 + (iy)) + 1]
+#define QY_(W, ix, iy) W[3 * ((ix)*N1 + (iy)) + 2]
+#pragma unroll
+  for (int ix = 0; ix < N1; ++ix) {
+#pragma unroll
+    for (int iy = 0; iy < N1; ++iy) {
+      double cqx = 0.0, g_x = 0.0, mqx = 0.0, cqy = 0.0, g_y = 0.0, mqy = 0.0;
+#pragma unroll
+      for (int b = 0; b < N1; ++b) {
+        cqx += tab.C[ix * N1 + b] * T_(U, b, iy);
+        g_x += tab.C[ix * N1 + b] * QX_(U, b, iy);
+        mqx += tab.Mx[ix * N1 + b] * QX_(U, b, iy);
+        cqy += tab.C[iy * N1 + b] * T_(U, ix, b);
+        g_y += tab.C[iy * N1 + b] * QY_(U, ix, b);
+        mqy += tab.My[iy * N1 + b] * QY_(U, ix, b);
+      }
+      g_x *= k;
+      g_y *= k;
+      if (ix == 0) {
+        cqx += tab.sqK[0][0][tL] * T_(U, 0, iy) + tab.sqN[0][0][tL] * T_(UL, P, iy);
+        g_x += tab.tqK[s][0][0][tL] * QX_(U, 0, iy) + tab.tqN[s][0][0][tL] * QX_(UL, P, iy) +
+               tab.tpK[0][0][tL] * T_(U, 0, iy) + tab.tpN[0][0][tL] * T_(UL, P, iy);
+      }
+      if (ix == P) {
+        cqx += tab.sqK[0][1][tR] * T_(U, P, iy) + tab.sqN[0][1][tR] * T_(UR, 0, iy);
+        g_x += tab.tqK[s][0][1][tR] * QX_(U, P, iy) + tab.tqN[s][0][1][tR] * QX_(UR, 0, iy) +
+               tab.tpK[0][1][tR] * T_(U, P, iy) + tab.tpN[0][1][tR] * T_(UR, 0, iy);
+      }
+      if (iy == 0) {
+        cqy += tab.sqK[1][0][tD] * T_(U, ix, 0) + tab.sqN[1][0][tD] * T_(UD, ix, P);
+        g_y += tab.tqK[s][1][0][tD] * QY_(U, ix, 0) + tab.tqN[s][1][0][tD] * QY_(UD, ix, P) +
+               tab.tpK[1][0][tD] * T_(U, ix, 0) + tab.tpN[1][0][tD] * T_(UD, ix, P);
+      }
+      if (iy == P) {
+        cqy += tab.sqK[1][1][tU] * T_(U, ix, P) + tab.sqN[1][1][tU] * T_(UU, ix, 0);
+        g_y += tab.tqK[s][1][1][tU] * QY_(U, ix, P) + tab.tqN[s][1][1][tU] * QY_(UU, ix, 0) +
+               tab.tpK[1][1][tU] * T_(U, ix, P) + tab.tpN[1][1][tU] * T_(UU, ix, 0);
+      }
+      aqx[ix * N1 + iy] = cqx + mqx;
+      aqy[ix * N1 + iy] = cqy + mqy;
+      gx[ix * N1 + iy] = g_x;
+      gy[ix * N1 + iy] = g_y;
+    }
+  }
+#pragma unroll
+  for (int ix = 0; ix < N1; ++ix) {
+#pragma unroll
+    for (int iy = 0; iy < N1; ++iy) {
+      double oT = 0.0, oqx = 0.0, oqy = 0.0;
+#pragma unroll
+      for (int c = 0; c < N1; ++c) {
+        oqx += tab.My[iy * N1 + c] * aqx[ix * N1 + c];
+        oT += tab.My[iy * N1 + c] * gx[ix * N1 + c];
+        oqy += tab.Mx[ix * N1 + c] * aqy[c * N1 + iy];
+        oT += tab.Mx[ix * N1 + c] * gy[c * N1 + iy];
+      }
+      T_(out, ix, iy) = oT;
+      QX_(out, ix, iy) = oqx;
+      QY_(out, ix, iy) = oqy;
+    }
+  }
+#undef T_
+#undef QX_
+#undef QY_
+}
+
+}  // namespace stefan

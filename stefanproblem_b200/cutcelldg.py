@@ -209,6 +209,49 @@ class IPOperator:
         return self.apply(x)
 
 
+class LDGOperator:
+    """Matrix-free `sparse_operator(sysmatrix, mesh, 3)` of a local-DG system on one GPU."""
+
+    def __init__(self, mesh, order, numqp, k1, k2, interiorpenalty, negboundarypenalty,
+                 posboundarypenalty, V0, phase_lo=None, phase_hi=None):
+        import torch
+        if not torch.cuda.is_available():
+            raise _lib.StefanError(-1, "no CUDA device: stefanproblem_b200 has no CPU fallback")
+        self.mesh, self.order, self.nf = mesh, order, (order + 1) ** 2
+        self.params = _lib.LdgParams(
+            nx=mesh.nx, ny=mesh.ny, hx=float(mesh.h[0]), hy=float(mesh.h[1]), order=order, numqp=numqp,
+            k1=float(k1), k2=float(k2), interiorpenalty=float(interiorpenalty),
+            negboundarypenalty=float(negboundarypenalty), posboundarypenalty=float(posboundarypenalty),
+            V0x=float(V0[0]), V0y=float(V0[1]))
+        i8 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.int8)  # noqa: E731
+        self._plo, self._phi = i8(phase_lo), i8(phase_hi)
+        p8 = lambda a: None if a is None else a.ctypes.data_as(_lib.c_int8_p)  # noqa: E731
+        h = ctypes.c_void_p()
+        _lib.check(_lib.lib().stefan_ldg_create(ctypes.byref(self.params), p8(mesh.phase), p8(self._plo),
+                                                p8(self._phi), ctypes.byref(h)))
+        self._h = h
+        self.ndofs = int(_lib.lib().stefan_ldg_ndofs(h))
+        self.shape = (self.ndofs, self.ndofs)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            _lib.lib().stefan_ldg_destroy(h)
+            self._h = None
+
+    def apply(self, x, out=None, x_lo=None, x_hi=None, stream=None):
+        import torch
+        assert x.is_cuda and x.dtype == torch.float64 and x.is_contiguous() and x.numel() == self.ndofs
+        if out is None:
+            out = torch.empty_like(x)
+        _lib.check(_lib.lib().stefan_ldg_apply(self._h, _ptr(x), _ptr(out), _ptr(x_lo), _ptr(x_hi),
+                                               _stream_ptr(stream)))
+        return out
+
+    def __matmul__(self, x):
+        return self.apply(x)
+
+
 def sparse_operator(sysmatrix, mesh, dofspernode):
     """`CutCellDG.sparse_operator(sysmatrix, mesh, dofspernode)`: device operator."""
     if sysmatrix.kind == "ip":
@@ -217,4 +260,13 @@ def sparse_operator(sysmatrix, mesh, dofspernode):
         s = sysmatrix.spec
         return IPOperator(mesh, s["order"], s["numqp"], s["k1"], s["k2"], s.get("penalty", 0.0),
                           s.get("lam", 0.0), 0.0, s.get("variant", "current"), s["terms"])
+    if sysmatrix.kind == "ldg":
+        if dofspernode != 3:
+            raise ValueError("local DG has 3 dofs per node")
+        s = sysmatrix.spec
+        if s.get("terms", 0) != 63:
+            raise ValueError("the LDG kernel applies the whole of assemble_LDG_linear_system!; "
+                             f"passes recorded: {s.get('terms', 0):#x}")
+        return LDGOperator(mesh, s["order"], s["numqp"], s["k1"], s["k2"], s["interiorpenalty"],
+                           s["negboundarypenalty"], s["posboundarypenalty"], s["V0"])
     raise ValueError(f"nothing assembled (kind={sysmatrix.kind})")
