@@ -108,6 +108,26 @@ int64_t stefan_ipdg_ndofs(const stefan_ipdg* h);
 int stefan_ipdg_apply(stefan_ipdg* h, const double* x, double* y, const double* x_lo,
                       const double* x_hi, int32_t algo, void* stream);
 
+/* Right-hand side of assemble_interior_penalty_rhs! (IP_assembly.jl:82-115) plus, when
+ * the handle has the ROBIN term, assemble_robin_source! (face-level form) -- on the
+ * device.  The reference calls its sourceterm(x) / boundaryfunc(x) closures at the
+ * physical quadrature points; here the caller passes their samples:
+ *   f_qp  [ncells][numqp*numqp]  at the cell quadrature points (x-point outer, y-point
+ *         inner; for two phases the host samples f1 / f2 by cell phase), or NULL
+ *   g_qp  [bottom nx*numqp][right ny*numqp][top nx*numqp][left ny*numqp] at the face
+ *         quadrature points of the boundary faces, or NULL
+ *   b     [ndofs] is overwritten. */
+int stefan_ipdg_rhs(stefan_ipdg* h, const double* f_qp, const double* g_qp, double* b, void* stream);
+
+/* The COO seam: the (row, col, val) triplets of the assembled operator, one dense
+ * NF x NF block per cell and per existing neighbour (duplicates already summed, explicit
+ * zeros kept), column-major inside a block like vec(M).  Feed them to
+ * sparse(rows, cols, vals, N, N) exactly as CutCellDG.sparse_operator does.
+ * index_base 1 gives Julia indices. */
+int64_t stefan_ipdg_coo_size(const stefan_ipdg* h);
+int stefan_ipdg_assemble_coo(stefan_ipdg* h, int64_t* rows, int64_t* cols, double* vals,
+                             int64_t capacity, int32_t index_base, int64_t* nnz_out, void* stream);
+
 /* Same operation with HOST buffers (pinned memory recommended): host->device
  * copies, kernels and device->host copies of `nslabs` column slabs are pipelined
  * on three streams inside the call (nslabs <= 0: default).  Synchronous. */

@@ -1,0 +1,247 @@
+// Interior-penalty DG: right-hand-side assembly and COO emission (the reference's
+// `SystemRHS` / `SystemMatrix` seam) on the device.
+//
+//   stefan_ipdg_rhs           assemble_interior_penalty_rhs!   IP_assembly.jl:82-115
+//                             = assemble_boundary_source!      IP_source_term.jl:201-258
+//                               (R1 - R2 at :145-156; legacy variant: R1 only)
+//                             + assemble_source! / assemble_two_phase_source!
+//                                                              IP_source_term.jl:19-91
+//                             + assemble_robin_source!         IP_robin_interface_source.jl
+//                               (face-level form, :12-25, on unlike-phase mesh faces)
+//   stefan_ipdg_assemble_coo  the triplets of assemble_interior_penalty_linear_system!
+//                             after `sparse()` has summed duplicates, block by block
+//
+// The reference evaluates its `sourceterm(x)` / `boundaryfunc(x)` closures at the
+// physical quadrature points inside the loops; callbacks cannot cross the C ABI, so
+// the host samples them once (same points, same order) and passes the samples.
+#include "../../include/stefan_b200.h"
+#include "common.cuh"
+#include "ipdg_handle.h"
+
+namespace stefan {
+
+struct RhsTab {
+  int n1, nq;
+  double Nq[kMaxQ][kMaxN1];  // N_a(x_q)
+  double w[kMaxQ];
+  double dNL[kMaxN1], dNR[kMaxN1];
+  double jx, jy, k1, k2, penalty, lamTm;  // lamTm = 0.5 lambda Tm if the Robin term is on
+  int flux_term;                           // 1: R1 - R2 (current), 0: R1 only (legacy)
+};
+
+__device__ __forceinline__ int aux_phase_at(const int8_t* __restrict__ ph, int ny, int i, int j) {
+  return ph[(size_t)(i + 1) * (ny + 2) + (j + 1)];
+}
+
+// one thread per cell; P is small, so plain loops over the tables
+__global__ void __launch_bounds__(128)
+ipdg_rhs_kernel(const __grid_constant__ RhsTab t, const int8_t* __restrict__ phase, int nx, int ny,
+                const double* __restrict__ f_qp, const double* __restrict__ g_qp,
+                double* __restrict__ b) {
+  const int64_t ncells = (int64_t)nx * ny;
+  const int n1 = t.n1, nq = t.nq, nf = n1 * n1;
+  // boundary samples: [bottom nx*nq][right ny*nq][top nx*nq][left ny*nq]
+  const double* g_bottom = g_qp;
+  const double* g_right = g_bottom + (size_t)nx * nq;
+  const double* g_top = g_right + (size_t)ny * nq;
+  const double* g_left = g_top + (size_t)nx * nq;
+  for (int64_t cell = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; cell < ncells;
+       cell += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(cell / ny), j = (int)(cell % ny);
+    const int s = aux_phase_at(phase, ny, i, j);
+    const double k = s == 1 ? t.k1 : t.k2;
+    double out[kMaxN1 * kMaxN1];
+    for (int a = 0; a < nf; ++a) out[a] = 0.0;
+    // volume: sum_q V f detjac w   (linear_form, IP_source_term.jl:97-107)
+    if (f_qp != nullptr) {
+      const double* f = f_qp + cell * (size_t)(nq * nq);
+      const double detjac = t.jx * t.jy;
+      for (int qx = 0; qx < nq; ++qx)
+        for (int qy = 0; qy < nq; ++qy) {
+          const double v = f[qx * nq + qy] * t.w[qx] * t.w[qy] * detjac;
+          for (int ix = 0; ix < n1; ++ix)
+            for (int iy = 0; iy < n1; ++iy) out[ix * n1 + iy] += t.Nq[qx][ix] * t.Nq[qy][iy] * v;
+        }
+    }
+    // faces: 0 bottom, 1 right, 2 top, 3 left
+    for (int face = 0; face < 4; ++face) {
+      const int sn = face == 0 ? aux_phase_at(phase, ny, i, j - 1)
+                     : face == 1 ? aux_phase_at(phase, ny, i + 1, j)
+                     : face == 2 ? aux_phase_at(phase, ny, i, j + 1)
+                                 : aux_phase_at(phase, ny, i - 1, j);
+      const bool xnormal = (face == 1 || face == 3);
+      const double jn = xnormal ? t.jx : t.jy, jt = xnormal ? t.jy : t.jx;
+      const bool high = (face == 1 || face == 2);
+      const int fnode = high ? n1 - 1 : 0;
+      if (sn == 0 && g_qp != nullptr) {
+        // boundary: pen sum V g sa w - k sum (G n) g sa w   (IP_source_term.jl:131-159)
+        const double* g = face == 0   ? g_bottom + (size_t)i * nq
+                          : face == 1 ? g_right + (size_t)j * nq
+                          : face == 2 ? g_top + (size_t)i * nq
+                                      : g_left + (size_t)j * nq;
+        for (int it = 0; it < n1; ++it) {
+          double m = 0.0;  // tangential moment of the data
+          for (int q = 0; q < nq; ++q) m += t.w[q] * t.Nq[q][it] * g[q];
+          m *= jt;
+          for (int in = 0; in < n1; ++in) {
+            const double gn = (high ? t.dNR[in] : -t.dNL[in]) / jn;  // outward normal derivative
+            double v = 0.0;
+            if (in == fnode) v += t.penalty * m;
+            if (t.flux_term) v -= k * gn * m;
+            const int a = xnormal ? in * n1 + it : it * n1 + in;
+            out[a] += v;
+          }
+        }
+      } else if (sn != 0 && sn != s && t.lamTm != 0.0) {
+        // Robin source on an unlike-phase face: 0.5 lambda Tm sum V sa w
+        for (int it = 0; it < n1; ++it) {
+          double m = 0.0;
+          for (int q = 0; q < nq; ++q) m += t.w[q] * t.Nq[q][it];
+          const int a = xnormal ? fnode * n1 + it : it * n1 + fnode;
+          out[a] += t.lamTm * jt * m;
+        }
+      }
+    }
+    double* bc = b + cell * nf;
+    for (int a = 0; a < nf; ++a) bc[a] = out[a];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// COO emission: block (cell, which) -> NF x NF triplets; which = 0 diag, 1 left,
+// 2 right, 3 down, 4 up.  Blocks are laid out cell by cell, existing neighbours only.
+template <int P>
+__global__ void __launch_bounds__(128)
+ipdg_coo_kernel(const __grid_constant__ IpTab<P> tab, const int8_t* __restrict__ phase, int nx, int ny,
+                int64_t index_base, int64_t* __restrict__ rows, int64_t* __restrict__ cols,
+                double* __restrict__ vals) {
+  constexpr int N1 = P + 1;
+  constexpr int NF = N1 * N1;
+  const int64_t nwork = (int64_t)nx * ny * 5;
+  for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < nwork;
+       w += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t cell = w / 5;
+    const int which = (int)(w % 5);
+    const int i = (int)(cell / ny), j = (int)(cell % ny);
+    const bool exists = which == 0 || (which == 1 && i > 0) || (which == 2 && i < nx - 1) ||
+                        (which == 3 && j > 0) || (which == 4 && j < ny - 1);
+    if (!exists) continue;
+    // blocks before this cell: closed form of the sum over earlier cells of (1 + #neighbours)
+    const int64_t per = 1 + (i > 0) + (i < nx - 1);
+    int64_t nb = (int64_t)i * (ny + 2 * (int64_t)(ny - 1)) +
+                 (int64_t)ny * ((i > 1 ? i - 1 : 0) + (i < nx - 1 ? i : nx - 1));
+    nb += (int64_t)j * per + (j > 1 ? j - 1 : 0) + (j < ny - 1 ? j : ny - 1);
+    int before = 0;  // blocks of this cell ahead of `which`
+    if (which > 0) before += 1;
+    if (which > 1) before += (i > 0);
+    if (which > 2) before += (i < nx - 1);
+    if (which > 3) before += (j > 0);
+    const int64_t o = (nb + before) * NF * NF;
+    const int s = aux_phase_at(phase, ny, i, j);
+    const int si = s == 1 ? 0 : 1;
+    const int tL = ip_face_type(s, aux_phase_at(phase, ny, i - 1, j));
+    const int tR = ip_face_type(s, aux_phase_at(phase, ny, i + 1, j));
+    const int tD = ip_face_type(s, aux_phase_at(phase, ny, i, j - 1));
+    const int tU = ip_face_type(s, aux_phase_at(phase, ny, i, j + 1));
+    const int64_t ncol = which == 0   ? cell
+                         : which == 1 ? cell - ny
+                         : which == 2 ? cell + ny
+                         : which == 3 ? cell - 1
+                                      : cell + 1;
+    for (int a = 0; a < NF; ++a) {
+      const int ix = a / N1, iy = a % N1;
+      for (int bb = 0; bb < NF; ++bb) {
+        const int bx = bb / N1, by = bb % N1;
+        double v;
+        if (which == 0) {
+          v = tab.My[iy * N1 + by] * tab.D[0][si][tL][tR][ix * N1 + bx] +
+              tab.Mx[ix * N1 + bx] * tab.D[1][si][tD][tU][iy * N1 + by];
+        } else if (which == 1) {
+          const double l = (ix == 0 ? tab.L0[0][si][tL][bx] : (bx == P ? tab.Lc[0][si][tL][ix] : 0.0));
+          v = tab.My[iy * N1 + by] * l;
+        } else if (which == 2) {
+          const double r = (ix == P ? tab.Rp[0][si][tR][bx] : (bx == 0 ? tab.Rc[0][si][tR][ix] : 0.0));
+          v = tab.My[iy * N1 + by] * r;
+        } else if (which == 3) {
+          const double l = (iy == 0 ? tab.L0[1][si][tD][by] : (by == P ? tab.Lc[1][si][tD][iy] : 0.0));
+          v = tab.Mx[ix * N1 + bx] * l;
+        } else {
+          const double r = (iy == P ? tab.Rp[1][si][tU][by] : (by == 0 ? tab.Rc[1][si][tU][iy] : 0.0));
+          v = tab.Mx[ix * N1 + bx] * r;
+        }
+        const int64_t e = o + (int64_t)bb * NF + a;  // column-major inside the block, like vec(M)
+        rows[e] = cell * NF + a + index_base;
+        cols[e] = ncol * NF + bb + index_base;
+        vals[e] = v;
+      }
+    }
+  }
+}
+
+}  // namespace stefan
+
+using namespace stefan;
+
+extern "C" {
+
+int stefan_ipdg_rhs(stefan_ipdg* hv, const double* f_qp, const double* g_qp, double* b, void* stream) {
+  IpdgHandle* h = reinterpret_cast<IpdgHandle*>(hv);
+  STEFAN_REQUIRE(h && b, "stefan_ipdg_rhs: null argument");
+  STEFAN_REQUIRE(!h->has_lo && !h->has_hi, "stefan_ipdg_rhs: slab handles are not supported yet");
+  RhsTab t;
+  std::memset(&t, 0, sizeof(t));
+  t.n1 = h->order + 1;
+  t.nq = h->numqp;
+  for (int q = 0; q < t.nq; ++q) {
+    t.w[q] = h->ref.qw[q];
+    for (int a = 0; a < t.n1; ++a) t.Nq[q][a] = h->ref.Nq[q][a];
+  }
+  for (int a = 0; a < t.n1; ++a) {
+    t.dNL[a] = h->ref.dNL[a];
+    t.dNR[a] = h->ref.dNR[a];
+  }
+  t.jx = 0.5 * h->hx;
+  t.jy = 0.5 * h->hy;
+  t.k1 = h->phys.k1;
+  t.k2 = h->phys.k2;
+  t.penalty = (h->phys.terms & IP_BOUNDARY_PENALTY) ? h->phys.penalty : 0.0;
+  t.lamTm = (h->phys.terms & IP_ROBIN) ? 0.5 * h->phys.lambda * h->Tm : 0.0;
+  t.flux_term = ((h->phys.terms & IP_BOUNDARY_FLUX) && h->phys.variant == IP_CURRENT) ? 1 : 0;
+  const int64_t ncells = (int64_t)h->nx * h->ny;
+  const int blocks = (int)std::min<int64_t>((ncells + 127) / 128, (int64_t)sm_count() * 32);
+  ipdg_rhs_kernel<<<blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(t, h->phase_dev, h->nx, h->ny, f_qp,
+                                                                          g_qp, b);
+  STEFAN_CUDA(cudaGetLastError());
+  return ST_OK;
+}
+
+int64_t stefan_ipdg_coo_size(const stefan_ipdg* hv) {
+  const IpdgHandle* h = reinterpret_cast<const IpdgHandle*>(hv);
+  if (!h) return -1;
+  const int64_t nx = h->nx, ny = h->ny, NF = (h->order + 1) * (h->order + 1);
+  return NF * NF * (nx * ny + 2 * (nx - 1) * ny + 2 * nx * (ny - 1));
+}
+
+int stefan_ipdg_assemble_coo(stefan_ipdg* hv, int64_t* rows, int64_t* cols, double* vals, int64_t capacity,
+                             int32_t index_base, int64_t* nnz_out, void* stream) {
+  IpdgHandle* h = reinterpret_cast<IpdgHandle*>(hv);
+  STEFAN_REQUIRE(h && rows && cols && vals && nnz_out, "stefan_ipdg_assemble_coo: null argument");
+  STEFAN_REQUIRE(!h->has_lo && !h->has_hi, "stefan_ipdg_assemble_coo: slab handles are not supported");
+  STEFAN_REQUIRE(index_base == 0 || index_base == 1, "stefan_ipdg_assemble_coo: index_base must be 0 or 1");
+  *nnz_out = stefan_ipdg_coo_size(hv);
+  if (*nnz_out > capacity)
+    return fail(ST_CAPACITY, "stefan_ipdg_assemble_coo: %lld triplets, capacity %lld", (long long)*nnz_out,
+                (long long)capacity);
+  const int64_t nwork = (int64_t)h->nx * h->ny * 5;
+  const int blocks = (int)std::min<int64_t>((nwork + 127) / 128, (int64_t)sm_count() * 32);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (h->order) {
+    case 1: ipdg_coo_kernel<1><<<blocks, 128, 0, st>>>(*static_cast<IpTab<1>*>(h->tab_host), h->phase_dev, h->nx, h->ny, index_base, rows, cols, vals); break;
+    case 2: ipdg_coo_kernel<2><<<blocks, 128, 0, st>>>(*static_cast<IpTab<2>*>(h->tab_host), h->phase_dev, h->nx, h->ny, index_base, rows, cols, vals); break;
+    case 3: ipdg_coo_kernel<3><<<blocks, 128, 0, st>>>(*static_cast<IpTab<3>*>(h->tab_host), h->phase_dev, h->nx, h->ny, index_base, rows, cols, vals); break;
+  }
+  STEFAN_CUDA(cudaGetLastError());
+  return ST_OK;
+}
+
+}  // extern "C"

@@ -136,9 +136,71 @@ class SystemMatrix:
 
 
 class SystemRHS:
+    """Records the rhs passes; `rhs_vector` samples the callbacks at the quadrature
+    points on the host (they are Julia / Python closures in the reference's call surface)
+    and runs the device kernel."""
+
     def __init__(self):
         self.kind = None
-        self.terms = []  # recorded rhs passes, evaluated by rhs_vector
+        self.spec = {}
+
+    def _merge(self, kind, **kw):
+        if self.kind is None:
+            self.kind = kind
+        elif self.kind != kind:
+            raise ValueError(f"SystemRHS already holds a {self.kind} right-hand side, not {kind}")
+        self.spec.update({k: v for k, v in kw.items() if v is not None})
+
+    def evaluate(self, mesh, dofspernode):
+        import torch
+        s = self.spec
+        if self.kind == "ip":
+            numqp = s["numqp"]
+            f_qp = g_qp = None
+            if "f1" in s:
+                x, y = cell_quadrature_points(mesh, numqp)
+                P = np.stack([x, y])
+                f = np.where((mesh.phase > 0)[:, None], s["f1"](P), s["f2"](P))
+                f_qp = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(f, x.shape), dtype=np.float64)).cuda()
+            if "g" in s:
+                x, y = boundary_quadrature_points(mesh, numqp)
+                g = np.broadcast_to(s["g"](np.stack([x, y])), x.shape)
+                g_qp = torch.from_numpy(np.ascontiguousarray(g, dtype=np.float64)).cuda()
+            terms = (32 | 64 if "g" in s else 0) | (128 if "lam" in s else 0)
+            op = IPOperator(mesh, s["order"], numqp, s.get("k1", 1.0), s.get("k2", 1.0), s.get("penalty", 0.0),
+                            s.get("lam", 0.0), s.get("Tm", 0.0), s.get("variant", "current"), terms or 1)
+            return op.rhs(f_qp, g_qp)
+        raise ValueError(f"unknown right-hand side kind {self.kind}")
+
+
+def cell_quadrature_points(mesh, numqp):
+    """Physical coordinates (x, y), each [ncells, numqp*numqp], of the cell quadrature
+    points in the order the kernels expect (x-point outer, y-point inner)."""
+    q = reference_tables(mesh.basis.order, numqp)["qpoints"]
+    i, j = np.divmod(np.arange(mesh.ncells), mesh.ny)
+    qx, qy = np.repeat(q, numqp), np.tile(q, numqp)
+    x = mesh.x0[0] + mesh.h[0] * (i[:, None] + 0.5 * (1.0 + qx[None, :]))
+    y = mesh.x0[1] + mesh.h[1] * (j[:, None] + 0.5 * (1.0 + qy[None, :]))
+    return x, y
+
+
+def boundary_quadrature_points(mesh, numqp):
+    """Physical coordinates of the boundary-face quadrature points, concatenated as
+    [bottom nx*numqp][right ny*numqp][top nx*numqp][left ny*numqp]."""
+    q = reference_tables(mesh.basis.order, numqp)["qpoints"]
+    xs = (mesh.x0[0] + mesh.h[0] * (np.arange(mesh.nx)[:, None] + 0.5 * (1.0 + q[None, :]))).ravel()
+    ys = (mesh.x0[1] + mesh.h[1] * (np.arange(mesh.ny)[:, None] + 0.5 * (1.0 + q[None, :]))).ravel()
+    x1, y1 = mesh.x0[0] + mesh.widths[0], mesh.x0[1] + mesh.widths[1]
+    x = np.concatenate([xs, np.full_like(ys, x1), xs, np.full_like(ys, mesh.x0[0])])
+    y = np.concatenate([np.full_like(xs, mesh.x0[1]), ys, np.full_like(xs, y1), ys])
+    return x, y
+
+
+def rhs_vector(sysrhs, mesh, dofspernode):
+    """`CutCellDG.rhs_vector(sysrhs, mesh, dofspernode)`: device vector."""
+    if sysrhs.kind is None:
+        raise ValueError("nothing assembled")
+    return sysrhs.evaluate(mesh, dofspernode)
 
 
 def _ptr(t):
@@ -192,6 +254,26 @@ class IPOperator:
         _lib.check(_lib.lib().stefan_ipdg_apply(self._h, _ptr(x), _ptr(out), _ptr(x_lo), _ptr(x_hi),
                                                 algo, _stream_ptr(stream)))
         return out
+
+    def rhs(self, f_qp=None, g_qp=None, out=None, stream=None):
+        """b of `assemble_interior_penalty_rhs!` (+ Robin source) from device samples."""
+        import torch
+        if out is None:
+            out = torch.empty(self.ndofs, dtype=torch.float64, device="cuda")
+        _lib.check(_lib.lib().stefan_ipdg_rhs(self._h, _ptr(f_qp), _ptr(g_qp), _ptr(out), _stream_ptr(stream)))
+        return out
+
+    def to_coo(self, index_base=0):
+        """(rows, cols, vals) device tensors of the assembled operator (the COO seam)."""
+        import torch
+        n = int(_lib.lib().stefan_ipdg_coo_size(self._h))
+        rows = torch.empty(n, dtype=torch.int64, device="cuda")
+        cols = torch.empty(n, dtype=torch.int64, device="cuda")
+        vals = torch.empty(n, dtype=torch.float64, device="cuda")
+        nnz = ctypes.c_int64()
+        _lib.check(_lib.lib().stefan_ipdg_assemble_coo(self._h, _ptr(rows), _ptr(cols), _ptr(vals), n,
+                                                       index_base, ctypes.byref(nnz), _stream_ptr()))
+        return rows, cols, vals
 
     def apply_host(self, x_host, out_host=None, nslabs=0):
         """y = A x for HOST tensors / arrays (pinned torch tensors are fastest);

