@@ -160,6 +160,40 @@ int64_t stefan_ldg_ndofs(const stefan_ldg* h);
 int stefan_ldg_apply(stefan_ldg* h, const double* x, double* y, const double* x_lo,
                      const double* x_hi, void* stream);
 
+/* ------------------------------------------------------------------- DG1D
+ * 1-D two-phase interior-penalty DG with a Robin interface on a DGMesh1D
+ * (StefanRobinIC/DG1D/dgmesh_1d.jl:1-51): nelmts1 uniform cells on [xL, interfacepoint]
+ * (label 1, k1), nelmts2 on [interfacepoint, xR] (label 2, k2).  `terms` = which passes
+ * were assembled: */
+enum {
+  STEFAN_DG1D_GRADIENT = 1,          /* assemble_gradient_operator!          assemble_gradient_operator.jl:25-48 */
+  STEFAN_DG1D_FLUX = 2,              /* assemble_flux_operator!              assemble_flux_operator.jl:93-120 */
+  STEFAN_DG1D_PENALTY = 4,           /* assemble_penalty_operator!           assemble_penalty_operator.jl:52-70 */
+  STEFAN_DG1D_ROBIN = 8,             /* assemble_interface_robin_operator!   assemble_interface_robin_operator.jl:46-69 */
+  STEFAN_DG1D_BOUNDARY_FLUX = 16,    /* assemble_boundary_flux_operator!     assemble_flux_operator.jl:122-173 */
+  STEFAN_DG1D_BOUNDARY_PENALTY = 32, /* assemble_boundary_penalty_operator!  assemble_penalty_operator.jl:72-102 */
+  STEFAN_DG1D_ALL_TERMS = 63
+};
+typedef struct {
+  int32_t nelmts1, nelmts2;
+  double xL, xR, interfacepoint;
+  int32_t order, numqp;
+  double k1, k2, penalty, lambda, Tm;
+  int32_t terms;
+} stefan_dg1d_params;
+typedef struct stefan_dg1d stefan_dg1d;
+int stefan_dg1d_create(const stefan_dg1d_params* params, stefan_dg1d** out);
+int stefan_dg1d_destroy(stefan_dg1d* h);
+int64_t stefan_dg1d_ndofs(const stefan_dg1d* h);
+/* y = A x (replaces DG1D.sparse_operator(sysmatrix, mesh, 1) * x, assembly.jl:1-5). */
+int stefan_dg1d_apply(stefan_dg1d* h, const double* x, double* y, void* stream);
+/* b = two-phase source (f_qp [ncells][numqp] samples of rhsfunc1 / rhsfunc2 at the cell
+ * quadrature points, or NULL) + Robin source (if the ROBIN term is set) + boundary rhs for
+ * Dirichlet values TL, TR (if with_boundary): assemble_source_term.jl:26-61,
+ * assemble_interface_robin_source.jl:19-43, assemble_boundary_conditions.jl:1-44. */
+int stefan_dg1d_rhs(stefan_dg1d* h, const double* f_qp, double TL, double TR, int32_t with_boundary,
+                    double* b, void* stream);
+
 /* --------------------------------------------------------------------- FD
  * Two-phase 1-D finite-difference Laplace operator of module FiniteDifference
  * (StefanFD/finite-difference.jl).  phaseid: host int8[numnodes] as produced by

@@ -47,6 +47,18 @@ class LdgParams(ctypes.Structure):
     ]
 
 
+class Dg1dParams(ctypes.Structure):
+    """`stefan_dg1d_params` (include/stefan_b200.h)."""
+    _fields_ = [
+        ("nelmts1", ctypes.c_int32), ("nelmts2", ctypes.c_int32),
+        ("xL", ctypes.c_double), ("xR", ctypes.c_double), ("interfacepoint", ctypes.c_double),
+        ("order", ctypes.c_int32), ("numqp", ctypes.c_int32),
+        ("k1", ctypes.c_double), ("k2", ctypes.c_double), ("penalty", ctypes.c_double),
+        ("lam", ctypes.c_double), ("Tm", ctypes.c_double),
+        ("terms", ctypes.c_int32),
+    ]
+
+
 _SIGNATURES = {
     "stefan_last_error": (ctypes.c_char_p, []),
     "stefan_version": (ctypes.c_int, []),
@@ -60,6 +72,12 @@ _SIGNATURES = {
     "stefan_ldg_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "stefan_ldg_ndofs": (ctypes.c_int64, [ctypes.c_void_p]),
     "stefan_ldg_apply": (ctypes.c_int, [ctypes.c_void_p] * 6),
+    "stefan_dg1d_create": (ctypes.c_int, [ctypes.POINTER(Dg1dParams), ctypes.POINTER(ctypes.c_void_p)]),
+    "stefan_dg1d_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "stefan_dg1d_ndofs": (ctypes.c_int64, [ctypes.c_void_p]),
+    "stefan_dg1d_apply": (ctypes.c_int, [ctypes.c_void_p] * 4),
+    "stefan_dg1d_rhs": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_double,
+                                       ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]),
     "stefan_fd_create": (ctypes.c_int, [ctypes.c_int64, ctypes.c_double, c_int8_p, ctypes.c_int32, c_int8_p,
                                         c_int8_p, ctypes.POINTER(ctypes.c_void_p)]),
     "stefan_fd_destroy": (ctypes.c_int, [ctypes.c_void_p]),
