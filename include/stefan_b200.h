@@ -108,6 +108,13 @@ int64_t stefan_ipdg_ndofs(const stefan_ipdg* h);
 int stefan_ipdg_apply(stefan_ipdg* h, const double* x, double* y, const double* x_lo,
                       const double* x_hi, int32_t algo, void* stream);
 
+/* Rows of the cell columns [col_begin, col_end) only.  Columns [1, nx-1) never read
+ * x_lo / x_hi, so a column-slab partition can run them while the halo exchange is in
+ * flight and finish with the two edge columns. */
+int stefan_ipdg_apply_columns(stefan_ipdg* h, const double* x, double* y, const double* x_lo,
+                              const double* x_hi, int32_t col_begin, int32_t col_end, int32_t algo,
+                              void* stream);
+
 /* Right-hand side of assemble_interior_penalty_rhs! (IP_assembly.jl:82-115) plus, when
  * the handle has the ROBIN term, assemble_robin_source! (face-level form) -- on the
  * device.  The reference calls its sourceterm(x) / boundaryfunc(x) closures at the

@@ -813,6 +813,25 @@ int stefan_ipdg_apply(stefan_ipdg* hv, const double* x, double* y, const double*
   return dispatch_apply(h, a, algo, static_cast<cudaStream_t>(stream));
 }
 
+// Rows of the cell columns [col_begin, col_end) only (same arguments otherwise).  Lets a
+// caller overlap the halo exchange of a column-slab partition with the interior:
+// columns [1, nx-1) do not read x_lo / x_hi.
+int stefan_ipdg_apply_columns(stefan_ipdg* hv, const double* x, double* y, const double* x_lo,
+                              const double* x_hi, int32_t col_begin, int32_t col_end, int32_t algo,
+                              void* stream) {
+  IpdgHandle* h = reinterpret_cast<IpdgHandle*>(hv);
+  STEFAN_REQUIRE(h && x && y && x != y, "stefan_ipdg_apply_columns: bad argument");
+  STEFAN_REQUIRE(0 <= col_begin && col_begin <= col_end && col_end <= h->nx,
+                 "stefan_ipdg_apply_columns: need 0 <= col_begin <= col_end <= nx");
+  STEFAN_REQUIRE(algo >= 0 && algo <= 2, "stefan_ipdg_apply_columns: unknown algo %d", algo);
+  const bool needs_lo = col_begin == 0, needs_hi = col_end == h->nx;
+  STEFAN_REQUIRE(!(needs_lo && h->has_lo && !x_lo) && !(needs_hi && h->has_hi && !x_hi),
+                 "stefan_ipdg_apply_columns: the halo column next to the requested range is missing");
+  ApplyArgs a{x, h->has_lo ? x_lo : nullptr, h->has_hi ? x_hi : nullptr, y, h->phase_dev, h->flags_dev,
+              (h->nx + 15) / 16 * 16, h->nx, h->ny, 1, col_begin, col_end, nullptr, 0};
+  return dispatch_apply(h, a, algo, static_cast<cudaStream_t>(stream));
+}
+
 // y = A x with HOST buffers (pinned memory recommended): the mesh is cut into
 // `nslabs` column slabs that are pipelined on three streams -- host->device copy
 // of slab s+1, kernel on slab s, device->host copy of slab s-1 run concurrently --

@@ -255,6 +255,12 @@ class IPOperator:
                                                 algo, _stream_ptr(stream)))
         return out
 
+    def apply_columns(self, x, out, col_begin, col_end, x_lo=None, x_hi=None, algo=STREAM, stream=None):
+        """Rows of the cell columns [col_begin, col_end) only (see stefan_ipdg_apply_columns)."""
+        _lib.check(_lib.lib().stefan_ipdg_apply_columns(self._h, _ptr(x), _ptr(out), _ptr(x_lo), _ptr(x_hi),
+                                                        col_begin, col_end, algo, _stream_ptr(stream)))
+        return out
+
     def rhs(self, f_qp=None, g_qp=None, out=None, stream=None):
         """b of `assemble_interior_penalty_rhs!` (+ Robin source) from device samples."""
         import torch

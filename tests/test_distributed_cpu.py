@@ -1,0 +1,71 @@
+"""world_size-2 (and 3) gloo tests of the slab partition and halo exchange (CPU)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, ncols, col, q):
+    sys.path.insert(0, ROOT)
+    from stefanproblem_b200.distributed import HaloExchange, allreduce_interface_sums, slab_range
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        b, e = slab_range(ncols, world, rank)
+        # global vector: entry (column c, k) = 1000 c + k
+        x = (1000.0 * torch.arange(b, e, dtype=torch.float64)[:, None]
+             + torch.arange(col, dtype=torch.float64)[None, :]).reshape(-1).contiguous()
+        halo = HaloExchange(col, rank, world, x)
+        lo, hi = halo.exchange(x)
+        ok = True
+        if rank > 0:
+            ok &= bool(torch.equal(lo, 1000.0 * (b - 1) + torch.arange(col, dtype=torch.float64)))
+        else:
+            ok &= lo is None
+        if rank < world - 1:
+            ok &= bool(torch.equal(hi, 1000.0 * e + torch.arange(col, dtype=torch.float64)))
+        else:
+            ok &= hi is None
+        s = allreduce_interface_sums(torch.tensor([float(rank + 1), 2.0, 0.0, 1.0], dtype=torch.float64))
+        ok &= bool(torch.equal(s, torch.tensor([world * (world + 1) / 2.0, 2.0 * world, 0.0, float(world)],
+                                               dtype=torch.float64)))
+        q.put((rank, b, e, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,ncols", [(2, 10), (2, 7), (3, 10)])
+def test_halo_exchange_and_partition(world, ncols):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + world * 10 + ncols
+    procs = [ctx.Process(target=_worker, args=(r, world, port, ncols, 6, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[3] for r in res)
+    # slabs tile [0, ncols) without gaps or overlap
+    assert res[0][1] == 0 and res[-1][2] == ncols
+    for a, b in zip(res[:-1], res[1:]):
+        assert a[2] == b[1]
+    sizes = [r[2] - r[1] for r in res]
+    assert max(sizes) - min(sizes) <= 1
+
+
+def test_slab_range_properties():
+    from stefanproblem_b200.distributed import slab_range
+    for n in (1, 5, 5000, 5001):
+        for w in (1, 2, 4, 8):
+            r = [slab_range(n, w, k) for k in range(w)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(r[:-1], r[1:]))

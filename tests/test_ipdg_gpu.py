@@ -115,3 +115,24 @@ def test_coo_seam_matches_oracle(cuda, order, nx, ny):
     assert r.min() == 1 and r.max() == A.shape[0]
     B = sp.coo_matrix((v, (r - 1, c - 1)), shape=A.shape).tocsr()
     assert abs(A - B).max() < 1e-13 * abs(A).max()
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_column_ranges_compose(cuda, order):
+    """apply_columns over a partition of the columns == one full apply (what the slab
+    overlap in stefanproblem_b200.distributed relies on), and apply_host == apply."""
+    import torch
+    from stefanproblem_b200 import cutcelldg as cc
+    nx, ny = 67, 95
+    basis = cc.LagrangeTensorProductBasis(2, order)
+    omesh = UniformMesh2D([0, 0], [1, 1], [nx, ny], basis.nf)
+    mesh = cc.UniformMesh([0, 0], [1, 1], [nx, ny], basis, phase=fast.circle_phase(omesh))
+    op = cc.IPOperator(mesh, order, order + 1, 1.0, 2.0, 1e3 * nx, 1.0, 0.5, "current", ALL)
+    x = torch.from_numpy(np.random.default_rng(5).uniform(-1, 1, op.ndofs)).cuda()
+    full = op.apply(x)
+    out = torch.full_like(x, float("nan"))
+    for b, e in ((1, nx - 1), (0, 1), (nx - 1, nx)):
+        op.apply_columns(x, out, b, e)
+    assert torch.equal(out, full)
+    yh = op.apply_host(x.cpu().pin_memory(), nslabs=5)
+    assert torch.equal(yh, full.cpu())
