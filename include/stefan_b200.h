@@ -135,6 +135,23 @@ int64_t stefan_ipdg_coo_size(const stefan_ipdg* h);
 int stefan_ipdg_assemble_coo(stefan_ipdg* h, int64_t* rows, int64_t* cols, double* vals,
                              int64_t capacity, int32_t index_base, int64_t* nnz_out, void* stream);
 
+/* Interface sums that drive the front velocity, over the mesh faces between a +1 cell
+ * (side 1) and a -1 cell (side 2), n = outward normal of side 1:
+ *   sums[0] = length, sums[1] = int lambda (Tm - {T}), sums[2] = int (k1 dn T1 - k2 dn T2),
+ *   sums[3] = int {T}.
+ * Face-integrated form of the point samples of IP_robin_interface_flux_velocity.jl:213-278
+ * (values / gradients as IP_postprocess.jl:1-52).  Faces are owned by their +1 cell, so the
+ * per-slab sums of a column partition add up with one 4-double all-reduce.  sums: device. */
+int stefan_ipdg_interface_sums(stefan_ipdg* h, const double* u, const double* u_lo, const double* u_hi,
+                               double* sums_dev, void* stream);
+
+/* u <- u + dt Minv (b - y) with y = A u from stefan_ipdg_apply and M the block-diagonal DG
+ * mass matrix: explicit Euler step of M du/dt = b - A u (b may be NULL).  No reference
+ * implementation exists (the reference only solves steady problems); defined in
+ * oracle/timeloop.py. */
+int stefan_ipdg_euler_update(stefan_ipdg* h, double* u, const double* y, const double* b, double dt,
+                             void* stream);
+
 /* Same operation with HOST buffers (pinned memory recommended): host->device
  * copies, kernels and device->host copies of `nslabs` column slabs are pipelined
  * on three streams inside the call (nslabs <= 0: default).  Synchronous. */

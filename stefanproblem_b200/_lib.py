@@ -88,6 +88,8 @@ _SIGNATURES = {
     "stefan_fd_nnz": (ctypes.c_int64, [ctypes.c_void_p]),
     "stefan_fd_assemble_coo": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int64, c_int64_p, ctypes.c_void_p]),
     "stefan_ipdg_apply_columns": (ctypes.c_int, [ctypes.c_void_p] * 5 + [ctypes.c_int32] * 3 + [ctypes.c_void_p]),
+    "stefan_ipdg_interface_sums": (ctypes.c_int, [ctypes.c_void_p] * 6),
+    "stefan_ipdg_euler_update": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_double, ctypes.c_void_p]),
     "stefan_ipdg_rhs": (ctypes.c_int, [ctypes.c_void_p] * 5),
     "stefan_ipdg_coo_size": (ctypes.c_int64, [ctypes.c_void_p]),
     "stefan_ipdg_assemble_coo": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int64, ctypes.c_int32,

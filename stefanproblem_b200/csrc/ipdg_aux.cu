@@ -245,3 +245,208 @@ int stefan_ipdg_assemble_coo(stefan_ipdg* hv, int64_t* rows, int64_t* cols, doub
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------
+// Interface sums that drive the front velocity, and the explicit time-step update.
+//
+// On every mesh face between a +1 cell (side 1, conductivity k1) and a -1 cell (side 2),
+// with n the outward normal of side 1, sa = face det-jacobian and the face Gauss rule:
+//   S[0] = sum sa w                              length of the interface
+//   S[1] = sum lambda (Tm - {T}) sa w            kinetic term  lambda (Tm - T_I)
+//   S[2] = sum (k1 dn T1 - k2 dn T2) sa w        jump of the normal heat flux
+//   S[3] = sum {T} sa w                          mean interface temperature x length
+// {T} = (T1 + T2)/2.  These are the face-integrated forms of what the reference samples
+// point-wise after the solve (IP_robin_interface_flux_velocity.jl:213-278: velocity
+// -lambda (Tm - T) per side, gvelocity = k2 dn T2 - k1 dn T1; values / gradients at
+// reference points as in IP_postprocess.jl:1-52).  Faces are owned by their +1 cell, so a
+// column-slab partition sums every face exactly once; the per-rank sums are added with a
+// 4-double all-reduce.  Deterministic: one partial per block, then a fixed-order sum.
+namespace stefan {
+
+struct IfaceTab {
+  int n1, nq;
+  double Nq[kMaxQ][kMaxN1], w[kMaxQ], dNL[kMaxN1], dNR[kMaxN1];
+  double jx, jy, k1, k2, lambda, Tm;
+};
+
+__global__ void __launch_bounds__(128)
+ipdg_interface_sums_kernel(const __grid_constant__ IfaceTab t, const int8_t* __restrict__ phase, int nx,
+                           int ny, const double* __restrict__ u, const double* __restrict__ u_lo,
+                           const double* __restrict__ u_hi, double* __restrict__ partial) {
+  const int n1 = t.n1, nq = t.nq, nf = n1 * n1, P = n1 - 1;
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+  const int64_t ncells = (int64_t)nx * ny;
+  for (int64_t cell = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; cell < ncells;
+       cell += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(cell / ny), j = (int)(cell % ny);
+    if (aux_phase_at(phase, ny, i, j) != 1) continue;  // faces are owned by the +1 cell
+    const double* u1 = u + cell * nf;
+    for (int face = 0; face < 4; ++face) {
+      const int di = face == 1 ? 1 : (face == 3 ? -1 : 0), dj = face == 2 ? 1 : (face == 0 ? -1 : 0);
+      if (aux_phase_at(phase, ny, i + di, j + dj) != 2) continue;
+      const double* u2 = (i + di < 0)    ? u_lo + (size_t)j * nf
+                         : (i + di >= nx) ? u_hi + (size_t)j * nf
+                                          : u + ((int64_t)(i + di) * ny + (j + dj)) * nf;
+      const bool xnormal = di != 0, high = (face == 1 || face == 2);
+      const double jn = xnormal ? t.jx : t.jy, sa = xnormal ? t.jy : t.jx;
+      // nodal traces and outward (side-1) normal derivatives along the face, per tangential node
+      for (int q = 0; q < nq; ++q) {
+        double T1 = 0, T2 = 0, d1 = 0, d2 = 0;
+        for (int it = 0; it < n1; ++it) {
+          const double Nt = t.Nq[q][it];
+          double a1 = 0, a2 = 0;  // normal derivative of side 1 / side 2 at tangential node it
+          for (int in = 0; in < n1; ++in) {
+            const int idx1 = xnormal ? in * n1 + it : it * n1 + in;
+            a1 += (high ? t.dNR[in] : -t.dNL[in]) / jn * u1[idx1];
+            a2 += (high ? t.dNL[in] : -t.dNR[in]) / jn * u2[idx1];  // neighbour: opposite end, same direction
+          }
+          const int f1 = high ? P : 0, f2 = high ? 0 : P;
+          T1 += Nt * u1[xnormal ? f1 * n1 + it : it * n1 + f1];
+          T2 += Nt * u2[xnormal ? f2 * n1 + it : it * n1 + f2];
+          d1 += Nt * a1;
+          d2 += Nt * a2;
+        }
+        const double wq = t.w[q] * sa, Tavg = 0.5 * (T1 + T2);
+        s0 += wq;
+        s1 += t.lambda * (t.Tm - Tavg) * wq;
+        s2 += (t.k1 * d1 - t.k2 * d2) * wq;
+        s3 += Tavg * wq;
+      }
+    }
+  }
+  // warp shuffle reduction, then one partial per block (fixed order -> deterministic)
+  __shared__ double red[4][4];
+  double v[4] = {s0, s1, s2, s3};
+  for (int k = 0; k < 4; ++k)
+    for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], off);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0)
+    for (int k = 0; k < 4; ++k) red[warp][k] = v[k];
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double s = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w][threadIdx.x];
+    partial[(size_t)blockIdx.x * 4 + threadIdx.x] = s;
+  }
+}
+
+__global__ void ipdg_interface_final_kernel(const double* __restrict__ partial, int nblocks,
+                                            double* __restrict__ out) {
+  if (threadIdx.x < 4) {
+    double s = 0;
+    for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * 4 + threadIdx.x];
+    out[threadIdx.x] = s;
+  }
+}
+
+// u <- u + dt * Minv (b - y), M = jx jy (Mh (x) Mh) the block-diagonal DG mass matrix:
+// the explicit Euler step of M du/dt = b - A u (no reference implementation; definition in
+// oracle/timeloop.py).  minv = inverse of the 1-D reference mass matrix.
+struct EulerTab {
+  int n1;
+  double minv[kMaxN1][kMaxN1];
+  double scale;  // dt / (jx jy)
+};
+
+__global__ void __launch_bounds__(128)
+ipdg_euler_kernel(const __grid_constant__ EulerTab t, int64_t ncells, const double* __restrict__ y,
+                  const double* __restrict__ b, double* __restrict__ u) {
+  const int n1 = t.n1, nf = n1 * n1;
+  for (int64_t cell = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; cell < ncells;
+       cell += (int64_t)gridDim.x * blockDim.x) {
+    double r[kMaxN1 * kMaxN1], tmp[kMaxN1 * kMaxN1];
+    for (int a = 0; a < nf; ++a) r[a] = (b ? b[cell * nf + a] : 0.0) - y[cell * nf + a];
+    for (int ix = 0; ix < n1; ++ix)
+      for (int iy = 0; iy < n1; ++iy) {
+        double v = 0;
+        for (int c = 0; c < n1; ++c) v += t.minv[iy][c] * r[ix * n1 + c];
+        tmp[ix * n1 + iy] = v;
+      }
+    for (int ix = 0; ix < n1; ++ix)
+      for (int iy = 0; iy < n1; ++iy) {
+        double v = 0;
+        for (int c = 0; c < n1; ++c) v += t.minv[ix][c] * tmp[c * n1 + iy];
+        u[cell * nf + ix * n1 + iy] += t.scale * v;
+      }
+  }
+}
+
+}  // namespace stefan
+
+extern "C" {
+
+int stefan_ipdg_interface_sums(stefan_ipdg* hv, const double* u, const double* u_lo, const double* u_hi,
+                               double* sums_dev, void* stream) {
+  IpdgHandle* h = reinterpret_cast<IpdgHandle*>(hv);
+  STEFAN_REQUIRE(h && u && sums_dev, "stefan_ipdg_interface_sums: null argument");
+  STEFAN_REQUIRE(h->has_lo == (u_lo != nullptr) && h->has_hi == (u_hi != nullptr),
+                 "stefan_ipdg_interface_sums: halo columns must be given exactly where the handle has halo phases");
+  IfaceTab t;
+  std::memset(&t, 0, sizeof(t));
+  t.n1 = h->order + 1;
+  t.nq = h->numqp;
+  for (int q = 0; q < t.nq; ++q) {
+    t.w[q] = h->ref.qw[q];
+    for (int a = 0; a < t.n1; ++a) t.Nq[q][a] = h->ref.Nq[q][a];
+  }
+  for (int a = 0; a < t.n1; ++a) {
+    t.dNL[a] = h->ref.dNL[a];
+    t.dNR[a] = h->ref.dNR[a];
+  }
+  t.jx = 0.5 * h->hx;
+  t.jy = 0.5 * h->hy;
+  t.k1 = h->phys.k1;
+  t.k2 = h->phys.k2;
+  t.lambda = h->phys.lambda;
+  t.Tm = h->Tm;
+  const int64_t ncells = (int64_t)h->nx * h->ny;
+  const int blocks = (int)std::min<int64_t>((ncells + 127) / 128, (int64_t)sm_count() * 8);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  double* partial = nullptr;
+  STEFAN_CUDA(cudaMallocAsync(&partial, (size_t)blocks * 4 * sizeof(double), st));
+  ipdg_interface_sums_kernel<<<blocks, 128, 0, st>>>(t, h->phase_dev, h->nx, h->ny, u, u_lo, u_hi, partial);
+  ipdg_interface_final_kernel<<<1, 32, 0, st>>>(partial, blocks, sums_dev);
+  STEFAN_CUDA(cudaGetLastError());
+  STEFAN_CUDA(cudaFreeAsync(partial, st));
+  return ST_OK;
+}
+
+int stefan_ipdg_euler_update(stefan_ipdg* hv, double* u, const double* y, const double* b, double dt,
+                             void* stream) {
+  IpdgHandle* h = reinterpret_cast<IpdgHandle*>(hv);
+  STEFAN_REQUIRE(h && u && y, "stefan_ipdg_euler_update: null argument");
+  EulerTab t;
+  std::memset(&t, 0, sizeof(t));
+  const int n = h->order + 1;
+  t.n1 = n;
+  // inverse of the (SPD, <= 4x4) reference mass matrix by Gauss-Jordan
+  double a[kMaxN1][2 * kMaxN1];
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) {
+      a[i][j] = h->ref.M[i][j];
+      a[i][n + j] = i == j ? 1.0 : 0.0;
+    }
+  for (int c = 0; c < n; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < n; ++r)
+      if (std::fabs(a[r][c]) > std::fabs(a[piv][c])) piv = r;
+    for (int j = 0; j < 2 * n; ++j) std::swap(a[c][j], a[piv][j]);
+    const double d = a[c][c];
+    for (int j = 0; j < 2 * n; ++j) a[c][j] /= d;
+    for (int r = 0; r < n; ++r)
+      if (r != c) {
+        const double f = a[r][c];
+        for (int j = 0; j < 2 * n; ++j) a[r][j] -= f * a[c][j];
+      }
+  }
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) t.minv[i][j] = a[i][n + j];
+  t.scale = dt / (0.25 * h->hx * h->hy);
+  const int64_t ncells = (int64_t)h->nx * h->ny;
+  const int blocks = (int)std::min<int64_t>((ncells + 127) / 128, (int64_t)sm_count() * 32);
+  ipdg_euler_kernel<<<blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(t, ncells, y, b, u);
+  STEFAN_CUDA(cudaGetLastError());
+  return ST_OK;
+}
+
+}  // extern "C"

@@ -261,6 +261,21 @@ class IPOperator:
                                                         col_begin, col_end, algo, _stream_ptr(stream)))
         return out
 
+    def interface_sums(self, u, u_lo=None, u_hi=None, stream=None):
+        """[length, int lambda (Tm - {T}), int (k1 dnT1 - k2 dnT2), int {T}] over the interface
+        faces owned by this slab (device tensor of 4 doubles)."""
+        import torch
+        out = torch.empty(4, dtype=torch.float64, device="cuda")
+        _lib.check(_lib.lib().stefan_ipdg_interface_sums(self._h, _ptr(u), _ptr(u_lo), _ptr(u_hi), _ptr(out),
+                                                         _stream_ptr(stream)))
+        return out
+
+    def euler_update(self, u, y, b, dt, stream=None):
+        """u <- u + dt Minv (b - y), in place."""
+        _lib.check(_lib.lib().stefan_ipdg_euler_update(self._h, _ptr(u), _ptr(y), _ptr(b), float(dt),
+                                                       _stream_ptr(stream)))
+        return u
+
     def rhs(self, f_qp=None, g_qp=None, out=None, stream=None):
         """b of `assemble_interior_penalty_rhs!` (+ Robin source) from device samples."""
         import torch

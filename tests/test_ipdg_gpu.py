@@ -136,3 +136,64 @@ def test_column_ranges_compose(cuda, order):
     assert torch.equal(out, full)
     yh = op.apply_host(x.cpu().pin_memory(), nslabs=5)
     assert torch.equal(yh, full.cpu())
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_interface_sums_match_oracle(cuda, order):
+    import torch
+    from oracle import timeloop
+    from stefanproblem_b200 import cutcelldg as cc
+    nx, ny = 12, 9
+    omesh = UniformMesh2D([0, 0], [1.0, 0.9], [nx, ny], (order + 1) ** 2)
+    omesh.cellsign[:] = fast.circle_phase(omesh, (0.45, 0.5), 0.3)
+    k1, k2, lam, Tm = 1.0, 2.0, 1.7, 0.4
+    basis = cc.LagrangeTensorProductBasis(2, order)
+    mesh = cc.UniformMesh([0, 0], [1.0, 0.9], [nx, ny], basis, phase=omesh.cellsign)
+    op = cc.IPOperator(mesh, order, order + 1, k1, k2, 1e3 * nx, lam, Tm, "current", ALL)
+    u = np.random.default_rng(7).uniform(-1, 1, op.ndofs)
+    ref = timeloop.ip_interface_sums(omesh, order, order + 1, k1, k2, lam, Tm, u)
+    got = op.interface_sums(torch.from_numpy(u).cuda()).cpu().numpy()
+    assert np.all(np.abs(got - ref) <= 1e-12 * np.abs(ref).max())
+    # two column slabs: every face is counted once (owned by its +1 cell)
+    cut = 5
+    P = omesh.cellsign.reshape(nx, ny)
+    col = ny * basis.nf
+    lo = cc.IPOperator(cc.UniformMesh([0, 0], [cut / nx, 0.9], [cut, ny], basis, phase=P[:cut].ravel()),
+                       order, order + 1, k1, k2, 1e3 * nx, lam, Tm, "current", ALL, phase_hi=P[cut])
+    hi = cc.IPOperator(cc.UniformMesh([cut / nx, 0], [1 - cut / nx, 0.9], [nx - cut, ny], basis, phase=P[cut:].ravel()),
+                       order, order + 1, k1, k2, 1e3 * nx, lam, Tm, "current", ALL, phase_lo=P[cut - 1])
+    ud = torch.from_numpy(u).cuda()
+    s = (lo.interface_sums(ud[:cut * col].contiguous(), u_hi=ud[cut * col:(cut + 1) * col].contiguous())
+         + hi.interface_sums(ud[cut * col:].contiguous(), u_lo=ud[(cut - 1) * col:cut * col].contiguous()))
+    assert np.all(np.abs(s.cpu().numpy() - ref) <= 1e-11 * np.abs(ref).max())
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_hundred_explicit_euler_steps(cuda, order):
+    """u <- u + dt Minv (b - A u), 100 steps, vs the oracle loop: <= 1e-10 (north star)."""
+    import torch
+    from oracle import timeloop
+    from stefanproblem_b200 import cutcelldg as cc
+    nx, ny, nq = 10, 8, order + 1
+    omesh = UniformMesh2D([0, 0], [1.0, 1.0], [nx, ny], (order + 1) ** 2)
+    omesh.cellsign[:] = fast.circle_phase(omesh)
+    k1, k2, pen, lam, Tm = 1.0, 2.0, 10.0 * nx, 1.0, 0.5
+    A = fast.ip_matrix(omesh, order, nq, k1, k2, pen, lam)
+    f = fast.sample_cell_quadrature(omesh, nq, lambda x, y: 1.0 + np.sin(3 * x) * y)
+    g = fast.sample_face_quadrature(omesh, nq, lambda x, y: x + y)
+    b = fast.ip_rhs(omesh, order, nq, k1, k2, pen, f, g, lam, Tm)
+    Minv = timeloop.ip_block_mass_inverse(omesh, order, nq)
+    lam_max = np.abs(np.linalg.eigvals((np.kron(np.eye(nx * ny), Minv) @ A.toarray()))).max()
+    dt = 1.0 / lam_max
+    u0 = np.random.default_rng(3).uniform(-1, 1, A.shape[0])
+    ref = timeloop.ip_euler_run(A, b, Minv, u0, dt, 100)
+    basis = cc.LagrangeTensorProductBasis(2, order)
+    mesh = cc.UniformMesh([0, 0], [1.0, 1.0], [nx, ny], basis, phase=omesh.cellsign)
+    op = cc.IPOperator(mesh, order, nq, k1, k2, pen, lam, Tm, "current", ALL)
+    u = torch.from_numpy(u0).cuda()
+    bd = torch.from_numpy(b).cuda()
+    y = torch.empty_like(u)
+    for _ in range(100):
+        op.apply(u, out=y)
+        op.euler_update(u, y, bd, dt)
+    assert np.linalg.norm(u.cpu().numpy() - ref) <= 1e-10 * np.linalg.norm(ref)
