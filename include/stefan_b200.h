@@ -218,6 +218,10 @@ int stefan_dg1d_apply(stefan_dg1d* h, const double* x, double* y, void* stream);
 int stefan_dg1d_rhs(stefan_dg1d* h, const double* f_qp, double TL, double TR, int32_t with_boundary,
                     double* b, void* stream);
 
+/* Right-hand side of assemble_LDG_rhs! (LDG_assembly.jl:93-131); f_qp / g_qp sampled as for
+ * stefan_ipdg_rhs; b [3*nnodes] is overwritten. */
+int stefan_ldg_rhs(stefan_ldg* h, const double* f_qp, const double* g_qp, double* b, void* stream);
+
 /* --------------------------------------------------------------------- FD
  * Two-phase 1-D finite-difference Laplace operator of module FiniteDifference
  * (StefanFD/finite-difference.jl).  phaseid: host int8[numnodes] as produced by

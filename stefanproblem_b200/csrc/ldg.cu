@@ -23,6 +23,7 @@ namespace stefan {
 
 struct LdgHandle {
   int nx, ny, order, numqp;
+  double phys_hx, phys_hy;
   LdgPhys phys;
   bool has_lo, has_hi;
   int8_t* phase_dev;
@@ -84,6 +85,69 @@ ldg_apply_cells(const __grid_constant__ LdgTab<P> tab, const LdgArgs a) {
   }
 }
 
+// Right-hand side of assemble_LDG_rhs! (LDG_assembly.jl:93-131):
+//   T rows: sum V f detjac w  (assemble_source!, LDG_source_term.jl:31-60)
+//           + alpha_b sum V g sa w on boundary faces (assemble_boundary_vector_flux_source!
+//             :265-321; the reference writes it as -alpha * linear_form(..., (-n.n) sa))
+//   q rows: sum IM(V)' n g sa w on boundary faces (assemble_boundary_scalar_flux_source! :152-198)
+struct LdgRhsTab {
+  int n1, nq;
+  double Nq[kMaxQ][kMaxN1], w[kMaxQ];
+  double jx, jy;
+  double alpha_b[4];  // per face 0 bottom, 1 right, 2 top, 3 left
+};
+
+__global__ void __launch_bounds__(128)
+ldg_rhs_kernel(const __grid_constant__ LdgRhsTab t, const int8_t* __restrict__ phase, int nx, int ny,
+               const double* __restrict__ f_qp, const double* __restrict__ g_qp, double* __restrict__ b) {
+  const int n1 = t.n1, nq = t.nq, nf = n1 * n1;
+  const double* g_bottom = g_qp;
+  const double* g_right = g_bottom + (size_t)nx * nq;
+  const double* g_top = g_right + (size_t)ny * nq;
+  const double* g_left = g_top + (size_t)nx * nq;
+  const int64_t ncells = (int64_t)nx * ny;
+  for (int64_t cell = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; cell < ncells;
+       cell += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(cell / ny), j = (int)(cell % ny);
+    double out[3 * kMaxN1 * kMaxN1];
+    for (int a = 0; a < 3 * nf; ++a) out[a] = 0.0;
+    if (f_qp != nullptr) {
+      const double* f = f_qp + cell * (size_t)(nq * nq);
+      const double detjac = t.jx * t.jy;
+      for (int qx = 0; qx < nq; ++qx)
+        for (int qy = 0; qy < nq; ++qy) {
+          const double v = f[qx * nq + qy] * t.w[qx] * t.w[qy] * detjac;
+          for (int ix = 0; ix < n1; ++ix)
+            for (int iy = 0; iy < n1; ++iy) out[3 * (ix * n1 + iy)] += t.Nq[qx][ix] * t.Nq[qy][iy] * v;
+        }
+    }
+    if (g_qp != nullptr)
+      for (int face = 0; face < 4; ++face) {
+        const int sn = face == 0 ? ldg_phase_at(phase, ny, i, j - 1)
+                       : face == 1 ? ldg_phase_at(phase, ny, i + 1, j)
+                       : face == 2 ? ldg_phase_at(phase, ny, i, j + 1)
+                                   : ldg_phase_at(phase, ny, i - 1, j);
+        if (sn != 0) continue;
+        const bool xnormal = (face == 1 || face == 3), high = (face == 1 || face == 2);
+        const double jt = xnormal ? t.jy : t.jx, n = high ? 1.0 : -1.0;
+        const int fnode = high ? n1 - 1 : 0;
+        const double* g = face == 0   ? g_bottom + (size_t)i * nq
+                          : face == 1 ? g_right + (size_t)j * nq
+                          : face == 2 ? g_top + (size_t)i * nq
+                                      : g_left + (size_t)j * nq;
+        for (int it = 0; it < n1; ++it) {
+          double m = 0.0;
+          for (int q = 0; q < nq; ++q) m += t.w[q] * t.Nq[q][it] * g[q];
+          m *= jt;
+          const int a = xnormal ? fnode * n1 + it : it * n1 + fnode;
+          out[3 * a + 0] += t.alpha_b[face] * m;
+          out[3 * a + (xnormal ? 1 : 2)] += n * m;
+        }
+      }
+    for (int a = 0; a < 3 * nf; ++a) b[cell * 3 * nf + a] = out[a];
+  }
+}
+
 template <int P>
 static int ldg_launch(const LdgHandle* h, const LdgArgs& a, cudaStream_t st) {
   const LdgTab<P>& tab = *static_cast<const LdgTab<P>*>(h->tab_host);
@@ -112,6 +176,8 @@ int stefan_ldg_create(const stefan_ldg_params* p, const int8_t* phase, const int
   h->ny = p->ny;
   h->order = p->order;
   h->numqp = p->numqp;
+  h->phys_hx = p->hx;
+  h->phys_hy = p->hy;
   h->phys = LdgPhys{p->k1, p->k2, p->interiorpenalty, p->negboundarypenalty, p->posboundarypenalty,
                     p->V0x, p->V0y};
   h->has_lo = phase_lo != nullptr;
@@ -168,6 +234,35 @@ int stefan_ldg_destroy(stefan_ldg* hv) {
 
 int64_t stefan_ldg_ndofs(const stefan_ldg* hv) {
   return hv ? reinterpret_cast<const LdgHandle*>(hv)->ndofs : -1;
+}
+
+int stefan_ldg_rhs(stefan_ldg* hv, const double* f_qp, const double* g_qp, double* b, void* stream) {
+  LdgHandle* h = reinterpret_cast<LdgHandle*>(hv);
+  STEFAN_REQUIRE(h && b, "stefan_ldg_rhs: null argument");
+  STEFAN_REQUIRE(!h->has_lo && !h->has_hi, "stefan_ldg_rhs: slab handles are not supported yet");
+  RefElem1D ref;
+  build_ref1d(h->order, h->numqp, &ref);
+  LdgRhsTab t;
+  std::memset(&t, 0, sizeof(t));
+  t.n1 = h->order + 1;
+  t.nq = h->numqp;
+  for (int q = 0; q < t.nq; ++q) {
+    t.w[q] = ref.qw[q];
+    for (int a = 0; a < t.n1; ++a) t.Nq[q][a] = ref.Nq[q][a];
+  }
+  t.jx = 0.5 * h->phys_hx;
+  t.jy = 0.5 * h->phys_hy;
+  const double nx_[4] = {0, 1, 0, -1}, ny_[4] = {-1, 0, 1, 0};
+  for (int f = 0; f < 4; ++f) {
+    const double v0n = h->phys.V0x * nx_[f] + h->phys.V0y * ny_[f];
+    t.alpha_b[f] = v0n < 0 ? h->phys.negboundarypenalty : h->phys.posboundarypenalty;
+  }
+  const int64_t ncells = (int64_t)h->nx * h->ny;
+  const int blocks = (int)std::min<int64_t>((ncells + 127) / 128, (int64_t)sm_count() * 32);
+  ldg_rhs_kernel<<<blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(t, h->phase_dev, h->nx, h->ny, f_qp,
+                                                                         g_qp, b);
+  STEFAN_CUDA(cudaGetLastError());
+  return ST_OK;
 }
 
 int stefan_ldg_apply(stefan_ldg* hv, const double* x, double* y, const double* x_lo, const double* x_hi,

@@ -170,6 +170,17 @@ class SystemRHS:
             op = IPOperator(mesh, s["order"], numqp, s.get("k1", 1.0), s.get("k2", 1.0), s.get("penalty", 0.0),
                             s.get("lam", 0.0), s.get("Tm", 0.0), s.get("variant", "current"), terms or 1)
             return op.rhs(f_qp, g_qp)
+        if self.kind == "ldg":
+            numqp = s["numqp"]
+            x, y = cell_quadrature_points(mesh, numqp)
+            f = np.broadcast_to(s["f"](np.stack([x, y])), x.shape)
+            f_qp = torch.from_numpy(np.ascontiguousarray(f, dtype=np.float64)).cuda()
+            x, y = boundary_quadrature_points(mesh, numqp)
+            g = np.broadcast_to(s["g"](np.stack([x, y])), x.shape)
+            g_qp = torch.from_numpy(np.ascontiguousarray(g, dtype=np.float64)).cuda()
+            op = LDGOperator(mesh, s["order"], numqp, 1.0, 1.0, 0.0, s["negboundarypenalty"],
+                             s["posboundarypenalty"], s["V0"])
+            return op.rhs(f_qp, g_qp)
         raise ValueError(f"unknown right-hand side kind {self.kind}")
 
 
@@ -349,6 +360,13 @@ class LDGOperator:
             out = torch.empty_like(x)
         _lib.check(_lib.lib().stefan_ldg_apply(self._h, _ptr(x), _ptr(out), _ptr(x_lo), _ptr(x_hi),
                                                _stream_ptr(stream)))
+        return out
+
+    def rhs(self, f_qp=None, g_qp=None, stream=None):
+        """b of `assemble_LDG_rhs!` from device samples (layout as IPOperator.rhs)."""
+        import torch
+        out = torch.empty(self.ndofs, dtype=torch.float64, device="cuda")
+        _lib.check(_lib.lib().stefan_ldg_rhs(self._h, _ptr(f_qp), _ptr(g_qp), _ptr(out), _stream_ptr(stream)))
         return out
 
     def __matmul__(self, x):

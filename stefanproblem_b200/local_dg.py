@@ -70,4 +70,13 @@ def assemble_LDG_linear_system(sysmatrix, solverbasis, cellquads, facequads, int
                                            negboundarypenalty, posboundarypenalty, V0, mesh)
 
 
+def assemble_LDG_rhs(sysrhs, sourceterm, boundaryfunc, solverbasis, cellquads, facequads,
+                     negboundarypenalty, posboundarypenalty, V0, mesh):
+    """LDG_assembly.jl:93-131 (`sourceterm(x)`, `boundaryfunc(x)` are called with x = [xs; ys])."""
+    sysrhs._merge("ldg", f=sourceterm, g=boundaryfunc, order=solverbasis.order, numqp=cellquads.numqp,
+                  negboundarypenalty=float(negboundarypenalty), posboundarypenalty=float(posboundarypenalty),
+                  V0=(float(V0[0]), float(V0[1])))
+
+
 sparse_operator = _cc.sparse_operator
+rhs_vector = _cc.rhs_vector

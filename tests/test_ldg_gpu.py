@@ -57,3 +57,48 @@ def test_two_slabs_equal_one(cuda):
     yhi = hi.apply(x[cut * col:].contiguous(), x_lo=x[(cut - 1) * col:cut * col].contiguous())
     # the slab meshes compute their cell width from their own extent: last-bit differences in h
     assert (torch.cat([ylo, yhi]) - yf).norm() <= 1e-14 * yf.norm()
+
+
+@pytest.mark.parametrize("order,nq", [(1, 2), (2, 5), (3, 4)])
+def test_rhs_and_golden_solve(cuda, order, nq):
+    """assemble_LDG_rhs! on the GPU vs the oracle; and the reference's golden convergence
+    number (MD-LDG_convergence.csv, n = 5) reproduced from the GPU operator + GPU rhs."""
+    import json
+    import os
+    import torch
+    from oracle.basis import LagrangeTensorProductBasis as OB
+    from oracle.mesh import CellQuadratures
+    from oracle.norms import integral_norm_on_mesh, mesh_L2_error
+    from stefanproblem_b200 import cutcelldg as cc
+    from stefanproblem_b200 import local_dg as LocalDG
+    n = 5
+    V0 = np.array([np.cos(np.pi / 4), np.sin(np.pi / 4)])
+    ex = lambda v: np.cos(2 * np.pi * v[0]) * np.sin(2 * np.pi * v[1])  # noqa: E731
+    src = lambda v: 8 * np.pi ** 2 * np.cos(2 * np.pi * v[0]) * np.sin(2 * np.pi * v[1])  # noqa: E731
+    omesh = UniformMesh2D([0, 0], [1, 1], [n, n], (order + 1) ** 2)
+    ref_b = fast.ldg_rhs(omesh, order, nq, 0.0, 1.0, V0,
+                         fast.sample_cell_quadrature(omesh, nq, lambda x, y: src((x, y))),
+                         fast.sample_face_quadrature(omesh, nq, lambda x, y: ex((x, y))))
+    basis = cc.LagrangeTensorProductBasis(2, order)
+    mesh = cc.UniformMesh([0, 0], [1, 1], [n, n], basis)
+    cq, fq = cc.CellQuadratures(mesh, nq), cc.FaceQuadratures(mesh, nq)
+    sm, rhs = cc.SystemMatrix(), cc.SystemRHS()
+    LocalDG.assemble_LDG_linear_system(sm, basis, cq, fq, None, 1.0, 1.0, 0.0, 0.0, 0.0, 1.0, V0, mesh)
+    LocalDG.assemble_LDG_rhs(rhs, src, ex, basis, cq, fq, 0.0, 1.0, V0, mesh)
+    op = LocalDG.sparse_operator(sm, mesh, 3)
+    b = LocalDG.rhs_vector(rhs, mesh, 3).cpu().numpy()
+    assert np.linalg.norm(b - ref_b) <= 1e-13 * np.linalg.norm(ref_b)
+    if order == 3:
+        return
+    # recover the matrix from the GPU operator (small: 3 * 25 * NF columns) and solve
+    N = op.ndofs
+    eye = torch.eye(N, dtype=torch.float64, device="cuda")
+    A = np.stack([(op @ eye[i].contiguous()).cpu().numpy() for i in range(N)], axis=1)
+    sol = np.linalg.solve(A, b).reshape(-1, 3).T
+    ob = OB(2, order)
+    ocq = CellQuadratures(nq)
+    errT = mesh_L2_error(sol[0:1], ex, ob, ocq, omesh)[0] / integral_norm_on_mesh(ex, ocq, omesh, 1)[0]
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_csv.json")))["ldg_uncut"][1]
+    assert gold[0] == 5
+    ref = gold[1] if order == 1 else gold[4]
+    assert abs(errT - ref) / ref < 1e-10
