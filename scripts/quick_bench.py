@@ -30,6 +30,32 @@ def run(order, nx, ny, two_phase, algo, reps=20):
     print(f"p={order} {nx}x{ny} two_phase={two_phase} algo={algo}: {ms:.3f} ms  {gdofs:.1f} GDOF/s  "
           f"{16 * gdofs:.0f} GB/s  ({16 * gdofs / 6551 * 100:.1f}% of 6551)", flush=True)
 
+def run_ldg(order, n, two_phase, reps=20):
+    basis = cc.LagrangeTensorProductBasis(2, order)
+    phase = None
+    if two_phase:
+        i, j = np.divmod(np.arange(n * n), n)
+        cx, cy = (i + 0.5) / n, (j + 0.5) / n
+        phase = np.where((cx - 0.5) ** 2 + (cy - 0.5) ** 2 < 0.16, -1, 1).astype(np.int8)
+    mesh = cc.UniformMesh([0, 0], [1, 1], [n, n], basis, phase=phase)
+    op = cc.LDGOperator(mesh, order, order + 1, 1.0, 2.0, 0.0, 0.0, 1.0, (np.cos(np.pi / 4), np.sin(np.pi / 4)))
+    x = torch.rand(op.ndofs, dtype=torch.float64, device="cuda") * 2 - 1
+    y = torch.empty_like(x)
+    for _ in range(3):
+        op.apply(x, out=y)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        op.apply(x, out=y)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    gdofs = op.ndofs / ms / 1e6
+    print(f"LDG p={order} {n}x{n} two_phase={two_phase}: {ms:.4f} ms  {gdofs:.1f} GDOF/s  "
+          f"{16 * gdofs:.0f} GB/s  ({16 * gdofs / 6551 * 100:.1f}% of 6551)", flush=True)
+
+
 if __name__ == "__main__":
     import argparse
     ap = argparse.ArgumentParser()
@@ -38,9 +64,16 @@ if __name__ == "__main__":
     ap.add_argument("--nx", type=int, default=0)
     ap.add_argument("--ny", type=int, default=0)
     ap.add_argument("--algo", type=int, default=0)
+    ap.add_argument("--sweep", type=int, default=0)
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--two-phase", type=int, default=1)
+    ap.add_argument("--ldg", type=int, default=0)
     args = ap.parse_args()
+    if args.ldg:
+        orders = [args.order] if args.order else [1, 2, 3]
+        for o in orders:
+            run_ldg(o, args.n or {1: 913, 2: 609, 3: 457}[o], bool(args.two_phase), args.reps)
+        sys.exit(0)
     if args.order:
         n = args.n or {1: 5000, 2: 3334, 3: 2500}[args.order]
         run(args.order, args.nx or n, args.ny or n, bool(args.two_phase), args.algo, args.reps)

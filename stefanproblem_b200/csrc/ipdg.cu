@@ -569,9 +569,64 @@ ipdg_apply_p1_tma(const __grid_constant__ IpTab<1> tab, const ApplyArgs a,
   fixup_tail<1>(tab, a);
 }
 
+}  // namespace stefan
+#include "ipdg_march.cuh"
+namespace stefan {
+
 // --------------------------------------------------------------------------
 // host side
 // --------------------------------------------------------------------------
+// cuTensorMapEncodeTiled through the runtime (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// x as a 2-D tensor {16 doubles, ncells}, tiles of 32 cells, 128-byte swizzle
+static int make_cell_tensor_map(const double* x, int64_t ncells, CUtensorMap* out) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (enc == nullptr) return fail(ST_CUDA_ERROR, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t gdim[2] = {16, (cuuint64_t)ncells};
+  const cuuint64_t gstr[1] = {128};
+  const cuuint32_t box[2] = {16, 32};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(x), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ST_CUDA_ERROR, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return ST_OK;
+}
+
+template <int P>
+static int launch_march(const IpdgHandle* h, const IpTab<P>& tab, const ApplyArgs& args, int grid, cudaStream_t st) {
+  using C = MarchCfg<P>;
+  constexpr int smem = MarchSmem<P>::TOTAL;
+  static bool attr_set = false;
+  if (!attr_set) {
+    STEFAN_CUDA(cudaFuncSetAttribute(ipdg_apply_march<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  CUtensorMap tm;
+  std::memset(&tm, 0, sizeof(tm));
+  if (C::TENSOR) {
+    int rc = make_cell_tensor_map(args.x, (int64_t)h->nx * h->ny, &tm);
+    if (rc) return rc;
+  }
+  ipdg_apply_march<P><<<grid, C::WARPS * 32, smem, st>>>(tab, args, h->runs_dev, h->run_ofs_dev, tm);
+  return ST_OK;
+}
+
 template <int P>
 static int launch_apply(const IpdgHandle* h, const ApplyArgs& args0, int algo, cudaStream_t st) {
   using C = StreamCfg<P>;
@@ -599,7 +654,11 @@ static int launch_apply(const IpdgHandle* h, const ApplyArgs& args0, int algo, c
     args.nseg = nseg;
     return ngroups * nseg;
   };
-  if (P == 1 && algo == 0) {
+  if (algo == 4 || (algo == 0 && P != 1)) {
+    const int grid = grid_for(MarchCfg<P>::WARPS, MarchCfg<P>::MINB);
+    int rc = launch_march<P>(h, tab, args, grid, st);
+    if (rc) return rc;
+  } else if (P == 1 && (algo == 0 || algo == 3)) {
     const int grid = grid_for(kTmaWarps, 2);
     if constexpr (P == 1) {
       const size_t smem = (size_t)kTmaWarps * kTmaWarpSmem;
@@ -808,7 +867,7 @@ int stefan_ipdg_apply(stefan_ipdg* hv, const double* x, double* y, const double*
   STEFAN_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
                  (reinterpret_cast<uintptr_t>(x_lo) & 15) == 0 && (reinterpret_cast<uintptr_t>(x_hi) & 15) == 0,
                  "stefan_ipdg_apply: device pointers must be 16-byte aligned");
-  STEFAN_REQUIRE(algo >= 0 && algo <= 2, "stefan_ipdg_apply: unknown algo %d", algo);
+  STEFAN_REQUIRE(algo >= 0 && algo <= 4 && !(algo == 3 && h->order != 1), "stefan_ipdg_apply: unknown algo %d", algo);
   ApplyArgs a{x, x_lo, x_hi, y, h->phase_dev, h->flags_dev, (h->nx + 15) / 16 * 16, h->nx, h->ny, 1, 0, h->nx, nullptr, 0};
   return dispatch_apply(h, a, algo, static_cast<cudaStream_t>(stream));
 }
@@ -823,7 +882,7 @@ int stefan_ipdg_apply_columns(stefan_ipdg* hv, const double* x, double* y, const
   STEFAN_REQUIRE(h && x && y && x != y, "stefan_ipdg_apply_columns: bad argument");
   STEFAN_REQUIRE(0 <= col_begin && col_begin <= col_end && col_end <= h->nx,
                  "stefan_ipdg_apply_columns: need 0 <= col_begin <= col_end <= nx");
-  STEFAN_REQUIRE(algo >= 0 && algo <= 2, "stefan_ipdg_apply_columns: unknown algo %d", algo);
+  STEFAN_REQUIRE(algo >= 0 && algo <= 4 && !(algo == 3 && h->order != 1), "stefan_ipdg_apply_columns: unknown algo %d", algo);
   const bool needs_lo = col_begin == 0, needs_hi = col_end == h->nx;
   STEFAN_REQUIRE(!(needs_lo && h->has_lo && !x_lo) && !(needs_hi && h->has_hi && !x_hi),
                  "stefan_ipdg_apply_columns: the halo column next to the requested range is missing");

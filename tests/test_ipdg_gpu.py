@@ -32,12 +32,14 @@ def _case(order, nx, ny, two_phase, terms, variant, lam=1.5):
 
 
 @pytest.mark.parametrize("order", [1, 2, 3])
-@pytest.mark.parametrize("algo", [0, 1, 2])
+@pytest.mark.parametrize("algo", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("nx,ny", [(3, 3), (7, 6), (17, 33), (40, 95)])
 @pytest.mark.parametrize("two_phase,terms,variant", [
     (False, REFSYS, "current"), (False, REFSYS, "legacy_boundary"),
     (True, ALL, "current"), (True, REFSYS, "current")])
 def test_apply_matches_oracle(cuda, order, algo, nx, ny, two_phase, terms, variant):
+    if algo == 3 and order != 1:
+        pytest.skip("algo 3 is the order-1 bulk-copy kernel")
     A, op, x, xd = _case(order, nx, ny, two_phase, terms, variant)
     y = op.apply(xd, algo=algo).cpu().numpy()
     yr = A @ x
@@ -60,6 +62,9 @@ def test_stream_equals_simple_large(cuda, order):
     y0 = op.apply(x, algo=0)
     y1 = op.apply(x, algo=1)
     assert torch.equal(y0, y1) or (y0 - y1).norm() / y1.norm() < 1e-15
+    for algo in (2, 4):
+        ya = op.apply(x, algo=algo)
+        assert (ya - y1).norm() / y1.norm() < 1e-15 and (ya - y1).abs().max() / y1.abs().max() < 1e-14
     # symmetry of the operator: x' A z == z' A x
     z = torch.from_numpy(np.random.default_rng(2).uniform(-1, 1, op.ndofs)).cuda()
     a = torch.dot(z, y0)
@@ -136,6 +141,34 @@ def test_column_ranges_compose(cuda, order):
     assert torch.equal(out, full)
     yh = op.apply_host(x.cpu().pin_memory(), nslabs=5)
     assert torch.equal(yh, full.cpu())
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
+@pytest.mark.parametrize("algo", [0, 1, 2, 4])
+@pytest.mark.parametrize("nx,ny,cut", [(64, 95, 29), (37, 64, 18), (9, 31, 4)])
+def test_two_slabs_equal_one(cuda, order, algo, nx, ny, cut):
+    """Column-slab partition: two slab handles fed each other's edge column reproduce the
+    one-GPU result (every production kernel reads the halo columns its own way)."""
+    import torch
+    from stefanproblem_b200 import cutcelldg as cc
+    basis = cc.LagrangeTensorProductBasis(2, order)
+    omesh = UniformMesh2D([0, 0], [1, 1], [nx, ny], basis.nf)
+    P = fast.circle_phase(omesh).reshape(nx, ny)
+    pen = 1e3 * nx
+    full = cc.IPOperator(cc.UniformMesh([0, 0], [1, 1], [nx, ny], basis, phase=P.ravel()),
+                         order, order + 1, 1.0, 2.0, pen, 1.0, 0.5, "current", ALL)
+    lo = cc.IPOperator(cc.UniformMesh([0, 0], [cut / nx, 1], [cut, ny], basis, phase=P[:cut].ravel()),
+                       order, order + 1, 1.0, 2.0, pen, 1.0, 0.5, "current", ALL, phase_hi=P[cut])
+    hi = cc.IPOperator(cc.UniformMesh([cut / nx, 0], [1 - cut / nx, 1], [nx - cut, ny], basis, phase=P[cut:].ravel()),
+                       order, order + 1, 1.0, 2.0, pen, 1.0, 0.5, "current", ALL, phase_lo=P[cut - 1])
+    x = torch.from_numpy(np.random.default_rng(11).uniform(-1, 1, full.ndofs)).cuda()
+    col = ny * basis.nf
+    yf = full.apply(x, algo=1)
+    # clones: fresh (aligned) allocations, as separate GPUs would hold them
+    ylo = lo.apply(x[:cut * col].clone(), x_hi=x[cut * col:(cut + 1) * col].clone(), algo=algo)
+    yhi = hi.apply(x[cut * col:].clone(), x_lo=x[(cut - 1) * col:cut * col].clone(), algo=algo)
+    # the slab meshes compute their cell width from their own extent: last-bit differences in h
+    assert (torch.cat([ylo, yhi]) - yf).norm() <= 1e-13 * yf.norm()
 
 
 @pytest.mark.parametrize("order", [1, 2, 3])
