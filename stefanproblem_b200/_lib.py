@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libstefan_b200.so")
+# STEFAN_B200_LIB: another build of the same library (kernel tuning variants)
+LIB_PATH = os.environ.get("STEFAN_B200_LIB") or os.path.join(_HERE, "lib", "libstefan_b200.so")
 
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_int8_p = ctypes.POINTER(ctypes.c_int8)

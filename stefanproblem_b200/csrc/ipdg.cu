@@ -67,6 +67,7 @@ struct ApplyArgs {
   int cbeg, cend;  // columns to produce (a sub-range when the host path pipelines slabs)
   const int32_t* fix;  // cells the stream kernels leave to their tail (see fixup_tail)
   int nfix;
+  unsigned zero;  // 0 at run time, unknown at compile time (see ipdg_march.cuh, slot release)
 };
 
 __device__ __forceinline__ int phase_at(const int8_t* __restrict__ ph, int ny, int i, int j) {

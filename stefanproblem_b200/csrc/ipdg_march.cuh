@@ -45,19 +45,19 @@ namespace stefan {
 #define MARCH_NST1 6
 #endif
 #ifndef MARCH_NST2
-#define MARCH_NST2 5
+#define MARCH_NST2 4
 #endif
 #ifndef MARCH_NST3
-#define MARCH_NST3 5
+#define MARCH_NST3 4
 #endif
 #ifndef MARCH_WARPS1
 #define MARCH_WARPS1 8
 #endif
 #ifndef MARCH_WARPS2
-#define MARCH_WARPS2 8
+#define MARCH_WARPS2 16
 #endif
 #ifndef MARCH_WARPS3
-#define MARCH_WARPS3 8
+#define MARCH_WARPS3 12
 #endif
 #ifndef MARCH_MINB1
 #define MARCH_MINB1 2
@@ -203,6 +203,55 @@ struct MarchMath {
   }
 };
 
+// 32-bit shared-window addresses keep the loop's address arithmetic in single registers
+__device__ __forceinline__ double2 lds_v2(unsigned addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f64(unsigned addr, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_s(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_s(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_s(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@!p bra WAIT_%=;\n}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load_s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tensor2d_load_s(unsigned dst, const CUtensorMap* map, int c0, int c1, unsigned bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_store_s(void* gdst, unsigned ssrc, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes)
+               : "memory");
+}
+// (end column, flag) of a run, loaded only when a run ends (an ordinary load would be
+// hoisted out of the rare branch and every iteration would wait for it)
+__device__ __forceinline__ int2 ld_run(const int2* p) {
+  int2 v;
+  asm volatile("ld.global.nc.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+  return v;
+}
+
 template <int P>
 __global__ void __launch_bounds__(MarchCfg<P>::WARPS * 32, MarchCfg<P>::MINB)
 ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const int2* __restrict__ runs,
@@ -214,16 +263,18 @@ ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const 
   constexpr int CB = C::CB;
   extern __shared__ char smem_raw[];
   const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
+  // broadcast from lane 0: the compiler then knows that everything derived from the warp
+  // index is warp-uniform and keeps it in uniform registers (TMA operands included)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   // 1024-byte aligned base (swizzle atoms of the tensor tiles)
-  char* const smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
-  char* const ring = smem + (size_t)warp * MarchSmem<P>::WARP;
-  char* const obuf = ring + NST * C::STAGE;  // P = 2: two output buffers
-  unsigned long long* const bars =
-      reinterpret_cast<unsigned long long*>(smem + (size_t)C::WARPS * MarchSmem<P>::WARP) + warp * NST;
+  const unsigned smem0 = (smem_addr(smem_raw) + 1023u) & ~1023u;
+  const unsigned ring = smem0 + (unsigned)warp * MarchSmem<P>::WARP;
+  [[maybe_unused]] const unsigned obuf = ring + NST * C::STAGE;  // P = 2: two output buffers
+  const unsigned bars = smem0 + (unsigned)C::WARPS * MarchSmem<P>::WARP + (unsigned)warp * NST * 8;
   if (lane == 0) {
 #pragma unroll
-    for (int s = 0; s < NST; ++s) mbar_init(&bars[s], 1);
+    for (int s = 0; s < NST; ++s)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bars + 8 * s), "r"(1));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
@@ -239,17 +290,20 @@ ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const 
     const int j0 = strip * kStripCells;
     const int jhi_out = min(j0 + kStripCells, a.ny);  // one past the strip's top output cell
     const int j = j0 - 1 + lane;                      // this lane's cell
-    const bool inmesh = j >= 0 && j < a.ny;
     const bool outlane = lane >= 1 && lane <= kStripCells && j < a.ny;
     const int jlo = max(j0 - 1, 0), jhi = min(j0 + kStripCells + 1, a.ny);
     const int rel0 = jlo - (j0 - 1);  // lane of the first staged cell (0, or 1 in strip 0)
-    const size_t colcells = (size_t)a.ny;
+    const unsigned nbytes = (unsigned)(jhi - jlo) * CB;  // bytes of one column chunk
+    const size_t colbytes = (size_t)a.ny * CB;
     const char* const xb = reinterpret_cast<const char*>(a.x);
+    // Lanes outside the mesh (j = -1 in strip 0, j >= ny in the top strip) and columns
+    // that do not exist (k = -1 / nx without a halo) read whatever their ring slot
+    // holds: every cell next to them is a boundary cell, i.e. an exception cell that
+    // the loop never stores (it is recomputed by fixup_tail), so the values go nowhere.
 
-    // ---- issue of column k into its ring slot (lane 0 only does the work) ----
-    // returns nothing; the reader recomputes where the data landed from (k, slot)
+    // ---- general forms (prologue, halo / missing columns, P = 2 array end) ----
     auto col_base = [&](int k) -> const char* {
-      if (k >= 0 && k < a.nx) return xb + ((size_t)k * colcells + jlo) * CB;
+      if (k >= 0 && k < a.nx) return xb + (size_t)k * colbytes + (size_t)jlo * CB;
       if (k < 0 && a.x_lo != nullptr) return reinterpret_cast<const char*>(a.x_lo) + (size_t)jlo * CB;
       if (k >= a.nx && a.x_hi != nullptr) return reinterpret_cast<const char*>(a.x_hi) + (size_t)jlo * CB;
       return nullptr;
@@ -262,83 +316,86 @@ ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const 
       if (k >= 0 && k < a.nx) return k == a.nx - 1;
       return true;  // halo columns are arrays of ny cells
     };
-    auto issue = [&](int k, int slot) {
-      if (k > c1) return;
-      if (lane != 0) return;
-      char* dst = ring + slot * C::STAGE;
+    auto issue_general = [&](int k, unsigned stage, unsigned bar) {
+      if (k > c1 || lane != 0) return;
       const char* src = col_base(k);
       if (src == nullptr) {  // no such column: nothing to copy, complete the phase
-        mbar_arrive(&bars[slot]);
+        mbar_arrive_s(bar);
         return;
       }
       if constexpr (C::TENSOR) {
         if (k >= 0 && k < a.nx) {
-          mbar_arrive_expect_tx(&bars[slot], (unsigned)C::STAGE);
-          tma_tensor2d_load(dst, &tmx, 0, (int)((int64_t)k * a.ny + (j0 - 1)), &bars[slot]);
+          mbar_expect_tx_s(bar, (unsigned)C::STAGE);
+          tensor2d_load_s(stage, &tmx, 0, (int)((int64_t)k * a.ny + (j0 - 1)), bar);
         } else {  // halo column: plain bulk copy, read back unswizzled
-          const unsigned bytes = (unsigned)(jhi - jlo) * CB;
-          mbar_arrive_expect_tx(&bars[slot], bytes);
-          tma_bulk_load(dst + rel0 * CB, src, bytes, &bars[slot]);
+          mbar_expect_tx_s(bar, nbytes);
+          bulk_load_s(stage + rel0 * CB, src, nbytes, bar);
         }
       } else if constexpr (P == 2) {
         const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(src) & 15u);  // 0 or 8
-        unsigned bytes = sh + (unsigned)(jhi - jlo) * CB;
+        unsigned bytes = sh + nbytes;
         if (chunk_is_array_end(k)) bytes &= ~15u;
         else bytes = (bytes + 15u) & ~15u;
-        mbar_arrive_expect_tx(&bars[slot], bytes);
-        tma_bulk_load(dst + rel0 * 80, src - sh, bytes, &bars[slot]);
+        mbar_expect_tx_s(bar, bytes);
+        bulk_load_s(stage + rel0 * 80, src - sh, bytes, bar);
       } else {
-        const unsigned bytes = (unsigned)(jhi - jlo) * CB;
-        mbar_arrive_expect_tx(&bars[slot], bytes);
-        tma_bulk_load(dst + rel0 * CB, src, bytes, &bars[slot]);
+        mbar_expect_tx_s(bar, nbytes);
+        bulk_load_s(stage + rel0 * CB, src, nbytes, bar);
       }
     };
-    auto wait_slot = [&](int slot, unsigned parity) {
-      while (!mbar_try_wait(&bars[slot], parity)) {
-      }
-    };
-    // this lane's cell of column k out of ring slot `slot`
-    auto read_cell = [&](int k, int slot, double* v) {
-      const char* st = ring + slot * C::STAGE;
+    // Slot release.  A ring slot may be refilled (an asynchronous-proxy write) only after
+    // every lane's shared-memory loads of it have COMPLETED; having issued them is not
+    // enough (with 12+ warps per SM a queued LDS was overtaken by the refill of an
+    // L2-resident column: wrong results, non-deterministically).  The readers therefore
+    // return a word h that depends on one destination register of every load instruction;
+    // lane 0 adds  redux.xor(h) & a.zero  (= 0) to the address operands of the refill, so
+    // the copy cannot be issued before all 32 lanes hold their data.
+    auto hi32 = [](double v) -> unsigned { return (unsigned)__double2hiint(v); };
+    auto read_general = [&](int k, unsigned stage, double* v) -> unsigned {
+      unsigned h = 0;
       if constexpr (C::TENSOR) {
         const unsigned m = (k >= 0 && k < a.nx) ? (unsigned)(lane & 7) : 0u;
-        const char* p = st + lane * CB;
+        const unsigned p = stage + lane * CB;
 #pragma unroll
         for (int q = 0; q < NF / 2; ++q) {
-          const double2 t = *reinterpret_cast<const double2*>(p + ((q ^ m) << 4));
+          const double2 t = lds_v2(p + ((q ^ m) << 4));
           v[2 * q] = t.x;
           v[2 * q + 1] = t.y;
+          h ^= hi32(t.x);
         }
       } else if constexpr (P == 2) {
         const char* src = col_base(k);
         const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(src) & 15u);
-        const double* p = reinterpret_cast<const double*>(st + lane * CB + 8 * rel0 + sh);
+        const unsigned p = stage + lane * CB + 8 * rel0 + sh;
 #pragma unroll
-        for (int q = 0; q < NF; ++q) v[q] = p[q];
+        for (int q = 0; q < NF; ++q) {
+          v[q] = lds_f64(p + 8 * q);
+          h ^= hi32(v[q]);
+        }
         if (chunk_is_array_end(k) && j == a.ny - 1 && src != nullptr) {
-          // (sh + n CB) was 8 mod 16: the copy stopped 8 bytes short of the array end
-          const unsigned total = sh + (unsigned)(jhi - jlo) * CB;
-          if (total & 8u) v[NF - 1] = *reinterpret_cast<const double*>(src + (size_t)(jhi - jlo) * CB - 8);
+          // (sh + nbytes) was 8 mod 16: the copy stopped 8 bytes short of the array end
+          if ((sh + nbytes) & 8u) v[NF - 1] = *reinterpret_cast<const double*>(src + nbytes - 8);
         }
       } else {
-        const double2* p = reinterpret_cast<const double2*>(st + lane * CB);
+        const unsigned p = stage + lane * CB;
 #pragma unroll
         for (int q = 0; q < NF / 2; ++q) {
-          const double2 t = p[q];
+          const double2 t = lds_v2(p + 16 * q);
           v[2 * q] = t.x;
           v[2 * q + 1] = t.y;
+          h ^= hi32(t.x);
         }
       }
-      const bool have = inmesh && col_base(k) != nullptr;
-#pragma unroll
-      for (int q = 0; q < NF; ++q) v[q] = have ? v[q] : 0.0;
+      return h;
     };
+    auto released = [&](unsigned h) -> unsigned { return __reduce_xor_sync(0xffffffffu, h) & a.zero; };
 
-    // run list of this strip (see ipdg_apply_p1_tma)
+    // run list of this strip: (end column, flag); flag & 3 = phase code all cells are
+    // treated as (0: the column is left to the tail), bit 2 / bit 3 = the bottom / top
+    // cell of the strip is an exception and is not stored
     const int2* rp = runs + run_ofs[strip];
-    int2 cur = rp[0];
-    while (cur.x <= c0) cur = *++rp;
-    int2 nxt = rp[1];
+    int2 cur = ld_run(rp);
+    while (cur.x <= c0) cur = ld_run(++rp);
     auto store_flag = [&](int f) {
       return outlane && (f & 3) != 0 && !((f & 4) && lane == 1) && !((f & 8) && j == jhi_out - 1);
     };
@@ -346,39 +403,117 @@ ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const 
 
     // prologue: columns c0-1 .. c0+NST-2 into slots 0 .. NST-1
 #pragma unroll
-    for (int k = 0; k < NST; ++k) issue(c0 - 1 + k, k);
+    for (int k = 0; k < NST; ++k) issue_general(c0 - 1 + k, ring + k * C::STAGE, bars + 8 * k);
     double X[NF], tL[N1], dL[N1];
     {
       double XLfull[NF];
-      wait_slot(0, 0);
-      read_cell(c0 - 1, 0, XLfull);
-      __syncwarp();
-      issue(c0 - 1 + NST, 0);
-      wait_slot(1, 0);
-      read_cell(c0, 1, X);
-      __syncwarp();
-      issue(c0 + NST, 1);
+      mbar_wait_s(bars + 0, 0);
+      unsigned z = released(read_general(c0 - 1, ring, XLfull));
+      issue_general(c0 - 1 + NST, ring + z, bars + z);
+      mbar_wait_s(bars + 8, 0);
+      z = released(read_general(c0, ring + C::STAGE, X));
+      issue_general(c0 + NST, ring + C::STAGE + z, bars + 8 + z);
 #pragma unroll
       for (int t = 0; t < N1; ++t) tL[t] = XLfull[P * N1 + t];
       if ((cur.y & 3) == 2) MarchMath<P, 1>::x_moment_lo(tab, XLfull, dL);
       else MarchMath<P, 0>::x_moment_lo(tab, XLfull, dL);
     }
 
-    int slot_r = 2 % NST;                       // slot of column c+1
-    unsigned par_r = (2 / NST) & 1;             // its phase parity
-    const size_t ycol = (size_t)a.ny * NF;      // doubles per column
+    // ---- steady-state bookkeeping, all incremental ----
+    int slot = 2 % NST;                               // slot of column c+1
+    unsigned stage_r = ring + slot * C::STAGE;        // ... its stage
+    unsigned bar_r = bars + 8 * slot;                 // ... its mbarrier
+    unsigned par_r = (2 / NST) & 1;                   // ... its phase parity
+    // columns k <= k_plain are issued / read by the short forms below
+    const int k_plain = min(c1, a.nx - 1) - (P == 2 ? 1 : 0);
+    const char* src_i = xb + (size_t)(c0 + 1 + NST) * colbytes + (size_t)jlo * CB;  // chunk of column c+1+NST
+    [[maybe_unused]] const unsigned tog = (P == 2 && (a.ny & 1)) ? 8u : 0u;  // sh alternates when ny is odd
+    [[maybe_unused]] unsigned sh_r = 0, sh_i = 0, shy = 0;
+    if constexpr (P == 2) {
+      sh_r = (unsigned)((reinterpret_cast<uintptr_t>(xb) + (size_t)(c0 + 1) * colbytes + (size_t)jlo * CB) & 15u);
+      sh_i = (unsigned)(reinterpret_cast<uintptr_t>(src_i) & 15u);
+    }
+    [[maybe_unused]] int trow = 0;
+    if constexpr (C::TENSOR) trow = (int)((int64_t)(c0 + 1 + NST) * a.ny + (j0 - 1));
+    const unsigned own = (unsigned)lane * CB + (P == 2 ? 8u * rel0 : 0u);
+    const unsigned dst_off = P == 2 ? rel0 * 80u : (C::TENSOR ? 0u : rel0 * (unsigned)CB);
+    const size_t ycol = (size_t)a.ny * NF;  // doubles per column
     double* yp = a.y + (size_t)c0 * ycol + (size_t)j * NF;
-    [[maybe_unused]] int obsel = 0;
+    [[maybe_unused]] char* gstrip = reinterpret_cast<char*>(a.y) + ((size_t)c0 * a.ny + j0) * CB;
+    if constexpr (P == 2) shy = (unsigned)(reinterpret_cast<uintptr_t>(gstrip) & 15u);
+    [[maybe_unused]] unsigned ob = obuf;
 
     for (int c = c0; c < c1; ++c) {
       double XR[NF];
-      wait_slot(slot_r, par_r);
-      read_cell(c + 1, slot_r, XR);
-      __syncwarp();  // every lane has its cell: the slot can be refilled
-      issue(c + 1 + NST, slot_r);
-      if (++slot_r == NST) {
-        slot_r = 0;
+      unsigned h = 0;
+      mbar_wait_s(bar_r, par_r);
+      if (c + 1 <= k_plain) {
+        if constexpr (C::TENSOR) {
+          const unsigned p = stage_r + own;
+          const unsigned m = (unsigned)(lane & 7) << 4;
+#pragma unroll
+          for (int q = 0; q < NF / 2; ++q) {
+            const double2 t = lds_v2(p + ((16u * q) ^ m));
+            XR[2 * q] = t.x;
+            XR[2 * q + 1] = t.y;
+            h ^= hi32(t.x);
+          }
+        } else if constexpr (P == 2) {
+          const unsigned p = stage_r + own + sh_r;
+#pragma unroll
+          for (int q = 0; q < NF; ++q) {
+            XR[q] = lds_f64(p + 8 * q);
+            h ^= hi32(XR[q]);
+          }
+        } else {
+          const unsigned p = stage_r + own;
+#pragma unroll
+          for (int q = 0; q < NF / 2; ++q) {
+            const double2 t = lds_v2(p + 16 * q);
+            XR[2 * q] = t.x;
+            XR[2 * q + 1] = t.y;
+            h ^= hi32(t.x);
+          }
+        }
+      } else {
+        h = read_general(c + 1, stage_r, XR);
+      }
+      {
+        // every lane holds its cell (see "slot release" above): refill the slot
+        const unsigned z = released(h);
+        const unsigned stage_i = stage_r + z, bar_i = bar_r + z;
+        if (c + 1 + NST <= k_plain) {
+          if (lane == 0) {
+            if constexpr (C::TENSOR) {
+              mbar_expect_tx_s(bar_i, (unsigned)C::STAGE);
+              tensor2d_load_s(stage_i, &tmx, 0, trow, bar_i);
+            } else if constexpr (P == 2) {
+              const unsigned bytes = (sh_i + nbytes + 15u) & ~15u;
+              mbar_expect_tx_s(bar_i, bytes);
+              bulk_load_s(stage_i + dst_off, src_i - sh_i, bytes, bar_i);
+            } else {
+              mbar_expect_tx_s(bar_i, nbytes);
+              bulk_load_s(stage_i + dst_off, src_i, nbytes, bar_i);
+            }
+          }
+        } else {
+          issue_general(c + 1 + NST, stage_i, bar_i);
+        }
+      }
+      src_i += colbytes;
+      if constexpr (P == 2) {
+        sh_r ^= tog;
+        sh_i ^= tog;
+      }
+      if constexpr (C::TENSOR) trow += a.ny;
+      if (++slot == NST) {
+        slot = 0;
+        stage_r = ring;
+        bar_r = bars;
         par_r ^= 1;
+      } else {
+        stage_r += C::STAGE;
+        bar_r += 8;
       }
 
       const int ph = cur.y & 3;
@@ -414,47 +549,42 @@ ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const 
             for (int q = 0; q < NF; q += 4) st_global_v4(yp + q, out[q], out[q + 1], out[q + 2], out[q + 3]);
           }
         } else {
-          // P = 2: stage the strip's results, one bulk store per column.  The gmem range is
-          // [first stored cell, one past the last stored cell) of the strip; head / tail
-          // doubles that do not fill a 16-byte unit go out as plain stores.
-          char* ob = obuf + obsel * C::OUTB;
-          obsel ^= 1;
+          // P = 2: stage the strip's results, one bulk store per column.  The stored byte
+          // range of the strip is [b0, b1); a head / tail double that does not fill a
+          // 16-byte unit is written by the lane that owns it.
+          const int f = cur.y;
+          const unsigned b0 = (f & 4) ? CB : 0u;
+          const unsigned b1 = (unsigned)(jhi_out - j0) * CB - ((f & 8) ? CB : 0u);
+          const bool any = b1 > b0;
+          const unsigned head = any ? (shy + b0) & 8u : 0u, tail = any ? (shy + b1) & 8u : 0u;
           if (lane == 0) tma_store_wait_read<1>();  // the buffer used two columns ago is drained
           __syncwarp();
-          char* const gstrip = reinterpret_cast<char*>(a.y) + ((size_t)c * colcells + j0) * CB;
-          const unsigned shy = (unsigned)(reinterpret_cast<uintptr_t>(gstrip) & 15u);
           if (outlane) {
-            double* o = reinterpret_cast<double*>(ob + shy + (lane - 1) * CB);
+            const unsigned o = ob + shy + (lane - 1) * CB;
 #pragma unroll
-            for (int q = 0; q < NF; ++q) o[q] = out[q];
+            for (int q = 0; q < NF; ++q) sts_f64(o + 8 * q, out[q]);
+            if (head && (unsigned)(lane - 1) * CB == b0) yp[0] = out[0];
+            if (tail && (unsigned)lane * CB == b1) yp[NF - 1] = out[NF - 1];
           }
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
-            const int f = cur.y;
-            unsigned b0 = (f & 4) ? CB : 0u;
-            unsigned b1 = (unsigned)(jhi_out - j0) * CB - ((f & 8) ? CB : 0u);
-            if (b1 > b0) {
-              if ((shy + b0) & 8u) {
-                *reinterpret_cast<double*>(gstrip + b0) = *reinterpret_cast<const double*>(ob + shy + b0);
-                b0 += 8;
-              }
-              if ((shy + b1) & 8u) {
-                b1 -= 8;
-                *reinterpret_cast<double*>(gstrip + b1) = *reinterpret_cast<const double*>(ob + shy + b1);
-              }
-              if (b1 > b0) tma_bulk_store(gstrip + b0, ob + shy + b0, b1 - b0);
-            }
+            const unsigned s0 = b0 + head, s1 = b1 - tail;
+            if (any && s1 > s0) bulk_store_s(gstrip + s0, ob + shy + s0, s1 - s0);
             tma_store_commit();
           }
+          ob = (ob == obuf) ? obuf + C::OUTB : obuf;
         }
       }
       yp += ycol;
+      if constexpr (P == 2) {
+        gstrip += colbytes;
+        shy ^= tog;
+      }
 
       // next column: its run, and the left-neighbour traces it needs from this column
       if (c + 1 >= cur.x) {
-        cur = nxt;
-        nxt = *(++rp + 1);
+        cur = ld_run(++rp);
         store = store_flag(cur.y);
       }
 #pragma unroll
