@@ -102,9 +102,8 @@ int64_t stefan_ipdg_ndofs(const stefan_ipdg* h);
 /* y = A x (replaces sparse_operator(sysmatrix, mesh, 1) * x).  x_lo / x_hi: the
  * neighbouring slabs' adjacent cell columns (ny*NF doubles each; local or peer
  * device memory), required iff the handle has phase_lo / phase_hi.
- * algo 0 = production kernel (order 1: TMA bulk-copy streaming kernel; orders 2, 3:
- * cp.async streaming kernel), 1 = simple one-thread-per-cell kernel, 2 = cp.async
- * streaming kernel for every order. */
+ * algo 0 = production kernel (TMA march kernel, csrc/ipdg_march.cuh), 1 = simple
+ * one-thread-per-cell kernel (independent second opinion used by the tests). */
 int stefan_ipdg_apply(stefan_ipdg* h, const double* x, double* y, const double* x_lo,
                       const double* x_hi, int32_t algo, void* stream);
 

@@ -37,18 +37,20 @@
 // bank operands of the DFMAs); the loop body exists once per phase.
 #pragma once
 
+#include <type_traits>
+
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched at run time)
 
 namespace stefan {
 
 #ifndef MARCH_NST1
-#define MARCH_NST1 6
+#define MARCH_NST1 2
 #endif
 #ifndef MARCH_NST2
-#define MARCH_NST2 4
+#define MARCH_NST2 2
 #endif
 #ifndef MARCH_NST3
-#define MARCH_NST3 4
+#define MARCH_NST3 2
 #endif
 #ifndef MARCH_WARPS1
 #define MARCH_WARPS1 8
@@ -57,7 +59,7 @@ namespace stefan {
 #define MARCH_WARPS2 16
 #endif
 #ifndef MARCH_WARPS3
-#define MARCH_WARPS3 12
+#define MARCH_WARPS3 8
 #endif
 #ifndef MARCH_MINB1
 #define MARCH_MINB1 2
@@ -91,6 +93,9 @@ struct MarchCfg<3> {
   static constexpr bool TENSOR = true;
 };
 
+// SegTab (ipdg_handle.h): one entry per CTA, {strip group, first column, one past the last
+// column, -}, built by the host so that every CTA gets the same COST rather than the same
+// column count (columns where a strip mixes phases run both phase bodies).
 template <int P>
 struct MarchSmem {
   using C = MarchCfg<P>;
@@ -244,18 +249,20 @@ __device__ __forceinline__ void bulk_store_s(void* gdst, unsigned ssrc, unsigned
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes)
                : "memory");
 }
-// (end column, flag) of a run, loaded only when a run ends (an ordinary load would be
-// hoisted out of the rare branch and every iteration would wait for it)
-__device__ __forceinline__ int2 ld_run(const int2* p) {
-  int2 v;
-  asm volatile("ld.global.nc.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+// A run {end column, mode, phase mask, store mask}, loaded only when a run ends (an
+// ordinary load would be hoisted out of the rare branch and every iteration would wait
+// for it); the kernel keeps one run of look-ahead so the load is never waited for.
+__device__ __forceinline__ int4 ld_run(const int4* p) {
+  int4 v;
+  asm volatile("ld.global.nc.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
 }
 
 template <int P>
 __global__ void __launch_bounds__(MarchCfg<P>::WARPS * 32, MarchCfg<P>::MINB)
-ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const int2* __restrict__ runs,
-                 const int* __restrict__ run_ofs, const __grid_constant__ CUtensorMap tmx) {
+ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const int4* __restrict__ runs,
+                 const int* __restrict__ run_ofs, const __grid_constant__ CUtensorMap tmx,
+                 const __grid_constant__ SegTab segs) {
   using C = MarchCfg<P>;
   constexpr int N1 = P + 1;
   constexpr int NF = N1 * N1;
@@ -280,17 +287,13 @@ ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const 
   __syncwarp();
 
   const int nstrips = (a.ny + kStripCells - 1) / kStripCells;
-  const int ngroups = (nstrips + C::WARPS - 1) / C::WARPS;
-  const int group = blockIdx.x % ngroups;
-  const int seg = blockIdx.x / ngroups;
+  const int4 myseg = segs.e[blockIdx.x];
+  const int group = myseg.x;
   const int strip = group * C::WARPS + warp;
-  const int c0 = a.cbeg + (int)((int64_t)(a.cend - a.cbeg) * seg / a.nseg);
-  const int c1 = a.cbeg + (int)((int64_t)(a.cend - a.cbeg) * (seg + 1) / a.nseg);
+  const int c0 = myseg.y, c1 = myseg.z;
   if (strip < nstrips && c0 < c1) {
     const int j0 = strip * kStripCells;
-    const int jhi_out = min(j0 + kStripCells, a.ny);  // one past the strip's top output cell
     const int j = j0 - 1 + lane;                      // this lane's cell
-    const bool outlane = lane >= 1 && lane <= kStripCells && j < a.ny;
     const int jlo = max(j0 - 1, 0), jhi = min(j0 + kStripCells + 1, a.ny);
     const int rel0 = jlo - (j0 - 1);  // lane of the first staged cell (0, or 1 in strip 0)
     const unsigned nbytes = (unsigned)(jhi - jlo) * CB;  // bytes of one column chunk
@@ -390,16 +393,16 @@ ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const 
     };
     auto released = [&](unsigned h) -> unsigned { return __reduce_xor_sync(0xffffffffu, h) & a.zero; };
 
-    // run list of this strip: (end column, flag); flag & 3 = phase code all cells are
-    // treated as (0: the column is left to the tail), bit 2 / bit 3 = the bottom / top
-    // cell of the strip is an exception and is not stored
-    const int2* rp = runs + run_ofs[strip];
-    int2 cur = ld_run(rp);
+    // run list of this strip (built by stefan_ipdg_create): {end column, mode, phase mask,
+    // store mask}.  Bit `lane` of the store mask: this lane's cell is interior-uniform and
+    // is stored by the loop; of the phase mask: it has phase code 2.  mode & 3: 0 nothing
+    // to store, 1 / 2 every stored cell has phase code 1 / 2, 3 both occur (both phase
+    // bodies run, each storing its own lanes); mode & 4: the stored lanes are contiguous.
+    const int4* rp = runs + run_ofs[strip];
+    int4 cur = ld_run(rp);
     while (cur.x <= c0) cur = ld_run(++rp);
-    auto store_flag = [&](int f) {
-      return outlane && (f & 3) != 0 && !((f & 4) && lane == 1) && !((f & 8) && j == jhi_out - 1);
-    };
-    bool store = store_flag(cur.y);
+    int4 nxt = ld_run(rp + 1);
+    bool mine1 = (cur.z >> lane) & 1;  // this lane's cell has phase code 2
 
     // prologue: columns c0-1 .. c0+NST-2 into slots 0 .. NST-1
 #pragma unroll
@@ -415,8 +418,11 @@ ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const 
       issue_general(c0 + NST, ring + C::STAGE + z, bars + 8 + z);
 #pragma unroll
       for (int t = 0; t < N1; ++t) tL[t] = XLfull[P * N1 + t];
-      if ((cur.y & 3) == 2) MarchMath<P, 1>::x_moment_lo(tab, XLfull, dL);
-      else MarchMath<P, 0>::x_moment_lo(tab, XLfull, dL);
+      double d1[N1];
+      MarchMath<P, 0>::x_moment_lo(tab, XLfull, dL);
+      MarchMath<P, 1>::x_moment_lo(tab, XLfull, d1);
+#pragma unroll
+      for (int t = 0; t < N1; ++t) dL[t] = mine1 ? d1[t] : dL[t];
     }
 
     // ---- steady-state bookkeeping, all incremental ----
@@ -443,40 +449,42 @@ ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const 
     if constexpr (P == 2) shy = (unsigned)(reinterpret_cast<uintptr_t>(gstrip) & 15u);
     [[maybe_unused]] unsigned ob = obuf;
 
-    for (int c = c0; c < c1; ++c) {
-      double XR[NF];
-      unsigned h = 0;
+    // One column: Xc = column c (in registers), Xn receives column c+1.  The callers
+    // alternate the two arrays, so no register copies are needed between columns.
+    auto column = [&](int c, double* __restrict__ Xc, double* __restrict__ Xn) {
       mbar_wait_s(bar_r, par_r);
-      if (c + 1 <= k_plain) {
-        if constexpr (C::TENSOR) {
-          const unsigned p = stage_r + own;
-          const unsigned m = (unsigned)(lane & 7) << 4;
+      // where this lane's cell of column c+1 sits: plain columns differ from halo columns
+      // only in the swizzle mask (P = 3) / the 8-byte shift (P = 2)
+      unsigned p = stage_r + own, m = 0, h = 0;
+      const bool plain = c + 1 <= k_plain;
+      if constexpr (C::TENSOR) m = (plain || c + 1 < a.nx) ? (unsigned)(lane & 7) << 4 : 0u;
+      if constexpr (P == 2) {
+        p += sh_r;
+        if (!plain) {
+          const char* src = col_base(c + 1);
+          p = stage_r + own + (unsigned)(reinterpret_cast<uintptr_t>(src) & 15u);
+        }
+      }
+      if constexpr (P == 2) {
 #pragma unroll
-          for (int q = 0; q < NF / 2; ++q) {
-            const double2 t = lds_v2(p + ((16u * q) ^ m));
-            XR[2 * q] = t.x;
-            XR[2 * q + 1] = t.y;
-            h ^= hi32(t.x);
-          }
-        } else if constexpr (P == 2) {
-          const unsigned p = stage_r + own + sh_r;
-#pragma unroll
-          for (int q = 0; q < NF; ++q) {
-            XR[q] = lds_f64(p + 8 * q);
-            h ^= hi32(XR[q]);
-          }
-        } else {
-          const unsigned p = stage_r + own;
-#pragma unroll
-          for (int q = 0; q < NF / 2; ++q) {
-            const double2 t = lds_v2(p + 16 * q);
-            XR[2 * q] = t.x;
-            XR[2 * q + 1] = t.y;
-            h ^= hi32(t.x);
-          }
+        for (int q = 0; q < NF; ++q) {
+          Xn[q] = lds_f64(p + 8 * q);
+          h ^= hi32(Xn[q]);
+        }
+        if (!plain && chunk_is_array_end(c + 1) && j == a.ny - 1) {
+          const char* src = col_base(c + 1);
+          // (sh + nbytes) was 8 mod 16: the copy stopped 8 bytes short of the array end
+          if (src != nullptr && (((unsigned)(reinterpret_cast<uintptr_t>(src) & 15u) + nbytes) & 8u))
+            Xn[NF - 1] = *reinterpret_cast<const double*>(src + nbytes - 8);
         }
       } else {
-        h = read_general(c + 1, stage_r, XR);
+#pragma unroll
+        for (int q = 0; q < NF / 2; ++q) {
+          const double2 t = lds_v2(p + ((16u * q) ^ m));
+          Xn[2 * q] = t.x;
+          Xn[2 * q + 1] = t.y;
+          h ^= hi32(t.x);
+        }
       }
       {
         // every lane holds its cell (see "slot release" above): refill the slot
@@ -516,65 +524,76 @@ ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const 
         bar_r += 8;
       }
 
-      const int ph = cur.y & 3;
-      if (ph != 0) {
+      // the arithmetic, once per phase (compile-time table offsets)
+      auto body = [&](auto phase_c) {
+        constexpr int S = decltype(phase_c)::value;
+        // lanes this body stores: the interior-uniform cells of phase index S
+        const unsigned ms = S ? ((unsigned)cur.w & (unsigned)cur.z) : ((unsigned)cur.w & ~(unsigned)cur.z);
+        const bool st = (ms >> lane) & 1;
+        using M = MarchMath<P, S>;
         double out[NF];
         double tR[N1], dR[N1], sU[N1], sD[N1], tD[N1], dD[N1], tU[N1], dU[N1];
 #pragma unroll
-        for (int t = 0; t < N1; ++t) tR[t] = XR[0 * N1 + t];
-        if (ph == 1) {
-          MarchMath<P, 0>::x_moment_hi(tab, XR, dR);
-          MarchMath<P, 0>::y_moment_lo(tab, X, sU);
-          MarchMath<P, 0>::y_moment_hi(tab, X, sD);
-        } else {
-          MarchMath<P, 1>::x_moment_hi(tab, XR, dR);
-          MarchMath<P, 1>::y_moment_lo(tab, X, sU);
-          MarchMath<P, 1>::y_moment_hi(tab, X, sD);
-        }
+        for (int t = 0; t < N1; ++t) tR[t] = Xn[0 * N1 + t];
+        M::x_moment_hi(tab, Xn, dR);
+        M::y_moment_lo(tab, Xc, sU);
+        M::y_moment_hi(tab, Xc, sD);
 #pragma unroll
         for (int t = 0; t < N1; ++t) {
           // from the cell below (lane - 1): its top trace and its moment for the cell above it
-          tD[t] = __shfl_up_sync(0xffffffffu, X[t * N1 + P], 1);
+          tD[t] = __shfl_up_sync(0xffffffffu, Xc[t * N1 + P], 1);
           dD[t] = __shfl_up_sync(0xffffffffu, sU[t], 1);
           // from the cell above (lane + 1)
-          tU[t] = __shfl_down_sync(0xffffffffu, X[t * N1 + 0], 1);
+          tU[t] = __shfl_down_sync(0xffffffffu, Xc[t * N1 + 0], 1);
           dU[t] = __shfl_down_sync(0xffffffffu, sD[t], 1);
         }
-        if (ph == 1) MarchMath<P, 0>::rows(tab, X, tL, dL, tR, dR, tD, dD, tU, dU, out);
-        else MarchMath<P, 1>::rows(tab, X, tL, dL, tR, dR, tD, dD, tU, dU, out);
+        M::rows(tab, Xc, tL, dL, tR, dR, tD, dD, tU, dU, out);
 
         if constexpr (C::OUTB == 0) {
-          if (store) {
+          if (st) {
 #pragma unroll
             for (int q = 0; q < NF; q += 4) st_global_v4(yp + q, out[q], out[q + 1], out[q + 2], out[q + 3]);
           }
-        } else {
-          // P = 2: stage the strip's results, one bulk store per column.  The stored byte
-          // range of the strip is [b0, b1); a head / tail double that does not fill a
-          // 16-byte unit is written by the lane that owns it.
-          const int f = cur.y;
-          const unsigned b0 = (f & 4) ? CB : 0u;
-          const unsigned b1 = (unsigned)(jhi_out - j0) * CB - ((f & 8) ? CB : 0u);
-          const bool any = b1 > b0;
-          const unsigned head = any ? (shy + b0) & 8u : 0u, tail = any ? (shy + b1) & 8u : 0u;
+        } else if (ms != 0 && (((ms >> (__ffs(ms) - 1)) + 1) & (ms >> (__ffs(ms) - 1))) == 0) {
+          // P = 2, contiguous stored lanes [l0, l1): stage the results, one bulk store per
+          // column.  The stored byte range of the strip is [b0, b1); a head / tail double
+          // that does not fill a 16-byte unit is written by the lane that owns it.
+          const unsigned l0 = __ffs(ms) - 1, l1 = 32 - __clz(ms);
+          const unsigned b0 = (l0 - 1) * CB, b1 = (l1 - 1) * CB;
+          const unsigned head = (shy + b0) & 8u, tail = (shy + b1) & 8u;
           if (lane == 0) tma_store_wait_read<1>();  // the buffer used two columns ago is drained
           __syncwarp();
-          if (outlane) {
+          if (st) {
             const unsigned o = ob + shy + (lane - 1) * CB;
 #pragma unroll
             for (int q = 0; q < NF; ++q) sts_f64(o + 8 * q, out[q]);
-            if (head && (unsigned)(lane - 1) * CB == b0) yp[0] = out[0];
-            if (tail && (unsigned)lane * CB == b1) yp[NF - 1] = out[NF - 1];
+            if (head && (unsigned)lane == l0) yp[0] = out[0];
+            if (tail && (unsigned)lane + 1 == l1) yp[NF - 1] = out[NF - 1];
           }
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
             const unsigned s0 = b0 + head, s1 = b1 - tail;
-            if (any && s1 > s0) bulk_store_s(gstrip + s0, ob + shy + s0, s1 - s0);
+            if (s1 > s0) bulk_store_s(gstrip + s0, ob + shy + s0, s1 - s0);
             tma_store_commit();
           }
           ob = (ob == obuf) ? obuf + C::OUTB : obuf;
+        } else {
+          // P = 2, stored lanes with holes (rare): plain stores
+          if (st) {
+#pragma unroll
+            for (int q = 0; q < NF; ++q) yp[q] = out[q];
+          }
         }
+      };
+      const int ph = cur.y & 3;
+      if (ph == 1) {
+        body(std::integral_constant<int, 0>{});
+      } else if (ph == 2) {
+        body(std::integral_constant<int, 1>{});
+      } else if (ph == 3) {
+        body(std::integral_constant<int, 0>{});
+        body(std::integral_constant<int, 1>{});
       }
       yp += ycol;
       if constexpr (P == 2) {
@@ -584,16 +603,33 @@ ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const 
 
       // next column: its run, and the left-neighbour traces it needs from this column
       if (c + 1 >= cur.x) {
-        cur = ld_run(++rp);
-        store = store_flag(cur.y);
+        cur = nxt;
+        nxt = ld_run(++rp + 1);
+        mine1 = (cur.z >> lane) & 1;
       }
 #pragma unroll
-      for (int t = 0; t < N1; ++t) tL[t] = X[P * N1 + t];
-      if ((cur.y & 3) == 2) MarchMath<P, 1>::x_moment_lo(tab, X, dL);
-      else MarchMath<P, 0>::x_moment_lo(tab, X, dL);
+      for (int t = 0; t < N1; ++t) tL[t] = Xc[P * N1 + t];
+      const int phn = cur.y & 3;
+      if (phn == 1) {
+        MarchMath<P, 0>::x_moment_lo(tab, Xc, dL);
+      } else if (phn == 2) {
+        MarchMath<P, 1>::x_moment_lo(tab, Xc, dL);
+      } else if (phn == 3) {
+        double d1[N1];
+        MarchMath<P, 0>::x_moment_lo(tab, Xc, dL);
+        MarchMath<P, 1>::x_moment_lo(tab, Xc, d1);
 #pragma unroll
-      for (int q = 0; q < NF; ++q) X[q] = XR[q];
+        for (int t = 0; t < N1; ++t) dL[t] = mine1 ? d1[t] : dL[t];
+      }
+    };
+
+    double Y[NF];  // the second cell buffer
+    int c = c0;
+    for (; c + 1 < c1; c += 2) {
+      column(c, X, Y);
+      column(c + 1, Y, X);
     }
+    if (c < c1) column(c, X, Y);
     if constexpr (C::OUTB != 0) {
       if (lane == 0) tma_store_wait_read<0>();
       __syncwarp();

@@ -227,7 +227,8 @@ def _stream_ptr(stream=None):
 class IPOperator:
     """Matrix-free `sparse_operator` of an interior-penalty system on one GPU."""
 
-    STREAM, SIMPLE = 0, 1
+    MARCH, SIMPLE = 0, 1
+    STREAM = MARCH  # former name
 
     def __init__(self, mesh, order, numqp, k1, k2, penalty, lam=0.0, Tm=0.0,
                  variant="current", terms=None, phase_lo=None, phase_hi=None):

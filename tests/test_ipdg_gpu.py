@@ -32,14 +32,12 @@ def _case(order, nx, ny, two_phase, terms, variant, lam=1.5):
 
 
 @pytest.mark.parametrize("order", [1, 2, 3])
-@pytest.mark.parametrize("algo", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("algo", [0, 1])
 @pytest.mark.parametrize("nx,ny", [(3, 3), (7, 6), (17, 33), (40, 95)])
 @pytest.mark.parametrize("two_phase,terms,variant", [
     (False, REFSYS, "current"), (False, REFSYS, "legacy_boundary"),
     (True, ALL, "current"), (True, REFSYS, "current")])
 def test_apply_matches_oracle(cuda, order, algo, nx, ny, two_phase, terms, variant):
-    if algo == 3 and order != 1:
-        pytest.skip("algo 3 is the order-1 bulk-copy kernel")
     A, op, x, xd = _case(order, nx, ny, two_phase, terms, variant)
     y = op.apply(xd, algo=algo).cpu().numpy()
     yr = A @ x
@@ -48,7 +46,7 @@ def test_apply_matches_oracle(cuda, order, algo, nx, ny, two_phase, terms, varia
 
 
 @pytest.mark.parametrize("order", [1, 2, 3])
-def test_stream_equals_simple_large(cuda, order):
+def test_march_equals_simple_large(cuda, order):
     """Two independent kernels agree on a mesh with many strips / segments."""
     import torch
     from stefanproblem_b200 import cutcelldg as cc
@@ -62,9 +60,7 @@ def test_stream_equals_simple_large(cuda, order):
     y0 = op.apply(x, algo=0)
     y1 = op.apply(x, algo=1)
     assert torch.equal(y0, y1) or (y0 - y1).norm() / y1.norm() < 1e-15
-    for algo in (2, 4):
-        ya = op.apply(x, algo=algo)
-        assert (ya - y1).norm() / y1.norm() < 1e-15 and (ya - y1).abs().max() / y1.abs().max() < 1e-14
+    assert (y0 - y1).abs().max() / y1.abs().max() < 1e-14
     # symmetry of the operator: x' A z == z' A x
     z = torch.from_numpy(np.random.default_rng(2).uniform(-1, 1, op.ndofs)).cuda()
     a = torch.dot(z, y0)
@@ -144,7 +140,7 @@ def test_column_ranges_compose(cuda, order):
 
 
 @pytest.mark.parametrize("order", [1, 2, 3])
-@pytest.mark.parametrize("algo", [0, 1, 2, 4])
+@pytest.mark.parametrize("algo", [0, 1])
 @pytest.mark.parametrize("nx,ny,cut", [(64, 95, 29), (37, 64, 18), (9, 31, 4)])
 def test_two_slabs_equal_one(cuda, order, algo, nx, ny, cut):
     """Column-slab partition: two slab handles fed each other's edge column reproduce the
