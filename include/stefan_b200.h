@@ -182,6 +182,10 @@ int64_t stefan_ldg_ndofs(const stefan_ldg* h);
  * x_lo / x_hi: the neighbouring slabs' adjacent cell columns (3*ny*NF doubles each). */
 int stefan_ldg_apply(stefan_ldg* h, const double* x, double* y, const double* x_lo,
                      const double* x_hi, void* stream);
+/* Same result from the plain one-thread-per-cell kernel (independent second opinion used by
+ * the tests; not the production path). */
+int stefan_ldg_apply_simple(stefan_ldg* h, const double* x, double* y, const double* x_lo,
+                            const double* x_hi, void* stream);
 
 /* ------------------------------------------------------------------- DG1D
  * 1-D two-phase interior-penalty DG with a Robin interface on a DGMesh1D

@@ -30,7 +30,7 @@ def run(order, nx, ny, two_phase, algo, reps=20):
     print(f"p={order} {nx}x{ny} two_phase={two_phase} algo={algo}: {ms:.3f} ms  {gdofs:.1f} GDOF/s  "
           f"{16 * gdofs:.0f} GB/s  ({16 * gdofs / 6551 * 100:.1f}% of 6551)", flush=True)
 
-def run_ldg(order, n, two_phase, reps=20):
+def run_ldg(order, n, two_phase, reps=20, algo=0):
     basis = cc.LagrangeTensorProductBasis(2, order)
     phase = None
     if two_phase:
@@ -42,17 +42,17 @@ def run_ldg(order, n, two_phase, reps=20):
     x = torch.rand(op.ndofs, dtype=torch.float64, device="cuda") * 2 - 1
     y = torch.empty_like(x)
     for _ in range(3):
-        op.apply(x, out=y)
+        op.apply(x, out=y, algo=algo)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
-        op.apply(x, out=y)
+        op.apply(x, out=y, algo=algo)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     gdofs = op.ndofs / ms / 1e6
-    print(f"LDG p={order} {n}x{n} two_phase={two_phase}: {ms:.4f} ms  {gdofs:.1f} GDOF/s  "
+    print(f"LDG p={order} {n}x{n} two_phase={two_phase} algo={algo}: {ms:.4f} ms  {gdofs:.1f} GDOF/s  "
           f"{16 * gdofs:.0f} GB/s  ({16 * gdofs / 6551 * 100:.1f}% of 6551)", flush=True)
 
 
@@ -72,7 +72,7 @@ if __name__ == "__main__":
     if args.ldg:
         orders = [args.order] if args.order else [1, 2, 3]
         for o in orders:
-            run_ldg(o, args.n or {1: 913, 2: 609, 3: 457}[o], bool(args.two_phase), args.reps)
+            run_ldg(o, args.n or {1: 913, 2: 609, 3: 457}[o], bool(args.two_phase), args.reps, args.algo)
         sys.exit(0)
     if args.order:
         n = args.n or {1: 5000, 2: 3334, 3: 2500}[args.order]

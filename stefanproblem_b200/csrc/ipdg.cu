@@ -34,7 +34,6 @@
 namespace stefan {
 
 
-constexpr int kStripCells = 30;
 
 struct ApplyArgs {
   const double* x;
@@ -123,23 +122,6 @@ __device__ __forceinline__ void fixup_tail(const IpTab<P>& tab, const ApplyArgs&
   }
 }
 
-// --------------------------------------------------------------------------
-// device helpers of the march kernels (ipdg_march.cuh)
-// --------------------------------------------------------------------------
-// 32 bytes per lane in one instruction (STG.256, sm_100): a warp writes whole
-// 32-byte sectors; two STG.128 per lane would send every sector to L2 twice, half
-// filled (measured: L1->XBAR request path 66% busy, 43% of it stores).
-__device__ __forceinline__ void st_global_v4(double* p, double a, double b, double c, double d) {
-  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d)
-               : "memory");
-}
-__device__ __forceinline__ unsigned smem_addr(const void* p) {
-  return (unsigned)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void fence_proxy_async() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-
 }  // namespace stefan
 #include "ipdg_march.cuh"
 namespace stefan {
@@ -183,76 +165,10 @@ static int march_warps(int order) {
   return order == 1 ? MarchCfg<1>::WARPS : order == 2 ? MarchCfg<2>::WARPS : MarchCfg<3>::WARPS;
 }
 
-// Cost-balanced (strip group, column segment) tiles, one per CTA, for columns [cbeg, cend).
-// A CTA is done when its slowest warp is; a warp pays 1 per column plus kMixedCost where its
-// strip mixes phases (both phase bodies run), so
-//     cost(group, [c0, c1)) = (c1 - c0) + kMixedCost * max over the group's strips of
-//                                          #mixed columns of that strip in [c0, c1).
-// Segments are cut greedily at the largest c1 with cost <= T; T is bisected until the tile
-// count fits the CTA budget (one wave).  Cached per column range in the handle.
-constexpr int kMixedCost = 1;
-static const SegCache& build_segments(IpdgHandle* h, int cbeg, int cend, int max_ctas) {
-  for (const SegCache& c : h->seg_cache)
-    if (c.cbeg == cbeg && c.cend == cend && c.max_ctas == max_ctas) return c;
-  const int ng = h->ngroups, nx = h->nx, gw = h->group_warps;
-  const int nstrips = (h->ny + kStripCells - 1) / kStripCells;
-  auto cost = [&](int g, int c0, int c1) {
-    int mx = 0;
-    for (int sidx = g * gw; sidx < std::min(nstrips, (g + 1) * gw); ++sidx) {
-      const int* cum = h->mixed_cum.data() + (size_t)sidx * (nx + 1);
-      mx = std::max(mx, cum[c1] - cum[c0]);
-    }
-    return (c1 - c0) + kMixedCost * mx;
-  };
-  auto cut = [&](int T, std::vector<int4>* tiles) {  // number of tiles with cost <= T each
-    int n = 0;
-    for (int g = 0; g < ng; ++g) {
-      int c0 = cbeg, s = 0;
-      while (c0 < cend) {
-        int lo = c0 + 1, hi = cend;  // largest c1 in (c0, cend] with cost <= T (at least one column)
-        while (lo < hi) {
-          const int mid = (lo + hi + 1) / 2;
-          if (cost(g, c0, mid) <= T) lo = mid;
-          else hi = mid - 1;
-        }
-        if (tiles) tiles->push_back(make_int4(g, c0, lo, s));
-        ++s;
-        ++n;
-        c0 = lo;
-      }
-    }
-    return n;
-  };
-  const int budget = std::max(ng, std::min(max_ctas, kMaxMarchCtas));
-  int lo = 16, hi = (1 + kMixedCost) * (cend - cbeg) + 1;  // segments of cost >= 16
-  lo = std::min(lo, hi);
-  while (lo < hi) {
-    const int mid = (lo + hi) / 2;
-    if (cut(mid, nullptr) <= budget) hi = mid;
-    else lo = mid + 1;
-  }
-  std::vector<int4> tiles;
-  cut(lo, &tiles);
-  // CTA order: segment-major = CTAs with neighbouring block indices work on neighbouring
-  // strips of the same columns
-  std::stable_sort(tiles.begin(), tiles.end(), [](const int4& a, const int4& b) { return a.w < b.w; });
-  SegCache c;
-  c.cbeg = cbeg;
-  c.cend = cend;
-  c.max_ctas = max_ctas;
-  c.n = (int)std::min<size_t>(tiles.size(), kMaxMarchCtas);
-  std::memset(&c.tab, 0, sizeof(c.tab));
-  for (int k = 0; k < c.n; ++k) c.tab.e[k] = tiles[k];
-  if ((int)tiles.size() > kMaxMarchCtas) c.n = -1;
-  if (h->seg_cache.size() >= 8) h->seg_cache.erase(h->seg_cache.begin());
-  h->seg_cache.push_back(c);
-  return h->seg_cache.back();
-}
-
 template <int P>
 static int launch_march(IpdgHandle* h, const IpTab<P>& tab, const ApplyArgs& args, cudaStream_t st) {
   using C = MarchCfg<P>;
-  const SegCache& sc = build_segments(h, args.cbeg, args.cend, sm_count() * C::MINB);
+  const SegCache& sc = h->plan.segments(args.cbeg, args.cend, sm_count() * C::MINB);
   const SegTab& segs = sc.tab;
   const int grid = sc.n;
   if (grid <= 0) return fail(ST_UNSUPPORTED, "stefan_ipdg_apply: more than %d strip groups (ny too large)", kMaxMarchCtas);
@@ -268,7 +184,7 @@ static int launch_march(IpdgHandle* h, const IpTab<P>& tab, const ApplyArgs& arg
     int rc = make_cell_tensor_map(args.x, (int64_t)h->nx * h->ny, &tm);
     if (rc) return rc;
   }
-  ipdg_apply_march<P><<<grid, C::WARPS * 32, smem, st>>>(tab, args, h->runs_dev, h->run_ofs_dev, tm, segs);
+  ipdg_apply_march<P><<<grid, C::WARPS * 32, smem, st>>>(tab, args, h->plan.runs_dev, h->plan.run_ofs_dev, tm, segs);
   return ST_OK;
 }
 
@@ -286,8 +202,8 @@ static int launch_apply(IpdgHandle* h, const ApplyArgs& args0, int algo, cudaStr
     return ST_OK;
   }
   // exception cells of the produced columns (the list is sorted by column)
-  args.fix = h->fix_dev + h->fix_col_ofs[args.cbeg];
-  args.nfix = h->fix_col_ofs[args.cend] - h->fix_col_ofs[args.cbeg];
+  args.fix = h->plan.fix_dev + h->plan.fix_col_ofs[args.cbeg];
+  args.nfix = h->plan.fix_col_ofs[args.cend] - h->plan.fix_col_ofs[args.cbeg];
   // CTA = (group of adjacent strips, x segment); one wave of MINB CTAs per SM
   int rc = launch_march<P>(h, tab, args, st);
   if (rc) return rc;
@@ -330,12 +246,8 @@ int stefan_ipdg_create(const stefan_ipdg_params* p, const int8_t* phase, const i
   h->has_lo = phase_lo != nullptr;
   h->has_hi = phase_hi != nullptr;
   h->phase_dev = nullptr;
-  h->fix_dev = nullptr;
-  h->nfix = 0;
-  h->runs_dev = nullptr;
   h->xh_dev = h->yh_dev = nullptr;
   h->host_ready = false;
-  h->run_ofs_dev = nullptr;
   h->tab_host = nullptr;
   const int NF = (p->order + 1) * (p->order + 1);
   h->ndofs = (int64_t)p->nx * p->ny * NF;
@@ -361,84 +273,14 @@ int stefan_ipdg_create(const stefan_ipdg_params* p, const int8_t* phase, const i
     if (phase_lo) ph[(size_t)0 * (p->ny + 2) + (j + 1)] = (phase_lo[j] == 1) ? 1 : 2;
     if (phase_hi) ph[(size_t)(p->nx + 1) * (p->ny + 2) + (j + 1)] = (phase_hi[j] == 1) ? 1 : 2;
   }
-  // What the march kernels do per (strip, column): a run list per strip.  A cell is
-  // "interior-uniform" iff its four neighbours exist and have its own phase; those are the
-  // cells the loop stores (bit `lane` of storemask; lane = j - j0 + 1), every other cell
-  // goes to the fix list.  mode: 0 nothing to store, 1 / 2 all stored cells are of phase
-  // code 1 / 2, 3 both occur (the loop then runs both phase bodies); bit 2: the stored
-  // lanes are contiguous (order 2 writes them with one bulk store).
-  const int nstrips = (p->ny + kStripCells - 1) / kStripCells;
-  std::vector<int32_t> fix;
   if ((int64_t)p->nx * p->ny >= (int64_t)INT32_MAX) {
     delete h;
     return fail(ST_UNSUPPORTED, "stefan_ipdg_create: more than 2^31 cells per slab");
   }
-  std::vector<int4> runs;
-  std::vector<int> run_ofs(nstrips);
-  {
-    const int ld = p->ny + 2;
-    std::vector<uint32_t> smask((size_t)nstrips * p->nx), pmask((size_t)nstrips * p->nx);
-    for (int i = 0; i < p->nx; ++i) {
-      const int8_t* col = ph.data() + (size_t)(i + 1) * ld + 1;
-      for (int j = 0; j < p->ny; ++j) {
-        const int8_t s = col[j];
-        const bool uniform = col[j - 1] == s && col[j + 1] == s && col[j - ld] == s && col[j + ld] == s;
-        const int sidx = j / kStripCells, lane = j - sidx * kStripCells + 1;
-        if (uniform) {
-          smask[(size_t)sidx * p->nx + i] |= 1u << lane;
-          if (s == 2) pmask[(size_t)sidx * p->nx + i] |= 1u << lane;
-        } else {
-          fix.push_back((int32_t)((int64_t)i * p->ny + j));
-        }
-      }
-    }
-    for (int sidx = 0; sidx < nstrips; ++sidx) {
-      run_ofs[sidx] = (int)runs.size();
-      const uint32_t* sm = smask.data() + (size_t)sidx * p->nx;
-      const uint32_t* pm = pmask.data() + (size_t)sidx * p->nx;
-      auto mode_of = [&](int i) {
-        if (sm[i] == 0) return 0;
-        int m = pm[i] == 0 ? 1 : (pm[i] == sm[i] ? 2 : 3);
-        const uint32_t t = sm[i] >> __builtin_ctz(sm[i]);
-        if ((t & (t + 1)) == 0) m |= 4;
-        return m;
-      };
-      for (int i = 0; i < p->nx;) {
-        int e = i + 1;
-        while (e < p->nx && sm[e] == sm[i] && pm[e] == pm[i]) ++e;
-        runs.push_back(make_int4(e, mode_of(i), (int)pm[i], (int)sm[i]));
-        i = e;
-      }
-      for (int k = 0; k < 3; ++k) runs.push_back(make_int4(INT32_MAX, 0, 0, 0));  // sentinels
-    }
-    // per strip: running count of the columns where it mixes phases (see build_segments)
-    h->group_warps = march_warps(p->order);
-    h->ngroups = (nstrips + h->group_warps - 1) / h->group_warps;
-    h->mixed_cum.assign((size_t)nstrips * (p->nx + 1), 0);
-    for (int sidx = 0; sidx < nstrips; ++sidx) {
-      int* cum = h->mixed_cum.data() + (size_t)sidx * (p->nx + 1);
-      for (int i = 0; i < p->nx; ++i) {
-        const uint32_t sm_ = smask[(size_t)sidx * p->nx + i], pm_ = pmask[(size_t)sidx * p->nx + i];
-        cum[i + 1] = cum[i] + ((sm_ != 0 && pm_ != 0 && pm_ != sm_) ? 1 : 0);
-      }
-    }
-  }
-  h->nfix = (int)fix.size();
-  h->fix_col_ofs.assign(p->nx + 1, 0);
-  for (int32_t cell : fix) h->fix_col_ofs[cell / p->ny + 1]++;
-  for (int i = 0; i < p->nx; ++i) h->fix_col_ofs[i + 1] += h->fix_col_ofs[i];
   cudaError_t e = cudaMalloc(&h->phase_dev, pn);
   if (e == cudaSuccess) e = cudaMemcpy(h->phase_dev, ph.data(), pn, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMalloc(&h->runs_dev, runs.size() * sizeof(int4));
-  if (e == cudaSuccess)
-    e = cudaMemcpy(h->runs_dev, runs.data(), runs.size() * sizeof(int4), cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMalloc(&h->run_ofs_dev, run_ofs.size() * sizeof(int));
-  if (e == cudaSuccess)
-    e = cudaMemcpy(h->run_ofs_dev, run_ofs.data(), run_ofs.size() * sizeof(int), cudaMemcpyHostToDevice);
-  if (e == cudaSuccess && h->nfix > 0) e = cudaMalloc(&h->fix_dev, fix.size() * sizeof(int32_t));
-  if (e == cudaSuccess && h->nfix > 0)
-    e = cudaMemcpy(h->fix_dev, fix.data(), fix.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
-  if (e != cudaSuccess) { delete h; return fail(ST_CUDA_ERROR, "stefan_ipdg_create: %s", cudaGetErrorString(e)); }
+  if (e == cudaSuccess) e = h->plan.build(ph.data(), p->nx, p->ny, march_warps(p->order));
+  if (e != cudaSuccess) { h->plan.destroy(); if (h->phase_dev) cudaFree(h->phase_dev); delete h; return fail(ST_CUDA_ERROR, "stefan_ipdg_create: %s", cudaGetErrorString(e)); }
   *out = reinterpret_cast<stefan_ipdg*>(h);
   return ST_OK;
 }
@@ -447,15 +289,13 @@ int stefan_ipdg_destroy(stefan_ipdg* hv) {
   IpdgHandle* h = reinterpret_cast<IpdgHandle*>(hv);
   if (!h) return ST_OK;
   if (h->phase_dev) cudaFree(h->phase_dev);
-  if (h->fix_dev) cudaFree(h->fix_dev);
-  if (h->runs_dev) cudaFree(h->runs_dev);
+  h->plan.destroy();
   if (h->xh_dev) cudaFree(h->xh_dev);
   if (h->yh_dev) cudaFree(h->yh_dev);
   if (h->host_ready) {
     for (auto& s : h->hs) cudaStreamDestroy(s);
     for (auto& e : h->hev) cudaEventDestroy(e);
   }
-  if (h->run_ofs_dev) cudaFree(h->run_ofs_dev);
   switch (h->order) {
     case 1: delete static_cast<IpTab<1>*>(h->tab_host); break;
     case 2: delete static_cast<IpTab<2>*>(h->tab_host); break;

@@ -41,6 +41,8 @@
 
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched at run time)
 
+#include "march_dev.cuh"
+
 namespace stefan {
 
 #ifndef MARCH_NST1
@@ -103,24 +105,6 @@ struct MarchSmem {
   // rings (1024-byte aligned for the swizzled tiles) + mbarriers + alignment slack
   static constexpr int TOTAL = C::WARPS * WARP + C::WARPS * C::NST * 8 + 1024;
 };
-
-__device__ __forceinline__ void tma_tensor2d_load(void* dst, const CUtensorMap* map, int c0, int c1, void* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
-          "r"(smem_addr(dst)),
-      "l"(map), "r"(c0), "r"(c1), "r"(smem_addr(bar))
-      : "memory");
-}
-__device__ __forceinline__ void tma_bulk_store(void* gdst, const void* ssrc, unsigned bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
-               "r"(smem_addr(ssrc)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void tma_store_wait_read() {
-  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
 
 // ---- the arithmetic of one interior cell of phase index S with same-phase neighbours ----
 template <int P, int S>
@@ -207,56 +191,6 @@ struct MarchMath {
     }
   }
 };
-
-// 32-bit shared-window addresses keep the loop's address arithmetic in single registers
-__device__ __forceinline__ double2 lds_v2(unsigned addr) {
-  double2 v;
-  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
-  return v;
-}
-__device__ __forceinline__ double lds_f64(unsigned addr) {
-  double v;
-  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
-  return v;
-}
-__device__ __forceinline__ void sts_f64(unsigned addr, double v) {
-  asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx_s(unsigned bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_s(unsigned bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_s(unsigned bar, unsigned parity) {
-  asm volatile(
-      "{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@!p bra WAIT_%=;\n}" ::"r"(bar),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_load_s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void tensor2d_load_s(unsigned dst, const CUtensorMap* map, int c0, int c1, unsigned bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
-      "l"(map), "r"(c0), "r"(c1), "r"(bar)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_store_s(void* gdst, unsigned ssrc, unsigned bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes)
-               : "memory");
-}
-// A run {end column, mode, phase mask, store mask}, loaded only when a run ends (an
-// ordinary load would be hoisted out of the rare branch and every iteration would wait
-// for it); the kernel keeps one run of look-ahead so the load is never waited for.
-__device__ __forceinline__ int4 ld_run(const int4* p) {
-  int4 v;
-  asm volatile("ld.global.nc.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-  return v;
-}
 
 template <int P>
 __global__ void __launch_bounds__(MarchCfg<P>::WARPS * 32, MarchCfg<P>::MINB)

@@ -8,14 +8,14 @@
 // c = 0: T, 1: q_x, 2: q_y; cells y-fastest.  Phase: one byte per cell (1: sign +1,
 // 2: sign -1), padded to (nx+2) x (ny+2) with 0 = "no cell".
 //
-// Kernel: one thread per cell; the cell's own 3 NF dofs and, of each neighbour, only
-// the face nodes' T and normal flux component (2 (P+1) values per face) are read.
-// At the BASELINE size (10 M dofs = 80 MB per vector) x and y fit the 126 MB L2
-// together only partly, so the kernel is bound by L2 / HBM streaming, not by the
-// 10 (P+1)/3 FMAs per dof of the sum-factorised rows (ldg_tables.h).
+// Kernels: ldg_apply_march<P> (ldg_march.cuh) is the production path -- warps march along
+// x over TMA-staged column chunks, neighbours enter as face traces; ldg_apply_cells<P>
+// (one thread per cell, everything straight from global memory) is the plain second
+// opinion the tests compare it with (stefan_ldg_apply_simple).
 #include "../../include/stefan_b200.h"
 #include "common.cuh"
 #include "ldg_tables.h"
+#include "march_dev.cuh"
 
 #include <vector>
 
@@ -27,6 +27,7 @@ struct LdgHandle {
   LdgPhys phys;
   bool has_lo, has_hi;
   int8_t* phase_dev;
+  MarchPlan plan;  // run lists, fix list and CTA tiles of the march kernel
   void* tab_host;
   int64_t ndofs;
 };
@@ -148,6 +149,32 @@ ldg_rhs_kernel(const __grid_constant__ LdgRhsTab t, const int8_t* __restrict__ p
   }
 }
 
+}  // namespace stefan
+#include "ldg_march.cuh"
+namespace stefan {
+
+static int ldg_march_warps(int order) {
+  return order == 1 ? LdgMarchCfg<1>::WARPS : order == 2 ? LdgMarchCfg<2>::WARPS : LdgMarchCfg<3>::WARPS;
+}
+
+template <int P>
+static int ldg_launch_march(LdgHandle* h, const LdgArgs& a, cudaStream_t st) {
+  using C = LdgMarchCfg<P>;
+  const LdgTab<P>& tab = *static_cast<const LdgTab<P>*>(h->tab_host);
+  const SegCache& sc = h->plan.segments(0, h->nx, sm_count() * C::MINB);
+  if (sc.n <= 0) return fail(ST_UNSUPPORTED, "stefan_ldg_apply: more than %d strip groups (ny too large)", kMaxMarchCtas);
+  constexpr int smem = LdgMarchSmem<P>::TOTAL;
+  static bool attr_set = false;
+  if (!attr_set) {
+    STEFAN_CUDA(cudaFuncSetAttribute(ldg_apply_march<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  LdgMarchArgs m{a.x, a.x_lo, a.x_hi, a.y, a.phase, a.nx, a.ny, h->plan.fix_dev, h->plan.nfix, 0u};
+  ldg_apply_march<P><<<sc.n, C::WARPS * 32, smem, st>>>(tab, m, h->plan.runs_dev, h->plan.run_ofs_dev, sc.tab);
+  STEFAN_CUDA(cudaGetLastError());
+  return ST_OK;
+}
+
 template <int P>
 static int ldg_launch(const LdgHandle* h, const LdgArgs& a, cudaStream_t st) {
   const LdgTab<P>& tab = *static_cast<const LdgTab<P>*>(h->tab_host);
@@ -212,9 +239,19 @@ int stefan_ldg_create(const stefan_ldg_params* p, const int8_t* phase, const int
     if (phase_lo) ph[(size_t)(j + 1)] = (phase_lo[j] == 1) ? 1 : 2;
     if (phase_hi) ph[(size_t)(p->nx + 1) * (p->ny + 2) + (j + 1)] = (phase_hi[j] == 1) ? 1 : 2;
   }
+  if ((int64_t)p->nx * p->ny >= (int64_t)INT32_MAX) {
+    delete h;
+    return fail(ST_UNSUPPORTED, "stefan_ldg_create: more than 2^31 cells per slab");
+  }
   cudaError_t e = cudaMalloc(&h->phase_dev, pn);
   if (e == cudaSuccess) e = cudaMemcpy(h->phase_dev, ph.data(), pn, cudaMemcpyHostToDevice);
-  if (e != cudaSuccess) { delete h; return fail(ST_CUDA_ERROR, "stefan_ldg_create: %s", cudaGetErrorString(e)); }
+  if (e == cudaSuccess) e = h->plan.build(ph.data(), p->nx, p->ny, ldg_march_warps(p->order));
+  if (e != cudaSuccess) {
+    h->plan.destroy();
+    if (h->phase_dev) cudaFree(h->phase_dev);
+    delete h;
+    return fail(ST_CUDA_ERROR, "stefan_ldg_create: %s", cudaGetErrorString(e));
+  }
   *out = reinterpret_cast<stefan_ldg*>(h);
   return ST_OK;
 }
@@ -223,6 +260,7 @@ int stefan_ldg_destroy(stefan_ldg* hv) {
   LdgHandle* h = reinterpret_cast<LdgHandle*>(hv);
   if (!h) return ST_OK;
   if (h->phase_dev) cudaFree(h->phase_dev);
+  h->plan.destroy();
   switch (h->order) {
     case 1: delete static_cast<LdgTab<1>*>(h->tab_host); break;
     case 2: delete static_cast<LdgTab<2>*>(h->tab_host); break;
@@ -265,21 +303,42 @@ int stefan_ldg_rhs(stefan_ldg* hv, const double* f_qp, const double* g_qp, doubl
   return ST_OK;
 }
 
-int stefan_ldg_apply(stefan_ldg* hv, const double* x, double* y, const double* x_lo, const double* x_hi,
-                     void* stream) {
+static int ldg_apply_impl(stefan_ldg* hv, const double* x, double* y, const double* x_lo, const double* x_hi,
+                          int algo, void* stream) {
   LdgHandle* h = reinterpret_cast<LdgHandle*>(hv);
   STEFAN_REQUIRE(h && x && y, "stefan_ldg_apply: null argument");
   STEFAN_REQUIRE(x != y, "stefan_ldg_apply: in-place application is not supported");
   STEFAN_REQUIRE(h->has_lo == (x_lo != nullptr) && h->has_hi == (x_hi != nullptr),
                  "stefan_ldg_apply: halo columns must be given exactly where the handle has halo phases");
+  STEFAN_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(x_lo) & 15) == 0 && (reinterpret_cast<uintptr_t>(x_hi) & 15) == 0,
+                 "stefan_ldg_apply: device pointers must be 16-byte aligned");
   LdgArgs a{x, x_lo, x_hi, y, h->phase_dev, h->nx, h->ny};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  switch (h->order) {
-    case 1: return ldg_launch<1>(h, a, st);
-    case 2: return ldg_launch<2>(h, a, st);
-    case 3: return ldg_launch<3>(h, a, st);
+  if (algo == 1) {
+    switch (h->order) {
+      case 1: return ldg_launch<1>(h, a, st);
+      case 2: return ldg_launch<2>(h, a, st);
+      case 3: return ldg_launch<3>(h, a, st);
+    }
+  } else {
+    switch (h->order) {
+      case 1: return ldg_launch_march<1>(h, a, st);
+      case 2: return ldg_launch_march<2>(h, a, st);
+      case 3: return ldg_launch_march<3>(h, a, st);
+    }
   }
   return fail(ST_UNSUPPORTED, "stefan_ldg_apply: order %d", h->order);
+}
+
+int stefan_ldg_apply(stefan_ldg* hv, const double* x, double* y, const double* x_lo, const double* x_hi,
+                     void* stream) {
+  return ldg_apply_impl(hv, x, y, x_lo, x_hi, 0, stream);
+}
+
+int stefan_ldg_apply_simple(stefan_ldg* hv, const double* x, double* y, const double* x_lo, const double* x_hi,
+                            void* stream) {
+  return ldg_apply_impl(hv, x, y, x_lo, x_hi, 1, stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,375 @@
+// Local-DG apply, "march" kernel (production path).  Included by ldg.cu.
+//
+// Same decomposition as ipdg_march.cuh: one warp owns a strip of 30 cells in y (+1 halo
+// cell each side = 32 lanes, one cell per lane) and marches along x; every column chunk
+// (32 cells, contiguous in memory: 3, 6.75 or 12 KiB) arrives by ONE bulk asynchronous
+// copy (TMA) into a per-warp ring guarded by mbarriers.
+//
+// In the LDG rows of a cell (ldg_tables.h) a face neighbour enters only through the face
+// nodes' T and normal flux component -- 2 (P+1) numbers per face.  Per column the lane
+// therefore holds its own cell (3 NF doubles) in registers and gets
+//   left  traces: kept in registers from the previous column,
+//   right traces: 2 (P+1) doubles read from the next column's ring slot,
+//   down / up traces: warp shuffles from lanes -1 / +1,
+// computes its rows with compile-time table offsets (one body per phase), stores them,
+// and then replaces its registers by the next column's cell out of the same ring slot,
+// which is released for the next copy.  Each dof is read from HBM once (+2/30 halo
+// re-reads) and written once: 16 B per dof-update.
+//   P = 1: 96-byte cells, STG.256 stores.
+//   P = 2: 216-byte cells: chunks may start 8 bytes off a 16-byte boundary (the copy then
+//          starts 8 bytes early); results leave through a staged bulk store.
+//   P = 3: 384-byte cells, STG.256 stores.
+// Cells that are not interior-uniform (march_plan.h) are recomputed by the tail.
+#pragma once
+
+#include <type_traits>
+
+namespace stefan {
+
+#ifndef LDGM_NST1
+#define LDGM_NST1 2
+#endif
+#ifndef LDGM_NST2
+#define LDGM_NST2 2
+#endif
+#ifndef LDGM_NST3
+#define LDGM_NST3 2
+#endif
+#ifndef LDGM_WARPS1
+#define LDGM_WARPS1 8
+#endif
+#ifndef LDGM_WARPS2
+#define LDGM_WARPS2 8
+#endif
+#ifndef LDGM_WARPS3
+#define LDGM_WARPS3 8
+#endif
+#ifndef LDGM_MINB1
+#define LDGM_MINB1 2
+#endif
+#ifndef LDGM_MINB2
+#define LDGM_MINB2 1
+#endif
+#ifndef LDGM_MINB3
+#define LDGM_MINB3 1
+#endif
+
+template <int P>
+struct LdgMarchCfg;
+template <>
+struct LdgMarchCfg<1> {
+  static constexpr int CB = 96, STAGE = 32 * 96, NST = LDGM_NST1, WARPS = LDGM_WARPS1, MINB = LDGM_MINB1;
+  static constexpr int OUTB = 0;
+};
+template <>
+struct LdgMarchCfg<2> {
+  static constexpr int CB = 216, STAGE = 32 * 216 + 32, NST = LDGM_NST2, WARPS = LDGM_WARPS2, MINB = LDGM_MINB2;
+  static constexpr int OUTB = 30 * 216 + 16;
+};
+template <>
+struct LdgMarchCfg<3> {
+  static constexpr int CB = 384, STAGE = 32 * 384, NST = LDGM_NST3, WARPS = LDGM_WARPS3, MINB = LDGM_MINB3;
+  static constexpr int OUTB = 0;
+};
+template <int P>
+struct LdgMarchSmem {
+  using C = LdgMarchCfg<P>;
+  static constexpr int WARP = C::NST * C::STAGE + 2 * C::OUTB;
+  static constexpr int TOTAL = C::WARPS * WARP + C::WARPS * C::NST * 8 + 128;
+};
+
+struct LdgMarchArgs {
+  const double* x;
+  const double* x_lo;
+  const double* x_hi;
+  double* y;
+  const int8_t* phase;  // padded
+  int nx, ny;
+  const int32_t* fix;
+  int nfix;
+  unsigned zero;  // 0 at run time, unknown at compile time (slot release, see ipdg_march.cuh)
+};
+
+// cells the loop does not store: one thread per cell, general tables
+template <int P>
+__device__ __forceinline__ void ldg_fixup_tail(const LdgTab<P>& tab, const LdgMarchArgs& a) {
+  constexpr int N1 = P + 1, NF = N1 * N1, CD = 3 * NF;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < a.nfix; t += gridDim.x * blockDim.x) {
+    const int64_t cell = a.fix[t];
+    const int i = (int)(cell / a.ny), j = (int)(cell % a.ny);
+    const int s = ldg_phase_at(a.phase, a.ny, i, j);
+    const int sL = ldg_phase_at(a.phase, a.ny, i - 1, j), sR = ldg_phase_at(a.phase, a.ny, i + 1, j);
+    const int sD = ldg_phase_at(a.phase, a.ny, i, j - 1), sU = ldg_phase_at(a.phase, a.ny, i, j + 1);
+    double U[CD], UL[CD], UR[CD], UD[CD], UU[CD], out[CD];
+    const double* xc = a.x + cell * CD;
+    const double* pl = (i > 0) ? xc - (size_t)a.ny * CD : a.x_lo + (size_t)j * CD;
+    const double* pr = (i < a.nx - 1) ? xc + (size_t)a.ny * CD : a.x_hi + (size_t)j * CD;
+#pragma unroll
+    for (int k = 0; k < CD; ++k) U[k] = xc[k];
+#pragma unroll
+    for (int q = 0; q < N1; ++q) {
+      const int nl = 3 * (P * N1 + q), nr = 3 * (0 * N1 + q);
+      UL[nl] = sL ? pl[nl] : 0.0;
+      UL[nl + 1] = sL ? pl[nl + 1] : 0.0;
+      UR[nr] = sR ? pr[nr] : 0.0;
+      UR[nr + 1] = sR ? pr[nr + 1] : 0.0;
+      const int nd = 3 * (q * N1 + P), nu = 3 * (q * N1 + 0);
+      UD[nd] = sD ? xc[nd - CD] : 0.0;
+      UD[nd + 2] = sD ? xc[nd + 2 - CD] : 0.0;
+      UU[nu] = sU ? xc[nu + CD] : 0.0;
+      UU[nu + 2] = sU ? xc[nu + 2 + CD] : 0.0;
+    }
+    ldg_cell_rows<P>(tab, s == 1 ? 0 : 1, ip_face_type(s, sL), ip_face_type(s, sR), ip_face_type(s, sD),
+                     ip_face_type(s, sU), U, UL, UR, UD, UU, out);
+    double* yc = a.y + cell * CD;
+#pragma unroll
+    for (int k = 0; k < CD; ++k) yc[k] = out[k];
+  }
+}
+
+template <int P>
+__global__ void __launch_bounds__(LdgMarchCfg<P>::WARPS * 32, LdgMarchCfg<P>::MINB)
+ldg_apply_march(const __grid_constant__ LdgTab<P> tab, const LdgMarchArgs a, const int4* __restrict__ runs,
+                const int* __restrict__ run_ofs, const __grid_constant__ SegTab segs) {
+  using C = LdgMarchCfg<P>;
+  constexpr int N1 = P + 1, NF = N1 * N1, CD = 3 * NF;
+  constexpr int NST = C::NST, CB = C::CB;
+  constexpr bool ODD = (CB % 16) != 0;  // cells are only 8-byte aligned (P = 2)
+  extern __shared__ char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
+  const unsigned smem0 = (smem_addr(smem_raw) + 127u) & ~127u;
+  const unsigned ring = smem0 + (unsigned)warp * LdgMarchSmem<P>::WARP;
+  [[maybe_unused]] const unsigned obuf = ring + NST * C::STAGE;
+  const unsigned bars = smem0 + (unsigned)C::WARPS * LdgMarchSmem<P>::WARP + (unsigned)warp * NST * 8;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < NST; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bars + 8 * s), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+
+  const int nstrips = (a.ny + kStripCells - 1) / kStripCells;
+  const int4 myseg = segs.e[blockIdx.x];
+  const int strip = myseg.x * C::WARPS + warp;
+  const int c0 = myseg.y, c1 = myseg.z;
+  if (strip < nstrips && c0 < c1) {
+    const int j0 = strip * kStripCells;
+    const int j = j0 - 1 + lane;
+    const int jlo = max(j0 - 1, 0), jhi = min(j0 + kStripCells + 1, a.ny);
+    const int rel0 = jlo - (j0 - 1);
+    const unsigned nbytes = (unsigned)(jhi - jlo) * CB;
+    const size_t colbytes = (size_t)a.ny * CB;
+    const char* const xb = reinterpret_cast<const char*>(a.x);
+    // Lanes outside the mesh and columns that do not exist read whatever their ring slot
+    // holds: every cell next to them is a boundary cell, which the loop never stores.
+
+    auto col_base = [&](int k) -> const char* {
+      if (k >= 0 && k < a.nx) return xb + (size_t)k * colbytes + (size_t)jlo * CB;
+      if (k < 0 && a.x_lo != nullptr) return reinterpret_cast<const char*>(a.x_lo) + (size_t)jlo * CB;
+      if (k >= a.nx && a.x_hi != nullptr) return reinterpret_cast<const char*>(a.x_hi) + (size_t)jlo * CB;
+      return nullptr;
+    };
+    // ODD cells: the last chunk of an array whose byte length is 8 mod 16 cannot be copied to
+    // its end in 16-byte units; the lane of the last cell patches its last double itself
+    auto chunk_is_array_end = [&](int k) -> bool {
+      if constexpr (!ODD) return false;
+      if (jhi != a.ny) return false;
+      if (k >= 0 && k < a.nx) return k == a.nx - 1;
+      return true;
+    };
+    const unsigned dst_off = ODD ? rel0 * (unsigned)(CB + 8) : rel0 * (unsigned)CB;
+    const unsigned own = (unsigned)lane * CB + (ODD ? 8u * rel0 : 0u);
+    auto issue = [&](int k, unsigned stage, unsigned bar) {
+      if (k > c1 || lane != 0) return;
+      const char* src = col_base(k);
+      if (src == nullptr) {
+        mbar_arrive_s(bar);
+        return;
+      }
+      if constexpr (ODD) {
+        const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(src) & 15u);
+        unsigned bytes = sh + nbytes;
+        if (chunk_is_array_end(k)) bytes &= ~15u;
+        else bytes = (bytes + 15u) & ~15u;
+        mbar_expect_tx_s(bar, bytes);
+        bulk_load_s(stage + dst_off, src - sh, bytes, bar);
+      } else {
+        mbar_expect_tx_s(bar, nbytes);
+        bulk_load_s(stage + dst_off, src, nbytes, bar);
+      }
+    };
+    // shared address of this lane's cell of column k in `stage`
+    auto cell_addr = [&](int k, unsigned stage) -> unsigned {
+      unsigned p = stage + own;
+      if constexpr (ODD) p += (unsigned)(reinterpret_cast<uintptr_t>(col_base(k)) & 15u);
+      return p;
+    };
+    auto hi32 = [](double v) -> unsigned { return (unsigned)__double2hiint(v); };
+    // the lane's whole cell; returns the release word (see ipdg_march.cuh, "slot release")
+    auto read_cell = [&](int k, unsigned stage, double* v) -> unsigned {
+      unsigned h = 0;
+      const unsigned p = cell_addr(k, stage);
+      if constexpr (ODD) {
+#pragma unroll
+        for (int q = 0; q < CD; ++q) {
+          v[q] = lds_f64(p + 8 * q);
+          h ^= hi32(v[q]);
+        }
+        if (chunk_is_array_end(k) && j == a.ny - 1) {
+          const char* src = col_base(k);
+          if (src != nullptr && (((unsigned)(reinterpret_cast<uintptr_t>(src) & 15u) + nbytes) & 8u))
+            v[CD - 1] = *reinterpret_cast<const double*>(src + nbytes - 8);
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < CD / 2; ++q) {
+          const double2 t = lds_v2(p + 16 * q);
+          v[2 * q] = t.x;
+          v[2 * q + 1] = t.y;
+          h ^= hi32(t.x);
+        }
+      }
+      return h;
+    };
+    auto released = [&](unsigned h) -> unsigned { return __reduce_xor_sync(0xffffffffu, h) & a.zero; };
+
+    const int4* rp = runs + run_ofs[strip];
+    int4 cur = ld_run(rp);
+    while (cur.x <= c0) cur = ld_run(++rp);
+    int4 nxt = ld_run(rp + 1);
+
+    // prologue: columns c0-1 .. c0+NST-2 into slots 0 .. NST-1
+#pragma unroll
+    for (int k = 0; k < NST; ++k) issue(c0 - 1 + k, ring + k * C::STAGE, bars + 8 * k);
+    double U[CD];
+    double tLT[N1], tLQ[N1];  // left neighbour: T and q_x at its ix = P nodes
+    {
+      mbar_wait_s(bars + 0, 0);
+      const unsigned p = cell_addr(c0 - 1, ring);
+      unsigned h = 0;
+#pragma unroll
+      for (int q = 0; q < N1; ++q) {
+        tLT[q] = lds_f64(p + 8 * (3 * (P * N1 + q) + 0));
+        tLQ[q] = lds_f64(p + 8 * (3 * (P * N1 + q) + 1));
+        h ^= hi32(tLT[q]) ^ hi32(tLQ[q]);
+      }
+      unsigned z = released(h);
+      issue(c0 - 1 + NST, ring + z, bars + z);
+      const int s1 = 1 % NST;
+      mbar_wait_s(bars + 8 * s1, (1 / NST) & 1);
+      z = released(read_cell(c0, ring + s1 * C::STAGE, U));
+      issue(c0 + NST, ring + s1 * C::STAGE + z, bars + 8 * s1 + z);
+    }
+
+    int slot = 2 % NST;
+    unsigned stage_r = ring + slot * C::STAGE, bar_r = bars + 8 * slot, par_r = (2 / NST) & 1;
+    double* yp = a.y + ((size_t)c0 * a.ny + j) * CD;
+    [[maybe_unused]] char* gstrip = reinterpret_cast<char*>(a.y) + ((size_t)c0 * a.ny + j0) * CB;
+    [[maybe_unused]] unsigned ob = obuf;
+
+    for (int c = c0; c < c1; ++c) {
+      mbar_wait_s(bar_r, par_r);
+      const unsigned pn = cell_addr(c + 1, stage_r);
+      double tRT[N1], tRQ[N1];  // right neighbour: T and q_x at its ix = 0 nodes
+#pragma unroll
+      for (int q = 0; q < N1; ++q) {
+        tRT[q] = lds_f64(pn + 8 * (3 * q + 0));
+        tRQ[q] = lds_f64(pn + 8 * (3 * q + 1));
+      }
+      auto body = [&](auto phase_c) {
+        constexpr int S = decltype(phase_c)::value;
+        const unsigned ms = S ? ((unsigned)cur.w & (unsigned)cur.z) : ((unsigned)cur.w & ~(unsigned)cur.z);
+        const bool st = (ms >> lane) & 1;
+        double UL[CD], UR[CD], UD[CD], UU[CD], out[CD];
+#pragma unroll
+        for (int q = 0; q < N1; ++q) {
+          UL[3 * (P * N1 + q) + 0] = tLT[q];
+          UL[3 * (P * N1 + q) + 1] = tLQ[q];
+          UR[3 * q + 0] = tRT[q];
+          UR[3 * q + 1] = tRQ[q];
+          // from the cell below (lane - 1): T and q_y at its iy = P nodes; from above: iy = 0
+          UD[3 * (q * N1 + P) + 0] = __shfl_up_sync(0xffffffffu, U[3 * (q * N1 + P) + 0], 1);
+          UD[3 * (q * N1 + P) + 2] = __shfl_up_sync(0xffffffffu, U[3 * (q * N1 + P) + 2], 1);
+          UU[3 * (q * N1 + 0) + 0] = __shfl_down_sync(0xffffffffu, U[3 * (q * N1 + 0) + 0], 1);
+          UU[3 * (q * N1 + 0) + 2] = __shfl_down_sync(0xffffffffu, U[3 * (q * N1 + 0) + 2], 1);
+        }
+        ldg_cell_rows<P>(tab, S, T_SAME, T_SAME, T_SAME, T_SAME, U, UL, UR, UD, UU, out);
+        if constexpr (C::OUTB == 0) {
+          if (st) {
+#pragma unroll
+            for (int q = 0; q < CD; q += 4) st_global_v4(yp + q, out[q], out[q + 1], out[q + 2], out[q + 3]);
+          }
+        } else if (ms != 0 && (((ms >> (__ffs(ms) - 1)) + 1) & (ms >> (__ffs(ms) - 1))) == 0) {
+          // contiguous stored lanes [l0, l1): staged, one bulk store per column; a head / tail
+          // double that does not fill a 16-byte unit is written by the lane that owns it
+          const unsigned shy = (unsigned)(reinterpret_cast<uintptr_t>(gstrip) & 15u);
+          const unsigned l0 = __ffs(ms) - 1, l1 = 32 - __clz(ms);
+          const unsigned b0 = (l0 - 1) * CB, b1 = (l1 - 1) * CB;
+          const unsigned head = (shy + b0) & 8u, tail = (shy + b1) & 8u;
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+          if (st) {
+            const unsigned o = ob + shy + (lane - 1) * CB;
+#pragma unroll
+            for (int q = 0; q < CD; ++q) sts_f64(o + 8 * q, out[q]);
+            if (head && (unsigned)lane == l0) yp[0] = out[0];
+            if (tail && (unsigned)lane + 1 == l1) yp[CD - 1] = out[CD - 1];
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            const unsigned s0 = b0 + head, s1 = b1 - tail;
+            if (s1 > s0) bulk_store_s(gstrip + s0, ob + shy + s0, s1 - s0);
+            tma_store_commit();
+          }
+          ob = (ob == obuf) ? obuf + C::OUTB : obuf;
+        } else {
+          if (st) {
+#pragma unroll
+            for (int q = 0; q < CD; ++q) yp[q] = out[q];
+          }
+        }
+      };
+      const int ph = cur.y & 3;
+      if (ph == 1) {
+        body(std::integral_constant<int, 0>{});
+      } else if (ph == 2) {
+        body(std::integral_constant<int, 1>{});
+      } else if (ph == 3) {
+        body(std::integral_constant<int, 0>{});
+        body(std::integral_constant<int, 1>{});
+      }
+      yp += (size_t)a.ny * CD;
+      if constexpr (C::OUTB != 0) gstrip += colbytes;
+      if (c + 1 >= cur.x) {
+        cur = nxt;
+        nxt = ld_run(++rp + 1);
+      }
+      // this column becomes the left neighbour; the next column's cell replaces it
+#pragma unroll
+      for (int q = 0; q < N1; ++q) {
+        tLT[q] = U[3 * (P * N1 + q) + 0];
+        tLQ[q] = U[3 * (P * N1 + q) + 1];
+      }
+      const unsigned z = released(read_cell(c + 1, stage_r, U));
+      issue(c + 1 + NST, stage_r + z, bar_r + z);
+      if (++slot == NST) {
+        slot = 0;
+        stage_r = ring;
+        bar_r = bars;
+        par_r ^= 1;
+      } else {
+        stage_r += C::STAGE;
+        bar_r += 8;
+      }
+    }
+    if constexpr (C::OUTB != 0) {
+      if (lane == 0) tma_store_wait_read<0>();
+      __syncwarp();
+    }
+  }
+  ldg_fixup_tail<P>(tab, a);
+}
+
+}  // namespace stefan

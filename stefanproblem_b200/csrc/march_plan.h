@@ -1,0 +1,188 @@
+// Host-side plan of the "march" kernels (ipdg_march.cuh, ldg_march.cuh): which cells the
+// marching loop stores, which ones go to the kernels' tail, and how the (strip group,
+// column segment) tiles are cut so that every CTA gets the same cost.
+//
+// Decomposition: a warp owns a strip of kStripCells = 30 cells in y (+1 halo cell each
+// side = 32 lanes, lane = j - j0 + 1) and marches along x; a CTA = `group_warps` adjacent
+// strips (a strip group) over a column segment.
+//
+// A cell is "interior-uniform" iff its four face neighbours exist and have its own phase;
+// those are the cells the loop stores, with compile-time table offsets.  Every other cell
+// (boundary cells, cells next to the other phase) goes to the fix list, which each CTA's
+// tail recomputes with the general per-cell row function.
+//
+// Run list of a strip: {end column, mode, phase mask, store mask}; bit `lane` of the store
+// mask = the lane's cell is interior-uniform, of the phase mask = it has phase code 2.
+// mode & 3: 0 nothing to store, 1 / 2 every stored cell has phase code 1 / 2, 3 both occur
+// (the loop runs both phase bodies); mode & 4: the stored lanes are contiguous.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <climits>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+namespace stefan {
+
+constexpr int kStripCells = 30;
+
+// One entry per CTA of a march kernel: {strip group, first column, one past the last, -}
+constexpr int kMaxMarchCtas = 320;
+struct SegTab {
+  int4 e[kMaxMarchCtas];
+};
+struct SegCache {
+  int cbeg, cend, max_ctas, n;
+  SegTab tab;
+};
+
+struct MarchPlan {
+  int nx = 0, ny = 0, nstrips = 0, ngroups = 0, group_warps = 0;
+  std::vector<int> mixed_cum;    // [nstrips][nx+1] running count of phase-mixing columns
+  std::vector<int> fix_col_ofs;  // the fix list is sorted by column: [nx+1] offsets
+  std::vector<SegCache> seg_cache;
+  int4* runs_dev = nullptr;
+  int* run_ofs_dev = nullptr;
+  int32_t* fix_dev = nullptr;
+  int nfix = 0;
+
+  // ph: padded phase array (nx+2) x (ny+2), 0 = no cell.  Returns a cudaError_t.
+  cudaError_t build(const int8_t* ph, int nx_, int ny_, int group_warps_) {
+    nx = nx_;
+    ny = ny_;
+    group_warps = group_warps_;
+    nstrips = (ny + kStripCells - 1) / kStripCells;
+    ngroups = (nstrips + group_warps - 1) / group_warps;
+    const int ld = ny + 2;
+    std::vector<int32_t> fix;
+    std::vector<int4> runs;
+    std::vector<int> run_ofs(nstrips);
+    std::vector<uint32_t> smask((size_t)nstrips * nx), pmask((size_t)nstrips * nx);
+    for (int i = 0; i < nx; ++i) {
+      const int8_t* col = ph + (size_t)(i + 1) * ld + 1;
+      for (int j = 0; j < ny; ++j) {
+        const int8_t s = col[j];
+        const bool uniform = col[j - 1] == s && col[j + 1] == s && col[j - ld] == s && col[j + ld] == s;
+        const int sidx = j / kStripCells, lane = j - sidx * kStripCells + 1;
+        if (uniform) {
+          smask[(size_t)sidx * nx + i] |= 1u << lane;
+          if (s == 2) pmask[(size_t)sidx * nx + i] |= 1u << lane;
+        } else {
+          fix.push_back((int32_t)((int64_t)i * ny + j));
+        }
+      }
+    }
+    mixed_cum.assign((size_t)nstrips * (nx + 1), 0);
+    for (int sidx = 0; sidx < nstrips; ++sidx) {
+      run_ofs[sidx] = (int)runs.size();
+      const uint32_t* sm = smask.data() + (size_t)sidx * nx;
+      const uint32_t* pm = pmask.data() + (size_t)sidx * nx;
+      auto mode_of = [&](int i) {
+        if (sm[i] == 0) return 0;
+        int m = pm[i] == 0 ? 1 : (pm[i] == sm[i] ? 2 : 3);
+        const uint32_t t = sm[i] >> __builtin_ctz(sm[i]);
+        if ((t & (t + 1)) == 0) m |= 4;
+        return m;
+      };
+      for (int i = 0; i < nx;) {
+        int e = i + 1;
+        while (e < nx && sm[e] == sm[i] && pm[e] == pm[i]) ++e;
+        runs.push_back(make_int4(e, mode_of(i), (int)pm[i], (int)sm[i]));
+        i = e;
+      }
+      for (int k = 0; k < 3; ++k) runs.push_back(make_int4(INT_MAX, 0, 0, 0));  // sentinels
+      int* cum = mixed_cum.data() + (size_t)sidx * (nx + 1);
+      for (int i = 0; i < nx; ++i) cum[i + 1] = cum[i] + ((sm[i] != 0 && pm[i] != 0 && pm[i] != sm[i]) ? 1 : 0);
+    }
+    nfix = (int)fix.size();
+    fix_col_ofs.assign(nx + 1, 0);
+    for (int32_t cell : fix) fix_col_ofs[cell / ny + 1]++;
+    for (int i = 0; i < nx; ++i) fix_col_ofs[i + 1] += fix_col_ofs[i];
+    cudaError_t e = cudaMalloc(&runs_dev, runs.size() * sizeof(int4));
+    if (e == cudaSuccess) e = cudaMemcpy(runs_dev, runs.data(), runs.size() * sizeof(int4), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&run_ofs_dev, run_ofs.size() * sizeof(int));
+    if (e == cudaSuccess)
+      e = cudaMemcpy(run_ofs_dev, run_ofs.data(), run_ofs.size() * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && nfix > 0) e = cudaMalloc(&fix_dev, fix.size() * sizeof(int32_t));
+    if (e == cudaSuccess && nfix > 0)
+      e = cudaMemcpy(fix_dev, fix.data(), fix.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+    return e;
+  }
+
+  void destroy() {
+    if (runs_dev) cudaFree(runs_dev);
+    if (run_ofs_dev) cudaFree(run_ofs_dev);
+    if (fix_dev) cudaFree(fix_dev);
+    runs_dev = nullptr;
+    run_ofs_dev = nullptr;
+    fix_dev = nullptr;
+  }
+
+  // Cost-balanced tiles, one per CTA, for columns [cbeg, cend).  A CTA is done when its
+  // slowest warp is; a warp pays 1 per column plus kMixedCost where its strip mixes phases
+  // (both phase bodies run), so
+  //     cost(group, [c0, c1)) = (c1 - c0) + kMixedCost * max over the group's strips of
+  //                                          #mixed columns of that strip in [c0, c1).
+  // Segments are cut greedily at the largest c1 with cost <= T; T is bisected until the tile
+  // count fits the CTA budget (one wave).  Cached per column range.
+  static constexpr int kMixedCost = 1;
+  const SegCache& segments(int cbeg, int cend, int max_ctas) {
+    for (const SegCache& c : seg_cache)
+      if (c.cbeg == cbeg && c.cend == cend && c.max_ctas == max_ctas) return c;
+    const int ng = ngroups, gw = group_warps;
+    auto cost = [&](int g, int c0, int c1) {
+      int mx = 0;
+      for (int sidx = g * gw; sidx < std::min(nstrips, (g + 1) * gw); ++sidx) {
+        const int* cum = mixed_cum.data() + (size_t)sidx * (nx + 1);
+        mx = std::max(mx, cum[c1] - cum[c0]);
+      }
+      return (c1 - c0) + kMixedCost * mx;
+    };
+    auto cut = [&](int T, std::vector<int4>* tiles) {  // number of tiles of cost <= T each
+      int n = 0;
+      for (int g = 0; g < ng; ++g) {
+        int c0 = cbeg, s = 0;
+        while (c0 < cend) {
+          int lo = c0 + 1, hi = cend;  // largest c1 in (c0, cend] with cost <= T (at least one column)
+          while (lo < hi) {
+            const int mid = (lo + hi + 1) / 2;
+            if (cost(g, c0, mid) <= T) lo = mid;
+            else hi = mid - 1;
+          }
+          if (tiles) tiles->push_back(make_int4(g, c0, lo, s));
+          ++s;
+          ++n;
+          c0 = lo;
+        }
+      }
+      return n;
+    };
+    const int budget = std::max(ng, std::min(max_ctas, kMaxMarchCtas));
+    int hi = (1 + kMixedCost) * (cend - cbeg) + 1;
+    int lo = std::min(16, hi);  // segments of cost >= 16
+    while (lo < hi) {
+      const int mid = (lo + hi) / 2;
+      if (cut(mid, nullptr) <= budget) hi = mid;
+      else lo = mid + 1;
+    }
+    std::vector<int4> tiles;
+    cut(lo, &tiles);
+    // CTA order: segment-major = CTAs with neighbouring block indices work on neighbouring
+    // strips of the same columns
+    std::stable_sort(tiles.begin(), tiles.end(), [](const int4& a, const int4& b) { return a.w < b.w; });
+    SegCache c;
+    c.cbeg = cbeg;
+    c.cend = cend;
+    c.max_ctas = max_ctas;
+    c.n = (int)tiles.size() > kMaxMarchCtas ? -1 : (int)tiles.size();
+    std::memset(&c.tab, 0, sizeof(c.tab));
+    for (int k = 0; k < std::max(c.n, 0); ++k) c.tab.e[k] = tiles[k];
+    if (seg_cache.size() >= 8) seg_cache.erase(seg_cache.begin());
+    seg_cache.push_back(c);
+    return seg_cache.back();
+  }
+};
+
+}  // namespace stefan

@@ -354,13 +354,14 @@ class LDGOperator:
             _lib.lib().stefan_ldg_destroy(h)
             self._h = None
 
-    def apply(self, x, out=None, x_lo=None, x_hi=None, stream=None):
+    def apply(self, x, out=None, x_lo=None, x_hi=None, stream=None, algo=0):
+        """y = A x; algo 0 = production (march) kernel, 1 = plain one-thread-per-cell kernel."""
         import torch
         assert x.is_cuda and x.dtype == torch.float64 and x.is_contiguous() and x.numel() == self.ndofs
         if out is None:
             out = torch.empty_like(x)
-        _lib.check(_lib.lib().stefan_ldg_apply(self._h, _ptr(x), _ptr(out), _ptr(x_lo), _ptr(x_hi),
-                                               _stream_ptr(stream)))
+        fn = _lib.lib().stefan_ldg_apply if algo == 0 else _lib.lib().stefan_ldg_apply_simple
+        _lib.check(fn(self._h, _ptr(x), _ptr(out), _ptr(x_lo), _ptr(x_hi), _stream_ptr(stream)))
         return out
 
     def rhs(self, f_qp=None, g_qp=None, stream=None):

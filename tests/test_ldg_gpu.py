@@ -10,10 +10,11 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("order", [1, 2, 3])
-@pytest.mark.parametrize("nx,ny", [(3, 3), (7, 6), (33, 18)])
+@pytest.mark.parametrize("algo", [0, 1])
+@pytest.mark.parametrize("nx,ny", [(3, 3), (7, 6), (33, 18), (21, 65)])
 @pytest.mark.parametrize("two_phase", [False, True])
 @pytest.mark.parametrize("theta,pens", [(45.0, (0.0, 0.0, 1.0)), (143.0, (0.7, 0.3, 1.1)), (0.0, (1.0, 1.0, 1.0))])
-def test_apply_matches_oracle(cuda, order, nx, ny, two_phase, theta, pens):
+def test_apply_matches_oracle(cuda, order, algo, nx, ny, two_phase, theta, pens):
     import torch
     from stefanproblem_b200 import cutcelldg as cc
     from stefanproblem_b200 import local_dg as LocalDG
@@ -30,15 +31,30 @@ def test_apply_matches_oracle(cuda, order, nx, ny, two_phase, theta, pens):
     LocalDG.assemble_LDG_linear_system(sm, basis, cq, fq, None, k1, k2, pens[0], 0.0, pens[1], pens[2], V0, mesh)
     op = cc.sparse_operator(sm, mesh, 3)
     x = np.random.default_rng(0).uniform(-1, 1, A.shape[0])
-    y = (op @ torch.from_numpy(x).cuda()).cpu().numpy()
+    y = op.apply(torch.from_numpy(x).cuda(), algo=algo).cpu().numpy()
     yr = A @ x
     assert np.linalg.norm(y - yr) / np.linalg.norm(yr) < 1e-13
 
 
-def test_two_slabs_equal_one(cuda):
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_march_equals_simple_large(cuda, order):
+    """The two independent kernels agree on a mesh with many strips / segments (odd sizes)."""
     import torch
     from stefanproblem_b200 import cutcelldg as cc
-    order, nx, ny, cut = 2, 20, 13, 8
+    nx, ny = 301, 263
+    basis = cc.LagrangeTensorProductBasis(2, order)
+    omesh = UniformMesh2D([0, 0], [1, 1], [nx, ny], basis.nf)
+    mesh = cc.UniformMesh([0, 0], [1, 1], [nx, ny], basis, phase=fast.circle_phase(omesh))
+    op = cc.LDGOperator(mesh, order, order + 1, 1.0, 2.0, 0.5, 0.2, 1.3, (np.cos(0.4), np.sin(0.4)))
+    x = torch.from_numpy(np.random.default_rng(1).uniform(-1, 1, op.ndofs)).cuda()
+    y0, y1 = op.apply(x, algo=0), op.apply(x, algo=1)
+    assert (y0 - y1).norm() / y1.norm() < 1e-15 and (y0 - y1).abs().max() / y1.abs().max() < 1e-14
+
+
+@pytest.mark.parametrize("order,nx,ny,cut", [(2, 20, 13, 8), (1, 40, 65, 17), (2, 37, 33, 11), (3, 12, 40, 5)])
+def test_two_slabs_equal_one(cuda, order, nx, ny, cut):
+    import torch
+    from stefanproblem_b200 import cutcelldg as cc
     basis = cc.LagrangeTensorProductBasis(2, order)
     omesh = UniformMesh2D([0, 0], [1, 1], [nx, ny], basis.nf)
     phase = fast.circle_phase(omesh)
@@ -46,17 +62,18 @@ def test_two_slabs_equal_one(cuda):
     args = (order, order + 1, 1.0, 2.0, 0.5, 0.2, 1.3, V0)
     full = cc.LDGOperator(cc.UniformMesh([0, 0], [1, 1], [nx, ny], basis, phase=phase), *args)
     x = torch.from_numpy(np.random.default_rng(3).uniform(-1, 1, full.ndofs)).cuda()
-    yf = full.apply(x)
+    yf = full.apply(x, algo=1)
     col = 3 * ny * basis.nf
     P = phase.reshape(nx, ny)
     m_lo = cc.UniformMesh([0, 0], [cut / nx, 1], [cut, ny], basis, phase=P[:cut].ravel())
     m_hi = cc.UniformMesh([cut / nx, 0], [1 - cut / nx, 1], [nx - cut, ny], basis, phase=P[cut:].ravel())
     lo = cc.LDGOperator(m_lo, *args, phase_hi=P[cut])
     hi = cc.LDGOperator(m_hi, *args, phase_lo=P[cut - 1])
-    ylo = lo.apply(x[:cut * col].contiguous(), x_hi=x[cut * col:(cut + 1) * col].contiguous())
-    yhi = hi.apply(x[cut * col:].contiguous(), x_lo=x[(cut - 1) * col:cut * col].contiguous())
+    # clones: fresh (aligned) allocations, as separate GPUs would hold them
+    ylo = lo.apply(x[:cut * col].clone(), x_hi=x[cut * col:(cut + 1) * col].clone())
+    yhi = hi.apply(x[cut * col:].clone(), x_lo=x[(cut - 1) * col:cut * col].clone())
     # the slab meshes compute their cell width from their own extent: last-bit differences in h
-    assert (torch.cat([ylo, yhi]) - yf).norm() <= 1e-14 * yf.norm()
+    assert (torch.cat([ylo, yhi]) - yf).norm() <= 1e-13 * yf.norm()
 
 
 @pytest.mark.parametrize("order,nq", [(1, 2), (2, 5), (3, 4)])
