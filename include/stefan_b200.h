@@ -182,10 +182,11 @@ int64_t stefan_ldg_ndofs(const stefan_ldg* h);
  * x_lo / x_hi: the neighbouring slabs' adjacent cell columns (3*ny*NF doubles each). */
 int stefan_ldg_apply(stefan_ldg* h, const double* x, double* y, const double* x_lo,
                      const double* x_hi, void* stream);
-/* Same result from the plain one-thread-per-cell kernel (independent second opinion used by
- * the tests; not the production path). */
-int stefan_ldg_apply_simple(stefan_ldg* h, const double* x, double* y, const double* x_lo,
-                            const double* x_hi, void* stream);
+/* Same with an explicit kernel choice: 0 = what stefan_ldg_apply does (the march kernel;
+ * order 3 below 1 M cells: the plain kernel), 1 = plain one-thread-per-cell kernel (the
+ * independent second opinion of the tests), 2 = march kernel (csrc/ldg_march.cuh). */
+int stefan_ldg_apply_algo(stefan_ldg* h, const double* x, double* y, const double* x_lo,
+                          const double* x_hi, int32_t algo, void* stream);
 
 /* ------------------------------------------------------------------- DG1D
  * 1-D two-phase interior-penalty DG with a Robin interface on a DGMesh1D

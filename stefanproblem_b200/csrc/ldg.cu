@@ -11,7 +11,7 @@
 // Kernels: ldg_apply_march<P> (ldg_march.cuh) is the production path -- warps march along
 // x over TMA-staged column chunks, neighbours enter as face traces; ldg_apply_cells<P>
 // (one thread per cell, everything straight from global memory) is the plain second
-// opinion the tests compare it with (stefan_ldg_apply_simple).
+// opinion the tests compare it with (stefan_ldg_apply_algo, algo 1).
 #include "../../include/stefan_b200.h"
 #include "common.cuh"
 #include "ldg_tables.h"
@@ -315,6 +315,10 @@ static int ldg_apply_impl(stefan_ldg* hv, const double* x, double* y, const doub
                  "stefan_ldg_apply: device pointers must be 16-byte aligned");
   LdgArgs a{x, x_lo, x_hi, y, h->phase_dev, h->nx, h->ny};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // order 3: 48 doubles in and out per cell do not fit the register file next to the
+  // sum-factorisation intermediates; below ~1 M cells the spilling march kernel loses to
+  // the plain kernel (measured: 59 vs 71 GDOF/s at 457^2, 157 vs 78 at 2000^2)
+  if (algo == 0 && h->order == 3 && (int64_t)h->nx * h->ny < 1000000) algo = 1;
   if (algo == 1) {
     switch (h->order) {
       case 1: return ldg_launch<1>(h, a, st);
@@ -336,9 +340,10 @@ int stefan_ldg_apply(stefan_ldg* hv, const double* x, double* y, const double* x
   return ldg_apply_impl(hv, x, y, x_lo, x_hi, 0, stream);
 }
 
-int stefan_ldg_apply_simple(stefan_ldg* hv, const double* x, double* y, const double* x_lo, const double* x_hi,
-                            void* stream) {
-  return ldg_apply_impl(hv, x, y, x_lo, x_hi, 1, stream);
+int stefan_ldg_apply_algo(stefan_ldg* hv, const double* x, double* y, const double* x_lo, const double* x_hi,
+                          int32_t algo, void* stream) {
+  STEFAN_REQUIRE(algo >= 0 && algo <= 2, "stefan_ldg_apply_algo: unknown algo %d", algo);
+  return ldg_apply_impl(hv, x, y, x_lo, x_hi, algo, stream);
 }
 
 }  // extern "C"

@@ -161,7 +161,7 @@ struct MarchPlan {
     };
     const int budget = std::max(ng, std::min(max_ctas, kMaxMarchCtas));
     int hi = (1 + kMixedCost) * (cend - cbeg) + 1;
-    int lo = std::min(16, hi);  // segments of cost >= 16
+    int lo = std::min(8, hi);  // segments of cost >= 8
     while (lo < hi) {
       const int mid = (lo + hi) / 2;
       if (cut(mid, nullptr) <= budget) hi = mid;

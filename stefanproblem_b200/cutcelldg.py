@@ -224,6 +224,14 @@ def _stream_ptr(stream=None):
     return ctypes.c_void_p(s.cuda_stream)
 
 
+def _aligned(t):
+    """The TMA copies of the apply kernels need 16-byte aligned vectors; a view that starts
+    8 bytes off (e.g. an odd row of a matrix) is copied into a fresh allocation."""
+    if t is not None and t.data_ptr() % 16:
+        return t.clone()
+    return t
+
+
 class IPOperator:
     """Matrix-free `sparse_operator` of an interior-penalty system on one GPU."""
 
@@ -261,6 +269,7 @@ class IPOperator:
     def apply(self, x, out=None, x_lo=None, x_hi=None, algo=STREAM, stream=None):
         import torch
         assert x.is_cuda and x.dtype == torch.float64 and x.is_contiguous() and x.numel() == self.ndofs
+        x, x_lo, x_hi = _aligned(x), _aligned(x_lo), _aligned(x_hi)
         if out is None:
             out = torch.empty_like(x)
         _lib.check(_lib.lib().stefan_ipdg_apply(self._h, _ptr(x), _ptr(out), _ptr(x_lo), _ptr(x_hi),
@@ -355,13 +364,14 @@ class LDGOperator:
             self._h = None
 
     def apply(self, x, out=None, x_lo=None, x_hi=None, stream=None, algo=0):
-        """y = A x; algo 0 = production (march) kernel, 1 = plain one-thread-per-cell kernel."""
+        """y = A x; algo 0 = production choice, 1 = plain one-thread-per-cell kernel, 2 = march kernel."""
         import torch
         assert x.is_cuda and x.dtype == torch.float64 and x.is_contiguous() and x.numel() == self.ndofs
+        x, x_lo, x_hi = _aligned(x), _aligned(x_lo), _aligned(x_hi)
         if out is None:
             out = torch.empty_like(x)
-        fn = _lib.lib().stefan_ldg_apply if algo == 0 else _lib.lib().stefan_ldg_apply_simple
-        _lib.check(fn(self._h, _ptr(x), _ptr(out), _ptr(x_lo), _ptr(x_hi), _stream_ptr(stream)))
+        _lib.check(_lib.lib().stefan_ldg_apply_algo(self._h, _ptr(x), _ptr(out), _ptr(x_lo), _ptr(x_hi),
+                                                    int(algo), _stream_ptr(stream)))
         return out
 
     def rhs(self, f_qp=None, g_qp=None, stream=None):
