@@ -58,19 +58,19 @@ namespace stefan {
 #define MARCH_WARPS1 8
 #endif
 #ifndef MARCH_WARPS2
-#define MARCH_WARPS2 16
+#define MARCH_WARPS2 8
 #endif
 #ifndef MARCH_WARPS3
-#define MARCH_WARPS3 8
+#define MARCH_WARPS3 4
 #endif
 #ifndef MARCH_MINB1
 #define MARCH_MINB1 2
 #endif
 #ifndef MARCH_MINB2
-#define MARCH_MINB2 1
+#define MARCH_MINB2 2
 #endif
 #ifndef MARCH_MINB3
-#define MARCH_MINB3 1
+#define MARCH_MINB3 2
 #endif
 
 template <int P>

@@ -28,6 +28,7 @@ struct LdgHandle {
   bool has_lo, has_hi;
   int8_t* phase_dev;
   MarchPlan plan;  // run lists, fix list and CTA tiles of the march kernel
+  int variant;     // CTA shape of the march kernel (ldg_march_variant)
   void* tab_host;
   int64_t ndofs;
 };
@@ -153,26 +154,37 @@ ldg_rhs_kernel(const __grid_constant__ LdgRhsTab t, const int8_t* __restrict__ p
 #include "ldg_march.cuh"
 namespace stefan {
 
-static int ldg_march_warps(int order) {
-  return order == 1 ? LdgMarchCfg<1>::WARPS : order == 2 ? LdgMarchCfg<2>::WARPS : LdgMarchCfg<3>::WARPS;
+// CTA shape of the march kernel for a mesh (see LdgMarchCfg)
+static int ldg_march_variant(int order, int64_t ncells) {
+  if (order == 1) return ncells >= 2000000 ? 1 : 0;
+  if (order == 2) return ncells >= 1000000 ? 0 : 1;
+  return 0;
+}
+static int ldg_march_warps(int order, int variant) {
+  (void)order;
+  return variant ? 4 : 8;
 }
 
-template <int P>
-static int ldg_launch_march(LdgHandle* h, const LdgArgs& a, cudaStream_t st) {
-  using C = LdgMarchCfg<P>;
+template <int P, int V>
+static int ldg_launch_march_v(LdgHandle* h, const LdgArgs& a, cudaStream_t st) {
+  using C = LdgMarchCfg<P, V>;
   const LdgTab<P>& tab = *static_cast<const LdgTab<P>*>(h->tab_host);
   const SegCache& sc = h->plan.segments(0, h->nx, sm_count() * C::MINB);
   if (sc.n <= 0) return fail(ST_UNSUPPORTED, "stefan_ldg_apply: more than %d strip groups (ny too large)", kMaxMarchCtas);
-  constexpr int smem = LdgMarchSmem<P>::TOTAL;
+  constexpr int smem = LdgMarchSmem<P, V>::TOTAL;
   static bool attr_set = false;
   if (!attr_set) {
-    STEFAN_CUDA(cudaFuncSetAttribute(ldg_apply_march<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    STEFAN_CUDA(cudaFuncSetAttribute(ldg_apply_march<P, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
   LdgMarchArgs m{a.x, a.x_lo, a.x_hi, a.y, a.phase, a.nx, a.ny, h->plan.fix_dev, h->plan.nfix, 0u};
-  ldg_apply_march<P><<<sc.n, C::WARPS * 32, smem, st>>>(tab, m, h->plan.runs_dev, h->plan.run_ofs_dev, sc.tab);
+  ldg_apply_march<P, V><<<sc.n, C::WARPS * 32, smem, st>>>(tab, m, h->plan.runs_dev, h->plan.run_ofs_dev, sc.tab);
   STEFAN_CUDA(cudaGetLastError());
   return ST_OK;
+}
+template <int P>
+static int ldg_launch_march(LdgHandle* h, const LdgArgs& a, cudaStream_t st) {
+  return h->variant ? ldg_launch_march_v<P, 1>(h, a, st) : ldg_launch_march_v<P, 0>(h, a, st);
 }
 
 template <int P>
@@ -245,7 +257,8 @@ int stefan_ldg_create(const stefan_ldg_params* p, const int8_t* phase, const int
   }
   cudaError_t e = cudaMalloc(&h->phase_dev, pn);
   if (e == cudaSuccess) e = cudaMemcpy(h->phase_dev, ph.data(), pn, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = h->plan.build(ph.data(), p->nx, p->ny, ldg_march_warps(p->order));
+  h->variant = ldg_march_variant(p->order, (int64_t)p->nx * p->ny);
+  if (e == cudaSuccess) e = h->plan.build(ph.data(), p->nx, p->ny, ldg_march_warps(p->order, h->variant));
   if (e != cudaSuccess) {
     h->plan.destroy();
     if (h->phase_dev) cudaFree(h->phase_dev);

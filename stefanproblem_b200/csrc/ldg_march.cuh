@@ -26,54 +26,33 @@
 
 namespace stefan {
 
-#ifndef LDGM_NST1
-#define LDGM_NST1 2
-#endif
-#ifndef LDGM_NST2
-#define LDGM_NST2 2
-#endif
-#ifndef LDGM_NST3
-#define LDGM_NST3 2
-#endif
-#ifndef LDGM_WARPS1
-#define LDGM_WARPS1 8
-#endif
-#ifndef LDGM_WARPS2
-#define LDGM_WARPS2 8
-#endif
-#ifndef LDGM_WARPS3
-#define LDGM_WARPS3 8
-#endif
-#ifndef LDGM_MINB1
-#define LDGM_MINB1 2
-#endif
-#ifndef LDGM_MINB2
-#define LDGM_MINB2 1
-#endif
-#ifndef LDGM_MINB3
-#define LDGM_MINB3 1
+#ifndef LDGM_NST
+#define LDGM_NST 2
 #endif
 
-template <int P>
+// V = 0: few large CTAs, V = 1: the other shape.  Measured (GDOF/s, 10 M dofs / 2000^2 cells):
+// P = 1: 8 warps x 2 CTAs 278 / 294, 4 warps x 2 CTAs - / 334 (x 4 CTAs: 243 / 306);
+// P = 2: 8 warps x 1 CTA 195 / 333, 4 warps x 2 CTAs 241 / 325.  ldg.cu picks per mesh size.
+template <int P, int V>
 struct LdgMarchCfg;
-template <>
-struct LdgMarchCfg<1> {
-  static constexpr int CB = 96, STAGE = 32 * 96, NST = LDGM_NST1, WARPS = LDGM_WARPS1, MINB = LDGM_MINB1;
+template <int V>
+struct LdgMarchCfg<1, V> {
+  static constexpr int CB = 96, STAGE = 32 * 96, NST = LDGM_NST, WARPS = V ? 4 : 8, MINB = 2;
   static constexpr int OUTB = 0;
 };
-template <>
-struct LdgMarchCfg<2> {
-  static constexpr int CB = 216, STAGE = 32 * 216 + 32, NST = LDGM_NST2, WARPS = LDGM_WARPS2, MINB = LDGM_MINB2;
+template <int V>
+struct LdgMarchCfg<2, V> {
+  static constexpr int CB = 216, STAGE = 32 * 216 + 32, NST = LDGM_NST, WARPS = V ? 4 : 8, MINB = V ? 2 : 1;
   static constexpr int OUTB = 30 * 216 + 16;
 };
-template <>
-struct LdgMarchCfg<3> {
-  static constexpr int CB = 384, STAGE = 32 * 384, NST = LDGM_NST3, WARPS = LDGM_WARPS3, MINB = LDGM_MINB3;
+template <int V>
+struct LdgMarchCfg<3, V> {
+  static constexpr int CB = 384, STAGE = 32 * 384, NST = LDGM_NST, WARPS = V ? 4 : 8, MINB = V ? 2 : 1;
   static constexpr int OUTB = 0;
 };
-template <int P>
+template <int P, int V>
 struct LdgMarchSmem {
-  using C = LdgMarchCfg<P>;
+  using C = LdgMarchCfg<P, V>;
   static constexpr int WARP = C::NST * C::STAGE + 2 * C::OUTB;
   static constexpr int TOTAL = C::WARPS * WARP + C::WARPS * C::NST * 8 + 128;
 };
@@ -127,11 +106,11 @@ __device__ __forceinline__ void ldg_fixup_tail(const LdgTab<P>& tab, const LdgMa
   }
 }
 
-template <int P>
-__global__ void __launch_bounds__(LdgMarchCfg<P>::WARPS * 32, LdgMarchCfg<P>::MINB)
+template <int P, int V>
+__global__ void __launch_bounds__(LdgMarchCfg<P, V>::WARPS * 32, LdgMarchCfg<P, V>::MINB)
 ldg_apply_march(const __grid_constant__ LdgTab<P> tab, const LdgMarchArgs a, const int4* __restrict__ runs,
                 const int* __restrict__ run_ofs, const __grid_constant__ SegTab segs) {
-  using C = LdgMarchCfg<P>;
+  using C = LdgMarchCfg<P, V>;
   constexpr int N1 = P + 1, NF = N1 * N1, CD = 3 * NF;
   constexpr int NST = C::NST, CB = C::CB;
   constexpr bool ODD = (CB % 16) != 0;  // cells are only 8-byte aligned (P = 2)
@@ -139,9 +118,9 @@ ldg_apply_march(const __grid_constant__ LdgTab<P> tab, const LdgMarchArgs a, con
   const int lane = threadIdx.x & 31;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
   const unsigned smem0 = (smem_addr(smem_raw) + 127u) & ~127u;
-  const unsigned ring = smem0 + (unsigned)warp * LdgMarchSmem<P>::WARP;
+  const unsigned ring = smem0 + (unsigned)warp * LdgMarchSmem<P, V>::WARP;
   [[maybe_unused]] const unsigned obuf = ring + NST * C::STAGE;
-  const unsigned bars = smem0 + (unsigned)C::WARPS * LdgMarchSmem<P>::WARP + (unsigned)warp * NST * 8;
+  const unsigned bars = smem0 + (unsigned)C::WARPS * LdgMarchSmem<P, V>::WARP + (unsigned)warp * NST * 8;
   if (lane == 0) {
 #pragma unroll
     for (int s = 0; s < NST; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bars + 8 * s), "r"(1));

@@ -29,7 +29,7 @@ namespace stefan {
 constexpr int kStripCells = 30;
 
 // One entry per CTA of a march kernel: {strip group, first column, one past the last, -}
-constexpr int kMaxMarchCtas = 320;
+constexpr int kMaxMarchCtas = 640;
 struct SegTab {
   int4 e[kMaxMarchCtas];
 };
