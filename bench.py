@@ -324,7 +324,7 @@ def main():
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel for the default
 # workload, from profiles/ (updated whenever the kernel is re-profiled)
-PROFILED_TRAFFIC_BYTES = 810.573312e6 + 748.008960e6  # profiles/r1_ipdg_p1_tma_ncu_full.csv
+PROFILED_TRAFFIC_BYTES = 819.148032e6 + 759.410176e6  # profiles/r1_ipdg_p1_march_ncu.csv
 
 if __name__ == "__main__":
     main()

@@ -255,6 +255,26 @@ int64_t stefan_fd_nnz(stefan_fd* h);
 int stefan_fd_assemble_coo(stefan_fd* h, int64_t* rows, int64_t* cols, double* vals,
                            int64_t capacity, int64_t* nnz_out, void* stream);
 
+/* ------------------------------------------------------------- peer memory
+ * Column-slab partition across the GPUs of one NVLink domain, one process per GPU (the
+ * reference is single-process; this is the multi-GPU extension of SURVEY.md 8(e)).  A slab
+ * vector allocated here can be mapped by the neighbouring ranks, whose apply kernels then
+ * read its edge column directly (pass the mapped address as x_lo / x_hi): the halo exchange
+ * becomes TMA copies over NVLink inside the apply kernel.  The 64-byte handle travels
+ * between the processes by any means the host program has. */
+typedef struct { unsigned char bytes[64]; } stefan_ipc_handle;
+int stefan_peer_alloc(int64_t nbytes, void** dev_ptr, stefan_ipc_handle* handle); /* zero-filled */
+int stefan_peer_free(void* dev_ptr);
+int stefan_peer_open(const stefan_ipc_handle* handle, void** peer_ptr);
+int stefan_peer_close(void* peer_ptr);
+/* Epoch flags (uint64 in peer memory): signal = "everything this stream wrote before is
+ * final for `epoch`" (release, system scope); wait holds the stream until *peer_flag >=
+ * epoch (acquire), gives up after timeout_ms and then sets *status_dev (device int32, may
+ * be NULL) to 1 instead of hanging. */
+int stefan_peer_signal(uint64_t* flag, uint64_t epoch, void* stream);
+int stefan_peer_wait(const uint64_t* peer_flag, uint64_t epoch, int32_t timeout_ms, int32_t* status_dev,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

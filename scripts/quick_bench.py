@@ -56,6 +56,30 @@ def run_ldg(order, n, two_phase, reps=20, algo=0):
           f"{16 * gdofs:.0f} GB/s  ({16 * gdofs / 6551 * 100:.1f}% of 6551)", flush=True)
 
 
+def run_fd(n, reps=20):
+    """FD Laplace apply / fused explicit step on n nodes, one interface in the middle."""
+    from stefanproblem_b200 import finite_difference as FD
+    phaseid = np.ones(n, dtype=np.int8)
+    phaseid[n // 2:] = 2
+    op = FD.FDOperator(phaseid, 1.0 / (n - 1))
+    u = torch.rand(n, dtype=torch.float64, device="cuda")
+    y = torch.empty_like(u)
+    for name, fn in (("apply", lambda: op.apply(u, out=y)), ("step", lambda: op.step(u, 1e-9, 1.0, 2.0, out=y))):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        g = n / ms / 1e6
+        print(f"FD {name} n={n}: {ms:.3f} ms  {g:.1f} Gnode/s  {17 * g:.0f} GB/s  ({17 * g / 6551 * 100:.1f}% of 6551; "
+              f"17 B per node: u read, y written, 1 B row kind)", flush=True)
+
+
 if __name__ == "__main__":
     import argparse
     ap = argparse.ArgumentParser()
@@ -68,7 +92,11 @@ if __name__ == "__main__":
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--two-phase", type=int, default=1)
     ap.add_argument("--ldg", type=int, default=0)
+    ap.add_argument("--fd", type=int, default=0)
     args = ap.parse_args()
+    if args.fd:
+        run_fd(args.n or (1 << 27), args.reps)
+        sys.exit(0)
     if args.ldg:
         orders = [args.order] if args.order else [1, 2, 3]
         for o in orders:

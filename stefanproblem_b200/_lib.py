@@ -75,6 +75,13 @@ _SIGNATURES = {
     "stefan_ldg_rhs": (ctypes.c_int, [ctypes.c_void_p] * 5),
     "stefan_ldg_apply": (ctypes.c_int, [ctypes.c_void_p] * 6),
     "stefan_ldg_apply_algo": (ctypes.c_int, [ctypes.c_void_p] * 5 + [ctypes.c_int32, ctypes.c_void_p]),
+    "stefan_peer_alloc": (ctypes.c_int, [ctypes.c_int64, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p]),
+    "stefan_peer_free": (ctypes.c_int, [ctypes.c_void_p]),
+    "stefan_peer_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]),
+    "stefan_peer_close": (ctypes.c_int, [ctypes.c_void_p]),
+    "stefan_peer_signal": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p]),
+    "stefan_peer_wait": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int32, ctypes.c_void_p,
+                                        ctypes.c_void_p]),
     "stefan_dg1d_create": (ctypes.c_int, [ctypes.POINTER(Dg1dParams), ctypes.POINTER(ctypes.c_void_p)]),
     "stefan_dg1d_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "stefan_dg1d_ndofs": (ctypes.c_int64, [ctypes.c_void_p]),

@@ -319,9 +319,13 @@ int stefan_ipdg_apply(stefan_ipdg* hv, const double* x, double* y, const double*
   STEFAN_REQUIRE(x != y, "stefan_ipdg_apply: in-place application is not supported");
   STEFAN_REQUIRE(h->has_lo == (x_lo != nullptr) && h->has_hi == (x_hi != nullptr),
                  "stefan_ipdg_apply: halo columns must be given exactly where the handle has halo phases");
+  // halo columns may be columns of a neighbour's slab vector (peer memory): with 72-byte
+  // cells (order 2) such a column can start 8 bytes off a 16-byte boundary, which the
+  // kernel handles like any odd column chunk
+  const uintptr_t hmask = h->order == 2 ? 7 : 15;
   STEFAN_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
-                 (reinterpret_cast<uintptr_t>(x_lo) & 15) == 0 && (reinterpret_cast<uintptr_t>(x_hi) & 15) == 0,
-                 "stefan_ipdg_apply: device pointers must be 16-byte aligned");
+                 (reinterpret_cast<uintptr_t>(x_lo) & hmask) == 0 && (reinterpret_cast<uintptr_t>(x_hi) & hmask) == 0,
+                 "stefan_ipdg_apply: x, y must be 16-byte aligned (halo columns: 16, order 2: 8)");
   STEFAN_REQUIRE(algo >= 0 && algo <= 1, "stefan_ipdg_apply: unknown algo %d", algo);
   ApplyArgs a{x, x_lo, x_hi, y, h->phase_dev, h->nx, h->ny, 1, 0, h->nx, nullptr, 0};
   return dispatch_apply(h, a, algo, static_cast<cudaStream_t>(stream));

@@ -323,9 +323,10 @@ static int ldg_apply_impl(stefan_ldg* hv, const double* x, double* y, const doub
   STEFAN_REQUIRE(x != y, "stefan_ldg_apply: in-place application is not supported");
   STEFAN_REQUIRE(h->has_lo == (x_lo != nullptr) && h->has_hi == (x_hi != nullptr),
                  "stefan_ldg_apply: halo columns must be given exactly where the handle has halo phases");
+  const uintptr_t hmask = h->order == 2 ? 7 : 15;  // see stefan_ipdg_apply
   STEFAN_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
-                 (reinterpret_cast<uintptr_t>(x_lo) & 15) == 0 && (reinterpret_cast<uintptr_t>(x_hi) & 15) == 0,
-                 "stefan_ldg_apply: device pointers must be 16-byte aligned");
+                 (reinterpret_cast<uintptr_t>(x_lo) & hmask) == 0 && (reinterpret_cast<uintptr_t>(x_hi) & hmask) == 0,
+                 "stefan_ldg_apply: x, y must be 16-byte aligned (halo columns: 16, order 2: 8)");
   LdgArgs a{x, x_lo, x_hi, y, h->phase_dev, h->nx, h->ny};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // order 3: 48 doubles in and out per cell do not fit the register file next to the

@@ -224,10 +224,10 @@ def _stream_ptr(stream=None):
     return ctypes.c_void_p(s.cuda_stream)
 
 
-def _aligned(t):
+def _aligned(t, align=16):
     """The TMA copies of the apply kernels need 16-byte aligned vectors; a view that starts
     8 bytes off (e.g. an odd row of a matrix) is copied into a fresh allocation."""
-    if t is not None and t.data_ptr() % 16:
+    if t is not None and t.data_ptr() % align:
         return t.clone()
     return t
 
@@ -269,7 +269,8 @@ class IPOperator:
     def apply(self, x, out=None, x_lo=None, x_hi=None, algo=STREAM, stream=None):
         import torch
         assert x.is_cuda and x.dtype == torch.float64 and x.is_contiguous() and x.numel() == self.ndofs
-        x, x_lo, x_hi = _aligned(x), _aligned(x_lo), _aligned(x_hi)
+        hal = 8 if self.order == 2 else 16
+        x, x_lo, x_hi = _aligned(x), _aligned(x_lo, hal), _aligned(x_hi, hal)
         if out is None:
             out = torch.empty_like(x)
         _lib.check(_lib.lib().stefan_ipdg_apply(self._h, _ptr(x), _ptr(out), _ptr(x_lo), _ptr(x_hi),
@@ -367,7 +368,8 @@ class LDGOperator:
         """y = A x; algo 0 = production choice, 1 = plain one-thread-per-cell kernel, 2 = march kernel."""
         import torch
         assert x.is_cuda and x.dtype == torch.float64 and x.is_contiguous() and x.numel() == self.ndofs
-        x, x_lo, x_hi = _aligned(x), _aligned(x_lo), _aligned(x_hi)
+        hal = 8 if self.order == 2 else 16
+        x, x_lo, x_hi = _aligned(x), _aligned(x_lo, hal), _aligned(x_hi, hal)
         if out is None:
             out = torch.empty_like(x)
         _lib.check(_lib.lib().stefan_ldg_apply_algo(self._h, _ptr(x), _ptr(out), _ptr(x_lo), _ptr(x_hi),

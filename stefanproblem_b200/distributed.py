@@ -7,10 +7,18 @@ face terms couple a cell to its four face neighbours only).  That halo trace exc
 is the only communication of the operator; the interface-flux reduction that drives
 the front velocity is a 4-double all-reduce (see `allreduce_interface_sums`).
 
-`torch.distributed` (NCCL on GPUs, gloo in the CPU tests) is the transport; the
-exchange runs on a side stream while the interior columns are applied, and the two
-edge columns follow once it has landed.
+Two transports:
+  * peer memory (`PeerSlab`, the default of `DistributedIPOperator.apply_peer`): every slab
+    vector lives in CUDA-IPC memory that the neighbouring ranks map; the apply kernel of a
+    rank reads the neighbours' edge columns straight out of their vectors -- TMA bulk copies
+    over NVLink issued by the marching warps -- so an application is ONE kernel launch with
+    no pack / send / recv / unpack step.  Epoch flags in the same peer memory order the reads.
+  * `torch.distributed` send / recv (NCCL on GPUs, gloo in the CPU tests), `HaloExchange`:
+    the exchange runs on a side stream while the interior columns are applied, and the two
+    edge columns follow once it has landed.
 """
+import ctypes
+
 import numpy as np
 
 
@@ -119,3 +127,121 @@ class DistributedIPOperator:
         self.op.apply_columns(x, out, 0, 1, x_lo=h.x_lo, x_hi=h.x_hi)
         self.op.apply_columns(x, out, self.nxl - 1, self.nxl, x_lo=h.x_lo, x_hi=h.x_hi)
         return out
+
+
+class _DevArray:
+    """__cuda_array_interface__ view of raw device memory (lets torch wrap it without a copy)."""
+
+    def __init__(self, ptr, n, typestr="<f8"):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2}
+
+
+class PeerSlab:
+    """A slab vector in peer-mappable memory plus the flags that order the neighbours' reads.
+
+    Layout of the allocation: [n doubles][pad to 128 B][ready flag u64][consumed flag u64].
+    Collective over the process group (handles are all-gathered)."""
+
+    FLAG_BYTES = 128
+
+    def __init__(self, n, rank, world):
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        L = _lib.lib()
+        self.n, self.rank, self.world = int(n), rank, world
+        self._flag_off = (self.n * 8 + 127) // 128 * 128
+        nbytes = self._flag_off + self.FLAG_BYTES
+        p = ctypes.c_void_p()
+        hbuf = ctypes.create_string_buffer(64)
+        _lib.check(L.stefan_peer_alloc(nbytes, ctypes.byref(p), hbuf))
+        self._ptr = p.value
+        self.x = torch.as_tensor(_DevArray(self._ptr, self.n), device="cuda")
+        self.status = torch.zeros(1, dtype=torch.int32, device="cuda")
+        handles = [None] * world
+        dist.all_gather_object(handles, (bytes(hbuf.raw), self.n))
+        self._peers = {}
+        for r in (rank - 1, rank + 1):
+            if 0 <= r < world:
+                q = ctypes.c_void_p()
+                _lib.check(L.stefan_peer_open(handles[r][0], ctypes.byref(q)))
+                n_r = handles[r][1]
+                self._peers[r] = (q.value, n_r, (n_r * 8 + 127) // 128 * 128)
+        self.epoch = 0
+
+    # addresses -----------------------------------------------------------------
+    def my_flag(self, which):
+        return self._ptr + self._flag_off + 8 * which
+
+    def peer_flag(self, r, which):
+        base, _, off = self._peers[r]
+        return base + off + 8 * which
+
+    def peer_column(self, r, col_len, last):
+        """Address of the neighbour r's first (last=False) / last (last=True) cell column."""
+        base, n_r, _ = self._peers[r]
+        return base + (8 * (n_r - col_len) if last else 0)
+
+    # ordering ------------------------------------------------------------------
+    def publish(self, stream=None):
+        """My vector is final for the next epoch (call after the kernels that wrote it)."""
+        from . import _lib
+        from .cutcelldg import _stream_ptr
+        self.epoch += 1
+        _lib.check(_lib.lib().stefan_peer_signal(ctypes.c_void_p(self.my_flag(0)), self.epoch, _stream_ptr(stream)))
+
+    def wait_neighbours(self, stream=None, timeout_ms=5000):
+        """Hold the stream until both neighbours have published the current epoch."""
+        from . import _lib
+        from .cutcelldg import _stream_ptr
+        for r in self._peers:
+            _lib.check(_lib.lib().stefan_peer_wait(ctypes.c_void_p(self.peer_flag(r, 0)), self.epoch, timeout_ms,
+                                                   ctypes.c_void_p(self.status.data_ptr()), _stream_ptr(stream)))
+
+    def release(self, stream=None):
+        """I am done reading my neighbours' vectors of the current epoch."""
+        from . import _lib
+        from .cutcelldg import _stream_ptr
+        _lib.check(_lib.lib().stefan_peer_signal(ctypes.c_void_p(self.my_flag(1)), self.epoch, _stream_ptr(stream)))
+
+    def wait_released(self, stream=None, timeout_ms=5000):
+        """Hold the stream until the neighbours are done reading my vector (before overwriting it)."""
+        from . import _lib
+        from .cutcelldg import _stream_ptr
+        for r in self._peers:
+            _lib.check(_lib.lib().stefan_peer_wait(ctypes.c_void_p(self.peer_flag(r, 1)), self.epoch, timeout_ms,
+                                                   ctypes.c_void_p(self.status.data_ptr()), _stream_ptr(stream)))
+
+    def close(self):
+        from . import _lib
+        L = _lib.lib()
+        for q, _, _ in self._peers.values():
+            L.stefan_peer_close(ctypes.c_void_p(q))
+        self._peers = {}
+        if self._ptr:
+            self.x = None
+            L.stefan_peer_free(ctypes.c_void_p(self._ptr))
+            self._ptr = None
+
+
+def apply_peer(dop, slab, out, publish=True):
+    """out = A x for the slab vector `slab.x` of a DistributedIPOperator: ONE kernel launch;
+    the neighbours' edge columns are read from their PeerSlab memory over NVLink.
+
+    publish=True: publish my vector, wait for the neighbours', apply, release.  A caller whose
+    x does not change between applications (a benchmark) can publish once and pass False."""
+    import torch
+    from . import _lib
+    from .cutcelldg import _stream_ptr
+    col = dop.halo.col
+    if publish:
+        slab.publish()
+        slab.wait_neighbours()
+    lo = ctypes.c_void_p(slab.peer_column(dop.rank - 1, col, last=True)) if dop.rank > 0 else None
+    hi = ctypes.c_void_p(slab.peer_column(dop.rank + 1, col, last=False)) if dop.rank < dop.world - 1 else None
+    _lib.check(_lib.lib().stefan_ipdg_apply(dop.op._h, ctypes.c_void_p(slab.x.data_ptr()),
+                                            ctypes.c_void_p(out.data_ptr()), lo, hi, 0, _stream_ptr()))
+    if publish:
+        slab.release()
+    return out

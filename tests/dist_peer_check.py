@@ -1,0 +1,106 @@
+"""Multi-GPU check of the column-slab partition (run under torchrun, one rank per GPU):
+peer-memory halos (one launch, neighbours' columns read over NVLink) and the NCCL
+send/recv halos both reproduce the one-GPU operator.  Prints 'PEER CHECK OK' on rank 0.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \\
+        --master-port 29511 tests/dist_peer_check.py [--time]
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from stefanproblem_b200 import cutcelldg as cc  # noqa: E402
+from stefanproblem_b200.distributed import DistributedIPOperator, PeerSlab, apply_peer, slab_range  # noqa: E402
+
+
+def column_phase(nxg, ny, i):
+    j = np.arange(ny)
+    cx, cy = (i + 0.5) / nxg, (j + 0.5) / ny
+    return np.where((cx - 0.5) ** 2 + (cy - 0.5) ** 2 < 0.16, -1, 1).astype(np.int8)
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+    worst = 0.0
+    for order in (1, 2, 3):
+        for nxg, ny in ((24 * world + 5, 95), (16 * world, 64)):
+            nf = (order + 1) ** 2
+            pen = 1e3 * nxg
+            dop = DistributedIPOperator(nxg, ny, (1.0, 1.0), order, order + 1, 1.0, 2.0, pen, 1.0, 0.5,
+                                        lambda i: column_phase(nxg, ny, i), rank, world)
+            # the whole mesh on every rank, plain kernel: the reference
+            basis = cc.LagrangeTensorProductBasis(2, order)
+            phase = np.concatenate([column_phase(nxg, ny, i) for i in range(nxg)])
+            full = cc.IPOperator(cc.UniformMesh([0, 0], [1, 1], [nxg, ny], basis, phase=phase), order, order + 1,
+                                 1.0, 2.0, pen, 1.0, 0.5, "current", 255)
+            xg = torch.from_numpy(np.random.default_rng(5).uniform(-1, 1, nxg * ny * nf)).cuda()
+            yref = full.apply(xg, algo=1)
+            i0, i1 = slab_range(nxg, world, rank)
+            sl = slice(i0 * ny * nf, i1 * ny * nf)
+            # peer-memory halos, two epochs (the second after every rank rewrote its vector)
+            slab = PeerSlab(dop.ndofs, rank, world)
+            out = torch.empty(dop.ndofs, dtype=torch.float64, device="cuda")
+            for epoch in range(2):
+                slab.wait_released()
+                slab.x.copy_(xg[sl] * (1.0 + epoch))
+                apply_peer(dop, slab, out)
+                err = float((out - yref[sl] * (1.0 + epoch)).norm() / yref[sl].norm())
+                worst = max(worst, err)
+            torch.cuda.synchronize()
+            assert int(slab.status.item()) == 0, "a peer wait timed out"
+            # NCCL halos
+            out2 = torch.empty_like(out)
+            dop.apply(xg[sl].clone(), out2)
+            worst = max(worst, float((out2 - yref[sl]).norm() / yref[sl].norm()))
+            dist.barrier()
+            slab.close()
+    t = torch.tensor([worst], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    assert float(t.item()) < 1e-13, f"slab partition differs from the one-GPU operator: {float(t.item()):.3e}"
+    if rank == 0:
+        print(f"PEER CHECK OK world={world} worst relative difference {float(t.item()):.2e}", flush=True)
+
+    if "--time" in sys.argv:
+        order, nxl, ny = 1, 5000, 5000
+        nxg = nxl * world
+        dop = DistributedIPOperator(nxg, ny, (1.0, 1.0), order, order + 1, 1.0, 2.0, 1e3 * nxg, 1.0, 0.5,
+                                    lambda i: column_phase(nxg, ny, i), rank, world)
+        slab = PeerSlab(dop.ndofs, rank, world)
+        slab.x.uniform_(-1, 1)
+        out = torch.empty(dop.ndofs, dtype=torch.float64, device="cuda")
+        x2 = slab.x.clone()
+        for name, fn in (("peer, static x", lambda: apply_peer(dop, slab, out, publish=False)),
+                         ("peer, publish/wait/release per apply", lambda: apply_peer(dop, slab, out)),
+                         ("nccl send/recv + 3 launches", lambda: dop.apply(x2, out))):
+            slab.publish()
+            slab.wait_neighbours()
+            for _ in range(5):
+                fn()
+            dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(50):
+                fn()
+            e1.record()
+            dist.barrier()
+            torch.cuda.synchronize()
+            ms = torch.tensor([e0.elapsed_time(e1) / 50], dtype=torch.float64, device="cuda")
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            if rank == 0:
+                print(f"  {name}: {float(ms):.4f} ms/apply  {dop.ndofs * world / float(ms) / 1e6:.1f} GDOF/s on {world} GPUs",
+                      flush=True)
+        assert int(slab.status.item()) == 0
+        slab.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
