@@ -5,8 +5,12 @@ Workload (BASELINE.json `configs[4]`): uniform 2-D mesh of Q_p c
 two phases (circle of radius 0.4, k1 = 1, k2 = 2), mesh-aligned interface with
 flux + penalty + Robin terms (lambda = 1), Dirichlet boundary, pen = 1e3 * nx.
 Default p = 1, 5000 x 5000 cells per GPU = 100 M dofs per GPU (weak scaling: rank r
-owns the r-th slab of 5000 cell columns of a (5000 N) x 5000 mesh; one halo cell
-column per neighbour is exchanged over NCCL before every application).
+owns the r-th slab of 5000 cell columns of a (5000 N) x 5000 mesh).  N > 1: the slab
+vectors live in CUDA-IPC peer memory and every rank's apply kernel reads its neighbours'
+edge columns over NVLink itself (`--halo peer`, the default: one launch per application,
+ordered by epoch flags that are published / waited for / released inside the timed
+step); `--halo nccl` exchanges the columns with NCCL send/recv on a side stream,
+overlapped with the interior columns.
 
 One "step" = one application of the operator.  `value` = dofs x steps / seconds with
 x resident in HBM; `e2e` = the same through stefan_ipdg_apply_host (host buffers,
@@ -120,7 +124,7 @@ def run_ours(args):
     p, nxl, ny = args.order, args.nx, args.ny
     nf = (p + 1) ** 2
     nxg = nxl * world
-    from stefanproblem_b200.distributed import DistributedIPOperator
+    from stefanproblem_b200.distributed import DistributedIPOperator, PeerSlab, apply_peer
     dop = DistributedIPOperator(nxg, ny, (1.0, 1.0), p, p + 1, 1.0, 2.0, 1e3 * nxg, 1.0, 0.5,
                                 lambda i: column_phase(nxg, ny, i), rank, world)
     op = dop.op
@@ -130,10 +134,21 @@ def run_ours(args):
     x = torch.rand(ndofs_local, dtype=torch.float64, device="cuda", generator=gen) * 2 - 1
     y = torch.empty_like(x)
     x_lo, x_hi = dop.halo.x_lo, dop.halo.x_hi
+    peer = world > 1 and args.halo == "peer"
+    slab = None
+    if peer:
+        slab = PeerSlab(ndofs_local, rank, world)
+        slab.x.copy_(x)
+        x = slab.x
 
     def step():
-        # halo trace exchange (NCCL, side stream) overlapped with the interior columns
-        dop.apply(x, y)
+        if peer:
+            # publish my vector's epoch, wait for the neighbours', ONE apply launch that reads
+            # their edge columns over NVLink, release
+            apply_peer(dop, slab, y)
+        else:
+            # halo trace exchange (NCCL, side stream) overlapped with the interior columns
+            dop.apply(x, y)
 
     def barrier():
         if world > 1:
@@ -165,7 +180,10 @@ def run_ours(args):
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k0.record()
     for _ in range(args.steps):
-        op.apply(x, out=y, x_lo=x_lo, x_hi=x_hi)
+        if peer:
+            apply_peer(dop, slab, y, publish=False)
+        else:
+            op.apply(x, out=y, x_lo=x_lo, x_hi=x_hi)
     k1.record()
     torch.cuda.synchronize()
     kernel_ms = k0.elapsed_time(k1) / args.steps
@@ -194,7 +212,16 @@ def run_ours(args):
         cpu_baseline = cpu_port_baseline(p, seconds=6.0)
 
     if rank == 0:
-        launches = args.steps * (1 if world == 1 else 3)  # N > 1: interior + two edge columns
+        # N > 1, nccl halos: interior + two edge columns; peer halos: apply + signal / wait / release
+        launches = args.steps * (1 if world == 1 else (3 if not peer else 3 + (2 if world > 2 else 1)))
+        if peer:
+            assert int(slab.status.item()) == 0, "a peer-flag wait timed out"
+        partition = (f"{world} column slabs; neighbours' edge columns read over NVLink from CUDA-IPC peer memory "
+                     "inside the apply kernel (epoch flags published / waited / released every step)") if peer else (
+                     f"{world} column slabs; 1 halo cell column per neighbour over NCCL send/recv, "
+                     "overlapped with the interior columns")
+        if world == 1:
+            partition = "1 slab (no halo)"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -203,8 +230,7 @@ def run_ours(args):
                 "workload": f"IP-DG p={p} matrix-free apply, two-phase circle + Robin interface, "
                             f"{nxl}x{ny} cells per GPU ({ndofs_local / 1e6:.1f} M dofs per GPU)",
                 "order": p, "cells_per_gpu": [nxl, ny], "global_cells": [nxg, ny],
-                "global_dofs": total_dofs, "partition": f"{world} column slabs; 1 halo cell column per neighbour over NCCL send/recv, "
-                             "overlapped with the interior columns",
+                "global_dofs": total_dofs, "partition": partition,
                 "l2": "inputs larger than L2 (x and y are 800 MB each per GPU at the default size)",
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -221,6 +247,8 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
+        if slab is not None:
+            slab.close()
         dist.destroy_process_group()
 
 
@@ -307,6 +335,7 @@ def main():
     ap.add_argument("--nx", type=int, default=0, help="cell columns per GPU")
     ap.add_argument("--ny", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"], help="N > 1: how the halo columns travel")
     ap.add_argument("--traffic-bytes", type=float, default=None,
                     help="dram bytes per launch from the committed ncu capture (profiles/)")
     args = ap.parse_args()

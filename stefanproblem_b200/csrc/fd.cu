@@ -17,6 +17,9 @@
 #include "../../include/stefan_b200.h"
 #include "common.cuh"
 
+#include <algorithm>
+#include <cstdlib>
+
 #include <vector>
 
 namespace stefan {
@@ -45,6 +48,7 @@ struct FdHandle {
   std::vector<FdContinuity> cont;
   FdContinuity* cont_dev;
   bool cont_dirty;
+  bool force_scalar;  // STEFAN_FD_SCALAR=1: always the shared-memory kernel (tests)
 };
 
 constexpr int kFdThreads = 256;
@@ -104,6 +108,94 @@ fd_apply_kernel(const double* __restrict__ u, const double* __restrict__ u_lo,
       const int row = kd & 7;
       const bool laplace = row == FD_CENTRAL || row == FD_BACKWARD || row == FD_FORWARD;
       y[g] = laplace ? c[0] + ((kd & FD_PHASE2) ? dtk2 : dtk1) * r : c[0];
+    }
+  }
+}
+
+// Vector form of the same kernel (production path when u, y are 32-byte aligned): a thread
+// owns 4 consecutive nodes -- one 32-byte load, one 32-byte store (whole sectors), the 4
+// row kinds in one 32-bit load -- and gets the 3 + 3 stencil neighbours from lanes -+1 by
+// warp shuffles; only the first / last lane of a warp reads its outer neighbours from
+// global memory.  No shared memory, no barrier; 17 B of HBM traffic per node.
+__device__ __forceinline__ void ld_global_v4(const double* p, double* v) {
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+__device__ __forceinline__ void st_global_v4f(double* p, const double* v) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+fd_apply_vec(const double* __restrict__ u, const double* __restrict__ u_lo, const double* __restrict__ u_hi,
+             double* __restrict__ y, const uint8_t* __restrict__ kind, int64_t n, double inv_h2, double dtk1,
+             double dtk2, const FdContinuity* __restrict__ cont, int ncont) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nvec = (n + 3) / 4;
+  const int64_t nvec_w = (nvec + 31) / 32 * 32;  // whole warps stay in the loop (shuffles)
+  auto node = [&](int64_t g) -> double {       // u[g] with the slab halos / zeros outside
+    if (g >= 0 && g < n) return u[g];
+    if (g < 0 && g >= -3 && u_lo != nullptr) return u_lo[3 + g];
+    if (g >= n && g < n + 3 && u_hi != nullptr) return u_hi[g - n];
+    return 0.0;
+  };
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec_w;
+       v += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t g0 = 4 * v;
+    double w[10];  // u[g0-3 .. g0+6]
+    if (g0 + 3 < n) {
+      ld_global_v4(u + g0, w + 3);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) w[3 + k] = node(g0 + k);
+    }
+    w[0] = __shfl_up_sync(0xffffffffu, w[4], 1);
+    w[1] = __shfl_up_sync(0xffffffffu, w[5], 1);
+    w[2] = __shfl_up_sync(0xffffffffu, w[6], 1);
+    w[7] = __shfl_down_sync(0xffffffffu, w[3], 1);
+    w[8] = __shfl_down_sync(0xffffffffu, w[4], 1);
+    w[9] = __shfl_down_sync(0xffffffffu, w[5], 1);
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) w[k] = node(g0 - 3 + k);
+    }
+    if (lane == 31) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) w[7 + k] = node(g0 + 4 + k);
+    }
+    if (v >= nvec) continue;
+    const unsigned kinds = *reinterpret_cast<const unsigned*>(kind + g0);
+    double r[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double* c = w + 3 + k;
+      const unsigned kd = (kinds >> (8 * k)) & 0xffu;
+      const unsigned row = kd & 7u;
+      double t = 0.0;
+      if (row == FD_CENTRAL) t = (c[-1] - 2.0 * c[0] + c[1]) * inv_h2;
+      else if (row == FD_BACKWARD) t = (-c[-3] + 4.0 * c[-2] - 5.0 * c[-1] + 2.0 * c[0]) * inv_h2;
+      else if (row == FD_FORWARD) t = (2.0 * c[0] - 5.0 * c[1] + 4.0 * c[2] - c[3]) * inv_h2;
+      else if (row == FD_IDENTITY) t = c[0];
+      else if (row == FD_CONTINUITY) {
+        for (int q = 0; q < ncont; ++q)
+          if (cont[q].node == g0 + k) {
+            const double rr = cont[q].r, ss = cont[q].s;
+            t += rr * c[-2] - 4.0 * rr * c[-1] + (1.0 + 3.0 * rr) * c[0] - (1.0 + 3.0 * ss) * c[1] +
+                 4.0 * ss * c[2] - ss * c[3];
+          }
+      }
+      if (MODE == 0) {
+        r[k] = t;
+      } else {
+        const bool laplace = row == FD_CENTRAL || row == FD_BACKWARD || row == FD_FORWARD;
+        r[k] = laplace ? c[0] + ((kd & FD_PHASE2) ? dtk2 : dtk1) * t : c[0];
+      }
+    }
+    if (g0 + 3 < n) {
+      st_global_v4f(y + g0, r);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (g0 + k < n) y[g0 + k] = r[k];
     }
   }
 }
@@ -199,6 +291,7 @@ int stefan_fd_create(int64_t numnodes, double stepsize, const int8_t* phaseid, i
   h->has_lo = phase_lo != nullptr;
   h->has_hi = phase_hi != nullptr;
   h->kind_dev = nullptr;
+  h->force_scalar = getenv("STEFAN_FD_SCALAR") != nullptr && getenv("STEFAN_FD_SCALAR")[0] == '1';
   h->cont_dev = nullptr;
   h->cont_dirty = false;
   h->kind_host.assign((size_t)n, FD_EMPTY);
@@ -239,7 +332,7 @@ int stefan_fd_create(int64_t numnodes, double stepsize, const int8_t* phaseid, i
   }
   for (int64_t i = 0; i < n; ++i)
     if (phaseid[i] == 2) h->kind_host[(size_t)i] |= FD_PHASE2;
-  cudaError_t e = cudaMalloc(&h->kind_dev, (size_t)n);
+  cudaError_t e = cudaMalloc(&h->kind_dev, (size_t)n + 4);  // + 4: the vector kernel reads 4 row kinds at once
   if (e == cudaSuccess) e = cudaMemcpy(h->kind_dev, h->kind_host.data(), (size_t)n, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
     delete h;
@@ -284,6 +377,20 @@ static int fd_launch(FdHandle* h, int mode, const double* u, double* y, const do
   const int blocks = (int)((h->n + kFdTile - 1) / kFdTile);
   const double inv_h2 = 1.0 / (h->h * h->h);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool vec = ((reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(y)) & 31) == 0 && !h->force_scalar;
+  if (vec) {
+    const int64_t nthreads = ((h->n + 3) / 4 + 31) / 32 * 32;
+    static const int per_sm = [] { const char* e = getenv("STEFAN_FD_BLOCKS_PER_SM"); return e ? atoi(e) : 16; }();
+    const int vb = (int)std::min<int64_t>((nthreads + 255) / 256, (int64_t)sm_count() * per_sm);
+    if (mode == 0)
+      fd_apply_vec<0><<<vb, 256, 0, st>>>(u, u_lo, u_hi, y, h->kind_dev, h->n, inv_h2, 0, 0, h->cont_dev,
+                                          (int)h->cont.size());
+    else
+      fd_apply_vec<1><<<vb, 256, 0, st>>>(u, u_lo, u_hi, y, h->kind_dev, h->n, inv_h2, dtk1, dtk2, h->cont_dev,
+                                          (int)h->cont.size());
+    STEFAN_CUDA(cudaGetLastError());
+    return ST_OK;
+  }
   if (mode == 0)
     fd_apply_kernel<0><<<blocks, kFdThreads, 0, st>>>(u, u_lo, u_hi, y, h->kind_dev, h->n, inv_h2, 0, 0,
                                                       h->cont_dev, (int)h->cont.size());

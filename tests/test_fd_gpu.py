@@ -22,11 +22,14 @@ def _phase(n, interfaces):
     return ofd.phase_id(phi)
 
 
+@pytest.mark.parametrize("scalar", ["0", "1"])
 @pytest.mark.parametrize("n,interfaces", [(9, [0.5]), (64, [0.3]), (1000, [0.2, 0.55, 0.8]),
-                                           (4099, [0.5]), (100003, [0.1, 0.9])])
-def test_apply_matches_oracle(cuda, n, interfaces):
+                                           (4099, [0.5]), (100003, [0.1, 0.9]), (131, [0.4]), (1 << 20, [0.37])])
+def test_apply_matches_oracle(cuda, monkeypatch, n, interfaces, scalar):
     import torch
     from stefanproblem_b200 import finite_difference as FD
+    # "1": the shared-memory kernel that misaligned vectors fall back to; "0": the vector kernel
+    monkeypatch.setenv("STEFAN_FD_SCALAR", scalar)
     ph = _phase(n, interfaces)
     if n == 9:  # the reference's own driver: phi = xI - x (phase 2 on the left)
         ph = ofd.phase_id(0.5 - np.linspace(0, 1, 9))
