@@ -151,6 +151,31 @@ int stefan_ipdg_interface_sums(stefan_ipdg* h, const double* u, const double* u_
 int stefan_ipdg_euler_update(stefan_ipdg* h, double* u, const double* y, const double* b, double dt,
                              void* stream);
 
+/* Solve A x = b by preconditioned conjugate gradients on the device (replaces the sparse
+ * direct solve `matrix \ rhs` of the reference's drivers, e.g.
+ * uncut_mesh_tests/test_uncut_IP_convergence.jl:90, for the symmetric `current` variant).
+ * x: initial guess in, solution out.  preconditioner 0 = none, 1 = block Jacobi (inverse of
+ * every cell's NF x NF diagonal block).  The residual is read back every check_every
+ * iterations (<= 0: 10).  Synchronous with respect to `stream`. */
+typedef struct {
+  int32_t max_iterations;
+  double rel_tolerance;   /* stop when ||b - A x|| <= rel_tolerance ||b|| */
+  int32_t preconditioner;
+  int32_t check_every;
+} stefan_cg_params;
+typedef struct {
+  int32_t iterations;
+  double residual_norm, rhs_norm;
+  int32_t converged;
+} stefan_cg_result;
+int stefan_ipdg_cg_solve(stefan_ipdg* h, const double* b, double* x, const stefan_cg_params* params,
+                         stefan_cg_result* result, void* stream);
+
+/* mesh_L2_error (useful_routines.jl:95-133) on the device: out2[0] = ||u_h - u_ex||_L2,
+ * out2[1] = ||u_ex||_L2 with the cell quadrature of the handle; uex_qp [ncells][numqp*numqp]
+ * are the exact solution's samples at the cell quadrature points (layout of f_qp). */
+int stefan_ipdg_l2_error(stefan_ipdg* h, const double* u, const double* uex_qp, double* out2_dev, void* stream);
+
 /* Same operation with HOST buffers (pinned memory recommended): host->device
  * copies, kernels and device->host copies of `nslabs` column slabs are pipelined
  * on three streams inside the call (nslabs <= 0: default).  Synchronous. */

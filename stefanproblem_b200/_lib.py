@@ -35,6 +35,18 @@ class IpdgParams(ctypes.Structure):
     ]
 
 
+class CgParams(ctypes.Structure):
+    """`stefan_cg_params`."""
+    _fields_ = [("max_iterations", ctypes.c_int32), ("rel_tolerance", ctypes.c_double),
+                ("preconditioner", ctypes.c_int32), ("check_every", ctypes.c_int32)]
+
+
+class CgResult(ctypes.Structure):
+    """`stefan_cg_result`."""
+    _fields_ = [("iterations", ctypes.c_int32), ("residual_norm", ctypes.c_double), ("rhs_norm", ctypes.c_double),
+                ("converged", ctypes.c_int32)]
+
+
 class LdgParams(ctypes.Structure):
     """`stefan_ldg_params` (include/stefan_b200.h)."""
     _fields_ = [
@@ -75,6 +87,9 @@ _SIGNATURES = {
     "stefan_ldg_rhs": (ctypes.c_int, [ctypes.c_void_p] * 5),
     "stefan_ldg_apply": (ctypes.c_int, [ctypes.c_void_p] * 6),
     "stefan_ldg_apply_algo": (ctypes.c_int, [ctypes.c_void_p] * 5 + [ctypes.c_int32, ctypes.c_void_p]),
+    "stefan_ipdg_cg_solve": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                            ctypes.POINTER(CgParams), ctypes.POINTER(CgResult), ctypes.c_void_p]),
+    "stefan_ipdg_l2_error": (ctypes.c_int, [ctypes.c_void_p] * 5),
     "stefan_peer_alloc": (ctypes.c_int, [ctypes.c_int64, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p]),
     "stefan_peer_free": (ctypes.c_int, [ctypes.c_void_p]),
     "stefan_peer_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]),

@@ -380,7 +380,7 @@ static int fd_launch(FdHandle* h, int mode, const double* u, double* y, const do
   const bool vec = ((reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(y)) & 31) == 0 && !h->force_scalar;
   if (vec) {
     const int64_t nthreads = ((h->n + 3) / 4 + 31) / 32 * 32;
-    static const int per_sm = [] { const char* e = getenv("STEFAN_FD_BLOCKS_PER_SM"); return e ? atoi(e) : 16; }();
+    static const int per_sm = [] { const char* e = getenv("STEFAN_FD_BLOCKS_PER_SM"); return e ? atoi(e) : 32; }();
     const int vb = (int)std::min<int64_t>((nthreads + 255) / 256, (int64_t)sm_count() * per_sm);
     if (mode == 0)
       fd_apply_vec<0><<<vb, 256, 0, st>>>(u, u_lo, u_hi, y, h->kind_dev, h->n, inv_h2, 0, 0, h->cont_dev,

@@ -306,6 +306,25 @@ class IPOperator:
         _lib.check(_lib.lib().stefan_ipdg_rhs(self._h, _ptr(f_qp), _ptr(g_qp), _ptr(out), _stream_ptr(stream)))
         return out
 
+    def solve(self, b, x0=None, tol=1e-12, maxiter=10000, preconditioner="block_jacobi", check_every=10):
+        """`matrix \\ rhs` by preconditioned CG on the device; returns (x, info dict)."""
+        import torch
+        x = torch.zeros_like(b) if x0 is None else x0.clone()
+        prm = _lib.CgParams(int(maxiter), float(tol), {"none": 0, "block_jacobi": 1}[preconditioner], int(check_every))
+        res = _lib.CgResult()
+        _lib.check(_lib.lib().stefan_ipdg_cg_solve(self._h, _ptr(b), _ptr(x), ctypes.byref(prm), ctypes.byref(res),
+                                                   _stream_ptr()))
+        return x, {"iterations": res.iterations, "residual_norm": res.residual_norm, "rhs_norm": res.rhs_norm,
+                   "converged": bool(res.converged)}
+
+    def l2_error(self, u, uex_qp):
+        """(||u_h - u_ex||_L2, ||u_ex||_L2) with the handle's cell quadrature (mesh_L2_error)."""
+        import torch
+        out = torch.empty(2, dtype=torch.float64, device="cuda")
+        _lib.check(_lib.lib().stefan_ipdg_l2_error(self._h, _ptr(u), _ptr(uex_qp), _ptr(out), _stream_ptr()))
+        e = out.cpu().numpy()
+        return float(e[0]), float(e[1])
+
     def to_coo(self, index_base=0):
         """(rows, cols, vals) device tensors of the assembled operator (the COO seam)."""
         import torch

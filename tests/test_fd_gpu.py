@@ -46,7 +46,8 @@ def test_apply_matches_oracle(cuda, monkeypatch, n, interfaces, scalar):
     # COO seam: same matrix as the reference's triplets
     r, c, v = (t.cpu().numpy() for t in op.to_coo())
     A = sp.coo_matrix((v, (r, c)), shape=(n, n)).tocsr()
-    assert abs(A - K).max() == 0.0 and A.nnz == K.nnz
+    # same structure; values to the last bit or two (1/h^2 is formed as 1/(h*h) on the host)
+    assert abs(A - K).max() <= 4e-16 * abs(K).max() and A.nnz == K.nnz
 
 
 def test_known_answer_of_the_reference_driver(cuda):

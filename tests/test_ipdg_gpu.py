@@ -226,3 +226,46 @@ def test_hundred_explicit_euler_steps(cuda, order):
         op.apply(u, out=y)
         op.euler_update(u, y, bd, dt)
     assert np.linalg.norm(u.cpu().numpy() - ref) <= 1e-10 * np.linalg.norm(ref)
+
+
+@pytest.mark.parametrize("order,n", [(1, 12), (2, 9), (3, 6)])
+@pytest.mark.parametrize("two_phase", [False, True])
+@pytest.mark.parametrize("precond", ["block_jacobi", "none"])
+def test_cg_solve_and_l2_error(cuda, order, n, two_phase, precond):
+    """`matrix \\ rhs` on the device (preconditioned CG over the matrix-free apply) against the
+    oracle's sparse direct solve, and mesh_L2_error on the device against the oracle's norm;
+    problem of uncut_mesh_tests/test_uncut_IP_convergence.jl:8-16 (trig solution, pen = 1e3/h)."""
+    import scipy.sparse.linalg as spla
+    import torch
+    from oracle.basis import LagrangeTensorProductBasis as OB
+    from oracle.mesh import CellQuadratures
+    from oracle.norms import integral_norm_on_mesh, mesh_L2_error
+    from stefanproblem_b200 import cutcelldg as cc
+    nq = order + 1
+    ex = lambda v: np.cos(2 * np.pi * v[0]) * np.sin(2 * np.pi * v[1])  # noqa: E731
+    src = lambda v: 8 * np.pi ** 2 * np.cos(2 * np.pi * v[0]) * np.sin(2 * np.pi * v[1])  # noqa: E731
+    omesh = UniformMesh2D([0, 0], [1, 1], [n, n], (order + 1) ** 2)
+    k1, k2, lam, Tm = 1.0, (2.0 if two_phase else 1.0), (1.0 if two_phase else 0.0), 0.5
+    if two_phase:
+        omesh.cellsign[:] = fast.circle_phase(omesh)
+    pen = 1e3 * n
+    A = fast.ip_matrix(omesh, order, nq, k1, k2, pen, lam)
+    b = fast.ip_rhs(omesh, order, nq, k1, k2, pen,
+                    fast.sample_cell_quadrature(omesh, nq, lambda x, y: src((x, y))),
+                    fast.sample_face_quadrature(omesh, nq, lambda x, y: ex((x, y))), lam, Tm)
+    xref = spla.spsolve(A.tocsc(), b)
+    basis = cc.LagrangeTensorProductBasis(2, order)
+    mesh = cc.UniformMesh([0, 0], [1, 1], [n, n], basis, phase=omesh.cellsign)
+    op = cc.IPOperator(mesh, order, nq, k1, k2, pen, lam, Tm, "current", ALL)
+    x, info = op.solve(torch.from_numpy(b).cuda(), tol=1e-13, maxiter=20000, preconditioner=precond)
+    assert info["converged"], info
+    assert np.linalg.norm(x.cpu().numpy() - xref) <= 1e-8 * np.linalg.norm(xref)
+    if precond == "block_jacobi":
+        _, plain = op.solve(torch.from_numpy(b).cuda(), tol=1e-13, maxiter=20000, preconditioner="none")
+        assert info["iterations"] <= plain["iterations"]
+    # error norms of the GPU solution against the exact solution
+    uex_qp = torch.from_numpy(fast.sample_cell_quadrature(omesh, nq, lambda xx, yy: ex((xx, yy)))).cuda()
+    err, ref = op.l2_error(x, uex_qp)
+    oerr = mesh_L2_error(xref[None, :], ex, OB(2, order), CellQuadratures(nq), omesh)[0]
+    oref = integral_norm_on_mesh(ex, CellQuadratures(nq), omesh, 1)[0]
+    assert abs(err - oerr) <= 1e-7 * oerr + 1e-12 and abs(ref - oref) <= 1e-12 * oref
