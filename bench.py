@@ -8,8 +8,7 @@ Default p = 1, 5000 x 5000 cells per GPU = 100 M dofs per GPU (weak scaling: ran
 owns the r-th slab of 5000 cell columns of a (5000 N) x 5000 mesh).  N > 1: the slab
 vectors live in CUDA-IPC peer memory and every rank's apply kernel reads its neighbours'
 edge columns over NVLink itself (`--halo peer`, the default: one launch per application,
-ordered by epoch flags that are published / waited for / released inside the timed
-step); `--halo nccl` exchanges the columns with NCCL send/recv on a side stream,
+ordered by epoch flags that the same kernel publishes, waits for and releases); `--halo nccl` exchanges the columns with NCCL send/recv on a side stream,
 overlapped with the interior columns.
 
 One "step" = one application of the operator.  `value` = dofs x steps / seconds with
@@ -124,7 +123,7 @@ def run_ours(args):
     p, nxl, ny = args.order, args.nx, args.ny
     nf = (p + 1) ** 2
     nxg = nxl * world
-    from stefanproblem_b200.distributed import DistributedIPOperator, PeerSlab, apply_peer
+    from stefanproblem_b200.distributed import DistributedIPOperator, PeerSlab, apply_peer, apply_peer_fused
     dop = DistributedIPOperator(nxg, ny, (1.0, 1.0), p, p + 1, 1.0, 2.0, 1e3 * nxg, 1.0, 0.5,
                                 lambda i: column_phase(nxg, ny, i), rank, world)
     op = dop.op
@@ -143,9 +142,10 @@ def run_ours(args):
 
     def step():
         if peer:
-            # publish my vector's epoch, wait for the neighbours', ONE apply launch that reads
-            # their edge columns over NVLink, release
-            apply_peer(dop, slab, y)
+            # ONE launch: the kernel publishes my vector's epoch, its warps wait for the
+            # neighbours' epoch before they read their edge columns over NVLink, its last CTA
+            # releases them
+            apply_peer_fused(dop, slab, y)
         else:
             # halo trace exchange (NCCL, side stream) overlapped with the interior columns
             dop.apply(x, y)
@@ -212,12 +212,12 @@ def run_ours(args):
         cpu_baseline = cpu_port_baseline(p, seconds=6.0)
 
     if rank == 0:
-        # N > 1, nccl halos: interior + two edge columns; peer halos: apply + signal / wait / release
-        launches = args.steps * (1 if world == 1 else (3 if not peer else 3 + (2 if world > 2 else 1)))
+        # N > 1, nccl halos: interior + two edge columns; peer halos: the one apply kernel
+        launches = args.steps * (3 if (world > 1 and not peer) else 1)
         if peer:
             assert int(slab.status.item()) == 0, "a peer-flag wait timed out"
         partition = (f"{world} column slabs; neighbours' edge columns read over NVLink from CUDA-IPC peer memory "
-                     "inside the apply kernel (epoch flags published / waited / released every step)") if peer else (
+                     "inside the apply kernel, which also publishes / waits for / releases the epoch flags: one launch per step") if peer else (
                      f"{world} column slabs; 1 halo cell column per neighbour over NCCL send/recv, "
                      "overlapped with the interior columns")
         if world == 1:

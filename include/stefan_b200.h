@@ -300,6 +300,23 @@ int stefan_peer_signal(uint64_t* flag, uint64_t epoch, void* stream);
 int stefan_peer_wait(const uint64_t* peer_flag, uint64_t epoch, int32_t timeout_ms, int32_t* status_dev,
                      void* stream);
 
+/* The same ordering fused into the apply kernel (one launch per application, nothing else
+ * on the stream): the kernel publishes *my_ready = epoch when it starts, the warps that fetch
+ * a neighbour's edge column (x_lo / x_hi = mapped peer addresses) first wait for *lo_ready /
+ * *hi_ready >= epoch, and the last CTA to finish publishes *my_done = epoch.  A rank that is
+ * about to overwrite its vector waits for its neighbours' my_done flags (stefan_peer_wait). */
+typedef struct {
+  uint64_t* my_ready;
+  uint64_t* my_done;
+  const uint64_t* lo_ready;   /* neighbours' my_ready flags in peer memory; NULL where there is none */
+  const uint64_t* hi_ready;
+  uint64_t epoch;             /* > 0, increasing */
+  int32_t timeout_ms;
+  int32_t* status;            /* device int32 set to 1 if a wait timed out; may be NULL */
+} stefan_peer_sync;
+int stefan_ipdg_apply_peer(stefan_ipdg* h, const double* x, double* y, const double* x_lo, const double* x_hi,
+                           const stefan_peer_sync* sync, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,6 +47,13 @@ class CgResult(ctypes.Structure):
                 ("converged", ctypes.c_int32)]
 
 
+class PeerSync(ctypes.Structure):
+    """`stefan_peer_sync`."""
+    _fields_ = [("my_ready", ctypes.c_void_p), ("my_done", ctypes.c_void_p), ("lo_ready", ctypes.c_void_p),
+                ("hi_ready", ctypes.c_void_p), ("epoch", ctypes.c_uint64), ("timeout_ms", ctypes.c_int32),
+                ("status", ctypes.c_void_p)]
+
+
 class LdgParams(ctypes.Structure):
     """`stefan_ldg_params` (include/stefan_b200.h)."""
     _fields_ = [
@@ -90,6 +97,7 @@ _SIGNATURES = {
     "stefan_ipdg_cg_solve": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                             ctypes.POINTER(CgParams), ctypes.POINTER(CgResult), ctypes.c_void_p]),
     "stefan_ipdg_l2_error": (ctypes.c_int, [ctypes.c_void_p] * 5),
+    "stefan_ipdg_apply_peer": (ctypes.c_int, [ctypes.c_void_p] * 5 + [ctypes.POINTER(PeerSync), ctypes.c_void_p]),
     "stefan_peer_alloc": (ctypes.c_int, [ctypes.c_int64, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p]),
     "stefan_peer_free": (ctypes.c_int, [ctypes.c_void_p]),
     "stefan_peer_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]),

@@ -47,7 +47,37 @@ struct ApplyArgs {
   const int32_t* fix;  // cells the march kernels leave to their tail (see fixup_tail)
   int nfix;
   unsigned zero;  // 0 at run time, unknown at compile time (see ipdg_march.cuh, slot release)
+  // peer-memory halos with the ordering fused into the kernel (stefan_ipdg_apply_peer);
+  // all null / 0 otherwise
+  unsigned long long* sync_my_ready;         // published at kernel start: "my x of this epoch is final"
+  unsigned long long* sync_my_done;          // published by the last CTA: "I am done reading my neighbours"
+  const unsigned long long* sync_lo_ready;   // neighbours' ready flags (peer memory)
+  const unsigned long long* sync_hi_ready;
+  unsigned long long sync_epoch, sync_timeout_ns;
+  int* sync_status;                          // set to 1 if a wait timed out
+  unsigned* sync_counter;                    // CTAs finished (local)
 };
+
+// Wait (acquire, system scope) until the neighbour has published `epoch`; bounded.
+__device__ __forceinline__ void peer_flag_wait(const unsigned long long* flag, unsigned long long epoch,
+                                               unsigned long long timeout_ns, int* status) {
+  unsigned long long t0, t, v;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+    if (v >= epoch) return;
+    __nanosleep(100);
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (t - t0 > timeout_ns) {
+      if (status) atomicExch(status, 1);
+      return;
+    }
+  }
+}
+__device__ __forceinline__ void peer_flag_publish(unsigned long long* flag, unsigned long long epoch) {
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(epoch) : "memory");
+}
 
 __device__ __forceinline__ int phase_at(const int8_t* __restrict__ ph, int ny, int i, int j) {
   return ph[(size_t)(i + 1) * (ny + 2) + (j + 1)];
@@ -106,6 +136,10 @@ __device__ __forceinline__ void fixup_tail(const IpTab<P>& tab, const ApplyArgs&
     const double* xc = a.x + cell * NF;
     const double* pl = (i > 0) ? xc - (size_t)a.ny * NF : a.x_lo + (size_t)j * NF;
     const double* pr = (i < a.nx - 1) ? xc + (size_t)a.ny * NF : a.x_hi + (size_t)j * NF;
+    if (a.sync_epoch != 0) {  // peer halos: the neighbour's column must be published
+      if (i == 0 && sL && a.sync_lo_ready) peer_flag_wait(a.sync_lo_ready, a.sync_epoch, a.sync_timeout_ns, a.sync_status);
+      if (i == a.nx - 1 && sR && a.sync_hi_ready) peer_flag_wait(a.sync_hi_ready, a.sync_epoch, a.sync_timeout_ns, a.sync_status);
+    }
 #pragma unroll
     for (int k = 0; k < NF; ++k) {
       X[k] = xc[k];
@@ -247,6 +281,7 @@ int stefan_ipdg_create(const stefan_ipdg_params* p, const int8_t* phase, const i
   h->has_hi = phase_hi != nullptr;
   h->phase_dev = nullptr;
   h->xh_dev = h->yh_dev = nullptr;
+  h->sync_counter_dev = nullptr;
   h->host_ready = false;
   h->tab_host = nullptr;
   const int NF = (p->order + 1) * (p->order + 1);
@@ -290,6 +325,7 @@ int stefan_ipdg_destroy(stefan_ipdg* hv) {
   if (!h) return ST_OK;
   if (h->phase_dev) cudaFree(h->phase_dev);
   h->plan.destroy();
+  if (h->sync_counter_dev) cudaFree(h->sync_counter_dev);
   if (h->xh_dev) cudaFree(h->xh_dev);
   if (h->yh_dev) cudaFree(h->yh_dev);
   if (h->host_ready) {
@@ -329,6 +365,39 @@ int stefan_ipdg_apply(stefan_ipdg* hv, const double* x, double* y, const double*
   STEFAN_REQUIRE(algo >= 0 && algo <= 1, "stefan_ipdg_apply: unknown algo %d", algo);
   ApplyArgs a{x, x_lo, x_hi, y, h->phase_dev, h->nx, h->ny, 1, 0, h->nx, nullptr, 0};
   return dispatch_apply(h, a, algo, static_cast<cudaStream_t>(stream));
+}
+
+// y = A x on a column slab whose halo columns are the neighbours' own vectors in peer memory,
+// with the ordering fused into the kernel: it publishes sync->my_ready = epoch when it starts
+// (everything the stream wrote to x before is final), the warps that fetch a neighbour's column
+// first wait for that neighbour's ready flag, and the last CTA publishes sync->my_done = epoch.
+int stefan_ipdg_apply_peer(stefan_ipdg* hv, const double* x, double* y, const double* x_lo, const double* x_hi,
+                           const stefan_peer_sync* sync, void* stream) {
+  IpdgHandle* h = reinterpret_cast<IpdgHandle*>(hv);
+  STEFAN_REQUIRE(h && x && y && sync && x != y, "stefan_ipdg_apply_peer: bad argument");
+  STEFAN_REQUIRE(h->has_lo == (x_lo != nullptr) && h->has_hi == (x_hi != nullptr),
+                 "stefan_ipdg_apply_peer: halo columns must be given exactly where the handle has halo phases");
+  STEFAN_REQUIRE(sync->epoch > 0 && sync->my_ready && sync->my_done && sync->timeout_ms > 0 &&
+                 (!x_lo || sync->lo_ready) && (!x_hi || sync->hi_ready),
+                 "stefan_ipdg_apply_peer: incomplete sync block");
+  const uintptr_t hmask = h->order == 2 ? 7 : 15;
+  STEFAN_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(x_lo) & hmask) == 0 && (reinterpret_cast<uintptr_t>(x_hi) & hmask) == 0,
+                 "stefan_ipdg_apply_peer: x, y must be 16-byte aligned (halo columns: 16, order 2: 8)");
+  if (h->sync_counter_dev == nullptr) {
+    STEFAN_CUDA(cudaMalloc(&h->sync_counter_dev, sizeof(unsigned)));
+    STEFAN_CUDA(cudaMemset(h->sync_counter_dev, 0, sizeof(unsigned)));
+  }
+  ApplyArgs a{x, x_lo, x_hi, y, h->phase_dev, h->nx, h->ny, 1, 0, h->nx, nullptr, 0};
+  a.sync_my_ready = reinterpret_cast<unsigned long long*>(sync->my_ready);
+  a.sync_my_done = reinterpret_cast<unsigned long long*>(sync->my_done);
+  a.sync_lo_ready = reinterpret_cast<const unsigned long long*>(sync->lo_ready);
+  a.sync_hi_ready = reinterpret_cast<const unsigned long long*>(sync->hi_ready);
+  a.sync_epoch = sync->epoch;
+  a.sync_timeout_ns = (unsigned long long)sync->timeout_ms * 1000000ull;
+  a.sync_status = sync->status;
+  a.sync_counter = h->sync_counter_dev;
+  return dispatch_apply(h, a, 0, static_cast<cudaStream_t>(stream));
 }
 
 // Rows of the cell columns [col_begin, col_end) only (same arguments otherwise).  Lets a

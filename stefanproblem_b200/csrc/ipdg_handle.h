@@ -19,6 +19,7 @@ struct IpdgHandle {
   int8_t* phase_dev;  // (nx+2)*(ny+2), padded
   MarchPlan plan;      // run lists, fix list and CTA tiles of the march kernel
   double *xh_dev, *yh_dev;       // device staging of the host path
+  unsigned* sync_counter_dev;    // finished-CTA counter of stefan_ipdg_apply_peer
   cudaStream_t hs[3];
   cudaEvent_t hev[64];
   bool host_ready;

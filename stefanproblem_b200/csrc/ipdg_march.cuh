@@ -219,6 +219,8 @@ ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
+  // peer halos: everything the stream wrote before this kernel is final -> publish my epoch
+  if (a.sync_epoch != 0 && blockIdx.x == 0 && threadIdx.x == 0) peer_flag_publish(a.sync_my_ready, a.sync_epoch);
 
   const int nstrips = (a.ny + kStripCells - 1) / kStripCells;
   const int4 myseg = segs.e[blockIdx.x];
@@ -260,6 +262,8 @@ ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const 
         mbar_arrive_s(bar);
         return;
       }
+      if (a.sync_epoch != 0 && (k < 0 || k >= a.nx))  // a neighbour's column: wait until it is published
+        peer_flag_wait(k < 0 ? a.sync_lo_ready : a.sync_hi_ready, a.sync_epoch, a.sync_timeout_ns, a.sync_status);
       if constexpr (C::TENSOR) {
         if (k >= 0 && k < a.nx) {
           mbar_expect_tx_s(bar, (unsigned)C::STAGE);
@@ -570,6 +574,17 @@ ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const 
     }
   }
   fixup_tail<P>(tab, a);
+  // peer halos: the last CTA to finish tells the neighbours that their columns are free
+  if (a.sync_epoch != 0) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(a.sync_counter, 1u) == gridDim.x - 1) {
+        *a.sync_counter = 0;
+        peer_flag_publish(a.sync_my_done, a.sync_epoch);
+      }
+    }
+  }
 }
 
 }  // namespace stefan

@@ -225,6 +225,30 @@ class PeerSlab:
             self._ptr = None
 
 
+def apply_peer_fused(dop, slab, out, timeout_ms=5000):
+    """out = A x for the slab vector `slab.x`: ONE kernel launch and nothing else on the stream.
+    The kernel publishes the slab's next epoch when it starts, its warps wait for the
+    neighbours' epoch right before they fetch the neighbours' edge columns over NVLink, and
+    its last CTA releases them (stefan_ipdg_apply_peer)."""
+    from . import _lib
+    from .cutcelldg import _stream_ptr
+    col = dop.halo.col
+    slab.epoch += 1
+    lo = hi = lo_f = hi_f = None
+    if dop.rank > 0:
+        lo = ctypes.c_void_p(slab.peer_column(dop.rank - 1, col, last=True))
+        lo_f = slab.peer_flag(dop.rank - 1, 0)
+    if dop.rank < dop.world - 1:
+        hi = ctypes.c_void_p(slab.peer_column(dop.rank + 1, col, last=False))
+        hi_f = slab.peer_flag(dop.rank + 1, 0)
+    sync = _lib.PeerSync(slab.my_flag(0), slab.my_flag(1), lo_f, hi_f, slab.epoch, int(timeout_ms),
+                         slab.status.data_ptr())
+    _lib.check(_lib.lib().stefan_ipdg_apply_peer(dop.op._h, ctypes.c_void_p(slab.x.data_ptr()),
+                                                 ctypes.c_void_p(out.data_ptr()), lo, hi, ctypes.byref(sync),
+                                                 _stream_ptr()))
+    return out
+
+
 def apply_peer(dop, slab, out, publish=True):
     """out = A x for the slab vector `slab.x` of a DistributedIPOperator: ONE kernel launch;
     the neighbours' edge columns are read from their PeerSlab memory over NVLink.

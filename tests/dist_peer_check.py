@@ -14,7 +14,8 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from stefanproblem_b200 import cutcelldg as cc  # noqa: E402
-from stefanproblem_b200.distributed import DistributedIPOperator, PeerSlab, apply_peer, slab_range  # noqa: E402
+from stefanproblem_b200.distributed import (DistributedIPOperator, PeerSlab, apply_peer, apply_peer_fused,  # noqa: E402
+                                            slab_range)
 
 
 def column_phase(nxg, ny, i):
@@ -46,10 +47,13 @@ def main():
             # peer-memory halos, two epochs (the second after every rank rewrote its vector)
             slab = PeerSlab(dop.ndofs, rank, world)
             out = torch.empty(dop.ndofs, dtype=torch.float64, device="cuda")
-            for epoch in range(2):
+            for epoch in range(4):
                 slab.wait_released()
                 slab.x.copy_(xg[sl] * (1.0 + epoch))
-                apply_peer(dop, slab, out)
+                if epoch % 2 == 0:
+                    apply_peer(dop, slab, out)        # signal / wait / apply / release launches
+                else:
+                    apply_peer_fused(dop, slab, out)  # everything inside the one apply launch
                 err = float((out - yref[sl] * (1.0 + epoch)).norm() / yref[sl].norm())
                 worst = max(worst, err)
             torch.cuda.synchronize()
@@ -77,6 +81,7 @@ def main():
         x2 = slab.x.clone()
         for name, fn in (("peer, static x", lambda: apply_peer(dop, slab, out, publish=False)),
                          ("peer, publish/wait/release per apply", lambda: apply_peer(dop, slab, out)),
+                         ("peer, ordering fused into the apply kernel", lambda: apply_peer_fused(dop, slab, out)),
                          ("nccl send/recv + 3 launches", lambda: dop.apply(x2, out))):
             slab.publish()
             slab.wait_neighbours()
