@@ -163,6 +163,40 @@ function apply_host!(y::Vector{Float64}, A::IPOperator, x::Vector{Float64})
     y
 end
 
+struct CgParams            # stefan_cg_params
+    max_iterations::Int32
+    rel_tolerance::Float64
+    preconditioner::Int32
+    check_every::Int32
+end
+struct CgResult            # stefan_cg_result
+    iterations::Int32
+    residual_norm::Float64
+    rhs_norm::Float64
+    converged::Int32
+end
+
+"`matrix \\ rhs` on the device: block-Jacobi preconditioned CG over the matrix-free apply."
+function Base.:\(A::IPOperator, b::CuVector{Float64}; tol = 1e-12, maxiter = 10000)
+    x = CUDA.zeros(Float64, length(b))
+    res = Ref(CgResult(0, 0.0, 0.0, 0))
+    check(ccall((:stefan_ipdg_cg_solve, lib), Cint,
+                (Ptr{Cvoid}, CuPtr{Float64}, CuPtr{Float64}, Ref{CgParams}, Ref{CgResult}, Ptr{Cvoid}),
+                A.handle, b, x, Ref(CgParams(maxiter, tol, 1, 10)), res, CUDA.stream().handle))
+    res[].converged == 1 || @warn "CG did not converge" res[]
+    x
+end
+
+"(||u_h - u_ex||, ||u_ex||) in L2 with the cell quadrature (`mesh_L2_error`, useful_routines.jl:95-133);
+`uex_qp` = exact solution at the cell quadrature points, [ncells][numqp^2]."
+function l2_error(A::IPOperator, u::CuVector{Float64}, uex_qp::CuVector{Float64})
+    out = CUDA.zeros(Float64, 2)
+    check(ccall((:stefan_ipdg_l2_error, lib), Cint,
+                (Ptr{Cvoid}, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, Ptr{Cvoid}),
+                A.handle, u, uex_qp, out, CUDA.stream().handle))
+    Tuple(Array(out))
+end
+
 "The COO seam: (rows, cols, vals) with Julia (1-based) indices, ready for `sparse(rows, cols, vals, N, N)`."
 function coo(A::IPOperator)
     n = ccall((:stefan_ipdg_coo_size, lib), Int64, (Ptr{Cvoid},), A.handle)
