@@ -247,6 +247,15 @@ int stefan_dg1d_apply(stefan_dg1d* h, const double* x, double* y, void* stream);
 int stefan_dg1d_rhs(stefan_dg1d* h, const double* f_qp, double TL, double TR, int32_t with_boundary,
                     double* b, void* stream);
 
+/* The COO seams of the LDG and DG1D systems (as stefan_ipdg_assemble_coo: dense blocks per
+ * cell and per existing neighbour, column-major inside a block, feed them to sparse()). */
+int64_t stefan_ldg_coo_size(const stefan_ldg* h);
+int stefan_ldg_assemble_coo(stefan_ldg* h, int64_t* rows, int64_t* cols, double* vals, int64_t capacity,
+                            int32_t index_base, int64_t* nnz_out, void* stream);
+int64_t stefan_dg1d_coo_size(const stefan_dg1d* h);
+int stefan_dg1d_assemble_coo(stefan_dg1d* h, int64_t* rows, int64_t* cols, double* vals, int64_t capacity,
+                             int32_t index_base, int64_t* nnz_out, void* stream);
+
 /* Right-hand side of assemble_LDG_rhs! (LDG_assembly.jl:93-131); f_qp / g_qp sampled as for
  * stefan_ipdg_rhs; b [3*nnodes] is overwritten. */
 int stefan_ldg_rhs(stefan_ldg* h, const double* f_qp, const double* g_qp, double* b, void* stream);

@@ -91,6 +91,12 @@ _SIGNATURES = {
                                          ctypes.POINTER(ctypes.c_void_p)]),
     "stefan_ldg_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "stefan_ldg_ndofs": (ctypes.c_int64, [ctypes.c_void_p]),
+    "stefan_ldg_coo_size": (ctypes.c_int64, [ctypes.c_void_p]),
+    "stefan_ldg_assemble_coo": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                               ctypes.c_int64, ctypes.c_int32, c_int64_p, ctypes.c_void_p]),
+    "stefan_dg1d_coo_size": (ctypes.c_int64, [ctypes.c_void_p]),
+    "stefan_dg1d_assemble_coo": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                ctypes.c_int64, ctypes.c_int32, c_int64_p, ctypes.c_void_p]),
     "stefan_ldg_rhs": (ctypes.c_int, [ctypes.c_void_p] * 5),
     "stefan_ldg_apply": (ctypes.c_int, [ctypes.c_void_p] * 6),
     "stefan_ldg_apply_algo": (ctypes.c_int, [ctypes.c_void_p] * 5 + [ctypes.c_int32, ctypes.c_void_p]),

@@ -18,6 +18,8 @@
 #include "common.cuh"
 #include "refelem.h"
 
+#include <algorithm>
+
 namespace stefan {
 
 enum Dg1dTerms : int {
@@ -37,15 +39,14 @@ struct Dg1dHandle {
   Dg1dTab tab;
 };
 
-__global__ void dg1d_apply_kernel(const __grid_constant__ Dg1dTab t, const double* __restrict__ x,
-                                  double* __restrict__ y) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= t.ncells) return;
+// rows of cell c; w / wl / wr: the dofs of the cell and of its left / right neighbour
+// (wl, wr are not read where there is no neighbour)
+__device__ __forceinline__ void dg1d_cell_rows(const Dg1dTab& t, int c, const double* __restrict__ w,
+                                               const double* __restrict__ wl, const double* __restrict__ wr,
+                                               double* __restrict__ out) {
   const int n1 = t.n1, P = n1 - 1;
   const int lab = c < t.ne1 ? 1 : 2;
   const double j = lab == 1 ? t.j1 : t.j2, k = lab == 1 ? t.k1 : t.k2;
-  const double* w = x + (size_t)c * n1;
-  double out[kMaxN1];
   for (int a = 0; a < n1; ++a) {
     double v = 0.0;
     if (t.terms & DG1D_GRADIENT)
@@ -68,7 +69,7 @@ __global__ void dg1d_apply_kernel(const __grid_constant__ Dg1dTab t, const doubl
     } else {
       const int labn = cn < t.ne1 ? 1 : 2;
       const double jn = labn == 1 ? t.j1 : t.j2, kn = labn == 1 ? t.k1 : t.k2;
-      const double* wn = x + (size_t)cn * n1;
+      const double* wn = side == 0 ? wl : wr;
       const double trN = wn[side == 0 ? P : 0];
       double dN = 0.0;  // neighbour's derivative along MY outward normal, at the shared point
       for (int b = 0; b < n1; ++b) dN += (side == 0 ? -t.dNR[b] : t.dNL[b]) / jn * wn[b];
@@ -82,7 +83,47 @@ __global__ void dg1d_apply_kernel(const __grid_constant__ Dg1dTab t, const doubl
     out[fnode] += e_term;
     for (int a = 0; a < n1; ++a) out[a] += (side == 0 ? -t.dNL[a] : t.dNR[a]) / j * g_coef;
   }
+}
+
+__global__ void dg1d_apply_kernel(const __grid_constant__ Dg1dTab t, const double* __restrict__ x,
+                                  double* __restrict__ y) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= t.ncells) return;
+  const int n1 = t.n1;
+  const double* w = x + (size_t)c * n1;
+  double out[kMaxN1];
+  dg1d_cell_rows(t, c, w, w - n1, w + n1, out);
   for (int a = 0; a < n1; ++a) y[(size_t)c * n1 + a] = out[a];
+}
+
+// The COO seam: blocks (cell, which = 0 diag / 1 left / 2 right) of n1 x n1 triplets,
+// existing neighbours only, cell by cell, column-major inside a block; every column is
+// the apply row function probed with a unit vector.  One thread per (cell, which, column).
+__global__ void dg1d_coo_kernel(const __grid_constant__ Dg1dTab t, int64_t index_base, int64_t* __restrict__ rows,
+                                int64_t* __restrict__ cols, double* __restrict__ vals) {
+  const int n1 = t.n1;
+  const int64_t nwork = (int64_t)t.ncells * 3 * n1;
+  for (int64_t wk = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; wk < nwork; wk += (int64_t)gridDim.x * blockDim.x) {
+    const int bcol = (int)(wk % n1);
+    const int64_t cw = wk / n1;
+    const int c = (int)(cw / 3), which = (int)(cw % 3);
+    if ((which == 1 && c == 0) || (which == 2 && c == t.ncells - 1)) continue;
+    // blocks before cell c: 3 per cell minus the missing left of cell 0 and (only counted
+    // for the last cell itself) nothing else; within the cell: diag, [left], [right]
+    const int64_t nb = (int64_t)c * 3 - (c > 0 ? 1 : 0) + (which > 0 ? 1 : 0) + (which > 1 && c > 0 ? 1 : 0);
+    const int64_t o = nb * n1 * n1 + (int64_t)bcol * n1;
+    double U[3][kMaxN1], out[kMaxN1];
+    for (int q = 0; q < 3; ++q)
+      for (int k = 0; k < kMaxN1; ++k) U[q][k] = 0.0;
+    U[which][bcol] = 1.0;
+    dg1d_cell_rows(t, c, U[0], U[1], U[2], out);
+    const int64_t cn = which == 0 ? c : which == 1 ? c - 1 : c + 1;
+    for (int a = 0; a < n1; ++a) {
+      rows[o + a] = (int64_t)c * n1 + a + index_base;
+      cols[o + a] = cn * n1 + bcol + index_base;
+      vals[o + a] = out[a];
+    }
+  }
 }
 
 __global__ void dg1d_rhs_kernel(const __grid_constant__ Dg1dTab t, const double* __restrict__ f_qp,
@@ -172,6 +213,29 @@ int stefan_dg1d_apply(stefan_dg1d* hv, const double* x, double* y, void* stream)
   Dg1dHandle* h = reinterpret_cast<Dg1dHandle*>(hv);
   STEFAN_REQUIRE(h && x && y && x != y, "stefan_dg1d_apply: bad argument");
   dg1d_apply_kernel<<<(h->tab.ncells + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(h->tab, x, y);
+  STEFAN_CUDA(cudaGetLastError());
+  return ST_OK;
+}
+
+int64_t stefan_dg1d_coo_size(const stefan_dg1d* hv) {
+  const Dg1dHandle* h = reinterpret_cast<const Dg1dHandle*>(hv);
+  if (!h) return -1;
+  const int64_t nc = h->tab.ncells, n1 = h->tab.n1;
+  return n1 * n1 * (nc + 2 * (nc - 1));
+}
+
+int stefan_dg1d_assemble_coo(stefan_dg1d* hv, int64_t* rows, int64_t* cols, double* vals, int64_t capacity,
+                             int32_t index_base, int64_t* nnz_out, void* stream) {
+  Dg1dHandle* h = reinterpret_cast<Dg1dHandle*>(hv);
+  STEFAN_REQUIRE(h && rows && cols && vals && nnz_out, "stefan_dg1d_assemble_coo: null argument");
+  STEFAN_REQUIRE(index_base == 0 || index_base == 1, "stefan_dg1d_assemble_coo: index_base must be 0 or 1");
+  *nnz_out = stefan_dg1d_coo_size(hv);
+  if (*nnz_out > capacity)
+    return fail(ST_CAPACITY, "stefan_dg1d_assemble_coo: %lld triplets, capacity %lld", (long long)*nnz_out,
+                (long long)capacity);
+  const int64_t nwork = (int64_t)h->tab.ncells * 3 * h->tab.n1;
+  const int blocks = (int)std::min<int64_t>((nwork + 127) / 128, 4096);
+  dg1d_coo_kernel<<<blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(h->tab, index_base, rows, cols, vals);
   STEFAN_CUDA(cudaGetLastError());
   return ST_OK;
 }

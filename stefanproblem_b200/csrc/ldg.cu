@@ -150,6 +150,57 @@ ldg_rhs_kernel(const __grid_constant__ LdgRhsTab t, const int8_t* __restrict__ p
   }
 }
 
+// The COO seam of the LDG system: block (cell, which) -> CD x CD triplets, which = 0 diag,
+// 1 left, 2 right, 3 down, 4 up; existing neighbours only; laid out cell by cell like the IP
+// seam.  Every column of a block is the apply row function probed with a unit vector, so the
+// triplets are by construction the matrix the apply kernels apply.  One thread per
+// (cell, which, column).
+template <int P>
+__global__ void __launch_bounds__(128)
+ldg_coo_kernel(const __grid_constant__ LdgTab<P> tab, const int8_t* __restrict__ phase, int nx, int ny,
+               int64_t index_base, int64_t* __restrict__ rows, int64_t* __restrict__ cols,
+               double* __restrict__ vals) {
+  constexpr int N1 = P + 1, NF = N1 * N1, CD = 3 * NF;
+  const int64_t nwork = (int64_t)nx * ny * 5 * CD;
+  for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < nwork;
+       w += (int64_t)gridDim.x * blockDim.x) {
+    const int bcol = (int)(w % CD);
+    const int64_t cw = w / CD;
+    const int64_t cell = cw / 5;
+    const int which = (int)(cw % 5);
+    const int i = (int)(cell / ny), j = (int)(cell % ny);
+    const bool exists = which == 0 || (which == 1 && i > 0) || (which == 2 && i < nx - 1) ||
+                        (which == 3 && j > 0) || (which == 4 && j < ny - 1);
+    if (!exists) continue;
+    const int64_t per = 1 + (i > 0) + (i < nx - 1);
+    int64_t nb = (int64_t)i * (ny + 2 * (int64_t)(ny - 1)) +
+                 (int64_t)ny * ((i > 1 ? i - 1 : 0) + (i < nx - 1 ? i : nx - 1));
+    nb += (int64_t)j * per + (j > 1 ? j - 1 : 0) + (j < ny - 1 ? j : ny - 1);
+    int before = 0;
+    if (which > 0) before += 1;
+    if (which > 1) before += (i > 0);
+    if (which > 2) before += (i < nx - 1);
+    if (which > 3) before += (j > 0);
+    const int64_t o = (nb + before) * CD * CD + (int64_t)bcol * CD;  // column-major inside the block
+    const int s = ldg_phase_at(phase, ny, i, j);
+    const int sL = ldg_phase_at(phase, ny, i - 1, j), sR = ldg_phase_at(phase, ny, i + 1, j);
+    const int sD = ldg_phase_at(phase, ny, i, j - 1), sU = ldg_phase_at(phase, ny, i, j + 1);
+    double U[5][CD], out[CD];
+    for (int q = 0; q < 5; ++q)
+      for (int k = 0; k < CD; ++k) U[q][k] = 0.0;
+    U[which][bcol] = 1.0;
+    ldg_cell_rows<P>(tab, s == 1 ? 0 : 1, ip_face_type(s, sL), ip_face_type(s, sR), ip_face_type(s, sD),
+                     ip_face_type(s, sU), U[0], U[1], U[2], U[3], U[4], out);
+    const int64_t ncell = which == 0 ? cell : which == 1 ? cell - ny : which == 2 ? cell + ny
+                          : which == 3 ? cell - 1 : cell + 1;
+    for (int a = 0; a < CD; ++a) {
+      rows[o + a] = cell * CD + a + index_base;
+      cols[o + a] = ncell * CD + bcol + index_base;
+      vals[o + a] = out[a];
+    }
+  }
+}
+
 }  // namespace stefan
 #include "ldg_march.cuh"
 namespace stefan {
@@ -285,6 +336,36 @@ int stefan_ldg_destroy(stefan_ldg* hv) {
 
 int64_t stefan_ldg_ndofs(const stefan_ldg* hv) {
   return hv ? reinterpret_cast<const LdgHandle*>(hv)->ndofs : -1;
+}
+
+int64_t stefan_ldg_coo_size(const stefan_ldg* hv) {
+  const LdgHandle* h = reinterpret_cast<const LdgHandle*>(hv);
+  if (!h) return -1;
+  const int64_t nx = h->nx, ny = h->ny, CD = 3 * (h->order + 1) * (h->order + 1);
+  return CD * CD * (nx * ny + 2 * (nx - 1) * ny + 2 * nx * (ny - 1));
+}
+
+int stefan_ldg_assemble_coo(stefan_ldg* hv, int64_t* rows, int64_t* cols, double* vals, int64_t capacity,
+                            int32_t index_base, int64_t* nnz_out, void* stream) {
+  LdgHandle* h = reinterpret_cast<LdgHandle*>(hv);
+  STEFAN_REQUIRE(h && rows && cols && vals && nnz_out, "stefan_ldg_assemble_coo: null argument");
+  STEFAN_REQUIRE(!h->has_lo && !h->has_hi, "stefan_ldg_assemble_coo: slab handles are not supported");
+  STEFAN_REQUIRE(index_base == 0 || index_base == 1, "stefan_ldg_assemble_coo: index_base must be 0 or 1");
+  *nnz_out = stefan_ldg_coo_size(hv);
+  if (*nnz_out > capacity)
+    return fail(ST_CAPACITY, "stefan_ldg_assemble_coo: %lld triplets, capacity %lld", (long long)*nnz_out,
+                (long long)capacity);
+  const int CD = 3 * (h->order + 1) * (h->order + 1);
+  const int64_t nwork = (int64_t)h->nx * h->ny * 5 * CD;
+  const int blocks = (int)std::min<int64_t>((nwork + 127) / 128, (int64_t)sm_count() * 32);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (h->order) {
+    case 1: ldg_coo_kernel<1><<<blocks, 128, 0, st>>>(*static_cast<LdgTab<1>*>(h->tab_host), h->phase_dev, h->nx, h->ny, index_base, rows, cols, vals); break;
+    case 2: ldg_coo_kernel<2><<<blocks, 128, 0, st>>>(*static_cast<LdgTab<2>*>(h->tab_host), h->phase_dev, h->nx, h->ny, index_base, rows, cols, vals); break;
+    case 3: ldg_coo_kernel<3><<<blocks, 128, 0, st>>>(*static_cast<LdgTab<3>*>(h->tab_host), h->phase_dev, h->nx, h->ny, index_base, rows, cols, vals); break;
+  }
+  STEFAN_CUDA(cudaGetLastError());
+  return ST_OK;
 }
 
 int stefan_ldg_rhs(stefan_ldg* hv, const double* f_qp, const double* g_qp, double* b, void* stream) {

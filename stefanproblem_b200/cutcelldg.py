@@ -395,6 +395,18 @@ class LDGOperator:
                                                     int(algo), _stream_ptr(stream)))
         return out
 
+    def to_coo(self, index_base=0):
+        """(rows, cols, vals) device tensors of the assembled operator (the COO seam)."""
+        import torch
+        n = int(_lib.lib().stefan_ldg_coo_size(self._h))
+        rows = torch.empty(n, dtype=torch.int64, device="cuda")
+        cols = torch.empty(n, dtype=torch.int64, device="cuda")
+        vals = torch.empty(n, dtype=torch.float64, device="cuda")
+        nnz = ctypes.c_int64()
+        _lib.check(_lib.lib().stefan_ldg_assemble_coo(self._h, _ptr(rows), _ptr(cols), _ptr(vals), n, index_base,
+                                                      ctypes.byref(nnz), _stream_ptr()))
+        return rows, cols, vals
+
     def rhs(self, f_qp=None, g_qp=None, stream=None):
         """b of `assemble_LDG_rhs!` from device samples (layout as IPOperator.rhs)."""
         import torch

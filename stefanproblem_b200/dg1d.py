@@ -140,6 +140,19 @@ class DG1DOperator:
     def __matmul__(self, x):
         return self.apply(x)
 
+    def to_coo(self, index_base=0):
+        """(rows, cols, vals) device tensors of the assembled operator (the COO seam)."""
+        import ctypes
+        import torch
+        n = int(_lib.lib().stefan_dg1d_coo_size(self._h))
+        rows = torch.empty(n, dtype=torch.int64, device="cuda")
+        cols = torch.empty(n, dtype=torch.int64, device="cuda")
+        vals = torch.empty(n, dtype=torch.float64, device="cuda")
+        nnz = ctypes.c_int64()
+        _lib.check(_lib.lib().stefan_dg1d_assemble_coo(self._h, _ptr(rows), _ptr(cols), _ptr(vals), n, index_base,
+                                                       ctypes.byref(nnz), _stream_ptr()))
+        return rows, cols, vals
+
     def rhs(self, f_qp=None, TL=0.0, TR=0.0, with_boundary=False, stream=None):
         import torch
         out = torch.empty(self.ndofs, dtype=torch.float64, device="cuda")

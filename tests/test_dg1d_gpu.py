@@ -63,6 +63,11 @@ def test_apply_and_rhs_match_oracle(cuda, p, nq, ne1, ne2):
     y = (op @ torch.from_numpy(x).cuda()).cpu().numpy()
     assert np.linalg.norm(y - M @ x) <= 1e-13 * np.linalg.norm(M @ x)
     assert np.linalg.norm(b.cpu().numpy() - r) <= 1e-13 * np.linalg.norm(r)
+    # COO seam: the triplets handed to sparse() give the oracle's matrix
+    import scipy.sparse as sp
+    rr, cc_, vv = (t.cpu().numpy() for t in op.to_coo(index_base=1))
+    B = sp.coo_matrix((vv, (rr - 1, cc_ - 1)), shape=M.shape).tocsr()
+    assert abs(B - M).max() <= 1e-13 * abs(M).max()
 
 
 def test_reference_robin_interface_test_on_gpu_operator(cuda):

@@ -34,6 +34,12 @@ def test_apply_matches_oracle(cuda, order, algo, nx, ny, two_phase, theta, pens)
     y = op.apply(torch.from_numpy(x).cuda(), algo=algo).cpu().numpy()
     yr = A @ x
     assert np.linalg.norm(y - yr) / np.linalg.norm(yr) < 1e-13
+    if algo == 0 and nx * ny <= 42:
+        # COO seam: the triplets handed to sparse() give the oracle's matrix
+        import scipy.sparse as sp
+        r, c, v = (t.cpu().numpy() for t in op.to_coo(index_base=1))
+        B = sp.coo_matrix((v, (r - 1, c - 1)), shape=A.shape).tocsr()
+        assert abs(A - B).max() < 1e-13 * abs(A).max()
 
 
 @pytest.mark.parametrize("order", [1, 2, 3])
