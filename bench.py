@@ -204,7 +204,7 @@ def run_ours(args):
         dt = (time.perf_counter() - t0) / n_e2e
         e2e = {"value": ndofs_local / dt, "unit": UNIT, "h2d_bytes_per_step": ndofs_local * 8,
                "d2h_bytes_per_step": ndofs_local * 8, "steps": n_e2e,
-               "api": "stefan_ipdg_apply_host (pinned host buffers, 16 pipelined slabs)"}
+               "api": "stefan_ipdg_apply_host (pinned host buffers, 32 pipelined slabs)"}
         del xh, yh
 
     cpu_baseline = None

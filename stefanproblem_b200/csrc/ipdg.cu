@@ -427,7 +427,7 @@ int stefan_ipdg_apply_host(stefan_ipdg* hv, const double* x_host, double* y_host
   STEFAN_REQUIRE(h && x_host && y_host, "stefan_ipdg_apply_host: null argument");
   STEFAN_REQUIRE(!h->has_lo && !h->has_hi,
                  "stefan_ipdg_apply_host: handles with halo columns take device buffers");
-  if (nslabs <= 0) nslabs = 16;
+  if (nslabs <= 0) nslabs = 32;  // measured: 16 slabs 5.38, 32 slabs 5.56 G dof/s (PCIe bound 5.84)
   nslabs = std::min<int>(std::min<int>(nslabs, 32), h->nx);
   if (!h->host_ready) {
     STEFAN_CUDA(cudaMalloc(&h->xh_dev, h->ndofs * sizeof(double)));

@@ -21,6 +21,7 @@
 #include <algorithm>
 #include <climits>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -48,17 +49,42 @@ struct MarchPlan {
   int32_t* fix_dev = nullptr;
   int nfix = 0;
 
+  std::vector<int4> runs_host;   // what compute() produced (kept: small, and the tests read it)
+  std::vector<int> run_ofs_host;
+  std::vector<int32_t> fix_host;
+
   // ph: padded phase array (nx+2) x (ny+2), 0 = no cell.  Returns a cudaError_t.
   cudaError_t build(const int8_t* ph, int nx_, int ny_, int group_warps_) {
+    compute(ph, nx_, ny_, group_warps_);
+    const std::vector<int4>& runs = runs_host;
+    const std::vector<int>& run_ofs = run_ofs_host;
+    const std::vector<int32_t>& fix = fix_host;
+    cudaError_t e = cudaMalloc(&runs_dev, runs.size() * sizeof(int4));
+    if (e == cudaSuccess) e = cudaMemcpy(runs_dev, runs.data(), runs.size() * sizeof(int4), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&run_ofs_dev, run_ofs.size() * sizeof(int));
+    if (e == cudaSuccess)
+      e = cudaMemcpy(run_ofs_dev, run_ofs.data(), run_ofs.size() * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && nfix > 0) e = cudaMalloc(&fix_dev, fix.size() * sizeof(int32_t));
+    if (e == cudaSuccess && nfix > 0)
+      e = cudaMemcpy(fix_dev, fix.data(), fix.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+    return e;
+  }
+
+  // the host part of build(): masks, run lists, fix list, mixed-column counts (no CUDA calls)
+  void compute(const int8_t* ph, int nx_, int ny_, int group_warps_) {
     nx = nx_;
     ny = ny_;
     group_warps = group_warps_;
     nstrips = (ny + kStripCells - 1) / kStripCells;
     ngroups = (nstrips + group_warps - 1) / group_warps;
     const int ld = ny + 2;
-    std::vector<int32_t> fix;
-    std::vector<int4> runs;
-    std::vector<int> run_ofs(nstrips);
+    std::vector<int32_t>& fix = fix_host;
+    std::vector<int4>& runs = runs_host;
+    std::vector<int>& run_ofs = run_ofs_host;
+    fix.clear();
+    runs.clear();
+    run_ofs.assign(nstrips, 0);
+    seg_cache.clear();
     std::vector<uint32_t> smask((size_t)nstrips * nx), pmask((size_t)nstrips * nx);
     for (int i = 0; i < nx; ++i) {
       const int8_t* col = ph + (size_t)(i + 1) * ld + 1;
@@ -100,15 +126,6 @@ struct MarchPlan {
     fix_col_ofs.assign(nx + 1, 0);
     for (int32_t cell : fix) fix_col_ofs[cell / ny + 1]++;
     for (int i = 0; i < nx; ++i) fix_col_ofs[i + 1] += fix_col_ofs[i];
-    cudaError_t e = cudaMalloc(&runs_dev, runs.size() * sizeof(int4));
-    if (e == cudaSuccess) e = cudaMemcpy(runs_dev, runs.data(), runs.size() * sizeof(int4), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMalloc(&run_ofs_dev, run_ofs.size() * sizeof(int));
-    if (e == cudaSuccess)
-      e = cudaMemcpy(run_ofs_dev, run_ofs.data(), run_ofs.size() * sizeof(int), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess && nfix > 0) e = cudaMalloc(&fix_dev, fix.size() * sizeof(int32_t));
-    if (e == cudaSuccess && nfix > 0)
-      e = cudaMemcpy(fix_dev, fix.data(), fix.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
-    return e;
   }
 
   void destroy() {
@@ -127,10 +144,11 @@ struct MarchPlan {
   //                                          #mixed columns of that strip in [c0, c1).
   // Segments are cut greedily at the largest c1 with cost <= T; T is bisected until the tile
   // count fits the CTA budget (one wave).  Cached per column range.
-  static constexpr int kMixedCost = 1;
+  int kMixedCost = 1;  // extra cost of a column where the strip mixes phases (STEFAN_MIXED_COST overrides)
   const SegCache& segments(int cbeg, int cend, int max_ctas) {
     for (const SegCache& c : seg_cache)
       if (c.cbeg == cbeg && c.cend == cend && c.max_ctas == max_ctas) return c;
+    if (const char* e = getenv("STEFAN_MIXED_COST")) kMixedCost = atoi(e);
     const int ng = ngroups, gw = group_warps;
     auto cost = [&](int g, int c0, int c1) {
       int mx = 0;

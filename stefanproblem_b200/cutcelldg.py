@@ -262,7 +262,7 @@ class IPOperator:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
+        if h and _lib is not None:  # (None during interpreter shutdown)
             _lib.lib().stefan_ipdg_destroy(h)
             self._h = None
 
@@ -379,7 +379,7 @@ class LDGOperator:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
+        if h and _lib is not None:  # (None during interpreter shutdown)
             _lib.lib().stefan_ldg_destroy(h)
             self._h = None
 

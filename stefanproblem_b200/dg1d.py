@@ -125,7 +125,7 @@ class DG1DOperator:
         self.shape = (self.ndofs, self.ndofs)
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and _lib is not None:  # (None during interpreter shutdown)
             _lib.lib().stefan_dg1d_destroy(self._h)
             self._h = None
 

@@ -65,7 +65,7 @@ class FDOperator:
         self.shape = (self.n, self.n)
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and _lib is not None:  # (None during interpreter shutdown)
             _lib.lib().stefan_fd_destroy(self._h)
             self._h = None
 

@@ -8,6 +8,7 @@
 #include <vector>
 #include "../../stefanproblem_b200/csrc/ipdg_tables.h"
 #include "../../stefanproblem_b200/csrc/ldg_tables.h"
+#include "../../stefanproblem_b200/csrc/march_plan.h"
 
 using namespace stefan;
 
@@ -89,4 +90,39 @@ extern "C" int hostcheck_ldg_apply(int order, int nx, int ny, int nq, double jx,
     case 3: return run_ldg<3>(nx, ny, nq, jx, jy, ph, phase, x, y);
   }
   return 3;
+}
+
+
+// The host plan of the march kernels (march_plan.h) for a mesh: run lists, fix list and the
+// CTA tiles of the column range [cbeg, cend).  phase: int8 +1/-1 per cell (no halos).
+// Outputs (caller-sized): runs [4 * nruns] (with the 3 sentinels per strip), run_ofs
+// [nstrips], fix [nx*ny], tiles [4 * 640]; counts come back through n_out[4] =
+// {nruns, nstrips, nfix, ntiles}.
+extern "C" int hostcheck_march_plan(int nx, int ny, const int8_t* phase, int group_warps, int cbeg, int cend,
+                                    int max_ctas, int* runs, int* run_ofs, int* fix, int* tiles, int* n_out) {
+  std::vector<int8_t> ph((size_t)(nx + 2) * (ny + 2), 0);
+  for (int i = 0; i < nx; ++i)
+    for (int j = 0; j < ny; ++j) ph[(size_t)(i + 1) * (ny + 2) + (j + 1)] = phase[(size_t)i * ny + j] == 1 ? 1 : 2;
+  MarchPlan plan;
+  plan.compute(ph.data(), nx, ny, group_warps);
+  const SegCache& sc = plan.segments(cbeg, cend, max_ctas);
+  for (size_t k = 0; k < plan.runs_host.size(); ++k) {
+    runs[4 * k + 0] = plan.runs_host[k].x;
+    runs[4 * k + 1] = plan.runs_host[k].y;
+    runs[4 * k + 2] = plan.runs_host[k].z;
+    runs[4 * k + 3] = plan.runs_host[k].w;
+  }
+  for (int s = 0; s < plan.nstrips; ++s) run_ofs[s] = plan.run_ofs_host[s];
+  for (int k = 0; k < plan.nfix; ++k) fix[k] = plan.fix_host[k];
+  for (int k = 0; k < sc.n; ++k) {
+    tiles[4 * k + 0] = sc.tab.e[k].x;
+    tiles[4 * k + 1] = sc.tab.e[k].y;
+    tiles[4 * k + 2] = sc.tab.e[k].z;
+    tiles[4 * k + 3] = sc.tab.e[k].w;
+  }
+  n_out[0] = (int)plan.runs_host.size();
+  n_out[1] = plan.nstrips;
+  n_out[2] = plan.nfix;
+  n_out[3] = sc.n;
+  return 0;
 }

@@ -62,7 +62,8 @@ def test_reference_tables(built_lib, order, numqp):
 def hostcheck():
     hc = os.path.join(ROOT, "tests", "hostcheck")
     so = os.path.join(hc, "_hostcheck.so")
-    subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-o", so, os.path.join(hc, "hostcheck.cpp")], check=True)
+    subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-I/usr/local/cuda/include", "-o", so,
+                    os.path.join(hc, "hostcheck.cpp")], check=True)
     return ctypes.CDLL(so)
 
 
@@ -161,3 +162,69 @@ def test_c_oracle_matches_numpy_oracle(order):
         x = np.random.default_rng(0).uniform(-1, 1, A.shape[0])
         for threads in (1, 0):
             assert np.linalg.norm(C.spmv(x, nthreads=threads) - A @ x) < 1e-13 * np.linalg.norm(A @ x)
+
+
+@pytest.mark.parametrize("nx,ny,warps,two_phase", [(40, 95, 8, True), (7, 6, 8, False), (257, 131, 4, True),
+                                                    (33, 1, 8, False), (1, 64, 4, True), (600, 90, 8, True)])
+@pytest.mark.parametrize("cbeg_frac,cend_frac,max_ctas", [(0.0, 1.0, 296), (0.0, 1.0, 7), (0.25, 0.8, 148)])
+def test_march_plan_invariants(hostcheck, nx, ny, warps, two_phase, cbeg_frac, cend_frac, max_ctas):
+    """Host plan of the march kernels (csrc/march_plan.h): the loop's store masks and the fix
+    list partition the cells exactly (interior-uniform cells vs the rest), phase masks and
+    modes are consistent with the phases, and the CTA tiles cover every (strip group, column)
+    of the requested range exactly once within the CTA budget."""
+    rng = np.random.default_rng(nx * 1000 + ny)
+    phase = np.ones((nx, ny), dtype=np.int8)
+    if two_phase:
+        i, j = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
+        phase[((i + 0.5) / nx - 0.5) ** 2 + ((j + 0.5) / ny - 0.45) ** 2 < 0.1] = -1
+        phase[rng.integers(0, nx, 5), rng.integers(0, ny, 5)] *= -1  # a few isolated cells
+    cbeg, cend = int(cbeg_frac * nx), max(int(cend_frac * nx), int(cbeg_frac * nx) + 1)
+    nstrips = (ny + 29) // 30
+    runs = np.zeros(4 * (nstrips * (nx + 3)), dtype=np.int32)
+    run_ofs = np.zeros(nstrips, dtype=np.int32)
+    fix = np.zeros(nx * ny, dtype=np.int32)
+    tiles = np.zeros(4 * 640, dtype=np.int32)
+    n_out = np.zeros(4, dtype=np.int32)
+    ip = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_int))  # noqa: E731
+    rc = hostcheck.hostcheck_march_plan(nx, ny, np.ascontiguousarray(phase).ctypes.data_as(ctypes.POINTER(ctypes.c_int8)),
+                                        warps, cbeg, cend, max_ctas, ip(runs), ip(run_ofs), ip(fix), ip(tiles), ip(n_out))
+    assert rc == 0
+    nruns, ns, nfix, ntiles = (int(v) for v in n_out)
+    assert ns == nstrips
+    runs = runs[:4 * nruns].reshape(-1, 4)
+    # expected classification
+    P = np.zeros((nx + 2, ny + 2), dtype=np.int8)
+    P[1:-1, 1:-1] = np.where(phase == 1, 1, 2)
+    c = P[1:-1, 1:-1]
+    uniform = (P[:-2, 1:-1] == c) & (P[2:, 1:-1] == c) & (P[1:-1, :-2] == c) & (P[1:-1, 2:] == c)
+    # fix list = the non-uniform cells, sorted by cell id (hence by column)
+    expect_fix = np.flatnonzero(~uniform.ravel())
+    assert nfix == expect_fix.size and np.array_equal(fix[:nfix], expect_fix)
+    # run lists reproduce the masks column by column
+    for s in range(nstrips):
+        k, col = int(run_ofs[s]), 0
+        j0, j1 = 30 * s, min(30 * s + 30, ny)
+        while col < nx:
+            end, mode, pm, sm = (int(v) for v in runs[k])
+            pm &= 0xffffffff
+            sm &= 0xffffffff
+            assert col < end <= nx
+            for i in range(col, end):
+                exp_s = sum(1 << (j - j0 + 1) for j in range(j0, j1) if uniform[i, j])
+                exp_p = sum(1 << (j - j0 + 1) for j in range(j0, j1) if uniform[i, j] and c[i, j] == 2)
+                assert sm == exp_s and pm == exp_p
+            want = 0 if sm == 0 else (1 if pm == 0 else (2 if pm == sm else 3))
+            assert (mode & 3) == want
+            if sm:
+                t = sm >> ((sm & -sm).bit_length() - 1)
+                assert bool(mode & 4) == ((t & (t + 1)) == 0)
+            col, k = end, k + 1
+        assert all(int(v) == 2 ** 31 - 1 for v in runs[k:k + 3, 0])  # sentinels
+    # tiles: exact cover of [cbeg, cend) per group, within budget (or one tile per group)
+    ngroups = (nstrips + warps - 1) // warps
+    tiles = tiles[:4 * ntiles].reshape(-1, 4)
+    assert ntiles <= max(max_ctas, ngroups) and ntiles >= ngroups
+    for g in range(ngroups):
+        seg = sorted((int(t[1]), int(t[2])) for t in tiles if t[0] == g)
+        assert seg[0][0] == cbeg and seg[-1][1] == cend
+        assert all(a[1] == b[0] for a, b in zip(seg, seg[1:])) and all(a < b for a, b in seg)
