@@ -289,6 +289,50 @@ int64_t stefan_fd_nnz(stefan_fd* h);
 int stefan_fd_assemble_coo(stefan_fd* h, int64_t* rows, int64_t* cols, double* vals,
                            int64_t capacity, int64_t* nnz_out, void* stream);
 
+/* ------------------------------------------------------- element-block path
+ * The reference's element-local assembly for ARBITRARY per-cell / per-face quadratures (what
+ * a cut-cell mesh produces: CellQuadratures, FaceQuadratures, InterfaceQuadratures), and the
+ * application of the resulting dense blocks.  A "cell" is a solution cell (a cut cell
+ * contributes one per phase, with the interface as an extra face slot between the two).
+ * For every cell: gradient_operator (IP_gradient_operator.jl:1-9); for every face slot, seen
+ * from the cell (side 1, outward normal): the (1,1) and (1,2) blocks of
+ * assemble_face_flux_operator! (IP_flux_operator.jl:35-118), assemble_face_penalty_operator!
+ * (IP_penalty_operator.jl:21-65) and assemble_face_robin_operator!
+ * (IP_robin_interface_operator.jl:1-45); boundary slots: -(M + M') + pen P
+ * (IP_flux_operator.jl:330-357, IP_penalty_operator.jl:239-254).  All arrays are DEVICE arrays. */
+typedef struct {
+  int32_t ncells;   /* solution cells */
+  int32_t order;    /* 1..3 */
+  int32_t nqv;      /* volume quadrature points per cell (pad with weight 0) */
+  int32_t nslots;   /* face slots per cell, <= 8 */
+  int32_t nqf;      /* quadrature points per face slot (pad with weight 0) */
+} stefan_blocks_dims;
+typedef struct {
+  const double* vol_pts;       /* [ncells][nqv][2]  reference coordinates */
+  const double* vol_wts;       /* [ncells][nqv]     quadrature weights (detjac is applied inside) */
+  const double* cell_jac;      /* [ncells][2]       jacobian (hx/2, hy/2) */
+  const double* cell_k;        /* [ncells]          conductivity */
+  const int32_t* slot_nbr;     /* [ncells][nslots]  neighbour cell; -1 boundary face; -2 empty slot */
+  const double* face_pts;      /* [ncells][nslots][nqf][2]  own reference coordinates */
+  const double* face_nbr_pts;  /* [ncells][nslots][nqf][2]  the neighbour's reference coordinates */
+  const double* face_wts;      /* [ncells][nslots][nqf]     weight x scale area */
+  const double* face_normals;  /* [ncells][nslots][nqf][2]  pointing out of the cell */
+  const double* slot_pen;      /* [ncells][nslots]  penalty */
+  const double* slot_lambda;   /* [ncells][nslots]  Robin coefficient (0: no Robin term) */
+} stefan_blocks_data;
+typedef struct stefan_blocks stefan_blocks;
+int stefan_blocks_create(const stefan_blocks_dims* dims, stefan_blocks** out);
+int stefan_blocks_destroy(stefan_blocks* h);
+int64_t stefan_blocks_ndofs(const stefan_blocks* h);
+/* fills the blocks [ncells][1 + nslots][NF][NF] (diag, then one per slot) */
+int stefan_blocks_assemble(stefan_blocks* h, const stefan_blocks_data* data, void* stream);
+/* y = A x with the assembled blocks; 16 + 8 (1 + nslots) NF bytes of HBM traffic per dof */
+int stefan_blocks_apply(stefan_blocks* h, const double* x, double* y, void* stream);
+/* the COO seam (explicit zeros for empty / boundary slots, as a dense block per slot) */
+int64_t stefan_blocks_coo_size(const stefan_blocks* h);
+int stefan_blocks_assemble_coo(stefan_blocks* h, int64_t* rows, int64_t* cols, double* vals, int64_t capacity,
+                               int32_t index_base, int64_t* nnz_out, void* stream);
+
 /* ------------------------------------------------------------- peer memory
  * Column-slab partition across the GPUs of one NVLink domain, one process per GPU (the
  * reference is single-process; this is the multi-GPU extension of SURVEY.md 8(e)).  A slab

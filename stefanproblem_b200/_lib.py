@@ -54,6 +54,19 @@ class PeerSync(ctypes.Structure):
                 ("status", ctypes.c_void_p)]
 
 
+class BlocksDims(ctypes.Structure):
+    """`stefan_blocks_dims`."""
+    _fields_ = [("ncells", ctypes.c_int32), ("order", ctypes.c_int32), ("nqv", ctypes.c_int32),
+                ("nslots", ctypes.c_int32), ("nqf", ctypes.c_int32)]
+
+
+class BlocksData(ctypes.Structure):
+    """`stefan_blocks_data` (device pointers)."""
+    _fields_ = [(n, ctypes.c_void_p) for n in (
+        "vol_pts", "vol_wts", "cell_jac", "cell_k", "slot_nbr", "face_pts", "face_nbr_pts", "face_wts",
+        "face_normals", "slot_pen", "slot_lambda")]
+
+
 class LdgParams(ctypes.Structure):
     """`stefan_ldg_params` (include/stefan_b200.h)."""
     _fields_ = [
@@ -104,6 +117,14 @@ _SIGNATURES = {
                                             ctypes.POINTER(CgParams), ctypes.POINTER(CgResult), ctypes.c_void_p]),
     "stefan_ipdg_l2_error": (ctypes.c_int, [ctypes.c_void_p] * 5),
     "stefan_ipdg_apply_peer": (ctypes.c_int, [ctypes.c_void_p] * 5 + [ctypes.POINTER(PeerSync), ctypes.c_void_p]),
+    "stefan_blocks_create": (ctypes.c_int, [ctypes.POINTER(BlocksDims), ctypes.POINTER(ctypes.c_void_p)]),
+    "stefan_blocks_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "stefan_blocks_ndofs": (ctypes.c_int64, [ctypes.c_void_p]),
+    "stefan_blocks_assemble": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(BlocksData), ctypes.c_void_p]),
+    "stefan_blocks_apply": (ctypes.c_int, [ctypes.c_void_p] * 4),
+    "stefan_blocks_coo_size": (ctypes.c_int64, [ctypes.c_void_p]),
+    "stefan_blocks_assemble_coo": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                  ctypes.c_int64, ctypes.c_int32, c_int64_p, ctypes.c_void_p]),
     "stefan_peer_alloc": (ctypes.c_int, [ctypes.c_int64, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p]),
     "stefan_peer_free": (ctypes.c_int, [ctypes.c_void_p]),
     "stefan_peer_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]),

@@ -1,0 +1,131 @@
+"""Element-block path (`stefan_blocks_*`): the reference's element-local assembly for
+arbitrary per-cell / per-face quadratures, and the application of the dense blocks.
+
+`uniform_mesh_block_data` produces the `stefan_blocks_data` arrays for an uncut uniform mesh
+(tensor Gauss rules, constant normals): the same system the matrix-free kernels apply, and
+the template for feeding `CellQuadratures` / `FaceQuadratures` / `InterfaceQuadratures`
+exported from a CutCellDG run (one solution cell per (cell, phase); the interface of a cut
+cell is an extra face slot between its two solution cells)."""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .cutcelldg import _ptr, _stream_ptr
+
+_FIELDS = ("vol_pts", "vol_wts", "cell_jac", "cell_k", "slot_nbr", "face_pts", "face_nbr_pts", "face_wts",
+           "face_normals", "slot_pen", "slot_lambda")
+
+
+class BlockSystem:
+    """Assembled dense element blocks on one GPU: `assemble(data)`, `A @ x`, `to_coo()`."""
+
+    def __init__(self, ncells, order, nqv, nslots, nqf):
+        import torch
+        if not torch.cuda.is_available():
+            raise _lib.StefanError(-1, "no CUDA device: stefanproblem_b200 has no CPU fallback")
+        self.dims = _lib.BlocksDims(int(ncells), int(order), int(nqv), int(nslots), int(nqf))
+        h = ctypes.c_void_p()
+        _lib.check(_lib.lib().stefan_blocks_create(ctypes.byref(self.dims), ctypes.byref(h)))
+        self._h = h
+        self.ndofs = int(_lib.lib().stefan_blocks_ndofs(h))
+        self.shape = (self.ndofs, self.ndofs)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h and _lib is not None:
+            _lib.lib().stefan_blocks_destroy(h)
+            self._h = None
+
+    def assemble(self, data, stream=None):
+        """data: dict of NumPy / torch arrays named like the fields of stefan_blocks_data."""
+        import torch
+        dev = {}
+        for name in _FIELDS:
+            a = data[name]
+            if not isinstance(a, torch.Tensor):
+                a = torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32 if name == "slot_nbr" else np.float64))
+            dev[name] = a.cuda().contiguous()
+        d = self.dims
+        expect = {"vol_pts": d.ncells * d.nqv * 2, "vol_wts": d.ncells * d.nqv, "cell_jac": d.ncells * 2,
+                  "cell_k": d.ncells, "slot_nbr": d.ncells * d.nslots, "face_pts": d.ncells * d.nslots * d.nqf * 2,
+                  "face_nbr_pts": d.ncells * d.nslots * d.nqf * 2, "face_wts": d.ncells * d.nslots * d.nqf,
+                  "face_normals": d.ncells * d.nslots * d.nqf * 2, "slot_pen": d.ncells * d.nslots,
+                  "slot_lambda": d.ncells * d.nslots}
+        for name, n in expect.items():
+            if dev[name].numel() != n:
+                raise ValueError(f"{name}: {dev[name].numel()} values, expected {n}")
+        self._data = dev  # keep the device arrays alive until the kernel has run
+        bd = _lib.BlocksData(*[dev[n].data_ptr() for n in _FIELDS])
+        _lib.check(_lib.lib().stefan_blocks_assemble(self._h, ctypes.byref(bd), _stream_ptr(stream)))
+        return self
+
+    def apply(self, x, out=None, stream=None):
+        import torch
+        assert x.is_cuda and x.dtype == torch.float64 and x.is_contiguous() and x.numel() == self.ndofs
+        if out is None:
+            out = torch.empty_like(x)
+        _lib.check(_lib.lib().stefan_blocks_apply(self._h, _ptr(x), _ptr(out), _stream_ptr(stream)))
+        return out
+
+    def __matmul__(self, x):
+        return self.apply(x)
+
+    def to_coo(self, index_base=0):
+        import torch
+        n = int(_lib.lib().stefan_blocks_coo_size(self._h))
+        rows = torch.empty(n, dtype=torch.int64, device="cuda")
+        cols = torch.empty(n, dtype=torch.int64, device="cuda")
+        vals = torch.empty(n, dtype=torch.float64, device="cuda")
+        nnz = ctypes.c_int64()
+        _lib.check(_lib.lib().stefan_blocks_assemble_coo(self._h, _ptr(rows), _ptr(cols), _ptr(vals), n, index_base,
+                                                         ctypes.byref(nnz), _stream_ptr()))
+        return rows, cols, vals
+
+
+def uniform_mesh_block_data(nx, ny, hx, hy, numqp, phase, k1, k2, penalty, lam=0.0, aligned_interface=True):
+    """`stefan_blocks_data` arrays (NumPy) of an uncut uniform nx x ny mesh of two phases.
+
+    Slots: 0 bottom, 1 right, 2 top, 3 left.  Faces between unlike phases: coupled with
+    flux + penalty + Robin(lam) if aligned_interface, else empty slots
+    (what the reference's drivers do on uncut cells, IP_flux_operator.jl:181)."""
+    gx, gw = np.polynomial.legendre.leggauss(numqp)
+    ncells = nx * ny
+    phase = np.asarray(phase).reshape(nx, ny)
+    jx, jy = 0.5 * hx, 0.5 * hy
+    X, Y = np.meshgrid(gx, gx, indexing="ij")
+    vol_pts = np.broadcast_to(np.stack([X.ravel(), Y.ravel()], axis=1), (ncells, numqp * numqp, 2)).copy()
+    vol_wts = np.broadcast_to(np.outer(gw, gw).ravel(), (ncells, numqp * numqp)).copy()
+    cell_jac = np.broadcast_to(np.array([jx, jy]), (ncells, 2)).copy()
+    cell_k = np.where(phase.ravel() == 1, k1, k2).astype(float)
+    t, one = gx, np.ones(numqp)
+    own = [np.stack([t, -one], 1), np.stack([one, t], 1), np.stack([t, one], 1), np.stack([-one, t], 1)]
+    nbr = [np.stack([t, one], 1), np.stack([-one, t], 1), np.stack([t, -one], 1), np.stack([one, t], 1)]
+    normal = [(0.0, -1.0), (1.0, 0.0), (0.0, 1.0), (-1.0, 0.0)]
+    sa = [jx, jy, jx, jy]
+    step = [(0, -1), (1, 0), (0, 1), (-1, 0)]
+    slot_nbr = np.full((ncells, 4), -2, dtype=np.int32)
+    face_pts = np.zeros((ncells, 4, numqp, 2))
+    face_nbr_pts = np.zeros((ncells, 4, numqp, 2))
+    face_wts = np.zeros((ncells, 4, numqp))
+    face_normals = np.zeros((ncells, 4, numqp, 2))
+    slot_pen = np.zeros((ncells, 4))
+    slot_lambda = np.zeros((ncells, 4))
+    for s in range(4):
+        face_pts[:, s], face_nbr_pts[:, s] = own[s], nbr[s]
+        face_wts[:, s] = gw * sa[s]
+        face_normals[:, s] = normal[s]
+    for i in range(nx):
+        for j in range(ny):
+            c = i * ny + j
+            for s, (di, dj) in enumerate(step):
+                ii, jj = i + di, j + dj
+                if ii < 0 or ii >= nx or jj < 0 or jj >= ny:
+                    slot_nbr[c, s], slot_pen[c, s] = -1, penalty
+                elif phase[ii, jj] == phase[i, j]:
+                    slot_nbr[c, s], slot_pen[c, s] = ii * ny + jj, penalty
+                elif aligned_interface:
+                    slot_nbr[c, s], slot_pen[c, s], slot_lambda[c, s] = ii * ny + jj, penalty, lam
+    return {"vol_pts": vol_pts, "vol_wts": vol_wts, "cell_jac": cell_jac, "cell_k": cell_k, "slot_nbr": slot_nbr,
+            "face_pts": face_pts, "face_nbr_pts": face_nbr_pts, "face_wts": face_wts, "face_normals": face_normals,
+            "slot_pen": slot_pen, "slot_lambda": slot_lambda}

@@ -1,0 +1,287 @@
+// Element-block path: the reference's element-local assembly with ARBITRARY per-cell and
+// per-face quadratures (what a cut-cell mesh produces), and the application of the blocks.
+//
+// The uniform-mesh kernels (ipdg_march.cuh) never form an element matrix: on an uncut
+// uniform mesh every block is a Kronecker product of 1-D tables.  A cut / merged cell has
+// its own quadrature points, weights, interface normals and scale areas, so its blocks have
+// to be assembled the way the reference does it -- quadrature loops over dense NF x NF
+// outer products:
+//   gradient_operator                 IP_gradient_operator.jl:1-9     sum k G G' detjac w
+//   flux_operator                     IP_flux_operator.jl:1-33        sum k (G n) V' sa w
+//   assemble_face_flux_operator!      IP_flux_operator.jl:35-118      M11 + M11', -M12 + M21'
+//   mass_operator / face penalty      IP_penalty_operator.jl:1-65     pen sum V V' sa w (+, -)
+//   assemble_face_robin_operator!     IP_robin_interface_operator.jl:1-45   lambda/4 sum V V' sa w
+//   boundary flux / penalty           IP_flux_operator.jl:330-357, IP_penalty_operator.jl:239-254
+// Cell-centric form: a solution cell (a cut cell contributes one per phase) has `nslots`
+// face slots; for every slot the caller gives the quadrature points in the cell's own and
+// in the neighbour's reference coordinates, weight x scale area, and the normal pointing out
+// of the cell.  Seen from the cell (side 1), with M11 = -1/2 sum k1 (G1 n) V1' w etc.:
+//     diag      += M11 + M11' + pen sum V1 V1' w + lambda/4 sum V1 V1' w
+//     off[slot]  = -M12 + M21' - pen sum V1 V2' w + lambda/4 sum V1 V2' w
+// which is exactly what the reference's face functions add to the (1,1) and (1,2) blocks;
+// the neighbour's own slot produces the reference's (2,2) and (2,1) blocks (its normal is
+// the opposite one).  Boundary slot: diag += -(M + M') + pen sum V1 V1' w, M = sum k1 (G1 n) V1' w.
+//
+// Assembly kernel: one thread per block entry (cell, a, b) -- coalesced block writes, no
+// atomics, every thread evaluates the two basis functions it needs at the quadrature points.
+// Apply kernel: one thread per row (cell, a); HBM-bound by the blocks: 16 + 8 (1 + nslots) NF
+// bytes per dof-update ("general block path").
+#include "../../include/stefan_b200.h"
+#include "common.cuh"
+
+#include <algorithm>
+
+namespace stefan {
+
+struct BlocksHandle {
+  stefan_blocks_dims d;
+  int nf;
+  double* blocks;       // [ncells][1 + nslots][nf][nf], row-major (row = test function)
+  int32_t* slot_nbr;    // [ncells][nslots] copy of the adjacency (apply needs it)
+  bool assembled;
+};
+
+// 1-D Lagrange basis on order+1 equispaced nodes of [-1, 1]: value and derivative of N_i at x
+template <int P>
+__device__ __forceinline__ void lagrange_vd(int i, double x, double& v, double& d) {
+  constexpr int n = P + 1;
+  const double xi = -1.0 + 2.0 * i / P;
+  v = 1.0;
+  d = 0.0;
+#pragma unroll
+  for (int j = 0; j < n; ++j) {
+    if (j == i) continue;
+    const double xj = -1.0 + 2.0 * j / P;
+    v *= (x - xj) / (xi - xj);
+    double t = 1.0 / (xi - xj);
+#pragma unroll
+    for (int k = 0; k < n; ++k) {
+      if (k == i || k == j) continue;
+      const double xk = -1.0 + 2.0 * k / P;
+      t *= (x - xk) / (xi - xk);
+    }
+    d += t;
+  }
+}
+
+// value V_a(p) and physical gradient (dV/dx, dV/dy) of the tensor basis function a = ax (P+1) + ay
+template <int P>
+__device__ __forceinline__ void basis_vg(int a, double px, double py, double jx, double jy, double& v, double& gx,
+                                         double& gy) {
+  const int ax = a / (P + 1), ay = a % (P + 1);
+  double vx, dx, vy, dy;
+  lagrange_vd<P>(ax, px, vx, dx);
+  lagrange_vd<P>(ay, py, vy, dy);
+  v = vx * vy;
+  gx = dx * vy / jx;
+  gy = vx * dy / jy;
+}
+
+template <int P>
+__global__ void __launch_bounds__(128)
+blocks_assemble_kernel(const stefan_blocks_dims d, const stefan_blocks_data in, double* __restrict__ blocks) {
+  constexpr int NF = (P + 1) * (P + 1);
+  const int64_t nwork = (int64_t)d.ncells * NF * NF;
+  const int nb = 1 + d.nslots;
+  for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < nwork; w += (int64_t)gridDim.x * blockDim.x) {
+    const int cell = (int)(w / (NF * NF));
+    const int a = (int)((w / NF) % NF), b = (int)(w % NF);
+    const double jx = in.cell_jac[2 * cell], jy = in.cell_jac[2 * cell + 1], k1 = in.cell_k[cell];
+    double diag = 0.0;
+    // volume: sum k G_a . G_b detjac w
+    for (int q = 0; q < d.nqv; ++q) {
+      const double wq = in.vol_wts[(size_t)cell * d.nqv + q];
+      if (wq == 0.0) continue;
+      const double px = in.vol_pts[((size_t)cell * d.nqv + q) * 2], py = in.vol_pts[((size_t)cell * d.nqv + q) * 2 + 1];
+      double va, gax, gay, vb, gbx, gby;
+      basis_vg<P>(a, px, py, jx, jy, va, gax, gay);
+      basis_vg<P>(b, px, py, jx, jy, vb, gbx, gby);
+      diag += k1 * (gax * gbx + gay * gby) * (jx * jy) * wq;
+    }
+    double* out = blocks + ((size_t)cell * nb) * NF * NF + (size_t)a * NF + b;
+    for (int s = 0; s < d.nslots; ++s) {
+      const size_t cs = (size_t)cell * d.nslots + s;
+      const int nbr = in.slot_nbr[cs];
+      double off = 0.0;
+      if (nbr >= -1) {
+        const double pen = in.slot_pen[cs], lam4 = 0.25 * in.slot_lambda[cs];
+        double jx2 = jx, jy2 = jy, k2 = k1;
+        if (nbr >= 0) {
+          jx2 = in.cell_jac[2 * nbr];
+          jy2 = in.cell_jac[2 * nbr + 1];
+          k2 = in.cell_k[nbr];
+        }
+        for (int q = 0; q < d.nqf; ++q) {
+          const size_t fq = cs * d.nqf + q;
+          const double wq = in.face_wts[fq];
+          if (wq == 0.0) continue;
+          const double nx = in.face_normals[2 * fq], ny = in.face_normals[2 * fq + 1];
+          double v1a, g1ax, g1ay, v1b, g1bx, g1by;
+          basis_vg<P>(a, in.face_pts[2 * fq], in.face_pts[2 * fq + 1], jx, jy, v1a, g1ax, g1ay);
+          basis_vg<P>(b, in.face_pts[2 * fq], in.face_pts[2 * fq + 1], jx, jy, v1b, g1bx, g1by);
+          const double gn1a = g1ax * nx + g1ay * ny, gn1b = g1bx * nx + g1by * ny;
+          if (nbr >= 0) {
+            // M11[a][b] = -1/2 k1 gn1a v1b ; (M11 + M11')[a][b] = -1/2 k1 (gn1a v1b + gn1b v1a)
+            diag += (-0.5 * k1 * (gn1a * v1b + gn1b * v1a) + (pen + lam4) * v1a * v1b) * wq;
+            double v2b, g2bx, g2by;
+            basis_vg<P>(b, in.face_nbr_pts[2 * fq], in.face_nbr_pts[2 * fq + 1], jx2, jy2, v2b, g2bx, g2by);
+            const double gn2b = g2bx * nx + g2by * ny;
+            // -M12[a][b] = +1/2 k1 gn1a v2b ; M21'[a][b] = M21[b][a] = -1/2 k2 gn2b v1a
+            off += (0.5 * k1 * gn1a * v2b - 0.5 * k2 * gn2b * v1a + (lam4 - pen) * v1a * v2b) * wq;
+          } else {
+            // boundary: -(M + M') + pen P, M[a][b] = k1 gn1a v1b
+            diag += (-k1 * (gn1a * v1b + gn1b * v1a) + pen * v1a * v1b) * wq;
+          }
+        }
+      }
+      out[(size_t)(1 + s) * NF * NF] = off;
+    }
+    out[0] = diag;
+  }
+}
+
+template <int P>
+__global__ void __launch_bounds__(256)
+blocks_apply_kernel(int ncells, int nslots, const double* __restrict__ blocks, const int32_t* __restrict__ slot_nbr,
+                    const double* __restrict__ x, double* __restrict__ y) {
+  constexpr int NF = (P + 1) * (P + 1);
+  const int64_t nrows = (int64_t)ncells * NF;
+  const int nb = 1 + nslots;
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nrows; r += (int64_t)gridDim.x * blockDim.x) {
+    const int cell = (int)(r / NF), a = (int)(r % NF);
+    const double* B = blocks + ((size_t)cell * nb) * NF * NF + (size_t)a * NF;
+    const double* xc = x + (size_t)cell * NF;
+    double v = 0.0;
+#pragma unroll
+    for (int b = 0; b < NF; ++b) v += B[b] * xc[b];
+    for (int s = 0; s < nslots; ++s) {
+      const int nbr = slot_nbr[(size_t)cell * nslots + s];
+      if (nbr < 0) continue;
+      const double* Bo = B + (size_t)(1 + s) * NF * NF;
+      const double* xn = x + (size_t)nbr * NF;
+#pragma unroll
+      for (int b = 0; b < NF; ++b) v += Bo[b] * xn[b];
+    }
+    y[r] = v;
+  }
+}
+
+__global__ void blocks_coo_kernel(int ncells, int nslots, int nf, const double* __restrict__ blocks,
+                                  const int32_t* __restrict__ slot_nbr, int64_t index_base, int64_t* __restrict__ rows,
+                                  int64_t* __restrict__ cols, double* __restrict__ vals) {
+  const int nb = 1 + nslots;
+  const int64_t n = (int64_t)ncells * nb * nf * nf;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(e % nf), a = (int)((e / nf) % nf);
+    const int s = (int)((e / ((int64_t)nf * nf)) % nb);
+    const int cell = (int)(e / ((int64_t)nf * nf * nb));
+    const int nbr = s == 0 ? cell : slot_nbr[(size_t)cell * nslots + (s - 1)];
+    rows[e] = (int64_t)cell * nf + a + index_base;
+    cols[e] = (nbr >= 0 ? (int64_t)nbr * nf + b : (int64_t)cell * nf + b) + index_base;  // empty slots: explicit zeros
+    vals[e] = nbr >= 0 ? blocks[e] : 0.0;
+  }
+}
+
+}  // namespace stefan
+
+using namespace stefan;
+
+extern "C" {
+
+int stefan_blocks_create(const stefan_blocks_dims* dims, stefan_blocks** out) {
+  STEFAN_REQUIRE(dims && out, "stefan_blocks_create: null argument");
+  STEFAN_REQUIRE(dims->ncells >= 1 && dims->order >= 1 && dims->order <= 3, "stefan_blocks_create: bad ncells / order");
+  STEFAN_REQUIRE(dims->nqv >= 1 && dims->nslots >= 1 && dims->nslots <= 8 && dims->nqf >= 1,
+                 "stefan_blocks_create: need nqv >= 1, 1 <= nslots <= 8, nqf >= 1");
+  BlocksHandle* h = new BlocksHandle();
+  h->d = *dims;
+  h->nf = (dims->order + 1) * (dims->order + 1);
+  h->blocks = nullptr;
+  h->slot_nbr = nullptr;
+  h->assembled = false;
+  const size_t nbytes = (size_t)dims->ncells * (1 + dims->nslots) * h->nf * h->nf * sizeof(double);
+  cudaError_t e = cudaMalloc(&h->blocks, nbytes);
+  if (e == cudaSuccess) e = cudaMalloc(&h->slot_nbr, (size_t)dims->ncells * dims->nslots * sizeof(int32_t));
+  if (e != cudaSuccess) {
+    if (h->blocks) cudaFree(h->blocks);
+    delete h;
+    return fail(ST_CUDA_ERROR, "stefan_blocks_create: %s", cudaGetErrorString(e));
+  }
+  *out = reinterpret_cast<stefan_blocks*>(h);
+  return ST_OK;
+}
+
+int stefan_blocks_destroy(stefan_blocks* hv) {
+  BlocksHandle* h = reinterpret_cast<BlocksHandle*>(hv);
+  if (!h) return ST_OK;
+  if (h->blocks) cudaFree(h->blocks);
+  if (h->slot_nbr) cudaFree(h->slot_nbr);
+  delete h;
+  return ST_OK;
+}
+
+int64_t stefan_blocks_ndofs(const stefan_blocks* hv) {
+  const BlocksHandle* h = reinterpret_cast<const BlocksHandle*>(hv);
+  return h ? (int64_t)h->d.ncells * h->nf : -1;
+}
+
+int stefan_blocks_assemble(stefan_blocks* hv, const stefan_blocks_data* in, void* stream) {
+  BlocksHandle* h = reinterpret_cast<BlocksHandle*>(hv);
+  STEFAN_REQUIRE(h && in, "stefan_blocks_assemble: null argument");
+  STEFAN_REQUIRE(in->vol_pts && in->vol_wts && in->cell_jac && in->cell_k && in->slot_nbr && in->face_pts &&
+                 in->face_nbr_pts && in->face_wts && in->face_normals && in->slot_pen && in->slot_lambda,
+                 "stefan_blocks_assemble: every array of stefan_blocks_data is required");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  STEFAN_CUDA(cudaMemcpyAsync(h->slot_nbr, in->slot_nbr, (size_t)h->d.ncells * h->d.nslots * sizeof(int32_t),
+                              cudaMemcpyDeviceToDevice, st));
+  const int64_t nwork = (int64_t)h->d.ncells * h->nf * h->nf;
+  const int blocks = (int)std::min<int64_t>((nwork + 127) / 128, (int64_t)sm_count() * 64);
+  switch (h->d.order) {
+    case 1: blocks_assemble_kernel<1><<<blocks, 128, 0, st>>>(h->d, *in, h->blocks); break;
+    case 2: blocks_assemble_kernel<2><<<blocks, 128, 0, st>>>(h->d, *in, h->blocks); break;
+    case 3: blocks_assemble_kernel<3><<<blocks, 128, 0, st>>>(h->d, *in, h->blocks); break;
+  }
+  STEFAN_CUDA(cudaGetLastError());
+  h->assembled = true;
+  return ST_OK;
+}
+
+int stefan_blocks_apply(stefan_blocks* hv, const double* x, double* y, void* stream) {
+  BlocksHandle* h = reinterpret_cast<BlocksHandle*>(hv);
+  STEFAN_REQUIRE(h && x && y && x != y, "stefan_blocks_apply: bad argument");
+  STEFAN_REQUIRE(h->assembled, "stefan_blocks_apply: call stefan_blocks_assemble first");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t nrows = (int64_t)h->d.ncells * h->nf;
+  const int blocks = (int)std::min<int64_t>((nrows + 255) / 256, (int64_t)sm_count() * 32);
+  switch (h->d.order) {
+    case 1: blocks_apply_kernel<1><<<blocks, 256, 0, st>>>(h->d.ncells, h->d.nslots, h->blocks, h->slot_nbr, x, y); break;
+    case 2: blocks_apply_kernel<2><<<blocks, 256, 0, st>>>(h->d.ncells, h->d.nslots, h->blocks, h->slot_nbr, x, y); break;
+    case 3: blocks_apply_kernel<3><<<blocks, 256, 0, st>>>(h->d.ncells, h->d.nslots, h->blocks, h->slot_nbr, x, y); break;
+  }
+  STEFAN_CUDA(cudaGetLastError());
+  return ST_OK;
+}
+
+int64_t stefan_blocks_coo_size(const stefan_blocks* hv) {
+  const BlocksHandle* h = reinterpret_cast<const BlocksHandle*>(hv);
+  return h ? (int64_t)h->d.ncells * (1 + h->d.nslots) * h->nf * h->nf : -1;
+}
+
+int stefan_blocks_assemble_coo(stefan_blocks* hv, int64_t* rows, int64_t* cols, double* vals, int64_t capacity,
+                               int32_t index_base, int64_t* nnz_out, void* stream) {
+  BlocksHandle* h = reinterpret_cast<BlocksHandle*>(hv);
+  STEFAN_REQUIRE(h && rows && cols && vals && nnz_out, "stefan_blocks_assemble_coo: null argument");
+  STEFAN_REQUIRE(h->assembled, "stefan_blocks_assemble_coo: call stefan_blocks_assemble first");
+  STEFAN_REQUIRE(index_base == 0 || index_base == 1, "stefan_blocks_assemble_coo: index_base must be 0 or 1");
+  *nnz_out = stefan_blocks_coo_size(hv);
+  if (*nnz_out > capacity)
+    return fail(ST_CAPACITY, "stefan_blocks_assemble_coo: %lld triplets, capacity %lld", (long long)*nnz_out,
+                (long long)capacity);
+  const int blocks = (int)std::min<int64_t>((*nnz_out + 255) / 256, (int64_t)sm_count() * 32);
+  blocks_coo_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(h->d.ncells, h->d.nslots, h->nf, h->blocks,
+                                                                           h->slot_nbr, index_base, rows, cols, vals);
+  STEFAN_CUDA(cudaGetLastError());
+  return ST_OK;
+}
+
+}  // extern "C"
