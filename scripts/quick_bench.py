@@ -56,6 +56,41 @@ def run_ldg(order, n, two_phase, reps=20, algo=0):
           f"{16 * gdofs:.0f} GB/s  ({16 * gdofs / 6551 * 100:.1f}% of 6551)", flush=True)
 
 
+def run_blocks(order, n, reps=10):
+    """Element-block path on an n x n uniform two-phase mesh: assembly and block apply."""
+    from stefanproblem_b200 import blocks as B
+    nq, nf = order + 1, (order + 1) ** 2
+    i, j = np.divmod(np.arange(n * n), n)
+    phase = np.where(((i + 0.5) / n - 0.5) ** 2 + ((j + 0.5) / n - 0.5) ** 2 < 0.16, -1, 1).astype(np.int8)
+    data = B.uniform_mesh_block_data(n, n, 1.0 / n, 1.0 / n, nq, phase, 1.0, 2.0, 1e3 * n, 1.0)
+    data = {k: torch.from_numpy(v).cuda() for k, v in data.items()}
+    sys_ = B.BlockSystem(n * n, order, nq * nq, 4, nq)
+    sys_.assemble(data)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        sys_.assemble(data)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_a = e0.elapsed_time(e1) / 3
+    x = torch.rand(sys_.ndofs, dtype=torch.float64, device="cuda")
+    y = torch.empty_like(x)
+    for _ in range(3):
+        sys_.apply(x, out=y)
+    e0.record()
+    for _ in range(reps):
+        sys_.apply(x, out=y)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    bpd = 16 + 8 * 5 * nf
+    g = sys_.ndofs / ms / 1e6
+    print(f"blocks p={order} {n}x{n}: assemble {ms_a:.2f} ms ({n * n * 5 * nf * nf / ms_a / 1e6:.1f} G block entries/s, "
+          f"{n * n * 5 * nf * nf * 8 / ms_a / 1e6:.0f} GB/s written); apply {ms:.3f} ms  {g:.1f} GDOF/s  "
+          f"{bpd * g:.0f} GB/s  ({bpd * g / 6551 * 100:.1f}% of 6551 at {bpd} B/dof)", flush=True)
+
+
 def run_fd(n, reps=20):
     """FD Laplace apply / fused explicit step on n nodes, one interface in the middle."""
     from stefanproblem_b200 import finite_difference as FD
@@ -93,7 +128,12 @@ if __name__ == "__main__":
     ap.add_argument("--two-phase", type=int, default=1)
     ap.add_argument("--ldg", type=int, default=0)
     ap.add_argument("--fd", type=int, default=0)
+    ap.add_argument("--blocks", type=int, default=0)
     args = ap.parse_args()
+    if args.blocks:
+        for o in ([args.order] if args.order else [1, 2, 3]):
+            run_blocks(o, args.n or {1: 2000, 2: 1000, 3: 600}[o], args.reps)
+        sys.exit(0)
     if args.fd:
         run_fd(args.n or (1 << 27), args.reps)
         sys.exit(0)

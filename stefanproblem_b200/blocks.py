@@ -115,17 +115,21 @@ def uniform_mesh_block_data(nx, ny, hx, hy, numqp, phase, k1, k2, penalty, lam=0
         face_pts[:, s], face_nbr_pts[:, s] = own[s], nbr[s]
         face_wts[:, s] = gw * sa[s]
         face_normals[:, s] = normal[s]
-    for i in range(nx):
-        for j in range(ny):
-            c = i * ny + j
-            for s, (di, dj) in enumerate(step):
-                ii, jj = i + di, j + dj
-                if ii < 0 or ii >= nx or jj < 0 or jj >= ny:
-                    slot_nbr[c, s], slot_pen[c, s] = -1, penalty
-                elif phase[ii, jj] == phase[i, j]:
-                    slot_nbr[c, s], slot_pen[c, s] = ii * ny + jj, penalty
-                elif aligned_interface:
-                    slot_nbr[c, s], slot_pen[c, s], slot_lambda[c, s] = ii * ny + jj, penalty, lam
+    cid = np.arange(ncells, dtype=np.int64).reshape(nx, ny)
+    pp = np.zeros((nx + 2, ny + 2), dtype=np.int8)       # 0 = outside the mesh
+    pp[1:-1, 1:-1] = np.where(phase == 1, 1, 2)
+    idp = np.full((nx + 2, ny + 2), -1, dtype=np.int64)
+    idp[1:-1, 1:-1] = cid
+    for s, (di, dj) in enumerate(step):
+        pn = pp[1 + di:nx + 1 + di, 1 + dj:ny + 1 + dj]   # neighbour's phase code
+        idn = idp[1 + di:nx + 1 + di, 1 + dj:ny + 1 + dj]
+        same = pn == pp[1:-1, 1:-1]
+        outside = pn == 0
+        coupled = same | ((~outside) & bool(aligned_interface))
+        nb = np.where(outside, -1, np.where(coupled, idn, -2))
+        slot_nbr[:, s] = nb.ravel()
+        slot_pen[:, s] = np.where(outside | coupled, penalty, 0.0).ravel()
+        slot_lambda[:, s] = np.where((~outside) & (~same) & bool(aligned_interface), lam, 0.0).ravel()
     return {"vol_pts": vol_pts, "vol_wts": vol_wts, "cell_jac": cell_jac, "cell_k": cell_k, "slot_nbr": slot_nbr,
             "face_pts": face_pts, "face_nbr_pts": face_nbr_pts, "face_wts": face_wts, "face_normals": face_normals,
             "slot_pen": slot_pen, "slot_lambda": slot_lambda}
