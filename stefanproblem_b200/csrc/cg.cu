@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 namespace stefan {
@@ -257,7 +258,18 @@ int stefan_ipdg_cg_solve(stefan_ipdg* hv, const double* b, double* x, const stef
   STEFAN_REQUIRE(!h->has_lo && !h->has_hi, "stefan_ipdg_cg_solve: slab handles are not supported");
   STEFAN_REQUIRE(prm->max_iterations >= 0 && prm->rel_tolerance >= 0.0, "stefan_ipdg_cg_solve: bad parameters");
   STEFAN_REQUIRE(prm->preconditioner == 0 || prm->preconditioner == 1, "stefan_ipdg_cg_solve: unknown preconditioner");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // The iteration runs on a stream of its own (ordered after the caller's stream): a batch of
+  // iterations is captured into a CUDA graph and replayed, which the legacy default stream
+  // cannot do.  The call is synchronous, so the caller's stream sees the result on return.
+  cudaStream_t caller = static_cast<cudaStream_t>(stream), st = nullptr;
+  cudaEvent_t ordered = nullptr;
+  STEFAN_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  STEFAN_CUDA(cudaEventCreateWithFlags(&ordered, cudaEventDisableTiming));
+  STEFAN_CUDA(cudaEventRecord(ordered, caller));
+  STEFAN_CUDA(cudaStreamWaitEvent(st, ordered, 0));
+  stream = st;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t gexec = nullptr;
   const int64_t n = h->ndofs;
   const int64_t ncells = (int64_t)h->nx * h->ny;
   const int nblk = (int)std::min<int64_t>((ncells + kRedThreads - 1) / kRedThreads, (int64_t)sm_count() * 8);
@@ -270,8 +282,13 @@ int stefan_ipdg_cg_solve(stefan_ipdg* hv, const double* b, double* x, const stef
          *scal = part2 + std::max(nblk, vblk);
   int rc = ST_OK;
   auto cleanup = [&]() {
+    cudaStreamSynchronize(st);
+    if (gexec) cudaGraphExecDestroy(gexec);
+    if (graph) cudaGraphDestroy(graph);
     cudaFree(work);
     if (Binv) cudaFree(Binv);
+    cudaEventDestroy(ordered);
+    cudaStreamDestroy(st);
   };
 #define CG_CUDA(call)                                                                        \
   do {                                                                                       \
@@ -319,16 +336,38 @@ int stefan_ipdg_cg_solve(stefan_ipdg* hv, const double* b, double* x, const stef
   const double target = prm->rel_tolerance * (bnorm > 0 ? bnorm : 1.0);
   const int check = prm->check_every > 0 ? prm->check_every : 10;
   int it = 0;
-  while (it < prm->max_iterations && rnorm > target) {
-    const int batch = std::min(check, prm->max_iterations - it);
-    for (int k = 0; k < batch; ++k) {
-      rc = stefan_ipdg_apply(hv, p, Ap, nullptr, nullptr, 0, stream);
-      if (rc) { cleanup(); return rc; }
+  auto iterations = [&](int count) -> int {
+    for (int k = 0; k < count; ++k) {
+      int rc2 = stefan_ipdg_apply(hv, p, Ap, nullptr, nullptr, 0, stream);
+      if (rc2) return rc2;
       cg_dot_kernel<<<vblk, kRedThreads, 0, st>>>(p, Ap, n, part);
       cg_scalar_kernel<<<1, 1, 0, st>>>(part, nullptr, vblk, scal, 0);
       update(0);
       cg_scalar_kernel<<<1, 1, 0, st>>>(part, part2, nblk, scal, 1);
       cg_direction_kernel<<<vblk, kRedThreads, 0, st>>>(p, z, scal, 0, n);
+    }
+    return ST_OK;
+  };
+  // one batch of `check` iterations (6 launches each) as a CUDA graph: one launch per batch;
+  // what makes the small systems of the reference's convergence studies launch-bound
+  const bool use_graph = prm->max_iterations >= check && getenv("STEFAN_CG_NO_GRAPH") == nullptr;
+  if (use_graph && rnorm > target) {
+    rc = stefan_ipdg_apply(hv, p, Ap, nullptr, nullptr, 0, stream);  // warm-up outside the capture (attributes)
+    if (rc) { cleanup(); return rc; }
+    CG_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    rc = iterations(check);
+    cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (rc) { cleanup(); return rc; }
+    CG_CUDA(ce);
+    CG_CUDA(cudaGraphInstantiate(&gexec, graph, 0));
+  }
+  while (it < prm->max_iterations && rnorm > target) {
+    const int batch = std::min(check, prm->max_iterations - it);
+    if (gexec != nullptr && batch == check) {
+      CG_CUDA(cudaGraphLaunch(gexec, st));
+    } else {
+      rc = iterations(batch);
+      if (rc) { cleanup(); return rc; }
     }
     it += batch;
     CG_CUDA(cudaMemcpyAsync(hs, scal, 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
