@@ -135,7 +135,7 @@ cg_direction_kernel(double* __restrict__ p, const double* __restrict__ z, const 
                     int64_t n) {
   const double beta = first ? 0.0 : scal[3];
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    p[i] = z[i] + beta * p[i];
+    p[i] = first ? z[i] : z[i] + beta * p[i];  // (p is uninitialised before the first call)
 }
 
 __global__ void __launch_bounds__(kRedThreads)
