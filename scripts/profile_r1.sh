@@ -18,7 +18,7 @@ ncu --set full --clock-control none --import-source on -k regex:ldg_apply_march 
     python scripts/quick_bench.py --ldg 1 --order $o --n 2000 --reps 2 > gpurun_out/r1_ncu_ldg$o.log 2>&1
 done
 python scripts/quick_bench.py --fd 1 --reps 2 > gpurun_out/r1_plain_fd.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:fd_apply_kernel -s 3 -c 2 -f -o gpurun_out/r1_fd \
+ncu --set full --clock-control none --import-source on -k regex:fd_apply -s 3 -c 2 -f -o gpurun_out/r1_fd \
     python scripts/quick_bench.py --fd 1 --reps 2 > gpurun_out/r1_ncu_fd.log 2>&1
 { for o in 1 2 3; do python scripts/quick_bench.py --order $o --reps 50; python scripts/quick_bench.py --order $o --reps 50 --two-phase 0; done
   python scripts/quick_bench.py --ldg 1 --reps 50; python scripts/quick_bench.py --ldg 1 --n 2000 --reps 50

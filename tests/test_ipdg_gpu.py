@@ -46,6 +46,17 @@ def test_apply_matches_oracle(cuda, order, algo, nx, ny, two_phase, terms, varia
 
 
 @pytest.mark.parametrize("order", [1, 2, 3])
+@pytest.mark.parametrize("nx,ny", [(1, 1), (1, 7), (2, 1), (5, 29), (4, 30), (3, 31), (2, 61), (33, 2)])
+def test_degenerate_mesh_shapes(cuda, order, nx, ny):
+    """Single cells, single rows / columns, strips of exactly 29 / 30 / 31 cells."""
+    A, op, x, xd = _case(order, nx, ny, nx * ny > 8, ALL, "current")
+    yr = A @ x
+    for algo in (0, 1):
+        y = op.apply(xd, algo=algo).cpu().numpy()
+        assert np.linalg.norm(y - yr) <= TOL * np.linalg.norm(yr)
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
 def test_march_equals_simple_large(cuda, order):
     """Two independent kernels agree on a mesh with many strips / segments."""
     import torch

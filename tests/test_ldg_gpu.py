@@ -43,6 +43,27 @@ def test_apply_matches_oracle(cuda, order, algo, nx, ny, two_phase, theta, pens)
 
 
 @pytest.mark.parametrize("order", [1, 2, 3])
+@pytest.mark.parametrize("nx,ny", [(1, 1), (1, 7), (2, 1), (5, 29), (4, 30), (3, 31), (2, 61)])
+def test_degenerate_mesh_shapes(cuda, order, nx, ny):
+    """Single cells, single rows / columns, strips of exactly 29 / 30 / 31 cells."""
+    import torch
+    from stefanproblem_b200 import cutcelldg as cc
+    omesh = UniformMesh2D([0, 0], [1.0, 0.8], [nx, ny], (order + 1) ** 2)
+    if nx * ny > 8:
+        omesh.cellsign[:] = fast.circle_phase(omesh, (0.5, 0.4), 0.3)
+    V0 = np.array([np.cos(0.7), np.sin(0.7)])
+    A = fast.ldg_matrix(omesh, order, order + 1, 1.0, 2.0, 0.4, 0.3, 1.1, V0)
+    basis = cc.LagrangeTensorProductBasis(2, order)
+    mesh = cc.UniformMesh([0, 0], [1.0, 0.8], [nx, ny], basis, phase=omesh.cellsign)
+    op = cc.LDGOperator(mesh, order, order + 1, 1.0, 2.0, 0.4, 0.3, 1.1, V0)
+    x = np.random.default_rng(0).uniform(-1, 1, A.shape[0])
+    yr = A @ x
+    for algo in (1, 2):
+        y = op.apply(torch.from_numpy(x).cuda(), algo=algo).cpu().numpy()
+        assert np.linalg.norm(y - yr) <= 1e-13 * np.linalg.norm(yr)
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
 def test_march_equals_simple_large(cuda, order):
     """The two independent kernels agree on a mesh with many strips / segments (odd sizes)."""
     import torch
