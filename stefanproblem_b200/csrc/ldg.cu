@@ -17,6 +17,8 @@
 #include "ldg_tables.h"
 #include "march_dev.cuh"
 
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 namespace stefan {
@@ -205,8 +207,35 @@ ldg_coo_kernel(const __grid_constant__ LdgTab<P> tab, const int8_t* __restrict__
 #include "ldg_march.cuh"
 namespace stefan {
 
+// x (order 3: 384-byte cells) as a 2-D tensor {16 doubles, 3 ncells rows of 128 B}, tiles of
+// 96 rows = 32 cells, 128-byte swizzle; cuTensorMapEncodeTiled through the runtime
+static int ldg_make_tensor_map(const double* x, int64_t ncells, CUtensorMap* out) {
+  typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeTiledFn enc = nullptr;
+  if (enc == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      enc = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  if (enc == nullptr) return fail(ST_CUDA_ERROR, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t gdim[2] = {16, (cuuint64_t)(3 * ncells)};
+  const cuuint64_t gstr[1] = {128};
+  const cuuint32_t box[2] = {16, 96};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(x), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ST_CUDA_ERROR, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return ST_OK;
+}
+
 // CTA shape of the march kernel for a mesh (see LdgMarchCfg)
 static int ldg_march_variant(int order, int64_t ncells) {
+  if (const char* e = getenv("STEFAN_LDG_VARIANT")) return atoi(e) ? 1 : 0;  // tuning override
   if (order == 1) return ncells >= 2000000 ? 1 : 0;
   if (order == 2) return ncells >= 1000000 ? 0 : 1;
   return 0;
@@ -229,7 +258,13 @@ static int ldg_launch_march_v(LdgHandle* h, const LdgArgs& a, cudaStream_t st) {
     attr_set = true;
   }
   LdgMarchArgs m{a.x, a.x_lo, a.x_hi, a.y, a.phase, a.nx, a.ny, h->plan.fix_dev, h->plan.nfix, 0u};
-  ldg_apply_march<P, V><<<sc.n, C::WARPS * 32, smem, st>>>(tab, m, h->plan.runs_dev, h->plan.run_ofs_dev, sc.tab);
+  CUtensorMap tm;
+  std::memset(&tm, 0, sizeof(tm));
+  if (C::TENSOR) {
+    int rc = ldg_make_tensor_map(a.x, (int64_t)h->nx * h->ny, &tm);
+    if (rc) return rc;
+  }
+  ldg_apply_march<P, V><<<sc.n, C::WARPS * 32, smem, st>>>(tab, m, h->plan.runs_dev, h->plan.run_ofs_dev, sc.tab, tm);
   STEFAN_CUDA(cudaGetLastError());
   return ST_OK;
 }
@@ -410,10 +445,6 @@ static int ldg_apply_impl(stefan_ldg* hv, const double* x, double* y, const doub
                  "stefan_ldg_apply: x, y must be 16-byte aligned (halo columns: 16, order 2: 8)");
   LdgArgs a{x, x_lo, x_hi, y, h->phase_dev, h->nx, h->ny};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // order 3: 48 doubles in and out per cell do not fit the register file next to the
-  // sum-factorisation intermediates; below ~1 M cells the spilling march kernel loses to
-  // the plain kernel (measured: 59 vs 71 GDOF/s at 457^2, 157 vs 78 at 2000^2)
-  if (algo == 0 && h->order == 3 && (int64_t)h->nx * h->ny < 1000000) algo = 1;
   if (algo == 1) {
     switch (h->order) {
       case 1: return ldg_launch<1>(h, a, st);

@@ -39,22 +39,27 @@ template <int V>
 struct LdgMarchCfg<1, V> {
   static constexpr int CB = 96, STAGE = 32 * 96, NST = LDGM_NST, WARPS = V ? 4 : 8, MINB = 2;
   static constexpr int OUTB = 0;
+  static constexpr bool TENSOR = false;
 };
 template <int V>
 struct LdgMarchCfg<2, V> {
   static constexpr int CB = 216, STAGE = 32 * 216 + 32, NST = LDGM_NST, WARPS = V ? 4 : 8, MINB = V ? 2 : 1;
   static constexpr int OUTB = 30 * 216 + 16;
+  static constexpr bool TENSOR = false;
 };
 template <int V>
 struct LdgMarchCfg<3, V> {
   static constexpr int CB = 384, STAGE = 32 * 384, NST = LDGM_NST, WARPS = V ? 4 : 8, MINB = V ? 2 : 1;
   static constexpr int OUTB = 0;
+  // 384-byte cells put all 32 lanes on the same banks: the chunk is fetched as a 2-D tensor
+  // tile {16 doubles, 96 rows of 128 B} with CU_TENSOR_MAP_SWIZZLE_128B (three rows per cell)
+  static constexpr bool TENSOR = true;
 };
 template <int P, int V>
 struct LdgMarchSmem {
   using C = LdgMarchCfg<P, V>;
   static constexpr int WARP = C::NST * C::STAGE + 2 * C::OUTB;
-  static constexpr int TOTAL = C::WARPS * WARP + C::WARPS * C::NST * 8 + 128;
+  static constexpr int TOTAL = C::WARPS * WARP + C::WARPS * C::NST * 8 + 1024;  // 1024: alignment of the swizzled tiles
 };
 
 struct LdgMarchArgs {
@@ -109,7 +114,8 @@ __device__ __forceinline__ void ldg_fixup_tail(const LdgTab<P>& tab, const LdgMa
 template <int P, int V>
 __global__ void __launch_bounds__(LdgMarchCfg<P, V>::WARPS * 32, LdgMarchCfg<P, V>::MINB)
 ldg_apply_march(const __grid_constant__ LdgTab<P> tab, const LdgMarchArgs a, const int4* __restrict__ runs,
-                const int* __restrict__ run_ofs, const __grid_constant__ SegTab segs) {
+                const int* __restrict__ run_ofs, const __grid_constant__ SegTab segs,
+                const __grid_constant__ CUtensorMap tmx) {
   using C = LdgMarchCfg<P, V>;
   constexpr int N1 = P + 1, NF = N1 * N1, CD = 3 * NF;
   constexpr int NST = C::NST, CB = C::CB;
@@ -117,7 +123,7 @@ ldg_apply_march(const __grid_constant__ LdgTab<P> tab, const LdgMarchArgs a, con
   extern __shared__ char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
-  const unsigned smem0 = (smem_addr(smem_raw) + 127u) & ~127u;
+  const unsigned smem0 = (smem_addr(smem_raw) + 1023u) & ~1023u;
   const unsigned ring = smem0 + (unsigned)warp * LdgMarchSmem<P, V>::WARP;
   [[maybe_unused]] const unsigned obuf = ring + NST * C::STAGE;
   const unsigned bars = smem0 + (unsigned)C::WARPS * LdgMarchSmem<P, V>::WARP + (unsigned)warp * NST * 8;
@@ -166,7 +172,15 @@ ldg_apply_march(const __grid_constant__ LdgTab<P> tab, const LdgMarchArgs a, con
         mbar_arrive_s(bar);
         return;
       }
-      if constexpr (ODD) {
+      if constexpr (C::TENSOR) {
+        if (k >= 0 && k < a.nx) {
+          mbar_expect_tx_s(bar, (unsigned)C::STAGE);
+          tensor2d_load_s(stage, &tmx, 0, 3 * (int)((int64_t)k * a.ny + (j0 - 1)), bar);
+        } else {  // halo column: plain bulk copy, read back unswizzled
+          mbar_expect_tx_s(bar, nbytes);
+          bulk_load_s(stage + dst_off, src, nbytes, bar);
+        }
+      } else if constexpr (ODD) {
         const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(src) & 15u);
         unsigned bytes = sh + nbytes;
         if (chunk_is_array_end(k)) bytes &= ~15u;
@@ -184,6 +198,20 @@ ldg_apply_march(const __grid_constant__ LdgTab<P> tab, const LdgMarchArgs a, con
       if constexpr (ODD) p += (unsigned)(reinterpret_cast<uintptr_t>(col_base(k)) & 15u);
       return p;
     };
+    // shared address of double `d` (compile-time) of this lane's cell whose base is p; swizzled
+    // tiles (TENSOR, in-mesh columns): 16-byte piece c of row r sits at piece c ^ (r & 7)
+    [[maybe_unused]] const unsigned m0 = ((3u * lane + 0u) & 7u) << 4, m1 = ((3u * lane + 1u) & 7u) << 4,
+                                    m2 = ((3u * lane + 2u) & 7u) << 4;
+    auto elem_addr = [&](unsigned p, bool swz, int d) -> unsigned {
+      if constexpr (C::TENSOR) {
+        const int part = d / 16, piece = (d % 16) / 2, sub = (d % 2) * 8;
+        const unsigned m = swz ? (part == 0 ? m0 : (part == 1 ? m1 : m2)) : 0u;
+        return p + part * 128 + (((unsigned)piece << 4) ^ m) + sub;
+      } else {
+        return p + 8 * d;
+      }
+    };
+    auto swizzled = [&](int k) -> bool { return C::TENSOR && k >= 0 && k < a.nx; };
     auto hi32 = [](double v) -> unsigned { return (unsigned)__double2hiint(v); };
     // the lane's whole cell; returns the release word (see ipdg_march.cuh, "slot release")
     auto read_cell = [&](int k, unsigned stage, double* v) -> unsigned {
@@ -201,9 +229,10 @@ ldg_apply_march(const __grid_constant__ LdgTab<P> tab, const LdgMarchArgs a, con
             v[CD - 1] = *reinterpret_cast<const double*>(src + nbytes - 8);
         }
       } else {
+        const bool swz = swizzled(k);
 #pragma unroll
         for (int q = 0; q < CD / 2; ++q) {
-          const double2 t = lds_v2(p + 16 * q);
+          const double2 t = lds_v2(elem_addr(p, swz, 2 * q));
           v[2 * q] = t.x;
           v[2 * q + 1] = t.y;
           h ^= hi32(t.x);
@@ -229,8 +258,8 @@ ldg_apply_march(const __grid_constant__ LdgTab<P> tab, const LdgMarchArgs a, con
       unsigned h = 0;
 #pragma unroll
       for (int q = 0; q < N1; ++q) {
-        tLT[q] = lds_f64(p + 8 * (3 * (P * N1 + q) + 0));
-        tLQ[q] = lds_f64(p + 8 * (3 * (P * N1 + q) + 1));
+        tLT[q] = lds_f64(elem_addr(p, swizzled(c0 - 1), 3 * (P * N1 + q) + 0));
+        tLQ[q] = lds_f64(elem_addr(p, swizzled(c0 - 1), 3 * (P * N1 + q) + 1));
         h ^= hi32(tLT[q]) ^ hi32(tLQ[q]);
       }
       unsigned z = released(h);
@@ -253,27 +282,24 @@ ldg_apply_march(const __grid_constant__ LdgTab<P> tab, const LdgMarchArgs a, con
       double tRT[N1], tRQ[N1];  // right neighbour: T and q_x at its ix = 0 nodes
 #pragma unroll
       for (int q = 0; q < N1; ++q) {
-        tRT[q] = lds_f64(pn + 8 * (3 * q + 0));
-        tRQ[q] = lds_f64(pn + 8 * (3 * q + 1));
+        tRT[q] = lds_f64(elem_addr(pn, swizzled(c + 1), 3 * q + 0));
+        tRQ[q] = lds_f64(elem_addr(pn, swizzled(c + 1), 3 * q + 1));
       }
       auto body = [&](auto phase_c) {
         constexpr int S = decltype(phase_c)::value;
         const unsigned ms = S ? ((unsigned)cur.w & (unsigned)cur.z) : ((unsigned)cur.w & ~(unsigned)cur.z);
         const bool st = (ms >> lane) & 1;
-        double UL[CD], UR[CD], UD[CD], UU[CD], out[CD];
+        double out[CD];
+        double tDT[N1], tDQ[N1], tUT[N1], tUQ[N1];
 #pragma unroll
         for (int q = 0; q < N1; ++q) {
-          UL[3 * (P * N1 + q) + 0] = tLT[q];
-          UL[3 * (P * N1 + q) + 1] = tLQ[q];
-          UR[3 * q + 0] = tRT[q];
-          UR[3 * q + 1] = tRQ[q];
           // from the cell below (lane - 1): T and q_y at its iy = P nodes; from above: iy = 0
-          UD[3 * (q * N1 + P) + 0] = __shfl_up_sync(0xffffffffu, U[3 * (q * N1 + P) + 0], 1);
-          UD[3 * (q * N1 + P) + 2] = __shfl_up_sync(0xffffffffu, U[3 * (q * N1 + P) + 2], 1);
-          UU[3 * (q * N1 + 0) + 0] = __shfl_down_sync(0xffffffffu, U[3 * (q * N1 + 0) + 0], 1);
-          UU[3 * (q * N1 + 0) + 2] = __shfl_down_sync(0xffffffffu, U[3 * (q * N1 + 0) + 2], 1);
+          tDT[q] = __shfl_up_sync(0xffffffffu, U[3 * (q * N1 + P) + 0], 1);
+          tDQ[q] = __shfl_up_sync(0xffffffffu, U[3 * (q * N1 + P) + 2], 1);
+          tUT[q] = __shfl_down_sync(0xffffffffu, U[3 * (q * N1 + 0) + 0], 1);
+          tUQ[q] = __shfl_down_sync(0xffffffffu, U[3 * (q * N1 + 0) + 2], 1);
         }
-        ldg_cell_rows<P>(tab, S, T_SAME, T_SAME, T_SAME, T_SAME, U, UL, UR, UD, UU, out);
+        ldg_rows_streamed<P, S>(tab, U, tLT, tLQ, tRT, tRQ, tDT, tDQ, tUT, tUQ, out);
         if constexpr (C::OUTB == 0) {
           if (st) {
 #pragma unroll

@@ -164,4 +164,97 @@ void ldg_cell_rows(const LdgTab<P>& tab, int s, int tL, int tR, int tD, int tU,
 #undef QY_
 }
 
+// The same rows for an interior cell of phase index S with four same-phase neighbours, in the
+// form the march kernel uses: the neighbours enter as face traces (T and the normal flux
+// component at the face nodes), and the sum-factorisation intermediates are never stored --
+// every x-line (fixed iy) / y-line (fixed ix) result is scattered straight into the output
+// accumulators through the 1-D mass matrix.  Live data: the cell (3 NF), the output (3 NF) and
+// 2 (P+1) line temporaries, instead of 4 NF intermediates on top (order 3: 110 instead of
+// 160 doubles, which is what fits the register file).
+template <int P, int S>
+#if defined(__CUDACC__)
+__host__ __device__ __forceinline__
+#else
+inline
+#endif
+void ldg_rows_streamed(const LdgTab<P>& tab, const double* __restrict__ U, const double* __restrict__ tLT,
+                       const double* __restrict__ tLQ, const double* __restrict__ tRT,
+                       const double* __restrict__ tRQ, const double* __restrict__ tDT,
+                       const double* __restrict__ tDQ, const double* __restrict__ tUT,
+                       const double* __restrict__ tUQ, double* __restrict__ out) {
+  constexpr int N1 = P + 1;
+  constexpr int NF = N1 * N1;
+  const double k = tab.kk[S];
+#pragma unroll
+  for (int a = 0; a < 3 * NF; ++a) out[a] = 0.0;
+  // x-lines
+#pragma unroll
+  for (int iy = 0; iy < N1; ++iy) {
+#pragma unroll
+    for (int ix = 0; ix < N1; ++ix) {
+      double cqx = 0.0, g_x = 0.0, mqx = 0.0;
+#pragma unroll
+      for (int b = 0; b < N1; ++b) {
+        const double t = U[3 * (b * N1 + iy) + 0], q = U[3 * (b * N1 + iy) + 1];
+        cqx += tab.C[ix * N1 + b] * t;
+        g_x += tab.C[ix * N1 + b] * q;
+        mqx += tab.Mx[ix * N1 + b] * q;
+      }
+      g_x *= k;
+      if (ix == 0) {
+        const double t = U[3 * (0 * N1 + iy) + 0], q = U[3 * (0 * N1 + iy) + 1];
+        cqx += tab.sqK[0][0][T_SAME] * t + tab.sqN[0][0][T_SAME] * tLT[iy];
+        g_x += tab.tqK[S][0][0][T_SAME] * q + tab.tqN[S][0][0][T_SAME] * tLQ[iy] + tab.tpK[0][0][T_SAME] * t +
+               tab.tpN[0][0][T_SAME] * tLT[iy];
+      }
+      if (ix == P) {
+        const double t = U[3 * (P * N1 + iy) + 0], q = U[3 * (P * N1 + iy) + 1];
+        cqx += tab.sqK[0][1][T_SAME] * t + tab.sqN[0][1][T_SAME] * tRT[iy];
+        g_x += tab.tqK[S][0][1][T_SAME] * q + tab.tqN[S][0][1][T_SAME] * tRQ[iy] + tab.tpK[0][1][T_SAME] * t +
+               tab.tpN[0][1][T_SAME] * tRT[iy];
+      }
+      const double a = cqx + mqx;
+#pragma unroll
+      for (int jy = 0; jy < N1; ++jy) {  // y-mass: rows (ix, jy) get My[jy][iy] times the line value
+        out[3 * (ix * N1 + jy) + 1] += tab.My[jy * N1 + iy] * a;
+        out[3 * (ix * N1 + jy) + 0] += tab.My[jy * N1 + iy] * g_x;
+      }
+    }
+  }
+  // y-lines
+#pragma unroll
+  for (int ix = 0; ix < N1; ++ix) {
+#pragma unroll
+    for (int iy = 0; iy < N1; ++iy) {
+      double cqy = 0.0, g_y = 0.0, mqy = 0.0;
+#pragma unroll
+      for (int c = 0; c < N1; ++c) {
+        const double t = U[3 * (ix * N1 + c) + 0], q = U[3 * (ix * N1 + c) + 2];
+        cqy += tab.C[iy * N1 + c] * t;
+        g_y += tab.C[iy * N1 + c] * q;
+        mqy += tab.My[iy * N1 + c] * q;
+      }
+      g_y *= k;
+      if (iy == 0) {
+        const double t = U[3 * (ix * N1 + 0) + 0], q = U[3 * (ix * N1 + 0) + 2];
+        cqy += tab.sqK[1][0][T_SAME] * t + tab.sqN[1][0][T_SAME] * tDT[ix];
+        g_y += tab.tqK[S][1][0][T_SAME] * q + tab.tqN[S][1][0][T_SAME] * tDQ[ix] + tab.tpK[1][0][T_SAME] * t +
+               tab.tpN[1][0][T_SAME] * tDT[ix];
+      }
+      if (iy == P) {
+        const double t = U[3 * (ix * N1 + P) + 0], q = U[3 * (ix * N1 + P) + 2];
+        cqy += tab.sqK[1][1][T_SAME] * t + tab.sqN[1][1][T_SAME] * tUT[ix];
+        g_y += tab.tqK[S][1][1][T_SAME] * q + tab.tqN[S][1][1][T_SAME] * tUQ[ix] + tab.tpK[1][1][T_SAME] * t +
+               tab.tpN[1][1][T_SAME] * tUT[ix];
+      }
+      const double a = cqy + mqy;
+#pragma unroll
+      for (int jx = 0; jx < N1; ++jx) {  // x-mass: rows (jx, iy) get Mx[jx][ix] times the line value
+        out[3 * (jx * N1 + iy) + 2] += tab.Mx[jx * N1 + ix] * a;
+        out[3 * (jx * N1 + iy) + 0] += tab.Mx[jx * N1 + ix] * g_y;
+      }
+    }
+  }
+}
+
 }  // namespace stefan

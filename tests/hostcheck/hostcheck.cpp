@@ -126,3 +126,46 @@ extern "C" int hostcheck_march_plan(int nx, int ny, const int8_t* phase, int gro
   n_out[3] = sc.n;
   return 0;
 }
+
+
+// ldg_rows_streamed (the march kernel's form) on the host for an all-interior evaluation:
+// a 3 x 3 patch of cells of one phase; returns the rows of the centre cell computed by the
+// general row function and by the streamed one (traces taken from the neighbours).
+template <int P>
+static int run_ldg_streamed(int nq, double jx, double jy, LdgPhys ph, int s, const double* x9, double* out_general,
+                            double* out_streamed) {
+  constexpr int N1 = P + 1, NF = N1 * N1, CD = 3 * NF;
+  RefElem1D r;
+  if (build_ref1d(P, nq, &r)) return 1;
+  static LdgTab<P> tab;
+  if (build_ldg_tables<P>(r, jx, jy, ph, &tab)) return 2;
+  auto cell = [&](int i, int j) { return x9 + (size_t)(i * 3 + j) * CD; };  // y fastest
+  const double *U = cell(1, 1), *UL = cell(0, 1), *UR = cell(2, 1), *UD = cell(1, 0), *UU = cell(1, 2);
+  ldg_cell_rows<P>(tab, s, T_SAME, T_SAME, T_SAME, T_SAME, U, UL, UR, UD, UU, out_general);
+  double tLT[N1], tLQ[N1], tRT[N1], tRQ[N1], tDT[N1], tDQ[N1], tUT[N1], tUQ[N1];
+  for (int q = 0; q < N1; ++q) {
+    tLT[q] = UL[3 * (P * N1 + q) + 0];
+    tLQ[q] = UL[3 * (P * N1 + q) + 1];
+    tRT[q] = UR[3 * (0 * N1 + q) + 0];
+    tRQ[q] = UR[3 * (0 * N1 + q) + 1];
+    tDT[q] = UD[3 * (q * N1 + P) + 0];
+    tDQ[q] = UD[3 * (q * N1 + P) + 2];
+    tUT[q] = UU[3 * (q * N1 + 0) + 0];
+    tUQ[q] = UU[3 * (q * N1 + 0) + 2];
+  }
+  if (s == 0) ldg_rows_streamed<P, 0>(tab, U, tLT, tLQ, tRT, tRQ, tDT, tDQ, tUT, tUQ, out_streamed);
+  else ldg_rows_streamed<P, 1>(tab, U, tLT, tLQ, tRT, tRQ, tDT, tDQ, tUT, tUQ, out_streamed);
+  return 0;
+}
+
+extern "C" int hostcheck_ldg_streamed(int order, int nq, double jx, double jy, double k1, double k2, double ai,
+                                      double an, double ap, double v0x, double v0y, int s, const double* x9,
+                                      double* out_general, double* out_streamed) {
+  LdgPhys ph{k1, k2, ai, an, ap, v0x, v0y};
+  switch (order) {
+    case 1: return run_ldg_streamed<1>(nq, jx, jy, ph, s, x9, out_general, out_streamed);
+    case 2: return run_ldg_streamed<2>(nq, jx, jy, ph, s, x9, out_general, out_streamed);
+    case 3: return run_ldg_streamed<3>(nq, jx, jy, ph, s, x9, out_general, out_streamed);
+  }
+  return 3;
+}

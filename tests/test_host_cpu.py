@@ -228,3 +228,20 @@ def test_march_plan_invariants(hostcheck, nx, ny, warps, two_phase, cbeg_frac, c
         seg = sorted((int(t[1]), int(t[2])) for t in tiles if t[0] == g)
         assert seg[0][0] == cbeg and seg[-1][1] == cend
         assert all(a[1] == b[0] for a, b in zip(seg, seg[1:])) and all(a < b for a, b in seg)
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
+@pytest.mark.parametrize("s", [0, 1])
+def test_ldg_streamed_rows_equal_general_rows(hostcheck, order, s):
+    """The march kernel's streamed LDG row function (traces in, no stored intermediates)
+    equals the general per-cell row function, which is checked against the oracle above."""
+    rng = np.random.default_rng(order * 10 + s)
+    cd = 3 * (order + 1) ** 2
+    x9 = rng.uniform(-1, 1, 9 * cd)
+    g, st = np.zeros(cd), np.zeros(cd)
+    d = ctypes.c_double
+    dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))  # noqa: E731
+    rc = hostcheck.hostcheck_ldg_streamed(order, order + 1, d(0.013), d(0.021), d(1.0), d(2.0), d(0.7), d(0.3), d(1.1),
+                                          d(np.cos(0.6)), d(np.sin(0.6)), s, dp(x9), dp(g), dp(st))
+    assert rc == 0
+    assert np.abs(g - st).max() <= 1e-13 * np.abs(g).max()
