@@ -238,7 +238,7 @@ static int ldg_march_variant(int order, int64_t ncells) {
   if (const char* e = getenv("STEFAN_LDG_VARIANT")) return atoi(e) ? 1 : 0;  // tuning override
   if (order == 1) return ncells >= 2000000 ? 1 : 0;
   if (order == 2) return ncells >= 1000000 ? 0 : 1;
-  return 0;
+  return 1;  // order 3: 4 warps x 2 CTAs (142 / 293 GDOF/s at 457^2 / 2000^2; 8 warps x 1: 121 / 288)
 }
 static int ldg_march_warps(int order, int variant) {
   (void)order;

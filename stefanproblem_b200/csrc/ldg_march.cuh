@@ -18,7 +18,9 @@
 //   P = 1: 96-byte cells, STG.256 stores.
 //   P = 2: 216-byte cells: chunks may start 8 bytes off a 16-byte boundary (the copy then
 //          starts 8 bytes early); results leave through a staged bulk store.
-//   P = 3: 384-byte cells, STG.256 stores.
+//   P = 3: 384-byte cells: a dense stage would put all 32 lanes on the same banks (measured:
+//          157 GDOF/s), so the chunk is a 2-D tensor tile {16 doubles, 96 rows} fetched with
+//          CU_TENSOR_MAP_SWIZZLE_128B (three 128-byte rows per cell; 290 GDOF/s); STG.256 stores.
 // Cells that are not interior-uniform (march_plan.h) are recomputed by the tail.
 #pragma once
 
