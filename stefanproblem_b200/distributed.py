@@ -269,3 +269,50 @@ def apply_peer(dop, slab, out, publish=True):
     if publish:
         slab.release()
     return out
+
+
+class DistributedLDGOperator:
+    """Local-DG operator (3 dofs per node) on a global nxg x ny mesh, one column slab per rank.
+
+    Halo = the neighbour's adjacent cell column (3 ny NF doubles).  `apply(x, out)` exchanges
+    it with torch.distributed send / recv; `apply_peer(slab, out)` reads it straight out of the
+    neighbour's PeerSlab over NVLink (ordering by stefan_peer_signal / stefan_peer_wait)."""
+
+    def __init__(self, nxg, ny, widths, order, numqp, k1, k2, interiorpenalty, negboundarypenalty,
+                 posboundarypenalty, V0, phase_of_column, rank, world):
+        import torch
+        from . import cutcelldg as cc
+        self.rank, self.world = rank, world
+        self.i0, self.i1 = slab_range(nxg, world, rank)
+        nxl = self.i1 - self.i0
+        hx = widths[0] / nxg
+        basis = cc.LagrangeTensorProductBasis(2, order)
+        phase = np.concatenate([np.asarray(phase_of_column(i), dtype=np.int8) for i in range(self.i0, self.i1)])
+        self.mesh = cc.UniformMesh([self.i0 * hx, 0.0], [nxl * hx, widths[1]], [nxl, ny], basis, phase=phase)
+        self.mesh.h = np.array([hx, widths[1] / ny])
+        plo = phase_of_column(self.i0 - 1) if rank > 0 else None
+        phi = phase_of_column(self.i1) if rank < world - 1 else None
+        self.op = cc.LDGOperator(self.mesh, order, numqp, k1, k2, interiorpenalty, negboundarypenalty,
+                                 posboundarypenalty, V0, phase_lo=plo, phase_hi=phi)
+        self.ndofs = self.op.ndofs
+        self.nxl = nxl
+        like = torch.empty(0, dtype=torch.float64, device="cuda")
+        self.halo = HaloExchange(3 * ny * basis.nf, rank, world, like)
+
+    def apply(self, x, out):
+        h = self.halo
+        h.exchange(x)
+        return self.op.apply(x, out=out, x_lo=h.x_lo, x_hi=h.x_hi)
+
+    def apply_peer(self, slab, out):
+        from . import _lib
+        from .cutcelldg import _stream_ptr
+        col = self.halo.col
+        slab.publish()
+        slab.wait_neighbours()
+        lo = ctypes.c_void_p(slab.peer_column(self.rank - 1, col, last=True)) if self.rank > 0 else None
+        hi = ctypes.c_void_p(slab.peer_column(self.rank + 1, col, last=False)) if self.rank < self.world - 1 else None
+        _lib.check(_lib.lib().stefan_ldg_apply(self.op._h, ctypes.c_void_p(slab.x.data_ptr()),
+                                               ctypes.c_void_p(out.data_ptr()), lo, hi, _stream_ptr()))
+        slab.release()
+        return out

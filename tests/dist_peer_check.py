@@ -14,8 +14,8 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from stefanproblem_b200 import cutcelldg as cc  # noqa: E402
-from stefanproblem_b200.distributed import (DistributedIPOperator, PeerSlab, apply_peer, apply_peer_fused,  # noqa: E402
-                                            slab_range)
+from stefanproblem_b200.distributed import (DistributedIPOperator, DistributedLDGOperator, PeerSlab,  # noqa: E402
+                                            apply_peer, apply_peer_fused, slab_range)
 
 
 def column_phase(nxg, ny, i):
@@ -64,6 +64,33 @@ def main():
             worst = max(worst, float((out2 - yref[sl]).norm() / yref[sl].norm()))
             dist.barrier()
             slab.close()
+    # local DG (3 dofs per node): peer halos and NCCL halos
+    V0 = (np.cos(0.4), np.sin(0.4))
+    for order in (1, 2, 3):
+        nxg, ny = 13 * world + 3, 65
+        nf = (order + 1) ** 2
+        dop = DistributedLDGOperator(nxg, ny, (1.0, 1.0), order, order + 1, 1.0, 2.0, 0.5, 0.2, 1.3, V0,
+                                     lambda i: column_phase(nxg, ny, i), rank, world)
+        basis = cc.LagrangeTensorProductBasis(2, order)
+        phase = np.concatenate([column_phase(nxg, ny, i) for i in range(nxg)])
+        full = cc.LDGOperator(cc.UniformMesh([0, 0], [1, 1], [nxg, ny], basis, phase=phase), order, order + 1,
+                              1.0, 2.0, 0.5, 0.2, 1.3, V0)
+        xg = torch.from_numpy(np.random.default_rng(6).uniform(-1, 1, nxg * ny * nf * 3)).cuda()
+        yref = full.apply(xg, algo=1)
+        i0, i1 = slab_range(nxg, world, rank)
+        sl = slice(i0 * ny * nf * 3, i1 * ny * nf * 3)
+        slab = PeerSlab(dop.ndofs, rank, world)
+        slab.x.copy_(xg[sl])
+        out = torch.empty(dop.ndofs, dtype=torch.float64, device="cuda")
+        dop.apply_peer(slab, out)
+        worst = max(worst, float((out - yref[sl]).norm() / yref[sl].norm()))
+        out2 = torch.empty_like(out)
+        dop.apply(xg[sl].clone(), out2)
+        worst = max(worst, float((out2 - yref[sl]).norm() / yref[sl].norm()))
+        torch.cuda.synchronize()
+        assert int(slab.status.item()) == 0, "a peer wait timed out"
+        dist.barrier()
+        slab.close()
     t = torch.tensor([worst], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     assert float(t.item()) < 1e-13, f"slab partition differs from the one-GPU operator: {float(t.item()):.3e}"
