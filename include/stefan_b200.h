@@ -122,7 +122,9 @@ int stefan_ipdg_apply_columns(stefan_ipdg* h, const double* x, double* y, const 
  *         inner; for two phases the host samples f1 / f2 by cell phase), or NULL
  *   g_qp  [bottom nx*numqp][right ny*numqp][top nx*numqp][left ny*numqp] at the face
  *         quadrature points of the boundary faces, or NULL
- *   b     [ndofs] is overwritten. */
+ *   b     [ndofs] is overwritten.
+ * Slab handles (phase_lo / phase_hi given): f_qp and the bottom / top parts of g_qp are the
+ * slab's own; the left / right parts are read only where the slab touches the domain boundary. */
 int stefan_ipdg_rhs(stefan_ipdg* h, const double* f_qp, const double* g_qp, double* b, void* stream);
 
 /* The COO seam: the (row, col, val) triplets of the assembled operator, one dense

@@ -187,7 +187,6 @@ extern "C" {
 int stefan_ipdg_rhs(stefan_ipdg* hv, const double* f_qp, const double* g_qp, double* b, void* stream) {
   IpdgHandle* h = reinterpret_cast<IpdgHandle*>(hv);
   STEFAN_REQUIRE(h && b, "stefan_ipdg_rhs: null argument");
-  STEFAN_REQUIRE(!h->has_lo && !h->has_hi, "stefan_ipdg_rhs: slab handles are not supported yet");
   RhsTab t;
   std::memset(&t, 0, sizeof(t));
   t.n1 = h->order + 1;

@@ -406,7 +406,6 @@ int stefan_ldg_assemble_coo(stefan_ldg* hv, int64_t* rows, int64_t* cols, double
 int stefan_ldg_rhs(stefan_ldg* hv, const double* f_qp, const double* g_qp, double* b, void* stream) {
   LdgHandle* h = reinterpret_cast<LdgHandle*>(hv);
   STEFAN_REQUIRE(h && b, "stefan_ldg_rhs: null argument");
-  STEFAN_REQUIRE(!h->has_lo && !h->has_hi, "stefan_ldg_rhs: slab handles are not supported yet");
   RefElem1D ref;
   build_ref1d(h->order, h->numqp, &ref);
   LdgRhsTab t;

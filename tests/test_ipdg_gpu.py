@@ -179,6 +179,35 @@ def test_two_slabs_equal_one(cuda, order, algo, nx, ny, cut):
 
 
 @pytest.mark.parametrize("order", [1, 2, 3])
+def test_rhs_of_two_slabs_equals_one(cuda, order):
+    """Slab handles produce their part of the right-hand side (boundary terms only where the slab
+    touches the domain boundary, Robin source on the faces they share with the neighbour)."""
+    import torch
+    from stefanproblem_b200 import cutcelldg as cc
+    nx, ny, cut, nq = 11, 9, 4, order + 1
+    basis = cc.LagrangeTensorProductBasis(2, order)
+    omesh = UniformMesh2D([0, 0], [1, 1], [nx, ny], basis.nf)
+    P = fast.circle_phase(omesh).reshape(nx, ny)
+    P[cut - 1, 3:6] = 1   # an interface that runs along the cut
+    P[cut, 3:6] = -1
+    pen, lam, Tm = 1e3 * nx, 1.3, 0.4
+    mk = lambda m, ph, **kw: cc.IPOperator(m, order, nq, 1.0, 2.0, pen, lam, Tm, "current", ALL, **kw)  # noqa: E731
+    full = mk(cc.UniformMesh([0, 0], [1, 1], [nx, ny], basis, phase=P.ravel()), P)
+    lo = mk(cc.UniformMesh([0, 0], [cut / nx, 1], [cut, ny], basis, phase=P[:cut].ravel()), P, phase_hi=P[cut])
+    hi = mk(cc.UniformMesh([cut / nx, 0], [1 - cut / nx, 1], [nx - cut, ny], basis, phase=P[cut:].ravel()), P,
+            phase_lo=P[cut - 1])
+    rng = np.random.default_rng(4)
+    f = rng.uniform(-1, 1, (nx, ny, nq * nq))
+    gb, gr, gt, gl = (rng.uniform(-1, 1, (n, nq)) for n in (nx, ny, nx, ny))
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()  # noqa: E731
+    bfull = full.rhs(dev(f), dev(np.concatenate([gb.ravel(), gr.ravel(), gt.ravel(), gl.ravel()])))
+    z = np.zeros((ny, nq))
+    blo = lo.rhs(dev(f[:cut]), dev(np.concatenate([gb[:cut].ravel(), z.ravel(), gt[:cut].ravel(), gl.ravel()])))
+    bhi = hi.rhs(dev(f[cut:]), dev(np.concatenate([gb[cut:].ravel(), gr.ravel(), gt[cut:].ravel(), z.ravel()])))
+    assert (torch.cat([blo, bhi]) - bfull).norm() <= 1e-13 * bfull.norm()
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
 def test_interface_sums_match_oracle(cuda, order):
     import torch
     from oracle import timeloop
