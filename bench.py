@@ -207,6 +207,48 @@ def run_ours(args):
                "api": "stefan_ipdg_apply_host (pinned host buffers, 32 pipelined slabs)"}
         del xh, yh
 
+    if world > 1 and peer:
+        # end to end at N GPUs: every rank moves its slab over its own PCIe link (pinned host
+        # buffers, H2D of x and D2H of y inside the timed region) around the one fused launch
+        xh = torch.empty(ndofs_local, dtype=torch.float64).pin_memory()
+        xh.copy_(x.cpu())
+        yh = torch.empty(ndofs_local, dtype=torch.float64).pin_memory()
+        n_e2e = max(2, min(args.steps, 10))
+        ybuf = [y, torch.empty_like(y)]
+        d2h, done, copied = torch.cuda.Stream(), [torch.cuda.Event(), torch.cuda.Event()], [None, None]
+        work = torch.cuda.Stream()  # not the legacy default stream, which serialises with other streams' copies
+
+        def e2e_step(k):
+            # the result of step k leaves on a second stream while step k+1's input arrives
+            # (PCIe is full duplex); two result buffers
+            b = k & 1
+            slab.wait_released()            # the neighbours are done with my previous vector
+            slab.x.copy_(xh, non_blocking=True)
+            if copied[b] is not None:
+                torch.cuda.current_stream().wait_event(copied[b])   # ybuf[b] has left the device
+            apply_peer_fused(dop, slab, ybuf[b])
+            done[b].record()
+            with torch.cuda.stream(d2h):
+                d2h.wait_event(done[b])
+                yh.copy_(ybuf[b], non_blocking=True)
+                copied[b] = torch.cuda.Event()
+                copied[b].record(d2h)
+
+        barrier()
+        with torch.cuda.stream(work):
+            e2e_step(0)
+            barrier()
+            t0 = time.perf_counter()
+            for k in range(n_e2e):
+                e2e_step(k + 1)
+            barrier()
+        dt = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": total_dofs / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": total_dofs * 8,
+               "d2h_bytes_per_step": total_dofs * 8, "steps": n_e2e,
+               "api": "PeerSlab + stefan_ipdg_apply_peer per rank (pinned host buffers, each rank over its own PCIe link)"}
+        del xh, yh
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_baseline = cpu_port_baseline(p, seconds=6.0)
