@@ -56,6 +56,7 @@ struct ApplyArgs {
   unsigned long long sync_epoch, sync_timeout_ns;
   int* sync_status;                          // set to 1 if a wait timed out
   unsigned* sync_counter;                    // CTAs finished (local)
+  unsigned long long* dbg_times;             // development only: per-CTA {start, end} globaltimer, or null
 };
 
 // Wait (acquire, system scope) until the neighbour has published `epoch`; bounded.
@@ -218,6 +219,25 @@ static int launch_march(IpdgHandle* h, const IpTab<P>& tab, const ApplyArgs& arg
     int rc = make_cell_tensor_map(args.x, (int64_t)h->nx * h->ny, &tm);
     if (rc) return rc;
   }
+  // development only: STEFAN_DEV_CTA_TIMES=<file> dumps per-CTA {group, c0, c1, start ns, end ns}
+  static const char* dbg_path = getenv("STEFAN_DEV_CTA_TIMES");
+  if (dbg_path != nullptr) {
+    ApplyArgs a2 = args;
+    unsigned long long* d = nullptr;
+    STEFAN_CUDA(cudaMalloc(&d, (size_t)grid * 2 * sizeof(unsigned long long)));
+    a2.dbg_times = d;
+    ipdg_apply_march<P><<<grid, C::WARPS * 32, smem, st>>>(tab, a2, h->plan.runs_dev, h->plan.run_ofs_dev, tm, segs);
+    STEFAN_CUDA(cudaStreamSynchronize(st));
+    std::vector<unsigned long long> t((size_t)grid * 2);
+    STEFAN_CUDA(cudaMemcpy(t.data(), d, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    if (FILE* f = fopen(dbg_path, "w")) {
+      for (int b = 0; b < grid; ++b)
+        fprintf(f, "%d %d %d %llu %llu\n", segs.e[b].x, segs.e[b].y, segs.e[b].z, t[2 * b], t[2 * b + 1]);
+      fclose(f);
+    }
+    return ST_OK;
+  }
   ipdg_apply_march<P><<<grid, C::WARPS * 32, smem, st>>>(tab, args, h->plan.runs_dev, h->plan.run_ofs_dev, tm, segs);
   return ST_OK;
 }
@@ -238,6 +258,8 @@ static int launch_apply(IpdgHandle* h, const ApplyArgs& args0, int algo, cudaStr
   // exception cells of the produced columns (the list is sorted by column)
   args.fix = h->plan.fix_dev + h->plan.fix_col_ofs[args.cbeg];
   args.nfix = h->plan.fix_col_ofs[args.cend] - h->plan.fix_col_ofs[args.cbeg];
+  static const bool skip_tail = getenv("STEFAN_DEV_SKIP_TAIL") != nullptr;  // timing experiments only (wrong results)
+  if (skip_tail) args.nfix = 0;
   // CTA = (group of adjacent strips, x segment); one wave of MINB CTAs per SM
   int rc = launch_march<P>(h, tab, args, st);
   if (rc) return rc;
@@ -315,6 +337,7 @@ int stefan_ipdg_create(const stefan_ipdg_params* p, const int8_t* phase, const i
   cudaError_t e = cudaMalloc(&h->phase_dev, pn);
   if (e == cudaSuccess) e = cudaMemcpy(h->phase_dev, ph.data(), pn, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = h->plan.build(ph.data(), p->nx, p->ny, march_warps(p->order));
+  h->plan.mixed_cost_q = p->order == 1 ? 1 : (p->order == 2 ? 4 : 6);  // measured, see MarchPlan::segments
   if (e != cudaSuccess) { h->plan.destroy(); if (h->phase_dev) cudaFree(h->phase_dev); delete h; return fail(ST_CUDA_ERROR, "stefan_ipdg_create: %s", cudaGetErrorString(e)); }
   *out = reinterpret_cast<stefan_ipdg*>(h);
   return ST_OK;

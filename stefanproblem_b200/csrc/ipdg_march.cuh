@@ -219,6 +219,11 @@ ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
+  if (a.dbg_times != nullptr && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    a.dbg_times[2 * blockIdx.x] = t;
+  }
   // peer halos: everything the stream wrote before this kernel is final -> publish my epoch
   if (a.sync_epoch != 0 && blockIdx.x == 0 && threadIdx.x == 0) peer_flag_publish(a.sync_my_ready, a.sync_epoch);
 
@@ -571,6 +576,14 @@ ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const 
     if constexpr (C::OUTB != 0) {
       if (lane == 0) tma_store_wait_read<0>();
       __syncwarp();
+    }
+  }
+  if (a.dbg_times != nullptr) {  // time of the marching part (before the tail)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      a.dbg_times[2 * blockIdx.x + 1] = t;
     }
   }
   fixup_tail<P>(tab, a);

@@ -138,17 +138,20 @@ struct MarchPlan {
   }
 
   // Cost-balanced tiles, one per CTA, for columns [cbeg, cend).  A CTA is done when its
-  // slowest warp is; a warp pays 1 per column plus kMixedCost where its strip mixes phases
-  // (both phase bodies run), so
-  //     cost(group, [c0, c1)) = (c1 - c0) + kMixedCost * max over the group's strips of
-  //                                          #mixed columns of that strip in [c0, c1).
-  // Segments are cut greedily at the largest c1 with cost <= T; T is bisected until the tile
-  // count fits the CTA budget (one wave).  Cached per column range.
-  int kMixedCost = 1;  // extra cost of a column where the strip mixes phases (STEFAN_MIXED_COST overrides)
+  // slowest warp is; a warp pays 4 cost units per column plus mixed_cost_q units where its strip
+  // mixes phases (both phase bodies run), so
+  //     cost(group, [c0, c1)) = 4 (c1 - c0) + mixed_cost_q * max over the group's strips of
+  //                                            #mixed columns of that strip in [c0, c1).
+  // mixed_cost_q is per kernel (measured per-CTA times: a mixed column costs an order-1 warp
+  // ~5 % more -- the kernel is memory-bound and the second body hides behind the loads -- but
+  // about as much as a whole column at orders 2 and 3).  T = the smallest tile cost whose
+  // greedy cut fits the CTA budget (one wave); every group is then re-cut into the same number
+  // of tiles of EQUAL cost (no short remainder tile).  Cached per column range.
+  int mixed_cost_q = 4;  // quarter columns; set by the kernel's host code before the first apply
   const SegCache& segments(int cbeg, int cend, int max_ctas) {
     for (const SegCache& c : seg_cache)
       if (c.cbeg == cbeg && c.cend == cend && c.max_ctas == max_ctas) return c;
-    if (const char* e = getenv("STEFAN_MIXED_COST")) kMixedCost = atoi(e);
+    if (const char* e = getenv("STEFAN_MIXED_COST_Q")) mixed_cost_q = atoi(e);
     const int ng = ngroups, gw = group_warps;
     auto cost = [&](int g, int c0, int c1) {
       int mx = 0;
@@ -156,37 +159,45 @@ struct MarchPlan {
         const int* cum = mixed_cum.data() + (size_t)sidx * (nx + 1);
         mx = std::max(mx, cum[c1] - cum[c0]);
       }
-      return (c1 - c0) + kMixedCost * mx;
+      return 4 * (c1 - c0) + mixed_cost_q * mx;
     };
-    auto cut = [&](int T, std::vector<int4>* tiles) {  // number of tiles of cost <= T each
-      int n = 0;
-      for (int g = 0; g < ng; ++g) {
-        int c0 = cbeg, s = 0;
-        while (c0 < cend) {
-          int lo = c0 + 1, hi = cend;  // largest c1 in (c0, cend] with cost <= T (at least one column)
-          while (lo < hi) {
-            const int mid = (lo + hi + 1) / 2;
-            if (cost(g, c0, mid) <= T) lo = mid;
-            else hi = mid - 1;
-          }
-          if (tiles) tiles->push_back(make_int4(g, c0, lo, s));
-          ++s;
-          ++n;
-          c0 = lo;
+    // greedy cut of group g into tiles of cost <= T (at least one column each)
+    auto cut_group = [&](int g, int T, std::vector<int4>* tiles) {
+      int n = 0, c0 = cbeg;
+      while (c0 < cend) {
+        int lo = c0 + 1, hi = cend;  // largest c1 in (c0, cend] with cost <= T
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) / 2;
+          if (cost(g, c0, mid) <= T) lo = mid;
+          else hi = mid - 1;
         }
+        if (tiles) tiles->push_back(make_int4(g, c0, lo, n));
+        ++n;
+        c0 = lo;
       }
       return n;
     };
+    auto cut = [&](int T) {
+      int n = 0;
+      for (int g = 0; g < ng; ++g) n += cut_group(g, T, nullptr);
+      return n;
+    };
     const int budget = std::max(ng, std::min(max_ctas, kMaxMarchCtas));
-    int hi = (1 + kMixedCost) * (cend - cbeg) + 1;
-    int lo = std::min(8, hi);  // segments of cost >= 8
+    int hi = (4 + mixed_cost_q) * (cend - cbeg) + 1;
+    int lo = std::min(4 * 8, hi);  // tiles of at least ~8 columns
     while (lo < hi) {
       const int mid = (lo + hi) / 2;
-      if (cut(mid, nullptr) <= budget) hi = mid;
+      if (cut(mid) <= budget) hi = mid;
       else lo = mid + 1;
     }
     std::vector<int4> tiles;
-    cut(lo, &tiles);
+    for (int g = 0; g < ng; ++g) {
+      // same tile count as the greedy cut at T, but equal shares of the group's cost
+      const int n = cut_group(g, lo, nullptr);
+      int Tg = (cost(g, cbeg, cend) + n - 1) / n;
+      while (cut_group(g, Tg, nullptr) > n) Tg += std::max(1, Tg / 64);
+      cut_group(g, Tg, &tiles);
+    }
     // CTA order: segment-major = CTAs with neighbouring block indices work on neighbouring
     // strips of the same columns
     std::stable_sort(tiles.begin(), tiles.end(), [](const int4& a, const int4& b) { return a.w < b.w; });
