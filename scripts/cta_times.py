@@ -1,3 +1,5 @@
+"""Per-CTA durations of the IP-DG march kernel (development hook STEFAN_DEV_CTA_TIMES of ipdg.cu):
+usage: python scripts/cta_times.py ORDER TWO_PHASE(0|1)   -- on a GPU box."""
 import os, sys, numpy as np, torch
 sys.path.insert(0, ".")
 order = int(sys.argv[1]); tp = int(sys.argv[2])
