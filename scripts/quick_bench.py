@@ -5,13 +5,18 @@ import torch
 sys.path.insert(0, ".")
 from stefanproblem_b200 import cutcelldg as cc
 
+PATTERN = "circle"
+
+
 def run(order, nx, ny, two_phase, algo, reps=20):
     basis = cc.LagrangeTensorProductBasis(2, order)
     phase = None
     if two_phase:
         i, j = np.divmod(np.arange(nx * ny), ny)
         cx, cy = (i + 0.5) / nx, (j + 0.5) / ny
-        phase = np.where((cx - 0.5) ** 2 + (cy - 0.5) ** 2 < 0.16, -1, 1).astype(np.int8)
+        inside = {"circle": (cx - 0.5) ** 2 + (cy - 0.5) ** 2 < 0.16, "vsplit": cx > 0.5, "hsplit": cy > 0.5,
+                  "allneg": cx > -1, "hstripes": (j // 300) % 2 == 1}[PATTERN]
+        phase = np.where(inside, -1, 1).astype(np.int8)
     mesh = cc.UniformMesh([0, 0], [1, 1], [nx, ny], basis, phase=phase)
     op = cc.IPOperator(mesh, order, order + 1, 1.0, 2.0, 1e3 * nx, 1.0, 0.5, "current", 255)
     x = torch.rand(op.ndofs, dtype=torch.float64, device="cuda") * 2 - 1
@@ -27,7 +32,7 @@ def run(order, nx, ny, two_phase, algo, reps=20):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     gdofs = op.ndofs / ms / 1e6
-    print(f"p={order} {nx}x{ny} two_phase={two_phase} algo={algo}: {ms:.3f} ms  {gdofs:.1f} GDOF/s  "
+    print(f"p={order} {nx}x{ny} two_phase={two_phase}{'/' + PATTERN if two_phase else ''} algo={algo}: {ms:.3f} ms  {gdofs:.1f} GDOF/s  "
           f"{16 * gdofs:.0f} GB/s  ({16 * gdofs / 6551 * 100:.1f}% of 6551)", flush=True)
 
 def run_ldg(order, n, two_phase, reps=20, algo=0):
@@ -129,7 +134,9 @@ if __name__ == "__main__":
     ap.add_argument("--ldg", type=int, default=0)
     ap.add_argument("--fd", type=int, default=0)
     ap.add_argument("--blocks", type=int, default=0)
+    ap.add_argument("--pattern", default="circle", help="two-phase pattern: circle|vsplit|hsplit|allneg|hstripes")
     args = ap.parse_args()
+    PATTERN = args.pattern
     if args.blocks:
         for o in ([args.order] if args.order else [1, 2, 3]):
             run_blocks(o, args.n or {1: 2000, 2: 1000, 3: 600}[o], args.reps)

@@ -529,15 +529,11 @@ ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const 
           }
         }
       };
+      // mode 1 / 2 / 3 = bit 0 / bit 1 / both: every phase body is instantiated exactly once
+      // (the code footprint matters: see the instruction-cache note at the end of the kernel)
       const int ph = cur.y & 3;
-      if (ph == 1) {
-        body(std::integral_constant<int, 0>{});
-      } else if (ph == 2) {
-        body(std::integral_constant<int, 1>{});
-      } else if (ph == 3) {
-        body(std::integral_constant<int, 0>{});
-        body(std::integral_constant<int, 1>{});
-      }
+      if (ph & 1) body(std::integral_constant<int, 0>{});
+      if (ph & 2) body(std::integral_constant<int, 1>{});
       yp += ycol;
       if constexpr (P == 2) {
         gstrip += colbytes;
@@ -553,26 +549,38 @@ ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const 
 #pragma unroll
       for (int t = 0; t < N1; ++t) tL[t] = Xc[P * N1 + t];
       const int phn = cur.y & 3;
-      if (phn == 1) {
-        MarchMath<P, 0>::x_moment_lo(tab, Xc, dL);
-      } else if (phn == 2) {
-        MarchMath<P, 1>::x_moment_lo(tab, Xc, dL);
-      } else if (phn == 3) {
+      if (phn & 1) MarchMath<P, 0>::x_moment_lo(tab, Xc, dL);
+      if (phn & 2) {
         double d1[N1];
-        MarchMath<P, 0>::x_moment_lo(tab, Xc, dL);
         MarchMath<P, 1>::x_moment_lo(tab, Xc, d1);
 #pragma unroll
-        for (int t = 0; t < N1; ++t) dL[t] = mine1 ? d1[t] : dL[t];
+        for (int t = 0; t < N1; ++t) dL[t] = (phn == 2 || mine1) ? d1[t] : dL[t];
       }
     };
 
     double Y[NF];  // the second cell buffer
-    int c = c0;
-    for (; c + 1 < c1; c += 2) {
-      column(c, X, Y);
-      column(c + 1, Y, X);
+#ifndef MARCH_PINGPONG3
+#define MARCH_PINGPONG3 0
+#endif
+    if constexpr (P != 3 || MARCH_PINGPONG3) {
+      // the two buffers alternate roles: no register copies between columns
+      int c = c0;
+      for (; c + 1 < c1; c += 2) {
+        column(c, X, Y);
+        column(c + 1, Y, X);
+      }
+      if (c < c1) column(c, X, Y);
+    } else {
+      // order 3: one copy of the (19 KB per phase) loop body instead of two, at the price of 32
+      // register moves per column -- where warps of one SM run both phase bodies the
+      // instruction cache is what limits (vertical-split mesh: 318 vs 352 GDOF/s single-phase)
+#pragma unroll 1
+      for (int c = c0; c < c1; ++c) {
+        column(c, X, Y);
+#pragma unroll
+        for (int q = 0; q < NF; ++q) X[q] = Y[q];
+      }
     }
-    if (c < c1) column(c, X, Y);
     if constexpr (C::OUTB != 0) {
       if (lane == 0) tma_store_wait_read<0>();
       __syncwarp();
