@@ -337,7 +337,7 @@ int stefan_ipdg_create(const stefan_ipdg_params* p, const int8_t* phase, const i
   cudaError_t e = cudaMalloc(&h->phase_dev, pn);
   if (e == cudaSuccess) e = cudaMemcpy(h->phase_dev, ph.data(), pn, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = h->plan.build(ph.data(), p->nx, p->ny, march_warps(p->order));
-  h->plan.mixed_cost_q = p->order == 1 ? 1 : (p->order == 2 ? 4 : 6);  // measured, see MarchPlan::segments
+  h->plan.mixed_cost_q = p->order == 1 ? 1 : 2;  // measured (quarter columns), see MarchPlan::segments
   if (e != cudaSuccess) { h->plan.destroy(); if (h->phase_dev) cudaFree(h->phase_dev); delete h; return fail(ST_CUDA_ERROR, "stefan_ipdg_create: %s", cudaGetErrorString(e)); }
   *out = reinterpret_cast<stefan_ipdg*>(h);
   return ST_OK;

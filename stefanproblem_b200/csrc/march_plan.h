@@ -142,9 +142,9 @@ struct MarchPlan {
   // mixes phases (both phase bodies run), so
   //     cost(group, [c0, c1)) = 4 (c1 - c0) + mixed_cost_q * max over the group's strips of
   //                                            #mixed columns of that strip in [c0, c1).
-  // mixed_cost_q is per kernel (measured per-CTA times: a mixed column costs an order-1 warp
-  // ~5 % more -- the kernel is memory-bound and the second body hides behind the loads -- but
-  // about as much as a whole column at orders 2 and 3).  T = the smallest tile cost whose
+  // mixed_cost_q is per kernel (measured: a mixed column costs an order-1 warp ~5 % more -- the
+  // kernel is memory-bound and the second body hides behind the loads -- and about half a
+  // column at orders 2 and 3).  T = the smallest tile cost whose
   // greedy cut fits the CTA budget (one wave); every group is then re-cut into the same number
   // of tiles of EQUAL cost (no short remainder tile).  Cached per column range.
   int mixed_cost_q = 4;  // quarter columns; set by the kernel's host code before the first apply
