@@ -338,15 +338,11 @@ ldg_apply_march(const __grid_constant__ LdgTab<P> tab, const LdgMarchArgs a, con
           }
         }
       };
+      // mode 1 / 2 / 3 = bit 0 / bit 1 / both: every phase body is instantiated exactly once
+      // (instruction-cache footprint)
       const int ph = cur.y & 3;
-      if (ph == 1) {
-        body(std::integral_constant<int, 0>{});
-      } else if (ph == 2) {
-        body(std::integral_constant<int, 1>{});
-      } else if (ph == 3) {
-        body(std::integral_constant<int, 0>{});
-        body(std::integral_constant<int, 1>{});
-      }
+      if (ph & 1) body(std::integral_constant<int, 0>{});
+      if (ph & 2) body(std::integral_constant<int, 1>{});
       yp += (size_t)a.ny * CD;
       if constexpr (C::OUTB != 0) gstrip += colbytes;
       if (c + 1 >= cur.x) {
