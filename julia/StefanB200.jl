@@ -119,7 +119,90 @@ function assemble_interior_penalty_linear_system!(s, solverbasis, cellquads, fac
 end
 end # module InteriorPenalty
 
+# ------------------------------------------------------------------------------ LocalDG
+module LocalDG
+import ..record!, ..SystemMatrix, ..SystemRHS
+# LDG_assembly.jl:1-91: divergence + mass + gradient cell operators, inter-element scalar and
+# vector fluxes with the switch V0 (passed positionally as `beta`, as the reference does),
+# boundary vector flux; interfacepenalty has no effect on an uncut mesh
+function assemble_LDG_linear_system!(s, basis, cellquads, facequads, interfacequads, k1, k2, interiorpenalty,
+                                     interfacepenalty, negboundarypenalty, posboundarypenalty, V0, mesh)
+    record!(s, :ldg, 63; order = basis.order, numqp = cellquads.numqp, k1 = k1, k2 = k2,
+            interiorpenalty = interiorpenalty, negboundarypenalty = negboundarypenalty,
+            posboundarypenalty = posboundarypenalty, V0 = (V0[1], V0[2]))
+end
+end # module LocalDG
+
 # ------------------------------------------------------------------------- C structs
+struct LdgParams           # stefan_ldg_params
+    nx::Int32; ny::Int32
+    hx::Float64; hy::Float64
+    order::Int32; numqp::Int32
+    k1::Float64; k2::Float64
+    interiorpenalty::Float64; negboundarypenalty::Float64; posboundarypenalty::Float64
+    V0x::Float64; V0y::Float64
+end
+
+mutable struct LDGOperator
+    handle::Ptr{Cvoid}
+    ndofs::Int
+    function LDGOperator(mesh::UniformMesh, sp::Dict{Symbol,Any})
+        h = element_size(mesh)
+        p = Ref(LdgParams(mesh.nelements[1], mesh.nelements[2], h[1], h[2], sp[:order], sp[:numqp], sp[:k1], sp[:k2],
+                          sp[:interiorpenalty], sp[:negboundarypenalty], sp[:posboundarypenalty], sp[:V0]...))
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:stefan_ldg_create, lib), Cint,
+                    (Ref{LdgParams}, Ptr{Int8}, Ptr{Int8}, Ptr{Int8}, Ref{Ptr{Cvoid}}),
+                    p, mesh.cellsign, C_NULL, C_NULL, out))
+        op = new(out[], ccall((:stefan_ldg_ndofs, lib), Int64, (Ptr{Cvoid},), out[]))
+        finalizer(o -> ccall((:stefan_ldg_destroy, lib), Cint, (Ptr{Cvoid},), o.handle), op)
+        op
+    end
+end
+
+"y = A x on the device (replaces `sparse_operator(sysmatrix, mesh, 3) * x`)."
+function Base.:*(A::LDGOperator, x::CuVector{Float64})
+    y = similar(x)
+    check(ccall((:stefan_ldg_apply, lib), Cint,
+                (Ptr{Cvoid}, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, Ptr{Cvoid}),
+                A.handle, x, y, CU_NULL, CU_NULL, CUDA.stream().handle))
+    y
+end
+
+# ------------------------------------------------------------------ element-block path
+# Arbitrary per-cell / per-face quadratures (cut and merged cells): flat device arrays in the
+# layout of `stefan_blocks_data` (include/stefan_b200.h); see INTEGRATION.md, "Cut-cell data".
+struct BlocksDims          # stefan_blocks_dims
+    ncells::Int32; order::Int32; nqv::Int32; nslots::Int32; nqf::Int32
+end
+struct BlocksData          # stefan_blocks_data (device pointers)
+    vol_pts::CuPtr{Float64}; vol_wts::CuPtr{Float64}; cell_jac::CuPtr{Float64}; cell_k::CuPtr{Float64}
+    slot_nbr::CuPtr{Int32}
+    face_pts::CuPtr{Float64}; face_nbr_pts::CuPtr{Float64}; face_wts::CuPtr{Float64}; face_normals::CuPtr{Float64}
+    slot_pen::CuPtr{Float64}; slot_lambda::CuPtr{Float64}
+end
+mutable struct BlockSystem
+    handle::Ptr{Cvoid}
+    ndofs::Int
+    function BlockSystem(dims::BlocksDims)
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:stefan_blocks_create, lib), Cint, (Ref{BlocksDims}, Ref{Ptr{Cvoid}}), Ref(dims), out))
+        b = new(out[], ccall((:stefan_blocks_ndofs, lib), Int64, (Ptr{Cvoid},), out[]))
+        finalizer(o -> ccall((:stefan_blocks_destroy, lib), Cint, (Ptr{Cvoid},), o.handle), b)
+        b
+    end
+end
+assemble!(b::BlockSystem, data::BlocksData) =
+    check(ccall((:stefan_blocks_assemble, lib), Cint, (Ptr{Cvoid}, Ref{BlocksData}, Ptr{Cvoid}),
+                b.handle, Ref(data), CUDA.stream().handle))
+function Base.:*(b::BlockSystem, x::CuVector{Float64})
+    y = similar(x)
+    check(ccall((:stefan_blocks_apply, lib), Cint, (Ptr{Cvoid}, CuPtr{Float64}, CuPtr{Float64}, Ptr{Cvoid}),
+                b.handle, x, y, CUDA.stream().handle))
+    y
+end
+
+# ------------------------------------------------------------------------- C structs (IP)
 struct IpdgParams          # stefan_ipdg_params
     nx::Int32; ny::Int32
     hx::Float64; hy::Float64
@@ -216,8 +299,12 @@ function sparse_operator(s::SystemMatrix, mesh::UniformMesh, dofspernode::Intege
         return IPOperator(mesh, sp[:order], sp[:numqp], sp[:k1], sp[:k2], get(sp, :penalty, 0.0),
                           get(sp, :lambda, 0.0), 0.0, 0, s.terms)
     end
-    # :ldg -> stefan_ldg_create / stefan_ldg_apply, :dg1d -> stefan_dg1d_*, same pattern
-    # (see INTEGRATION.md and the Python twin stefanproblem_b200/{local_dg,dg1d}.py)
+    if s.kind == :ldg
+        dofspernode == 3 || error("local DG has 3 dofs per node")
+        return LDGOperator(mesh, s.spec)
+    end
+    # :dg1d -> stefan_dg1d_create / stefan_dg1d_apply, same pattern
+    # (see INTEGRATION.md and the Python twin stefanproblem_b200/dg1d.py)
     error("nothing assembled (kind = $(s.kind))")
 end
 

@@ -42,7 +42,6 @@ struct ApplyArgs {
   double* y;
   const int8_t* phase;  // padded
   int nx, ny;
-  int nseg;  // x segments (march kernels)
   int cbeg, cend;  // columns to produce (a sub-range when the host path pipelines slabs)
   const int32_t* fix;  // cells the march kernels leave to their tail (see fixup_tail)
   int nfix;
@@ -386,7 +385,7 @@ int stefan_ipdg_apply(stefan_ipdg* hv, const double* x, double* y, const double*
                  (reinterpret_cast<uintptr_t>(x_lo) & hmask) == 0 && (reinterpret_cast<uintptr_t>(x_hi) & hmask) == 0,
                  "stefan_ipdg_apply: x, y must be 16-byte aligned (halo columns: 16, order 2: 8)");
   STEFAN_REQUIRE(algo >= 0 && algo <= 1, "stefan_ipdg_apply: unknown algo %d", algo);
-  ApplyArgs a{x, x_lo, x_hi, y, h->phase_dev, h->nx, h->ny, 1, 0, h->nx, nullptr, 0};
+  ApplyArgs a{x, x_lo, x_hi, y, h->phase_dev, h->nx, h->ny, 0, h->nx, nullptr, 0};
   return dispatch_apply(h, a, algo, static_cast<cudaStream_t>(stream));
 }
 
@@ -411,7 +410,7 @@ int stefan_ipdg_apply_peer(stefan_ipdg* hv, const double* x, double* y, const do
     STEFAN_CUDA(cudaMalloc(&h->sync_counter_dev, sizeof(unsigned)));
     STEFAN_CUDA(cudaMemset(h->sync_counter_dev, 0, sizeof(unsigned)));
   }
-  ApplyArgs a{x, x_lo, x_hi, y, h->phase_dev, h->nx, h->ny, 1, 0, h->nx, nullptr, 0};
+  ApplyArgs a{x, x_lo, x_hi, y, h->phase_dev, h->nx, h->ny, 0, h->nx, nullptr, 0};
   a.sync_my_ready = reinterpret_cast<unsigned long long*>(sync->my_ready);
   a.sync_my_done = reinterpret_cast<unsigned long long*>(sync->my_done);
   a.sync_lo_ready = reinterpret_cast<const unsigned long long*>(sync->lo_ready);
@@ -437,7 +436,7 @@ int stefan_ipdg_apply_columns(stefan_ipdg* hv, const double* x, double* y, const
   const bool needs_lo = col_begin == 0, needs_hi = col_end == h->nx;
   STEFAN_REQUIRE(!(needs_lo && h->has_lo && !x_lo) && !(needs_hi && h->has_hi && !x_hi),
                  "stefan_ipdg_apply_columns: the halo column next to the requested range is missing");
-  ApplyArgs a{x, h->has_lo ? x_lo : nullptr, h->has_hi ? x_hi : nullptr, y, h->phase_dev, h->nx, h->ny, 1, col_begin, col_end, nullptr, 0};
+  ApplyArgs a{x, h->has_lo ? x_lo : nullptr, h->has_hi ? x_hi : nullptr, y, h->phase_dev, h->nx, h->ny, col_begin, col_end, nullptr, 0};
   return dispatch_apply(h, a, algo, static_cast<cudaStream_t>(stream));
 }
 
@@ -472,7 +471,7 @@ int stefan_ipdg_apply_host(stefan_ipdg* hv, const double* x_host, double* y_host
     if (s >= 1) {  // slab s-1 needs the first column of slab s: wait for that upload
       const int k = s - 1;
       STEFAN_CUDA(cudaStreamWaitEvent(h->hs[1], h->hev[std::min(s, nslabs - 1)], 0));
-      ApplyArgs a{h->xh_dev, nullptr, nullptr, h->yh_dev, h->phase_dev, h->nx, h->ny, 1, slab_begin(k), slab_begin(k + 1), nullptr, 0};
+      ApplyArgs a{h->xh_dev, nullptr, nullptr, h->yh_dev, h->phase_dev, h->nx, h->ny, slab_begin(k), slab_begin(k + 1), nullptr, 0};
       int rc = dispatch_apply(h, a, 0, h->hs[1]);
       if (rc) return rc;
       STEFAN_CUDA(cudaEventRecord(h->hev[32 + k], h->hs[1]));
