@@ -52,10 +52,26 @@ __device__ __forceinline__ void mbar_wait_s(unsigned bar, unsigned parity) {
       "r"(parity)
       : "memory");
 }
+#ifndef MARCH_L2_HINT
+#define MARCH_L2_HINT 0  // 1: evict_first, 2: evict_last on the streaming TMA loads (tuning experiment)
+#endif
 __device__ __forceinline__ void bulk_load_s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+#if MARCH_L2_HINT
+  unsigned long long pol;
+#if MARCH_L2_HINT == 1
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+#else
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+#endif
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "l"(pol)
+      : "memory");
+#else
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+#endif
 }
 __device__ __forceinline__ void tensor2d_load_s(unsigned dst, const CUtensorMap* map, int c0, int c1, unsigned bar) {
   asm volatile(
