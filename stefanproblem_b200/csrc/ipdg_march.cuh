@@ -341,9 +341,20 @@ ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const 
     // is stored by the loop; of the phase mask: it has phase code 2.  mode & 3: 0 nothing
     // to store, 1 / 2 every stored cell has phase code 1 / 2, 3 both occur (both phase
     // bodies run, each storing its own lanes); mode & 4: the stored lanes are contiguous.
-    const int4* rp = runs + run_ofs[strip];
+    // the run that holds column c0: bisection over the strip's list (end columns increase);
+    // walking it from the start cost a chain of dependent L2 loads per tile -- hundreds in the
+    // strips that follow the interface
+    const int4* rp;
+    {
+      int lo = run_ofs[strip], hi = run_ofs[strip + 1] - 1;  // the sentinels end at INT_MAX
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(&runs[mid].x) > c0) hi = mid;
+        else lo = mid + 1;
+      }
+      rp = runs + lo;
+    }
     int4 cur = ld_run(rp);
-    while (cur.x <= c0) cur = ld_run(++rp);
     int4 nxt = ld_run(rp + 1);
     bool mine1 = (cur.z >> lane) & 1;  // this lane's cell has phase code 2
 

@@ -244,9 +244,20 @@ ldg_apply_march(const __grid_constant__ LdgTab<P> tab, const LdgMarchArgs a, con
     };
     auto released = [&](unsigned h) -> unsigned { return __reduce_xor_sync(0xffffffffu, h) & a.zero; };
 
-    const int4* rp = runs + run_ofs[strip];
+    // the run that holds column c0: bisection over the strip's list (end columns increase);
+    // walking it from the start cost a chain of dependent L2 loads per tile -- hundreds in the
+    // strips that follow the interface
+    const int4* rp;
+    {
+      int lo = run_ofs[strip], hi = run_ofs[strip + 1] - 1;  // the sentinels end at INT_MAX
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(&runs[mid].x) > c0) hi = mid;
+        else lo = mid + 1;
+      }
+      rp = runs + lo;
+    }
     int4 cur = ld_run(rp);
-    while (cur.x <= c0) cur = ld_run(++rp);
     int4 nxt = ld_run(rp + 1);
 
     // prologue: columns c0-1 .. c0+NST-2 into slots 0 .. NST-1

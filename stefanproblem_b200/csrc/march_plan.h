@@ -83,7 +83,7 @@ struct MarchPlan {
     std::vector<int>& run_ofs = run_ofs_host;
     fix.clear();
     runs.clear();
-    run_ofs.assign(nstrips, 0);
+    run_ofs.assign(nstrips + 1, 0);  // [nstrips] = total: the kernels bisect a strip's list
     seg_cache.clear();
     std::vector<uint32_t> smask((size_t)nstrips * nx), pmask((size_t)nstrips * nx);
     for (int i = 0; i < nx; ++i) {
@@ -122,6 +122,7 @@ struct MarchPlan {
       int* cum = mixed_cum.data() + (size_t)sidx * (nx + 1);
       for (int i = 0; i < nx; ++i) cum[i + 1] = cum[i] + ((sm[i] != 0 && pm[i] != 0 && pm[i] != sm[i]) ? 1 : 0);
     }
+    run_ofs[nstrips] = (int)runs.size();
     nfix = (int)fix.size();
     fix_col_ofs.assign(nx + 1, 0);
     for (int32_t cell : fix) fix_col_ofs[cell / ny + 1]++;
@@ -148,6 +149,7 @@ struct MarchPlan {
   // greedy cut fits the CTA budget (one wave); every group is then re-cut into the same number
   // of tiles of EQUAL cost (no short remainder tile).  Cached per column range.
   int mixed_cost_q = 4;  // quarter columns; set by the kernel's host code before the first apply
+  int min_tile_cols = 8;
   const SegCache& segments(int cbeg, int cend, int max_ctas) {
     for (const SegCache& c : seg_cache)
       if (c.cbeg == cbeg && c.cend == cend && c.max_ctas == max_ctas) return c;
@@ -184,7 +186,8 @@ struct MarchPlan {
     };
     const int budget = std::max(ng, std::min(max_ctas, kMaxMarchCtas));
     int hi = (4 + mixed_cost_q) * (cend - cbeg) + 1;
-    int lo = std::min(4 * 8, hi);  // tiles of at least ~8 columns
+    if (const char* e = getenv("STEFAN_MIN_TILE_COLS")) min_tile_cols = std::max(1, atoi(e));
+    int lo = std::min(4 * min_tile_cols, hi);  // tiles no shorter than this (pipeline fill per tile)
     while (lo < hi) {
       const int mid = (lo + hi) / 2;
       if (cut(mid) <= budget) hi = mid;

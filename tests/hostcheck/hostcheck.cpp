@@ -96,7 +96,7 @@ extern "C" int hostcheck_ldg_apply(int order, int nx, int ny, int nq, double jx,
 // The host plan of the march kernels (march_plan.h) for a mesh: run lists, fix list and the
 // CTA tiles of the column range [cbeg, cend).  phase: int8 +1/-1 per cell (no halos).
 // Outputs (caller-sized): runs [4 * nruns] (with the 3 sentinels per strip), run_ofs
-// [nstrips], fix [nx*ny], tiles [4 * 640]; counts come back through n_out[4] =
+// [nstrips + 1], fix [nx*ny], tiles [4 * 640]; counts come back through n_out[4] =
 // {nruns, nstrips, nfix, ntiles}.
 extern "C" int hostcheck_march_plan(int nx, int ny, const int8_t* phase, int group_warps, int cbeg, int cend,
                                     int max_ctas, int* runs, int* run_ofs, int* fix, int* tiles, int* n_out) {
@@ -112,7 +112,7 @@ extern "C" int hostcheck_march_plan(int nx, int ny, const int8_t* phase, int gro
     runs[4 * k + 2] = plan.runs_host[k].z;
     runs[4 * k + 3] = plan.runs_host[k].w;
   }
-  for (int s = 0; s < plan.nstrips; ++s) run_ofs[s] = plan.run_ofs_host[s];
+  for (int s = 0; s <= plan.nstrips; ++s) run_ofs[s] = plan.run_ofs_host[s];
   for (int k = 0; k < plan.nfix; ++k) fix[k] = plan.fix_host[k];
   for (int k = 0; k < sc.n; ++k) {
     tiles[4 * k + 0] = sc.tab.e[k].x;

@@ -181,7 +181,7 @@ def test_march_plan_invariants(hostcheck, nx, ny, warps, two_phase, cbeg_frac, c
     cbeg, cend = int(cbeg_frac * nx), max(int(cend_frac * nx), int(cbeg_frac * nx) + 1)
     nstrips = (ny + 29) // 30
     runs = np.zeros(4 * (nstrips * (nx + 3)), dtype=np.int32)
-    run_ofs = np.zeros(nstrips, dtype=np.int32)
+    run_ofs = np.zeros(nstrips + 1, dtype=np.int32)
     fix = np.zeros(nx * ny, dtype=np.int32)
     tiles = np.zeros(4 * 640, dtype=np.int32)
     n_out = np.zeros(4, dtype=np.int32)
