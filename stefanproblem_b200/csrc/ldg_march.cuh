@@ -86,27 +86,29 @@ __device__ __forceinline__ void ldg_fixup_tail(const LdgTab<P>& tab, const LdgMa
     const int s = ldg_phase_at(a.phase, a.ny, i, j);
     const int sL = ldg_phase_at(a.phase, a.ny, i - 1, j), sR = ldg_phase_at(a.phase, a.ny, i + 1, j);
     const int sD = ldg_phase_at(a.phase, a.ny, i, j - 1), sU = ldg_phase_at(a.phase, a.ny, i, j + 1);
-    double U[CD], UL[CD], UR[CD], UD[CD], UU[CD], out[CD];
+    double U[CD], out[CD];
+    double tLT[N1], tLQ[N1], tRT[N1], tRQ[N1], tDT[N1], tDQ[N1], tUT[N1], tUQ[N1];
     const double* xc = a.x + cell * CD;
     const double* pl = (i > 0) ? xc - (size_t)a.ny * CD : a.x_lo + (size_t)j * CD;
     const double* pr = (i < a.nx - 1) ? xc + (size_t)a.ny * CD : a.x_hi + (size_t)j * CD;
 #pragma unroll
     for (int k = 0; k < CD; ++k) U[k] = xc[k];
+    // of the neighbours only the face nodes' T and normal flux component (zeros where there is none)
 #pragma unroll
     for (int q = 0; q < N1; ++q) {
       const int nl = 3 * (P * N1 + q), nr = 3 * (0 * N1 + q);
-      UL[nl] = sL ? pl[nl] : 0.0;
-      UL[nl + 1] = sL ? pl[nl + 1] : 0.0;
-      UR[nr] = sR ? pr[nr] : 0.0;
-      UR[nr + 1] = sR ? pr[nr + 1] : 0.0;
+      tLT[q] = sL ? pl[nl] : 0.0;
+      tLQ[q] = sL ? pl[nl + 1] : 0.0;
+      tRT[q] = sR ? pr[nr] : 0.0;
+      tRQ[q] = sR ? pr[nr + 1] : 0.0;
       const int nd = 3 * (q * N1 + P), nu = 3 * (q * N1 + 0);
-      UD[nd] = sD ? xc[nd - CD] : 0.0;
-      UD[nd + 2] = sD ? xc[nd + 2 - CD] : 0.0;
-      UU[nu] = sU ? xc[nu + CD] : 0.0;
-      UU[nu + 2] = sU ? xc[nu + 2 + CD] : 0.0;
+      tDT[q] = sD ? xc[nd - CD] : 0.0;
+      tDQ[q] = sD ? xc[nd + 2 - CD] : 0.0;
+      tUT[q] = sU ? xc[nu + CD] : 0.0;
+      tUQ[q] = sU ? xc[nu + 2 + CD] : 0.0;
     }
-    ldg_cell_rows<P>(tab, s == 1 ? 0 : 1, ip_face_type(s, sL), ip_face_type(s, sR), ip_face_type(s, sD),
-                     ip_face_type(s, sU), U, UL, UR, UD, UU, out);
+    ldg_rows_streamed_general<P>(tab, s == 1 ? 0 : 1, ip_face_type(s, sL), ip_face_type(s, sR), ip_face_type(s, sD),
+                                 ip_face_type(s, sU), U, tLT, tLQ, tRT, tRQ, tDT, tDQ, tUT, tUQ, out);
     double* yc = a.y + cell * CD;
 #pragma unroll
     for (int k = 0; k < CD; ++k) yc[k] = out[k];

@@ -164,20 +164,20 @@ void ldg_cell_rows(const LdgTab<P>& tab, int s, int tL, int tR, int tD, int tU,
 #undef QY_
 }
 
-// The same rows for an interior cell of phase index S with four same-phase neighbours, in the
-// form the march kernel uses: the neighbours enter as face traces (T and the normal flux
+// The same rows (phase index S, face types tL .. tU) in the form the march kernel uses: the neighbours enter as face traces (T and the normal flux
 // component at the face nodes), and the sum-factorisation intermediates are never stored --
 // every x-line (fixed iy) / y-line (fixed ix) result is scattered straight into the output
 // accumulators through the 1-D mass matrix.  Live data: the cell (3 NF), the output (3 NF) and
 // 2 (P+1) line temporaries, instead of 4 NF intermediates on top (order 3: 110 instead of
 // 160 doubles, which is what fits the register file).
-template <int P, int S>
+template <int P>
 #if defined(__CUDACC__)
 __host__ __device__ __forceinline__
 #else
 inline
 #endif
-void ldg_rows_streamed(const LdgTab<P>& tab, const double* __restrict__ U, const double* __restrict__ tLT,
+void ldg_rows_streamed_general(const LdgTab<P>& tab, const int S, const int tL, const int tR, const int tD,
+                               const int tU, const double* __restrict__ U, const double* __restrict__ tLT,
                        const double* __restrict__ tLQ, const double* __restrict__ tRT,
                        const double* __restrict__ tRQ, const double* __restrict__ tDT,
                        const double* __restrict__ tDQ, const double* __restrict__ tUT,
@@ -203,15 +203,15 @@ void ldg_rows_streamed(const LdgTab<P>& tab, const double* __restrict__ U, const
       g_x *= k;
       if (ix == 0) {
         const double t = U[3 * (0 * N1 + iy) + 0], q = U[3 * (0 * N1 + iy) + 1];
-        cqx += tab.sqK[0][0][T_SAME] * t + tab.sqN[0][0][T_SAME] * tLT[iy];
-        g_x += tab.tqK[S][0][0][T_SAME] * q + tab.tqN[S][0][0][T_SAME] * tLQ[iy] + tab.tpK[0][0][T_SAME] * t +
-               tab.tpN[0][0][T_SAME] * tLT[iy];
+        cqx += tab.sqK[0][0][tL] * t + tab.sqN[0][0][tL] * tLT[iy];
+        g_x += tab.tqK[S][0][0][tL] * q + tab.tqN[S][0][0][tL] * tLQ[iy] + tab.tpK[0][0][tL] * t +
+               tab.tpN[0][0][tL] * tLT[iy];
       }
       if (ix == P) {
         const double t = U[3 * (P * N1 + iy) + 0], q = U[3 * (P * N1 + iy) + 1];
-        cqx += tab.sqK[0][1][T_SAME] * t + tab.sqN[0][1][T_SAME] * tRT[iy];
-        g_x += tab.tqK[S][0][1][T_SAME] * q + tab.tqN[S][0][1][T_SAME] * tRQ[iy] + tab.tpK[0][1][T_SAME] * t +
-               tab.tpN[0][1][T_SAME] * tRT[iy];
+        cqx += tab.sqK[0][1][tR] * t + tab.sqN[0][1][tR] * tRT[iy];
+        g_x += tab.tqK[S][0][1][tR] * q + tab.tqN[S][0][1][tR] * tRQ[iy] + tab.tpK[0][1][tR] * t +
+               tab.tpN[0][1][tR] * tRT[iy];
       }
       const double a = cqx + mqx;
 #pragma unroll
@@ -237,15 +237,15 @@ void ldg_rows_streamed(const LdgTab<P>& tab, const double* __restrict__ U, const
       g_y *= k;
       if (iy == 0) {
         const double t = U[3 * (ix * N1 + 0) + 0], q = U[3 * (ix * N1 + 0) + 2];
-        cqy += tab.sqK[1][0][T_SAME] * t + tab.sqN[1][0][T_SAME] * tDT[ix];
-        g_y += tab.tqK[S][1][0][T_SAME] * q + tab.tqN[S][1][0][T_SAME] * tDQ[ix] + tab.tpK[1][0][T_SAME] * t +
-               tab.tpN[1][0][T_SAME] * tDT[ix];
+        cqy += tab.sqK[1][0][tD] * t + tab.sqN[1][0][tD] * tDT[ix];
+        g_y += tab.tqK[S][1][0][tD] * q + tab.tqN[S][1][0][tD] * tDQ[ix] + tab.tpK[1][0][tD] * t +
+               tab.tpN[1][0][tD] * tDT[ix];
       }
       if (iy == P) {
         const double t = U[3 * (ix * N1 + P) + 0], q = U[3 * (ix * N1 + P) + 2];
-        cqy += tab.sqK[1][1][T_SAME] * t + tab.sqN[1][1][T_SAME] * tUT[ix];
-        g_y += tab.tqK[S][1][1][T_SAME] * q + tab.tqN[S][1][1][T_SAME] * tUQ[ix] + tab.tpK[1][1][T_SAME] * t +
-               tab.tpN[1][1][T_SAME] * tUT[ix];
+        cqy += tab.sqK[1][1][tU] * t + tab.sqN[1][1][tU] * tUT[ix];
+        g_y += tab.tqK[S][1][1][tU] * q + tab.tqN[S][1][1][tU] * tUQ[ix] + tab.tpK[1][1][tU] * t +
+               tab.tpN[1][1][tU] * tUT[ix];
       }
       const double a = cqy + mqy;
 #pragma unroll
@@ -255,6 +255,21 @@ void ldg_rows_streamed(const LdgTab<P>& tab, const double* __restrict__ U, const
       }
     }
   }
+}
+
+// compile-time phase, four same-phase neighbours: what the march loop calls
+template <int P, int S>
+#if defined(__CUDACC__)
+__host__ __device__ __forceinline__
+#else
+inline
+#endif
+void ldg_rows_streamed(const LdgTab<P>& tab, const double* __restrict__ U, const double* __restrict__ tLT,
+                       const double* __restrict__ tLQ, const double* __restrict__ tRT,
+                       const double* __restrict__ tRQ, const double* __restrict__ tDT,
+                       const double* __restrict__ tDQ, const double* __restrict__ tUT,
+                       const double* __restrict__ tUQ, double* __restrict__ out) {
+  ldg_rows_streamed_general<P>(tab, S, T_SAME, T_SAME, T_SAME, T_SAME, U, tLT, tLQ, tRT, tRQ, tDT, tDQ, tUT, tUQ, out);
 }
 
 }  // namespace stefan

@@ -155,6 +155,17 @@ static int run_ldg_streamed(int nq, double jx, double jy, LdgPhys ph, int s, con
   }
   if (s == 0) ldg_rows_streamed<P, 0>(tab, U, tLT, tLQ, tRT, tRQ, tDT, tDQ, tUT, tUQ, out_streamed);
   else ldg_rows_streamed<P, 1>(tab, U, tLT, tLQ, tRT, tRQ, tDT, tDQ, tUT, tUQ, out_streamed);
+  // every combination of face types: the general streamed form (the kernels' tail) against the
+  // general row function; both outputs are appended after the first CD entries
+  int n = 1;
+  for (int tL = 0; tL < 3; ++tL)
+    for (int tR = 0; tR < 3; ++tR)
+      for (int tD = 0; tD < 3; ++tD)
+        for (int tU = 0; tU < 3; ++tU, ++n) {
+          ldg_cell_rows<P>(tab, s, tL, tR, tD, tU, U, UL, UR, UD, UU, out_general + (size_t)n * CD);
+          ldg_rows_streamed_general<P>(tab, s, tL, tR, tD, tU, U, tLT, tLQ, tRT, tRQ, tDT, tDQ, tUT, tUQ,
+                                       out_streamed + (size_t)n * CD);
+        }
   return 0;
 }
 

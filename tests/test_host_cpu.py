@@ -238,7 +238,7 @@ def test_ldg_streamed_rows_equal_general_rows(hostcheck, order, s):
     rng = np.random.default_rng(order * 10 + s)
     cd = 3 * (order + 1) ** 2
     x9 = rng.uniform(-1, 1, 9 * cd)
-    g, st = np.zeros(cd), np.zeros(cd)
+    g, st = np.zeros(82 * cd), np.zeros(82 * cd)  # T_SAME everywhere, then all 81 face-type combinations
     d = ctypes.c_double
     dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))  # noqa: E731
     rc = hostcheck.hostcheck_ldg_streamed(order, order + 1, d(0.013), d(0.021), d(1.0), d(2.0), d(0.7), d(0.3), d(1.1),
