@@ -395,7 +395,7 @@ def main():
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel for the default
 # workload, from profiles/ (updated whenever the kernel is re-profiled)
-PROFILED_TRAFFIC_BYTES = 819.267584e6 + 759.06304e6  # profiles/r1_ipdg_p1_march_ncu.csv
+PROFILED_TRAFFIC_BYTES = 819.482624e6 + 758.8672e6  # profiles/r1_ipdg_p1_march_ncu.csv
 
 if __name__ == "__main__":
     main()
