@@ -245,3 +245,18 @@ def test_ldg_streamed_rows_equal_general_rows(hostcheck, order, s):
                                           d(np.cos(0.6)), d(np.sin(0.6)), s, dp(x9), dp(g), dp(st))
     assert rc == 0
     assert np.abs(g - st).max() <= 1e-13 * np.abs(g).max()
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU path of the reference restated in C) runs without a
+    GPU and prints one JSON line with the keys the driver reads."""
+    import json
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "1"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "DOF-updates/s" and line["value"] > 0
+    assert line["metric"].startswith("fp64 DOF-updates/sec") and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
