@@ -260,3 +260,20 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["metric"].startswith("fp64 DOF-updates/sec") and line["higher_is_better"] is True
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/stefan_b200.h is what a cgo / ccall / ctypes binding reads: it must compile as
+    C99 on its own (no C++-isms, no CUDA headers), and link against the built library."""
+    src = tmp_path / "abi.c"
+    src.write_text('#include "stefan_b200.h"\n'
+                   "int main(void) {\n"
+                   "  stefan_ipdg_params p; stefan_blocks_dims d; stefan_peer_sync s; stefan_cg_params c;\n"
+                   "  (void)p; (void)d; (void)s; (void)c;\n"
+                   "  return stefan_version() > 0 && stefan_last_error() != 0 ? 0 : 1;\n"
+                   "}\n")
+    exe = tmp_path / "abi"
+    libdir = os.path.join(ROOT, "stefanproblem_b200", "lib")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src),
+                    "-o", str(exe), "-L", libdir, "-lstefan_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    assert subprocess.run([str(exe)]).returncode == 0
