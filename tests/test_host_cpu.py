@@ -262,7 +262,7 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
 
 
-def test_header_is_plain_c(tmp_path):
+def test_header_is_plain_c(tmp_path, built_lib):
     """include/stefan_b200.h is what a cgo / ccall / ctypes binding reads: it must compile as
     C99 on its own (no C++-isms, no CUDA headers), and link against the built library."""
     src = tmp_path / "abi.c"
