@@ -136,9 +136,23 @@ def run_ours(args):
     peer = world > 1 and args.halo == "peer"
     slab = None
     if peer:
-        slab = PeerSlab(ndofs_local, rank, world)
-        slab.x.copy_(x)
-        x = slab.x
+        # collective; if CUDA IPC is not available to some rank (container policy), every rank
+        # falls back to the NCCL halos together and the line says so
+        failed = 0
+        try:
+            slab = PeerSlab(ndofs_local, rank, world)
+        except Exception as exc:  # noqa: BLE001
+            failed = 1
+            sys.stderr.write(f"rank {rank}: peer memory unavailable ({exc}); falling back to --halo nccl\n")
+        flag = torch.tensor([failed], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        if int(flag.item()):
+            if slab is not None:
+                slab.close()
+            slab, peer = None, False
+        else:
+            slab.x.copy_(x)
+            x = slab.x
 
     def step():
         if peer:
