@@ -309,3 +309,34 @@ def test_cg_solve_and_l2_error(cuda, order, n, two_phase, precond):
     oerr = mesh_L2_error(xref[None, :], ex, OB(2, order), CellQuadratures(nq), omesh)[0]
     oref = integral_norm_on_mesh(ex, CellQuadratures(nq), omesh, 1)[0]
     assert abs(err - oerr) <= 1e-7 * oerr + 1e-12 and abs(ref - oref) <= 1e-12 * oref
+
+
+def test_reference_convergence_study_end_to_end_on_gpu(cuda):
+    """examples/uncut_ip_convergence.py = test_uncut_IP_convergence.jl through the Python twin
+    (GPU operator, GPU rhs, device CG, device L2 error).  The reference's acceptance
+    criterion for this study is the convergence rate (`rate > 1.95`-style @tests, SURVEY.md
+    4.1); the errors themselves are checked against the oracle's direct solve above."""
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "uncut_ip_convergence.py")
+    spec = importlib.util.spec_from_file_location("uncut_ip_convergence", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    nelmts, err, rate = mod.main(1, powers=(1, 2, 3, 4, 5))
+    assert np.all(np.diff(err) < 0) and rate[-1] > 1.95 and rate[-2] > 1.9
+    nelmts, err2, rate2 = mod.main(2, powers=(1, 2, 3, 4))
+    assert rate2[-1] > 2.9
+    # the oracle's numbers for the first meshes (same variant, direct solve)
+    from oracle.basis import LagrangeTensorProductBasis as OB
+    from oracle.mesh import CellQuadratures
+    from oracle.norms import mesh_L2_error
+    import scipy.sparse.linalg as spla
+    for n, e in zip(nelmts[:2], err[:2]):
+        om = UniformMesh2D([0, 0], [1, 1], [n, n], 4)
+        A = fast.ip_matrix(om, 1, 2, 1.0, 1.0, 1e3 * n)
+        b = fast.ip_rhs(om, 1, 2, 1.0, 1.0, 1e3 * n,
+                        fast.sample_cell_quadrature(om, 2, lambda x, y: mod.source_term((x, y), 1.0)),
+                        fast.sample_face_quadrature(om, 2, lambda x, y: mod.exact_solution((x, y))))
+        xo = spla.spsolve(A.tocsc(), b)
+        eo = mesh_L2_error(xo[None, :], mod.exact_solution, OB(2, 1), CellQuadratures(2), om)[0]
+        assert abs(e - eo) <= 1e-7 * eo
