@@ -146,3 +146,21 @@ def test_rhs_and_golden_solve(cuda, order, nq):
     assert gold[0] == 5
     ref = gold[1] if order == 1 else gold[4]
     assert abs(errT - ref) / ref < 1e-10
+
+
+def test_reference_ldg_convergence_csv_through_the_coo_seam(cuda):
+    """examples/uncut_ldg_convergence.py: GPU-assembled triplets (COO seam) + GPU right-hand
+    side, solved on the host the way the reference does, reproduce the rows of the reference's
+    stored MD-LDG_convergence.csv (tests/golden/reference_csv.json) for nelmts = 3 .. 17."""
+    import importlib.util
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("uncut_ldg_convergence", os.path.join(root, "examples", "uncut_ldg_convergence.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    table = mod.main(powers=(1, 2, 3, 4))
+    gold = json.load(open(os.path.join(root, "tests", "golden", "reference_csv.json")))["ldg_uncut"]
+    for got, ref in zip(table, gold):
+        assert got[0] == ref[0]
+        assert np.allclose(got[1:], ref[1:], rtol=1e-9, atol=0.0), (got, ref)
