@@ -277,3 +277,26 @@ def test_header_is_plain_c(tmp_path, built_lib):
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src),
                     "-o", str(exe), "-L", libdir, "-lstefan_b200", f"-Wl,-rpath,{libdir}"], check=True)
     assert subprocess.run([str(exe)]).returncode == 0
+
+
+@pytest.mark.parametrize("order,nq", [(1, 2), (2, 5)])
+def test_ldg_example_host_error_norm_matches_oracle(order, nq):
+    """examples/uncut_ldg_convergence.py's host `mesh_L2_error` (node / point ordering of the
+    device layout) against the oracle's restatement of useful_routines.jl:95-133."""
+    import importlib.util
+    from oracle.basis import LagrangeTensorProductBasis as OB
+    from oracle.mesh import CellQuadratures, UniformMesh2D
+    from oracle.norms import mesh_L2_error
+    from stefanproblem_b200 import cutcelldg as cc
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("uncut_ldg_convergence", os.path.join(root, "examples", "uncut_ldg_convergence.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    n, nf = 4, (order + 1) ** 2
+    om = UniformMesh2D([0, 0], [1, 1], [n, n], nf)
+    f = np.random.default_rng(3).standard_normal((1, n * n * nf))
+    ref = mesh_L2_error(f, m.exact_solution, OB(2, order), CellQuadratures(nq), om)[0]
+    mesh = cc.UniformMesh([0, 0], [1, 1], [n, n], cc.LagrangeTensorProductBasis(2, order))
+    x, y = cc.cell_quadrature_points(mesh, nq)
+    got = m.mesh_L2_error(f.reshape(-1, nf), m.exact_solution((x, y)), order, nq, n, 1.0 / n)
+    assert abs(got - ref) <= 1e-13 * ref
