@@ -129,6 +129,37 @@ class DistributedIPOperator:
         return out
 
 
+class DistributedFDOperator:
+    """The 1-D finite-difference operator (finite-difference.jl:34-116) on `numnodes` global
+    nodes, one contiguous node range per rank; the one-sided interface rows reach three nodes,
+    so the halo is the neighbour's three adjacent nodes (`HaloExchange(3, ...)`).  Dirichlet
+    identity rows exist on the first node of rank 0 and the last node of the last rank."""
+
+    def __init__(self, phaseid, stepsize, rank, world):
+        import torch
+        from . import finite_difference as FD
+        phaseid = np.ascontiguousarray(phaseid, dtype=np.int8)
+        self.rank, self.world = rank, world
+        self.i0, self.i1 = slab_range(phaseid.size, world, rank)
+        if world > 1 and self.i1 - self.i0 < 3:
+            raise ValueError("a rank's node range must hold the 3-node halo of its neighbour")
+        plo = phaseid[self.i0 - 3:self.i0] if rank > 0 else None
+        phi = phaseid[self.i1:self.i1 + 3] if rank < world - 1 else None
+        self.op = FD.FDOperator(phaseid[self.i0:self.i1], stepsize, phase_lo=plo, phase_hi=phi)
+        self.n = self.i1 - self.i0
+        self.halo = HaloExchange(3, rank, world, torch.empty(0, dtype=torch.float64, device="cuda"))
+
+    def apply(self, u, out=None):
+        """out = A u on this rank's nodes."""
+        lo, hi = self.halo.exchange(u)
+        return self.op.apply(u, out=out, u_lo=lo, u_hi=hi)
+
+    def step(self, u, dt, kappa1, kappa2, out=None):
+        """One fused explicit step u + dt * kappa(phase) * (A u) on this rank's nodes."""
+        lo, hi = self.halo.exchange(u)
+        return self.op.step(u, dt, kappa1, kappa2, out=out, u_lo=lo, u_hi=hi)
+
+
 class _DevArray:
     """__cuda_array_interface__ view of raw device memory (lets torch wrap it without a copy)."""
 

@@ -69,3 +69,45 @@ def test_slab_range_properties():
             r = [slab_range(n, w, k) for k in range(w)]
             assert r[0][0] == 0 and r[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(r[:-1], r[1:]))
+
+
+def _fd_worker(rank, world, port, n, q):
+    sys.path.insert(0, ROOT)
+    from oracle import fd as ofd
+    from stefanproblem_b200.distributed import HaloExchange, slab_range
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # an interface two nodes beyond the first cut: the one-sided rows reach across the halo
+        cut = slab_range(n, world, 1)[0]
+        ph = np.where((np.arange(n) >= n // 5) & (np.arange(n) < cut + 2), 1, 2).astype(np.int8)
+        A = ofd.laplace_matrix(ph, 1.0 / (n - 1)).tocsr()
+        ug = np.random.default_rng(4).uniform(-1, 1, n)
+        b, e = slab_range(n, world, rank)
+        u = torch.from_numpy(ug[b:e].copy())
+        lo, hi = HaloExchange(3, rank, world, u).exchange(u)
+        c0, c1 = (b - 3 if rank > 0 else b), (e + 3 if rank < world - 1 else e)
+        padded = np.concatenate([t.numpy() for t in (lo, u, hi) if t is not None])
+        rows = A[b:e]
+        inside = (rows.indices >= c0) & (rows.indices < c1)   # every row of the node range stays within the halo
+        ok = bool(inside.all()) and np.array_equal(rows[:, c0:c1] @ padded, (A @ ug)[b:e])
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_fd_three_node_halos_reproduce_the_global_rows(world):
+    """The node-range partition of `DistributedFDOperator`: three halo nodes per side carry every
+    row of finite-difference.jl:34-85 (the one-sided interface rows included) on world_size 2 and 3."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_fd_worker, args=(r, world, 29680 + world, 101, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res)
