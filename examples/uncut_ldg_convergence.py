@@ -10,7 +10,11 @@ LDG system is not symmetric, so the device CG does not apply.  With the referenc
 parameters (penalties (0, 0, 0, 1), V0 at 45 degrees, numqp = p+1 for p = 1 and p+3 for
 p = 2) the printed numbers are the rows of its stored MD-LDG_convergence.csv.
 
-    python examples/uncut_ldg_convergence.py
+`--device-solve` replaces the host solve by `op.solve(rhs)`: Schur complement on T + BiCGStab
+over the device operator (stefanproblem_b200/ldg_solve.py), nothing assembled at all; the
+errors then agree with the CSV to the iteration's tolerance instead of to round-off.
+
+    python examples/uncut_ldg_convergence.py [--device-solve]
 """
 import os
 import sys
@@ -59,7 +63,7 @@ def mesh_L2_error(field, exact_qp, order, numqp, nelmts, h):
 
 
 def measure_error(nelmts, solverorder, numqp, k1, k2, interiorpenalty, interfacepenalty, negboundarypenalty,
-                  posboundarypenalty, V0):
+                  posboundarypenalty, V0, device_solve=False):
     import scipy.sparse as sp
     import scipy.sparse.linalg as spla
     from stefanproblem_b200 import cutcelldg as CutCellDG
@@ -73,11 +77,16 @@ def measure_error(nelmts, solverorder, numqp, k1, k2, interiorpenalty, interface
     LocalDG.assemble_LDG_rhs(sysrhs, lambda v: source_term(v, k1), exact_solution, basis, cellquads, facequads,
                              negboundarypenalty, posboundarypenalty, V0, mesh)
     op = LocalDG.sparse_operator(sysmatrix, mesh, 3)            # device operator
-    rhs = LocalDG.rhs_vector(sysrhs, mesh, 3).cpu().numpy()
-    rows, cols, vals = (t.cpu().numpy() for t in op.to_coo(index_base=1))      # the COO seam, Julia indices
-    matrix = sp.coo_matrix((vals, (rows - 1, cols - 1)), shape=(op.ndofs, op.ndofs)).tocsc()
-    matrix.eliminate_zeros()                                    # dropzeros!(sparse(rows, cols, vals, N, N))
-    sol = spla.spsolve(matrix, rhs).reshape(-1, 3)              # [node, (T, qx, qy)]
+    rhs = LocalDG.rhs_vector(sysrhs, mesh, 3)
+    if device_solve:
+        sol, info = op.solve(rhs, tol=1e-13)
+        assert info["converged"], info
+        sol = sol.cpu().numpy().reshape(-1, 3)
+    else:
+        rows, cols, vals = (t.cpu().numpy() for t in op.to_coo(index_base=1))      # the COO seam, Julia indices
+        matrix = sp.coo_matrix((vals, (rows - 1, cols - 1)), shape=(op.ndofs, op.ndofs)).tocsc()
+        matrix.eliminate_zeros()                                # dropzeros!(sparse(rows, cols, vals, N, N))
+        sol = spla.spsolve(matrix, rhs.cpu().numpy()).reshape(-1, 3)               # [node, (T, qx, qy)]
     nf = (solverorder + 1) ** 2
     T, Gx, Gy = (sol[:, c].reshape(-1, nf) for c in range(3))
     x, y = CutCellDG.cell_quadrature_points(mesh, numqp)
@@ -89,17 +98,17 @@ def measure_error(nelmts, solverorder, numqp, k1, k2, interiorpenalty, interface
             mesh_L2_error(Gx, gx, solverorder, numqp, nelmts, h), mesh_L2_error(Gy, gy, solverorder, numqp, nelmts, h))
 
 
-def main(powers=(1, 2, 3, 4, 5)):
+def main(powers=(1, 2, 3, 4, 5), device_solve=False):
     V0 = (np.cos(np.radians(45.0)), np.sin(np.radians(45.0)))
     table = []
     for n in [2 ** p + 1 for p in powers]:
         row = [n]
         for order, numqp in ((1, 2), (2, 5)):
-            row += list(measure_error(n, order, numqp, 1.0, 1.0, 0.0, 0.0, 0.0, 1.0, V0))
+            row += list(measure_error(n, order, numqp, 1.0, 1.0, 0.0, 0.0, 0.0, 1.0, V0, device_solve))
         table.append(row)
         print("  ".join([f"{row[0]:3d}"] + [f"{v:.12e}" for v in row[1:]]))
     return table
 
 
 if __name__ == "__main__":
-    main()
+    main(device_solve="--device-solve" in sys.argv)

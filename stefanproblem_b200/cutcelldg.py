@@ -395,6 +395,17 @@ class LDGOperator:
                                                     int(algo), _stream_ptr(stream)))
         return out
 
+    def solve(self, rhs, tol=1e-12, maxiter=20000):
+        """`matrix \\ rhs` on the device: Schur complement on T + BiCGStab over this operator's
+        kernels (`ldg_solve.schur_solve`; unpreconditioned, for the sizes of the reference's
+        convergence studies).  Returns (solution, info)."""
+        import torch
+        from .ldg_solve import cell_mass_inverse, schur_solve
+        assert rhs.is_cuda and rhs.dtype == torch.float64 and rhs.numel() == self.ndofs
+        mass1d = reference_tables(self.order, self.params.numqp)["mass"]
+        minv = torch.from_numpy(cell_mass_inverse(mass1d, 0.25 * self.params.hx * self.params.hy)).cuda()
+        return schur_solve(lambda x: self.apply(x), minv, rhs.contiguous(), self.nf, tol, maxiter)
+
     def to_coo(self, index_base=0):
         """(rows, cols, vals) device tensors of the assembled operator (the COO seam)."""
         import torch

@@ -300,3 +300,29 @@ def test_ldg_example_host_error_norm_matches_oracle(order, nq):
     x, y = cc.cell_quadrature_points(mesh, nq)
     got = m.mesh_L2_error(f.reshape(-1, nf), m.exact_solution((x, y)), order, nq, n, 1.0 / n)
     assert abs(got - ref) <= 1e-13 * ref
+
+
+@pytest.mark.parametrize("order,nq,n", [(1, 2, 9), (2, 5, 5), (3, 4, 4)])
+def test_ldg_schur_bicgstab_against_direct_solve(order, nq, n):
+    """`ldg_solve.schur_solve` (the device `matrix \\ rhs` of the LDG twin) driven on the CPU with
+    the oracle's assembled matrix as the operator: same solution as the sparse direct solve."""
+    import scipy.sparse.linalg as spla
+    import torch
+    from stefanproblem_b200 import cutcelldg as cc
+    from stefanproblem_b200.ldg_solve import cell_mass_inverse, schur_solve
+    V0 = np.array([np.cos(np.pi / 4), np.sin(np.pi / 4)])
+    ex = lambda x, y: np.cos(2 * np.pi * x) * np.sin(2 * np.pi * y)  # noqa: E731
+    src = lambda x, y: 8 * np.pi ** 2 * np.cos(2 * np.pi * x) * np.sin(2 * np.pi * y)  # noqa: E731
+    nf = (order + 1) ** 2
+    om = UniformMesh2D([0, 0], [1, 1], [n, n], nf)
+    A = fast.ldg_matrix(om, order, nq, 1.0, 1.0, 0.0, 0.0, 1.0, V0).tocsr()
+    b = fast.ldg_rhs(om, order, nq, 0.0, 1.0, V0, fast.sample_cell_quadrature(om, nq, src),
+                     fast.sample_face_quadrature(om, nq, ex))
+    minv = torch.from_numpy(cell_mass_inverse(cc.reference_tables(order, nq)["mass"], 0.25 / (n * n)))
+    # the q-q block of the reference's system is exactly the cell mass matrix the elimination assumes
+    qq = A[1:3 * nf:3, 1:3 * nf:3].toarray()
+    assert np.allclose(qq @ minv.numpy(), np.eye(nf), atol=1e-12)
+    sol, info = schur_solve(lambda x: torch.from_numpy(A @ x.numpy()), minv, torch.from_numpy(b), nf, tol=1e-13)
+    ref = spla.spsolve(A.tocsc(), b)
+    assert info["converged"] and info["relative_residual"] < 1e-12
+    assert np.linalg.norm(sol.numpy() - ref) <= 1e-10 * np.linalg.norm(ref)

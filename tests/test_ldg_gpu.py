@@ -164,3 +164,21 @@ def test_reference_ldg_convergence_csv_through_the_coo_seam(cuda):
     for got, ref in zip(table, gold):
         assert got[0] == ref[0]
         assert np.allclose(got[1:], ref[1:], rtol=1e-9, atol=0.0), (got, ref)
+
+
+def test_device_schur_solve_reproduces_the_reference_csv(cuda):
+    """`LDGOperator.solve` (Schur complement on T, BiCGStab over the device operator) in the
+    reference's convergence study: the errors of nelmts = 3, 5, 9 agree with the stored
+    MD-LDG_convergence.csv to the iteration's tolerance (1e-7 relative; solver tol 1e-13)."""
+    import importlib.util
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("uncut_ldg_convergence", os.path.join(root, "examples", "uncut_ldg_convergence.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    table = mod.main(powers=(1, 2, 3), device_solve=True)
+    gold = json.load(open(os.path.join(root, "tests", "golden", "reference_csv.json")))["ldg_uncut"]
+    for got, ref in zip(table, gold):
+        assert got[0] == ref[0]
+        assert np.allclose(got[1:], ref[1:], rtol=1e-7, atol=0.0), (got, ref)
