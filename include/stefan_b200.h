@@ -372,6 +372,19 @@ typedef struct {
 int stefan_ipdg_apply_peer(stefan_ipdg* h, const double* x, double* y, const double* x_lo, const double* x_hi,
                            const stefan_peer_sync* sync, void* stream);
 
+/* The fused explicit time step (the reference assembles a steady operator and never
+ * time-steps, so the definition is oracle/timeloop.py::ip_euler_run):
+ *     unew = u + dt * Minv * (b - A u),   M = block-diagonal DG mass matrix (CutCellDG.mass_matrix),
+ * in ONE pass of the apply kernel: u and b are read once and unew is written once (24 B per dof; apply +
+ * stefan_ipdg_euler_update move 48).  b may be NULL.  u != unew.  u_lo / u_hi as in stefan_ipdg_apply;
+ * sync != NULL selects the peer-halo form of stefan_ipdg_apply_peer (u_lo / u_hi then point into the
+ * neighbours' u in peer memory; the kernel publishes sync->my_ready = epoch when it starts -- which also tells
+ * the neighbours that this rank is done reading THEIR previous vector -- and its edge tiles wait for the
+ * neighbours' flag of the same epoch before they read the halo columns and before they overwrite the edge
+ * columns of unew, so two buffers alternating between u and unew need no other ordering). */
+int stefan_ipdg_step(stefan_ipdg* h, const double* u, double* unew, const double* b, double dt, const double* u_lo,
+                     const double* u_hi, const stefan_peer_sync* sync, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

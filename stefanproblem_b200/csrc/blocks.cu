@@ -352,15 +352,15 @@ int stefan_blocks_assemble(stefan_blocks* hv, const stefan_blocks_data* in, void
     }
     case 2: {
       constexpr int smem = kAsmWarps * AsmSmem<2>::WARP_DOUBLES * 8;
-      static bool set2 = false;
-      if (!set2) { STEFAN_CUDA(cudaFuncSetAttribute(blocks_assemble_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set2 = true; }
+      static PerDeviceFlag set2;
+      if (!set2.here()) { STEFAN_CUDA(cudaFuncSetAttribute(blocks_assemble_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set2.here() = true; }
       blocks_assemble_kernel<2><<<blocks, kAsmWarps * 32, smem, st>>>(h->d, *in, h->blocks);
       break;
     }
     case 3: {
       constexpr int smem = kAsmWarps * AsmSmem<3>::WARP_DOUBLES * 8;
-      static bool set3 = false;
-      if (!set3) { STEFAN_CUDA(cudaFuncSetAttribute(blocks_assemble_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set3 = true; }
+      static PerDeviceFlag set3;
+      if (!set3.here()) { STEFAN_CUDA(cudaFuncSetAttribute(blocks_assemble_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set3.here() = true; }
       blocks_assemble_kernel<3><<<blocks, kAsmWarps * 32, smem, st>>>(h->d, *in, h->blocks);
       break;
     }

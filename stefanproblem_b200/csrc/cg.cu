@@ -263,32 +263,19 @@ int stefan_ipdg_cg_solve(stefan_ipdg* hv, const double* b, double* x, const stef
   // cannot do.  The call is synchronous, so the caller's stream sees the result on return.
   cudaStream_t caller = static_cast<cudaStream_t>(stream), st = nullptr;
   cudaEvent_t ordered = nullptr;
-  STEFAN_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-  STEFAN_CUDA(cudaEventCreateWithFlags(&ordered, cudaEventDisableTiming));
-  STEFAN_CUDA(cudaEventRecord(ordered, caller));
-  STEFAN_CUDA(cudaStreamWaitEvent(st, ordered, 0));
-  stream = st;
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t gexec = nullptr;
-  const int64_t n = h->ndofs;
-  const int64_t ncells = (int64_t)h->nx * h->ny;
-  const int nblk = (int)std::min<int64_t>((ncells + kRedThreads - 1) / kRedThreads, (int64_t)sm_count() * 8);
-  const int vblk = (int)std::min<int64_t>((n + kRedThreads - 1) / kRedThreads, (int64_t)sm_count() * 8);
   double *work = nullptr, *Binv = nullptr;
-  const int64_t ns = (n + 3) / 4 * 4;  // 32-byte aligned vectors (the apply kernel needs 16)
-  const size_t wbytes = (size_t)(4 * ns + 2 * (size_t)std::max(nblk, vblk) + 8) * sizeof(double);
-  STEFAN_CUDA(cudaMalloc(&work, wbytes));
-  double *r = work, *z = r + ns, *p = z + ns, *Ap = p + ns, *part = Ap + ns, *part2 = part + std::max(nblk, vblk),
-         *scal = part2 + std::max(nblk, vblk);
   int rc = ST_OK;
+  // defined before the first fallible call: every early return releases what exists so far
   auto cleanup = [&]() {
-    cudaStreamSynchronize(st);
+    if (st) cudaStreamSynchronize(st);
     if (gexec) cudaGraphExecDestroy(gexec);
     if (graph) cudaGraphDestroy(graph);
-    cudaFree(work);
+    if (work) cudaFree(work);
     if (Binv) cudaFree(Binv);
-    cudaEventDestroy(ordered);
-    cudaStreamDestroy(st);
+    if (ordered) cudaEventDestroy(ordered);
+    if (st) cudaStreamDestroy(st);
   };
 #define CG_CUDA(call)                                                                        \
   do {                                                                                       \
@@ -298,6 +285,20 @@ int stefan_ipdg_cg_solve(stefan_ipdg* hv, const double* b, double* x, const stef
       return fail(ST_CUDA_ERROR, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
     }                                                                                        \
   } while (0)
+  CG_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  CG_CUDA(cudaEventCreateWithFlags(&ordered, cudaEventDisableTiming));
+  CG_CUDA(cudaEventRecord(ordered, caller));
+  CG_CUDA(cudaStreamWaitEvent(st, ordered, 0));
+  stream = st;
+  const int64_t n = h->ndofs;
+  const int64_t ncells = (int64_t)h->nx * h->ny;
+  const int nblk = (int)std::min<int64_t>((ncells + kRedThreads - 1) / kRedThreads, (int64_t)sm_count() * 8);
+  const int vblk = (int)std::min<int64_t>((n + kRedThreads - 1) / kRedThreads, (int64_t)sm_count() * 8);
+  const int64_t ns = (n + 3) / 4 * 4;  // 32-byte aligned vectors (the apply kernel needs 16)
+  const size_t wbytes = (size_t)(4 * ns + 2 * (size_t)std::max(nblk, vblk) + 8) * sizeof(double);
+  CG_CUDA(cudaMalloc(&work, wbytes));
+  double *r = work, *z = r + ns, *p = z + ns, *Ap = p + ns, *part = Ap + ns, *part2 = part + std::max(nblk, vblk),
+         *scal = part2 + std::max(nblk, vblk);
   if (prm->preconditioner == 1) {
     std::vector<double> inv;
     switch (h->order) {

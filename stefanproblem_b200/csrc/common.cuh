@@ -40,15 +40,27 @@ inline int fail(int status, const char* fmt, ...) {
     if (!(cond)) return ::stefan::fail(::stefan::ST_BAD_ARGUMENT, __VA_ARGS__);        \
   } while (0)
 
+// Function attributes (the > 48 KB shared-memory opt-in) and SM counts are per DEVICE, not per
+// process: everything cached about them is keyed by the current device.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+struct PerDeviceFlag {
+  bool set[kMaxDevices] = {};
+  bool& here() { return set[current_device()]; }
+};
+
 inline int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static int n[kMaxDevices] = {};
+  const int dev = current_device();
+  if (n[dev] == 0) {
+    cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (n[dev] <= 0) n[dev] = 148;
   }
-  return n;
+  return n[dev];
 }
 
 #if defined(__CUDACC__)

@@ -30,8 +30,11 @@ enum FdRow : uint8_t {
   FD_BACKWARD = 2,
   FD_FORWARD = 3,
   FD_IDENTITY = 4,
-  FD_CONTINUITY = 5,  // coefficients in the side table
   FD_PHASE2 = 8,      // bit: node belongs to phase 2 (selects kappa2 in the step)
+  // bit: interface-continuity rows were added to this node (coefficients in the side table).  They
+  // ADD to whatever row the node already has, as the reference's triplets do in sparse()
+  // (assemble_interface_continuity!, finite-difference.jl:111-116 only appends).
+  FD_CONTINUITY = 16,
 };
 
 struct FdContinuity {
@@ -91,16 +94,15 @@ fd_apply_kernel(const double* __restrict__ u, const double* __restrict__ u_lo,
       case FD_BACKWARD: r = (-c[-3] + 4.0 * c[-2] - 5.0 * c[-1] + 2.0 * c[0]) * inv_h2; break;
       case FD_FORWARD: r = (2.0 * c[0] - 5.0 * c[1] + 4.0 * c[2] - c[3]) * inv_h2; break;
       case FD_IDENTITY: r = c[0]; break;
-      case FD_CONTINUITY: {
-        for (int q = 0; q < ncont; ++q)
-          if (cont[q].node == g) {
-            const double rr = cont[q].r, ss = cont[q].s;
-            r += rr * c[-2] - 4.0 * rr * c[-1] + (1.0 + 3.0 * rr) * c[0] - (1.0 + 3.0 * ss) * c[1] +
-                 4.0 * ss * c[2] - ss * c[3];
-          }
-        break;
-      }
       default: break;
+    }
+    if (kd & FD_CONTINUITY) {
+      for (int q = 0; q < ncont; ++q)
+        if (cont[q].node == g) {
+          const double rr = cont[q].r, ss = cont[q].s;
+          r += rr * c[-2] - 4.0 * rr * c[-1] + (1.0 + 3.0 * rr) * c[0] - (1.0 + 3.0 * ss) * c[1] +
+               4.0 * ss * c[2] - ss * c[3];
+        }
     }
     if (MODE == 0) {
       y[g] = r;
@@ -175,7 +177,7 @@ fd_apply_vec(const double* __restrict__ u, const double* __restrict__ u_lo, cons
       else if (row == FD_BACKWARD) t = (-c[-3] + 4.0 * c[-2] - 5.0 * c[-1] + 2.0 * c[0]) * inv_h2;
       else if (row == FD_FORWARD) t = (2.0 * c[0] - 5.0 * c[1] + 4.0 * c[2] - c[3]) * inv_h2;
       else if (row == FD_IDENTITY) t = c[0];
-      else if (row == FD_CONTINUITY) {
+      if (kd & FD_CONTINUITY) {
         for (int q = 0; q < ncont; ++q)
           if (cont[q].node == g0 + k) {
             const double rr = cont[q].r, ss = cont[q].s;
@@ -227,16 +229,15 @@ __global__ void fd_coo_kernel(const uint8_t* __restrict__ kind, const int64_t* _
       put(g, 2.0 * inv_h2); put(g + 1, -5.0 * inv_h2); put(g + 2, 4.0 * inv_h2); put(g + 3, -1.0 * inv_h2);
       break;
     case FD_IDENTITY: put(g, 1.0); break;
-    case FD_CONTINUITY:
-      for (int q = 0; q < ncont; ++q)
-        if (cont[q].node == g) {
-          const double r = cont[q].r, s = cont[q].s;
-          put(g - 2, r); put(g - 1, -4.0 * r); put(g, 1.0 + 3.0 * r);
-          put(g + 1, -(1.0 + 3.0 * s)); put(g + 2, 4.0 * s); put(g + 3, -s);
-        }
-      break;
     default: break;
   }
+  if (kind[g] & FD_CONTINUITY)
+    for (int q = 0; q < ncont; ++q)
+      if (cont[q].node == g) {
+        const double r = cont[q].r, s = cont[q].s;
+        put(g - 2, r); put(g - 1, -4.0 * r); put(g, 1.0 + 3.0 * r);
+        put(g + 1, -(1.0 + 3.0 * s)); put(g + 2, 4.0 * s); put(g + 3, -s);
+      }
 }
 
 static int row_nnz(uint8_t kind) {
@@ -356,12 +357,8 @@ int stefan_fd_add_interface_continuity(stefan_fd* hv, double r, double s, int64_
   STEFAN_REQUIRE(h, "stefan_fd_add_interface_continuity: null handle");
   STEFAN_REQUIRE(nodeid - 2 >= 0 && nodeid + 3 < h->n,
                  "stefan_fd_add_interface_continuity: row needs nodes nodeid-2 .. nodeid+3");
-  STEFAN_REQUIRE((h->kind_host[(size_t)nodeid] & 7) == FD_EMPTY ||
-                     (h->kind_host[(size_t)nodeid] & 7) == FD_CONTINUITY,
-                 "stefan_fd_add_interface_continuity: node %lld already has a Laplace / identity row",
-                 (long long)nodeid);
   h->cont.push_back(FdContinuity{nodeid, r, s});
-  h->kind_host[(size_t)nodeid] = (h->kind_host[(size_t)nodeid] & FD_PHASE2) | FD_CONTINUITY;
+  h->kind_host[(size_t)nodeid] |= FD_CONTINUITY;
   h->cont_dirty = true;
   return ST_OK;
 }

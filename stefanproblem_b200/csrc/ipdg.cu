@@ -54,9 +54,23 @@ struct ApplyArgs {
   const unsigned long long* sync_hi_ready;
   unsigned long long sync_epoch, sync_timeout_ns;
   int* sync_status;                          // set to 1 if a wait timed out
-  unsigned* sync_counter;                    // CTAs finished (local)
-  unsigned long long* dbg_times;             // development only: per-CTA {start, end} globaltimer, or null
+  unsigned long long* dbg_times;             // development only: per-CTA {start, prologue, loop, end} globaltimer, or null
+  // dynamic tail queue: [0] next fix-list index, [1] CTAs finished; both reset by the last CTA
+  unsigned* tail_ctr;
+  // fused explicit step (MODE 1 of the kernels): y = x + step_scale * Minv (b - A x), Minv the
+  // Kronecker square of the inverse 1-D reference mass matrix
+  const double* b;
+  double step_scale;
+  double minv[kMaxN1][kMaxN1];
 };
+
+// Programmatic dependent launch: the kernels may start while the previous kernel of the stream
+// drains (their CTAs take SM slots as they free up and run their prologue); griddep_wait()
+// returns once the previous kernel has completed and its memory is visible, and must precede
+// every access to memory a previous kernel may have written.  Both are no-ops in a launch
+// without the attribute.
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // Wait (acquire, system scope) until the neighbour has published `epoch`; bounded.
 __device__ __forceinline__ void peer_flag_wait(const unsigned long long* flag, unsigned long long epoch,
@@ -118,15 +132,51 @@ ipdg_apply_simple(const __grid_constant__ IpTab<P> tab, const ApplyArgs a) {
   }
 }
 
-// Cells the streaming loops do not produce (they skip the store): boundary cells,
-// cells next to the other phase, and every cell of a (strip, column) that mixes
-// phases or has such a column next to it.  They are disjoint from what the loops
-// write, so each CTA simply works through its share of the list after its strips:
-// one thread per cell, general tables, neighbours straight from global memory.
+// The step epilogue of one cell: out (= A x rows) becomes x + scale * Minv (b - out).
 template <int P>
+__device__ __forceinline__ void step_epilogue(const ApplyArgs& a, const double* __restrict__ X,
+                                              const double* __restrict__ B, double* __restrict__ out) {
+  constexpr int N1 = P + 1, NF = N1 * N1;
+  double t[NF];
+#pragma unroll
+  for (int ix = 0; ix < N1; ++ix)
+#pragma unroll
+    for (int iy = 0; iy < N1; ++iy) {
+      double v = 0.0;
+#pragma unroll
+      for (int c = 0; c < N1; ++c) v += a.minv[iy][c] * (B[ix * N1 + c] - out[ix * N1 + c]);
+      t[ix * N1 + iy] = v;
+    }
+#pragma unroll
+  for (int ix = 0; ix < N1; ++ix)
+#pragma unroll
+    for (int iy = 0; iy < N1; ++iy) {
+      double v = 0.0;
+#pragma unroll
+      for (int c = 0; c < N1; ++c) v += a.minv[ix][c] * t[c * N1 + iy];
+      out[ix * N1 + iy] = X[ix * N1 + iy] + a.step_scale * v;
+    }
+}
+
+// Cells the marching loops do not produce (they skip the store): boundary cells and cells
+// next to the other phase.  They are disjoint from what the loops write.  Round 2: the list is
+// a QUEUE -- every warp that is done with its strip takes 32 cells at a time through an atomic
+// counter until the list is empty, so the warps whose tiles finish first absorb the tail
+// (round 1 gave CTA b the cells b*blockDim .. : the first CTAs of the grid, which also own
+// the boundary column, paid for all of it -- up to 34 us at LDG order 3, 457^2 cells).
+// One thread per cell, general tables, neighbours straight from global memory.
+template <int P, int MODE>
 __device__ __forceinline__ void fixup_tail(const IpTab<P>& tab, const ApplyArgs& a) {
   constexpr int NF = (P + 1) * (P + 1);
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < a.nfix; t += gridDim.x * blockDim.x) {
+  if (a.nfix <= 0) return;
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(a.tail_ctr, 32u);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= (unsigned)a.nfix) break;
+    const int t = (int)base + lane;
+    if (t >= a.nfix) continue;
     const int64_t cell = a.fix[t];
     const int i = (int)(cell / a.ny), j = (int)(cell % a.ny);
     const int s = phase_at(a.phase, a.ny, i, j);
@@ -150,9 +200,30 @@ __device__ __forceinline__ void fixup_tail(const IpTab<P>& tab, const ApplyArgs&
     }
     ip_cell_rows<P>(tab, s == 1 ? 0 : 1, ip_face_type(s, sL), ip_face_type(s, sR),
                     ip_face_type(s, sD), ip_face_type(s, sU), X, XL, XR, XD, XU, out);
+    if constexpr (MODE == 1) {
+      double B[NF];
+#pragma unroll
+      for (int k = 0; k < NF; ++k) B[k] = a.b ? a.b[cell * NF + k] : 0.0;
+      step_epilogue<P>(a, X, B, out);
+    }
     double* yc = a.y + cell * NF;
 #pragma unroll
     for (int k = 0; k < NF; ++k) yc[k] = out[k];
+  }
+}
+
+// End of a march kernel: the last CTA to get here resets the tail queue for the next launch
+// and, with peer halos, tells the neighbours that their columns are free.
+__device__ __forceinline__ void march_finish(const ApplyArgs& a) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(a.tail_ctr + 1, 1u) == gridDim.x - 1) {
+      a.tail_ctr[0] = 0;
+      a.tail_ctr[1] = 0;
+      __threadfence();
+      if (a.sync_epoch != 0) peer_flag_publish(a.sync_my_done, a.sync_epoch);
+    }
   }
 }
 
@@ -199,45 +270,72 @@ static int march_warps(int order) {
   return order == 1 ? MarchCfg<1>::WARPS : order == 2 ? MarchCfg<2>::WARPS : MarchCfg<3>::WARPS;
 }
 
-template <int P>
-static int launch_march(IpdgHandle* h, const IpTab<P>& tab, const ApplyArgs& args, cudaStream_t st) {
+// Launch with the programmatic-stream-serialization attribute (see griddep_wait above);
+// STEFAN_PDL=0 turns it off (A/B timing).
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  static const bool pdl = [] { const char* e = getenv("STEFAN_PDL"); return e == nullptr || atoi(e) != 0; }();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+
+template <int P, int MODE>
+static int launch_march(IpdgHandle* h, const IpTab<P>& tab, const ApplyArgs& args0, cudaStream_t st) {
   using C = MarchCfg<P>;
-  const SegCache& sc = h->plan.segments(args.cbeg, args.cend, sm_count() * C::MINB);
+  const SegCache& sc = h->plan.segments(args0.cbeg, args0.cend, sm_count() * C::MINB);
   const SegTab& segs = sc.tab;
   const int grid = sc.n;
   if (grid <= 0) return fail(ST_UNSUPPORTED, "stefan_ipdg_apply: more than %d strip groups (ny too large)", kMaxMarchCtas);
   constexpr int smem = MarchSmem<P>::TOTAL;
-  static bool attr_set = false;
-  if (!attr_set) {
-    STEFAN_CUDA(cudaFuncSetAttribute(ipdg_apply_march<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
+  static PerDeviceFlag attr_set;
+  if (!attr_set.here()) {
+    STEFAN_CUDA(cudaFuncSetAttribute(ipdg_apply_march<P, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set.here() = true;
   }
+  ApplyArgs args = args0;
+  if (h->tail_ctr_dev == nullptr) {
+    STEFAN_CUDA(cudaMalloc(&h->tail_ctr_dev, kTailRing * 2 * sizeof(unsigned)));
+    STEFAN_CUDA(cudaMemset(h->tail_ctr_dev, 0, kTailRing * 2 * sizeof(unsigned)));
+  }
+  args.tail_ctr = h->tail_ctr_dev + 2 * (h->launch_seq++ % kTailRing);
   CUtensorMap tm;
   std::memset(&tm, 0, sizeof(tm));
   if (C::TENSOR) {
     int rc = make_cell_tensor_map(args.x, (int64_t)h->nx * h->ny, &tm);
     if (rc) return rc;
   }
-  // development only: STEFAN_DEV_CTA_TIMES=<file> dumps per-CTA {group, c0, c1, start ns, end ns}
+  // development only: STEFAN_DEV_CTA_TIMES=<file> dumps per-CTA {group, c0, c1, 4 x globaltimer ns}
   static const char* dbg_path = getenv("STEFAN_DEV_CTA_TIMES");
   if (dbg_path != nullptr) {
-    ApplyArgs a2 = args;
     unsigned long long* d = nullptr;
-    STEFAN_CUDA(cudaMalloc(&d, (size_t)grid * 2 * sizeof(unsigned long long)));
-    a2.dbg_times = d;
-    ipdg_apply_march<P><<<grid, C::WARPS * 32, smem, st>>>(tab, a2, h->plan.runs_dev, h->plan.run_ofs_dev, tm, segs);
+    STEFAN_CUDA(cudaMalloc(&d, (size_t)grid * 4 * sizeof(unsigned long long)));
+    STEFAN_CUDA(cudaMemset(d, 0, (size_t)grid * 4 * sizeof(unsigned long long)));
+    args.dbg_times = d;
+    ipdg_apply_march<P, MODE><<<grid, C::WARPS * 32, smem, st>>>(tab, args, h->plan.runs_dev, h->plan.run_ofs_dev, tm, segs);
     STEFAN_CUDA(cudaStreamSynchronize(st));
-    std::vector<unsigned long long> t((size_t)grid * 2);
+    std::vector<unsigned long long> t((size_t)grid * 4);
     STEFAN_CUDA(cudaMemcpy(t.data(), d, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     cudaFree(d);
     if (FILE* f = fopen(dbg_path, "w")) {
       for (int b = 0; b < grid; ++b)
-        fprintf(f, "%d %d %d %llu %llu\n", segs.e[b].x, segs.e[b].y, segs.e[b].z, t[2 * b], t[2 * b + 1]);
+        fprintf(f, "%d %d %d %llu %llu %llu %llu\n", segs.e[b].x, segs.e[b].y, segs.e[b].z, t[4 * b], t[4 * b + 1],
+                t[4 * b + 2], t[4 * b + 3]);
       fclose(f);
     }
     return ST_OK;
   }
-  ipdg_apply_march<P><<<grid, C::WARPS * 32, smem, st>>>(tab, args, h->plan.runs_dev, h->plan.run_ofs_dev, tm, segs);
+  STEFAN_CUDA(launch_pdl(ipdg_apply_march<P, MODE>, grid, C::WARPS * 32, smem, st, tab, args,
+                         (const int4*)h->plan.runs_dev, (const int*)h->plan.run_ofs_dev, tm, segs));
   return ST_OK;
 }
 
@@ -247,7 +345,9 @@ static int launch_apply(IpdgHandle* h, const ApplyArgs& args0, int algo, cudaStr
   ApplyArgs args = args0;
   const int ncol = args.cend - args.cbeg;
   if (ncol <= 0) return ST_OK;
+  const bool step = args.step_scale != 0.0;
   if (algo == 1) {
+    if (step) return fail(ST_UNSUPPORTED, "stefan_ipdg_step: the plain kernel has no fused step");
     const int64_t ncells = (int64_t)ncol * h->ny;
     int blocks = (int)std::min<int64_t>((ncells + 127) / 128, (int64_t)sm_count() * 32);
     ipdg_apply_simple<P><<<blocks, 128, 0, st>>>(tab, args);
@@ -260,7 +360,7 @@ static int launch_apply(IpdgHandle* h, const ApplyArgs& args0, int algo, cudaStr
   static const bool skip_tail = getenv("STEFAN_DEV_SKIP_TAIL") != nullptr;  // timing experiments only (wrong results)
   if (skip_tail) args.nfix = 0;
   // CTA = (group of adjacent strips, x segment); one wave of MINB CTAs per SM
-  int rc = launch_march<P>(h, tab, args, st);
+  int rc = step ? launch_march<P, 1>(h, tab, args, st) : launch_march<P, 0>(h, tab, args, st);
   if (rc) return rc;
   STEFAN_CUDA(cudaGetLastError());
   return ST_OK;
@@ -302,12 +402,14 @@ int stefan_ipdg_create(const stefan_ipdg_params* p, const int8_t* phase, const i
   h->has_hi = phase_hi != nullptr;
   h->phase_dev = nullptr;
   h->xh_dev = h->yh_dev = nullptr;
-  h->sync_counter_dev = nullptr;
+  h->tail_ctr_dev = nullptr;
+  h->launch_seq = 0;
   h->host_ready = false;
   h->tab_host = nullptr;
   const int NF = (p->order + 1) * (p->order + 1);
   h->ndofs = (int64_t)p->nx * p->ny * NF;
   build_ref1d(p->order, p->numqp, &h->ref);
+  invert_mass_1d(h->ref, p->order + 1, h->minv1d);
   int rc = 0;
   const double jx = 0.5 * p->hx, jy = 0.5 * p->hy;
   switch (p->order) {
@@ -347,7 +449,7 @@ int stefan_ipdg_destroy(stefan_ipdg* hv) {
   if (!h) return ST_OK;
   if (h->phase_dev) cudaFree(h->phase_dev);
   h->plan.destroy();
-  if (h->sync_counter_dev) cudaFree(h->sync_counter_dev);
+  if (h->tail_ctr_dev) cudaFree(h->tail_ctr_dev);
   if (h->xh_dev) cudaFree(h->xh_dev);
   if (h->yh_dev) cudaFree(h->yh_dev);
   if (h->host_ready) {
@@ -406,10 +508,6 @@ int stefan_ipdg_apply_peer(stefan_ipdg* hv, const double* x, double* y, const do
   STEFAN_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
                  (reinterpret_cast<uintptr_t>(x_lo) & hmask) == 0 && (reinterpret_cast<uintptr_t>(x_hi) & hmask) == 0,
                  "stefan_ipdg_apply_peer: x, y must be 16-byte aligned (halo columns: 16, order 2: 8)");
-  if (h->sync_counter_dev == nullptr) {
-    STEFAN_CUDA(cudaMalloc(&h->sync_counter_dev, sizeof(unsigned)));
-    STEFAN_CUDA(cudaMemset(h->sync_counter_dev, 0, sizeof(unsigned)));
-  }
   ApplyArgs a{x, x_lo, x_hi, y, h->phase_dev, h->nx, h->ny, 0, h->nx, nullptr, 0};
   a.sync_my_ready = reinterpret_cast<unsigned long long*>(sync->my_ready);
   a.sync_my_done = reinterpret_cast<unsigned long long*>(sync->my_done);
@@ -418,7 +516,44 @@ int stefan_ipdg_apply_peer(stefan_ipdg* hv, const double* x, double* y, const do
   a.sync_epoch = sync->epoch;
   a.sync_timeout_ns = (unsigned long long)sync->timeout_ms * 1000000ull;
   a.sync_status = sync->status;
-  a.sync_counter = h->sync_counter_dev;
+  return dispatch_apply(h, a, 0, static_cast<cudaStream_t>(stream));
+}
+
+// The fused explicit step: unew = u + dt Minv (b - A u) in ONE pass of the march
+// kernel -- u and b read once, unew written once (24 B per dof; apply + stefan_ipdg_euler_update
+// move 48).  M = the block-diagonal DG mass matrix.  b may be NULL (no right-hand side).
+// sync != NULL: the peer-halo form (see stefan_ipdg_apply_peer); u_lo / u_hi are then the
+// neighbours' edge columns of THEIR u in peer memory.
+int stefan_ipdg_step(stefan_ipdg* hv, const double* u, double* unew, const double* b, double dt, const double* u_lo,
+                     const double* u_hi, const stefan_peer_sync* sync, void* stream) {
+  IpdgHandle* h = reinterpret_cast<IpdgHandle*>(hv);
+  STEFAN_REQUIRE(h && u && unew && u != unew, "stefan_ipdg_step: bad argument (in-place steps are not supported)");
+  STEFAN_REQUIRE(dt != 0.0, "stefan_ipdg_step: dt must not be 0");
+  STEFAN_REQUIRE(h->has_lo == (u_lo != nullptr) && h->has_hi == (u_hi != nullptr),
+                 "stefan_ipdg_step: halo columns must be given exactly where the handle has halo phases");
+  const uintptr_t hmask = h->order == 2 ? 7 : 15;
+  const uintptr_t bmask = h->order == 2 ? 7 : 31;  // b cells are fetched with 256-bit loads (orders 1, 3)
+  STEFAN_REQUIRE((reinterpret_cast<uintptr_t>(u) & 15) == 0 && (reinterpret_cast<uintptr_t>(unew) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(b) & bmask) == 0 &&
+                 (reinterpret_cast<uintptr_t>(u_lo) & hmask) == 0 && (reinterpret_cast<uintptr_t>(u_hi) & hmask) == 0,
+                 "stefan_ipdg_step: u, unew must be 16-byte aligned, b 32-byte (order 2: 8), halo columns 16 (order 2: 8)");
+  ApplyArgs a{u, u_lo, u_hi, unew, h->phase_dev, h->nx, h->ny, 0, h->nx, nullptr, 0};
+  a.b = b;
+  a.step_scale = dt / (0.25 * h->hx * h->hy);
+  for (int i = 0; i < kMaxN1; ++i)
+    for (int j = 0; j < kMaxN1; ++j) a.minv[i][j] = h->minv1d[i][j];
+  if (sync != nullptr) {
+    STEFAN_REQUIRE(sync->epoch > 0 && sync->my_ready && sync->my_done && sync->timeout_ms > 0 &&
+                   (!u_lo || sync->lo_ready) && (!u_hi || sync->hi_ready),
+                   "stefan_ipdg_step: incomplete sync block");
+    a.sync_my_ready = reinterpret_cast<unsigned long long*>(sync->my_ready);
+    a.sync_my_done = reinterpret_cast<unsigned long long*>(sync->my_done);
+    a.sync_lo_ready = reinterpret_cast<const unsigned long long*>(sync->lo_ready);
+    a.sync_hi_ready = reinterpret_cast<const unsigned long long*>(sync->hi_ready);
+    a.sync_epoch = sync->epoch;
+    a.sync_timeout_ns = (unsigned long long)sync->timeout_ms * 1000000ull;
+    a.sync_status = sync->status;
+  }
   return dispatch_apply(h, a, 0, static_cast<cudaStream_t>(stream));
 }
 

@@ -418,28 +418,8 @@ int stefan_ipdg_euler_update(stefan_ipdg* hv, double* u, const double* y, const 
   std::memset(&t, 0, sizeof(t));
   const int n = h->order + 1;
   t.n1 = n;
-  // inverse of the (SPD, <= 4x4) reference mass matrix by Gauss-Jordan
-  double a[kMaxN1][2 * kMaxN1];
   for (int i = 0; i < n; ++i)
-    for (int j = 0; j < n; ++j) {
-      a[i][j] = h->ref.M[i][j];
-      a[i][n + j] = i == j ? 1.0 : 0.0;
-    }
-  for (int c = 0; c < n; ++c) {
-    int piv = c;
-    for (int r = c + 1; r < n; ++r)
-      if (std::fabs(a[r][c]) > std::fabs(a[piv][c])) piv = r;
-    for (int j = 0; j < 2 * n; ++j) std::swap(a[c][j], a[piv][j]);
-    const double d = a[c][c];
-    for (int j = 0; j < 2 * n; ++j) a[c][j] /= d;
-    for (int r = 0; r < n; ++r)
-      if (r != c) {
-        const double f = a[r][c];
-        for (int j = 0; j < 2 * n; ++j) a[r][j] -= f * a[c][j];
-      }
-  }
-  for (int i = 0; i < n; ++i)
-    for (int j = 0; j < n; ++j) t.minv[i][j] = a[i][n + j];
+    for (int j = 0; j < n; ++j) t.minv[i][j] = h->minv1d[i][j];
   t.scale = dt / (0.25 * h->hx * h->hy);
   const int64_t ncells = (int64_t)h->nx * h->ny;
   const int blocks = (int)std::min<int64_t>((ncells + 127) / 128, (int64_t)sm_count() * 32);

@@ -192,7 +192,9 @@ struct MarchMath {
   }
 };
 
-template <int P>
+// MODE 0: y = A x.  MODE 1: the fused explicit step y = x + dt Minv (b - A x) (SURVEY 2.4 K9:
+// 24 B per dof -- x and b read once, y written once -- instead of the 48 B of apply + update).
+template <int P, int MODE>
 __global__ void __launch_bounds__(MarchCfg<P>::WARPS * 32, MarchCfg<P>::MINB)
 ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const int4* __restrict__ runs,
                  const int* __restrict__ run_ofs, const __grid_constant__ CUtensorMap tmx,
@@ -212,6 +214,7 @@ ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const 
   const unsigned ring = smem0 + (unsigned)warp * MarchSmem<P>::WARP;
   [[maybe_unused]] const unsigned obuf = ring + NST * C::STAGE;  // P = 2: two output buffers
   const unsigned bars = smem0 + (unsigned)C::WARPS * MarchSmem<P>::WARP + (unsigned)warp * NST * 8;
+  griddep_launch();  // the next kernel of the stream may start its prologue while this one drains
   if (lane == 0) {
 #pragma unroll
     for (int s = 0; s < NST; ++s)
@@ -219,13 +222,6 @@ ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-  if (a.dbg_times != nullptr && threadIdx.x == 0) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    a.dbg_times[2 * blockIdx.x] = t;
-  }
-  // peer halos: everything the stream wrote before this kernel is final -> publish my epoch
-  if (a.sync_epoch != 0 && blockIdx.x == 0 && threadIdx.x == 0) peer_flag_publish(a.sync_my_ready, a.sync_epoch);
 
   const int nstrips = (a.ny + kStripCells - 1) / kStripCells;
   const int4 myseg = segs.e[blockIdx.x];
@@ -358,6 +354,18 @@ ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const 
     int4 nxt = ld_run(rp + 1);
     bool mine1 = (cur.z >> lane) & 1;  // this lane's cell has phase code 2
 
+    // everything above read only what stefan_ipdg_create wrote; from here on the kernel touches
+    // the vectors, the flags and the queue counters: the previous kernel must be complete
+    griddep_wait();
+    if (a.dbg_times != nullptr && threadIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      a.dbg_times[4 * blockIdx.x] = t;
+    }
+    // peer halos: everything the stream wrote before this kernel is final -> publish my epoch
+    // (warp 0 of CTA 0 always owns a strip: tiles are never empty)
+    if (a.sync_epoch != 0 && blockIdx.x == 0 && threadIdx.x == 0) peer_flag_publish(a.sync_my_ready, a.sync_epoch);
+
     // prologue: columns c0-1 .. c0+NST-2 into slots 0 .. NST-1
 #pragma unroll
     for (int k = 0; k < NST; ++k) issue_general(c0 - 1 + k, ring + k * C::STAGE, bars + 8 * k);
@@ -377,6 +385,12 @@ ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const 
       MarchMath<P, 1>::x_moment_lo(tab, XLfull, d1);
 #pragma unroll
       for (int t = 0; t < N1; ++t) dL[t] = mine1 ? d1[t] : dL[t];
+    }
+
+    if (a.dbg_times != nullptr && threadIdx.x == 0) {  // development: end of the prologue
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      a.dbg_times[4 * blockIdx.x + 1] = t;
     }
 
     // ---- steady-state bookkeeping, all incremental ----
@@ -399,6 +413,8 @@ ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const 
     const unsigned dst_off = P == 2 ? rel0 * 80u : (C::TENSOR ? 0u : rel0 * (unsigned)CB);
     const size_t ycol = (size_t)a.ny * NF;  // doubles per column
     double* yp = a.y + (size_t)c0 * ycol + (size_t)j * NF;
+    [[maybe_unused]] const double* bp = a.b + (size_t)c0 * ycol + (size_t)j * NF;
+    [[maybe_unused]] const bool bp_valid = a.b != nullptr && lane >= 1 && lane <= kStripCells && j < a.ny;
     [[maybe_unused]] char* gstrip = reinterpret_cast<char*>(a.y) + ((size_t)c0 * a.ny + j0) * CB;
     if constexpr (P == 2) shy = (unsigned)(reinterpret_cast<uintptr_t>(gstrip) & 15u);
     [[maybe_unused]] unsigned ob = obuf;
@@ -406,6 +422,23 @@ ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const 
     // One column: Xc = column c (in registers), Xn receives column c+1.  The callers
     // alternate the two arrays, so no register copies are needed between columns.
     auto column = [&](int c, double* __restrict__ Xc, double* __restrict__ Xn) {
+      // fused step: this cell's b, requested before the wait for the next column (in flight
+      // behind it); only the lanes whose cells the loop may store
+      [[maybe_unused]] double Bc[NF];
+      if constexpr (MODE == 1) {
+        if (bp_valid) {
+          if constexpr (P == 2) {
+#pragma unroll
+            for (int q = 0; q < NF; ++q) Bc[q] = __ldg(bp + q);
+          } else {
+#pragma unroll
+            for (int q = 0; q < NF; q += 4) ld_global_nc_v4(bp + q, Bc + q);
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < NF; ++q) Bc[q] = 0.0;
+        }
+      }
       mbar_wait_s(bar_r, par_r);
       // where this lane's cell of column c+1 sits: plain columns differ from halo columns
       // only in the swizzle mask (P = 3) / the 8-byte shift (P = 2)
@@ -502,6 +535,7 @@ ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const 
           dU[t] = __shfl_down_sync(0xffffffffu, sD[t], 1);
         }
         M::rows(tab, Xc, tL, dL, tR, dR, tD, dD, tU, dU, out);
+        if constexpr (MODE == 1) step_epilogue<P>(a, Xc, Bc, out);
 
         if constexpr (C::OUTB == 0) {
           if (st) {
@@ -546,6 +580,7 @@ ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const 
       if (ph & 1) body(std::integral_constant<int, 0>{});
       if (ph & 2) body(std::integral_constant<int, 1>{});
       yp += ycol;
+      if constexpr (MODE == 1) bp += ycol;
       if constexpr (P == 2) {
         gstrip += colbytes;
         shy ^= tog;
@@ -602,21 +637,20 @@ ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const 
     if (threadIdx.x == 0) {
       unsigned long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-      a.dbg_times[2 * blockIdx.x + 1] = t;
+      a.dbg_times[4 * blockIdx.x + 2] = t;
     }
   }
-  fixup_tail<P>(tab, a);
-  // peer halos: the last CTA to finish tells the neighbours that their columns are free
-  if (a.sync_epoch != 0) {
+  griddep_wait();  // (warps without a strip have not waited yet)
+  fixup_tail<P, MODE>(tab, a);
+  if (a.dbg_times != nullptr) {  // development: end of the tail
     __syncthreads();
     if (threadIdx.x == 0) {
-      __threadfence();
-      if (atomicAdd(a.sync_counter, 1u) == gridDim.x - 1) {
-        *a.sync_counter = 0;
-        peer_flag_publish(a.sync_my_done, a.sync_epoch);
-      }
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      a.dbg_times[4 * blockIdx.x + 3] = t;
     }
   }
+  march_finish(a);
 }
 
 }  // namespace stefan

@@ -23,6 +23,8 @@
 
 namespace stefan {
 
+constexpr int kLdgTailRing = 8;
+
 struct LdgHandle {
   int nx, ny, order, numqp;
   double phys_hx, phys_hy;
@@ -31,6 +33,8 @@ struct LdgHandle {
   int8_t* phase_dev;
   MarchPlan plan;  // run lists, fix list and CTA tiles of the march kernel
   int variant;     // CTA shape of the march kernel (ldg_march_variant)
+  unsigned* tail_ctr_dev;  // ring of {next, finished} counter pairs of the march kernel's tail queue
+  unsigned launch_seq;
   void* tab_host;
   int64_t ndofs;
 };
@@ -252,12 +256,17 @@ static int ldg_launch_march_v(LdgHandle* h, const LdgArgs& a, cudaStream_t st) {
   const SegCache& sc = h->plan.segments(0, h->nx, sm_count() * C::MINB);
   if (sc.n <= 0) return fail(ST_UNSUPPORTED, "stefan_ldg_apply: more than %d strip groups (ny too large)", kMaxMarchCtas);
   constexpr int smem = LdgMarchSmem<P, V>::TOTAL;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceFlag attr_set;
+  if (!attr_set.here()) {
     STEFAN_CUDA(cudaFuncSetAttribute(ldg_apply_march<P, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
+    attr_set.here() = true;
   }
-  LdgMarchArgs m{a.x, a.x_lo, a.x_hi, a.y, a.phase, a.nx, a.ny, h->plan.fix_dev, h->plan.nfix, 0u};
+  if (h->tail_ctr_dev == nullptr) {
+    STEFAN_CUDA(cudaMalloc(&h->tail_ctr_dev, kLdgTailRing * 2 * sizeof(unsigned)));
+    STEFAN_CUDA(cudaMemset(h->tail_ctr_dev, 0, kLdgTailRing * 2 * sizeof(unsigned)));
+  }
+  LdgMarchArgs m{a.x, a.x_lo, a.x_hi, a.y, a.phase, a.nx, a.ny, h->plan.fix_dev, h->plan.nfix, 0u, nullptr,
+                 h->tail_ctr_dev + 2 * (h->launch_seq++ % kLdgTailRing)};
   static const bool skip_tail = getenv("STEFAN_DEV_SKIP_TAIL") != nullptr;  // timing experiments only (wrong results)
   if (skip_tail) m.nfix = 0;
   CUtensorMap tm;
@@ -266,7 +275,42 @@ static int ldg_launch_march_v(LdgHandle* h, const LdgArgs& a, cudaStream_t st) {
     int rc = ldg_make_tensor_map(a.x, (int64_t)h->nx * h->ny, &tm);
     if (rc) return rc;
   }
-  ldg_apply_march<P, V><<<sc.n, C::WARPS * 32, smem, st>>>(tab, m, h->plan.runs_dev, h->plan.run_ofs_dev, sc.tab, tm);
+  // development only: STEFAN_DEV_CTA_TIMES=<file> dumps per-CTA {group, c0, c1, 4 x globaltimer ns}
+  static const char* dbg_path = getenv("STEFAN_DEV_CTA_TIMES");
+  if (dbg_path != nullptr) {
+    unsigned long long* d = nullptr;
+    STEFAN_CUDA(cudaMalloc(&d, (size_t)sc.n * 4 * sizeof(unsigned long long)));
+    STEFAN_CUDA(cudaMemset(d, 0, (size_t)sc.n * 4 * sizeof(unsigned long long)));
+    m.dbg_times = d;
+    ldg_apply_march<P, V><<<sc.n, C::WARPS * 32, smem, st>>>(tab, m, h->plan.runs_dev, h->plan.run_ofs_dev, sc.tab, tm);
+    STEFAN_CUDA(cudaStreamSynchronize(st));
+    std::vector<unsigned long long> t((size_t)sc.n * 4);
+    STEFAN_CUDA(cudaMemcpy(t.data(), d, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    if (FILE* f = fopen(dbg_path, "w")) {
+      for (int b = 0; b < sc.n; ++b)
+        fprintf(f, "%d %d %d %llu %llu %llu %llu\n", sc.tab.e[b].x, sc.tab.e[b].y, sc.tab.e[b].z, t[4 * b],
+                t[4 * b + 1], t[4 * b + 2], t[4 * b + 3]);
+      fclose(f);
+    }
+    return ST_OK;
+  }
+  {
+    // programmatic stream serialization: see griddep_wait in ipdg.cu (STEFAN_PDL=0 turns it off)
+    static const bool pdl = [] { const char* e = getenv("STEFAN_PDL"); return e == nullptr || atoi(e) != 0; }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)sc.n);
+    cfg.blockDim = dim3(C::WARPS * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    STEFAN_CUDA(cudaLaunchKernelEx(&cfg, ldg_apply_march<P, V>, tab, m, (const int4*)h->plan.runs_dev,
+                                   (const int*)h->plan.run_ofs_dev, sc.tab, tm));
+  }
   STEFAN_CUDA(cudaGetLastError());
   return ST_OK;
 }
@@ -311,6 +355,8 @@ int stefan_ldg_create(const stefan_ldg_params* p, const int8_t* phase, const int
   h->has_hi = phase_hi != nullptr;
   h->phase_dev = nullptr;
   h->tab_host = nullptr;
+  h->tail_ctr_dev = nullptr;
+  h->launch_seq = 0;
   const int NF = (p->order + 1) * (p->order + 1);
   h->ndofs = (int64_t)p->nx * p->ny * NF * 3;
   RefElem1D ref;
@@ -361,6 +407,7 @@ int stefan_ldg_destroy(stefan_ldg* hv) {
   LdgHandle* h = reinterpret_cast<LdgHandle*>(hv);
   if (!h) return ST_OK;
   if (h->phase_dev) cudaFree(h->phase_dev);
+  if (h->tail_ctr_dev) cudaFree(h->tail_ctr_dev);
   h->plan.destroy();
   switch (h->order) {
     case 1: delete static_cast<LdgTab<1>*>(h->tab_host); break;

@@ -74,13 +74,35 @@ struct LdgMarchArgs {
   const int32_t* fix;
   int nfix;
   unsigned zero;  // 0 at run time, unknown at compile time (slot release, see ipdg_march.cuh)
+  unsigned long long* dbg_times;  // development only: per-CTA {start, prologue end, loop end, end} globaltimer, or null
+  unsigned* tail_ctr;  // dynamic tail queue: [0] next fix-list index, [1] CTAs finished (reset by the last CTA)
 };
+__device__ __forceinline__ void ldg_griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void ldg_griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-// cells the loop does not store: one thread per cell, general tables
+__device__ __forceinline__ void ldg_dbg_stamp(const LdgMarchArgs& a, int slot) {
+  if (a.dbg_times != nullptr && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    a.dbg_times[4 * blockIdx.x + slot] = t;
+  }
+}
+
+// cells the loop does not store: one thread per cell, general tables.  The list is a queue:
+// every warp that is done with its strip takes 32 cells at a time until it is empty (see
+// fixup_tail in ipdg.cu).
 template <int P>
 __device__ __forceinline__ void ldg_fixup_tail(const LdgTab<P>& tab, const LdgMarchArgs& a) {
   constexpr int N1 = P + 1, NF = N1 * N1, CD = 3 * NF;
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < a.nfix; t += gridDim.x * blockDim.x) {
+  if (a.nfix <= 0) return;
+  const int lane_t = threadIdx.x & 31;
+  for (;;) {
+    unsigned base = 0;
+    if (lane_t == 0) base = atomicAdd(a.tail_ctr, 32u);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= (unsigned)a.nfix) break;
+    const int t = (int)base + lane_t;
+    if (t >= a.nfix) continue;
     const int64_t cell = a.fix[t];
     const int i = (int)(cell / a.ny), j = (int)(cell % a.ny);
     const int s = ldg_phase_at(a.phase, a.ny, i, j);
@@ -137,6 +159,7 @@ ldg_apply_march(const __grid_constant__ LdgTab<P> tab, const LdgMarchArgs a, con
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
+  ldg_griddep_launch();  // the next kernel of the stream may start its prologue while this one drains
 
   const int nstrips = (a.ny + kStripCells - 1) / kStripCells;
   const int4 myseg = segs.e[blockIdx.x];
@@ -261,6 +284,10 @@ ldg_apply_march(const __grid_constant__ LdgTab<P> tab, const LdgMarchArgs a, con
     }
     int4 cur = ld_run(rp);
     int4 nxt = ld_run(rp + 1);
+    // up to here only the handle's own tables were read; the vectors and the queue counters may
+    // have been written by the previous kernel of the stream
+    ldg_griddep_wait();
+    ldg_dbg_stamp(a, 0);
 
     // prologue: columns c0-1 .. c0+NST-2 into slots 0 .. NST-1
 #pragma unroll
@@ -285,6 +312,7 @@ ldg_apply_march(const __grid_constant__ LdgTab<P> tab, const LdgMarchArgs a, con
       issue(c0 + NST, ring + s1 * C::STAGE + z, bars + 8 * s1 + z);
     }
 
+    ldg_dbg_stamp(a, 1);
     int slot = 2 % NST;
     unsigned stage_r = ring + slot * C::STAGE, bar_r = bars + 8 * slot, par_r = (2 / NST) & 1;
     double* yp = a.y + ((size_t)c0 * a.ny + j) * CD;
@@ -385,7 +413,25 @@ ldg_apply_march(const __grid_constant__ LdgTab<P> tab, const LdgMarchArgs a, con
       __syncwarp();
     }
   }
+  if (a.dbg_times != nullptr) {
+    __syncthreads();
+    ldg_dbg_stamp(a, 2);
+  }
+  ldg_griddep_wait();  // (warps without a strip have not waited yet)
   ldg_fixup_tail<P>(tab, a);
+  if (a.dbg_times != nullptr) {
+    __syncthreads();
+    ldg_dbg_stamp(a, 3);
+  }
+  // the last CTA to get here resets the tail queue for the next launch
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(a.tail_ctr + 1, 1u) == gridDim.x - 1) {
+      a.tail_ctr[0] = 0;
+      a.tail_ctr[1] = 0;
+    }
+  }
 }
 
 }  // namespace stefan

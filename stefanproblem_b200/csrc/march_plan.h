@@ -139,67 +139,82 @@ struct MarchPlan {
   }
 
   // Cost-balanced tiles, one per CTA, for columns [cbeg, cend).  A CTA is done when its
-  // slowest warp is; a warp pays 4 cost units per column plus mixed_cost_q units where its strip
-  // mixes phases (both phase bodies run), so
-  //     cost(group, [c0, c1)) = 4 (c1 - c0) + mixed_cost_q * max over the group's strips of
-  //                                            #mixed columns of that strip in [c0, c1).
-  // mixed_cost_q is per kernel (measured: a mixed column costs an order-1 warp ~5 % more -- the
-  // kernel is memory-bound and the second body hides behind the loads -- and about half a
-  // column at orders 2 and 3).  T = the smallest tile cost whose
-  // greedy cut fits the CTA budget (one wave); every group is then re-cut into the same number
-  // of tiles of EQUAL cost (no short remainder tile).  Cached per column range.
-  int mixed_cost_q = 4;  // quarter columns; set by the kernel's host code before the first apply
-  int min_tile_cols = 8;
+  // slowest warp is; a warp pays 4 cost units per column plus mixed_cost_q units where a strip of
+  // its group mixes phases (both phase bodies run), plus edge_lo_q / edge_hi_q units on the first /
+  // last column of a slab whose halo column comes from a neighbour (the tile may have to wait for
+  // the neighbour's flag, so it gets fewer columns).  The loops are memory-bound: measured per-CTA
+  // times (STEFAN_DEV_CTA_TIMES, profiles/r2_*cta*) follow the column count, a mixed column costs
+  // about a quarter column more.
+  // Round 2: (1) the whole CTA budget (one wave) is handed out -- tiles go one by one to the group
+  // whose tiles are currently the most expensive; (2) a group is cut into tiles of EQUAL cost.
+  // (Round 1 cut greedily at a common cost T: 625 columns became 12 x 49 + 37 with 17 of 296 CTA
+  // slots unused; now 14 x 44-45.)  Cached per column range.
+  int mixed_cost_q = 1;  // quarter columns; set by the kernel's host code before the first apply
+  int min_tile_cols = 4;
+  int edge_lo_q = 0, edge_hi_q = 0;
   const SegCache& segments(int cbeg, int cend, int max_ctas) {
     for (const SegCache& c : seg_cache)
       if (c.cbeg == cbeg && c.cend == cend && c.max_ctas == max_ctas) return c;
     if (const char* e = getenv("STEFAN_MIXED_COST_Q")) mixed_cost_q = atoi(e);
-    const int ng = ngroups, gw = group_warps;
-    auto cost = [&](int g, int c0, int c1) {
-      int mx = 0;
-      for (int sidx = g * gw; sidx < std::min(nstrips, (g + 1) * gw); ++sidx) {
-        const int* cum = mixed_cum.data() + (size_t)sidx * (nx + 1);
-        mx = std::max(mx, cum[c1] - cum[c0]);
-      }
-      return 4 * (c1 - c0) + mixed_cost_q * mx;
-    };
-    // greedy cut of group g into tiles of cost <= T (at least one column each)
-    auto cut_group = [&](int g, int T, std::vector<int4>* tiles) {
-      int n = 0, c0 = cbeg;
-      while (c0 < cend) {
-        int lo = c0 + 1, hi = cend;  // largest c1 in (c0, cend] with cost <= T
-        while (lo < hi) {
-          const int mid = (lo + hi + 1) / 2;
-          if (cost(g, c0, mid) <= T) lo = mid;
-          else hi = mid - 1;
-        }
-        if (tiles) tiles->push_back(make_int4(g, c0, lo, n));
-        ++n;
-        c0 = lo;
-      }
-      return n;
-    };
-    auto cut = [&](int T) {
-      int n = 0;
-      for (int g = 0; g < ng; ++g) n += cut_group(g, T, nullptr);
-      return n;
-    };
-    const int budget = std::max(ng, std::min(max_ctas, kMaxMarchCtas));
-    int hi = (4 + mixed_cost_q) * (cend - cbeg) + 1;
     if (const char* e = getenv("STEFAN_MIN_TILE_COLS")) min_tile_cols = std::max(1, atoi(e));
-    int lo = std::min(4 * min_tile_cols, hi);  // tiles no shorter than this (pipeline fill per tile)
-    while (lo < hi) {
-      const int mid = (lo + hi) / 2;
-      if (cut(mid) <= budget) hi = mid;
-      else lo = mid + 1;
+    if (const char* e = getenv("STEFAN_EDGE_COST_Q")) {
+      if (edge_lo_q) edge_lo_q = atoi(e);
+      if (edge_hi_q) edge_hi_q = atoi(e);
+    }
+    const int ng = ngroups, gw = group_warps, ncol = cend - cbeg;
+    // cumulative cost per group: cum[g][c - cbeg] = cost of columns [cbeg, c)
+    std::vector<int64_t> cum((size_t)ng * (ncol + 1), 0);
+    for (int g = 0; g < ng; ++g) {
+      int64_t* cg = cum.data() + (size_t)g * (ncol + 1);
+      for (int c = cbeg; c < cend; ++c) {
+        int mixed = 0;
+        for (int sidx = g * gw; sidx < std::min(nstrips, (g + 1) * gw); ++sidx) {
+          const int* mc = mixed_cum.data() + (size_t)sidx * (nx + 1);
+          mixed |= mc[c + 1] - mc[c];
+        }
+        int64_t v = 4 + (mixed ? mixed_cost_q : 0);
+        if (c == 0) v += edge_lo_q;
+        if (c == nx - 1) v += edge_hi_q;
+        cg[c - cbeg + 1] = cg[c - cbeg] + v;
+      }
+    }
+    // tiles per group: hand out the budget one tile at a time to the group with the costliest tiles
+    const int budget = std::max(ng, std::min(max_ctas, kMaxMarchCtas));
+    const int max_per_group = std::max(1, ncol / std::max(1, min_tile_cols));
+    std::vector<int> ntile(ng, 1);
+    for (int total = ng; total < budget; ++total) {
+      int best = -1;
+      double best_cost = 0.0;
+      for (int g = 0; g < ng; ++g) {
+        if (ntile[g] >= max_per_group) continue;
+        const double c = (double)cum[(size_t)g * (ncol + 1) + ncol] / ntile[g];
+        if (c > best_cost) {
+          best_cost = c;
+          best = g;
+        }
+      }
+      if (best < 0) break;
+      ++ntile[best];
     }
     std::vector<int4> tiles;
     for (int g = 0; g < ng; ++g) {
-      // same tile count as the greedy cut at T, but equal shares of the group's cost
-      const int n = cut_group(g, lo, nullptr);
-      int Tg = (cost(g, cbeg, cend) + n - 1) / n;
-      while (cut_group(g, Tg, nullptr) > n) Tg += std::max(1, Tg / 64);
-      cut_group(g, Tg, &tiles);
+      const int64_t* cg = cum.data() + (size_t)g * (ncol + 1);
+      const int n = ntile[g];
+      int c0 = 0;
+      for (int k = 1; k <= n && c0 < ncol; ++k) {
+        // end of tile k: the first column count whose cost reaches k / n of the group's cost
+        int c1 = ncol;
+        if (k < n) {
+          const int64_t target = (cg[ncol] * k + n / 2) / n;
+          c1 = (int)(std::lower_bound(cg + c0 + 1, cg + ncol + 1, target) - cg);
+          // the nearer of the two columns around the target
+          if (c1 > c0 + 1 && target - cg[c1 - 1] < cg[c1] - target) --c1;
+          c1 = std::min(std::max(c1, c0 + 1), ncol - (n - k));  // at least one column for every tile left
+          c1 = std::max(c1, c0 + 1);
+        }
+        tiles.push_back(make_int4(g, cbeg + c0, cbeg + c1, k - 1));
+        c0 = c1;
+      }
     }
     // CTA order: segment-major = CTAs with neighbouring block indices work on neighbouring
     // strips of the same columns

@@ -298,6 +298,18 @@ class IPOperator:
                                                        _stream_ptr(stream)))
         return u
 
+    def step(self, u, b, dt, out=None, u_lo=None, u_hi=None, sync=None, stream=None):
+        """out = u + dt Minv (b - A u): the fused explicit step, one pass of the apply kernel
+        (stefan_ipdg_step); b may be None."""
+        import torch
+        assert u.is_cuda and u.dtype == torch.float64 and u.is_contiguous() and u.numel() == self.ndofs
+        if out is None:
+            out = torch.empty_like(u)
+        _lib.check(_lib.lib().stefan_ipdg_step(self._h, _ptr(u), _ptr(out), _ptr(b), float(dt), _ptr(u_lo),
+                                               _ptr(u_hi), ctypes.byref(sync) if sync is not None else None,
+                                               _stream_ptr(stream)))
+        return out
+
     def rhs(self, f_qp=None, g_qp=None, out=None, stream=None):
         """b of `assemble_interior_penalty_rhs!` (+ Robin source) from device samples."""
         import torch

@@ -94,6 +94,32 @@ def test_interface_continuity_row(cuda):
     assert np.linalg.norm(y - K @ u) <= 1e-13 * np.linalg.norm(K @ u)
 
 
+def test_interface_continuity_adds_to_existing_row(cuda):
+    """assemble_interface_continuity! only appends triplets (finite-difference.jl:111-116): on a node that
+    already has a Laplace row, sparse() sums the two -- apply and the COO seam must do the same."""
+    import torch
+    from stefanproblem_b200 import finite_difference as FD
+    n = 40
+    ph = ofd.phase_id(0.5 - np.linspace(0, 1, n))
+    h = 1.0 / (n - 1)
+    m, om = FD.SystemMatrix(), ofd.SystemMatrix()
+    FD.assemble_laplace_operator(m, ph, h)
+    FD.assemble_dirichlet_boundary_condition(m, n)
+    ofd.assemble_laplace_operator(om, ph, h)
+    ofd.assemble_dirichlet_boundary_condition(om, n)
+    for node, r, s in ((10, 2.0, 3.0), (10, -1.0, 0.5), (30, 0.25, 4.0)):  # 1-based; node 10 twice
+        FD.assemble_interface_continuity(m, r, s, node)
+        ofd.assemble_interface_continuity(om, r, s, node - 1)
+    K = ofd.sparse_operator(om, n)
+    op = FD.sparse_operator(m, n)
+    u = np.random.default_rng(3).uniform(-1, 1, n)
+    y = (op @ torch.from_numpy(u).cuda()).cpu().numpy()
+    assert np.linalg.norm(y - K @ u) <= 1e-13 * np.linalg.norm(K @ u)
+    r_, c_, v_ = (t.cpu().numpy() for t in op.to_coo())
+    Kg = sp.coo_matrix((v_, (r_, c_)), shape=(n, n)).toarray()
+    assert np.abs(Kg - K.toarray()).max() <= 1e-12 * np.abs(K.toarray()).max()
+
+
 def test_hundred_explicit_steps(cuda):
     import torch
     from stefanproblem_b200 import finite_difference as FD

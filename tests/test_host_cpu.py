@@ -229,6 +229,13 @@ def test_march_plan_invariants(hostcheck, nx, ny, warps, two_phase, cbeg_frac, c
         seg = sorted((int(t[1]), int(t[2])) for t in tiles if t[0] == g)
         assert seg[0][0] == cbeg and seg[-1][1] == cend
         assert all(a[1] == b[0] for a, b in zip(seg, seg[1:])) and all(a < b for a, b in seg)
+        if not two_phase:  # equal-cost tiles: without mixed columns a group's tiles differ by one column at most
+            lens = [b - a for a, b in seg]
+            assert max(lens) - min(lens) <= 1
+    if not two_phase and ngroups > 0:  # the whole budget is handed out (tiles of >= 4 columns)
+        per = [sum(1 for t in tiles if t[0] == g) for g in range(ngroups)]
+        assert max(per) - min(per) <= 1
+        assert ntiles == max(ngroups, min(max_ctas, 640, ngroups * max(1, (cend - cbeg) // 4))) or max(per) == max(1, (cend - cbeg) // 4)
 
 
 @pytest.mark.parametrize("order", [1, 2, 3])
@@ -342,10 +349,10 @@ def test_production_kernels_carry_tma_and_mbarrier_instructions(built_lib):
     keys = [k.strip() for k in out[0].split("|")]
     rows = {r.split("|")[0].strip(): dict(zip(keys[1:], (int(v) for v in r.split("|")[1:]))) for r in out[1:]}
     march = [k for k in rows if "apply_march" in k]
-    assert len(march) == 9          # IP p = 1..3, LDG p = 1..3 in two CTA shapes
+    assert len(march) == 12         # IP p = 1..3 x {apply, fused step}, LDG p = 1..3 in two CTA shapes
     for k in march:
         assert rows[k]["UBLKCP"] > 0 and rows[k]["SYNCS"] > 0 and rows[k]["REDUX"] > 0, k
-    for k in ("ipdg_apply_march<3>", "ldg_apply_march<3, 0>", "ldg_apply_march<3, 1>"):
+    for k in ("ipdg_apply_march<3, 0>", "ipdg_apply_march<3, 1>", "ldg_apply_march<3, 0>", "ldg_apply_march<3, 1>"):
         assert rows[k]["UTMALDG"] > 0, k
     for k in ("fd_apply_vec<0>", "fd_apply_vec<1>"):
         assert rows[k]["STG.E.ENL2.256"] > 0 and rows[k]["LDG.E.ENL2.256"] > 0, k

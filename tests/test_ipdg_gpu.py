@@ -268,6 +268,71 @@ def test_hundred_explicit_euler_steps(cuda, order):
     assert np.linalg.norm(u.cpu().numpy() - ref) <= 1e-10 * np.linalg.norm(ref)
 
 
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_hundred_fused_steps(cuda, order):
+    """stefan_ipdg_step (apply + mass inverse + update fused into the march kernel's store epilogue, K9):
+    100 steps vs the oracle loop <= 1e-10 (north star), on one slab and on two slabs that read each other's
+    edge column of the CURRENT iterate."""
+    import torch
+    from oracle import timeloop
+    from stefanproblem_b200 import cutcelldg as cc
+    nx, ny, nq = 10, 8, order + 1
+    omesh = UniformMesh2D([0, 0], [1.0, 1.0], [nx, ny], (order + 1) ** 2)
+    omesh.cellsign[:] = fast.circle_phase(omesh)
+    k1, k2, pen, lam, Tm = 1.0, 2.0, 10.0 * nx, 1.0, 0.5
+    A = fast.ip_matrix(omesh, order, nq, k1, k2, pen, lam)
+    f = fast.sample_cell_quadrature(omesh, nq, lambda x, y: 1.0 + np.sin(3 * x) * y)
+    g = fast.sample_face_quadrature(omesh, nq, lambda x, y: x + y)
+    b = fast.ip_rhs(omesh, order, nq, k1, k2, pen, f, g, lam, Tm)
+    Minv = timeloop.ip_block_mass_inverse(omesh, order, nq)
+    lam_max = np.abs(np.linalg.eigvals((np.kron(np.eye(nx * ny), Minv) @ A.toarray()))).max()
+    dt = 1.0 / lam_max
+    u0 = np.random.default_rng(3).uniform(-1, 1, A.shape[0])
+    ref = timeloop.ip_euler_run(A, b, Minv, u0, dt, 100)
+    basis = cc.LagrangeTensorProductBasis(2, order)
+    P = omesh.cellsign.reshape(nx, ny)
+    mk = lambda m, **kw: cc.IPOperator(m, order, nq, k1, k2, pen, lam, Tm, "current", ALL, **kw)  # noqa: E731
+    op = mk(cc.UniformMesh([0, 0], [1.0, 1.0], [nx, ny], basis, phase=omesh.cellsign))
+    u, v = torch.from_numpy(u0).cuda(), torch.empty(A.shape[0], dtype=torch.float64, device="cuda")
+    bd = torch.from_numpy(b).cuda()
+    for _ in range(100):
+        op.step(u, bd, dt, out=v)
+        u, v = v, u
+    assert np.linalg.norm(u.cpu().numpy() - ref) <= 1e-10 * np.linalg.norm(ref)
+    # two slabs
+    cut, col = 4, ny * basis.nf
+    lo = mk(cc.UniformMesh([0, 0], [cut / nx, 1], [cut, ny], basis, phase=P[:cut].ravel()), phase_hi=P[cut])
+    hi = mk(cc.UniformMesh([cut / nx, 0], [1 - cut / nx, 1], [nx - cut, ny], basis, phase=P[cut:].ravel()),
+            phase_lo=P[cut - 1])
+    u, v = torch.from_numpy(u0).cuda(), torch.empty(A.shape[0], dtype=torch.float64, device="cuda")
+    for _ in range(100):
+        lo.step(u[:cut * col], bd[:cut * col], dt, out=v[:cut * col], u_hi=u[cut * col:(cut + 1) * col])
+        hi.step(u[cut * col:], bd[cut * col:], dt, out=v[cut * col:], u_lo=u[(cut - 1) * col:cut * col])
+        u, v = v, u
+    assert np.linalg.norm(u.cpu().numpy() - ref) <= 1e-10 * np.linalg.norm(ref)
+
+
+@pytest.mark.parametrize("order,nx,ny", [(1, 300, 217), (2, 131, 170), (3, 97, 125)])
+def test_fused_step_equals_apply_plus_update(cuda, order, nx, ny):
+    """Many strips / tiles / mixed columns: the fused step against apply (plain kernel) + euler_update."""
+    import torch
+    from stefanproblem_b200 import cutcelldg as cc
+    basis = cc.LagrangeTensorProductBasis(2, order)
+    omesh = UniformMesh2D([0, 0], [1, 1], [nx, ny], basis.nf)
+    mesh = cc.UniformMesh([0, 0], [1, 1], [nx, ny], basis, phase=fast.circle_phase(omesh))
+    op = cc.IPOperator(mesh, order, order + 1, 1.0, 2.0, 1e3 * nx, 1.0, 0.5, "current", ALL)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    u = torch.rand(op.ndofs, dtype=torch.float64, device="cuda", generator=gen) * 2 - 1
+    b = torch.rand(op.ndofs, dtype=torch.float64, device="cuda", generator=gen) * 2 - 1
+    dt = 1e-7
+    for bb in (b, None):
+        got = op.step(u, bb, dt)
+        want = u.clone()
+        op.euler_update(want, op.apply(u, algo=op.SIMPLE), bb, dt)
+        assert (got - want).norm() <= 1e-14 * want.norm()
+        assert (got - u).norm() > 0
+
+
 @pytest.mark.parametrize("order,n", [(1, 12), (2, 9), (3, 6)])
 @pytest.mark.parametrize("two_phase", [False, True])
 @pytest.mark.parametrize("precond", ["block_jacobi", "none"])
