@@ -4,12 +4,19 @@
 Workload (BASELINE.json `configs[4]`): uniform 2-D mesh of Q_p cells,
 two phases (circle of radius 0.4, k1 = 1, k2 = 2), mesh-aligned interface with
 flux + penalty + Robin terms (lambda = 1), Dirichlet boundary, pen = 1e3 * nx.
-Default p = 1, 5000 x 5000 cells per GPU = 100 M dofs per GPU (weak scaling: rank r
-owns the r-th slab of 5000 cell columns of a (5000 N) x 5000 mesh).  N > 1: the slab
-vectors live in CUDA-IPC peer memory and every rank's apply kernel reads its neighbours'
-edge columns over NVLink itself (`--halo peer`, the default: one launch per application,
-ordered by epoch flags that the same kernel publishes, waits for and releases); `--halo nccl` exchanges the columns with NCCL send/recv on a side stream,
-overlapped with the interior columns.
+Parity of this workload: oracle extrapolation -- the reference's
+face-level functions on the faces between unlike phases, driven by the oracle's own loop.
+
+`--gpus N` is STRONG scaling (default): the global mesh is fixed (p = 1: 5000 x 5000 cells =
+100 M dofs) and rank r owns the r-th slab of nx/N cell columns.  The slab vectors live in
+CUDA-IPC peer memory and every rank's apply kernel reads its neighbours' edge columns over
+NVLink itself (one launch per application, ordered by epoch flags that the same kernel
+publishes and waits for); the K timed steps are one CUDA-graph replay per rank.  The line also
+carries `weak` (5000 x 5000 cells PER GPU, the round-1 measurement), `parity_max_rel` (fused
+peer halos + march kernel against NCCL halos + the plain one-thread-per-cell kernel, max over
+ranks, asserted <= 1e-13) and `step_loop` (the explicit time loop: fused step kernel + interface
+sums + 4-double NCCL all-reduce per step).  `--halo nccl` exchanges the columns with NCCL
+send/recv on a side stream, overlapped with the interior columns.
 
 One "step" = one application of the operator.  `value` = dofs x steps / seconds with
 x resident in HBM; `e2e` = the same through stefan_ipdg_apply_host (host buffers,
@@ -31,6 +38,8 @@ sys.path.insert(0, ROOT)
 METRIC = "fp64 DOF-updates/sec for IP-DG heat operator"
 UNIT = "DOF-updates/s"
 ALGO_BYTES_PER_DOF = 16  # read x once + write y once
+STEP_BYTES_PER_DOF = 24  # fused explicit step: u and b read, unew written
+PARITY_NOTE = "oracle extrapolation (SURVEY 8(d)(ii)): reference face-level functions on unlike-phase faces, oracle's own driver loop"
 
 
 def measured_hbm_peak():
@@ -71,7 +80,7 @@ class ClockSampler:
                         self.reasons.add(n)
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.05)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -104,11 +113,221 @@ def column_phase(nx_global, ny, i):
     return np.where((cx - 0.5) ** 2 + (cy - 0.5) ** 2 < 0.16, -1, 1).astype(np.int8)
 
 
-def run_ours(args):
-    import numpy as np
+class SlabProblem:
+    """One rank's part of a global nxg x ny mesh: operator, slab vector(s), result vector."""
+
+    def __init__(self, order, nxg, ny, rank, world, want_peer, nbuf=1):
+        import torch
+        import torch.distributed as dist
+        from stefanproblem_b200.distributed import DistributedIPOperator, PeerSlab
+        self.rank, self.world, self.order = rank, world, order
+        self.dop = DistributedIPOperator(nxg, ny, (1.0, 1.0), order, order + 1, 1.0, 2.0, 1e3 * nxg, 1.0, 0.5,
+                                         lambda i: column_phase(nxg, ny, i), rank, world)
+        self.op = self.dop.op
+        self.ndofs = self.op.ndofs
+        gen = torch.Generator(device="cuda")
+        gen.manual_seed(1234 + rank)
+        self.x = torch.rand(self.ndofs, dtype=torch.float64, device="cuda", generator=gen) * 2 - 1
+        self.y = torch.empty_like(self.x)
+        self.slab = None
+        self.peer = False
+        if world > 1 and want_peer:
+            # collective; if CUDA IPC is not available to some rank (container policy), every rank
+            # falls back to the NCCL halos together and the line says so
+            failed = 0
+            try:
+                self.slab = PeerSlab(self.ndofs, rank, world, nbuf=nbuf)
+            except Exception as exc:  # noqa: BLE001
+                failed = 1
+                sys.stderr.write(f"rank {rank}: peer memory unavailable ({exc}); falling back to --halo nccl\n")
+            flag = torch.tensor([failed], dtype=torch.int32, device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+            if int(flag.item()):
+                if self.slab is not None:
+                    self.slab.close()
+                self.slab = None
+            else:
+                self.slab.x.copy_(self.x)
+                self.x = self.slab.x
+                self.peer = True
+
+    def step(self, device_epoch=False):
+        from stefanproblem_b200.distributed import apply_peer_fused
+        if self.peer:
+            # ONE launch: the kernel publishes my epoch, its edge tiles wait for the neighbours' epoch before
+            # they read their edge columns over NVLink, its last CTA releases them
+            apply_peer_fused(self.dop, self.slab, self.y, device_epoch=device_epoch)
+        elif self.world > 1:
+            # halo trace exchange (NCCL, side stream) overlapped with the interior columns
+            self.dop.apply(self.x, self.y)
+        else:
+            self.op.apply(self.x, out=self.y)
+
+    def close(self):
+        if self.slab is not None:
+            self.slab.close()
+            self.slab = None
+
+
+def barrier(world):
     import torch
     import torch.distributed as dist
-    from stefanproblem_b200 import cutcelldg as cc
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(v, world):
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return float(v)
+    t = torch.tensor([v], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def timed_steps(prob, steps, warmup, use_graph, clk_gpu=None):
+    """W untimed steps, then exactly `steps` steps between barrier + synchronize, CUDA events, max over ranks.
+    use_graph: the K steps are ONE CUDA-graph replay (the peer epochs live on the device)."""
+    import torch
+    world = prob.world
+    graph = None
+    dev_epoch = bool(use_graph and prob.peer)
+    stream = torch.cuda.Stream()
+    if dev_epoch:
+        torch.cuda.synchronize()
+        prob.slab.to_device_epochs()
+        torch.cuda.synchronize()
+    with torch.cuda.stream(stream):
+        for _ in range(warmup):
+            prob.step(device_epoch=dev_epoch)
+        stream.synchronize()
+        if use_graph and (prob.peer or world == 1):
+            try:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=stream):
+                    for _ in range(steps):
+                        prob.step(device_epoch=dev_epoch)
+            except Exception as exc:  # noqa: BLE001
+                sys.stderr.write(f"rank {prob.rank}: CUDA-graph capture failed ({exc}); timing plain launches\n")
+                graph = None
+    # capture must have worked on every rank (a replay launches `steps` kernels, the epochs must agree)
+    ok = max_over_ranks(0.0 if graph is not None else 1.0, world) == 0.0
+    if not ok:
+        graph = None
+        if dev_epoch:   # back to host-side epochs: resynchronise them with the device counter
+            torch.cuda.synchronize()
+            prob.slab.to_host_epochs()
+            dev_epoch = False
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(clk_gpu) if clk_gpu is not None else None
+    if sampler:
+        sampler.__enter__()
+    with torch.cuda.stream(stream):
+        if graph is not None:   # one untimed replay: uploads the graph
+            graph.replay()
+        barrier(world)
+        e0.record(stream)
+        if graph is not None:
+            graph.replay()
+        else:
+            for _ in range(steps):
+                prob.step(device_epoch=dev_epoch)
+        e1.record(stream)
+        barrier(world)
+    if sampler:
+        # keep sampling for a moment if the region was shorter than one nvidia-smi call
+        t_end = time.time() + 0.3
+        while not sampler.samples and time.time() < t_end:
+            time.sleep(0.02)
+        sampler.__exit__()
+    ms = max_over_ranks(e0.elapsed_time(e1), world)
+    if dev_epoch:
+        prob.slab.to_host_epochs()
+    return ms / steps, graph is not None, (sampler.summary() if sampler else None)
+
+
+def parity_check(prob):
+    """Fused peer halos + march kernel against NCCL halos + the plain one-thread-per-cell kernel on this rank's slab
+    (N = 1: march against plain).  Returns (max over ranks of the relative difference, checksum of y)."""
+    import torch
+    import torch.distributed as dist
+    world = prob.world
+    prob.step()
+    y1 = prob.y.clone()
+    if world > 1:
+        h = prob.dop.halo
+        h.exchange(prob.x)
+        y2 = prob.op.apply(prob.x, x_lo=h.x_lo, x_hi=h.x_hi, algo=prob.op.SIMPLE)
+    else:
+        y2 = prob.op.apply(prob.x, algo=prob.op.SIMPLE)
+    rel = float((y1 - y2).norm() / y2.norm())
+    chk = torch.stack([y1.sum(), y2.sum()])
+    if world > 1:
+        dist.all_reduce(chk, op=dist.ReduceOp.SUM)
+        if prob.peer:
+            prob.slab.check()   # raises on every rank if a flag wait timed out anywhere
+    return max_over_ranks(rel, world), float(chk[0].item()), float(chk[1].item())
+
+
+def time_step_loop(order, nxg, ny, rank, world, steps, warmup):
+    """The explicit time loop that drives the front: per step ONE fused kernel (unew = u + dt Minv (b - A u), the
+    neighbours' edge columns of u read over NVLink), then the interface sums of unew and their 4-double all-reduce."""
+    import torch
+    import torch.distributed as dist
+    from stefanproblem_b200.distributed import interface_sums_peer, step_peer_fused
+    prob = SlabProblem(order, nxg, ny, rank, world, want_peer=True, nbuf=2)
+    if world > 1 and not prob.peer:
+        prob.close()
+        return None
+    b = torch.rand_like(prob.x)
+    dt = 1e-9
+    if world > 1:
+        bufs = prob.slab.bufs
+    else:
+        bufs = [prob.x, torch.empty_like(prob.x)]
+    sums = torch.zeros(4, dtype=torch.float64, device="cuda")
+
+    def one(k):
+        src, dst = k & 1, (k + 1) & 1
+        if world > 1:
+            step_peer_fused(prob.dop, prob.slab, src, dst, b, dt)
+            interface_sums_peer(prob.dop, prob.slab, dst, sums)
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+        else:
+            prob.op.step(bufs[src], b, dt, out=bufs[dst])
+            prob.op.interface_sums(bufs[dst], out=sums)
+
+    for k in range(warmup):
+        one(k)
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(warmup, warmup + steps):
+        one(k)
+    e1.record()
+    barrier(world)
+    ms = max_over_ranks(e0.elapsed_time(e1), world) / steps
+    if world > 1:
+        prob.slab.check()
+    ndofs = prob.ndofs
+    prob.close()
+    tot = ndofs
+    if world > 1:
+        t = torch.tensor([ndofs], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        tot = float(t.item())
+    return {"ms_per_step": ms, "value": tot / (ms * 1e-3), "unit": "DOF-updates/s (time steps)",
+            "per_step": "stefan_ipdg_step (fused apply + mass inverse + update, peer halos) + stefan_ipdg_interface_sums "
+                        "+ 4-double NCCL all-reduce; plain launches",
+            "algorithmic_bytes_per_dof": STEP_BYTES_PER_DOF,
+            "interface_sums_last": [float(v) for v in sums.cpu()]}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -120,148 +339,123 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    p, nxl, ny = args.order, args.nx, args.ny
-    nf = (p + 1) ** 2
-    nxg = nxl * world
-    from stefanproblem_b200.distributed import DistributedIPOperator, PeerSlab, apply_peer, apply_peer_fused
-    dop = DistributedIPOperator(nxg, ny, (1.0, 1.0), p, p + 1, 1.0, 2.0, 1e3 * nxg, 1.0, 0.5,
-                                lambda i: column_phase(nxg, ny, i), rank, world)
-    op = dop.op
-    ndofs_local = op.ndofs
-    gen = torch.Generator(device="cuda")
-    gen.manual_seed(1234 + rank)
-    x = torch.rand(ndofs_local, dtype=torch.float64, device="cuda", generator=gen) * 2 - 1
-    y = torch.empty_like(x)
-    x_lo, x_hi = dop.halo.x_lo, dop.halo.x_hi
-    peer = world > 1 and args.halo == "peer"
-    slab = None
-    if peer:
-        # collective; if CUDA IPC is not available to some rank (container policy), every rank
-        # falls back to the NCCL halos together and the line says so
-        failed = 0
-        try:
-            slab = PeerSlab(ndofs_local, rank, world)
-        except Exception as exc:  # noqa: BLE001
-            failed = 1
-            sys.stderr.write(f"rank {rank}: peer memory unavailable ({exc}); falling back to --halo nccl\n")
-        flag = torch.tensor([failed], dtype=torch.int32, device="cuda")
-        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
-        if int(flag.item()):
-            if slab is not None:
-                slab.close()
-            slab, peer = None, False
-        else:
-            slab.x.copy_(x)
-            x = slab.x
-
-    def step():
-        if peer:
-            # ONE launch: the kernel publishes my vector's epoch, its warps wait for the
-            # neighbours' epoch before they read their edge columns over NVLink, its last CTA
-            # releases them
-            apply_peer_fused(dop, slab, y)
-        else:
-            # halo trace exchange (NCCL, side stream) overlapped with the interior columns
-            dop.apply(x, y)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
-        barrier()
-        e0.record()
-        for _ in range(args.steps):
-            step()
-        e1.record()
-        barrier()
-    ms = e0.elapsed_time(e1)
+    p, n_x, ny = args.order, args.nx, args.ny
+    strong = args.scaling == "strong"
+    nxg = n_x if strong else n_x * world
+    want_peer = args.halo == "peer"
+    prob = SlabProblem(p, nxg, ny, rank, world, want_peer)
+    peer = prob.peer
+    ndofs_local = prob.ndofs
+    t = torch.tensor([ndofs_local], dtype=torch.float64, device="cuda")
     if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    ms_per_step = ms / args.steps
-    total_dofs = ndofs_local * world
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    total_dofs = int(t.item())
+
+    # ---- parity before anything is timed (driver-visible: the line carries the number) ----
+    parity_rel, chk_fused, chk_plain = parity_check(prob)
+    if parity_rel > 1e-13:
+        raise SystemExit(f"rank {rank}: parity check failed: relative difference {parity_rel:.3e} > 1e-13")
+
+    # ---- the timed region ----
+    use_graph = not args.no_graph
+    ms_per_step, graphed, clocks = timed_steps(prob, args.steps, args.warmup, use_graph, clk_gpu=local)
     value = total_dofs / (ms_per_step * 1e-3)
 
-    # kernel-only duration for the roofline (no halo exchange), same stream, CUDA events
-    barrier()
+    # kernel-only duration of this rank's slab for the roofline (no flags, static x), CUDA events on the launching stream
+    barrier(world)
+    x_lo, x_hi = prob.dop.halo.x_lo, prob.dop.halo.x_hi
+    if world > 1:
+        prob.dop.halo.exchange(prob.x)
+    for _ in range(3):
+        prob.op.apply(prob.x, out=prob.y, x_lo=x_lo, x_hi=x_hi)
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k0.record()
     for _ in range(args.steps):
-        if peer:
-            apply_peer(dop, slab, y, publish=False)
-        else:
-            op.apply(x, out=y, x_lo=x_lo, x_hi=x_hi)
+        prob.op.apply(prob.x, out=prob.y, x_lo=x_lo, x_hi=x_hi)
     k1.record()
     torch.cuda.synchronize()
     kernel_ms = k0.elapsed_time(k1) / args.steps
     peak, peak_src = measured_hbm_peak()
     achieved = ALGO_BYTES_PER_DOF * ndofs_local / (kernel_ms * 1e-3) / 1e9
 
-    # end to end through the C ABI with host buffers (rank-local slab, no halo: N = 1 only)
+    # ---- end to end through the C ABI with host buffers ----
     e2e = None
     if world == 1:
         xh = torch.empty(ndofs_local, dtype=torch.float64).pin_memory()
-        xh.copy_(x.cpu())
+        xh.copy_(prob.x.cpu())
         yh = torch.empty(ndofs_local, dtype=torch.float64).pin_memory()
         n_e2e = max(2, min(args.steps, 10))
-        op.apply_host(xh, yh)
+        prob.op.apply_host(xh, yh)
         t0 = time.perf_counter()
         for _ in range(n_e2e):
-            op.apply_host(xh, yh)
+            prob.op.apply_host(xh, yh)
         dt = (time.perf_counter() - t0) / n_e2e
         e2e = {"value": ndofs_local / dt, "unit": UNIT, "h2d_bytes_per_step": ndofs_local * 8,
                "d2h_bytes_per_step": ndofs_local * 8, "steps": n_e2e,
-               "api": "stefan_ipdg_apply_host (pinned host buffers, 32 pipelined slabs)"}
+               "api": "stefan_ipdg_apply_host (pinned host buffers, 32 pipelined slabs)",
+               "bound": "PCIe (about 45 GB/s each way)"}
         del xh, yh
-
-    if world > 1 and peer:
+    elif peer:
+        from stefanproblem_b200.distributed import apply_peer_fused
         # end to end at N GPUs: every rank moves its slab over its own PCIe link (pinned host
         # buffers, H2D of x and D2H of y inside the timed region) around the one fused launch
+        slab, dop = prob.slab, prob.dop
         xh = torch.empty(ndofs_local, dtype=torch.float64).pin_memory()
-        xh.copy_(x.cpu())
+        xh.copy_(prob.x.cpu())
         yh = torch.empty(ndofs_local, dtype=torch.float64).pin_memory()
         n_e2e = max(2, min(args.steps, 10))
-        ybuf = [y, torch.empty_like(y)]
+        ybuf = [prob.y, torch.empty_like(prob.y)]
         d2h, done, copied = torch.cuda.Stream(), [torch.cuda.Event(), torch.cuda.Event()], [None, None]
         work = torch.cuda.Stream()  # not the legacy default stream, which serialises with other streams' copies
 
         def e2e_step(k):
             # the result of step k leaves on a second stream while step k+1's input arrives
             # (PCIe is full duplex); two result buffers
-            b = k & 1
-            slab.wait_released()            # the neighbours are done with my previous vector
+            bb = k & 1
+            slab.begin_write()              # the neighbours are done with my previous vector
             slab.x.copy_(xh, non_blocking=True)
-            if copied[b] is not None:
-                torch.cuda.current_stream().wait_event(copied[b])   # ybuf[b] has left the device
-            apply_peer_fused(dop, slab, ybuf[b])
-            done[b].record()
+            if copied[bb] is not None:
+                torch.cuda.current_stream().wait_event(copied[bb])   # ybuf[b] has left the device
+            apply_peer_fused(dop, slab, ybuf[bb])
+            done[bb].record()
             with torch.cuda.stream(d2h):
-                d2h.wait_event(done[b])
-                yh.copy_(ybuf[b], non_blocking=True)
-                copied[b] = torch.cuda.Event()
-                copied[b].record(d2h)
+                d2h.wait_event(done[bb])
+                yh.copy_(ybuf[bb], non_blocking=True)
+                copied[bb] = torch.cuda.Event()
+                copied[bb].record(d2h)
 
-        barrier()
+        barrier(world)
         with torch.cuda.stream(work):
             e2e_step(0)
-            barrier()
+            barrier(world)
             t0 = time.perf_counter()
             for k in range(n_e2e):
                 e2e_step(k + 1)
-            barrier()
-        dt = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device="cuda")
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": total_dofs / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": total_dofs * 8,
+            barrier(world)
+        dt = max_over_ranks((time.perf_counter() - t0) / n_e2e, world)
+        slab.check()
+        e2e = {"value": total_dofs / dt, "unit": UNIT, "h2d_bytes_per_step": total_dofs * 8,
                "d2h_bytes_per_step": total_dofs * 8, "steps": n_e2e,
-               "api": "PeerSlab + stefan_ipdg_apply_peer per rank (pinned host buffers, each rank over its own PCIe link)"}
+               "api": "PeerSlab + stefan_ipdg_apply_peer per rank (pinned host buffers, each rank over its own PCIe link)",
+               "bound": "host memory system: every rank's slab crosses PCIe twice per step (all GPUs of a box share the "
+                        "host's memory controllers), so this number does not scale with N"}
         del xh, yh
+    prob.close()
+
+    # ---- the other scaling mode and the time loop, as extra fields (not the headline) ----
+    other = None
+    if world > 1 and not args.no_extras:
+        nxg2 = n_x * world if strong else n_x
+        p2 = SlabProblem(p, nxg2, ny, rank, world, want_peer)
+        t2 = torch.tensor([p2.ndofs], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t2, op=dist.ReduceOp.SUM)
+        ms2, g2, _ = timed_steps(p2, max(10, args.steps // 2), args.warmup, use_graph)
+        other = {"scaling": "weak" if strong else "strong", "global_cells": [nxg2, ny], "global_dofs": int(t2.item()),
+                 "ms_per_step": ms2, "value": float(t2.item()) / (ms2 * 1e-3), "unit": UNIT, "cuda_graph": g2}
+        p2.close()
+    step_loop = None
+    if not args.no_extras:
+        step_loop = time_step_loop(p, nxg, ny, rank, world, max(10, args.steps // 2), args.warmup)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -271,31 +465,47 @@ def run_ours(args):
         # N > 1, nccl halos: interior + two edge columns; peer halos: the one apply kernel
         launches = args.steps * (3 if (world > 1 and not peer) else 1)
         if peer:
-            assert int(slab.status.item()) == 0, "a peer-flag wait timed out"
-        partition = (f"{world} column slabs; neighbours' edge columns read over NVLink from CUDA-IPC peer memory "
-                     "inside the apply kernel, which also publishes / waits for / releases the epoch flags: one launch per step") if peer else (
-                     f"{world} column slabs; 1 halo cell column per neighbour over NCCL send/recv, "
-                     "overlapped with the interior columns")
-        if world == 1:
-            partition = "1 slab (no halo)"
+            partition = (f"{world} column slabs of the fixed global mesh (strong scaling)" if strong else
+                         f"{world} column slabs, {n_x} columns per GPU (weak scaling)")
+            partition += ("; neighbours' edge columns read over NVLink from CUDA-IPC peer memory inside the apply kernel, "
+                          "which also publishes / waits for the epoch flags: one launch per step"
+                          + (", the K steps are one CUDA-graph replay per rank" if graphed else ""))
+        elif world > 1:
+            partition = (f"{world} column slabs ({'strong' if strong else 'weak'} scaling); 1 halo cell column per "
+                         "neighbour over NCCL send/recv, overlapped with the interior columns")
+        else:
+            partition = "1 slab (no halo)" + ("; the K steps are one CUDA-graph replay" if graphed else "")
+        nxl = prob.dop.nxl
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
-                "workload": f"IP-DG p={p} matrix-free apply, two-phase circle + Robin interface, "
-                            f"{nxl}x{ny} cells per GPU ({ndofs_local / 1e6:.1f} M dofs per GPU)",
-                "order": p, "cells_per_gpu": [nxl, ny], "global_cells": [nxg, ny],
-                "global_dofs": total_dofs, "partition": partition,
-                "l2": "inputs larger than L2 (x and y are 800 MB each per GPU at the default size)",
+                "workload": f"IP-DG p={p} matrix-free apply, two-phase circle + Robin interface, global mesh "
+                            f"{nxg}x{ny} cells ({total_dofs / 1e6:.1f} M dofs), {nxl}x{ny} cells on rank 0",
+                "order": p, "cells_rank0": [nxl, ny], "global_cells": [nxg, ny],
+                "global_dofs": total_dofs, "partition": partition, "cuda_graph": graphed,
+                "parity_of_workload": PARITY_NOTE,
+                "l2": ("inputs larger than L2: x and y of a rank are "
+                       f"{ndofs_local * 8 / 1e6:.0f} MB each (L2: 126 MB)"),
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": args.traffic_bytes,
                          "peak_source": peak_src, "kernel_ms": kernel_ms,
-                         "algorithmic_bytes_per_dof": ALGO_BYTES_PER_DOF},
-            "clocks": clk.summary(),
+                         "algorithmic_bytes_per_dof": ALGO_BYTES_PER_DOF,
+                         "kernel": f"ipdg_apply_march<{p}, 0> on rank 0's slab ({ndofs_local / 1e6:.1f} M dofs), plain launches"},
+            "clocks": clocks,
             "gpu_launches": launches,
+            "parity_max_rel": parity_rel,
+            "parity": {"max_rel": parity_rel, "tolerance": 1e-13,
+                       "what": ("fused peer halos + march kernel vs NCCL halos + plain per-cell kernel, every rank's slab"
+                                if world > 1 else "march kernel vs plain per-cell kernel"),
+                       "checksum_fused": chk_fused, "checksum_plain": chk_plain},
         }
+        if other is not None:
+            line[other["scaling"]] = other
+        if step_loop is not None:
+            line["step_loop"] = step_loop
         if e2e is not None:
             line["e2e"] = e2e
         if cpu_baseline is not None:
@@ -303,12 +513,25 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
-        if slab is not None:
-            slab.close()
         dist.destroy_process_group()
 
 
 _REF_CACHE = {}
+
+
+def reference_sample_cells():
+    """Cells per side of the CPU sample: the largest of 1024 / 768 / 512 whose COO -> CSR path (about 13 KB per
+    p = 1 cell at its peak) fits a quarter of the host's free memory; 1024^2 cells = 4.2 M dofs, CSR about 1 GB
+    (well outside the caches)."""
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:  # noqa: BLE001
+        avail = 16 << 30
+    for n in (1024, 768, 512):
+        if n * n * 13e3 < 0.25 * avail:
+            return n
+    return 512
 
 
 def _cpu_port(order, n):
@@ -326,55 +549,59 @@ def _cpu_port(order, n):
     return _REF_CACHE[key]
 
 
-def _spmv_rate(C, x, seconds, threads=0):
+def _spmv_time(C, x, reps, threads=0):
     import numpy as np
     y = np.empty_like(x)
-    C.spmv(x, y, threads)
-    reps, t0 = 0, time.perf_counter()
-    while time.perf_counter() - t0 < seconds:
+    t0 = time.perf_counter()
+    for _ in range(reps):
         C.spmv(x, y, threads)
-        reps += 1
-    return C.nrows / ((time.perf_counter() - t0) / reps), reps
+    return (time.perf_counter() - t0) / reps
 
 
-def cpu_port_baseline(order, seconds=6.0, n=512, threads=0):
+def cpu_port_baseline(order, seconds=6.0, n=None, threads=0):
     """The reference's CPU path (COO assembly -> sparse -> A*x) as restated in C, on a
     bounded sample: n x n cells, same physics as the GPU workload, all host threads."""
     from oracle.cport import CIPOracle
+    n = n or (reference_sample_cells() if order == 1 else 512)
     C, x, t_asm = _cpu_port(order, n)
-    rate, reps = _spmv_rate(C, x, seconds, threads)
+    t1 = _spmv_time(C, x, 2, threads)
+    reps = max(3, int(seconds / max(t1, 1e-6)))
+    t = _spmv_time(C, x, reps, threads)
     cores = CIPOracle.max_threads() if threads <= 0 else threads
-    return {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{n}x{n} cells p={order} ({C.nrows / 1e6:.2f} M dofs): CSR SpMV of the "
-                      f"oracle-assembled matrix, {reps} applications; assembly (COO + compress) "
+    return {"value": C.nrows / t, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n}x{n} cells p={order} ({C.nrows / 1e6:.2f} M dofs, CSR {C.nnz * 12 / 1e9:.2f} GB): CSR SpMV of the "
+                      f"oracle-assembled matrix, {reps} applications of {t * 1e3:.2f} ms; assembly (COO + compress) "
                       f"took {t_asm:.1f} s once and is not in the rate",
-            "assembly_seconds": t_asm, "nnz": C.nnz}
+            "assembly_seconds": t_asm, "nnz": C.nnz, "ms_per_apply": t * 1e3}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    C, x, _ = _cpu_port(args.order, 512)
+    n = reference_sample_cells() if args.order == 1 else 512
+    C, x, t_asm = _cpu_port(args.order, n)
     for _ in range(args.warmup):
-        _spmv_rate(C, x, 0.2)
-    # one step = a bounded sample (about 1 s) of applications with all host threads
-    nsteps = max(1, min(args.steps, 10))
-    t0 = time.perf_counter()
-    rates = [_spmv_rate(C, x, 1.0)[0] for _ in range(nsteps)]
-    wall = time.perf_counter() - t0
-    value = sum(rates) / len(rates)
-    b = cpu_port_baseline(args.order, seconds=1.0, n=512)
-    b["value"] = value
+        _spmv_time(C, x, 1)
+    # one step = one application (CSR SpMV with all host threads) of the bounded sample; K steps timed
+    steps = args.steps
+    t = _spmv_time(C, x, steps)
+    value = C.nrows / t
+    from oracle.cport import CIPOracle
+    b = {"value": value, "unit": UNIT, "cores": CIPOracle.max_threads(), "kind": "port",
+         "sample": f"{n}x{n} cells p={args.order} ({C.nrows / 1e6:.2f} M dofs, CSR {C.nnz * 12 / 1e9:.2f} GB): {steps} CSR SpMV "
+                   f"applications of the oracle-assembled matrix with all host threads; assembly {t_asm:.1f} s, not timed",
+         "assembly_seconds": t_asm, "nnz": C.nnz}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / nsteps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * t,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": f"IP-DG p={args.order} two-phase circle + Robin: CPU path of the reference "
                                "(COO assembly -> sparse -> A*x) restated in C (the reference is Julia; "
-                               "no Julia runtime in this image)", "order": args.order,
-                   "timed_steps": nsteps},
+                               f"no Julia runtime in this image); bounded sample {n}x{n} cells, one step = one A*x",
+                   "order": args.order, "sample_cells": [n, n], "sample_dofs": C.nrows,
+                   "parity_of_workload": PARITY_NOTE},
         "cpu_baseline": b,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -388,18 +615,23 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--order", type=int, default=1)
-    ap.add_argument("--nx", type=int, default=0, help="cell columns per GPU")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: --nx is the GLOBAL column count; weak: columns per GPU")
+    ap.add_argument("--nx", type=int, default=0, help="cell columns (global if strong, per GPU if weak)")
     ap.add_argument("--ny", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time plain launches instead of one CUDA-graph replay")
+    ap.add_argument("--no-extras", action="store_true", help="skip the weak-scaling and time-loop fields")
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"], help="N > 1: how the halo columns travel")
     ap.add_argument("--traffic-bytes", type=float, default=None,
                     help="dram bytes per launch from the committed ncu capture (profiles/)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    args.steps = max(args.steps, 1)
     n = {1: 5000, 2: 3334, 3: 2500}[args.order]
     args.nx = args.nx or n
     args.ny = args.ny or n
-    if args.traffic_bytes is None and args.order == 1 and (args.nx, args.ny) == (5000, 5000):
+    if args.traffic_bytes is None and args.order == 1 and (args.nx, args.ny) == (5000, 5000) and args.gpus == 1:
         args.traffic_bytes = PROFILED_TRAFFIC_BYTES
     if args.impl == "reference":
         run_reference(args)

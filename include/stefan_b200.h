@@ -365,9 +365,13 @@ typedef struct {
   uint64_t* my_done;
   const uint64_t* lo_ready;   /* neighbours' my_ready flags in peer memory; NULL where there is none */
   const uint64_t* hi_ready;
-  uint64_t epoch;             /* > 0, increasing */
+  uint64_t epoch;             /* > 0, increasing (ignored, but still > 0, when epoch_dev is given) */
   int32_t timeout_ms;
   int32_t* status;            /* device int32 set to 1 if a wait timed out; may be NULL */
+  /* Optional device-resident epoch (local memory, initialised to the last completed epoch, e.g. 0): the kernel
+   * works with *epoch_dev + 1 and its last CTA stores that value back.  The launch then carries no
+   * per-step host state, so a step captured in a CUDA graph advances the protocol on every replay. */
+  uint64_t* epoch_dev;
 } stefan_peer_sync;
 int stefan_ipdg_apply_peer(stefan_ipdg* h, const double* x, double* y, const double* x_lo, const double* x_hi,
                            const stefan_peer_sync* sync, void* stream);

@@ -59,3 +59,55 @@ def dense_matrix(blocks, slot_nbr):
             if n >= 0:
                 A[c * nf:(c + 1) * nf, n * nf:(n + 1) * nf] += blocks[c, 1 + s]
     return A
+
+
+def assemble_rhs(order, data, f_qp, g_qp, Tm=0.0):
+    """Right-hand side for block data, from the reference's linear forms applied per solution cell:
+    volume source `linear_form` (IP_source_term.jl:97-107), boundary slots `R1 - R2` =
+    pen * linear_form - flux_linear_form (IP_source_term.jl:109-159), slots with a Robin coefficient
+    1/2 lambda Tm * robin_interface_linear_form (IP_robin_interface_source.jl:1-25).
+    f_qp [ncells][nqv]: source at the volume points; g_qp [ncells][nslots][nqf]: boundary data."""
+    basis = LagrangeTensorProductBasis(2, order)
+    nf = basis.nf
+    ncells, nslots = data["slot_nbr"].shape
+    ident = lambda p: p  # noqa: E731
+    rhs = np.zeros((ncells, nf))
+    for c in range(ncells):
+        jac = data["cell_jac"][c]
+        k = data["cell_k"][c]
+        for p, w, fv in zip(data["vol_pts"][c], data["vol_wts"][c], f_qp[c]):
+            if w != 0.0:   # (one point at a time: the sampled value belongs to the point, padding has weight 0)
+                rhs[c] += ip.linear_form(lambda _p, fv=fv: fv, basis, [(p, w)], ident, jac[0] * jac[1])
+        for s in range(nslots):
+            nbr = int(data["slot_nbr"][c, s])
+            keep = data["face_wts"][c, s] != 0.0
+            pts, w = data["face_pts"][c, s][keep], data["face_wts"][c, s][keep]
+            if nbr == -1:
+                pen = data["slot_pen"][c, s]
+                for p, wq, n, gq in zip(pts, w, data["face_normals"][c, s][keep], g_qp[c, s][keep]):
+                    q1 = [(p, wq)]
+                    g = lambda _p, gq=gq: gq  # noqa: E731
+                    rhs[c] += pen * ip.linear_form(g, basis, q1, ident, 1.0)
+                    rhs[c] -= ip.flux_linear_form(g, basis, q1, n, k, ident, jac, 1.0)
+            elif nbr >= 0 and data["slot_lambda"][c, s] != 0.0:
+                quad = list(zip(pts, w))
+                rhs[c] += 0.5 * data["slot_lambda"][c, s] * Tm * ip.robin_interface_linear_form(
+                    basis, quad, np.ones(len(quad)))
+    return rhs.ravel()
+
+
+def l2_error(order, data, u, uex_qp):
+    """(||u_h - u_ex||, ||u_ex||) over the volume points of all solution cells: mesh_L2_error and
+    integral_norm_on_mesh (useful_routines.jl:95-133, :203-221) for per-cell quadratures."""
+    basis = LagrangeTensorProductBasis(2, order)
+    nf = basis.nf
+    e2 = n2 = 0.0
+    for c in range(data["slot_nbr"].shape[0]):
+        jac = data["cell_jac"][c]
+        uc = u[c * nf:(c + 1) * nf]
+        for p, w, ue in zip(data["vol_pts"][c], data["vol_wts"][c], uex_qp[c]):
+            if w == 0.0:
+                continue
+            e2 += (basis(p) @ uc - ue) ** 2 * jac[0] * jac[1] * w
+            n2 += ue ** 2 * jac[0] * jac[1] * w
+    return np.sqrt(e2), np.sqrt(n2)

@@ -51,7 +51,7 @@ class PeerSync(ctypes.Structure):
     """`stefan_peer_sync`."""
     _fields_ = [("my_ready", ctypes.c_void_p), ("my_done", ctypes.c_void_p), ("lo_ready", ctypes.c_void_p),
                 ("hi_ready", ctypes.c_void_p), ("epoch", ctypes.c_uint64), ("timeout_ms", ctypes.c_int32),
-                ("status", ctypes.c_void_p)]
+                ("status", ctypes.c_void_p), ("epoch_dev", ctypes.c_void_p)]
 
 
 class BlocksDims(ctypes.Structure):

@@ -43,7 +43,7 @@ struct ApplyArgs {
   const int8_t* phase;  // padded
   int nx, ny;
   int cbeg, cend;  // columns to produce (a sub-range when the host path pipelines slabs)
-  const int32_t* fix;  // cells the march kernels leave to their tail (see fixup_tail)
+  const int2* fix;  // {cell, face-type code} of the cells the march kernels leave to their tail (see fixup_tail)
   int nfix;
   unsigned zero;  // 0 at run time, unknown at compile time (see ipdg_march.cuh, slot release)
   // peer-memory halos with the ordering fused into the kernel (stefan_ipdg_apply_peer);
@@ -52,7 +52,10 @@ struct ApplyArgs {
   unsigned long long* sync_my_done;          // published by the last CTA: "I am done reading my neighbours"
   const unsigned long long* sync_lo_ready;   // neighbours' ready flags (peer memory)
   const unsigned long long* sync_hi_ready;
-  unsigned long long sync_epoch, sync_timeout_ns;
+  unsigned long long sync_epoch, sync_timeout_ns;  // epoch != 0: peer mode
+  // graph-replayable form: the epoch lives on the device -- the kernel uses *sync_epoch_dev + 1 and
+  // its last CTA stores that back -- so the same captured launch advances the protocol on every replay
+  unsigned long long* sync_epoch_dev;
   int* sync_status;                          // set to 1 if a wait timed out
   unsigned long long* dbg_times;             // development only: per-CTA {start, prologue, loop, end} globaltimer, or null
   // dynamic tail queue: [0] next fix-list index, [1] CTAs finished; both reset by the last CTA
@@ -79,7 +82,12 @@ __device__ __forceinline__ void peer_flag_wait(const unsigned long long* flag, u
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
   for (;;) {
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
-    if (v >= epoch) return;
+    if (v >= epoch) {
+      // the neighbour's column is fetched next by a bulk copy (asynchronous proxy): order the
+      // acquire (generic proxy) before it
+      asm volatile("fence.proxy.async.global;" ::: "memory");
+      return;
+    }
     __nanosleep(100);
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     if (t - t0 > timeout_ns) {
@@ -87,6 +95,14 @@ __device__ __forceinline__ void peer_flag_wait(const unsigned long long* flag, u
       return;
     }
   }
+}
+// the epoch of this launch (call after griddep_wait: the previous launch's last CTA wrote the counter)
+struct ApplyArgs;
+__device__ __forceinline__ unsigned long long peer_epoch(const unsigned long long* epoch_dev, unsigned long long epoch) {
+  if (epoch_dev == nullptr) return epoch;
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(epoch_dev) : "memory");
+  return v + 1;
 }
 __device__ __forceinline__ void peer_flag_publish(unsigned long long* flag, unsigned long long epoch) {
   __threadfence_system();
@@ -160,55 +176,112 @@ __device__ __forceinline__ void step_epilogue(const ApplyArgs& a, const double* 
 
 // Cells the marching loops do not produce (they skip the store): boundary cells and cells
 // next to the other phase.  They are disjoint from what the loops write.  Round 2: the list is
-// a QUEUE -- every warp that is done with its strip takes 32 cells at a time through an atomic
+// a QUEUE -- every warp that is done with its strip takes a batch of cells through an atomic
 // counter until the list is empty, so the warps whose tiles finish first absorb the tail
 // (round 1 gave CTA b the cells b*blockDim .. : the first CTAs of the grid, which also own
-// the boundary column, paid for all of it -- up to 34 us at LDG order 3, 457^2 cells).
-// One thread per cell, general tables, neighbours straight from global memory.
+// the boundary column, paid for all of it) -- and the cells are processed COOPERATIVELY: one
+// lane per NODE, NF lanes per cell (8 / 3 / 2 cells per warp at orders 1 / 2 / 3).  The line
+// operators of ipdg_tables.h become warp shuffles along the x- / y-lines of the cell, every
+// load and store is coalesced, and a cell costs ~150 instructions at ~40 registers instead of a
+// whole per-thread ip_cell_rows with run-time table indices (10-25 us per 32-cell chunk).
 template <int P, int MODE>
 __device__ __forceinline__ void fixup_tail(const IpTab<P>& tab, const ApplyArgs& a) {
-  constexpr int NF = (P + 1) * (P + 1);
+  constexpr int N1 = P + 1, NF = N1 * N1;
+  constexpr int CW = 32 / NF;      // cells per warp and round
+  constexpr int BATCH = 4;         // rounds per queue access; their loads are issued together
   if (a.nfix <= 0) return;
   const int lane = threadIdx.x & 31;
+  const bool lane_live = lane < CW * NF;
+  const int grp = lane_live ? lane / NF : 0;          // (idle lanes shadow group 0 and never store)
+  const int node = lane_live ? lane - grp * NF : 0;
+  const int ix = node / N1, iy = node % N1;
+  const int gbase = grp * NF;
+  unsigned long long epoch = 0;
+  if (a.sync_epoch != 0) epoch = peer_epoch(a.sync_epoch_dev, a.sync_epoch);
   for (;;) {
     unsigned base = 0;
-    if (lane == 0) base = atomicAdd(a.tail_ctr, 32u);
+    if (lane == 0) base = atomicAdd(a.tail_ctr, (unsigned)(CW * BATCH));
     base = __shfl_sync(0xffffffffu, base, 0);
     if (base >= (unsigned)a.nfix) break;
-    const int t = (int)base + lane;
-    if (t >= a.nfix) continue;
-    const int64_t cell = a.fix[t];
-    const int i = (int)(cell / a.ny), j = (int)(cell % a.ny);
-    const int s = phase_at(a.phase, a.ny, i, j);
-    const int sL = phase_at(a.phase, a.ny, i - 1, j), sR = phase_at(a.phase, a.ny, i + 1, j);
-    const int sD = phase_at(a.phase, a.ny, i, j - 1), sU = phase_at(a.phase, a.ny, i, j + 1);
-    double X[NF], XL[NF], XR[NF], XD[NF], XU[NF], out[NF];
-    const double* xc = a.x + cell * NF;
-    const double* pl = (i > 0) ? xc - (size_t)a.ny * NF : a.x_lo + (size_t)j * NF;
-    const double* pr = (i < a.nx - 1) ? xc + (size_t)a.ny * NF : a.x_hi + (size_t)j * NF;
-    if (a.sync_epoch != 0) {  // peer halos: the neighbour's column must be published
-      if (i == 0 && sL && a.sync_lo_ready) peer_flag_wait(a.sync_lo_ready, a.sync_epoch, a.sync_timeout_ns, a.sync_status);
-      if (i == a.nx - 1 && sR && a.sync_hi_ready) peer_flag_wait(a.sync_hi_ready, a.sync_epoch, a.sync_timeout_ns, a.sync_status);
-    }
+    // ---- all loads of the batch first (two dependent levels: record, then dofs) ----
+    int2 rec[BATCH];
+    double X[BATCH], XL[BATCH], XR[BATCH], XD[BATCH], XU[BATCH];
+    [[maybe_unused]] double Bv[BATCH];
 #pragma unroll
-    for (int k = 0; k < NF; ++k) {
-      X[k] = xc[k];
-      XL[k] = sL ? pl[k] : 0.0;
-      XR[k] = sR ? pr[k] : 0.0;
-      XD[k] = sD ? xc[k - NF] : 0.0;
-      XU[k] = sU ? xc[k + NF] : 0.0;
-    }
-    ip_cell_rows<P>(tab, s == 1 ? 0 : 1, ip_face_type(s, sL), ip_face_type(s, sR),
-                    ip_face_type(s, sD), ip_face_type(s, sU), X, XL, XR, XD, XU, out);
-    if constexpr (MODE == 1) {
-      double B[NF];
+    for (int rd = 0; rd < BATCH; ++rd) rec[rd] = a.fix[min((int)base + rd * CW + grp, a.nfix - 1)];
 #pragma unroll
-      for (int k = 0; k < NF; ++k) B[k] = a.b ? a.b[cell * NF + k] : 0.0;
-      step_epilogue<P>(a, X, B, out);
+    for (int rd = 0; rd < BATCH; ++rd) {
+      const int64_t cell = rec[rd].x;
+      const int code = rec[rd].y;
+      const int i = (int)(cell / a.ny), j = (int)(cell - (int64_t)i * a.ny);
+      const int tL = (code >> 1) & 3, tR = (code >> 3) & 3, tD = (code >> 5) & 3, tU = (code >> 7) & 3;
+      const double* xc = a.x + cell * NF;
+      const double* pl = (i > 0) ? xc - (size_t)a.ny * NF : a.x_lo + (size_t)j * NF;
+      const double* pr = (i < a.nx - 1) ? xc + (size_t)a.ny * NF : a.x_hi + (size_t)j * NF;
+      if (a.sync_epoch != 0) {  // peer halos: the neighbour's column must be published
+        if (i == 0 && tL != T_BDRY && a.sync_lo_ready) peer_flag_wait(a.sync_lo_ready, epoch, a.sync_timeout_ns, a.sync_status);
+        if (i == a.nx - 1 && tR != T_BDRY && a.sync_hi_ready) peer_flag_wait(a.sync_hi_ready, epoch, a.sync_timeout_ns, a.sync_status);
+      }
+      // this lane's node of the cell and of its four neighbours (zeros where there is none)
+      X[rd] = xc[node];
+      XL[rd] = tL != T_BDRY ? pl[node] : 0.0;
+      XR[rd] = tR != T_BDRY ? pr[node] : 0.0;
+      XD[rd] = tD != T_BDRY ? xc[node - NF] : 0.0;
+      XU[rd] = tU != T_BDRY ? xc[node + NF] : 0.0;
+      if constexpr (MODE == 1) Bv[rd] = a.b ? a.b[cell * NF + node] : 0.0;
     }
-    double* yc = a.y + cell * NF;
+    // ---- the line operators of each cell, by shuffles along its x- / y-lines ----
 #pragma unroll
-    for (int k = 0; k < NF; ++k) yc[k] = out[k];
+    for (int rd = 0; rd < BATCH; ++rd) {
+      const int t0 = (int)base + rd * CW;
+      if (t0 < a.nfix) {  // (warp-uniform)
+        const bool live = lane_live && (t0 + grp) < a.nfix;
+        const int code = rec[rd].y;
+        const int S = code & 1, tL = (code >> 1) & 3, tR = (code >> 3) & 3, tD = (code >> 5) & 3, tU = (code >> 7) & 3;
+        const double* Dx = tab.D[0][S][tL][tR];
+        const double* Dy = tab.D[1][S][tD][tU];
+        const double* L0x = tab.L0[0][S][tL];
+        const double* Rpx = tab.Rp[0][S][tR];
+        const double* L0y = tab.L0[1][S][tD];
+        const double* Rpy = tab.Rp[1][S][tU];
+        double ax = 0.0, sl = 0.0, sr = 0.0, ay = 0.0, sd = 0.0, su = 0.0;
+#pragma unroll
+        for (int b = 0; b < N1; ++b) {
+          const int lx = gbase + b * N1 + iy, ly = gbase + ix * N1 + b;
+          ax += Dx[ix * N1 + b] * __shfl_sync(0xffffffffu, X[rd], lx);
+          sl += L0x[b] * __shfl_sync(0xffffffffu, XL[rd], lx);
+          sr += Rpx[b] * __shfl_sync(0xffffffffu, XR[rd], lx);
+          ay += Dy[iy * N1 + b] * __shfl_sync(0xffffffffu, X[rd], ly);
+          sd += L0y[b] * __shfl_sync(0xffffffffu, XD[rd], ly);
+          su += Rpy[b] * __shfl_sync(0xffffffffu, XU[rd], ly);
+        }
+        const double xlP = __shfl_sync(0xffffffffu, XL[rd], gbase + P * N1 + iy);
+        const double xr0 = __shfl_sync(0xffffffffu, XR[rd], gbase + iy);
+        const double xdP = __shfl_sync(0xffffffffu, XD[rd], gbase + ix * N1 + P);
+        const double xu0 = __shfl_sync(0xffffffffu, XU[rd], gbase + ix * N1);
+        ax += (ix == 0) ? sl : tab.Lc[0][S][tL][ix] * xlP;
+        ax += (ix == P) ? sr : tab.Rc[0][S][tR][ix] * xr0;
+        ay += (iy == 0) ? sd : tab.Lc[1][S][tD][iy] * xdP;
+        ay += (iy == P) ? su : tab.Rc[1][S][tU][iy] * xu0;
+        double out = 0.0;
+#pragma unroll
+        for (int c = 0; c < N1; ++c) {
+          out += tab.My[iy * N1 + c] * __shfl_sync(0xffffffffu, ax, gbase + ix * N1 + c);
+          out += tab.Mx[ix * N1 + c] * __shfl_sync(0xffffffffu, ay, gbase + c * N1 + iy);
+        }
+        if constexpr (MODE == 1) {
+          // step epilogue: out <- X + scale (Minv (x) Minv) (b - out), again along the lines
+          const double r = Bv[rd] - out;
+          double tt = 0.0, z = 0.0;
+#pragma unroll
+          for (int c = 0; c < N1; ++c) tt += a.minv[iy][c] * __shfl_sync(0xffffffffu, r, gbase + ix * N1 + c);
+#pragma unroll
+          for (int c = 0; c < N1; ++c) z += a.minv[ix][c] * __shfl_sync(0xffffffffu, tt, gbase + c * N1 + iy);
+          out = X[rd] + a.step_scale * z;
+        }
+        if (live) a.y[(int64_t)rec[rd].x * NF + node] = out;
+      }
+    }
   }
 }
 
@@ -222,7 +295,11 @@ __device__ __forceinline__ void march_finish(const ApplyArgs& a) {
       a.tail_ctr[0] = 0;
       a.tail_ctr[1] = 0;
       __threadfence();
-      if (a.sync_epoch != 0) peer_flag_publish(a.sync_my_done, a.sync_epoch);
+      if (a.sync_epoch != 0) {
+        const unsigned long long epoch = peer_epoch(a.sync_epoch_dev, a.sync_epoch);
+        peer_flag_publish(a.sync_my_done, epoch);
+        if (a.sync_epoch_dev != nullptr) *a.sync_epoch_dev = epoch;  // every CTA has read it: all are done
+      }
     }
   }
 }
@@ -438,7 +515,10 @@ int stefan_ipdg_create(const stefan_ipdg_params* p, const int8_t* phase, const i
   cudaError_t e = cudaMalloc(&h->phase_dev, pn);
   if (e == cudaSuccess) e = cudaMemcpy(h->phase_dev, ph.data(), pn, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = h->plan.build(ph.data(), p->nx, p->ny, march_warps(p->order));
-  h->plan.mixed_cost_q = p->order == 1 ? 1 : 2;  // measured (quarter columns), see MarchPlan::segments
+  h->plan.mixed_cost_q = p->order == 1 ? 1 : (p->order == 2 ? 2 : 4);  // measured (quarter columns), see MarchPlan::segments
+  // tiles that touch a neighbouring slab get two columns less: they may have to wait for its flag
+  h->plan.edge_lo_q = h->has_lo ? 8 : 0;
+  h->plan.edge_hi_q = h->has_hi ? 8 : 0;
   if (e != cudaSuccess) { h->plan.destroy(); if (h->phase_dev) cudaFree(h->phase_dev); delete h; return fail(ST_CUDA_ERROR, "stefan_ipdg_create: %s", cudaGetErrorString(e)); }
   *out = reinterpret_cast<stefan_ipdg*>(h);
   return ST_OK;
@@ -514,6 +594,7 @@ int stefan_ipdg_apply_peer(stefan_ipdg* hv, const double* x, double* y, const do
   a.sync_lo_ready = reinterpret_cast<const unsigned long long*>(sync->lo_ready);
   a.sync_hi_ready = reinterpret_cast<const unsigned long long*>(sync->hi_ready);
   a.sync_epoch = sync->epoch;
+  a.sync_epoch_dev = reinterpret_cast<unsigned long long*>(sync->epoch_dev);
   a.sync_timeout_ns = (unsigned long long)sync->timeout_ms * 1000000ull;
   a.sync_status = sync->status;
   return dispatch_apply(h, a, 0, static_cast<cudaStream_t>(stream));
@@ -551,6 +632,7 @@ int stefan_ipdg_step(stefan_ipdg* hv, const double* u, double* unew, const doubl
     a.sync_lo_ready = reinterpret_cast<const unsigned long long*>(sync->lo_ready);
     a.sync_hi_ready = reinterpret_cast<const unsigned long long*>(sync->hi_ready);
     a.sync_epoch = sync->epoch;
+    a.sync_epoch_dev = reinterpret_cast<unsigned long long*>(sync->epoch_dev);
     a.sync_timeout_ns = (unsigned long long)sync->timeout_ms * 1000000ull;
     a.sync_status = sync->status;
   }

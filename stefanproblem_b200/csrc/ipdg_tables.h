@@ -250,8 +250,10 @@ inline int ip_face_type(int s, int sn) {
 // Rows of one cell.  X* are the NF = (P+1)^2 dofs (a = ix (P+1) + iy) of the cell
 // and of its left / right / down / up neighbours (zeros where there is none).
 // All table indices are either compile-time constants (interior fast path) or
-// per-thread values (general path); the body is the same.
-template <int P>
+// per-thread values (general path); the body is the same.  ROLLED keeps the two outer loop
+// levels as loops (the march kernels' tail: code that runs once per warp must be small, every
+// instruction line of an unrolled body is a cold instruction-cache miss).
+template <int P, bool ROLLED = false>
 #if defined(__CUDACC__)
 __host__ __device__ __forceinline__
 #else
@@ -273,9 +275,9 @@ void ip_cell_rows(const IpTab<P>& tab, int s, int tL, int tR, int tD, int tU,
   const double* Rpy = tab.Rp[1][s][tU];
   const double* Rcy = tab.Rc[1][s][tU];
   double ax[N1 * N1], ay[N1 * N1];
-#pragma unroll
+#pragma unroll(ROLLED ? 1 : N1)
   for (int ix = 0; ix < N1; ++ix) {
-#pragma unroll
+#pragma unroll(ROLLED ? 1 : N1)
     for (int iy = 0; iy < N1; ++iy) {
       // x-line through node (ix, iy): couples ix' in K, L, R at fixed iy
       double v = 0.0;
@@ -313,9 +315,9 @@ void ip_cell_rows(const IpTab<P>& tab, int s, int tL, int tR, int tD, int tU,
       ay[ix * N1 + iy] = u;
     }
   }
-#pragma unroll
+#pragma unroll(ROLLED ? 1 : N1)
   for (int ix = 0; ix < N1; ++ix) {
-#pragma unroll
+#pragma unroll(ROLLED ? 1 : N1)
     for (int iy = 0; iy < N1; ++iy) {
       double v = 0.0;
 #pragma unroll

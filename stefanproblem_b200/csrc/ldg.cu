@@ -392,6 +392,11 @@ int stefan_ldg_create(const stefan_ldg_params* p, const int8_t* phase, const int
   cudaError_t e = cudaMalloc(&h->phase_dev, pn);
   if (e == cudaSuccess) e = cudaMemcpy(h->phase_dev, ph.data(), pn, cudaMemcpyHostToDevice);
   h->variant = ldg_march_variant(p->order, (int64_t)p->nx * p->ny);
+  // cost of a column in which a strip runs both phase bodies, in quarter columns (MarchPlan::segments).
+  // The loops are memory-bound at every order: a least-squares fit of the per-CTA loop times of the
+  // 457^2 order-3 mesh (profiles/r2_ldg_cta_times.txt) gives 4.15 us per column, +0.29 us per mixed
+  // column and 4.3 us per tile -- the second body hides behind the loads.
+  h->plan.mixed_cost_q = p->order == 2 ? 2 : 1;
   if (e == cudaSuccess) e = h->plan.build(ph.data(), p->nx, p->ny, ldg_march_warps(p->order, h->variant));
   if (e != cudaSuccess) {
     h->plan.destroy();

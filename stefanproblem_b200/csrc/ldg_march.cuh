@@ -71,7 +71,7 @@ struct LdgMarchArgs {
   double* y;
   const int8_t* phase;  // padded
   int nx, ny;
-  const int32_t* fix;
+  const int2* fix;  // {cell, face-type code}, see MarchPlan::fix_dev
   int nfix;
   unsigned zero;  // 0 at run time, unknown at compile time (slot release, see ipdg_march.cuh)
   unsigned long long* dbg_times;  // development only: per-CTA {start, prologue end, loop end, end} globaltimer, or null
@@ -88,52 +88,115 @@ __device__ __forceinline__ void ldg_dbg_stamp(const LdgMarchArgs& a, int slot) {
   }
 }
 
-// cells the loop does not store: one thread per cell, general tables.  The list is a queue:
-// every warp that is done with its strip takes 32 cells at a time until it is empty (see
-// fixup_tail in ipdg.cu).
+// Cells the loop does not store (boundary cells, cells next to the other phase).  The list is a
+// QUEUE: every warp that is done with its strip takes a batch of cells through an atomic counter
+// until the list is empty, so the warps whose tiles finish first absorb the tail.
+// Round 2: COOPERATIVE form -- one lane per NODE, NF lanes per cell (8 / 3 / 2 cells per warp at
+// orders 1 / 2 / 3).  A lane holds its node's (T, q_x, q_y); the 1-D line operators of
+// ldg_tables.h become warp shuffles along the x- / y-lines of the cell, loads and stores are
+// coalesced (24 contiguous bytes per lane), about 40 registers and ~200 instructions per cell
+// instead of one thread working through a whole cell with run-time table indices (measured in
+// round 1 / 2: 10-25 us per 32-cell chunk at orders 2, 3 -- the kernel's critical path).
 template <int P>
 __device__ __forceinline__ void ldg_fixup_tail(const LdgTab<P>& tab, const LdgMarchArgs& a) {
   constexpr int N1 = P + 1, NF = N1 * N1, CD = 3 * NF;
+  constexpr int CW = 32 / NF;      // cells per warp and round
+  constexpr int BATCH = 4;         // rounds per queue access; their loads are issued together
   if (a.nfix <= 0) return;
   const int lane_t = threadIdx.x & 31;
+  const bool lane_live = lane_t < CW * NF;
+  const int grp = lane_live ? lane_t / NF : 0;          // (idle lanes shadow group 0 and never store)
+  const int node = lane_live ? lane_t - grp * NF : 0;
+  const int ix = node / N1, iy = node % N1;
+  const int gbase = grp * NF;
   for (;;) {
     unsigned base = 0;
-    if (lane_t == 0) base = atomicAdd(a.tail_ctr, 32u);
+    if (lane_t == 0) base = atomicAdd(a.tail_ctr, (unsigned)(CW * BATCH));
     base = __shfl_sync(0xffffffffu, base, 0);
     if (base >= (unsigned)a.nfix) break;
-    const int t = (int)base + lane_t;
-    if (t >= a.nfix) continue;
-    const int64_t cell = a.fix[t];
-    const int i = (int)(cell / a.ny), j = (int)(cell % a.ny);
-    const int s = ldg_phase_at(a.phase, a.ny, i, j);
-    const int sL = ldg_phase_at(a.phase, a.ny, i - 1, j), sR = ldg_phase_at(a.phase, a.ny, i + 1, j);
-    const int sD = ldg_phase_at(a.phase, a.ny, i, j - 1), sU = ldg_phase_at(a.phase, a.ny, i, j + 1);
-    double U[CD], out[CD];
-    double tLT[N1], tLQ[N1], tRT[N1], tRQ[N1], tDT[N1], tDQ[N1], tUT[N1], tUQ[N1];
-    const double* xc = a.x + cell * CD;
-    const double* pl = (i > 0) ? xc - (size_t)a.ny * CD : a.x_lo + (size_t)j * CD;
-    const double* pr = (i < a.nx - 1) ? xc + (size_t)a.ny * CD : a.x_hi + (size_t)j * CD;
+    // ---- all loads of the batch first (two dependent levels: record, then dofs) ----
+    int2 rec[BATCH];
+    double T[BATCH], Qx[BATCH], Qy[BATCH], nxT[BATCH], nxQ[BATCH], nyT[BATCH], nyQ[BATCH];
 #pragma unroll
-    for (int k = 0; k < CD; ++k) U[k] = xc[k];
-    // of the neighbours only the face nodes' T and normal flux component (zeros where there is none)
+    for (int rd = 0; rd < BATCH; ++rd) rec[rd] = a.fix[min((int)base + rd * CW + grp, a.nfix - 1)];
 #pragma unroll
-    for (int q = 0; q < N1; ++q) {
-      const int nl = 3 * (P * N1 + q), nr = 3 * (0 * N1 + q);
-      tLT[q] = sL ? pl[nl] : 0.0;
-      tLQ[q] = sL ? pl[nl + 1] : 0.0;
-      tRT[q] = sR ? pr[nr] : 0.0;
-      tRQ[q] = sR ? pr[nr + 1] : 0.0;
-      const int nd = 3 * (q * N1 + P), nu = 3 * (q * N1 + 0);
-      tDT[q] = sD ? xc[nd - CD] : 0.0;
-      tDQ[q] = sD ? xc[nd + 2 - CD] : 0.0;
-      tUT[q] = sU ? xc[nu + CD] : 0.0;
-      tUQ[q] = sU ? xc[nu + 2 + CD] : 0.0;
+    for (int rd = 0; rd < BATCH; ++rd) {
+      const int64_t cell = rec[rd].x;
+      const int code = rec[rd].y;
+      const int i = (int)(cell / a.ny), j = (int)(cell - (int64_t)i * a.ny);
+      const int tL = (code >> 1) & 3, tR = (code >> 3) & 3, tD = (code >> 5) & 3, tU = (code >> 7) & 3;
+      const double* xc = a.x + cell * CD;
+      const double* pl = (i > 0) ? xc - (size_t)a.ny * CD : a.x_lo + (size_t)j * CD;
+      const double* pr = (i < a.nx - 1) ? xc + (size_t)a.ny * CD : a.x_hi + (size_t)j * CD;
+      T[rd] = xc[3 * node];
+      Qx[rd] = xc[3 * node + 1];
+      Qy[rd] = xc[3 * node + 2];
+      // the neighbours' face-node T and normal flux component, on the lanes of the face nodes (a lane is on
+      // at most one x-face and one y-face unless N1 = 2, where ix = 0 and ix = P are different lanes anyway)
+      nxT[rd] = nxQ[rd] = nyT[rd] = nyQ[rd] = 0.0;
+      if (ix == 0 && tL != T_BDRY) { nxT[rd] = pl[3 * (P * N1 + iy)]; nxQ[rd] = pl[3 * (P * N1 + iy) + 1]; }
+      if (ix == P && tR != T_BDRY) { nxT[rd] = pr[3 * iy]; nxQ[rd] = pr[3 * iy + 1]; }
+      if (iy == 0 && tD != T_BDRY) { nyT[rd] = xc[3 * (ix * N1 + P) - CD]; nyQ[rd] = xc[3 * (ix * N1 + P) + 2 - CD]; }
+      if (iy == P && tU != T_BDRY) { nyT[rd] = xc[3 * (ix * N1) + CD]; nyQ[rd] = xc[3 * (ix * N1) + 2 + CD]; }
     }
-    ldg_rows_streamed_general<P>(tab, s == 1 ? 0 : 1, ip_face_type(s, sL), ip_face_type(s, sR), ip_face_type(s, sD),
-                                 ip_face_type(s, sU), U, tLT, tLQ, tRT, tRQ, tDT, tDQ, tUT, tUQ, out);
-    double* yc = a.y + cell * CD;
 #pragma unroll
-    for (int k = 0; k < CD; ++k) yc[k] = out[k];
+    for (int rd = 0; rd < BATCH; ++rd) {
+      const int t0 = (int)base + rd * CW;
+      if (t0 < a.nfix) {  // (warp-uniform)
+        const bool live = lane_live && (t0 + grp) < a.nfix;
+        const int code = rec[rd].y;
+        const int S = code & 1, tL = (code >> 1) & 3, tR = (code >> 3) & 3, tD = (code >> 5) & 3, tU = (code >> 7) & 3;
+        const double k = tab.kk[S];
+        // ---- 1-D operators along the x-line (fixed iy) and the y-line (fixed ix) of the node
+        double cqx = 0.0, g_x = 0.0, mqx = 0.0, cqy = 0.0, g_y = 0.0, mqy = 0.0;
+#pragma unroll
+        for (int b = 0; b < N1; ++b) {
+          const int lx = gbase + b * N1 + iy, ly = gbase + ix * N1 + b;
+          const double tx = __shfl_sync(0xffffffffu, T[rd], lx), qx = __shfl_sync(0xffffffffu, Qx[rd], lx);
+          const double ty = __shfl_sync(0xffffffffu, T[rd], ly), qy = __shfl_sync(0xffffffffu, Qy[rd], ly);
+          const double cx = tab.C[ix * N1 + b], cy = tab.C[iy * N1 + b];
+          cqx += cx * tx;
+          g_x += cx * qx;
+          mqx += tab.Mx[ix * N1 + b] * qx;
+          cqy += cy * ty;
+          g_y += cy * qy;
+          mqy += tab.My[iy * N1 + b] * qy;
+        }
+        g_x *= k;
+        g_y *= k;
+        // face terms on the face nodes' lanes (side 0 = low, 1 = high); N1 >= 2, so a node is on one x-face at most
+        if (ix == 0 || ix == P) {
+          const int side = ix == 0 ? 0 : 1, ty_ = ix == 0 ? tL : tR;
+          cqx += tab.sqK[0][side][ty_] * T[rd] + tab.sqN[0][side][ty_] * nxT[rd];
+          g_x += tab.tqK[S][0][side][ty_] * Qx[rd] + tab.tqN[S][0][side][ty_] * nxQ[rd] + tab.tpK[0][side][ty_] * T[rd] +
+                 tab.tpN[0][side][ty_] * nxT[rd];
+        }
+        if (iy == 0 || iy == P) {
+          const int side = iy == 0 ? 0 : 1, ty_ = iy == 0 ? tD : tU;
+          cqy += tab.sqK[1][side][ty_] * T[rd] + tab.sqN[1][side][ty_] * nyT[rd];
+          g_y += tab.tqK[S][1][side][ty_] * Qy[rd] + tab.tqN[S][1][side][ty_] * nyQ[rd] + tab.tpK[1][side][ty_] * T[rd] +
+                 tab.tpN[1][side][ty_] * nyT[rd];
+        }
+        const double a_x = cqx + mqx, a_y = cqy + mqy;
+        // ---- mass matrix across the other direction
+        double oT = 0.0, oqx = 0.0, oqy = 0.0;
+#pragma unroll
+        for (int c = 0; c < N1; ++c) {
+          const int ly = gbase + ix * N1 + c, lx = gbase + c * N1 + iy;
+          const double my = tab.My[iy * N1 + c], mx = tab.Mx[ix * N1 + c];
+          oqx += my * __shfl_sync(0xffffffffu, a_x, ly);
+          oT += my * __shfl_sync(0xffffffffu, g_x, ly);
+          oqy += mx * __shfl_sync(0xffffffffu, a_y, lx);
+          oT += mx * __shfl_sync(0xffffffffu, g_y, lx);
+        }
+        if (live) {
+          double* yc = a.y + (int64_t)rec[rd].x * CD + 3 * node;
+          yc[0] = oT;
+          yc[1] = oqx;
+          yc[2] = oqy;
+        }
+      }
+    }
   }
 }
 

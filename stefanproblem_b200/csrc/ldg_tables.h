@@ -167,10 +167,12 @@ void ldg_cell_rows(const LdgTab<P>& tab, int s, int tL, int tR, int tD, int tU,
 // The same rows (phase index S, face types tL .. tU) in the form the march kernel uses: the neighbours enter as face traces (T and the normal flux
 // component at the face nodes), and the sum-factorisation intermediates are never stored --
 // every x-line (fixed iy) / y-line (fixed ix) result is scattered straight into the output
-// accumulators through the 1-D mass matrix.  Live data: the cell (3 NF), the output (3 NF) and
+// accumulators through the 1-D mass matrix.  ROLLED keeps the two outer loop levels as loops:
+// the kernels' tail runs this code ONCE per warp, and straight-line code that is executed once
+// is one instruction-cache miss after the other (measured: 8-10 us per tail chunk at orders 2, 3).  Live data: the cell (3 NF), the output (3 NF) and
 // 2 (P+1) line temporaries, instead of 4 NF intermediates on top (order 3: 110 instead of
 // 160 doubles, which is what fits the register file).
-template <int P>
+template <int P, bool ROLLED = false>
 #if defined(__CUDACC__)
 __host__ __device__ __forceinline__
 #else
@@ -185,12 +187,12 @@ void ldg_rows_streamed_general(const LdgTab<P>& tab, const int S, const int tL, 
   constexpr int N1 = P + 1;
   constexpr int NF = N1 * N1;
   const double k = tab.kk[S];
-#pragma unroll
+#pragma unroll(ROLLED ? 1 : 3 * NF)
   for (int a = 0; a < 3 * NF; ++a) out[a] = 0.0;
   // x-lines
-#pragma unroll
+#pragma unroll(ROLLED ? 1 : N1)
   for (int iy = 0; iy < N1; ++iy) {
-#pragma unroll
+#pragma unroll(ROLLED ? 1 : N1)
     for (int ix = 0; ix < N1; ++ix) {
       double cqx = 0.0, g_x = 0.0, mqx = 0.0;
 #pragma unroll
@@ -222,9 +224,9 @@ void ldg_rows_streamed_general(const LdgTab<P>& tab, const int S, const int tL, 
     }
   }
   // y-lines
-#pragma unroll
+#pragma unroll(ROLLED ? 1 : N1)
   for (int ix = 0; ix < N1; ++ix) {
-#pragma unroll
+#pragma unroll(ROLLED ? 1 : N1)
     for (int iy = 0; iy < N1; ++iy) {
       double cqy = 0.0, g_y = 0.0, mqy = 0.0;
 #pragma unroll

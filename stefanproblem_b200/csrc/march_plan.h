@@ -46,12 +46,13 @@ struct MarchPlan {
   std::vector<SegCache> seg_cache;
   int4* runs_dev = nullptr;
   int* run_ofs_dev = nullptr;
-  int32_t* fix_dev = nullptr;
+  int2* fix_dev = nullptr;  // {cell, code}: code = phase index | tL << 1 | tR << 3 | tD << 5 | tU << 7 (face types)
   int nfix = 0;
 
   std::vector<int4> runs_host;   // what compute() produced (kept: small, and the tests read it)
   std::vector<int> run_ofs_host;
   std::vector<int32_t> fix_host;
+  std::vector<int32_t> fix_code_host;  // per fix cell, see fix_dev
 
   // ph: padded phase array (nx+2) x (ny+2), 0 = no cell.  Returns a cudaError_t.
   cudaError_t build(const int8_t* ph, int nx_, int ny_, int group_warps_) {
@@ -64,9 +65,12 @@ struct MarchPlan {
     if (e == cudaSuccess) e = cudaMalloc(&run_ofs_dev, run_ofs.size() * sizeof(int));
     if (e == cudaSuccess)
       e = cudaMemcpy(run_ofs_dev, run_ofs.data(), run_ofs.size() * sizeof(int), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess && nfix > 0) e = cudaMalloc(&fix_dev, fix.size() * sizeof(int32_t));
-    if (e == cudaSuccess && nfix > 0)
-      e = cudaMemcpy(fix_dev, fix.data(), fix.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && nfix > 0) e = cudaMalloc(&fix_dev, fix.size() * sizeof(int2));
+    if (e == cudaSuccess && nfix > 0) {
+      std::vector<int2> rec(fix.size());
+      for (size_t k = 0; k < fix.size(); ++k) rec[k] = make_int2(fix[k], fix_code_host[k]);
+      e = cudaMemcpy(fix_dev, rec.data(), rec.size() * sizeof(int2), cudaMemcpyHostToDevice);
+    }
     return e;
   }
 
@@ -82,6 +86,7 @@ struct MarchPlan {
     std::vector<int4>& runs = runs_host;
     std::vector<int>& run_ofs = run_ofs_host;
     fix.clear();
+    fix_code_host.clear();
     runs.clear();
     run_ofs.assign(nstrips + 1, 0);  // [nstrips] = total: the kernels bisect a strip's list
     seg_cache.clear();
@@ -97,6 +102,10 @@ struct MarchPlan {
           if (s == 2) pmask[(size_t)sidx * nx + i] |= 1u << lane;
         } else {
           fix.push_back((int32_t)((int64_t)i * ny + j));
+          // face types as ip_face_type(s, neighbour): 0 same phase, 1 other phase, 2 no cell
+          auto ft = [&](int8_t sn) { return sn == 0 ? 2 : (sn == s ? 0 : 1); };
+          fix_code_host.push_back((s == 2 ? 1 : 0) | ft(col[j - ld]) << 1 | ft(col[j + ld]) << 3 | ft(col[j - 1]) << 5 |
+                                  ft(col[j + 1]) << 7);
         }
       }
     }
@@ -161,6 +170,8 @@ struct MarchPlan {
       if (edge_lo_q) edge_lo_q = atoi(e);
       if (edge_hi_q) edge_hi_q = atoi(e);
     }
+    const int max_ctas_key = max_ctas;
+    if (const char* e = getenv("STEFAN_CTA_BUDGET")) max_ctas = std::max(1, std::min(max_ctas, atoi(e)));  // tuning
     const int ng = ngroups, gw = group_warps, ncol = cend - cbeg;
     // cumulative cost per group: cum[g][c - cbeg] = cost of columns [cbeg, c)
     std::vector<int64_t> cum((size_t)ng * (ncol + 1), 0);
@@ -222,7 +233,7 @@ struct MarchPlan {
     SegCache c;
     c.cbeg = cbeg;
     c.cend = cend;
-    c.max_ctas = max_ctas;
+    c.max_ctas = max_ctas_key;
     c.n = (int)tiles.size() > kMaxMarchCtas ? -1 : (int)tiles.size();
     std::memset(&c.tab, 0, sizeof(c.tab));
     for (int k = 0; k < std::max(c.n, 0); ++k) c.tab.e[k] = tiles[k];

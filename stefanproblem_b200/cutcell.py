@@ -1,0 +1,390 @@
+"""Cut-cell data for the element-block path: a uniform Cartesian mesh cut by a CIRCLE.
+
+In the reference the geometry of cut cells comes from three un-vendored packages
+(`CutCellDG.CutMesh` / `CellQuadratures` / `FaceQuadratures` / `InterfaceQuadratures` over
+`ImplicitDomainQuadrature`, level set = Q2 interpolant of `circle_distance_function`,
+StefanDG/useful_routines.jl:40-44).  This module is an independent host-side generator of the
+SAME KIND of data for the analytic circle, in the layout of `stefan_blocks_data`
+(include/stefan_b200.h), so that the reference's cylinder studies
+(InteriorPenalty/cylindrical_bc_tests/IP_test_cylindrical_bc_convergence.jl,
+robin_cylindrical_bc_tests/IP_test_cylndrical_robin_bc_convergence.jl) run end to end on the
+block path.  Parity with the reference's cut-cell CSVs is at DISCRETISATION level (same scheme,
+different geometry approximation and quadrature rules), never digit for digit.
+
+Conventions (as in the reference): level set phi = R - |x - c| (> 0 inside); phase +1 (k1) is
+phi > 0, phase -1 (k2) is phi < 0; a cut cell carries two solution cells, (cell, +1) and
+(cell, -1), coupled through an interface slot whose normal points out of the + side.
+
+Quadrature ("height function" rules, exact geometry): a line parallel to an axis meets the
+disk in ONE chord, so the part of a cell inside the disk is a union of strips
+{t in [ta, tb], s in [a(t), b(t)]} with smooth a, b once [ta, tb] is split at the kinks (where a
+chord end passes a cell corner or the chord appears); tensor Gauss rules on the strips.  The
+outer variable is the one along which the interface is a graph of bounded slope.
+
+Slots of a solution cell: 0 bottom, 1 right, 2 top, 3 left, 4 interface; further slots (5 ...)
+hold the faces of tiny neighbouring pieces that were merged into the cell (see `merge`).
+"""
+import numpy as np
+
+SLOT_STEP = [(0, -1), (1, 0), (0, 1), (-1, 0)]     # neighbour cell of slots 0..3
+SLOT_NORMAL = [(0.0, -1.0), (1.0, 0.0), (0.0, 1.0), (-1.0, 0.0)]
+OPPOSITE = [2, 3, 0, 1]
+
+
+def _gauss(n):
+    return np.polynomial.legendre.leggauss(n)
+
+
+def _chord(t, c_t, c_s, R):
+    """Chord of the disk on the line {coordinate_t = t}: (s_lo, s_hi) or None."""
+    d2 = R * R - (t - c_t) ** 2
+    if d2 <= 0.0:
+        return None
+    s = np.sqrt(d2)
+    return c_s - s, c_s + s
+
+
+def _split_interval(lo, hi, a, b, tol):
+    """[lo, hi] cut by the chord [a, b] -> (inside intervals, outside intervals)."""
+    if a is None:
+        return [], [(lo, hi)]
+    ia, ib = max(lo, a), min(hi, b)
+    if ib - ia <= tol:
+        return [], [(lo, hi)]
+    ins = [(ia, ib)]
+    out = []
+    if ia - lo > tol:
+        out.append((lo, ia))
+    if hi - ib > tol:
+        out.append((ib, hi))
+    return ins, out
+
+
+def disk_rect_rules(x0, x1, y0, y1, cx, cy, R, nq):
+    """Quadrature of the parts of the rectangle inside / outside the disk.
+    Returns ((pts_in [n,2], w_in [n]), (pts_out, w_out)) in physical coordinates."""
+    xc, yc = 0.5 * (x0 + x1), 0.5 * (y0 + y1)
+    swap = abs(xc - cx) < abs(yc - cy)       # interface is a graph over x: outer variable x
+    if swap:
+        x0, x1, y0, y1, cx, cy = y0, y1, x0, x1, cy, cx
+    # outer variable t = y in [y0, y1], inner s = x in [x0, x1]
+    h = max(x1 - x0, y1 - y0)
+    tol = 1e-13 * h
+    cuts = [y0, y1]
+    for xe in (x0, x1):
+        d2 = R * R - (xe - cx) ** 2
+        if d2 > 0:
+            cuts += [cy - np.sqrt(d2), cy + np.sqrt(d2)]
+    cuts += [cy - R, cy + R]
+    cuts = sorted(set(c for c in cuts if y0 <= c <= y1))
+    g, w = _gauss(nq)
+    pin, win, pout, wout = [], [], [], []
+    for ta, tb in zip(cuts[:-1], cuts[1:]):
+        if tb - ta <= tol:
+            continue
+        tq = 0.5 * (ta + tb) + 0.5 * (tb - ta) * g
+        twq = 0.5 * (tb - ta) * w
+        for t, tw in zip(tq, twq):
+            ch = _chord(t, cy, cx, R)
+            ins, outs = _split_interval(x0, x1, ch[0] if ch else None, ch[1] if ch else None, tol)
+            for (lst_p, lst_w, ivs) in ((pin, win, ins), (pout, wout, outs)):
+                for a, b in ivs:
+                    sq = 0.5 * (a + b) + 0.5 * (b - a) * g
+                    lst_p.append(np.stack([sq, np.full(nq, t)], axis=1))
+                    lst_w.append(0.5 * (b - a) * w * tw)
+
+    def pack(lp, lw):
+        if not lp:
+            return np.zeros((0, 2)), np.zeros(0)
+        p, ww = np.concatenate(lp), np.concatenate(lw)
+        if swap:
+            p = p[:, ::-1].copy()
+        return p, ww
+    return pack(pin, win), pack(pout, wout)
+
+
+def edge_rules(p0, p1, cx, cy, R, nq):
+    """Gauss rules on the parts of the segment p0 -> p1 (axis parallel) inside / outside the disk.
+    Returns ((pts_in, w_in), (pts_out, w_out)); weights are physical lengths."""
+    p0, p1 = np.asarray(p0, float), np.asarray(p1, float)
+    horizontal = abs(p1[1] - p0[1]) < abs(p1[0] - p0[0])
+    L = np.abs(p1 - p0).max()
+    tol = 1e-13 * L
+    if horizontal:
+        lo, hi = sorted((p0[0], p1[0]))
+        ch = _chord(p0[1], cy, cx, R)
+    else:
+        lo, hi = sorted((p0[1], p1[1]))
+        ch = _chord(p0[0], cx, cy, R)
+    ins, outs = _split_interval(lo, hi, ch[0] if ch else None, ch[1] if ch else None, tol)
+    g, w = _gauss(nq)
+
+    def rule(ivs):
+        P, W = [], []
+        for a, b in ivs:
+            s = 0.5 * (a + b) + 0.5 * (b - a) * g
+            P.append(np.stack([s, np.full(nq, p0[1])], 1) if horizontal else np.stack([np.full(nq, p0[0]), s], 1))
+            W.append(0.5 * (b - a) * w)
+        if not P:
+            return np.zeros((0, 2)), np.zeros(0)
+        return np.concatenate(P), np.concatenate(W)
+    return rule(ins), rule(outs)
+
+
+def arc_rule(x0, x1, y0, y1, cx, cy, R, nq):
+    """Gauss rule on the part of the circle inside the rectangle: points, weights (arc length),
+    outward (radial) unit normals."""
+    h = max(x1 - x0, y1 - y0)
+    tol = 1e-12 * h
+    ang = []
+    for xe in (x0, x1):
+        d2 = R * R - (xe - cx) ** 2
+        if d2 > 0:
+            for sgn in (-1.0, 1.0):
+                y = cy + sgn * np.sqrt(d2)
+                if y0 - tol <= y <= y1 + tol:
+                    ang.append(np.arctan2(y - cy, xe - cx))
+    for ye in (y0, y1):
+        d2 = R * R - (ye - cy) ** 2
+        if d2 > 0:
+            for sgn in (-1.0, 1.0):
+                x = cx + sgn * np.sqrt(d2)
+                if x0 - tol <= x <= x1 + tol:
+                    ang.append(np.arctan2(ye - cy, x - cx))
+    ang = sorted(set(np.round(ang, 14)))
+    arcs = []
+    if not ang:
+        if x0 < cx - R and cx + R < x1 and y0 < cy - R and cy + R < y1:
+            arcs.append((-np.pi, np.pi))
+    else:
+        for a, b in zip(ang, ang[1:] + [ang[0] + 2 * np.pi]):
+            if b - a <= 1e-13:
+                continue
+            m = 0.5 * (a + b)
+            px, py = cx + R * np.cos(m), cy + R * np.sin(m)
+            if x0 - tol <= px <= x1 + tol and y0 - tol <= py <= y1 + tol:
+                arcs.append((a, b))
+    g, w = _gauss(nq)
+    P, W, N = [], [], []
+    for a, b in arcs:
+        th = 0.5 * (a + b) + 0.5 * (b - a) * g
+        n = np.stack([np.cos(th), np.sin(th)], 1)
+        P.append(np.array([cx, cy]) + R * n)
+        W.append(0.5 * (b - a) * w * R)
+        N.append(n)
+    if not P:
+        return np.zeros((0, 2)), np.zeros(0), np.zeros((0, 2))
+    return np.concatenate(P), np.concatenate(W), np.concatenate(N)
+
+
+class CircleCutMesh:
+    """Uniform nx x ny mesh on [x0, x0 + widths] cut by the circle |x - center| = radius.
+
+    Attributes after construction:
+      sol_cell [nsol], sol_phase [nsol]   geometric cell / phase of every solution cell
+      sol_id[(cell, phase)]               solution-cell id
+      data                                dict of NumPy arrays in the stefan_blocks_data layout
+      vol_xy [nsol][nqv][2]               physical coordinates of the volume points (source sampling)
+      face_xy [nsol][nslots][nqf][2]      physical coordinates of the face points (boundary data)
+      merged_into[sol]                    -1, or the solution cell a tiny piece was merged into
+    `merge_fraction`: pieces whose area is below this fraction of a cell are merged into the
+    same-phase neighbour across their longest face (the role of CutCellDG.MergedMesh!)."""
+
+    def __init__(self, x0, widths, nelements, center, radius, numqp, k1, k2, penalty, lam=0.0,
+                 merge_fraction=0.0, face_numqp=None):
+        self.x0 = np.asarray(x0, float)
+        self.widths = np.asarray(widths, float)
+        self.nx, self.ny = int(nelements[0]), int(nelements[1])
+        self.h = self.widths / np.array([self.nx, self.ny], float)
+        self.center, self.R = np.asarray(center, float), float(radius)
+        self.nq = int(numqp)
+        self.nqf1 = int(face_numqp or numqp)
+        self.k = {1: float(k1), -1: float(k2)}
+        self.penalty, self.lam = float(penalty), float(lam)
+        self.merge_fraction = float(merge_fraction)
+        self._build()
+
+    # ------------------------------------------------------------------ geometry
+    def cell_box(self, c):
+        i, j = divmod(c, self.ny)
+        xa = self.x0[0] + i * self.h[0]
+        ya = self.x0[1] + j * self.h[1]
+        return xa, xa + self.h[0], ya, ya + self.h[1]
+
+    def _ref(self, c, pts):
+        xa, xb, ya, yb = self.cell_box(c)
+        ctr = np.array([0.5 * (xa + xb), 0.5 * (ya + yb)])
+        return (np.asarray(pts) - ctr) / (0.5 * self.h)
+
+    def _build(self):
+        nx, ny, nq = self.nx, self.ny, self.nq
+        ncell = nx * ny
+        cx, cy = self.center
+        area = self.h[0] * self.h[1]
+        pieces = {}          # (cell, phase) -> dict(vol=(pts, w), faces=[(pts, w)] * 4, area)
+        iface = {}           # cell -> (pts, w, normals)
+        eps = 1e-12
+        for c in range(ncell):
+            xa, xb, ya, yb = self.cell_box(c)
+            (pi, wi), (po, wo) = disk_rect_rules(xa, xb, ya, yb, cx, cy, self.R, nq)
+            ain, aout = wi.sum(), wo.sum()
+            corners = [((xa, ya), (xb, ya)), ((xb, ya), (xb, yb)), ((xa, yb), (xb, yb)), ((xa, ya), (xa, yb))]
+            fr = [edge_rules(p0, p1, cx, cy, self.R, self.nqf1) for p0, p1 in corners]
+            if ain > eps * area:
+                pieces[(c, 1)] = dict(vol=(pi, wi), faces=[f[0] for f in fr], area=ain)
+            if aout > eps * area:
+                pieces[(c, -1)] = dict(vol=(po, wo), faces=[f[1] for f in fr], area=aout)
+            if (c, 1) in pieces and (c, -1) in pieces:
+                iface[c] = arc_rule(xa, xb, ya, yb, cx, cy, self.R, self.nqf1)
+        self.pieces, self.iface = pieces, iface
+        self.cell_sign = np.array([0 if ((c, 1) in pieces and (c, -1) in pieces) else (1 if (c, 1) in pieces else -1)
+                                   for c in range(ncell)], dtype=np.int8)
+        # ---- merging of tiny pieces
+        host = {}
+        if self.merge_fraction > 0:
+            for key, pc in pieces.items():
+                if pc["area"] >= self.merge_fraction * area:
+                    continue
+                c, s = key
+                i, j = divmod(c, ny)
+                best, best_len = None, 0.0
+                for f, (di, dj) in enumerate(SLOT_STEP):
+                    ii, jj = i + di, j + dj
+                    if not (0 <= ii < nx and 0 <= jj < ny):
+                        continue
+                    nb = (ii * ny + jj, s)
+                    if nb not in pieces or pieces[nb]["area"] < self.merge_fraction * area:
+                        continue
+                    ln = pc["faces"][f][1].sum()
+                    if ln > best_len:
+                        best, best_len = (nb, f), ln
+                if best is not None:
+                    host[key] = best
+        self.host = host
+        # ---- solution cells (pieces that own dofs)
+        owners = [k for k in sorted(pieces, key=lambda t: (t[0], -t[1])) if k not in host]
+        self.sol_id = {k: n for n, k in enumerate(owners)}
+        self.sol_cell = np.array([k[0] for k in owners])
+        self.sol_phase = np.array([k[1] for k in owners])
+        nsol = len(owners)
+        sol_of = lambda key: self.sol_id[host[key][0]] if key in host else self.sol_id[key]  # noqa: E731
+        frame = lambda key: host[key][0][0] if key in host else key[0]   # geometric cell whose reference frame is used  # noqa: E731
+        # ---- gather per solution cell: volume points, and face groups keyed by neighbour solution cell
+        vol = [[] for _ in range(nsol)]
+        groups = [dict() for _ in range(nsol)]   # sol -> {(kind, nbr_sol): [(pts_phys, w, normals, nbr_frame_cell)]}
+        order_keys = [[] for _ in range(nsol)]
+        def add(sol, slot_hint, nbr_sol, pts, w, normals, nbr_frame):
+            if len(w) == 0:
+                return
+            key = (slot_hint, nbr_sol)
+            if key not in groups[sol]:
+                groups[sol][key] = []
+                order_keys[sol].append(key)
+            groups[sol][key].append((pts, w, normals, nbr_frame))
+        for key, pc in pieces.items():
+            c, s = key
+            me = sol_of(key)
+            vol[me].append(pc["vol"])
+            i, j = divmod(c, ny)
+            merged = key in host
+            for f, (di, dj) in enumerate(SLOT_STEP):
+                pts, w = pc["faces"][f]
+                if len(w) == 0 or w.sum() <= 1e-13 * self.h.max():
+                    continue
+                ii, jj = i + di, j + dj
+                nrm = np.tile(np.array(SLOT_NORMAL[f]), (len(w), 1))
+                if not (0 <= ii < nx and 0 <= jj < ny):
+                    add(me, f if not merged else 100 + f, -1, pts, w, nrm, -1)
+                    continue
+                nbk = (ii * ny + jj, s)
+                if nbk not in pieces:
+                    continue       # (a sliver below the tolerance on the other side)
+                nb_sol = sol_of(nbk)
+                if nb_sol == me:
+                    continue       # the face between a merged piece and its host is interior to the solution cell
+                add(me, f if not merged and nbk not in host else 100 + f, nb_sol, pts, w, nrm, frame(nbk))
+            if c in iface:
+                pts, w, nrm = iface[c]
+                other = sol_of((c, -s))
+                if other != me and len(w):
+                    add(me, 4 if not merged and (c, -s) not in host else 104, other, pts, w,
+                        nrm if s == 1 else -nrm, frame((c, -s)))
+        # slots: own faces 0..3 and interface 4 keep their index; everything else is appended
+        slot_lists = []
+        for sol in range(nsol):
+            fixed = {}
+            extra = []
+            for key in order_keys[sol]:
+                hint = key[0]
+                if hint < 100 and hint not in fixed:
+                    fixed[hint] = key
+                else:
+                    extra.append(key)
+            slots = [fixed.get(sidx) for sidx in range(5)] + extra
+            slot_lists.append(slots)
+        nslots = max(5, max(len(s) for s in slot_lists))
+        nqv = max(sum(len(w) for _, w in v) for v in vol)
+        nqf = 1
+        for sol in range(nsol):
+            for key in slot_lists[sol]:
+                if key is not None:
+                    nqf = max(nqf, sum(len(g[1]) for g in groups[sol][key]))
+        self.nsol, self.nslots, self.nqv, self.nqf = nsol, nslots, nqv, nqf
+        d = {
+            "vol_pts": np.zeros((nsol, nqv, 2)), "vol_wts": np.zeros((nsol, nqv)),
+            "cell_jac": np.tile(0.5 * self.h, (nsol, 1)), "cell_k": np.array([self.k[int(s)] for s in self.sol_phase]),
+            "slot_nbr": np.full((nsol, nslots), -2, dtype=np.int32),
+            "face_pts": np.zeros((nsol, nslots, nqf, 2)), "face_nbr_pts": np.zeros((nsol, nslots, nqf, 2)),
+            "face_wts": np.zeros((nsol, nslots, nqf)), "face_normals": np.zeros((nsol, nslots, nqf, 2)),
+            "slot_pen": np.zeros((nsol, nslots)), "slot_lambda": np.zeros((nsol, nslots)),
+        }
+        self.vol_xy = np.zeros((nsol, nqv, 2))
+        self.face_xy = np.zeros((nsol, nslots, nqf, 2))
+        self.slot_is_interface = np.zeros((nsol, nslots), dtype=bool)
+        detj = 0.25 * area
+        for sol in range(nsol):
+            c = int(self.sol_cell[sol])
+            p = np.concatenate([v[0] for v in vol[sol]])
+            w = np.concatenate([v[1] for v in vol[sol]])
+            n = len(w)
+            d["vol_pts"][sol, :n] = self._ref(c, p)
+            d["vol_wts"][sol, :n] = w / detj           # the kernels multiply by detjac = jx jy
+            self.vol_xy[sol, :n] = p
+            for sidx, key in enumerate(slot_lists[sol]):
+                if key is None:
+                    continue
+                hint, nb_sol = key
+                gl = groups[sol][key]
+                p = np.concatenate([g[0] for g in gl])
+                w = np.concatenate([g[1] for g in gl])
+                nr = np.concatenate([g[2] for g in gl])
+                n = len(w)
+                d["slot_nbr"][sol, sidx] = nb_sol
+                d["face_pts"][sol, sidx, :n] = self._ref(c, p)
+                if nb_sol >= 0:
+                    d["face_nbr_pts"][sol, sidx, :n] = self._ref(int(self.sol_cell[nb_sol]), p)
+                d["face_wts"][sol, sidx, :n] = w
+                d["face_normals"][sol, sidx, :n] = nr
+                d["slot_pen"][sol, sidx] = self.penalty
+                is_if = hint in (4, 104)
+                self.slot_is_interface[sol, sidx] = is_if
+                d["slot_lambda"][sol, sidx] = self.lam if is_if else 0.0
+                self.face_xy[sol, sidx, :n] = p
+        self.data = d
+
+    # ------------------------------------------------------------------ sampling helpers
+    def sample_source(self, f1, f2):
+        """[nsol][nqv] values of the two-phase source (f1 on +1 cells, f2 on -1 cells; callables of (x, y))."""
+        x, y = self.vol_xy[..., 0], self.vol_xy[..., 1]
+        plus = (self.sol_phase == 1)[:, None]
+        return np.where(plus, np.broadcast_to(f1(x, y), x.shape), np.broadcast_to(f2(x, y), x.shape)) * (self.data["vol_wts"] != 0)
+
+    def sample_boundary(self, g):
+        """[nsol][nslots][nqf] boundary data at the points of the boundary slots (0 elsewhere)."""
+        x, y = self.face_xy[..., 0], self.face_xy[..., 1]
+        bd = (self.data["slot_nbr"] == -1)[..., None]
+        return np.where(bd & (self.data["face_wts"] != 0), np.broadcast_to(g(x, y), x.shape), 0.0)
+
+    def sample_exact(self, u):
+        x, y = self.vol_xy[..., 0], self.vol_xy[..., 1]
+        return np.broadcast_to(u(x, y), x.shape) * (self.data["vol_wts"] != 0)

@@ -283,11 +283,12 @@ class IPOperator:
                                                         col_begin, col_end, algo, _stream_ptr(stream)))
         return out
 
-    def interface_sums(self, u, u_lo=None, u_hi=None, stream=None):
+    def interface_sums(self, u, u_lo=None, u_hi=None, stream=None, out=None):
         """[length, int lambda (Tm - {T}), int (k1 dnT1 - k2 dnT2), int {T}] over the interface
         faces owned by this slab (device tensor of 4 doubles)."""
         import torch
-        out = torch.empty(4, dtype=torch.float64, device="cuda")
+        if out is None:
+            out = torch.empty(4, dtype=torch.float64, device="cuda")
         _lib.check(_lib.lib().stefan_ipdg_interface_sums(self._h, _ptr(u), _ptr(u_lo), _ptr(u_hi), _ptr(out),
                                                          _stream_ptr(stream)))
         return out

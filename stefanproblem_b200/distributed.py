@@ -169,36 +169,51 @@ class _DevArray:
 
 
 class PeerSlab:
-    """A slab vector in peer-mappable memory plus the flags that order the neighbours' reads.
+    """Slab vectors in peer-mappable memory plus the flags that order the neighbours' reads.
 
-    Layout of the allocation: [n doubles][pad to 128 B][ready flag u64][consumed flag u64].
-    Collective over the process group (handles are all-gathered)."""
+    Layout of the allocation: nbuf x [n doubles, padded to 128 B][ready flag u64][consumed flag u64].
+    `x` is buffer 0 (`bufs[k]` the others: a time loop alternates between two).  Collective over
+    the process group (handles are all-gathered).
+
+    Protocol (see stefan_ipdg_apply_peer / stefan_ipdg_step in include/stefan_b200.h): the flags belong to
+    the RANK, not to a buffer.  Epoch k of a rank's ready flag says "my kernel of epoch k has started", i.e.
+    everything my stream wrote before it is final AND my kernel of epoch k-1 -- the last one that read my
+    neighbours' vectors -- is complete.  The fused kernels wait for the neighbours' epoch-k flag before
+    they read a halo column and before they store the slab's own edge columns, which is all a two-buffer
+    time loop needs.  A caller that overwrites a slab vector by other means (a copy, its own kernel)
+    calls `begin_write()` first."""
 
     FLAG_BYTES = 128
 
-    def __init__(self, n, rank, world):
+    def __init__(self, n, rank, world, nbuf=1):
         import torch
         import torch.distributed as dist
         from . import _lib
         L = _lib.lib()
-        self.n, self.rank, self.world = int(n), rank, world
-        self._flag_off = (self.n * 8 + 127) // 128 * 128
+        self.n, self.rank, self.world, self.nbuf = int(n), rank, world, int(nbuf)
+        self._stride = (self.n * 8 + 127) // 128 * 128
+        self._flag_off = self._stride * self.nbuf
         nbytes = self._flag_off + self.FLAG_BYTES
         p = ctypes.c_void_p()
         hbuf = ctypes.create_string_buffer(64)
         _lib.check(L.stefan_peer_alloc(nbytes, ctypes.byref(p), hbuf))
         self._ptr = p.value
-        self.x = torch.as_tensor(_DevArray(self._ptr, self.n), device="cuda")
+        self.bufs = [torch.as_tensor(_DevArray(self._ptr + k * self._stride, self.n), device="cuda")
+                     for k in range(self.nbuf)]
+        self.x = self.bufs[0]
         self.status = torch.zeros(1, dtype=torch.int32, device="cuda")
+        # device-resident epoch (graph-replayable launches, see stefan_peer_sync.epoch_dev)
+        self.epoch_dev = torch.zeros(1, dtype=torch.int64, device="cuda")
         handles = [None] * world
-        dist.all_gather_object(handles, (bytes(hbuf.raw), self.n))
+        dist.all_gather_object(handles, (bytes(hbuf.raw), self.n, self.nbuf))
         self._peers = {}
         for r in (rank - 1, rank + 1):
             if 0 <= r < world:
                 q = ctypes.c_void_p()
                 _lib.check(L.stefan_peer_open(handles[r][0], ctypes.byref(q)))
-                n_r = handles[r][1]
-                self._peers[r] = (q.value, n_r, (n_r * 8 + 127) // 128 * 128)
+                n_r, nbuf_r = handles[r][1], handles[r][2]
+                stride_r = (n_r * 8 + 127) // 128 * 128
+                self._peers[r] = (q.value, n_r, stride_r * nbuf_r, stride_r)
         self.epoch = 0
 
     # addresses -----------------------------------------------------------------
@@ -206,13 +221,34 @@ class PeerSlab:
         return self._ptr + self._flag_off + 8 * which
 
     def peer_flag(self, r, which):
-        base, _, off = self._peers[r]
+        base, _, off, _ = self._peers[r]
         return base + off + 8 * which
 
-    def peer_column(self, r, col_len, last):
-        """Address of the neighbour r's first (last=False) / last (last=True) cell column."""
-        base, n_r, _ = self._peers[r]
-        return base + (8 * (n_r - col_len) if last else 0)
+    def peer_column(self, r, col_len, last, buf=0):
+        """Address of the neighbour r's first (last=False) / last (last=True) cell column of its buffer `buf`."""
+        base, n_r, _, stride_r = self._peers[r]
+        return base + buf * stride_r + (8 * (n_r - col_len) if last else 0)
+
+    def sync_block(self, rank, world, timeout_ms=5000, device_epoch=False):
+        """The `stefan_peer_sync` of the NEXT epoch for the fused kernels.  device_epoch=True: the epoch
+        lives on the device (`epoch_dev`), the launch can be captured in a CUDA graph and replayed."""
+        from . import _lib
+        lo_f = self.peer_flag(rank - 1, 0) if rank > 0 else None
+        hi_f = self.peer_flag(rank + 1, 0) if rank < world - 1 else None
+        if device_epoch:
+            return _lib.PeerSync(self.my_flag(0), self.my_flag(1), lo_f, hi_f, 1, int(timeout_ms),
+                                 self.status.data_ptr(), self.epoch_dev.data_ptr())
+        self.epoch += 1
+        return _lib.PeerSync(self.my_flag(0), self.my_flag(1), lo_f, hi_f, self.epoch, int(timeout_ms),
+                             self.status.data_ptr(), None)
+
+    def to_device_epochs(self):
+        """Continue the epoch count on the device (before graph-captured / device_epoch=True launches)."""
+        self.epoch_dev.fill_(self.epoch)
+
+    def to_host_epochs(self):
+        """Back to host-side epochs after device_epoch=True launches (synchronises the device)."""
+        self.epoch = int(self.epoch_dev.item())
 
     # ordering ------------------------------------------------------------------
     def publish(self, stream=None):
@@ -244,37 +280,83 @@ class PeerSlab:
             _lib.check(_lib.lib().stefan_peer_wait(ctypes.c_void_p(self.peer_flag(r, 1)), self.epoch, timeout_ms,
                                                    ctypes.c_void_p(self.status.data_ptr()), _stream_ptr(stream)))
 
+    def begin_write(self, stream=None, timeout_ms=5000):
+        """Write-after-read guard: call before overwriting a slab vector that the neighbours read in the
+        current epoch (a host upload, an update kernel).  Enqueues the wait for their `done` flags; no-op
+        before the first epoch."""
+        if self.epoch > 0:
+            self.wait_released(stream, timeout_ms)
+
+    def check(self, collective=True):
+        """Raise on EVERY rank if a flag wait timed out anywhere (stale halos must not go unnoticed).
+        Synchronises the device; collective=True all-reduces the status over the process group."""
+        import torch
+        import torch.distributed as dist
+        st = self.status.clone()
+        if collective and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(st, op=dist.ReduceOp.MAX)
+        if int(st.item()) != 0:
+            raise RuntimeError("a peer-flag wait timed out (a neighbour did not publish its epoch): "
+                               "the halo columns of that application are stale")
+
     def close(self):
         from . import _lib
         L = _lib.lib()
-        for q, _, _ in self._peers.values():
+        for q, _, _, _ in self._peers.values():
             L.stefan_peer_close(ctypes.c_void_p(q))
         self._peers = {}
         if self._ptr:
             self.x = None
+            self.bufs = []
             L.stefan_peer_free(ctypes.c_void_p(self._ptr))
             self._ptr = None
 
 
-def apply_peer_fused(dop, slab, out, timeout_ms=5000):
-    """out = A x for the slab vector `slab.x`: ONE kernel launch and nothing else on the stream.
-    The kernel publishes the slab's next epoch when it starts, its warps wait for the
-    neighbours' epoch right before they fetch the neighbours' edge columns over NVLink, and
-    its last CTA releases them (stefan_ipdg_apply_peer)."""
+def step_peer_fused(dop, slab, src, dst, b, dt, timeout_ms=5000, device_epoch=False):
+    """slab.bufs[dst] = u + dt Minv (b - A u) with u = slab.bufs[src]: ONE launch (stefan_ipdg_step, peer form).
+    The neighbours' edge columns of THEIR buffer `src` are read over NVLink inside the kernel."""
     from . import _lib
     from .cutcelldg import _stream_ptr
     col = dop.halo.col
-    slab.epoch += 1
-    lo = hi = lo_f = hi_f = None
-    if dop.rank > 0:
-        lo = ctypes.c_void_p(slab.peer_column(dop.rank - 1, col, last=True))
-        lo_f = slab.peer_flag(dop.rank - 1, 0)
-    if dop.rank < dop.world - 1:
-        hi = ctypes.c_void_p(slab.peer_column(dop.rank + 1, col, last=False))
-        hi_f = slab.peer_flag(dop.rank + 1, 0)
-    sync = _lib.PeerSync(slab.my_flag(0), slab.my_flag(1), lo_f, hi_f, slab.epoch, int(timeout_ms),
-                         slab.status.data_ptr())
-    _lib.check(_lib.lib().stefan_ipdg_apply_peer(dop.op._h, ctypes.c_void_p(slab.x.data_ptr()),
+    lo = ctypes.c_void_p(slab.peer_column(dop.rank - 1, col, last=True, buf=src)) if dop.rank > 0 else None
+    hi = ctypes.c_void_p(slab.peer_column(dop.rank + 1, col, last=False, buf=src)) if dop.rank < dop.world - 1 else None
+    sync = slab.sync_block(dop.rank, dop.world, timeout_ms, device_epoch)
+    _lib.check(_lib.lib().stefan_ipdg_step(dop.op._h, ctypes.c_void_p(slab.bufs[src].data_ptr()),
+                                           ctypes.c_void_p(slab.bufs[dst].data_ptr()),
+                                           ctypes.c_void_p(b.data_ptr()) if b is not None else None, float(dt),
+                                           lo, hi, ctypes.byref(sync), _stream_ptr()))
+    return slab.bufs[dst]
+
+
+def interface_sums_peer(dop, slab, buf, out, timeout_ms=5000):
+    """Front-velocity sums (stefan_ipdg_interface_sums) of slab.bufs[buf] right after the fused kernel of the
+    current epoch wrote it: the neighbours' edge columns are read from peer memory once THEIR kernel of this
+    epoch is complete (their `done` flag, published by its last CTA).  `out`: 4 doubles on the device
+    (this rank's part; all-reduce it)."""
+    from . import _lib
+    from .cutcelldg import _stream_ptr
+    col = dop.halo.col
+    slab.wait_released(timeout_ms=timeout_ms)   # neighbours' done flags of the current epoch
+    lo = ctypes.c_void_p(slab.peer_column(dop.rank - 1, col, last=True, buf=buf)) if dop.rank > 0 else None
+    hi = ctypes.c_void_p(slab.peer_column(dop.rank + 1, col, last=False, buf=buf)) if dop.rank < dop.world - 1 else None
+    _lib.check(_lib.lib().stefan_ipdg_interface_sums(dop.op._h, ctypes.c_void_p(slab.bufs[buf].data_ptr()), lo, hi,
+                                                     ctypes.c_void_p(out.data_ptr()), _stream_ptr()))
+    return out
+
+
+def apply_peer_fused(dop, slab, out, timeout_ms=5000, device_epoch=False, buf=0):
+    """out = A x for the slab vector `slab.bufs[buf]`: ONE kernel launch and nothing else on the stream.
+    The kernel publishes the slab's next epoch when it starts, its warps wait for the
+    neighbours' epoch right before they fetch the neighbours' edge columns over NVLink, and
+    its last CTA releases them (stefan_ipdg_apply_peer).  device_epoch=True keeps the epoch on the
+    device so that the launch can be captured in a CUDA graph and replayed."""
+    from . import _lib
+    from .cutcelldg import _stream_ptr
+    col = dop.halo.col
+    lo = ctypes.c_void_p(slab.peer_column(dop.rank - 1, col, last=True, buf=buf)) if dop.rank > 0 else None
+    hi = ctypes.c_void_p(slab.peer_column(dop.rank + 1, col, last=False, buf=buf)) if dop.rank < dop.world - 1 else None
+    sync = slab.sync_block(dop.rank, dop.world, timeout_ms, device_epoch)
+    _lib.check(_lib.lib().stefan_ipdg_apply_peer(dop.op._h, ctypes.c_void_p(slab.bufs[buf].data_ptr()),
                                                  ctypes.c_void_p(out.data_ptr()), lo, hi, ctypes.byref(sync),
                                                  _stream_ptr()))
     return out

@@ -15,7 +15,8 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from stefanproblem_b200 import cutcelldg as cc  # noqa: E402
 from stefanproblem_b200.distributed import (DistributedIPOperator, DistributedLDGOperator, PeerSlab,  # noqa: E402
-                                            apply_peer, apply_peer_fused, slab_range)
+                                            apply_peer, apply_peer_fused, interface_sums_peer, slab_range,
+                                            step_peer_fused)
 
 
 def column_phase(nxg, ny, i):
@@ -145,6 +146,43 @@ def main():
         assert float((sums - sums_ref).abs().max()) <= 1e-9 * float(sums_ref.abs().max())
         torch.cuda.synchronize()
         assert int(slab.status.item()) == 0, "a peer wait timed out"
+        dist.barrier()
+        slab.close()
+        # the same loop with the FUSED step kernel (stefan_ipdg_step, peer form): two buffers alternate and the only
+        # ordering is the kernels' own flag protocol.  First half eager (host-side epochs), second half as CUDA-graph
+        # replays of a captured pair of steps (device-resident epochs); interface sums of the last iterate.
+        slab = PeerSlab(dop.ndofs, rank, world, nbuf=2)
+        slab.bufs[0].copy_(u0[sl])
+        half = nsteps // 2
+        for k in range(half):
+            step_peer_fused(dop, slab, k & 1, (k + 1) & 1, bloc, dt)
+        torch.cuda.synchronize()
+        dist.barrier()
+        slab.to_device_epochs()
+        st = torch.cuda.Stream()
+        with torch.cuda.stream(st):
+            step_peer_fused(dop, slab, half & 1, (half + 1) & 1, bloc, dt, device_epoch=True)       # (warm-up of the mode;
+            step_peer_fused(dop, slab, (half + 1) & 1, half & 1, bloc, dt, device_epoch=True)       #  two real steps)
+            st.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr, stream=st):
+                step_peer_fused(dop, slab, half & 1, (half + 1) & 1, bloc, dt, device_epoch=True)
+                step_peer_fused(dop, slab, (half + 1) & 1, half & 1, bloc, dt, device_epoch=True)
+            for _ in range((nsteps - half - 2) // 2):
+                gr.replay()
+        torch.cuda.synchronize()
+        slab.to_host_epochs()
+        done_steps = half + 2 + 2 * ((nsteps - half - 2) // 2)
+        for k in range(done_steps, nsteps):
+            step_peer_fused(dop, slab, k & 1, (k + 1) & 1, bloc, dt)
+        ufin = slab.bufs[nsteps & 1]
+        assert float((ufin - uf[sl]).norm()) <= 1e-10 * float(uf[sl].norm()), "fused peer time loop differs from one GPU"
+        worst = max(worst, float((ufin - uf[sl]).norm() / uf[sl].norm()) * 1e-3)
+        sums2 = torch.zeros(4, dtype=torch.float64, device="cuda")
+        interface_sums_peer(dop, slab, nsteps & 1, sums2)
+        allreduce_interface_sums(sums2)
+        assert float((sums2 - sums_ref).abs().max()) <= 1e-9 * float(sums_ref.abs().max())
+        slab.check()
         dist.barrier()
         slab.close()
     # local DG (3 dofs per node): peer halos and NCCL halos

@@ -42,6 +42,28 @@ def test_apply_matches_oracle(cuda, order, algo, nx, ny, two_phase, theta, pens)
         assert abs(A - B).max() < 1e-13 * abs(A).max()
 
 
+@pytest.mark.parametrize("order,nx,ny", [(1, 300, 200), (2, 200, 150), (3, 130, 100)])
+def test_apply_matches_oracle_many_tiles(cuda, order, nx, ny):
+    """The march kernel against the ORACLE (vectorised NumPy assembly oracle/fast.py, pinned to the literal
+    restatement and through it to MD-LDG_convergence.csv) on meshes with several strips, one tile per CTA slot and
+    a two-phase circle (mixed columns, exception cells in the tail queue) -- not only against the plain kernel."""
+    import torch
+    from stefanproblem_b200 import cutcelldg as cc
+    omesh = UniformMesh2D([0, 0], [1.0, 1.0], [nx, ny], (order + 1) ** 2)
+    omesh.cellsign[:] = fast.circle_phase(omesh)
+    V0 = np.array([np.cos(0.4), np.sin(0.4)])
+    A = fast.ldg_matrix(omesh, order, order + 1, 1.0, 2.0, 0.5, 0.2, 1.3, V0)
+    basis = cc.LagrangeTensorProductBasis(2, order)
+    mesh = cc.UniformMesh([0, 0], [1.0, 1.0], [nx, ny], basis, phase=omesh.cellsign)
+    op = cc.LDGOperator(mesh, order, order + 1, 1.0, 2.0, 0.5, 0.2, 1.3, V0)
+    x = np.random.default_rng(12).uniform(-1, 1, A.shape[0])
+    yr = A @ x
+    y = op.apply(torch.from_numpy(x).cuda()).cpu().numpy()
+    assert np.linalg.norm(y - yr) <= 1e-13 * np.linalg.norm(yr)
+    d = np.abs(y - yr).reshape(nx * ny, -1).max(axis=1)
+    assert d.max() <= 1e-12 * np.abs(yr).max()
+
+
 @pytest.mark.parametrize("order", [1, 2, 3])
 @pytest.mark.parametrize("nx,ny", [(1, 1), (1, 7), (2, 1), (5, 29), (4, 30), (3, 31), (2, 61)])
 def test_degenerate_mesh_shapes(cuda, order, nx, ny):

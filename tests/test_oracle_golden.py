@@ -46,15 +46,19 @@ def ip_error(n, p, variant, exactsolution=exact, sourceterm=source):
     return mesh_L2_error(sol[None, :], exactsolution, basis, cq, mesh)[0], M
 
 
-@pytest.mark.parametrize("row", [0, 1, 2])
+@pytest.mark.parametrize("row", [0, 1, 2, 3, 4])
 def test_ip_uncut_convergence_csv_legacy_boundary(row):
     """StefanDG/InteriorPenalty/uncut_mesh_tests/IP_convergence.csv (legacy boundary
-    form); driver test_uncut_IP_convergence.jl:18-98."""
+    form); driver test_uncut_IP_convergence.jl:18-98.  All five rows (n = 3 ... 33).
+    Tolerance 1e-10 up to n = 17; at n = 33 the system (pen = 1e3 / h) is conditioned badly enough
+    that two sparse direct solvers (Julia's `\\` behind the CSV, SuperLU here) agree to 1e-9 only
+    (observed 5.6e-10 / 1.3e-9)."""
     n, lin, quad = GOLD["ip_uncut"][row]
     e1, _ = ip_error(n, 1, "legacy_boundary")
     e2, _ = ip_error(n, 2, "legacy_boundary")
-    assert abs(e1 - lin) / lin < 1e-10
-    assert abs(e2 - quad) / quad < 1e-10
+    tol = 1e-10 if n <= 17 else 5e-9
+    assert abs(e1 - lin) / lin < tol
+    assert abs(e2 - quad) / quad < tol
 
 
 @pytest.mark.parametrize("p", [1, 2])
@@ -83,7 +87,7 @@ def ldg_errors(n, p, nq, pens=(0.0, 0.0, 0.0, 1.0)):
     return eT / integral_norm_on_mesh(exact, cq, mesh, 1)[0], eG[0], eG[1]
 
 
-@pytest.mark.parametrize("row", [0, 1, 2])
+@pytest.mark.parametrize("row", [0, 1, 2, 3, 4])
 def test_ldg_uncut_convergence_csv(row):
     """StefanDG/LocalDG/uncut_mesh_tests/MD-LDG_convergence.csv: penalties (0,0,0,1),
     literal bn = n.V0; driver test_uncut_LDG_convergence.jl:25-118."""
