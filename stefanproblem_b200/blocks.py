@@ -57,8 +57,48 @@ class BlockSystem:
                 raise ValueError(f"{name}: {dev[name].numel()} values, expected {n}")
         self._data = dev  # keep the device arrays alive until the kernel has run
         bd = _lib.BlocksData(*[dev[n].data_ptr() for n in _FIELDS])
+        self._bd = bd
         _lib.check(_lib.lib().stefan_blocks_assemble(self._h, ctypes.byref(bd), _stream_ptr(stream)))
         return self
+
+    def _dev(self, a):
+        import torch
+        if a is None:
+            return None
+        if not isinstance(a, torch.Tensor):
+            a = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64))
+        return a.cuda().contiguous()
+
+    def rhs(self, f_qp=None, g_qp=None, Tm=0.0, stream=None):
+        """Right-hand side of the assembled data (stefan_blocks_rhs): f_qp [ncells][nqv] source samples,
+        g_qp [ncells][nslots][nqf] boundary data, Tm of the Robin source.  Device tensor [ndofs]."""
+        import torch
+        f, g = self._dev(f_qp), self._dev(g_qp)
+        out = torch.empty(self.ndofs, dtype=torch.float64, device="cuda")
+        _lib.check(_lib.lib().stefan_blocks_rhs(self._h, ctypes.byref(self._bd), _ptr(f), _ptr(g), float(Tm), _ptr(out),
+                                                _stream_ptr(stream)))
+        return out
+
+    def l2_error(self, u, uex_qp):
+        """(||u_h - u_ex||, ||u_ex||) over the volume points of all solution cells (stefan_blocks_l2_error)."""
+        import torch
+        out = torch.empty(2, dtype=torch.float64, device="cuda")
+        ue = self._dev(uex_qp)
+        _lib.check(_lib.lib().stefan_blocks_l2_error(self._h, ctypes.byref(self._bd), _ptr(u), _ptr(ue), _ptr(out),
+                                                     _stream_ptr()))
+        e = out.cpu().numpy()
+        return float(e[0]), float(e[1])
+
+    def solve(self, b, x0=None, tol=1e-12, maxiter=20000, preconditioner="block_jacobi", check_every=10):
+        """`matrix \\ rhs` by preconditioned CG on the device (stefan_blocks_cg_solve); returns (x, info)."""
+        import torch
+        x = torch.zeros_like(b) if x0 is None else x0.clone()
+        prm = _lib.CgParams(int(maxiter), float(tol), {"none": 0, "block_jacobi": 1}[preconditioner], int(check_every))
+        res = _lib.CgResult()
+        _lib.check(_lib.lib().stefan_blocks_cg_solve(self._h, _ptr(b), _ptr(x), ctypes.byref(prm), ctypes.byref(res),
+                                                     _stream_ptr()))
+        return x, {"iterations": res.iterations, "residual_norm": res.residual_norm, "rhs_norm": res.rhs_norm,
+                   "converged": bool(res.converged)}
 
     def apply(self, x, out=None, stream=None):
         import torch

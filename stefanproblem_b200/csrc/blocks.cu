@@ -28,55 +28,12 @@
 // reduction; HBM-bound by the blocks: 16 + 8 (1 + nslots) NF bytes per dof-update
 // ("general block path").
 #include "../../include/stefan_b200.h"
+#include "blocks_handle.cuh"
 #include "common.cuh"
 
 #include <algorithm>
 
 namespace stefan {
-
-struct BlocksHandle {
-  stefan_blocks_dims d;
-  int nf;
-  double* blocks;       // [ncells][1 + nslots][nf][nf], row-major (row = test function)
-  int32_t* slot_nbr;    // [ncells][nslots] copy of the adjacency (apply needs it)
-  bool assembled;
-};
-
-// 1-D Lagrange basis on order+1 equispaced nodes of [-1, 1]: value and derivative of N_i at x
-template <int P>
-__device__ __forceinline__ void lagrange_vd(int i, double x, double& v, double& d) {
-  constexpr int n = P + 1;
-  const double xi = -1.0 + 2.0 * i / P;
-  v = 1.0;
-  d = 0.0;
-#pragma unroll
-  for (int j = 0; j < n; ++j) {
-    if (j == i) continue;
-    const double xj = -1.0 + 2.0 * j / P;
-    v *= (x - xj) / (xi - xj);
-    double t = 1.0 / (xi - xj);
-#pragma unroll
-    for (int k = 0; k < n; ++k) {
-      if (k == i || k == j) continue;
-      const double xk = -1.0 + 2.0 * k / P;
-      t *= (x - xk) / (xi - xk);
-    }
-    d += t;
-  }
-}
-
-// value V_a(p) and physical gradient (dV/dx, dV/dy) of the tensor basis function a = ax (P+1) + ay
-template <int P>
-__device__ __forceinline__ void basis_vg(int a, double px, double py, double jx, double jy, double& v, double& gx,
-                                         double& gy) {
-  const int ax = a / (P + 1), ay = a % (P + 1);
-  double vx, dx, vy, dy;
-  lagrange_vd<P>(ax, px, vx, dx);
-  lagrange_vd<P>(ay, py, vy, dy);
-  v = vx * vy;
-  gx = dx * vy / jx;
-  gy = vx * dy / jy;
-}
 
 // Assembly: one WARP per cell.  The lanes first tabulate, in shared memory, the basis values
 // and physical gradients at the cell's quadrature points (volume points, then slot by slot
@@ -300,8 +257,8 @@ extern "C" {
 int stefan_blocks_create(const stefan_blocks_dims* dims, stefan_blocks** out) {
   STEFAN_REQUIRE(dims && out, "stefan_blocks_create: null argument");
   STEFAN_REQUIRE(dims->ncells >= 1 && dims->order >= 1 && dims->order <= 3, "stefan_blocks_create: bad ncells / order");
-  STEFAN_REQUIRE(dims->nqv >= 1 && dims->nslots >= 1 && dims->nslots <= 8 && dims->nqf >= 1,
-                 "stefan_blocks_create: need nqv >= 1, 1 <= nslots <= 8, nqf >= 1");
+  STEFAN_REQUIRE(dims->nqv >= 1 && dims->nslots >= 1 && dims->nslots <= 16 && dims->nqf >= 1,
+                 "stefan_blocks_create: need nqv >= 1, 1 <= nslots <= 16, nqf >= 1");
   BlocksHandle* h = new BlocksHandle();
   h->d = *dims;
   h->nf = (dims->order + 1) * (dims->order + 1);

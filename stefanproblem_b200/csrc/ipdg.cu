@@ -56,6 +56,12 @@ struct ApplyArgs {
   // graph-replayable form: the epoch lives on the device -- the kernel uses *sync_epoch_dev + 1 and
   // its last CTA stores that back -- so the same captured launch advances the protocol on every replay
   unsigned long long* sync_epoch_dev;
+  // push-style mailboxes in the NEIGHBOURS' memory (null = none): the kernel also stores its ready value (at
+  // start) / done value (by its last CTA) there, so that the neighbours poll their own memory instead of
+  // reading a flag over NVLink (a remote poll is a 1-2 us round trip)
+  unsigned long long* sync_post_ready[2];
+  unsigned long long* sync_post_done[2];
+  int sync_chained;  // 1: the halo gate is the neighbours' DONE value of the previous epoch (see stefan_peer_sync)
   int* sync_status;                          // set to 1 if a wait timed out
   unsigned long long* dbg_times;             // development only: per-CTA {start, prologue, loop, end} globaltimer, or null
   // dynamic tail queue: [0] next fix-list index, [1] CTAs finished; both reset by the last CTA
@@ -196,8 +202,8 @@ __device__ __forceinline__ void fixup_tail(const IpTab<P>& tab, const ApplyArgs&
   const int node = lane_live ? lane - grp * NF : 0;
   const int ix = node / N1, iy = node % N1;
   const int gbase = grp * NF;
-  unsigned long long epoch = 0;
-  if (a.sync_epoch != 0) epoch = peer_epoch(a.sync_epoch_dev, a.sync_epoch);
+  unsigned long long epoch = 0;   // the value the neighbours' flags must have reached
+  if (a.sync_epoch != 0) epoch = peer_epoch(a.sync_epoch_dev, a.sync_epoch) - (unsigned long long)a.sync_chained;
   for (;;) {
     unsigned base = 0;
     if (lane == 0) base = atomicAdd(a.tail_ctr, (unsigned)(CW * BATCH));
@@ -298,6 +304,8 @@ __device__ __forceinline__ void march_finish(const ApplyArgs& a) {
       if (a.sync_epoch != 0) {
         const unsigned long long epoch = peer_epoch(a.sync_epoch_dev, a.sync_epoch);
         peer_flag_publish(a.sync_my_done, epoch);
+        if (a.sync_post_done[0]) peer_flag_publish(a.sync_post_done[0], epoch);
+        if (a.sync_post_done[1]) peer_flag_publish(a.sync_post_done[1], epoch);
         if (a.sync_epoch_dev != nullptr) *a.sync_epoch_dev = epoch;  // every CTA has read it: all are done
       }
     }
@@ -515,7 +523,7 @@ int stefan_ipdg_create(const stefan_ipdg_params* p, const int8_t* phase, const i
   cudaError_t e = cudaMalloc(&h->phase_dev, pn);
   if (e == cudaSuccess) e = cudaMemcpy(h->phase_dev, ph.data(), pn, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = h->plan.build(ph.data(), p->nx, p->ny, march_warps(p->order));
-  h->plan.mixed_cost_q = p->order == 1 ? 1 : (p->order == 2 ? 2 : 4);  // measured (quarter columns), see MarchPlan::segments
+  h->plan.mixed_cost_q = p->order == 1 ? 1 : (p->order == 2 ? 4 : 2);  // measured (quarter columns), see MarchPlan::segments
   // tiles that touch a neighbouring slab get two columns less: they may have to wait for its flag
   h->plan.edge_lo_q = h->has_lo ? 8 : 0;
   h->plan.edge_hi_q = h->has_hi ? 8 : 0;
@@ -597,6 +605,11 @@ int stefan_ipdg_apply_peer(stefan_ipdg* hv, const double* x, double* y, const do
   a.sync_epoch_dev = reinterpret_cast<unsigned long long*>(sync->epoch_dev);
   a.sync_timeout_ns = (unsigned long long)sync->timeout_ms * 1000000ull;
   a.sync_status = sync->status;
+  for (int k = 0; k < 2; ++k) {
+    a.sync_post_ready[k] = reinterpret_cast<unsigned long long*>(sync->post_ready[k]);
+    a.sync_post_done[k] = reinterpret_cast<unsigned long long*>(sync->post_done[k]);
+  }
+  a.sync_chained = sync->chained ? 1 : 0;
   return dispatch_apply(h, a, 0, static_cast<cudaStream_t>(stream));
 }
 
@@ -631,6 +644,11 @@ int stefan_ipdg_step(stefan_ipdg* hv, const double* u, double* unew, const doubl
     a.sync_my_done = reinterpret_cast<unsigned long long*>(sync->my_done);
     a.sync_lo_ready = reinterpret_cast<const unsigned long long*>(sync->lo_ready);
     a.sync_hi_ready = reinterpret_cast<const unsigned long long*>(sync->hi_ready);
+    for (int k = 0; k < 2; ++k) {
+      a.sync_post_ready[k] = reinterpret_cast<unsigned long long*>(sync->post_ready[k]);
+      a.sync_post_done[k] = reinterpret_cast<unsigned long long*>(sync->post_done[k]);
+    }
+    a.sync_chained = sync->chained ? 1 : 0;
     a.sync_epoch = sync->epoch;
     a.sync_epoch_dev = reinterpret_cast<unsigned long long*>(sync->epoch_dev);
     a.sync_timeout_ns = (unsigned long long)sync->timeout_ms * 1000000ull;

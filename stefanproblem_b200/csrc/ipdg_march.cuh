@@ -264,7 +264,8 @@ ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const 
         return;
       }
       if (a.sync_epoch != 0 && (k < 0 || k >= a.nx))  // a neighbour's column: wait until it is published
-        peer_flag_wait(k < 0 ? a.sync_lo_ready : a.sync_hi_ready, peer_epoch(a.sync_epoch_dev, a.sync_epoch),
+        peer_flag_wait(k < 0 ? a.sync_lo_ready : a.sync_hi_ready,
+                       peer_epoch(a.sync_epoch_dev, a.sync_epoch) - (unsigned long long)a.sync_chained,
                        a.sync_timeout_ns, a.sync_status);
       if constexpr (C::TENSOR) {
         if (k >= 0 && k < a.nx) {
@@ -365,8 +366,12 @@ ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const 
     }
     // peer halos: everything the stream wrote before this kernel is final -> publish my epoch
     // (warp 0 of CTA 0 always owns a strip: tiles are never empty)
-    if (a.sync_epoch != 0 && blockIdx.x == 0 && threadIdx.x == 0)
-      peer_flag_publish(a.sync_my_ready, peer_epoch(a.sync_epoch_dev, a.sync_epoch));
+    if (a.sync_epoch != 0 && blockIdx.x == 0 && threadIdx.x == 0) {
+      const unsigned long long epoch = peer_epoch(a.sync_epoch_dev, a.sync_epoch);
+      peer_flag_publish(a.sync_my_ready, epoch);
+      if (a.sync_post_ready[0]) peer_flag_publish(a.sync_post_ready[0], epoch);
+      if (a.sync_post_ready[1]) peer_flag_publish(a.sync_post_ready[1], epoch);
+    }
 
     // prologue: columns c0-1 .. c0+NST-2 into slots 0 .. NST-1
 #pragma unroll

@@ -14,6 +14,7 @@
 // opinion the tests compare it with (stefan_ldg_apply_algo, algo 1).
 #include "../../include/stefan_b200.h"
 #include "common.cuh"
+#include "ldg_handle.h"
 #include "ldg_tables.h"
 #include "march_dev.cuh"
 
@@ -22,22 +23,6 @@
 #include <vector>
 
 namespace stefan {
-
-constexpr int kLdgTailRing = 8;
-
-struct LdgHandle {
-  int nx, ny, order, numqp;
-  double phys_hx, phys_hy;
-  LdgPhys phys;
-  bool has_lo, has_hi;
-  int8_t* phase_dev;
-  MarchPlan plan;  // run lists, fix list and CTA tiles of the march kernel
-  int variant;     // CTA shape of the march kernel (ldg_march_variant)
-  unsigned* tail_ctr_dev;  // ring of {next, finished} counter pairs of the march kernel's tail queue
-  unsigned launch_seq;
-  void* tab_host;
-  int64_t ndofs;
-};
 
 struct LdgArgs {
   const double* x;
@@ -396,7 +381,7 @@ int stefan_ldg_create(const stefan_ldg_params* p, const int8_t* phase, const int
   // The loops are memory-bound at every order: a least-squares fit of the per-CTA loop times of the
   // 457^2 order-3 mesh (profiles/r2_ldg_cta_times.txt) gives 4.15 us per column, +0.29 us per mixed
   // column and 4.3 us per tile -- the second body hides behind the loads.
-  h->plan.mixed_cost_q = p->order == 2 ? 2 : 1;
+  h->plan.mixed_cost_q = p->order == 1 ? 1 : 2;  // (sweep: profiles/r2_sweep_mixed_cost.log)
   if (e == cudaSuccess) e = h->plan.build(ph.data(), p->nx, p->ny, ldg_march_warps(p->order, h->variant));
   if (e != cudaSuccess) {
     h->plan.destroy();

@@ -408,13 +408,24 @@ class LDGOperator:
                                                     int(algo), _stream_ptr(stream)))
         return out
 
-    def solve(self, rhs, tol=1e-12, maxiter=20000):
-        """`matrix \\ rhs` on the device: Schur complement on T + BiCGStab over this operator's
-        kernels (`ldg_solve.schur_solve`; unpreconditioned, for the sizes of the reference's
-        convergence studies).  Returns (solution, info)."""
+    def solve(self, rhs, tol=1e-12, maxiter=20000, check_every=10, native=True):
+        """`matrix \\ rhs` on the device: Schur complement on T + BiCGStab (stefan_ldg_solve: the whole
+        iteration is native, scalars on the device; unpreconditioned, for the sizes of the reference's
+        convergence studies).  native=False runs the host-side twin of the same algorithm
+        (`ldg_solve.schur_solve`, kept for the CPU tests).  Returns (solution, info)."""
         import torch
-        from .ldg_solve import cell_mass_inverse, schur_solve
         assert rhs.is_cuda and rhs.dtype == torch.float64 and rhs.numel() == self.ndofs
+        if native:
+            rhs = _aligned(rhs.contiguous())
+            sol = torch.empty_like(rhs)
+            prm = _lib.CgParams(int(maxiter), float(tol), 0, int(check_every))
+            res = _lib.CgResult()
+            _lib.check(_lib.lib().stefan_ldg_solve(self._h, _ptr(rhs), _ptr(sol), ctypes.byref(prm), ctypes.byref(res),
+                                                   _stream_ptr()))
+            rel = res.residual_norm / res.rhs_norm if res.rhs_norm > 0 else 0.0
+            return sol, {"iterations": res.iterations, "converged": bool(res.converged), "relative_residual": rel,
+                         "operator_applications": 1 + 2 * (2 * res.iterations + 1)}
+        from .ldg_solve import cell_mass_inverse, schur_solve
         mass1d = reference_tables(self.order, self.params.numqp)["mass"]
         minv = torch.from_numpy(cell_mass_inverse(mass1d, 0.25 * self.params.hx * self.params.hy)).cuda()
         return schur_solve(lambda x: self.apply(x), minv, rhs.contiguous(), self.nf, tol, maxiter)

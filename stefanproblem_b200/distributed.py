@@ -229,18 +229,42 @@ class PeerSlab:
         base, n_r, _, stride_r = self._peers[r]
         return base + buf * stride_r + (8 * (n_r - col_len) if last else 0)
 
-    def sync_block(self, rank, world, timeout_ms=5000, device_epoch=False):
-        """The `stefan_peer_sync` of the NEXT epoch for the fused kernels.  device_epoch=True: the epoch
-        lives on the device (`epoch_dev`), the launch can be captured in a CUDA graph and replayed."""
+    def sync_block(self, rank, world, timeout_ms=5000, device_epoch=False, chained=False, push=True):
+        """The `stefan_peer_sync` of the NEXT epoch for the fused kernels.
+        device_epoch: the epoch lives on the device (`epoch_dev`): the launch can be captured in a CUDA graph.
+        push: the kernel also posts its ready / done values into the neighbours' mailbox slots and polls its
+        own slots (flag slots of a rank: 0 my_ready, 1 my_done, 2 / 3 ready / done posted by the low neighbour,
+        4 / 5 by the high neighbour) instead of reading the neighbours' flags over NVLink.
+        chained: gate the halo reads on the neighbours' DONE value of the previous epoch (valid when the vector
+        read in epoch k is final once the kernel of epoch k - 1 is complete: a static vector, or the two-buffer
+        loop of `step_peer_fused`)."""
         from . import _lib
-        lo_f = self.peer_flag(rank - 1, 0) if rank > 0 else None
-        hi_f = self.peer_flag(rank + 1, 0) if rank < world - 1 else None
+        has_lo, has_hi = rank > 0, rank < world - 1
+        kind = 1 if chained else 0
+        if push:
+            lo_f = self.my_flag(2 + kind) if has_lo else None
+            hi_f = self.my_flag(4 + kind) if has_hi else None
+        else:
+            lo_f = self.peer_flag(rank - 1, kind) if has_lo else None
+            hi_f = self.peer_flag(rank + 1, kind) if has_hi else None
+        sync = _lib.PeerSync()
+        sync.my_ready, sync.my_done = self.my_flag(0), self.my_flag(1)
+        sync.lo_ready, sync.hi_ready = lo_f, hi_f
+        sync.timeout_ms = int(timeout_ms)
+        sync.status = self.status.data_ptr()
+        sync.chained = 1 if chained else 0
+        if push:
+            # my low neighbour sees me as ITS high neighbour (slots 4 / 5), my high neighbour as its low one (2 / 3)
+            sync.post_ready[0] = self.peer_flag(rank - 1, 4) if has_lo else None
+            sync.post_ready[1] = self.peer_flag(rank + 1, 2) if has_hi else None
+            sync.post_done[0] = self.peer_flag(rank - 1, 5) if has_lo else None
+            sync.post_done[1] = self.peer_flag(rank + 1, 3) if has_hi else None
         if device_epoch:
-            return _lib.PeerSync(self.my_flag(0), self.my_flag(1), lo_f, hi_f, 1, int(timeout_ms),
-                                 self.status.data_ptr(), self.epoch_dev.data_ptr())
-        self.epoch += 1
-        return _lib.PeerSync(self.my_flag(0), self.my_flag(1), lo_f, hi_f, self.epoch, int(timeout_ms),
-                             self.status.data_ptr(), None)
+            sync.epoch, sync.epoch_dev = 1, self.epoch_dev.data_ptr()
+        else:
+            self.epoch += 1
+            sync.epoch, sync.epoch_dev = self.epoch, None
+        return sync
 
     def to_device_epochs(self):
         """Continue the epoch count on the device (before graph-captured / device_epoch=True launches)."""
@@ -312,15 +336,18 @@ class PeerSlab:
             self._ptr = None
 
 
-def step_peer_fused(dop, slab, src, dst, b, dt, timeout_ms=5000, device_epoch=False):
+def step_peer_fused(dop, slab, src, dst, b, dt, timeout_ms=5000, device_epoch=False, chained=True):
     """slab.bufs[dst] = u + dt Minv (b - A u) with u = slab.bufs[src]: ONE launch (stefan_ipdg_step, peer form).
-    The neighbours' edge columns of THEIR buffer `src` are read over NVLink inside the kernel."""
+    The neighbours' edge columns of THEIR buffer `src` are read over NVLink inside the kernel.  chained (default):
+    in a loop that alternates two buffers the neighbours' buffer `src` is final once THEIR previous step kernel is
+    complete, so the halo gate is their done value of the previous epoch (see PeerSlab.sync_block); the very first
+    step of a loop must follow a barrier (the initial vectors are final) -- epoch 0 counts as done."""
     from . import _lib
     from .cutcelldg import _stream_ptr
     col = dop.halo.col
     lo = ctypes.c_void_p(slab.peer_column(dop.rank - 1, col, last=True, buf=src)) if dop.rank > 0 else None
     hi = ctypes.c_void_p(slab.peer_column(dop.rank + 1, col, last=False, buf=src)) if dop.rank < dop.world - 1 else None
-    sync = slab.sync_block(dop.rank, dop.world, timeout_ms, device_epoch)
+    sync = slab.sync_block(dop.rank, dop.world, timeout_ms, device_epoch, chained=chained)
     _lib.check(_lib.lib().stefan_ipdg_step(dop.op._h, ctypes.c_void_p(slab.bufs[src].data_ptr()),
                                            ctypes.c_void_p(slab.bufs[dst].data_ptr()),
                                            ctypes.c_void_p(b.data_ptr()) if b is not None else None, float(dt),
@@ -344,18 +371,20 @@ def interface_sums_peer(dop, slab, buf, out, timeout_ms=5000):
     return out
 
 
-def apply_peer_fused(dop, slab, out, timeout_ms=5000, device_epoch=False, buf=0):
+def apply_peer_fused(dop, slab, out, timeout_ms=5000, device_epoch=False, buf=0, chained=False):
     """out = A x for the slab vector `slab.bufs[buf]`: ONE kernel launch and nothing else on the stream.
     The kernel publishes the slab's next epoch when it starts, its warps wait for the
     neighbours' epoch right before they fetch the neighbours' edge columns over NVLink, and
     its last CTA releases them (stefan_ipdg_apply_peer).  device_epoch=True keeps the epoch on the
-    device so that the launch can be captured in a CUDA graph and replayed."""
+    device so that the launch can be captured in a CUDA graph and replayed.  chained=True: the slab vector
+    does not change between the applications of a loop (or only inside such kernels), so the halo gate is the
+    neighbours' DONE value of the previous epoch (see PeerSlab.sync_block)."""
     from . import _lib
     from .cutcelldg import _stream_ptr
     col = dop.halo.col
     lo = ctypes.c_void_p(slab.peer_column(dop.rank - 1, col, last=True, buf=buf)) if dop.rank > 0 else None
     hi = ctypes.c_void_p(slab.peer_column(dop.rank + 1, col, last=False, buf=buf)) if dop.rank < dop.world - 1 else None
-    sync = slab.sync_block(dop.rank, dop.world, timeout_ms, device_epoch)
+    sync = slab.sync_block(dop.rank, dop.world, timeout_ms, device_epoch, chained=chained)
     _lib.check(_lib.lib().stefan_ipdg_apply_peer(dop.op._h, ctypes.c_void_p(slab.bufs[buf].data_ptr()),
                                                  ctypes.c_void_p(out.data_ptr()), lo, hi, ctypes.byref(sync),
                                                  _stream_ptr()))

@@ -17,12 +17,19 @@ def main():
     ip_rows = rows("StefanDG/InteriorPenalty/uncut_mesh_tests/IP_convergence.csv")
     ldg_rows = rows("StefanDG/LocalDG/uncut_mesh_tests/MD-LDG_convergence.csv")
     robin = rows("StefanRobinIC/DG1D/robin-interface-tests/robin-convergence.csv")
+    cyl = rows("StefanDG/InteriorPenalty/cylindrical_bc_tests/IP_convergence.csv")
+    cylr = rows("StefanDG/InteriorPenalty/robin_cylindrical_bc_tests/IP_convergence.csv")
     gold = {
         "ip_uncut": [[int(r[0]), r[1], r[2]] for r in ip_rows],
         "ldg_uncut": [[int(r[0])] + r[1:] for r in ldg_rows],
         "dg1d_robin_linear": [r[1] for r in robin],
         "dg1d_robin_quadratic": [r[2] for r in robin],
+        # cut-cell studies: NElmts, linear, quadratic (relative L2 errors); parity at discretisation level only
+        "ip_cylinder": [[int(r[0]), r[1], r[2]] for r in cyl],
+        "ip_cylinder_robin": [[int(r[0]), r[1], r[3]] for r in cylr],
         "sources": {
+            "ip_cylinder": "StefanDG/InteriorPenalty/cylindrical_bc_tests/IP_convergence.csv",
+            "ip_cylinder_robin": "StefanDG/InteriorPenalty/robin_cylindrical_bc_tests/IP_convergence.csv",
             "ip_uncut": "StefanDG/InteriorPenalty/uncut_mesh_tests/IP_convergence.csv",
             "ldg_uncut": "StefanDG/LocalDG/uncut_mesh_tests/MD-LDG_convergence.csv",
             "dg1d_robin": "StefanRobinIC/DG1D/robin-interface-tests/robin-convergence.csv",

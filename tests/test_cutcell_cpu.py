@@ -1,0 +1,124 @@
+"""CPU checks of the cut-cell generator (stefanproblem_b200/cutcell.py: host-side geometry, no GPU) and of the
+analytic cylinder solutions (oracle/analytical.py), plus the reference's cylinder study on small meshes with the
+ORACLE's block assembly (oracle/blocks.py) -- the same data the GPU block path consumes in tests/test_cutcell_gpu.py."""
+import json
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from oracle import blocks as ob
+from oracle.analytical import CylindricalSolver, RobinCylindricalSolver
+from stefanproblem_b200.cutcell import CircleCutMesh, arc_rule, disk_rect_rules, edge_rules
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_csv.json")))
+
+
+def test_analytical_solution_identities():
+    """test_robin_interface_analytical_solution.jl:28-37 (continuity, Robin flux balance) and the outer / interface
+    conditions of cylinder-analytical-solution.jl."""
+    s = RobinCylindricalSolver(2.0, 1.0, 1.0, 2.0, 1.0, 0.3, 1.0, 1.0, 0.5)
+    assert np.isclose(s.core_solution(0.3), s.rim_solution(0.3))               # TR1 ~ TR2 (:31)
+    assert np.isclose(s(1.0), 1.0)                                             # Touter = Tw
+    flux = 1.0 * s.core_radial_derivative(0.3) - 2.0 * s.rim_radial_derivative(0.3) - 1.0 * (0.5 - s.core_solution(0.3))
+    assert abs(flux) < 1e-13                                                   # :36
+    c = CylindricalSolver(1.0, 1.0, 2.0, 2.0, 0.5, 1.5, 1.0)
+    assert np.isclose(c.core_solution(0.5), c.rim_solution(0.5)) and np.isclose(c(1.5), 1.0)
+    assert abs(1.0 * c.radial_derivative(0.5 - 1e-9) - 2.0 * c.radial_derivative(0.5 + 1e-9)) < 1e-8   # flux continuity
+    # the PDE itself: -k (T'' + T'/r) = q in both phases (finite differences)
+    for r0, q, k in ((0.2, 1.0, 1.0), (1.0, 2.0, 2.0)):
+        h = 1e-4
+        lap = (c(r0 + h) - 2 * c(r0) + c(r0 - h)) / h ** 2 + (c(r0 + h) - c(r0 - h)) / (2 * h) / r0
+        assert abs(-k * lap - q) < 1e-5
+
+
+@pytest.mark.parametrize("box,circle", [((0.2, 0.5, 0.1, 0.4), (0.0, 0.0, 0.45)), ((0.0, 1.0, 0.0, 1.0), (0.5, 0.5, 0.3)),
+                                        ((0.3, 0.4, 0.3, 0.4), (0.0, 0.0, 0.5)), ((-0.2, 0.3, 0.1, 0.9), (0.1, 0.5, 0.35))])
+def test_disk_rect_rules_integrate_polynomials(box, circle):
+    """inside + outside rules add up to the rectangle rule for polynomials; the inside area matches a brute-force
+    estimate; face portions add up to the edge; the arc rule gives the arc length and unit radial normals."""
+    x0, x1, y0, y1 = box
+    cx, cy, R = circle
+    (pi, wi), (po, wo) = disk_rect_rules(x0, x1, y0, y1, cx, cy, R, 5)
+    f = lambda p: 1.0 + p[:, 0] ** 2 * p[:, 1] - 0.5 * p[:, 1] ** 3  # noqa: E731
+    g, w = np.polynomial.legendre.leggauss(5)
+    X, Y = np.meshgrid(0.5 * (x0 + x1) + 0.5 * (x1 - x0) * g, 0.5 * (y0 + y1) + 0.5 * (y1 - y0) * g, indexing="ij")
+    exact = (np.outer(w, w) * 0.25 * (x1 - x0) * (y1 - y0) * f(np.stack([X.ravel(), Y.ravel()], 1)).reshape(5, 5)).sum()
+    assert abs((wi * f(pi)).sum() + (wo * f(po)).sum() - exact) < 1e-12
+    xs, ys = np.meshgrid(np.linspace(x0, x1, 1201), np.linspace(y0, y1, 1201), indexing="ij")
+    brute = ((xs - cx) ** 2 + (ys - cy) ** 2 < R * R).mean() * (x1 - x0) * (y1 - y0)
+    assert abs(wi.sum() - brute) < 2e-3 * (x1 - x0) * (y1 - y0)
+    assert np.all((pi[:, 0] - cx) ** 2 + (pi[:, 1] - cy) ** 2 < R * R + 1e-12)
+    assert np.all((po[:, 0] - cx) ** 2 + (po[:, 1] - cy) ** 2 > R * R - 1e-12)
+    for p0, p1 in (((x0, y0), (x1, y0)), ((x1, y0), (x1, y1)), ((x0, y1), (x1, y1)), ((x0, y0), (x0, y1))):
+        (_, a), (_, b) = edge_rules(p0, p1, cx, cy, R, 3)
+        assert abs(a.sum() + b.sum() - max(abs(p1[0] - p0[0]), abs(p1[1] - p0[1]))) < 1e-13
+    P, W, N = arc_rule(x0, x1, y0, y1, cx, cy, R, 4)
+    if len(W):
+        assert np.allclose(np.hypot(P[:, 0] - cx, P[:, 1] - cy), R) and np.allclose(np.hypot(N[:, 0], N[:, 1]), 1.0)
+        assert np.all((P[:, 0] >= x0 - 1e-12) & (P[:, 0] <= x1 + 1e-12) & (P[:, 1] >= y0 - 1e-12) & (P[:, 1] <= y1 + 1e-12))
+
+
+@pytest.mark.parametrize("merge", [0.0, 0.25])
+def test_cut_mesh_geometry_is_consistent(merge):
+    n, R = 9, 0.5
+    m = CircleCutMesh([0, 0], [1, 1], [n, n], [0, 0], R, 3, 1.0, 2.0, 1e3 * n, 1.0, merge_fraction=merge)
+    d = m.data
+    detj = d["cell_jac"][:, 0] * d["cell_jac"][:, 1]
+    area = (d["vol_wts"] * detj[:, None]).sum(axis=1)
+    plus = m.sol_phase == 1
+    assert abs(area.sum() - 1.0) < 1e-12                                # the pieces tile the square
+    assert abs(area[plus].sum() - np.pi * R * R / 4) < 1e-6             # quarter disk (exact boundary; 3-point Gauss of the chord length)
+    iface = m.slot_is_interface & (d["slot_nbr"] >= 0)
+    assert abs(d["face_wts"][iface & plus[:, None]].sum() - np.pi * R / 2) < 1e-12     # quarter circumference, once per side
+    assert abs(d["face_wts"][iface & ~plus[:, None]].sum() - np.pi * R / 2) < 1e-12
+    bd = d["slot_nbr"] == -1
+    assert abs(d["face_wts"][bd].sum() - 4.0) < 1e-12                   # the boundary of the square
+    # every coupled slot has a partner slot on the neighbour with the same weights and opposite normals
+    nsol, nslots = d["slot_nbr"].shape
+    for c in range(nsol):
+        for s in range(nslots):
+            nb = int(d["slot_nbr"][c, s])
+            if nb < 0:
+                continue
+            back = [t for t in range(nslots) if int(d["slot_nbr"][nb, t]) == c and
+                    np.isclose(d["face_wts"][nb, t].sum(), d["face_wts"][c, s].sum(), rtol=1e-12, atol=1e-15)]
+            assert back, (c, s, nb)
+            t = back[0]
+            k = d["face_wts"][c, s] != 0
+            assert np.allclose(d["face_normals"][c, s][k].sum(axis=0), -d["face_normals"][nb, t][d["face_wts"][nb, t] != 0].sum(axis=0))
+    if merge:
+        assert m.nsol < len(m.pieces) and (area > 0.2 * (1.0 / n) ** 2).all()   # no tiny solution cell is left
+
+
+def _study(n, order, prm, merge=0.25):
+    sol = (RobinCylindricalSolver(prm["q1"], prm["k1"], prm["q2"], prm["k2"], prm["lam"], prm["R"], prm["b"], prm["Tw"], prm["Tm"])
+           if prm["lam"] else CylindricalSolver(prm["q1"], prm["k1"], prm["q2"], prm["k2"], prm["R"], prm["b"], prm["Tw"]))
+    m = CircleCutMesh([0, 0], [1, 1], [n, n], [0, 0], prm["R"], prm["numqp"][order], prm["k1"], prm["k2"], 1e3 * n, prm["lam"],
+                      merge_fraction=merge)
+    A = sp.csr_matrix(ob.dense_matrix(ob.assemble_blocks(order, m.data), m.data["slot_nbr"]))
+    assert abs(A - A.T).max() <= 1e-12 * abs(A).max()          # `@assert issymmetric(matrix)` of the drivers
+    rhs = ob.assemble_rhs(order, m.data, m.sample_source(lambda x, y: prm["q1"] + 0 * x, lambda x, y: prm["q2"] + 0 * x),
+                          m.sample_boundary(sol.at), prm["Tm"])
+    u = spla.spsolve(A.tocsc(), rhs)
+    e, den = ob.l2_error(order, m.data, u, m.sample_exact(sol.at))
+    return e / den
+
+
+PLAIN = dict(k1=1.0, k2=2.0, q1=1.0, q2=2.0, lam=0.0, Tm=0.0, R=0.5, b=1.5, Tw=1.0, numqp={1: 2, 2: 5})
+ROBIN = dict(k1=1.0, k2=2.0, q1=2.0, q2=1.0, lam=1.0, Tm=0.5, R=0.7, b=1.5, Tw=1.0, numqp={1: 4, 2: 5})
+
+
+@pytest.mark.parametrize("name,prm", [("ip_cylinder", PLAIN), ("ip_cylinder_robin", ROBIN)])
+def test_cylinder_study_small_meshes_against_the_reference_csv(name, prm):
+    """n = 3, 5, 9 of the reference's cut-cell cylinder studies with the oracle's block assembly on the generator's
+    data.  Discretisation-level parity: the stored CSVs come from a Q2-interpolated level set and other quadrature
+    rules, this generator from the exact circle.  Observed ratio this / CSV over all 20 entries of the two studies
+    (n = 3 ... 33, p = 1, 2): 0.73 ... 1.08, within 4 % from n = 9 on except Robin p = 2 (0.91); asserted 0.7 ... 1.12."""
+    for row in GOLD[name][:3]:
+        n = row[0]
+        for order, want in ((1, row[1]), (2, row[2])):
+            got = _study(n, order, prm)
+            assert 0.7 * want < got < 1.12 * want, (name, n, order, got, want)
