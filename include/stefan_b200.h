@@ -360,6 +360,30 @@ int stefan_blocks_l2_error(stefan_blocks* h, const stefan_blocks_data* data, con
  * (params->preconditioner 1: inverse of every solution cell's diagonal block), scalars on the device. */
 int stefan_blocks_cg_solve(stefan_blocks* h, const double* b, double* x, const stefan_cg_params* params,
                            stefan_cg_result* result, void* stream);
+/* interface_L2_error / integral_norm_on_interface (useful_routines.jl:239-274, :288-307) on the face slots
+ * selected by slot_select [ncells][nslots] (non-zero = include; e.g. the interface slots of the solution cells
+ * of one level-set sign): out2[0] = sqrt(sum (u_h - u_ex)^2 sa w), out2[1] = sqrt(sum u_ex^2 sa w);
+ * uex_fq [ncells][nslots][nqf] are the exact values at the slots' points. */
+int stefan_blocks_interface_l2_error(stefan_blocks* h, const stefan_blocks_data* data, const int8_t* slot_select,
+                                     const double* u, const double* uex_fq, double* out2_dev, void* stream);
+
+/* ------------------------------------------------- point evaluation and front velocity
+ * InteriorPenalty.interpolate_at_reference_points (IP_postprocess.jl:30-52) and gradient_at_reference_points
+ * (:1-28) as device gathers: nodalvalues holds NF = (order + 1)^2 dofs per (solution) cell, refpoints [numpts][2]
+ * are reference coordinates in the cells refcellids [numpts] (0-based; the caller picks the solution cell of the
+ * wanted level-set sign, which is what `nodal_connectivity(mesh, levelsetsign, cellid)` does).  vals [numpts];
+ * grads [numpts][2] physical gradients (transform_gradient with jacobian (jx, jy) = (hx/2, hy/2)). */
+int stefan_interpolate_at_reference_points(int32_t order, const double* nodalvalues, const double* refpoints,
+                                           const int32_t* refcellids, int64_t numpts, double* vals, void* stream);
+int stefan_gradient_at_reference_points(int32_t order, const double* nodalvalues, const double* refpoints,
+                                        const int32_t* refcellids, int64_t numpts, double jx, double jy, double* grads,
+                                        void* stream);
+/* The velocity formulas of robin_interface_velocity/IP_robin_interface_flux_velocity.jl:213-278 at numpts interface
+ * points: velocity_s = -lambda (Tm - vals_s), meanvelocity = their mean, gvelocity = k2 dnT2 - k1 dnT1 with
+ * dnT_s = grads_s . normals.  Any output may be NULL; gvelocity needs grads1, grads2, normals ([numpts][2]). */
+int stefan_front_velocity(int64_t numpts, double lambda, double Tm, double k1, double k2, const double* vals1,
+                          const double* vals2, const double* grads1, const double* grads2, const double* normals,
+                          double* velocity1, double* velocity2, double* meanvelocity, double* gvelocity, void* stream);
 
 /* ------------------------------------------------------------- peer memory
  * Column-slab partition across the GPUs of one NVLink domain, one process per GPU (the

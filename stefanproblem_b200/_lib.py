@@ -135,6 +135,14 @@ _SIGNATURES = {
     "stefan_blocks_l2_error": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(BlocksData)] + [ctypes.c_void_p] * 4),
     "stefan_blocks_cg_solve": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                               ctypes.POINTER(CgParams), ctypes.POINTER(CgResult), ctypes.c_void_p]),
+    "stefan_blocks_interface_l2_error": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(BlocksData)] + [ctypes.c_void_p] * 5),
+    "stefan_interpolate_at_reference_points": (ctypes.c_int, [ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
+                                                              ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                                              ctypes.c_void_p]),
+    "stefan_gradient_at_reference_points": (ctypes.c_int, [ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
+                                                           ctypes.c_void_p, ctypes.c_int64, ctypes.c_double,
+                                                           ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]),
+    "stefan_front_velocity": (ctypes.c_int, [ctypes.c_int64] + [ctypes.c_double] * 4 + [ctypes.c_void_p] * 10),
     "stefan_peer_alloc": (ctypes.c_int, [ctypes.c_int64, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p]),
     "stefan_peer_free": (ctypes.c_int, [ctypes.c_void_p]),
     "stefan_peer_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]),

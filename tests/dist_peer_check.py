@@ -153,6 +153,8 @@ def main():
         # replays of a captured pair of steps (device-resident epochs); interface sums of the last iterate.
         slab = PeerSlab(dop.ndofs, rank, world, nbuf=2)
         slab.bufs[0].copy_(u0[sl])
+        torch.cuda.synchronize()
+        dist.barrier()          # chained halo gate: every rank's initial vector is final before the first step
         half = nsteps // 2
         for k in range(half):
             step_peer_fused(dop, slab, k & 1, (k + 1) & 1, bloc, dt)
