@@ -151,14 +151,19 @@ class SlabProblem:
                 self.x = self.slab.x
                 self.peer = True
 
+    chain_ok = True    # --sync ready: gate on the neighbours' ready flag of the same epoch even in the timed loop
+    push = True        # --no-push: poll the neighbours' flags over NVLink instead of local mailboxes
+
     def step(self, device_epoch=False, chained=False):
         from stefanproblem_b200.distributed import apply_peer_fused
+        chained = chained and SlabProblem.chain_ok
         if self.peer:
             # ONE launch: the kernel publishes my epoch, its edge tiles wait for the neighbours' flags before
             # they read their edge columns over NVLink, its last CTA releases them.  chained (the timed loop:
             # x does not change between its applications): the gate is the neighbours' done value of the
             # previous epoch, posted into this rank's own memory
-            apply_peer_fused(self.dop, self.slab, self.y, device_epoch=device_epoch, chained=chained)
+            apply_peer_fused(self.dop, self.slab, self.y, device_epoch=device_epoch, chained=chained,
+                             push=SlabProblem.push)
         elif self.world > 1:
             # halo trace exchange (NCCL, side stream) overlapped with the interior columns
             self.dop.apply(self.x, self.y)
@@ -625,6 +630,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time plain launches instead of one CUDA-graph replay")
     ap.add_argument("--no-extras", action="store_true", help="skip the weak-scaling and time-loop fields")
+    ap.add_argument("--sync", default="chained", choices=["chained", "ready"],
+                    help="halo gate of the timed loop: the neighbours' done value of the previous epoch (x is static), "
+                         "or their ready flag of the same epoch")
+    ap.add_argument("--no-push", action="store_true", help="poll the neighbours' flags over NVLink (no mailboxes)")
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"], help="N > 1: how the halo columns travel")
     ap.add_argument("--traffic-bytes", type=float, default=None,
                     help="dram bytes per launch from the committed ncu capture (profiles/)")
@@ -639,6 +648,8 @@ def main():
     if args.impl == "reference":
         run_reference(args)
     else:
+        SlabProblem.chain_ok = args.sync == "chained"
+        SlabProblem.push = not args.no_push
         run_ours(args)
 
 

@@ -189,8 +189,13 @@ int stefan_ipdg_apply_host(stefan_ipdg* h, const double* x_host, double* y_host,
  * uniform mesh: divergence + mass + gradient cell operators, inter-element scalar and
  * vector fluxes with the directional switch V0, boundary vector flux.  As in the
  * reference, V0 itself is used as `beta` in the vector flux (LDG_assembly.jl:44-53) and
- * faces between unlike phases are not coupled.  interfacepenalty has no effect on an
- * uncut mesh and is not part of the parameters. */
+ * faces between unlike phases are not coupled by the reference's drivers (they couple phases
+ * only inside cut cells).  aligned_interface != 0 (extension, SURVEY.md 8(d)(ii), the LDG analogue of the
+ * STEFAN_IP_INTERFACE_* terms): the reference's face-level functions
+ * assemble_face_scalar_flux_operator! / assemble_face_vector_flux_operator! are also applied to the
+ * faces between uncut cells of unlike phase, in both orientations, with alpha = interfacepenalty and
+ * the neighbour's conductivity on the neighbour's flux -- what LDG_scalar_flux_operator.jl:241-283 and
+ * LDG_vector_flux_operator.jl:318-355 do with the two sides of a cut cell's interface. */
 typedef struct {
   int32_t nx, ny;
   double hx, hy;
@@ -198,6 +203,8 @@ typedef struct {
   double k1, k2;
   double interiorpenalty, negboundarypenalty, posboundarypenalty;
   double V0x, V0y;
+  double interfacepenalty;      /* used only with aligned_interface */
+  int32_t aligned_interface;
 } stefan_ldg_params;
 
 typedef struct stefan_ldg stefan_ldg;

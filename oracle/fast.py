@@ -197,9 +197,10 @@ def ip_rhs(mesh, order, numqp, k1, k2, penalty, f_qp, g_qp, lam=0.0, Tm=0.0,
 
 # ----------------------------------------------------------------------- LDG
 def ldg_matrix(mesh, order, numqp, k1, k2, interiorpenalty, negboundarypenalty,
-               posboundarypenalty, V0):
-    """CSR of `assemble_LDG_linear_system!` on an uncut mesh (cells of unlike sign
-    are not coupled, exactly as the reference's drivers do)."""
+               posboundarypenalty, V0, interfacepenalty=None):
+    """CSR of `assemble_LDG_linear_system!` on an uncut mesh.  interfacepenalty=None: cells of unlike sign
+    are not coupled, exactly as the reference's drivers do; a number: the face-level functions are also applied
+    to the unlike-phase faces (ldg.assemble_aligned_interface_*_operator)."""
     basis = LagrangeTensorProductBasis(2, order)
     nf = basis.nf
     cq, fq = CellQuadratures(numqp), FaceQuadratures(numqp)
@@ -246,6 +247,21 @@ def ldg_matrix(mesh, order, numqp, k1, k2, interiorpenalty, negboundarypenalty,
                 n = 3 * nf
                 dA = _celldofs(cid[sel], nf, 3)
                 dB = _celldofs(nbr[f][sel], nf, 3)
+                coo.add(dA, dA, L[:n, :n])
+                coo.add(dA, dB, L[:n, n:])
+            seli = has & (sign == s) & (sign[safe] == -s)
+            if interfacepenalty is not None and np.any(seli):
+                kb = k2 if s == 1 else k1
+                q2i = fq[-s, opposite_face(f), 0]
+
+                def iface(sm, k=k, kb=kb, q2i=q2i):
+                    ldg.assemble_face_scalar_flux_operator(sm, basis, q1, q2i, nrm, V0, sa, n1, n2)
+                    ldg.assemble_face_vector_flux_operator(
+                        sm, basis, q1, q2i, nrm, k, kb, interfacepenalty, V0, sa, n1, n2)
+                L = _local_dense(iface, 2 * nf, 3)
+                n = 3 * nf
+                dA = _celldofs(cid[seli], nf, 3)
+                dB = _celldofs(nbr[f][seli], nf, 3)
                 coo.add(dA, dA, L[:n, :n])
                 coo.add(dA, dB, L[:n, n:])
             selb = (~has) & (sign == s)

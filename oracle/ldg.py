@@ -390,6 +390,48 @@ def assemble_boundary_vector_flux_source(sysrhs, rhsfunc, basis, facequads,
                     assemble_cell_rhs(sysrhs, nodeids, 3, rhs, T_DOF)
 
 
+# --------------------------------------------- mesh-aligned interface (extension)
+def _aligned_interface_faces_from_each_cell(mesh, facequads, k1, k2):
+    """Faces between UNCUT cells of unlike sign, seen from each of the two cells (the loop structure of
+    assemble_cell_interface_scalar_flux_operator!, LDG_scalar_flux_operator.jl:241-283, which applies the face
+    function once per orientation).  The reference's drivers couple phases only inside cut cells; on a mesh-aligned
+    interface the same FACE-LEVEL functions are applied to these faces (as for IP).
+    Yields (faceid, k_own, k_nbr, quad1, quad2, nodeids1, nodeids2)."""
+    for cellid in range(mesh.number_of_cells()):
+        s1 = mesh.cell_sign(cellid)
+        for faceid in range(facequads.number_of_faces_per_cell()):
+            nbr = mesh.cell_connectivity(faceid, cellid)
+            if nbr < 0:
+                continue
+            s2 = mesh.cell_sign(nbr)
+            if s1 == s2 or s1 == 0 or s2 == 0:
+                continue
+            yield (faceid, k1 if s1 == 1 else k2, k1 if s2 == 1 else k2,
+                   facequads[s1, faceid, cellid], facequads[s2, opposite_face(faceid), nbr],
+                   mesh.nodal_connectivity(s1, cellid), mesh.nodal_connectivity(s2, nbr))
+
+
+def assemble_aligned_interface_scalar_flux_operator(sysmatrix, basis, facequads, V0, mesh):
+    """assemble_face_scalar_flux_operator! (LDG_scalar_flux_operator.jl:25-107) on unlike-phase faces, both
+    orientations (as :261-282 does for the two sides of a cut cell's interface)."""
+    facedetjac = mesh.face_determinant_jacobian()
+    normals_ref = reference_face_normals()
+    for faceid, _, _, quad1, quad2, n1, n2 in _aligned_interface_faces_from_each_cell(mesh, facequads, None, None):
+        normals, scaleareas = _const_face_data(normals_ref[faceid], facedetjac[faceid], len(quad1))
+        assemble_face_scalar_flux_operator(sysmatrix, basis, quad1, quad2, normals, V0, scaleareas, n1, n2)
+
+
+def assemble_aligned_interface_vector_flux_operator(sysmatrix, basis, facequads, k1, k2, alpha, beta, mesh):
+    """assemble_face_vector_flux_operator! (LDG_vector_flux_operator.jl:47-154) on unlike-phase faces with the own
+    cell's conductivity first and the neighbour's second, alpha = interfacepenalty (as :318-355)."""
+    facedetjac = mesh.face_determinant_jacobian()
+    normals_ref = reference_face_normals()
+    for faceid, ka, kb, quad1, quad2, n1, n2 in _aligned_interface_faces_from_each_cell(mesh, facequads, k1, k2):
+        normals, scaleareas = _const_face_data(normals_ref[faceid], facedetjac[faceid], len(quad1))
+        assemble_face_vector_flux_operator(sysmatrix, basis, quad1, quad2, normals, ka, kb, alpha, beta,
+                                           scaleareas, n1, n2)
+
+
 # ---------------------------------------------------------------- top level
 def assemble_LDG_linear_system(sysmatrix, solverbasis, cellquads, facequads, interfacequads,
                                k1, k2, interiorpenalty, interfacepenalty,

@@ -31,7 +31,7 @@ if __name__ == "__main__":
     for order in [int(a) for a in sys.argv[2:]]:
         for budget in (296,):
             row = []
-            for mq in (0, 1, 2, 4):
-                g, us = run(kind, order, {"STEFAN_CTA_BUDGET": budget, "STEFAN_MIXED_COST_Q": mq})
+            for mq in (0, 1, 4, 8, 16):
+                g, us = run(kind, order, {"STEFAN_CTA_BUDGET": budget, "STEFAN_MIXED_COST_16": mq})
                 row.append(f"mq{mq}: {us:6.2f} us {g:6.1f} G")
             print(f"{kind} p={order} budget {budget}: " + "   ".join(row), flush=True)

@@ -78,6 +78,7 @@ class LdgParams(ctypes.Structure):
         ("interiorpenalty", ctypes.c_double), ("negboundarypenalty", ctypes.c_double),
         ("posboundarypenalty", ctypes.c_double),
         ("V0x", ctypes.c_double), ("V0y", ctypes.c_double),
+        ("interfacepenalty", ctypes.c_double), ("aligned_interface", ctypes.c_int32),
     ]
 
 

@@ -89,6 +89,18 @@ class BlockSystem:
         e = out.cpu().numpy()
         return float(e[0]), float(e[1])
 
+    def interface_l2_error(self, slot_select, u, uex_fq):
+        """interface_L2_error / integral_norm_on_interface over the slots with slot_select != 0
+        (stefan_blocks_interface_l2_error); uex_fq [ncells][nslots][nqf]."""
+        import torch
+        sel = torch.from_numpy(np.ascontiguousarray(slot_select, dtype=np.int8)).cuda()
+        out = torch.empty(2, dtype=torch.float64, device="cuda")
+        ue = self._dev(uex_fq)
+        _lib.check(_lib.lib().stefan_blocks_interface_l2_error(self._h, ctypes.byref(self._bd), _ptr(sel), _ptr(u), _ptr(ue),
+                                                               _ptr(out), _stream_ptr()))
+        e = out.cpu().numpy()
+        return float(e[0]), float(e[1])
+
     def solve(self, b, x0=None, tol=1e-12, maxiter=20000, preconditioner="block_jacobi", check_every=10):
         """`matrix \\ rhs` by preconditioned CG on the device (stefan_blocks_cg_solve); returns (x, info)."""
         import torch

@@ -110,9 +110,15 @@ __device__ __forceinline__ unsigned long long peer_epoch(const unsigned long lon
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(epoch_dev) : "memory");
   return v + 1;
 }
-__device__ __forceinline__ void peer_flag_publish(unsigned long long* flag, unsigned long long epoch) {
+// Publish `epoch` to the local flag and to the neighbours' mailboxes (null = none): ONE system-scope fence, then
+// relaxed stores (fence + relaxed store is a release pattern).  A release store per target costs a system fence
+// each -- measured: three of them at the kernel's start and end added 9 us to a 48 us step at 8 GPUs.
+__device__ __forceinline__ void peer_flag_publish(unsigned long long* flag, unsigned long long epoch,
+                                                  unsigned long long* post0 = nullptr, unsigned long long* post1 = nullptr) {
   __threadfence_system();
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(epoch) : "memory");
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(epoch) : "memory");
+  if (post0) asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(post0), "l"(epoch) : "memory");
+  if (post1) asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(post1), "l"(epoch) : "memory");
 }
 
 __device__ __forceinline__ int phase_at(const int8_t* __restrict__ ph, int ny, int i, int j) {
@@ -303,9 +309,7 @@ __device__ __forceinline__ void march_finish(const ApplyArgs& a) {
       __threadfence();
       if (a.sync_epoch != 0) {
         const unsigned long long epoch = peer_epoch(a.sync_epoch_dev, a.sync_epoch);
-        peer_flag_publish(a.sync_my_done, epoch);
-        if (a.sync_post_done[0]) peer_flag_publish(a.sync_post_done[0], epoch);
-        if (a.sync_post_done[1]) peer_flag_publish(a.sync_post_done[1], epoch);
+        peer_flag_publish(a.sync_my_done, epoch, a.sync_post_done[0], a.sync_post_done[1]);
         if (a.sync_epoch_dev != nullptr) *a.sync_epoch_dev = epoch;  // every CTA has read it: all are done
       }
     }
@@ -523,10 +527,13 @@ int stefan_ipdg_create(const stefan_ipdg_params* p, const int8_t* phase, const i
   cudaError_t e = cudaMalloc(&h->phase_dev, pn);
   if (e == cudaSuccess) e = cudaMemcpy(h->phase_dev, ph.data(), pn, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = h->plan.build(ph.data(), p->nx, p->ny, march_warps(p->order));
-  h->plan.mixed_cost_q = p->order == 1 ? 1 : (p->order == 2 ? 4 : 2);  // measured (quarter columns), see MarchPlan::segments
+  // measured (sixteenths of a column, see MarchPlan::segments; profiles/r2_sweep_mixed_cost.log and the per-CTA
+  // times of the 625 x 5000 slab: a mixed column costs an order-1 warp 3-5 % more, about one column at order 2,
+  // half a column at order 3)
+  h->plan.mixed_cost_q = p->order == 1 ? 1 : (p->order == 2 ? 16 : 8);
   // tiles that touch a neighbouring slab get two columns less: they may have to wait for its flag
-  h->plan.edge_lo_q = h->has_lo ? 8 : 0;
-  h->plan.edge_hi_q = h->has_hi ? 8 : 0;
+  h->plan.edge_lo_q = h->has_lo ? 32 : 0;
+  h->plan.edge_hi_q = h->has_hi ? 32 : 0;
   if (e != cudaSuccess) { h->plan.destroy(); if (h->phase_dev) cudaFree(h->phase_dev); delete h; return fail(ST_CUDA_ERROR, "stefan_ipdg_create: %s", cudaGetErrorString(e)); }
   *out = reinterpret_cast<stefan_ipdg*>(h);
   return ST_OK;

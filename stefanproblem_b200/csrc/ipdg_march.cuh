@@ -366,11 +366,12 @@ ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const 
     }
     // peer halos: everything the stream wrote before this kernel is final -> publish my epoch
     // (warp 0 of CTA 0 always owns a strip: tiles are never empty)
+    // (chained mode: nobody waits for the ready value -- the gate is the previous epoch's done value -- and the
+    // fence would sit on this warp's critical path: the value is stored without one, for bookkeeping only)
     if (a.sync_epoch != 0 && blockIdx.x == 0 && threadIdx.x == 0) {
       const unsigned long long epoch = peer_epoch(a.sync_epoch_dev, a.sync_epoch);
-      peer_flag_publish(a.sync_my_ready, epoch);
-      if (a.sync_post_ready[0]) peer_flag_publish(a.sync_post_ready[0], epoch);
-      if (a.sync_post_ready[1]) peer_flag_publish(a.sync_post_ready[1], epoch);
+      if (a.sync_chained) *reinterpret_cast<volatile unsigned long long*>(a.sync_my_ready) = epoch;
+      else peer_flag_publish(a.sync_my_ready, epoch, a.sync_post_ready[0], a.sync_post_ready[1]);
     }
 
     // prologue: columns c0-1 .. c0+NST-2 into slots 0 .. NST-1

@@ -13,7 +13,8 @@
 //   boundary vector flux  LDG_vector_flux_operator.jl:391-439
 //        e [-k n_d tr q_d,K + alpha_b tr T_K],  alpha_b = (V0 . n < 0) ? negpen : pospen
 // Every cell assembles its own rows for every face with a same-phase neighbour
-// (LDG_scalar_flux_operator.jl:159); faces between unlike phases get nothing.
+// (LDG_scalar_flux_operator.jl:159); faces between unlike phases get nothing -- unless
+// LdgPhys::aligned_interface asks for the face-level interface functions there (T_IFACE entries).
 // With M = sum_q w N N', C = sum_q w N' N' (1-D, reference cell):
 //   y_qx = jy (I (x) M) [ jx (M (x) I) q_x + (Cx (x) I) T ]      Cx = C + face terms along x
 //   y_qy = jx (M (x) I) [ jy (I (x) M) q_y + (I (x) Cy) T ]
@@ -27,6 +28,11 @@ struct LdgPhys {
   double k1, k2;
   double interiorpenalty, negboundarypenalty, posboundarypenalty;
   double V0x, V0y;
+  // mesh-aligned interface (extension): the face-level scalar / vector flux functions also on
+  // the faces between uncut cells of unlike phase, with alpha = interfacepenalty and the neighbour's conductivity
+  // on the neighbour's flux (LDG_scalar_flux_operator.jl:241-283, LDG_vector_flux_operator.jl:318-355)
+  double interfacepenalty = 0.0;
+  int aligned_interface = 0;
 };
 
 template <int P>
@@ -71,11 +77,21 @@ int build_ldg_tables(const RefElem1D& r, double jx, double jy, const LdgPhys& ph
       t->tpK[ax][side][T_SAME] = ph.interiorpenalty;
       t->tpN[ax][side][T_SAME] = -ph.interiorpenalty;
       t->tpK[ax][side][T_BDRY] = alpha_b;
+      if (ph.aligned_interface) {
+        t->sqK[ax][side][T_IFACE] = n * (-0.5 - bp);
+        t->sqN[ax][side][T_IFACE] = n * (-0.5 + bp);
+        t->tpK[ax][side][T_IFACE] = ph.interfacepenalty;
+        t->tpN[ax][side][T_IFACE] = -ph.interfacepenalty;
+      }
       for (int s = 0; s < 2; ++s) {
         const double k = t->kk[s];
         t->tqK[s][ax][side][T_SAME] = n * k * (-0.5 + bn);
         t->tqN[s][ax][side][T_SAME] = n * k * (-0.5 - bn);
         t->tqK[s][ax][side][T_BDRY] = -k * n;
+        if (ph.aligned_interface) {
+          t->tqK[s][ax][side][T_IFACE] = n * k * (-0.5 + bn);
+          t->tqN[s][ax][side][T_IFACE] = n * t->kk[1 - s] * (-0.5 - bn);   // the NEIGHBOUR's conductivity
+        }
       }
     }
   return 0;

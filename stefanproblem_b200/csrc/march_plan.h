@@ -148,7 +148,7 @@ struct MarchPlan {
   }
 
   // Cost-balanced tiles, one per CTA, for columns [cbeg, cend).  A CTA is done when its
-  // slowest warp is; a warp pays 4 cost units per column plus mixed_cost_q units where a strip of
+  // slowest warp is; a warp pays kCol = 16 cost units per column plus mixed_cost_q units where a strip of
   // its group mixes phases (both phase bodies run), plus edge_lo_q / edge_hi_q units on the first /
   // last column of a slab whose halo column comes from a neighbour (the tile may have to wait for
   // the neighbour's flag, so it gets fewer columns).  The loops are memory-bound: measured per-CTA
@@ -158,15 +158,18 @@ struct MarchPlan {
   // whose tiles are currently the most expensive; (2) a group is cut into tiles of EQUAL cost.
   // (Round 1 cut greedily at a common cost T: 625 columns became 12 x 49 + 37 with 17 of 296 CTA
   // slots unused; now 14 x 44-45.)  Cached per column range.
-  int mixed_cost_q = 1;  // quarter columns; set by the kernel's host code before the first apply
+  // all costs in SIXTEENTHS of a column (finer than the tile counts can resolve: with 21 groups and 296 CTA
+  // slots a quarter column of over-estimate per mixed column took two tiles away from two plain groups)
+  static constexpr int kCol = 16;
+  int mixed_cost_q = 4;  // per mixed column; set by the kernel's host code before the first apply
   int min_tile_cols = 4;
   int edge_lo_q = 0, edge_hi_q = 0;
   const SegCache& segments(int cbeg, int cend, int max_ctas) {
     for (const SegCache& c : seg_cache)
       if (c.cbeg == cbeg && c.cend == cend && c.max_ctas == max_ctas) return c;
-    if (const char* e = getenv("STEFAN_MIXED_COST_Q")) mixed_cost_q = atoi(e);
+    if (const char* e = getenv("STEFAN_MIXED_COST_16")) mixed_cost_q = atoi(e);
     if (const char* e = getenv("STEFAN_MIN_TILE_COLS")) min_tile_cols = std::max(1, atoi(e));
-    if (const char* e = getenv("STEFAN_EDGE_COST_Q")) {
+    if (const char* e = getenv("STEFAN_EDGE_COST_16")) {
       if (edge_lo_q) edge_lo_q = atoi(e);
       if (edge_hi_q) edge_hi_q = atoi(e);
     }
@@ -183,7 +186,7 @@ struct MarchPlan {
           const int* mc = mixed_cum.data() + (size_t)sidx * (nx + 1);
           mixed |= mc[c + 1] - mc[c];
         }
-        int64_t v = 4 + (mixed ? mixed_cost_q : 0);
+        int64_t v = kCol + (mixed ? mixed_cost_q : 0);
         if (c == 0) v += edge_lo_q;
         if (c == nx - 1) v += edge_hi_q;
         cg[c - cbeg + 1] = cg[c - cbeg] + v;

@@ -370,7 +370,9 @@ class LDGOperator:
     """Matrix-free `sparse_operator(sysmatrix, mesh, 3)` of a local-DG system on one GPU."""
 
     def __init__(self, mesh, order, numqp, k1, k2, interiorpenalty, negboundarypenalty,
-                 posboundarypenalty, V0, phase_lo=None, phase_hi=None):
+                 posboundarypenalty, V0, phase_lo=None, phase_hi=None, interfacepenalty=None):
+        """interfacepenalty=None: unlike-phase faces are not coupled (the reference's drivers on uncut cells);
+        a number: the face-level interface functions are applied there (mesh-aligned interface)."""
         import torch
         if not torch.cuda.is_available():
             raise _lib.StefanError(-1, "no CUDA device: stefanproblem_b200 has no CPU fallback")
@@ -379,7 +381,9 @@ class LDGOperator:
             nx=mesh.nx, ny=mesh.ny, hx=float(mesh.h[0]), hy=float(mesh.h[1]), order=order, numqp=numqp,
             k1=float(k1), k2=float(k2), interiorpenalty=float(interiorpenalty),
             negboundarypenalty=float(negboundarypenalty), posboundarypenalty=float(posboundarypenalty),
-            V0x=float(V0[0]), V0y=float(V0[1]))
+            V0x=float(V0[0]), V0y=float(V0[1]),
+            interfacepenalty=0.0 if interfacepenalty is None else float(interfacepenalty),
+            aligned_interface=0 if interfacepenalty is None else 1)
         i8 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.int8)  # noqa: E731
         self._plo, self._phi = i8(phase_lo), i8(phase_hi)
         p8 = lambda a: None if a is None else a.ctypes.data_as(_lib.c_int8_p)  # noqa: E731
@@ -469,5 +473,6 @@ def sparse_operator(sysmatrix, mesh, dofspernode):
             raise ValueError("the LDG kernel applies the whole of assemble_LDG_linear_system!; "
                              f"passes recorded: {s.get('terms', 0):#x}")
         return LDGOperator(mesh, s["order"], s["numqp"], s["k1"], s["k2"], s["interiorpenalty"],
-                           s["negboundarypenalty"], s["posboundarypenalty"], s["V0"])
+                           s["negboundarypenalty"], s["posboundarypenalty"], s["V0"],
+                           interfacepenalty=s.get("interfacepenalty"))
     raise ValueError(f"nothing assembled (kind={sysmatrix.kind})")

@@ -371,7 +371,7 @@ def interface_sums_peer(dop, slab, buf, out, timeout_ms=5000):
     return out
 
 
-def apply_peer_fused(dop, slab, out, timeout_ms=5000, device_epoch=False, buf=0, chained=False):
+def apply_peer_fused(dop, slab, out, timeout_ms=5000, device_epoch=False, buf=0, chained=False, push=True):
     """out = A x for the slab vector `slab.bufs[buf]`: ONE kernel launch and nothing else on the stream.
     The kernel publishes the slab's next epoch when it starts, its warps wait for the
     neighbours' epoch right before they fetch the neighbours' edge columns over NVLink, and
@@ -384,7 +384,7 @@ def apply_peer_fused(dop, slab, out, timeout_ms=5000, device_epoch=False, buf=0,
     col = dop.halo.col
     lo = ctypes.c_void_p(slab.peer_column(dop.rank - 1, col, last=True, buf=buf)) if dop.rank > 0 else None
     hi = ctypes.c_void_p(slab.peer_column(dop.rank + 1, col, last=False, buf=buf)) if dop.rank < dop.world - 1 else None
-    sync = slab.sync_block(dop.rank, dop.world, timeout_ms, device_epoch, chained=chained)
+    sync = slab.sync_block(dop.rank, dop.world, timeout_ms, device_epoch, chained=chained, push=push)
     _lib.check(_lib.lib().stefan_ipdg_apply_peer(dop.op._h, ctypes.c_void_p(slab.bufs[buf].data_ptr()),
                                                  ctypes.c_void_p(out.data_ptr()), lo, hi, ctypes.byref(sync),
                                                  _stream_ptr()))

@@ -78,5 +78,21 @@ def assemble_LDG_rhs(sysrhs, sourceterm, boundaryfunc, solverbasis, cellquads, f
                   V0=(float(V0[0]), float(V0[1])))
 
 
+# ---- mesh-aligned interface: the reference's face-level interface functions applied to the faces between uncut
+# ---- cells of unlike phase; both must be called (the kernel applies them together)
+def assemble_aligned_interface_scalar_flux_operator(sysmatrix, basis, facequads, V0, mesh):
+    """assemble_face_scalar_flux_operator! (LDG_scalar_flux_operator.jl:25-107) on unlike-phase faces, both
+    orientations (as :241-283 does for the two sides of a cut cell's interface)."""
+    sysmatrix._merge("ldg", V0=(float(V0[0]), float(V0[1])), **_common(basis, facequads))
+    sysmatrix.spec["aligned_scalar"] = True
+
+
+def assemble_aligned_interface_vector_flux_operator(sysmatrix, basis, facequads, k1, k2, alpha, beta, mesh):
+    """assemble_face_vector_flux_operator! (LDG_vector_flux_operator.jl:47-154) on unlike-phase faces,
+    alpha = interfacepenalty (as :318-355)."""
+    sysmatrix._merge("ldg", k1=float(k1), k2=float(k2), interfacepenalty=float(alpha),
+                     V0=(float(beta[0]), float(beta[1])), **_common(basis, facequads))
+
+
 sparse_operator = _cc.sparse_operator
 rhs_vector = _cc.rhs_vector

@@ -92,6 +92,20 @@ extern "C" int hostcheck_ldg_apply(int order, int nx, int ny, int nq, double jx,
   return 3;
 }
 
+// the same with the mesh-aligned interface terms (LdgPhys::aligned_interface)
+extern "C" int hostcheck_ldg_apply_aligned(int order, int nx, int ny, int nq, double jx, double jy, double k1,
+                                           double k2, double interiorpenalty, double negboundarypenalty,
+                                           double posboundarypenalty, double V0x, double V0y, double interfacepenalty,
+                                           const int8_t* phase, const double* x, double* y) {
+  LdgPhys ph{k1, k2, interiorpenalty, negboundarypenalty, posboundarypenalty, V0x, V0y, interfacepenalty, 1};
+  switch (order) {
+    case 1: return run_ldg<1>(nx, ny, nq, jx, jy, ph, phase, x, y);
+    case 2: return run_ldg<2>(nx, ny, nq, jx, jy, ph, phase, x, y);
+    case 3: return run_ldg<3>(nx, ny, nq, jx, jy, ph, phase, x, y);
+  }
+  return 3;
+}
+
 
 // The host plan of the march kernels (march_plan.h) for a mesh: run lists, fix list and the
 // CTA tiles of the column range [cbeg, cend).  phase: int8 +1/-1 per cell (no halos).

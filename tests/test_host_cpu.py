@@ -122,6 +122,32 @@ def test_ldg_cell_row_functions_match_oracle(hostcheck, order, two_phase, theta)
     assert np.linalg.norm(y - yr) / np.linalg.norm(yr) < 1e-13
 
 
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_ldg_aligned_interface_rows_match_oracle(hostcheck, order):
+    """Mesh-aligned LDG interface (the face-level scalar / vector flux functions on unlike-phase faces,
+    alpha = interfacepenalty, neighbour's conductivity on the neighbour's flux): the kernels' row function with the
+    T_IFACE tables against the oracle (fast.ldg_matrix(interfacepenalty=...), itself equal to the literal drivers
+    oracle/ldg.assemble_aligned_interface_*_operator)."""
+    nx, ny = 7, 6
+    mesh = UniformMesh2D([0, 0], [1.0, 0.8], [nx, ny], (order + 1) ** 2)
+    mesh.cellsign[:] = fast.circle_phase(mesh, (0.5, 0.4), 0.3)
+    V0 = np.array([np.cos(0.4), np.sin(0.4)])
+    k1, k2, ai, an, ap, aif = 1.0, 2.0, 0.7, 0.3, 1.1, 0.9
+    A = fast.ldg_matrix(mesh, order, order + 1, k1, k2, ai, an, ap, V0, interfacepenalty=aif)
+    x = np.random.default_rng(0).uniform(-1, 1, A.shape[0])
+    y = np.zeros_like(x)
+    ph = np.ascontiguousarray(mesh.cellsign, dtype=np.int8)
+    jx, jy = mesh.jacobian()
+    dp, d = ctypes.POINTER(ctypes.c_double), ctypes.c_double
+    rc = hostcheck.hostcheck_ldg_apply_aligned(order, nx, ny, order + 1, d(jx), d(jy), d(k1), d(k2), d(ai), d(an), d(ap),
+                                               d(V0[0]), d(V0[1]), d(aif),
+                                               ph.ctypes.data_as(ctypes.POINTER(ctypes.c_int8)),
+                                               x.ctypes.data_as(dp), y.ctypes.data_as(dp))
+    assert rc == 0
+    yr = A @ x
+    assert np.linalg.norm(y - yr) / np.linalg.norm(yr) < 1e-13
+
+
 def ip_matrix_terms(mesh, order, k1, k2, pen, lam, variant, terms):
     """Oracle matrix for a subset of the reference's assemble passes (literal loops)."""
     from oracle import ip

@@ -42,6 +42,39 @@ def test_apply_matches_oracle(cuda, order, algo, nx, ny, two_phase, theta, pens)
         assert abs(A - B).max() < 1e-13 * abs(A).max()
 
 
+@pytest.mark.parametrize("order", [1, 2, 3])
+@pytest.mark.parametrize("algo", [0, 1])
+@pytest.mark.parametrize("nx,ny", [(7, 6), (33, 65)])
+def test_aligned_interface_apply_matches_oracle(cuda, order, algo, nx, ny):
+    """LDG with the mesh-aligned interface terms (interfacepenalty; stefan_ldg_params.aligned_interface) against the
+    oracle, through the reference-named call surface; the COO seam gives the oracle's matrix."""
+    import torch
+    from stefanproblem_b200 import cutcelldg as cc
+    from stefanproblem_b200 import local_dg as LocalDG
+    omesh = UniformMesh2D([0, 0], [1.0, 0.8], [nx, ny], (order + 1) ** 2)
+    omesh.cellsign[:] = fast.circle_phase(omesh, (0.5, 0.4), 0.3)
+    V0 = np.array([np.cos(0.4), np.sin(0.4)])
+    k1, k2, ai, aif, an, ap = 1.0, 2.0, 0.7, 0.9, 0.3, 1.1
+    A = fast.ldg_matrix(omesh, order, order + 1, k1, k2, ai, an, ap, V0, interfacepenalty=aif)
+    basis = cc.LagrangeTensorProductBasis(2, order)
+    mesh = cc.UniformMesh([0, 0], [1.0, 0.8], [nx, ny], basis, phase=omesh.cellsign)
+    cq, fq = cc.CellQuadratures(mesh, order + 1), cc.FaceQuadratures(mesh, order + 1)
+    sm = cc.SystemMatrix()
+    LocalDG.assemble_LDG_linear_system(sm, basis, cq, fq, None, k1, k2, ai, aif, an, ap, V0, mesh)
+    LocalDG.assemble_aligned_interface_scalar_flux_operator(sm, basis, fq, V0, mesh)
+    LocalDG.assemble_aligned_interface_vector_flux_operator(sm, basis, fq, k1, k2, aif, V0, mesh)
+    op = cc.sparse_operator(sm, mesh, 3)
+    x = np.random.default_rng(0).uniform(-1, 1, A.shape[0])
+    y = op.apply(torch.from_numpy(x).cuda(), algo=algo).cpu().numpy()
+    yr = A @ x
+    assert np.linalg.norm(y - yr) / np.linalg.norm(yr) < 1e-13
+    if algo == 0 and nx * ny <= 42:
+        import scipy.sparse as sp
+        r, c, v = (t.cpu().numpy() for t in op.to_coo())
+        B = sp.coo_matrix((v, (r, c)), shape=A.shape).tocsr()
+        assert abs(A - B).max() < 1e-13 * abs(A).max()
+
+
 @pytest.mark.parametrize("order,nx,ny", [(1, 300, 200), (2, 200, 150), (3, 130, 100)])
 def test_apply_matches_oracle_many_tiles(cuda, order, nx, ny):
     """The march kernel against the ORACLE (vectorised NumPy assembly oracle/fast.py, pinned to the literal
