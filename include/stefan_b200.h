@@ -457,6 +457,11 @@ int stefan_ipdg_apply_peer(stefan_ipdg* h, const double* x, double* y, const dou
  * columns of unew, so two buffers alternating between u and unew need no other ordering). */
 int stefan_ipdg_step(stefan_ipdg* h, const double* u, double* unew, const double* b, double dt, const double* u_lo,
                      const double* u_hi, const stefan_peer_sync* sync, void* stream);
+/* stefan_ipdg_interface_sums with the neighbours' edge columns in peer memory, ordered inside the one launch: the
+ * threads that read a halo column first wait until the flag sync->lo_ready / sync->hi_ready points at has reached
+ * sync->epoch -- point them at DONE-type flags (the neighbour's kernel that wrote its vector is complete). */
+int stefan_ipdg_interface_sums_peer(stefan_ipdg* h, const double* u, const double* u_lo, const double* u_hi,
+                                    const stefan_peer_sync* sync, double* sums_dev, void* stream);
 
 #ifdef __cplusplus
 }

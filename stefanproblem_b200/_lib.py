@@ -123,6 +123,8 @@ _SIGNATURES = {
     "stefan_ipdg_apply_peer": (ctypes.c_int, [ctypes.c_void_p] * 5 + [ctypes.POINTER(PeerSync), ctypes.c_void_p]),
     "stefan_ipdg_step": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p,
                                         ctypes.POINTER(PeerSync), ctypes.c_void_p]),
+    "stefan_ipdg_interface_sums_peer": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.POINTER(PeerSync), ctypes.c_void_p,
+                                                       ctypes.c_void_p]),
     "stefan_blocks_create": (ctypes.c_int, [ctypes.POINTER(BlocksDims), ctypes.POINTER(ctypes.c_void_p)]),
     "stefan_blocks_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "stefan_blocks_ndofs": (ctypes.c_int64, [ctypes.c_void_p]),

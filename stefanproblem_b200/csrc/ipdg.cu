@@ -26,6 +26,7 @@
 #include "../../include/stefan_b200.h"
 #include "common.cuh"
 #include "ipdg_handle.h"
+#include "peer_dev.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -62,6 +63,7 @@ struct ApplyArgs {
   unsigned long long* sync_post_ready[2];
   unsigned long long* sync_post_done[2];
   int sync_chained;  // 1: the halo gate is the neighbours' DONE value of the previous epoch (see stefan_peer_sync)
+  int sync_dev;      // development only (STEFAN_DEV_PEER): 1 = never wait for a flag, 2 = never post one (timing experiments)
   int* sync_status;                          // set to 1 if a wait timed out
   unsigned long long* dbg_times;             // development only: per-CTA {start, prologue, loop, end} globaltimer, or null
   // dynamic tail queue: [0] next fix-list index, [1] CTAs finished; both reset by the last CTA
@@ -80,46 +82,6 @@ struct ApplyArgs {
 // without the attribute.
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-
-// Wait (acquire, system scope) until the neighbour has published `epoch`; bounded.
-__device__ __forceinline__ void peer_flag_wait(const unsigned long long* flag, unsigned long long epoch,
-                                               unsigned long long timeout_ns, int* status) {
-  unsigned long long t0, t, v;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-  for (;;) {
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
-    if (v >= epoch) {
-      // the neighbour's column is fetched next by a bulk copy (asynchronous proxy): order the
-      // acquire (generic proxy) before it
-      asm volatile("fence.proxy.async.global;" ::: "memory");
-      return;
-    }
-    __nanosleep(100);
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    if (t - t0 > timeout_ns) {
-      if (status) atomicExch(status, 1);
-      return;
-    }
-  }
-}
-// the epoch of this launch (call after griddep_wait: the previous launch's last CTA wrote the counter)
-struct ApplyArgs;
-__device__ __forceinline__ unsigned long long peer_epoch(const unsigned long long* epoch_dev, unsigned long long epoch) {
-  if (epoch_dev == nullptr) return epoch;
-  unsigned long long v;
-  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(epoch_dev) : "memory");
-  return v + 1;
-}
-// Publish `epoch` to the local flag and to the neighbours' mailboxes (null = none): ONE system-scope fence, then
-// relaxed stores (fence + relaxed store is a release pattern).  A release store per target costs a system fence
-// each -- measured: three of them at the kernel's start and end added 9 us to a 48 us step at 8 GPUs.
-__device__ __forceinline__ void peer_flag_publish(unsigned long long* flag, unsigned long long epoch,
-                                                  unsigned long long* post0 = nullptr, unsigned long long* post1 = nullptr) {
-  __threadfence_system();
-  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(epoch) : "memory");
-  if (post0) asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(post0), "l"(epoch) : "memory");
-  if (post1) asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(post1), "l"(epoch) : "memory");
-}
 
 __device__ __forceinline__ int phase_at(const int8_t* __restrict__ ph, int ny, int i, int j) {
   return ph[(size_t)(i + 1) * (ny + 2) + (j + 1)];
@@ -231,8 +193,8 @@ __device__ __forceinline__ void fixup_tail(const IpTab<P>& tab, const ApplyArgs&
       const double* pl = (i > 0) ? xc - (size_t)a.ny * NF : a.x_lo + (size_t)j * NF;
       const double* pr = (i < a.nx - 1) ? xc + (size_t)a.ny * NF : a.x_hi + (size_t)j * NF;
       if (a.sync_epoch != 0) {  // peer halos: the neighbour's column must be published
-        if (i == 0 && tL != T_BDRY && a.sync_lo_ready) peer_flag_wait(a.sync_lo_ready, epoch, a.sync_timeout_ns, a.sync_status);
-        if (i == a.nx - 1 && tR != T_BDRY && a.sync_hi_ready) peer_flag_wait(a.sync_hi_ready, epoch, a.sync_timeout_ns, a.sync_status);
+        if (i == 0 && tL != T_BDRY && a.sync_lo_ready && !(a.sync_dev & 1)) peer_flag_wait(a.sync_lo_ready, epoch, a.sync_timeout_ns, a.sync_status);
+        if (i == a.nx - 1 && tR != T_BDRY && a.sync_hi_ready && !(a.sync_dev & 1)) peer_flag_wait(a.sync_hi_ready, epoch, a.sync_timeout_ns, a.sync_status);
       }
       // this lane's node of the cell and of its four neighbours (zeros where there is none)
       X[rd] = xc[node];
@@ -309,7 +271,7 @@ __device__ __forceinline__ void march_finish(const ApplyArgs& a) {
       __threadfence();
       if (a.sync_epoch != 0) {
         const unsigned long long epoch = peer_epoch(a.sync_epoch_dev, a.sync_epoch);
-        peer_flag_publish(a.sync_my_done, epoch, a.sync_post_done[0], a.sync_post_done[1]);
+        if (!(a.sync_dev & 2)) peer_flag_publish(a.sync_my_done, epoch, a.sync_post_done[0], a.sync_post_done[1]);
         if (a.sync_epoch_dev != nullptr) *a.sync_epoch_dev = epoch;  // every CTA has read it: all are done
       }
     }
@@ -493,6 +455,10 @@ int stefan_ipdg_create(const stefan_ipdg_params* p, const int8_t* phase, const i
   h->xh_dev = h->yh_dev = nullptr;
   h->tail_ctr_dev = nullptr;
   h->launch_seq = 0;
+  h->iface_dev = nullptr;
+  h->niface = 0;
+  h->iface_partial_dev = nullptr;
+  h->iface_ctr_dev = nullptr;
   h->host_ready = false;
   h->tab_host = nullptr;
   const int NF = (p->order + 1) * (p->order + 1);
@@ -527,10 +493,27 @@ int stefan_ipdg_create(const stefan_ipdg_params* p, const int8_t* phase, const i
   cudaError_t e = cudaMalloc(&h->phase_dev, pn);
   if (e == cudaSuccess) e = cudaMemcpy(h->phase_dev, ph.data(), pn, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = h->plan.build(ph.data(), p->nx, p->ny, march_warps(p->order));
+  {
+    // the interface faces, owned by their +1 cell (every face is summed exactly once across slabs)
+    std::vector<int2> faces;
+    const int ld = p->ny + 2;
+    const int step[4] = {-1, ld, 1, -ld};  // bottom, right, top, left in the padded array
+    for (int i = 0; i < p->nx; ++i)
+      for (int j = 0; j < p->ny; ++j) {
+        const int8_t* c = ph.data() + (size_t)(i + 1) * ld + (j + 1);
+        if (*c != 1) continue;
+        for (int f = 0; f < 4; ++f)
+          if (c[step[f]] == 2) faces.push_back(make_int2(i * p->ny + j, f));
+      }
+    h->niface = (int)faces.size();
+    if (e == cudaSuccess && h->niface > 0) e = cudaMalloc(&h->iface_dev, faces.size() * sizeof(int2));
+    if (e == cudaSuccess && h->niface > 0)
+      e = cudaMemcpy(h->iface_dev, faces.data(), faces.size() * sizeof(int2), cudaMemcpyHostToDevice);
+  }
   // measured (sixteenths of a column, see MarchPlan::segments; profiles/r2_sweep_mixed_cost.log and the per-CTA
   // times of the 625 x 5000 slab: a mixed column costs an order-1 warp 3-5 % more, about one column at order 2,
   // half a column at order 3)
-  h->plan.mixed_cost_q = p->order == 1 ? 1 : (p->order == 2 ? 16 : 8);
+  h->plan.mixed_cost_q = p->order == 1 ? 4 : (p->order == 2 ? 16 : 8);
   // tiles that touch a neighbouring slab get two columns less: they may have to wait for its flag
   h->plan.edge_lo_q = h->has_lo ? 32 : 0;
   h->plan.edge_hi_q = h->has_hi ? 32 : 0;
@@ -545,6 +528,9 @@ int stefan_ipdg_destroy(stefan_ipdg* hv) {
   if (h->phase_dev) cudaFree(h->phase_dev);
   h->plan.destroy();
   if (h->tail_ctr_dev) cudaFree(h->tail_ctr_dev);
+  if (h->iface_dev) cudaFree(h->iface_dev);
+  if (h->iface_partial_dev) cudaFree(h->iface_partial_dev);
+  if (h->iface_ctr_dev) cudaFree(h->iface_ctr_dev);
   if (h->xh_dev) cudaFree(h->xh_dev);
   if (h->yh_dev) cudaFree(h->yh_dev);
   if (h->host_ready) {
@@ -617,6 +603,8 @@ int stefan_ipdg_apply_peer(stefan_ipdg* hv, const double* x, double* y, const do
     a.sync_post_done[k] = reinterpret_cast<unsigned long long*>(sync->post_done[k]);
   }
   a.sync_chained = sync->chained ? 1 : 0;
+  static const int dev_peer = [] { const char* e = getenv("STEFAN_DEV_PEER"); return e ? atoi(e) : 0; }();
+  a.sync_dev = dev_peer;
   return dispatch_apply(h, a, 0, static_cast<cudaStream_t>(stream));
 }
 

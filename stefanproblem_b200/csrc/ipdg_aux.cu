@@ -17,6 +17,7 @@
 #include "../../include/stefan_b200.h"
 #include "common.cuh"
 #include "ipdg_handle.h"
+#include "peer_dev.cuh"
 
 namespace stefan {
 
@@ -268,53 +269,69 @@ struct IfaceTab {
   double jx, jy, k1, k2, lambda, Tm;
 };
 
+// One launch: one thread per interface face of the handle's list, one partial per block, and the last block to
+// finish (atomic ticket) adds the partials in a fixed order -- deterministic -- and resets the ticket.
+// Peer form (wait_lo / wait_hi non-null): a thread whose -1 neighbour lies in a halo column first waits until the
+// neighbour's flag has reached `epoch` (its kernel that wrote the vector is complete).
+struct IfaceSync {
+  const unsigned long long* wait_lo;
+  const unsigned long long* wait_hi;
+  unsigned long long epoch, timeout_ns;
+  int* status;
+};
+
 __global__ void __launch_bounds__(128)
-ipdg_interface_sums_kernel(const __grid_constant__ IfaceTab t, const int8_t* __restrict__ phase, int nx,
-                           int ny, const double* __restrict__ u, const double* __restrict__ u_lo,
-                           const double* __restrict__ u_hi, double* __restrict__ partial) {
+ipdg_interface_list_kernel(const __grid_constant__ IfaceTab t, const int2* __restrict__ faces, int nfaces, int nx, int ny,
+                           const double* __restrict__ u, const double* __restrict__ u_lo,
+                           const double* __restrict__ u_hi, const IfaceSync sync, double* __restrict__ partial,
+                           unsigned* __restrict__ ticket, double* __restrict__ out) {
   const int n1 = t.n1, nq = t.nq, nf = n1 * n1, P = n1 - 1;
   double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-  const int64_t ncells = (int64_t)nx * ny;
-  for (int64_t cell = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; cell < ncells;
-       cell += (int64_t)gridDim.x * blockDim.x) {
-    const int i = (int)(cell / ny), j = (int)(cell % ny);
-    if (aux_phase_at(phase, ny, i, j) != 1) continue;  // faces are owned by the +1 cell
-    const double* u1 = u + cell * nf;
-    for (int face = 0; face < 4; ++face) {
-      const int di = face == 1 ? 1 : (face == 3 ? -1 : 0), dj = face == 2 ? 1 : (face == 0 ? -1 : 0);
-      if (aux_phase_at(phase, ny, i + di, j + dj) != 2) continue;
-      const double* u2 = (i + di < 0)    ? u_lo + (size_t)j * nf
-                         : (i + di >= nx) ? u_hi + (size_t)j * nf
-                                          : u + ((int64_t)(i + di) * ny + (j + dj)) * nf;
-      const bool xnormal = di != 0, high = (face == 1 || face == 2);
-      const double jn = xnormal ? t.jx : t.jy, sa = xnormal ? t.jy : t.jx;
-      // nodal traces and outward (side-1) normal derivatives along the face, per tangential node
-      for (int q = 0; q < nq; ++q) {
-        double T1 = 0, T2 = 0, d1 = 0, d2 = 0;
-        for (int it = 0; it < n1; ++it) {
-          const double Nt = t.Nq[q][it];
-          double a1 = 0, a2 = 0;  // normal derivative of side 1 / side 2 at tangential node it
-          for (int in = 0; in < n1; ++in) {
-            const int idx1 = xnormal ? in * n1 + it : it * n1 + in;
-            a1 += (high ? t.dNR[in] : -t.dNL[in]) / jn * u1[idx1];
-            a2 += (high ? t.dNL[in] : -t.dNR[in]) / jn * u2[idx1];  // neighbour: opposite end, same direction
-          }
-          const int f1 = high ? P : 0, f2 = high ? 0 : P;
-          T1 += Nt * u1[xnormal ? f1 * n1 + it : it * n1 + f1];
-          T2 += Nt * u2[xnormal ? f2 * n1 + it : it * n1 + f2];
-          d1 += Nt * a1;
-          d2 += Nt * a2;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nfaces; k += gridDim.x * blockDim.x) {
+    const int2 cf = faces[k];
+    const int cell = cf.x, face = cf.y;
+    const int i = cell / ny, j = cell - i * ny;
+    const int di = face == 1 ? 1 : (face == 3 ? -1 : 0), dj = face == 2 ? 1 : (face == 0 ? -1 : 0);
+    const double* u1 = u + (size_t)cell * nf;
+    const double* u2;
+    if (i + di < 0) {
+      if (sync.wait_lo) peer_flag_wait(sync.wait_lo, sync.epoch, sync.timeout_ns, sync.status);
+      u2 = u_lo + (size_t)j * nf;
+    } else if (i + di >= nx) {
+      if (sync.wait_hi) peer_flag_wait(sync.wait_hi, sync.epoch, sync.timeout_ns, sync.status);
+      u2 = u_hi + (size_t)j * nf;
+    } else {
+      u2 = u + ((size_t)(i + di) * ny + (j + dj)) * nf;
+    }
+    const bool xnormal = di != 0, high = (face == 1 || face == 2);
+    const double jn = xnormal ? t.jx : t.jy, sa = xnormal ? t.jy : t.jx;
+    // nodal traces and outward (side-1) normal derivatives along the face, per tangential node
+    for (int q = 0; q < nq; ++q) {
+      double T1 = 0, T2 = 0, d1 = 0, d2 = 0;
+      for (int it = 0; it < n1; ++it) {
+        const double Nt = t.Nq[q][it];
+        double a1 = 0, a2 = 0;  // normal derivative of side 1 / side 2 at tangential node it
+        for (int in = 0; in < n1; ++in) {
+          const int idx1 = xnormal ? in * n1 + it : it * n1 + in;
+          a1 += (high ? t.dNR[in] : -t.dNL[in]) / jn * u1[idx1];
+          a2 += (high ? t.dNL[in] : -t.dNR[in]) / jn * u2[idx1];  // neighbour: opposite end, same direction
         }
-        const double wq = t.w[q] * sa, Tavg = 0.5 * (T1 + T2);
-        s0 += wq;
-        s1 += t.lambda * (t.Tm - Tavg) * wq;
-        s2 += (t.k1 * d1 - t.k2 * d2) * wq;
-        s3 += Tavg * wq;
+        const int f1 = high ? P : 0, f2 = high ? 0 : P;
+        T1 += Nt * u1[xnormal ? f1 * n1 + it : it * n1 + f1];
+        T2 += Nt * u2[xnormal ? f2 * n1 + it : it * n1 + f2];
+        d1 += Nt * a1;
+        d2 += Nt * a2;
       }
+      const double wq = t.w[q] * sa, Tavg = 0.5 * (T1 + T2);
+      s0 += wq;
+      s1 += t.lambda * (t.Tm - Tavg) * wq;
+      s2 += (t.k1 * d1 - t.k2 * d2) * wq;
+      s3 += Tavg * wq;
     }
   }
   // warp shuffle reduction, then one partial per block (fixed order -> deterministic)
   __shared__ double red[4][4];
+  __shared__ bool last;
   double v[4] = {s0, s1, s2, s3};
   for (int k = 0; k < 4; ++k)
     for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], off);
@@ -327,14 +344,16 @@ ipdg_interface_sums_kernel(const __grid_constant__ IfaceTab t, const int8_t* __r
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w][threadIdx.x];
     partial[(size_t)blockIdx.x * 4 + threadIdx.x] = s;
   }
-}
-
-__global__ void ipdg_interface_final_kernel(const double* __restrict__ partial, int nblocks,
-                                            double* __restrict__ out) {
-  if (threadIdx.x < 4) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (last && threadIdx.x < 4) {
+    __threadfence();
     double s = 0;
-    for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * 4 + threadIdx.x];
+    for (unsigned b = 0; b < gridDim.x; ++b) s += partial[(size_t)b * 4 + threadIdx.x];
     out[threadIdx.x] = s;
+    if (threadIdx.x == 0) *ticket = 0;
   }
 }
 
@@ -374,12 +393,8 @@ ipdg_euler_kernel(const __grid_constant__ EulerTab t, int64_t ncells, const doub
 
 extern "C" {
 
-int stefan_ipdg_interface_sums(stefan_ipdg* hv, const double* u, const double* u_lo, const double* u_hi,
-                               double* sums_dev, void* stream) {
-  IpdgHandle* h = reinterpret_cast<IpdgHandle*>(hv);
-  STEFAN_REQUIRE(h && u && sums_dev, "stefan_ipdg_interface_sums: null argument");
-  STEFAN_REQUIRE(h->has_lo == (u_lo != nullptr) && h->has_hi == (u_hi != nullptr),
-                 "stefan_ipdg_interface_sums: halo columns must be given exactly where the handle has halo phases");
+static int interface_sums_impl(IpdgHandle* h, const double* u, const double* u_lo, const double* u_hi,
+                               const stefan_peer_sync* sync, double* sums_dev, cudaStream_t st) {
   IfaceTab t;
   std::memset(&t, 0, sizeof(t));
   t.n1 = h->order + 1;
@@ -398,16 +413,47 @@ int stefan_ipdg_interface_sums(stefan_ipdg* hv, const double* u, const double* u
   t.k2 = h->phys.k2;
   t.lambda = h->phys.lambda;
   t.Tm = h->Tm;
-  const int64_t ncells = (int64_t)h->nx * h->ny;
-  const int blocks = (int)std::min<int64_t>((ncells + 127) / 128, (int64_t)sm_count() * 8);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  double* partial = nullptr;
-  STEFAN_CUDA(cudaMallocAsync(&partial, (size_t)blocks * 4 * sizeof(double), st));
-  ipdg_interface_sums_kernel<<<blocks, 128, 0, st>>>(t, h->phase_dev, h->nx, h->ny, u, u_lo, u_hi, partial);
-  ipdg_interface_final_kernel<<<1, 32, 0, st>>>(partial, blocks, sums_dev);
+  const int blocks = std::max(1, std::min((h->niface + 127) / 128, sm_count() * 4));
+  if (h->iface_partial_dev == nullptr) {
+    STEFAN_CUDA(cudaMalloc(&h->iface_partial_dev, (size_t)sm_count() * 4 * 4 * sizeof(double)));
+    STEFAN_CUDA(cudaMalloc(&h->iface_ctr_dev, sizeof(unsigned)));
+    STEFAN_CUDA(cudaMemset(h->iface_ctr_dev, 0, sizeof(unsigned)));
+  }
+  IfaceSync sy{nullptr, nullptr, 0, 0, nullptr};
+  if (sync != nullptr) {
+    sy.wait_lo = u_lo ? reinterpret_cast<const unsigned long long*>(sync->lo_ready) : nullptr;
+    sy.wait_hi = u_hi ? reinterpret_cast<const unsigned long long*>(sync->hi_ready) : nullptr;
+    sy.epoch = sync->epoch;
+    sy.timeout_ns = (unsigned long long)sync->timeout_ms * 1000000ull;
+    sy.status = sync->status;
+  }
+  ipdg_interface_list_kernel<<<blocks, 128, 0, st>>>(t, h->iface_dev, h->niface, h->nx, h->ny, u, u_lo, u_hi, sy,
+                                                     h->iface_partial_dev, h->iface_ctr_dev, sums_dev);
   STEFAN_CUDA(cudaGetLastError());
-  STEFAN_CUDA(cudaFreeAsync(partial, st));
   return ST_OK;
+}
+
+int stefan_ipdg_interface_sums(stefan_ipdg* hv, const double* u, const double* u_lo, const double* u_hi,
+                               double* sums_dev, void* stream) {
+  IpdgHandle* h = reinterpret_cast<IpdgHandle*>(hv);
+  STEFAN_REQUIRE(h && u && sums_dev, "stefan_ipdg_interface_sums: null argument");
+  STEFAN_REQUIRE(h->has_lo == (u_lo != nullptr) && h->has_hi == (u_hi != nullptr),
+                 "stefan_ipdg_interface_sums: halo columns must be given exactly where the handle has halo phases");
+  return interface_sums_impl(h, u, u_lo, u_hi, nullptr, sums_dev, static_cast<cudaStream_t>(stream));
+}
+
+// The same with the neighbours' columns read from peer memory: the threads that touch a halo column first wait
+// until the flag sync->lo_ready / sync->hi_ready points at has reached sync->epoch (point them at DONE-type flags
+// or mailboxes: the neighbour's kernel that wrote the vector must be complete).  One launch.
+int stefan_ipdg_interface_sums_peer(stefan_ipdg* hv, const double* u, const double* u_lo, const double* u_hi,
+                                    const stefan_peer_sync* sync, double* sums_dev, void* stream) {
+  IpdgHandle* h = reinterpret_cast<IpdgHandle*>(hv);
+  STEFAN_REQUIRE(h && u && sums_dev && sync, "stefan_ipdg_interface_sums_peer: null argument");
+  STEFAN_REQUIRE(h->has_lo == (u_lo != nullptr) && h->has_hi == (u_hi != nullptr),
+                 "stefan_ipdg_interface_sums_peer: halo columns must be given exactly where the handle has halo phases");
+  STEFAN_REQUIRE(sync->timeout_ms > 0 && (!u_lo || sync->lo_ready) && (!u_hi || sync->hi_ready),
+                 "stefan_ipdg_interface_sums_peer: incomplete sync block");
+  return interface_sums_impl(h, u, u_lo, u_hi, sync, sums_dev, static_cast<cudaStream_t>(stream));
 }
 
 int stefan_ipdg_euler_update(stefan_ipdg* hv, double* u, const double* y, const double* b, double dt,

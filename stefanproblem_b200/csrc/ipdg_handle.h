@@ -28,6 +28,12 @@ struct IpdgHandle {
   unsigned* tail_ctr_dev;
   unsigned launch_seq;
   double minv1d[kMaxN1][kMaxN1];  // inverse of the 1-D reference mass matrix (fused explicit step)
+  // interface faces owned by this slab (faces of +1 cells towards a -1 cell, halo columns included):
+  // {cell, face 0 bottom / 1 right / 2 top / 3 left}; partial sums + ticket of the one-launch reduction
+  int2* iface_dev;
+  int niface;
+  double* iface_partial_dev;
+  unsigned* iface_ctr_dev;
   cudaStream_t hs[3];
   cudaEvent_t hev[64];
   bool host_ready;

@@ -263,7 +263,7 @@ ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const 
         mbar_arrive_s(bar);
         return;
       }
-      if (a.sync_epoch != 0 && (k < 0 || k >= a.nx))  // a neighbour's column: wait until it is published
+      if (a.sync_epoch != 0 && (k < 0 || k >= a.nx) && !(a.sync_dev & 1))  // a neighbour's column: wait until it is published
         peer_flag_wait(k < 0 ? a.sync_lo_ready : a.sync_hi_ready,
                        peer_epoch(a.sync_epoch_dev, a.sync_epoch) - (unsigned long long)a.sync_chained,
                        a.sync_timeout_ns, a.sync_status);
@@ -370,7 +370,7 @@ ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const 
     // fence would sit on this warp's critical path: the value is stored without one, for bookkeeping only)
     if (a.sync_epoch != 0 && blockIdx.x == 0 && threadIdx.x == 0) {
       const unsigned long long epoch = peer_epoch(a.sync_epoch_dev, a.sync_epoch);
-      if (a.sync_chained) *reinterpret_cast<volatile unsigned long long*>(a.sync_my_ready) = epoch;
+      if (a.sync_chained || (a.sync_dev & 2)) *reinterpret_cast<volatile unsigned long long*>(a.sync_my_ready) = epoch;
       else peer_flag_publish(a.sync_my_ready, epoch, a.sync_post_ready[0], a.sync_post_ready[1]);
     }
 

@@ -381,7 +381,7 @@ int stefan_ldg_create(const stefan_ldg_params* p, const int8_t* phase, const int
   // The loops are memory-bound at every order: a least-squares fit of the per-CTA loop times of the
   // 457^2 order-3 mesh (profiles/r2_ldg_cta_times.txt) gives 4.15 us per column, +0.29 us per mixed
   // column and 4.3 us per tile -- the second body hides behind the loads.
-  h->plan.mixed_cost_q = p->order == 1 ? 4 : 8;  // sixteenths of a column (sweep: profiles/r2_sweep_mixed_cost.log)
+  h->plan.mixed_cost_q = p->order == 1 ? 4 : 8;   // sixteenths of a column (sweep: profiles/r2_sweep_mixed_cost.log)
   if (e == cudaSuccess) e = h->plan.build(ph.data(), p->nx, p->ny, ldg_march_warps(p->order, h->variant));
   if (e != cudaSuccess) {
     h->plan.destroy();

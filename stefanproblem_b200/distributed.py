@@ -356,18 +356,23 @@ def step_peer_fused(dop, slab, src, dst, b, dt, timeout_ms=5000, device_epoch=Fa
 
 
 def interface_sums_peer(dop, slab, buf, out, timeout_ms=5000):
-    """Front-velocity sums (stefan_ipdg_interface_sums) of slab.bufs[buf] right after the fused kernel of the
-    current epoch wrote it: the neighbours' edge columns are read from peer memory once THEIR kernel of this
-    epoch is complete (their `done` flag, published by its last CTA).  `out`: 4 doubles on the device
-    (this rank's part; all-reduce it)."""
+    """Front-velocity sums (stefan_ipdg_interface_sums_peer) of slab.bufs[buf] right after the fused kernel of the
+    current epoch wrote it: ONE launch; the threads that read a neighbour's edge column wait (inside the kernel) for
+    that neighbour's done value of this epoch in the local mailbox.  `out`: 4 doubles on the device (this rank's
+    part; all-reduce it)."""
     from . import _lib
     from .cutcelldg import _stream_ptr
     col = dop.halo.col
-    slab.wait_released(timeout_ms=timeout_ms)   # neighbours' done flags of the current epoch
-    lo = ctypes.c_void_p(slab.peer_column(dop.rank - 1, col, last=True, buf=buf)) if dop.rank > 0 else None
-    hi = ctypes.c_void_p(slab.peer_column(dop.rank + 1, col, last=False, buf=buf)) if dop.rank < dop.world - 1 else None
-    _lib.check(_lib.lib().stefan_ipdg_interface_sums(dop.op._h, ctypes.c_void_p(slab.bufs[buf].data_ptr()), lo, hi,
-                                                     ctypes.c_void_p(out.data_ptr()), _stream_ptr()))
+    has_lo, has_hi = dop.rank > 0, dop.rank < dop.world - 1
+    lo = ctypes.c_void_p(slab.peer_column(dop.rank - 1, col, last=True, buf=buf)) if has_lo else None
+    hi = ctypes.c_void_p(slab.peer_column(dop.rank + 1, col, last=False, buf=buf)) if has_hi else None
+    sync = _lib.PeerSync()
+    sync.lo_ready = slab.my_flag(3) if has_lo else None     # the neighbours' done values, posted into my slots
+    sync.hi_ready = slab.my_flag(5) if has_hi else None
+    sync.epoch, sync.timeout_ms, sync.status = slab.epoch, int(timeout_ms), slab.status.data_ptr()
+    _lib.check(_lib.lib().stefan_ipdg_interface_sums_peer(dop.op._h, ctypes.c_void_p(slab.bufs[buf].data_ptr()), lo, hi,
+                                                          ctypes.byref(sync), ctypes.c_void_p(out.data_ptr()),
+                                                          _stream_ptr()))
     return out
 
 
