@@ -116,13 +116,13 @@ def column_phase(nx_global, ny, i):
 class SlabProblem:
     """One rank's part of a global nxg x ny mesh: operator, slab vector(s), result vector."""
 
-    def __init__(self, order, nxg, ny, rank, world, want_peer, nbuf=1):
+    def __init__(self, order, nxg, ny, rank, world, want_peer, nbuf=1, bounds=None):
         import torch
         import torch.distributed as dist
         from stefanproblem_b200.distributed import DistributedIPOperator, PeerSlab
         self.rank, self.world, self.order = rank, world, order
         self.dop = DistributedIPOperator(nxg, ny, (1.0, 1.0), order, order + 1, 1.0, 2.0, 1e3 * nxg, 1.0, 0.5,
-                                         lambda i: column_phase(nxg, ny, i), rank, world)
+                                         lambda i: column_phase(nxg, ny, i), rank, world, bounds=bounds)
         self.op = self.dop.op
         self.ndofs = self.op.ndofs
         gen = torch.Generator(device="cuda")
@@ -174,6 +174,21 @@ class SlabProblem:
         if self.slab is not None:
             self.slab.close()
             self.slab = None
+
+    def kernel_seconds(self, reps=30):
+        """This rank's apply kernel alone (no flags, local halo buffers), CUDA events, plain launches."""
+        import torch
+        h = self.dop.halo
+        for _ in range(3):
+            self.op.apply(self.x, out=self.y, x_lo=h.x_lo, x_hi=h.x_hi)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            self.op.apply(self.x, out=self.y, x_lo=h.x_lo, x_hi=h.x_hi)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e-3 / reps
 
 
 def barrier(world):
@@ -278,13 +293,13 @@ def parity_check(prob):
     return max_over_ranks(rel, world), float(chk[0].item()), float(chk[1].item())
 
 
-def time_step_loop(order, nxg, ny, rank, world, steps, warmup):
+def time_step_loop(order, nxg, ny, rank, world, steps, warmup, bounds=None):
     """The explicit time loop that drives the front: per step ONE fused kernel (unew = u + dt Minv (b - A u), the
     neighbours' edge columns of u read over NVLink), then the interface sums of unew and their 4-double all-reduce."""
     import torch
     import torch.distributed as dist
     from stefanproblem_b200.distributed import interface_sums_peer, step_peer_fused
-    prob = SlabProblem(order, nxg, ny, rank, world, want_peer=True, nbuf=2)
+    prob = SlabProblem(order, nxg, ny, rank, world, want_peer=True, nbuf=2, bounds=bounds)
     if world > 1 and not prob.peer:
         prob.close()
         return None
@@ -352,6 +367,21 @@ def run_ours(args):
     nxg = n_x if strong else n_x * world
     want_peer = args.halo == "peer"
     prob = SlabProblem(p, nxg, ny, rank, world, want_peer)
+    # optional cost-balanced slabs (--balance): the slabs' per-column costs differ (exception cells of the interface
+    # and of the domain boundary are not spread evenly over the columns), and every step waits for the slowest
+    # rank.  One measurement of every rank's kernel, one re-partition.
+    bounds, per_rank_ms = None, None
+    if world > 1 and strong and args.balance:
+        from stefanproblem_b200.distributed import balanced_bounds
+        tw = torch.tensor([prob.kernel_seconds(), float(prob.dop.nxl)], dtype=torch.float64, device="cuda")
+        allv = [torch.zeros_like(tw) for _ in range(world)]
+        dist.all_gather(allv, tw)
+        secs, wid = [float(v[0]) for v in allv], [int(v[1]) for v in allv]
+        per_rank_ms = [s_ * 1e3 for s_ in secs]
+        bounds = balanced_bounds(nxg, secs, wid, fixed_seconds=8e-6)
+        prob.close()
+        del prob
+        prob = SlabProblem(p, nxg, ny, rank, world, want_peer, bounds=bounds)
     peer = prob.peer
     ndofs_local = prob.ndofs
     t = torch.tensor([ndofs_local], dtype=torch.float64, device="cuda")
@@ -463,7 +493,7 @@ def run_ours(args):
         p2.close()
     step_loop = None
     if not args.no_extras:
-        step_loop = time_step_loop(p, nxg, ny, rank, world, max(10, args.steps // 2), args.warmup)
+        step_loop = time_step_loop(p, nxg, ny, rank, world, max(10, args.steps // 2), args.warmup, bounds=bounds)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -504,6 +534,7 @@ def run_ours(args):
                          "kernel": f"ipdg_apply_march<{p}, 0> on rank 0's slab ({ndofs_local / 1e6:.1f} M dofs), plain launches"},
             "clocks": clocks,
             "gpu_launches": launches,
+            "slab_bounds": bounds, "per_rank_kernel_ms_equal_slabs": per_rank_ms,
             "parity_max_rel": parity_rel,
             "parity": {"max_rel": parity_rel, "tolerance": 1e-13,
                        "what": ("fused peer halos + march kernel vs NCCL halos + plain per-cell kernel, every rank's slab"
@@ -633,6 +664,10 @@ def main():
     ap.add_argument("--sync", default="chained", choices=["chained", "ready"],
                     help="halo gate of the timed loop: the neighbours' done value of the previous epoch (x is static), "
                          "or their ready flag of the same epoch")
+    ap.add_argument("--balance", action="store_true",
+                    help="N > 1, strong scaling: re-partition the columns by one measurement of every rank's kernel "
+                         "(measured at 8 GPUs: the ranks' kernels differ by 1.4 us of 41 and the re-cut tiles cost more "
+                         "than the balance gains -- 46.2 vs 44.5 us per step -- so equal shares are the default)")
     ap.add_argument("--no-push", action="store_true", help="poll the neighbours' flags over NVLink (no mailboxes)")
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"], help="N > 1: how the halo columns travel")
     ap.add_argument("--traffic-bytes", type=float, default=None,

@@ -124,13 +124,19 @@ module LocalDG
 import ..record!, ..SystemMatrix, ..SystemRHS
 # LDG_assembly.jl:1-91: divergence + mass + gradient cell operators, inter-element scalar and
 # vector fluxes with the switch V0 (passed positionally as `beta`, as the reference does),
-# boundary vector flux; interfacepenalty has no effect on an uncut mesh
+# boundary vector flux; on an uncut mesh the reference's interface passes find no cut cell
 function assemble_LDG_linear_system!(s, basis, cellquads, facequads, interfacequads, k1, k2, interiorpenalty,
                                      interfacepenalty, negboundarypenalty, posboundarypenalty, V0, mesh)
     record!(s, :ldg, 63; order = basis.order, numqp = cellquads.numqp, k1 = k1, k2 = k2,
             interiorpenalty = interiorpenalty, negboundarypenalty = negboundarypenalty,
             posboundarypenalty = posboundarypenalty, V0 = (V0[1], V0[2]))
 end
+# mesh-aligned interface: the face-level functions (LDG_scalar_flux_operator.jl:25-107,
+# LDG_vector_flux_operator.jl:47-154) on the faces between uncut cells of unlike phase
+assemble_aligned_interface_scalar_flux_operator!(s, basis, facequads, V0, mesh) =
+    record!(s, :ldg, 0; V0 = (V0[1], V0[2]))
+assemble_aligned_interface_vector_flux_operator!(s, basis, facequads, k1, k2, alpha, beta, mesh) =
+    record!(s, :ldg, 0; k1 = k1, k2 = k2, interfacepenalty = alpha, V0 = (beta[1], beta[2]))
 end # module LocalDG
 
 # ------------------------------------------------------------------------- C structs
@@ -141,6 +147,7 @@ struct LdgParams           # stefan_ldg_params
     k1::Float64; k2::Float64
     interiorpenalty::Float64; negboundarypenalty::Float64; posboundarypenalty::Float64
     V0x::Float64; V0y::Float64
+    interfacepenalty::Float64; aligned_interface::Int32
 end
 
 mutable struct LDGOperator
@@ -149,7 +156,8 @@ mutable struct LDGOperator
     function LDGOperator(mesh::UniformMesh, sp::Dict{Symbol,Any})
         h = element_size(mesh)
         p = Ref(LdgParams(mesh.nelements[1], mesh.nelements[2], h[1], h[2], sp[:order], sp[:numqp], sp[:k1], sp[:k2],
-                          sp[:interiorpenalty], sp[:negboundarypenalty], sp[:posboundarypenalty], sp[:V0]...))
+                          sp[:interiorpenalty], sp[:negboundarypenalty], sp[:posboundarypenalty], sp[:V0]...,
+                          get(sp, :interfacepenalty, 0.0), haskey(sp, :interfacepenalty) ? 1 : 0))
         out = Ref{Ptr{Cvoid}}(C_NULL)
         check(ccall((:stefan_ldg_create, lib), Cint,
                     (Ref{LdgParams}, Ptr{Int8}, Ptr{Int8}, Ptr{Int8}, Ref{Ptr{Cvoid}}),
@@ -167,6 +175,17 @@ function Base.:*(A::LDGOperator, x::CuVector{Float64})
                 (Ptr{Cvoid}, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, Ptr{Cvoid}),
                 A.handle, x, y, CU_NULL, CU_NULL, CUDA.stream().handle))
     y
+end
+
+"`matrix \\ rhs` for the local-DG system on the device: Schur complement on T + BiCGStab (stefan_ldg_solve)."
+function Base.:\(A::LDGOperator, b::CuVector{Float64}; tol = 1e-12, maxiter = 20000)
+    x = similar(b)
+    res = Ref(CgResult(0, 0.0, 0.0, 0))
+    check(ccall((:stefan_ldg_solve, lib), Cint,
+                (Ptr{Cvoid}, CuPtr{Float64}, CuPtr{Float64}, Ref{CgParams}, Ref{CgResult}, Ptr{Cvoid}),
+                A.handle, b, x, Ref(CgParams(maxiter, tol, 0, 10)), res, CUDA.stream().handle))
+    res[].converged == 1 || @warn "BiCGStab did not converge" res[]
+    x
 end
 
 # ------------------------------------------------------------------ element-block path
@@ -200,6 +219,54 @@ function Base.:*(b::BlockSystem, x::CuVector{Float64})
     check(ccall((:stefan_blocks_apply, lib), Cint, (Ptr{Cvoid}, CuPtr{Float64}, CuPtr{Float64}, Ptr{Cvoid}),
                 b.handle, x, y, CUDA.stream().handle))
     y
+end
+"rhs of assemble_interior_penalty_rhs! + assemble_two_phase_source! + assemble_robin_source! for block data
+(f_qp [ncells][nqv] source samples, g_qp [ncells][nslots][nqf] boundary data; stefan_blocks_rhs)."
+function rhs_vector(b::BlockSystem, data::BlocksData, f_qp::CuVector{Float64}, g_qp::CuVector{Float64}, Tm)
+    out = CUDA.zeros(Float64, b.ndofs)
+    check(ccall((:stefan_blocks_rhs, lib), Cint,
+                (Ptr{Cvoid}, Ref{BlocksData}, CuPtr{Float64}, CuPtr{Float64}, Float64, CuPtr{Float64}, Ptr{Cvoid}),
+                b.handle, Ref(data), f_qp, g_qp, Tm, out, CUDA.stream().handle))
+    out
+end
+"`matrix \\ rhs` for the (symmetric) cut-cell IP system: block-Jacobi CG on the device (stefan_blocks_cg_solve)."
+function Base.:\(b::BlockSystem, rhs::CuVector{Float64}; tol = 1e-12, maxiter = 100000)
+    x = CUDA.zeros(Float64, length(rhs))
+    res = Ref(CgResult(0, 0.0, 0.0, 0))
+    check(ccall((:stefan_blocks_cg_solve, lib), Cint,
+                (Ptr{Cvoid}, CuPtr{Float64}, CuPtr{Float64}, Ref{CgParams}, Ref{CgResult}, Ptr{Cvoid}),
+                b.handle, rhs, x, Ref(CgParams(maxiter, tol, 1, 10)), res, CUDA.stream().handle))
+    res[].converged == 1 || @warn "CG did not converge" res[]
+    x
+end
+"mesh_L2_error / integral_norm_on_mesh over the solution cells' volume points (stefan_blocks_l2_error)."
+function l2_error(b::BlockSystem, data::BlocksData, u::CuVector{Float64}, uex_qp::CuVector{Float64})
+    out = CUDA.zeros(Float64, 2)
+    check(ccall((:stefan_blocks_l2_error, lib), Cint,
+                (Ptr{Cvoid}, Ref{BlocksData}, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, Ptr{Cvoid}),
+                b.handle, Ref(data), u, uex_qp, out, CUDA.stream().handle))
+    Tuple(Array(out))
+end
+
+# ------------------------------------------------- point evaluation / front velocity (IP_postprocess.jl)
+"InteriorPenalty.interpolate_at_reference_points (IP_postprocess.jl:30-52): refpoints 2 x numpts, refcellids 1-based
+solution-cell ids (the caller picks the cell of the wanted level-set sign)."
+function interpolate_at_reference_points(nodalvalues::CuVector{Float64}, basis, refpoints::Matrix{Float64}, refcellids)
+    n = size(refpoints, 2)
+    pts, ids, out = CuArray(vec(refpoints)), CuArray(Int32.(refcellids .- 1)), CUDA.zeros(Float64, n)
+    check(ccall((:stefan_interpolate_at_reference_points, lib), Cint,
+                (Int32, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Int32}, Int64, CuPtr{Float64}, Ptr{Cvoid}),
+                basis.order, nodalvalues, pts, ids, n, out, CUDA.stream().handle))
+    out
+end
+"InteriorPenalty.gradient_at_reference_points (IP_postprocess.jl:1-28): 2 x numpts physical gradients."
+function gradient_at_reference_points(nodalvalues::CuVector{Float64}, basis, refpoints::Matrix{Float64}, refcellids, jacobian)
+    n = size(refpoints, 2)
+    pts, ids, out = CuArray(vec(refpoints)), CuArray(Int32.(refcellids .- 1)), CUDA.zeros(Float64, 2, n)
+    check(ccall((:stefan_gradient_at_reference_points, lib), Cint,
+                (Int32, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Int32}, Int64, Float64, Float64, CuPtr{Float64}, Ptr{Cvoid}),
+                basis.order, nodalvalues, pts, ids, n, jacobian[1], jacobian[2], out, CUDA.stream().handle))
+    out
 end
 
 # ------------------------------------------------------------------------- C structs (IP)
@@ -237,6 +304,15 @@ function Base.:*(A::IPOperator, x::CuVector{Float64})
                 (Ptr{Cvoid}, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, Int32, Ptr{Cvoid}),
                 A.handle, x, y, CU_NULL, CU_NULL, 0, CUDA.stream().handle))
     y
+end
+
+"unew = u + dt Minv (b - A u): the fused explicit step, one pass of the apply kernel (stefan_ipdg_step)."
+function step!(unew::CuVector{Float64}, A::IPOperator, u::CuVector{Float64}, b::CuVector{Float64}, dt)
+    check(ccall((:stefan_ipdg_step, lib), Cint,
+                (Ptr{Cvoid}, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, Float64, CuPtr{Float64}, CuPtr{Float64},
+                 Ptr{Cvoid}, Ptr{Cvoid}),
+                A.handle, u, unew, b, dt, CU_NULL, CU_NULL, C_NULL, CUDA.stream().handle))
+    unew
 end
 
 "y = A x for host vectors (pinned memory recommended); copies are pipelined inside the call."

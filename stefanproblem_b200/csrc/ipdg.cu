@@ -510,10 +510,10 @@ int stefan_ipdg_create(const stefan_ipdg_params* p, const int8_t* phase, const i
     if (e == cudaSuccess && h->niface > 0)
       e = cudaMemcpy(h->iface_dev, faces.data(), faces.size() * sizeof(int2), cudaMemcpyHostToDevice);
   }
-  // measured (sixteenths of a column, see MarchPlan::segments; profiles/r2_sweep_mixed_cost.log and the per-CTA
-  // times of the 625 x 5000 slab: a mixed column costs an order-1 warp 3-5 % more, about one column at order 2,
-  // half a column at order 3)
-  h->plan.mixed_cost_q = p->order == 1 ? 4 : (p->order == 2 ? 16 : 8);
+  // measured (sixteenths of a column, see MarchPlan::segments; profiles/r2_sweep_mixed_cost.log): a quarter column
+  // at order 1, half a column at orders 2 and 3 (order 2: a whole column is 2 % better on the 416-column slab
+  // and 8 % worse on the 3334-column mesh)
+  h->plan.mixed_cost_q = p->order == 1 ? 4 : 8;
   // tiles that touch a neighbouring slab get two columns less: they may have to wait for its flag
   h->plan.edge_lo_q = h->has_lo ? 32 : 0;
   h->plan.edge_hi_q = h->has_hi ? 32 : 0;

@@ -31,6 +31,25 @@ def slab_range(ncols, world, rank):
     return slab_begin(ncols, world, rank), slab_begin(ncols, world, rank + 1)
 
 
+def balanced_bounds(ncols, seconds, widths, fixed_seconds=0.0, min_cols=4):
+    """Column bounds [b_0 = 0, ..., b_world = ncols] that equalise the ranks' kernel times, from one measurement:
+    rank r took seconds[r] for widths[r] columns; model t_r = fixed + c_r * width_r (the per-column cost c_r differs
+    between slabs: exception cells, mixed columns).  Deterministic on every rank (same inputs -> same bounds)."""
+    world = len(seconds)
+    c = [max(seconds[r] - fixed_seconds, 1e-12) / max(widths[r], 1) for r in range(world)]
+    inv = [1.0 / cr for cr in c]
+    scale = ncols / sum(inv)
+    w = [max(min_cols, int(round(scale * v))) for v in inv]
+    # fix the rounding so that the widths add up, taking from / giving to the widest slabs
+    while sum(w) != ncols:
+        k = max(range(world), key=lambda r: w[r]) if sum(w) > ncols else min(range(world), key=lambda r: w[r] * c[r])
+        w[k] += -1 if sum(w) > ncols else 1
+    bounds = [0]
+    for v in w:
+        bounds.append(bounds[-1] + v)
+    return bounds
+
+
 class HaloExchange:
     """Exchange of the first / last cell column of a slab with the left / right neighbour.
 
@@ -84,11 +103,13 @@ class DistributedIPOperator:
     phase_of_column(i) -> int8[ny] gives the phases of global cell column i."""
 
     def __init__(self, nxg, ny, widths, order, numqp, k1, k2, penalty, lam, Tm, phase_of_column,
-                 rank, world, variant="current", terms=255):
+                 rank, world, variant="current", terms=255, bounds=None):
+        """bounds: optional column bounds [b_0 = 0, ..., b_world = nxg] (e.g. `balanced_bounds`); default: equal
+        shares."""
         import torch
         from . import cutcelldg as cc
         self.rank, self.world = rank, world
-        self.i0, self.i1 = slab_range(nxg, world, rank)
+        self.i0, self.i1 = (bounds[rank], bounds[rank + 1]) if bounds is not None else slab_range(nxg, world, rank)
         nxl = self.i1 - self.i0
         hx = widths[0] / nxg
         basis = cc.LagrangeTensorProductBasis(2, order)

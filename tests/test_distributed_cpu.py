@@ -111,3 +111,20 @@ def test_fd_three_node_halos_reproduce_the_global_rows(world):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(ok for _, ok in res)
+
+
+def test_balanced_bounds_properties():
+    """Cost-balanced column slabs (distributed.balanced_bounds): bounds are monotone, cover [0, ncols], equal costs
+    give equal shares, and a rank that was slower per column gets fewer columns."""
+    from stefanproblem_b200.distributed import balanced_bounds
+    b = balanced_bounds(5000, [40e-6] * 8, [625] * 8, fixed_seconds=8e-6)
+    assert b == [0, 625, 1250, 1875, 2500, 3125, 3750, 4375, 5000]
+    secs = [39.6e-6, 42e-6, 41e-6, 40.4e-6, 40.4e-6, 41e-6, 42e-6, 39.6e-6]
+    b = balanced_bounds(5000, secs, [625] * 8, fixed_seconds=8e-6)
+    w = [b[r + 1] - b[r] for r in range(8)]
+    assert b[0] == 0 and b[-1] == 5000 and all(x > 0 for x in w)
+    assert w[1] < w[3] < w[0] and w[1] == w[6] and w[0] == w[7]
+    # the model's predicted times are equal to within one column
+    pred = [8e-6 + (secs[r] - 8e-6) / 625 * w[r] for r in range(8)]
+    assert max(pred) - min(pred) < 1.5 * max(secs) / 625
+    assert balanced_bounds(13, [1.0, 1.0, 5.0], [4, 4, 5])[-1] == 13
