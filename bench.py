@@ -690,7 +690,7 @@ def main():
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel for the default
 # workload, from profiles/ (updated whenever the kernel is re-profiled)
-PROFILED_TRAFFIC_BYTES = 819.482624e6 + 758.8672e6  # profiles/r1_ipdg_p1_march_ncu.csv
+PROFILED_TRAFFIC_BYTES = 812.808704e6 + 755.800832e6  # profiles/r2_ipdg_p1_march_ncu.csv
 
 if __name__ == "__main__":
     main()

@@ -391,6 +391,28 @@ int stefan_gradient_at_reference_points(int32_t order, const double* nodalvalues
 int stefan_front_velocity(int64_t numpts, double lambda, double Tm, double k1, double k2, const double* vals1,
                           const double* vals2, const double* grads1, const double* grads2, const double* normals,
                           double* velocity1, double* velocity2, double* meanvelocity, double* gvelocity, void* stream);
+/* CutCellDG.interpolate_at_reference_points(G, ndofs, ...) for a field with several dofs per node (e.g. the LDG
+ * solution: T, q_x, q_y interleaved): `ncomponents` (<= 3) consecutive components from `first_component` on;
+ * vals [numpts][ncomponents]. */
+int stefan_interpolate_field_at_reference_points(int32_t order, const double* nodalvalues, int32_t dofspernode,
+                                                 int32_t first_component, int32_t ncomponents, const double* refpoints,
+                                                 const int32_t* refcellids, int64_t numpts, double* vals, void* stream);
+/* LocalDG/cylindrical-bc-flux/lagrange_levelset_LDG_interface_flux.jl:266-307: with grads_s = q of side s at the
+ * interface points ([numpts][2]) and the interface normals: normalflux_s = k_s grads_s . n, and the LDG numerical flux
+ * 1/2 (k1 grads1 + k2 grads2) - beta (normalflux2 - normalflux1), beta = edge_switch(V0, n) (LDG_utilities.jl:1-4),
+ * dotted with n.  Any output may be NULL. */
+int stefan_ldg_interface_flux(int64_t numpts, double k1, double k2, double V0x, double V0y, const double* grads1,
+                              const double* grads2, const double* normals, double* normalflux1, double* normalflux2,
+                              double* numericalnormalflux, void* stream);
+/* mesh_L2_error / integral_norm_on_mesh (StefanDG/useful_routines.jl:95-133, :203-221) and uniform_mesh_L2_error /
+ * integral_norm_on_uniform_mesh (StefanRobinIC/useful_routines.jl:52-78) for any field on an uncut mesh: dim 2
+ * (NF = (order+1)^2 nodes, numqp^2 tensor Gauss points per cell, x-point outer) or dim 1; `dofspernode` (<= 3)
+ * interleaved dofs per node (1: IP / DG1D, 3: LDG).  detjac: constant cell det-jacobian, or per-cell values in
+ * cell_detjac [ncells] (DG1D: two element sizes).  uex_qp [ncells][points][dofspernode].  out_dev [2 * dofspernode]:
+ * per component (||u_h - u_ex||, ||u_ex||). */
+int stefan_mesh_l2_error(int32_t dim, int32_t order, int32_t numqp, int64_t ncells, double detjac,
+                         const double* cell_detjac, int32_t dofspernode, const double* u, const double* uex_qp,
+                         double* out_dev, void* stream);
 
 /* ------------------------------------------------------------- peer memory
  * Column-slab partition across the GPUs of one NVLink domain, one process per GPU (the

@@ -66,3 +66,28 @@ def interface_L2_error(order, data, slot_select, u, uex_fq):
                 e2 += (basis(p) @ uc - ue) ** 2 * w
                 n2 += ue ** 2 * w
     return np.sqrt(e2), np.sqrt(n2)
+
+
+def interpolate_field_at_reference_points(nodalvalues, ndofs, basis, refpoints, refcellids):
+    """CutCellDG.interpolate_at_reference_points(G, ndofs, basis, refpoints, refcellids, sign, mesh) as the reference's
+    drivers call it for vector fields (lagrange_levelset_LDG_interface_flux.jl:256-291): nodalvalues [ndofs, nnodes]
+    (the reference's `G`), returns [ndofs, numpts]."""
+    dim, numpts = refpoints.shape
+    nf = basis.nf
+    out = np.zeros((ndofs, numpts))
+    for idx in range(numpts):
+        c = refcellids[idx]
+        out[:, idx] = nodalvalues[:, c * nf:(c + 1) * nf] @ basis(refpoints[:, idx])
+    return out
+
+
+def ldg_interface_flux(grads1, grads2, normals, k1, k2, V0):
+    """lagrange_levelset_LDG_interface_flux.jl:266-307: normalflux1, normalflux2 and the LDG numerical normal flux
+    (beta = LocalDG.edge_switch(V0, normals), LDG_utilities.jl:1-4)."""
+    from .ldg import edge_switch
+    normalflux1 = k1 * np.sum(grads1 * normals, axis=0)
+    normalflux2 = k2 * np.sum(grads2 * normals, axis=0)
+    beta = edge_switch(np.asarray(V0, dtype=float), normals)
+    betaqn = beta * (-normalflux1 + normalflux2)
+    numericalflux = 0.5 * (k1 * grads1 + k2 * grads2) - betaqn
+    return normalflux1, normalflux2, np.sum(numericalflux * normals, axis=0)

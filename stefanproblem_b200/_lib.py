@@ -146,6 +146,14 @@ _SIGNATURES = {
                                                            ctypes.c_void_p, ctypes.c_int64, ctypes.c_double,
                                                            ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]),
     "stefan_front_velocity": (ctypes.c_int, [ctypes.c_int64] + [ctypes.c_double] * 4 + [ctypes.c_void_p] * 10),
+    "stefan_interpolate_field_at_reference_points": (ctypes.c_int, [ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32,
+                                                                    ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
+                                                                    ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                                                    ctypes.c_void_p]),
+    "stefan_ldg_interface_flux": (ctypes.c_int, [ctypes.c_int64] + [ctypes.c_double] * 4 + [ctypes.c_void_p] * 7),
+    "stefan_mesh_l2_error": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int64, ctypes.c_double,
+                                            ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
+                                            ctypes.c_void_p, ctypes.c_void_p]),
     "stefan_peer_alloc": (ctypes.c_int, [ctypes.c_int64, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p]),
     "stefan_peer_free": (ctypes.c_int, [ctypes.c_void_p]),
     "stefan_peer_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]),

@@ -166,6 +166,7 @@ fd_apply_vec(const double* __restrict__ u, const double* __restrict__ u_lo, cons
     }
     if (v >= nvec) continue;
     const unsigned kinds = *reinterpret_cast<const unsigned*>(kind + g0);
+    const bool any_cont = (kinds & (0x01010101u * FD_CONTINUITY)) != 0u;
     double r[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -177,7 +178,8 @@ fd_apply_vec(const double* __restrict__ u, const double* __restrict__ u_lo, cons
       else if (row == FD_BACKWARD) t = (-c[-3] + 4.0 * c[-2] - 5.0 * c[-1] + 2.0 * c[0]) * inv_h2;
       else if (row == FD_FORWARD) t = (2.0 * c[0] - 5.0 * c[1] + 4.0 * c[2] - c[3]) * inv_h2;
       else if (row == FD_IDENTITY) t = c[0];
-      if (kd & FD_CONTINUITY) {
+      // interface rows are a handful per mesh: one test of the packed word keeps the loop off the common path
+      if (any_cont && (kd & FD_CONTINUITY)) {
         for (int q = 0; q < ncont; ++q)
           if (cont[q].node == g0 + k) {
             const double rr = cont[q].r, ss = cont[q].s;

@@ -122,3 +122,29 @@ def test_cylinder_study_small_meshes_against_the_reference_csv(name, prm):
         for order, want in ((1, row[1]), (2, row[2])):
             got = _study(n, order, prm)
             assert 0.7 * want < got < 1.12 * want, (name, n, order, got, want)
+
+
+def test_distance_functions_restated():
+    """StefanDG/useful_routines.jl:26-74 (oracle/geometry.py): signs, closest points, the corner function's branches;
+    the cut-cell generator's phases agree with circle_distance_function (> 0 inside = phase +1)."""
+    from oracle import geometry as geo
+    pts = np.array([[0.1, 0.6, 0.3, 0.9], [0.2, 0.1, 0.4, 0.9]])
+    d = geo.circle_distance_function(pts, [0.0, 0.0], 0.5)
+    assert np.allclose(d, 0.5 - np.hypot(pts[0], pts[1])) and d[0] > 0 > d[1]
+    cp = geo.closest_point_on_arc(pts, [0.0, 0.0], 0.5)
+    assert np.allclose(np.hypot(cp[0], cp[1]), 0.5) and np.allclose(cp[0] * pts[1], cp[1] * pts[0])   # same ray
+    n = np.array([0.6, 0.8])
+    pd = geo.plane_distance_function(pts, n, [0.25, 0.0])
+    on = geo.closest_point_on_plane(pts, n, [0.25, 0.0])
+    assert np.allclose(geo.plane_distance_function(on, n, [0.25, 0.0]), 0.0) and np.allclose(np.linalg.norm(pts - on, axis=0), np.abs(pd))
+    xc = [0.5, 0.5]
+    assert np.isclose(geo.corner_distance_function(np.array([0.1, 0.2]), xc), 0.3)                 # inside the corner: min
+    assert np.isclose(geo.corner_distance_function(np.array([0.9, 0.8]), xc), -np.hypot(0.4, 0.3))  # beyond: -distance
+    assert np.isclose(geo.corner_distance_function(np.array([0.2, 0.9]), xc), -0.4)                 # above: v[2]
+    assert np.isclose(geo.corner_distance_function(np.array([0.9, 0.2]), xc), -0.4)                 # right: v[1]
+    assert np.allclose(geo.corner_distance_function(np.array([[0.1, 0.9], [0.2, 0.8]]), xc), [0.3, -0.5])
+    m = CircleCutMesh([0, 0], [1, 1], [9, 9], [0, 0], 0.5, 2, 1.0, 2.0, 9e3)
+    for sol in range(m.nsol):
+        k = m.data["vol_wts"][sol] != 0
+        dd = geo.circle_distance_function(m.vol_xy[sol][k].T, [0.0, 0.0], 0.5)
+        assert np.all(dd * m.sol_phase[sol] > 0)

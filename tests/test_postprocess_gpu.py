@@ -97,3 +97,77 @@ def test_robin_cylinder_front_velocity_and_interface_error(cuda):
         er, nr = opp.interface_L2_error(order, m.data, ssel, u.cpu().numpy(), uex)
         assert abs(e - er) <= 1e-10 * er + 1e-16 and abs(nn - nr) <= 1e-12 * nr
         assert e / nn < 1e-5
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_ldg_field_interpolation_flux_and_error_norms_match_oracle(cuda, order):
+    """Vector-field interpolation and the LDG numerical interface flux (lagrange_levelset_LDG_interface_flux.jl:256-307)
+    against the literal restatement; mesh_L2_error for a 3-dof-per-node field (useful_routines.jl:95-133) against
+    oracle/norms.py on an LDG-shaped solution vector."""
+    import torch
+    from oracle.mesh import CellQuadratures, UniformMesh2D
+    from oracle.norms import integral_norm_on_mesh, mesh_L2_error
+    from stefanproblem_b200 import cutcelldg as cc
+    from stefanproblem_b200 import postprocess as PP
+    rng = np.random.default_rng(20 + order)
+    nx, ny, npts = 6, 5, 300
+    basis, obasis = cc.LagrangeTensorProductBasis(2, order), OB(2, order)
+    nf, ncells = basis.nf, nx * ny
+    u = rng.uniform(-1, 1, ncells * nf * 3)            # (T, qx, qy) interleaved per node
+    ud = torch.from_numpy(u).cuda()
+    ref = rng.uniform(-1, 1, (2, npts))
+    ids = rng.integers(0, ncells, npts).astype(np.int32)
+    G = u.reshape(-1, 3).T                              # the reference's [ndofs, nnodes] view
+    q = PP.interpolate_field_at_reference_points(ud, 3, 1, 2, basis, ref, ids).cpu().numpy()
+    qr = opp.interpolate_field_at_reference_points(G[1:3], 2, obasis, ref, ids)
+    assert np.abs(q - qr).max() <= 1e-13 * np.abs(qr).max()
+    T = PP.interpolate_field_at_reference_points(ud, 3, 0, 1, basis, ref, ids).cpu().numpy()
+    assert np.abs(T - opp.interpolate_field_at_reference_points(G[0:1], 1, obasis, ref, ids)).max() <= 1e-13
+    q2 = rng.uniform(-1, 1, (2, npts))
+    ang = rng.uniform(0, 2 * np.pi, npts)
+    normals = np.stack([np.cos(ang), np.sin(ang)])
+    V0 = (np.cos(0.7), np.sin(0.7))
+    got = PP.ldg_interface_flux(torch.from_numpy(np.ascontiguousarray(qr)).cuda(), torch.from_numpy(q2).cuda(),
+                                torch.from_numpy(normals).cuda(), 1.0, 2.0, V0)
+    want = opp.ldg_interface_flux(qr, q2, normals, 1.0, 2.0, V0)
+    for a, b in zip(got, want):
+        assert np.abs(a.cpu().numpy() - b).max() <= 1e-13 * np.abs(b).max()
+    # error norms of the three components
+    omesh = UniformMesh2D([0, 0], [1.0, 0.8], [nx, ny], nf)
+    nq = order + 2
+    cq = CellQuadratures(nq)
+    ex = lambda v: np.array([np.sin(v[0]) * v[1], np.cos(v[0] + v[1]), v[0] * v[1] ** 2])  # noqa: E731
+    err_ref = mesh_L2_error(G, ex, obasis, cq, omesh)
+    nrm_ref = integral_norm_on_mesh(ex, cq, omesh, 3)
+    mesh = cc.UniformMesh([0, 0], [1.0, 0.8], [nx, ny], basis)
+    xq, yq = cc.cell_quadrature_points(mesh, nq)
+    uex = np.stack([np.sin(xq) * yq, np.cos(xq + yq), xq * yq ** 2], axis=-1)
+    err, nrm = PP.mesh_l2_error(2, order, nq, ncells, 0.25 * mesh.h[0] * mesh.h[1], 3, ud, uex)
+    assert np.abs(err - err_ref).max() <= 1e-12 * err_ref.max() and np.abs(nrm - nrm_ref).max() <= 1e-12 * nrm_ref.max()
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_dg1d_error_norm_matches_oracle(cuda, order):
+    """uniform_mesh_L2_error / integral_norm_on_uniform_mesh of StefanRobinIC/useful_routines.jl:52-78 (two element
+    sizes either side of the interface) on the device against oracle/dg1d.py."""
+    import torch
+    from oracle import dg1d as od
+    from oracle.basis import interpolation_points, tensor_product_quadrature
+    from stefanproblem_b200 import postprocess as PP
+    ne1, ne2, xi, nq = 5, 7, 0.37, order + 2
+    obasis = OB(1, order)
+    quad = tensor_product_quadrature(1, nq)
+    mesh = od.DGMesh1D(0.0, 1.0, xi, ne1, ne2, interpolation_points(obasis))
+    rng = np.random.default_rng(order)
+    ncells, n1 = ne1 + ne2, order + 1
+    u = rng.uniform(-1, 1, ncells * n1)
+    ex = lambda x: np.sin(3 * x) + x * x  # noqa: E731
+    err_ref = od.uniform_mesh_L2_error(u, ex, obasis, quad, mesh)
+    nrm_ref = od.integral_norm_on_uniform_mesh(ex, quad, mesh)
+    g, _ = np.polynomial.legendre.leggauss(nq)
+    dx = np.array([xi / ne1] * ne1 + [(1.0 - xi) / ne2] * ne2)
+    left = np.concatenate([[0.0], np.cumsum(dx)[:-1]])
+    xq = left[:, None] + 0.5 * dx[:, None] * (1.0 + g[None, :])
+    err, nrm = PP.mesh_l2_error(1, order, nq, ncells, 0.0, 1, torch.from_numpy(u).cuda(), ex(xq)[..., None], cell_detjac=0.5 * dx)
+    assert abs(err[0] - float(np.ravel(err_ref)[0])) <= 1e-12 * float(np.ravel(err_ref)[0])
+    assert abs(nrm[0] - float(np.ravel(nrm_ref)[0])) <= 1e-12 * float(np.ravel(nrm_ref)[0])
