@@ -173,6 +173,22 @@ typedef struct {
 int stefan_ipdg_cg_solve(stefan_ipdg* h, const double* b, double* x, const stefan_cg_params* params,
                          stefan_cg_result* result, void* stream);
 
+/* The same solve across column slabs, one process per GPU: every rank calls it with its slab handle
+ * (created with phase_lo / phase_hi) and its slab of b and x.  Two callbacks carry what crosses the slabs:
+ *   exchange(ctx, v, stream): fill the caller's halo buffers halo_lo / halo_hi (one cell column each, layout of
+ *     stefan_ipdg_apply's x_lo / x_hi) with the neighbours' edge columns of the slab vector v, ordered on `stream`
+ *     (NCCL send / recv, or peer copies); called before every operator application;
+ *   allreduce(ctx, dev, count, stream): sum `count` device doubles over the ranks in place, ordered on `stream`
+ *     (the r.z, r.r and p.Ap sums; everything else in the iteration is rank-local).
+ * Both return 0 on success.  `stream` inside the callbacks is the solver's own stream, not the caller's.  The
+ * residual every rank reads back is the all-reduced one, so all ranks stop at the same iteration.  Null callbacks
+ * on a handle without neighbours: identical to stefan_ipdg_cg_solve (without its CUDA-graph batching). */
+typedef int (*stefan_halo_fn)(void* ctx, const double* v, void* stream);
+typedef int (*stefan_allreduce_fn)(void* ctx, double* dev, int32_t count, void* stream);
+int stefan_ipdg_cg_solve_slab(stefan_ipdg* h, const double* b, double* x, const stefan_cg_params* params,
+                              stefan_cg_result* result, const double* halo_lo, const double* halo_hi,
+                              stefan_halo_fn exchange, stefan_allreduce_fn allreduce, void* ctx, void* stream);
+
 /* mesh_L2_error (useful_routines.jl:95-133) on the device: out2[0] = ||u_h - u_ex||_L2,
  * out2[1] = ||u_ex||_L2 with the cell quadrature of the handle; uex_qp [ncells][numqp*numqp]
  * are the exact solution's samples at the cell quadrature points (layout of f_qp). */

@@ -46,6 +46,10 @@ class CgResult(ctypes.Structure):
     _fields_ = [("iterations", ctypes.c_int32), ("residual_norm", ctypes.c_double), ("rhs_norm", ctypes.c_double),
                 ("converged", ctypes.c_int32)]
 
+# callbacks of stefan_ipdg_cg_solve_slab (include/stefan_b200.h: stefan_halo_fn, stefan_allreduce_fn)
+HALO_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p)
+ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p)
+
 
 class PeerSync(ctypes.Structure):
     """`stefan_peer_sync`."""
@@ -119,6 +123,9 @@ _SIGNATURES = {
                                         ctypes.POINTER(CgParams), ctypes.POINTER(CgResult), ctypes.c_void_p]),
     "stefan_ipdg_cg_solve": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                             ctypes.POINTER(CgParams), ctypes.POINTER(CgResult), ctypes.c_void_p]),
+    "stefan_ipdg_cg_solve_slab": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                 ctypes.POINTER(CgParams), ctypes.POINTER(CgResult), ctypes.c_void_p,
+                                                 ctypes.c_void_p, HALO_FN, ALLREDUCE_FN, ctypes.c_void_p, ctypes.c_void_p]),
     "stefan_ipdg_l2_error": (ctypes.c_int, [ctypes.c_void_p] * 5),
     "stefan_ipdg_apply_peer": (ctypes.c_int, [ctypes.c_void_p] * 5 + [ctypes.POINTER(PeerSync), ctypes.c_void_p]),
     "stefan_ipdg_step": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p,

@@ -15,6 +15,7 @@
 #include "../../include/stefan_b200.h"
 #include "common.cuh"
 #include "ipdg_handle.h"
+#include "krylov.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -39,39 +40,6 @@ __device__ __forceinline__ double block_sum(double v) {
   return s;  // valid in thread 0
 }
 
-// scal layout (device doubles): 0 rz, 1 pAp, 2 alpha, 3 beta, 4 rz_new, 5 rr
-__global__ void __launch_bounds__(kRedThreads)
-cg_dot_kernel(const double* __restrict__ a, const double* __restrict__ b, int64_t n, double* __restrict__ partial) {
-  double s = 0.0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    s += a[i] * b[i];
-  s = block_sum(s);
-  if (threadIdx.x == 0) partial[blockIdx.x] = s;
-}
-
-// mode 0: pAp = sum, alpha = rz / pAp.   mode 1: rz_new = sum(partial), rr = sum(partial2),
-// beta = rz_new / rz, rz = rz_new.       mode 2: rz = sum(partial), rr = sum(partial2) (start).
-__global__ void cg_scalar_kernel(const double* __restrict__ partial, const double* __restrict__ partial2, int nblocks,
-                                 double* __restrict__ scal, int mode) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  double s = 0.0, s2 = 0.0;
-  for (int k = 0; k < nblocks; ++k) s += partial[k];
-  if (partial2)
-    for (int k = 0; k < nblocks; ++k) s2 += partial2[k];
-  if (mode == 0) {
-    scal[1] = s;
-    scal[2] = s != 0.0 ? scal[0] / s : 0.0;
-  } else if (mode == 1) {
-    scal[4] = s;
-    scal[5] = s2;
-    scal[3] = scal[0] != 0.0 ? s / scal[0] : 0.0;
-    scal[0] = s;
-  } else {
-    scal[0] = s;
-    scal[5] = s2;
-  }
-}
-
 // x += alpha p, r -= alpha Ap (skipped when first), z = Binv r per cell, partials of r.z and r.r.
 // One thread per cell; Binv: [162][NF*NF] inverse diagonal blocks, or nullptr (z = r).
 template <int P>
@@ -79,9 +47,9 @@ __global__ void __launch_bounds__(kRedThreads)
 cg_update_kernel(double* __restrict__ x, double* __restrict__ r, double* __restrict__ z, const double* __restrict__ p,
                  const double* __restrict__ Ap, const double* __restrict__ scal, int first,
                  const double* __restrict__ Binv, const int8_t* __restrict__ phase, int nx, int ny,
-                 double* __restrict__ partial_rz, double* __restrict__ partial_rr) {
+                 double* __restrict__ partial) {
   constexpr int NF = (P + 1) * (P + 1);
-  const double alpha = first ? 0.0 : scal[2];
+  const double alpha = first ? 0.0 : scal[kry::S_ALPHA];
   const int64_t ncells = (int64_t)nx * ny;
   double srz = 0.0, srr = 0.0;
   for (int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; cell < ncells;
@@ -123,25 +91,10 @@ cg_update_kernel(double* __restrict__ x, double* __restrict__ r, double* __restr
   }
   srz = block_sum(srz);
   srr = block_sum(srr);
-  if (threadIdx.x == 0) {
-    partial_rz[blockIdx.x] = srz;
-    partial_rr[blockIdx.x] = srr;
+  if (threadIdx.x == 0) {  // (kry::Reducer layout: sum0 = r.z, sum1 = r.r)
+    partial[2 * blockIdx.x] = srz;
+    partial[2 * blockIdx.x + 1] = srr;
   }
-}
-
-// p = z + beta p   (first: p = z)
-__global__ void __launch_bounds__(kRedThreads)
-cg_direction_kernel(double* __restrict__ p, const double* __restrict__ z, const double* __restrict__ scal, int first,
-                    int64_t n) {
-  const double beta = first ? 0.0 : scal[3];
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    p[i] = first ? z[i] : z[i] + beta * p[i];  // (p is uninitialised before the first call)
-}
-
-__global__ void __launch_bounds__(kRedThreads)
-cg_residual_kernel(double* __restrict__ r, const double* __restrict__ b, const double* __restrict__ Ax, int64_t n) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    r[i] = b[i] - Ax[i];
 }
 
 // dense inverse by Gauss-Jordan with partial pivoting; false if singular
@@ -249,15 +202,15 @@ __global__ void l2_final_kernel(const double* __restrict__ pe, const double* __r
 
 using namespace stefan;
 
-extern "C" {
-
-int stefan_ipdg_cg_solve(stefan_ipdg* hv, const double* b, double* x, const stefan_cg_params* prm,
-                         stefan_cg_result* res, void* stream) {
+// One implementation for the single-GPU solve and the column-slab solve (one process per GPU):
+// `exchange` fills the caller's halo buffers with the neighbours' edge columns of a slab vector
+// before every operator application, `allreduce` sums the two dot products of a reduction over
+// the ranks (kry::Reducer's hook).  Both null: the single-GPU solver.
+static int cg_solve_impl(stefan_ipdg* hv, const double* b, double* x, const stefan_cg_params* prm,
+                         stefan_cg_result* res, const double* halo_lo, const double* halo_hi,
+                         stefan_halo_fn exchange, stefan_allreduce_fn allreduce, void* ctx, void* stream) {
   IpdgHandle* h = reinterpret_cast<IpdgHandle*>(hv);
-  STEFAN_REQUIRE(h && b && x && prm && res, "stefan_ipdg_cg_solve: null argument");
-  STEFAN_REQUIRE(!h->has_lo && !h->has_hi, "stefan_ipdg_cg_solve: slab handles are not supported");
-  STEFAN_REQUIRE(prm->max_iterations >= 0 && prm->rel_tolerance >= 0.0, "stefan_ipdg_cg_solve: bad parameters");
-  STEFAN_REQUIRE(prm->preconditioner == 0 || prm->preconditioner == 1, "stefan_ipdg_cg_solve: unknown preconditioner");
+  const bool slab = exchange != nullptr || allreduce != nullptr;
   // The iteration runs on a stream of its own (ordered after the caller's stream): a batch of
   // iterations is captured into a CUDA graph and replayed, which the legacy default stream
   // cannot do.  The call is synchronous, so the caller's stream sees the result on return.
@@ -285,6 +238,14 @@ int stefan_ipdg_cg_solve(stefan_ipdg* hv, const double* b, double* x, const stef
       return fail(ST_CUDA_ERROR, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
     }                                                                                        \
   } while (0)
+#define CG_RC(expr)          \
+  do {                       \
+    rc = (expr);             \
+    if (rc) {                \
+      cleanup();             \
+      return rc;             \
+    }                        \
+  } while (0)
   CG_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   CG_CUDA(cudaEventCreateWithFlags(&ordered, cudaEventDisableTiming));
   CG_CUDA(cudaEventRecord(ordered, caller));
@@ -293,12 +254,12 @@ int stefan_ipdg_cg_solve(stefan_ipdg* hv, const double* b, double* x, const stef
   const int64_t n = h->ndofs;
   const int64_t ncells = (int64_t)h->nx * h->ny;
   const int nblk = (int)std::min<int64_t>((ncells + kRedThreads - 1) / kRedThreads, (int64_t)sm_count() * 8);
-  const int vblk = (int)std::min<int64_t>((n + kRedThreads - 1) / kRedThreads, (int64_t)sm_count() * 8);
   const int64_t ns = (n + 3) / 4 * 4;  // 32-byte aligned vectors (the apply kernel needs 16)
-  const size_t wbytes = (size_t)(4 * ns + 2 * (size_t)std::max(nblk, vblk) + 8) * sizeof(double);
+  const size_t wbytes = (size_t)(4 * ns + 2 * (size_t)nblk + kry::S_COUNT) * sizeof(double);
   CG_CUDA(cudaMalloc(&work, wbytes));
-  double *r = work, *z = r + ns, *p = z + ns, *Ap = p + ns, *part = Ap + ns, *part2 = part + std::max(nblk, vblk),
-         *scal = part2 + std::max(nblk, vblk);
+  double *r = work, *z = r + ns, *p = z + ns, *Ap = p + ns, *part = Ap + ns, *scal = part + 2 * (size_t)nblk;
+  CG_CUDA(cudaMemsetAsync(scal, 0, kry::S_COUNT * sizeof(double), st));
+  const kry::Reducer red{part, scal, nblk, st, allreduce, ctx};
   if (prm->preconditioner == 1) {
     std::vector<double> inv;
     switch (h->order) {
@@ -312,49 +273,55 @@ int stefan_ipdg_cg_solve(stefan_ipdg* hv, const double* b, double* x, const stef
   }
   auto update = [&](int first) {
     switch (h->order) {
-      case 1: cg_update_kernel<1><<<nblk, kRedThreads, 0, st>>>(x, r, z, p, Ap, scal, first, Binv, h->phase_dev, h->nx, h->ny, part, part2); break;
-      case 2: cg_update_kernel<2><<<nblk, kRedThreads, 0, st>>>(x, r, z, p, Ap, scal, first, Binv, h->phase_dev, h->nx, h->ny, part, part2); break;
-      case 3: cg_update_kernel<3><<<nblk, kRedThreads, 0, st>>>(x, r, z, p, Ap, scal, first, Binv, h->phase_dev, h->nx, h->ny, part, part2); break;
+      case 1: cg_update_kernel<1><<<nblk, kRedThreads, 0, st>>>(x, r, z, p, Ap, scal, first, Binv, h->phase_dev, h->nx, h->ny, part); break;
+      case 2: cg_update_kernel<2><<<nblk, kRedThreads, 0, st>>>(x, r, z, p, Ap, scal, first, Binv, h->phase_dev, h->nx, h->ny, part); break;
+      case 3: cg_update_kernel<3><<<nblk, kRedThreads, 0, st>>>(x, r, z, p, Ap, scal, first, Binv, h->phase_dev, h->nx, h->ny, part); break;
     }
   };
+  // Ap = A v on this slab (halo columns of v fetched first)
+  auto apply = [&](const double* v) -> int {
+    if (exchange != nullptr) {
+      int e = exchange(ctx, v, stream);
+      if (e) return fail(ST_BAD_ARGUMENT, "stefan_ipdg_cg_solve_slab: the halo exchange callback returned %d", e);
+    }
+    return stefan_ipdg_apply(hv, v, Ap, halo_lo, halo_hi, 0, stream);
+  };
+  auto hook_failed = [&](int e) {
+    return fail(ST_BAD_ARGUMENT, "stefan_ipdg_cg_solve_slab: the all-reduce callback returned %d", e);
+  };
   // r = b - A x0
-  rc = stefan_ipdg_apply(hv, x, Ap, nullptr, nullptr, 0, stream);
-  if (rc) { cleanup(); return rc; }
-  cg_residual_kernel<<<vblk, kRedThreads, 0, st>>>(r, b, Ap, n);
+  CG_RC(apply(x));
+  kry::residual_kernel<<<nblk, kRedThreads, 0, st>>>(r, b, Ap, n);
   // ||b||
-  cg_dot_kernel<<<vblk, kRedThreads, 0, st>>>(b, b, n, part);
-  cg_scalar_kernel<<<1, 1, 0, st>>>(part, nullptr, vblk, scal, 2);
-  double hs[6];
-  CG_CUDA(cudaMemcpyAsync(hs, scal, sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (int e = red.dot(b, b, nullptr, nullptr, n, kry::P_BB)) { cleanup(); return hook_failed(e); }
+  update(1);  // z = Binv r, r.z, r.r
+  if (int e = red.finish(kry::P_CG_START)) { cleanup(); return hook_failed(e); }
+  kry::cg_p_kernel<<<nblk, kRedThreads, 0, st>>>(p, z, scal, 1, n);
+  double hs[kry::S_COUNT];
+  CG_CUDA(cudaMemcpyAsync(hs, scal, sizeof(hs), cudaMemcpyDeviceToHost, st));
   CG_CUDA(cudaStreamSynchronize(st));
-  const double bnorm = std::sqrt(hs[0]);
-  update(1);  // z = Binv r, rz, rr
-  cg_scalar_kernel<<<1, 1, 0, st>>>(part, part2, nblk, scal, 2);
-  cg_direction_kernel<<<vblk, kRedThreads, 0, st>>>(p, z, scal, 1, n);
-  CG_CUDA(cudaMemcpyAsync(hs, scal, 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
-  CG_CUDA(cudaStreamSynchronize(st));
-  double rnorm = std::sqrt(hs[5]);
+  const double bnorm = std::sqrt(hs[kry::S_BB]);
+  double rnorm = std::sqrt(hs[kry::S_RR]);
   const double target = prm->rel_tolerance * (bnorm > 0 ? bnorm : 1.0);
   const int check = prm->check_every > 0 ? prm->check_every : 10;
   int it = 0;
   auto iterations = [&](int count) -> int {
     for (int k = 0; k < count; ++k) {
-      int rc2 = stefan_ipdg_apply(hv, p, Ap, nullptr, nullptr, 0, stream);
+      int rc2 = apply(p);
       if (rc2) return rc2;
-      cg_dot_kernel<<<vblk, kRedThreads, 0, st>>>(p, Ap, n, part);
-      cg_scalar_kernel<<<1, 1, 0, st>>>(part, nullptr, vblk, scal, 0);
+      if (int e = red.dot(p, Ap, nullptr, nullptr, n, kry::P_CG_ALPHA)) return hook_failed(e);
       update(0);
-      cg_scalar_kernel<<<1, 1, 0, st>>>(part, part2, nblk, scal, 1);
-      cg_direction_kernel<<<vblk, kRedThreads, 0, st>>>(p, z, scal, 0, n);
+      if (int e = red.finish(kry::P_CG_BETA)) return hook_failed(e);
+      kry::cg_p_kernel<<<nblk, kRedThreads, 0, st>>>(p, z, scal, 0, n);
     }
     return ST_OK;
   };
-  // one batch of `check` iterations (6 launches each) as a CUDA graph: one launch per batch;
-  // what makes the small systems of the reference's convergence studies launch-bound
-  const bool use_graph = prm->max_iterations >= check && getenv("STEFAN_CG_NO_GRAPH") == nullptr;
+  // one batch of `check` iterations (8 launches each) as a CUDA graph: one launch per batch;
+  // what makes the small systems of the reference's convergence studies launch-bound.  The slab
+  // form calls back into the host every iteration and is launched plainly.
+  const bool use_graph = !slab && prm->max_iterations >= check && getenv("STEFAN_CG_NO_GRAPH") == nullptr;
   if (use_graph && rnorm > target) {
-    rc = stefan_ipdg_apply(hv, p, Ap, nullptr, nullptr, 0, stream);  // warm-up outside the capture (attributes)
-    if (rc) { cleanup(); return rc; }
+    CG_RC(stefan_ipdg_apply(hv, p, Ap, nullptr, nullptr, 0, stream));  // warm-up outside the capture (attributes)
     CG_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     rc = iterations(check);
     cudaError_t ce = cudaStreamEndCapture(st, &graph);
@@ -367,13 +334,12 @@ int stefan_ipdg_cg_solve(stefan_ipdg* hv, const double* b, double* x, const stef
     if (gexec != nullptr && batch == check) {
       CG_CUDA(cudaGraphLaunch(gexec, st));
     } else {
-      rc = iterations(batch);
-      if (rc) { cleanup(); return rc; }
+      CG_RC(iterations(batch));
     }
     it += batch;
-    CG_CUDA(cudaMemcpyAsync(hs, scal, 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CG_CUDA(cudaMemcpyAsync(hs, scal, sizeof(hs), cudaMemcpyDeviceToHost, st));
     CG_CUDA(cudaStreamSynchronize(st));
-    rnorm = std::sqrt(hs[5]);
+    rnorm = std::sqrt(hs[kry::S_RR]);  // (all-reduced: every rank takes the same decision)
     if (!(rnorm == rnorm)) break;  // NaN: breakdown
   }
   CG_CUDA(cudaGetLastError());
@@ -383,7 +349,34 @@ int stefan_ipdg_cg_solve(stefan_ipdg* hv, const double* b, double* x, const stef
   res->converged = rnorm <= target ? 1 : 0;
   cleanup();
 #undef CG_CUDA
+#undef CG_RC
   return ST_OK;
+}
+
+extern "C" {
+
+int stefan_ipdg_cg_solve(stefan_ipdg* hv, const double* b, double* x, const stefan_cg_params* prm,
+                         stefan_cg_result* res, void* stream) {
+  IpdgHandle* h = reinterpret_cast<IpdgHandle*>(hv);
+  STEFAN_REQUIRE(h && b && x && prm && res, "stefan_ipdg_cg_solve: null argument");
+  STEFAN_REQUIRE(!h->has_lo && !h->has_hi, "stefan_ipdg_cg_solve: slab handles need stefan_ipdg_cg_solve_slab");
+  STEFAN_REQUIRE(prm->max_iterations >= 0 && prm->rel_tolerance >= 0.0, "stefan_ipdg_cg_solve: bad parameters");
+  STEFAN_REQUIRE(prm->preconditioner == 0 || prm->preconditioner == 1, "stefan_ipdg_cg_solve: unknown preconditioner");
+  return cg_solve_impl(hv, b, x, prm, res, nullptr, nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+int stefan_ipdg_cg_solve_slab(stefan_ipdg* hv, const double* b, double* x, const stefan_cg_params* prm,
+                              stefan_cg_result* res, const double* halo_lo, const double* halo_hi,
+                              stefan_halo_fn exchange, stefan_allreduce_fn allreduce, void* ctx, void* stream) {
+  IpdgHandle* h = reinterpret_cast<IpdgHandle*>(hv);
+  STEFAN_REQUIRE(h && b && x && prm && res, "stefan_ipdg_cg_solve_slab: null argument");
+  STEFAN_REQUIRE((!h->has_lo || halo_lo) && (!h->has_hi || halo_hi),
+                 "stefan_ipdg_cg_solve_slab: the handle has a neighbour slab whose halo buffer is null");
+  STEFAN_REQUIRE((!h->has_lo && !h->has_hi) || exchange, "stefan_ipdg_cg_solve_slab: a slab handle needs the halo exchange callback");
+  STEFAN_REQUIRE(prm->max_iterations >= 0 && prm->rel_tolerance >= 0.0, "stefan_ipdg_cg_solve_slab: bad parameters");
+  STEFAN_REQUIRE(prm->preconditioner == 0 || prm->preconditioner == 1, "stefan_ipdg_cg_solve_slab: unknown preconditioner");
+  return cg_solve_impl(hv, b, x, prm, res, h->has_lo ? halo_lo : nullptr, h->has_hi ? halo_hi : nullptr, exchange,
+                       allreduce, ctx, stream);
 }
 
 int stefan_ipdg_l2_error(stefan_ipdg* hv, const double* u, const double* uex_qp, double* out2_dev, void* stream) {

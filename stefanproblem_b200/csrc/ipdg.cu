@@ -347,7 +347,7 @@ static int launch_march(IpdgHandle* h, const IpTab<P>& tab, const ApplyArgs& arg
   const SegTab& segs = sc.tab;
   const int grid = sc.n;
   if (grid <= 0) return fail(ST_UNSUPPORTED, "stefan_ipdg_apply: more than %d strip groups (ny too large)", kMaxMarchCtas);
-  constexpr int smem = MarchSmem<P>::TOTAL;
+  constexpr int smem = MarchSmem<P, MODE>::TOTAL;
   static PerDeviceFlag attr_set;
   if (!attr_set.here()) {
     STEFAN_CUDA(cudaFuncSetAttribute(ipdg_apply_march<P, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

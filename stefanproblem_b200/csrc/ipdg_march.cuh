@@ -98,10 +98,12 @@ struct MarchCfg<3> {
 // SegTab (ipdg_handle.h): one entry per CTA, {strip group, first column, one past the last
 // column, -}, built by the host so that every CTA gets the same COST rather than the same
 // column count (columns where a strip mixes phases run both phase bodies).
-template <int P>
+template <int P, int MODE = 0>
 struct MarchSmem {
   using C = MarchCfg<P>;
-  static constexpr int WARP = C::NST * C::STAGE + 2 * C::OUTB;
+  // P = 2 fused step: one strip of b (30 cells x 72 B), loaded coalesced and read back per cell
+  static constexpr int BBUF = (P == 2 && MODE == 1) ? 30 * 72 + 16 : 0;
+  static constexpr int WARP = C::NST * C::STAGE + 2 * C::OUTB + BBUF;
   // rings (1024-byte aligned for the swizzled tiles) + mbarriers + alignment slack
   static constexpr int TOTAL = C::WARPS * WARP + C::WARPS * C::NST * 8 + 1024;
 };
@@ -211,9 +213,10 @@ ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   // 1024-byte aligned base (swizzle atoms of the tensor tiles)
   const unsigned smem0 = (smem_addr(smem_raw) + 1023u) & ~1023u;
-  const unsigned ring = smem0 + (unsigned)warp * MarchSmem<P>::WARP;
+  const unsigned ring = smem0 + (unsigned)warp * MarchSmem<P, MODE>::WARP;
   [[maybe_unused]] const unsigned obuf = ring + NST * C::STAGE;  // P = 2: two output buffers
-  const unsigned bars = smem0 + (unsigned)C::WARPS * MarchSmem<P>::WARP + (unsigned)warp * NST * 8;
+  [[maybe_unused]] const unsigned bbuf = obuf + 2 * C::OUTB;     // P = 2 fused step: the strip of b
+  const unsigned bars = smem0 + (unsigned)C::WARPS * MarchSmem<P, MODE>::WARP + (unsigned)warp * NST * 8;
   griddep_launch();  // the next kernel of the stream may start its prologue while this one drains
   if (lane == 0) {
 #pragma unroll
@@ -423,6 +426,24 @@ ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const 
     double* yp = a.y + (size_t)c0 * ycol + (size_t)j * NF;
     [[maybe_unused]] const double* bp = a.b + (size_t)c0 * ycol + (size_t)j * NF;
     [[maybe_unused]] const bool bp_valid = a.b != nullptr && lane >= 1 && lane <= kStripCells && j < a.ny;
+    // P = 2 fused step: 72-byte cells make a per-cell read of b touch every 32-byte sector from several
+    // instructions (measured: the fused step at 62 % of the roofline against 79 % for the apply).  The warp
+    // reads the strip's 270 doubles of b COALESCED instead (lane + 32 r), one column ahead, parks them in shared
+    // memory at the top of the column and every lane picks up its own cell for the epilogue.
+    constexpr bool BSTAGE = (P == 2 && MODE == 1);
+    constexpr int BR = BSTAGE ? (kStripCells * NF + 31) / 32 : 1;  // rounds of 32 doubles
+    [[maybe_unused]] double Bnext[BR];
+    [[maybe_unused]] const double* bchunk = a.b + (size_t)c0 * ycol + (size_t)j0 * NF;
+    [[maybe_unused]] const int bvalid = a.b != nullptr ? min(kStripCells, a.ny - j0) * NF : 0;  // doubles of the strip
+    [[maybe_unused]] auto load_b_chunk = [&]() {
+#pragma unroll
+      for (int r = 0; r < BR; ++r) {
+        const int d = lane + 32 * r;
+        Bnext[r] = d < bvalid ? __ldg(bchunk + d) : 0.0;
+      }
+      bchunk += ycol;
+    };
+    if constexpr (BSTAGE) load_b_chunk();
     [[maybe_unused]] char* gstrip = reinterpret_cast<char*>(a.y) + ((size_t)c0 * a.ny + j0) * CB;
     if constexpr (P == 2) shy = (unsigned)(reinterpret_cast<uintptr_t>(gstrip) & 15u);
     [[maybe_unused]] unsigned ob = obuf;
@@ -433,15 +454,19 @@ ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const 
       // fused step: this cell's b, requested before the wait for the next column (in flight
       // behind it); only the lanes whose cells the loop may store
       [[maybe_unused]] double Bc[NF];
-      if constexpr (MODE == 1) {
+      if constexpr (BSTAGE) {
+        // (the previous column's reads of bbuf precede these stores in program order)
+#pragma unroll
+        for (int r = 0; r < BR; ++r) {
+          const int d = lane + 32 * r;
+          if (d < kStripCells * NF) sts_f64(bbuf + 8 * d, Bnext[r]);
+        }
+        __syncwarp();
+        if (c + 1 < c1) load_b_chunk();  // in flight behind the whole column
+      } else if constexpr (MODE == 1) {
         if (bp_valid) {
-          if constexpr (P == 2) {
 #pragma unroll
-            for (int q = 0; q < NF; ++q) Bc[q] = __ldg(bp + q);
-          } else {
-#pragma unroll
-            for (int q = 0; q < NF; q += 4) ld_global_nc_v4(bp + q, Bc + q);
-          }
+          for (int q = 0; q < NF; q += 4) ld_global_nc_v4(bp + q, Bc + q);
         } else {
 #pragma unroll
           for (int q = 0; q < NF; ++q) Bc[q] = 0.0;
@@ -543,6 +568,11 @@ ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const 
           dU[t] = __shfl_down_sync(0xffffffffu, sD[t], 1);
         }
         M::rows(tab, Xc, tL, dL, tR, dR, tD, dD, tU, dU, out);
+        if constexpr (BSTAGE) {
+          const unsigned pb = bbuf + (unsigned)(lane >= 1 && lane <= kStripCells ? lane - 1 : 0) * CB;
+#pragma unroll
+          for (int q = 0; q < NF; ++q) Bc[q] = lds_f64(pb + 8 * q);
+        }
         if constexpr (MODE == 1) step_epilogue<P>(a, Xc, Bc, out);
 
         if constexpr (C::OUTB == 0) {

@@ -385,17 +385,43 @@ ldg_apply_march(const __grid_constant__ LdgTab<P> tab, const LdgMarchArgs a, con
     for (int c = c0; c < c1; ++c) {
       mbar_wait_s(bar_r, par_r);
       const unsigned pn = cell_addr(c + 1, stage_r);
-      double tRT[N1], tRQ[N1];  // right neighbour: T and q_x at its ix = 0 nodes
+      [[maybe_unused]] double tRT[N1], tRQ[N1];  // right neighbour: T and q_x at its ix = 0 nodes
+      if constexpr (P != 3) {  // (order 3 fetches them when its last x-line needs them)
 #pragma unroll
-      for (int q = 0; q < N1; ++q) {
-        tRT[q] = lds_f64(elem_addr(pn, swizzled(c + 1), 3 * q + 0));
-        tRQ[q] = lds_f64(elem_addr(pn, swizzled(c + 1), 3 * q + 1));
+        for (int q = 0; q < N1; ++q) {
+          tRT[q] = lds_f64(elem_addr(pn, swizzled(c + 1), 3 * q + 0));
+          tRQ[q] = lds_f64(elem_addr(pn, swizzled(c + 1), 3 * q + 1));
+        }
       }
       auto body = [&](auto phase_c) {
         constexpr int S = decltype(phase_c)::value;
         const unsigned ms = S ? ((unsigned)cur.w & (unsigned)cur.z) : ((unsigned)cur.w & ~(unsigned)cur.z);
         const bool st = (ms >> lane) & 1;
-        double out[CD];
+        if constexpr (P == 3) {
+          // order 3: rows leave as they complete (ldg_rows_progressive: no spills)
+          ldg_rows_progressive<P, S>(
+              tab, U, tLT, tLQ,
+              [&](int ix, double& dT, double& dQ, double& uT, double& uQ) {
+                dT = __shfl_up_sync(0xffffffffu, U[3 * (ix * N1 + P) + 0], 1);
+                dQ = __shfl_up_sync(0xffffffffu, U[3 * (ix * N1 + P) + 2], 1);
+                uT = __shfl_down_sync(0xffffffffu, U[3 * (ix * N1 + 0) + 0], 1);
+                uQ = __shfl_down_sync(0xffffffffu, U[3 * (ix * N1 + 0) + 2], 1);
+              },
+              [&](double* rT, double* rQ) {
+#pragma unroll
+                for (int q = 0; q < N1; ++q) {
+                  rT[q] = lds_f64(elem_addr(pn, swizzled(c + 1), 3 * q + 0));
+                  rQ[q] = lds_f64(elem_addr(pn, swizzled(c + 1), 3 * q + 1));
+                }
+              },
+              [&](int jx, const double* rows) {
+                if (st) {
+#pragma unroll
+                  for (int q = 0; q < 3 * N1; q += 4)
+                    st_global_v4(yp + 3 * N1 * jx + q, rows[q], rows[q + 1], rows[q + 2], rows[q + 3]);
+                }
+              });
+        } else {
         double tDT[N1], tDQ[N1], tUT[N1], tUQ[N1];
 #pragma unroll
         for (int q = 0; q < N1; ++q) {
@@ -405,6 +431,7 @@ ldg_apply_march(const __grid_constant__ LdgTab<P> tab, const LdgMarchArgs a, con
           tUT[q] = __shfl_down_sync(0xffffffffu, U[3 * (q * N1 + 0) + 0], 1);
           tUQ[q] = __shfl_down_sync(0xffffffffu, U[3 * (q * N1 + 0) + 2], 1);
         }
+        double out[CD];
         ldg_rows_streamed<P, S>(tab, U, tLT, tLQ, tRT, tRQ, tDT, tDQ, tUT, tUQ, out);
         if constexpr (C::OUTB == 0) {
           if (st) {
@@ -441,6 +468,7 @@ ldg_apply_march(const __grid_constant__ LdgTab<P> tab, const LdgMarchArgs a, con
             for (int q = 0; q < CD; ++q) yp[q] = out[q];
           }
         }
+        }  // P != 3
       };
       // mode 1 / 2 / 3 = bit 0 / bit 1 / both: every phase body is instantiated exactly once
       // (instruction-cache footprint)

@@ -290,4 +290,111 @@ void ldg_rows_streamed(const LdgTab<P>& tab, const double* __restrict__ U, const
   ldg_rows_streamed_general<P>(tab, S, T_SAME, T_SAME, T_SAME, T_SAME, U, tLT, tLQ, tRT, tRQ, tDT, tDQ, tUT, tUQ, out);
 }
 
+// The all-interior rows once more, ordered so that the OUTPUT leaves progressively (order 3 of the
+// march kernel: the streamed form above keeps the cell, the whole output and the traces live --
+// 48 + 48 + 32 doubles, which does not fit 255 registers and spilled 292 bytes per thread).
+// First every y-line (fixed ix) is contracted: that consumes q_y and the down / up traces and
+// leaves 2 NF line values.  Then, for one jx after the other, the N1 x-lines' values at ix = jx
+// are formed and the 3 N1 rows of the nodes (jx, 0 .. P) are complete: `emit(jx, rows)` stores
+// them and their registers are free again.  traceR(T, Q) fetches the right neighbour's face
+// values only when jx reaches P.  Live: T and q_x of the cell (2 NF), the y-line values (2 NF),
+// the left traces, 2 N1 line values and 3 N1 rows -- about 90 doubles at order 3.
+template <int P, int S, class TraceDU, class TraceR, class Emit>
+#if defined(__CUDACC__)
+__host__ __device__ __forceinline__
+#else
+inline
+#endif
+void ldg_rows_progressive(const LdgTab<P>& tab, const double* __restrict__ U, const double* __restrict__ tLT,
+                          const double* __restrict__ tLQ, TraceDU&& traceDU, TraceR&& traceR, Emit&& emit) {
+  constexpr int N1 = P + 1;
+  constexpr int NF = N1 * N1;
+  constexpr int tS = T_SAME;
+  const double k = tab.kk[S];
+  double ay[NF], gy[NF];
+#pragma unroll
+  for (int ix = 0; ix < N1; ++ix) {
+    double dT, dQ, uT, uQ;  // the y-neighbours' T and q_y at the face nodes of this line
+    traceDU(ix, dT, dQ, uT, uQ);
+#pragma unroll
+    for (int iy = 0; iy < N1; ++iy) {
+      double cqy = 0.0, g_y = 0.0, mqy = 0.0;
+#pragma unroll
+      for (int c = 0; c < N1; ++c) {
+        const double t = U[3 * (ix * N1 + c) + 0], q = U[3 * (ix * N1 + c) + 2];
+        cqy += tab.C[iy * N1 + c] * t;
+        g_y += tab.C[iy * N1 + c] * q;
+        mqy += tab.My[iy * N1 + c] * q;
+      }
+      g_y *= k;
+      if (iy == 0) {
+        const double t = U[3 * (ix * N1 + 0) + 0], q = U[3 * (ix * N1 + 0) + 2];
+        cqy += tab.sqK[1][0][tS] * t + tab.sqN[1][0][tS] * dT;
+        g_y += tab.tqK[S][1][0][tS] * q + tab.tqN[S][1][0][tS] * dQ + tab.tpK[1][0][tS] * t +
+               tab.tpN[1][0][tS] * dT;
+      }
+      if (iy == P) {
+        const double t = U[3 * (ix * N1 + P) + 0], q = U[3 * (ix * N1 + P) + 2];
+        cqy += tab.sqK[1][1][tS] * t + tab.sqN[1][1][tS] * uT;
+        g_y += tab.tqK[S][1][1][tS] * q + tab.tqN[S][1][1][tS] * uQ + tab.tpK[1][1][tS] * t +
+               tab.tpN[1][1][tS] * uT;
+      }
+      ay[ix * N1 + iy] = cqy + mqy;
+      gy[ix * N1 + iy] = g_y;
+    }
+  }
+#ifndef LDG_PROG_UNROLL
+#define LDG_PROG_UNROLL 1
+#endif
+  constexpr int kUnrollX = LDG_PROG_UNROLL;
+#pragma unroll(kUnrollX)
+  for (int jx = 0; jx < N1; ++jx) {
+    double ax[N1], gx[N1];
+    double tRT[N1], tRQ[N1];
+    if (jx == P) traceR(tRT, tRQ);
+#pragma unroll
+    for (int iy = 0; iy < N1; ++iy) {
+      double cqx = 0.0, g_x = 0.0, mqx = 0.0;
+#pragma unroll
+      for (int b = 0; b < N1; ++b) {
+        const double t = U[3 * (b * N1 + iy) + 0], q = U[3 * (b * N1 + iy) + 1];
+        cqx += tab.C[jx * N1 + b] * t;
+        g_x += tab.C[jx * N1 + b] * q;
+        mqx += tab.Mx[jx * N1 + b] * q;
+      }
+      g_x *= k;
+      if (jx == 0) {
+        const double t = U[3 * (0 * N1 + iy) + 0], q = U[3 * (0 * N1 + iy) + 1];
+        cqx += tab.sqK[0][0][tS] * t + tab.sqN[0][0][tS] * tLT[iy];
+        g_x += tab.tqK[S][0][0][tS] * q + tab.tqN[S][0][0][tS] * tLQ[iy] + tab.tpK[0][0][tS] * t +
+               tab.tpN[0][0][tS] * tLT[iy];
+      }
+      if (jx == P) {
+        const double t = U[3 * (P * N1 + iy) + 0], q = U[3 * (P * N1 + iy) + 1];
+        cqx += tab.sqK[0][1][tS] * t + tab.sqN[0][1][tS] * tRT[iy];
+        g_x += tab.tqK[S][0][1][tS] * q + tab.tqN[S][0][1][tS] * tRQ[iy] + tab.tpK[0][1][tS] * t +
+               tab.tpN[0][1][tS] * tRT[iy];
+      }
+      ax[iy] = cqx + mqx;
+      gx[iy] = g_x;
+    }
+    double rows[3 * N1];
+#pragma unroll
+    for (int iy = 0; iy < N1; ++iy) {
+      double oT = 0.0, oqx = 0.0, oqy = 0.0;
+#pragma unroll
+      for (int c = 0; c < N1; ++c) {
+        oqx += tab.My[iy * N1 + c] * ax[c];
+        oT += tab.My[iy * N1 + c] * gx[c];
+        oqy += tab.Mx[jx * N1 + c] * ay[c * N1 + iy];
+        oT += tab.Mx[jx * N1 + c] * gy[c * N1 + iy];
+      }
+      rows[3 * iy + 0] = oT;
+      rows[3 * iy + 1] = oqx;
+      rows[3 * iy + 2] = oqy;
+    }
+    emit(jx, rows);
+  }
+}
+
 }  // namespace stefan

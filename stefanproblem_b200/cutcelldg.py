@@ -330,6 +330,37 @@ class IPOperator:
         return x, {"iterations": res.iterations, "residual_norm": res.residual_norm, "rhs_norm": res.rhs_norm,
                    "converged": bool(res.converged)}
 
+    def solve_slab(self, b, halo_lo, halo_hi, exchange, allreduce, x0=None, tol=1e-12, maxiter=10000,
+                   preconditioner="block_jacobi", check_every=10):
+        """The same CG across column slabs (stefan_ipdg_cg_solve_slab): this operator is one rank's slab,
+        `exchange(v_ptr, stream_ptr)` fills halo_lo / halo_hi with the neighbours' edge columns of the slab
+        vector at v_ptr, `allreduce(dev_ptr, count, stream_ptr)` sums device doubles over the ranks in place;
+        both are enqueued on the raw stream they are given.  Returns (x, info)."""
+        import torch
+        x = torch.zeros_like(b) if x0 is None else x0.clone()
+        prm = _lib.CgParams(int(maxiter), float(tol), {"none": 0, "block_jacobi": 1}[preconditioner], int(check_every))
+        res = _lib.CgResult()
+        errors = []
+
+        def guard(fn, *a):
+            try:
+                fn(*a)
+                return 0
+            except Exception as e:  # an exception must not unwind through the C frames
+                errors.append(e)
+                return 1
+
+        ex = _lib.HALO_FN(lambda ctx, v, st: guard(exchange, v, st)) if exchange is not None else _lib.HALO_FN()
+        ar = _lib.ALLREDUCE_FN(lambda ctx, d, n, st: guard(allreduce, d, n, st)) if allreduce is not None \
+            else _lib.ALLREDUCE_FN()
+        rc = _lib.lib().stefan_ipdg_cg_solve_slab(self._h, _ptr(b), _ptr(x), ctypes.byref(prm), ctypes.byref(res),
+                                                  _ptr(halo_lo), _ptr(halo_hi), ex, ar, None, _stream_ptr())
+        if errors:
+            raise errors[0]
+        _lib.check(rc)
+        return x, {"iterations": res.iterations, "residual_norm": res.residual_norm, "rhs_norm": res.rhs_norm,
+                   "converged": bool(res.converged)}
+
     def l2_error(self, u, uex_qp):
         """(||u_h - u_ex||_L2, ||u_ex||_L2) with the handle's cell quadrature (mesh_L2_error)."""
         import torch

@@ -150,6 +150,38 @@ class DistributedIPOperator:
         return out
 
 
+def _wrap_device(ptr, n):
+    """torch view of n device doubles at a raw pointer."""
+    import torch
+    return torch.as_tensor(_DevArray(ptr, n), device="cuda")
+
+
+def cg_solve_distributed(dop, b, x0=None, tol=1e-12, maxiter=10000, preconditioner="block_jacobi", check_every=10):
+    r"""`matrix \ rhs` for the global IP-DG system, every rank holding its slab of b and x
+    (stefan_ipdg_cg_solve_slab).  Per iteration one halo exchange of the search direction (NCCL
+    send / recv of one cell column each way) and two all-reduces of two doubles; the operator, the
+    block-Jacobi preconditioner and the vector updates are rank-local kernels.  Collective."""
+    import torch
+    import torch.distributed as dist
+    h = dop.halo
+    col = h.col
+    n = dop.ndofs
+
+    def exchange(v_ptr, stream_ptr):
+        with torch.cuda.stream(torch.cuda.ExternalStream(stream_ptr)):
+            h.exchange(_wrap_device(v_ptr, n))
+
+    def allreduce(dev_ptr, count, stream_ptr):
+        with torch.cuda.stream(torch.cuda.ExternalStream(stream_ptr)):
+            dist.all_reduce(_wrap_device(dev_ptr, count), op=dist.ReduceOp.SUM)
+
+    if dop.world == 1:
+        return dop.op.solve(b, x0=x0, tol=tol, maxiter=maxiter, preconditioner=preconditioner, check_every=check_every)
+    assert h.col == col
+    return dop.op.solve_slab(b, h.x_lo, h.x_hi, exchange, allreduce, x0=x0, tol=tol, maxiter=maxiter,
+                             preconditioner=preconditioner, check_every=check_every)
+
+
 class DistributedFDOperator:
     """The 1-D finite-difference operator (finite-difference.jl:34-116) on `numnodes` global
     nodes, one contiguous node range per rank; the one-sided interface rows reach three nodes,

@@ -187,6 +187,18 @@ def main():
         slab.check()
         dist.barrier()
         slab.close()
+        # `matrix \\ rhs` across the slabs (stefan_ipdg_cg_solve_slab: NCCL halo of the search direction, all-reduced
+        # dot products) against the one-GPU solve of the global system
+        from stefanproblem_b200.distributed import cg_solve_distributed
+        xfull, ifull = full.solve(bfull, tol=1e-11, maxiter=5000, check_every=5)
+        xloc, iloc = cg_solve_distributed(dop, bloc, tol=1e-11, maxiter=5000, check_every=5)
+        assert ifull["converged"] and iloc["converged"], (ifull, iloc)
+        assert abs(ifull["iterations"] - iloc["iterations"]) <= 5, (ifull, iloc)
+        assert float((xloc - xfull[sl]).norm()) <= 1e-8 * float(xfull[sl].norm()), "slab CG differs from the one-GPU solve"
+        if rank == 0:
+            print(f"slab CG order {order}: {iloc['iterations']} iterations (one GPU: {ifull['iterations']}), "
+                  f"residual {iloc['residual_norm']:.2e}", flush=True)
+        dist.barrier()
     # local DG (3 dofs per node): peer halos and NCCL halos
     V0 = (np.cos(0.4), np.sin(0.4))
     for order in (1, 2, 3):

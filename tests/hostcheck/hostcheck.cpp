@@ -180,6 +180,20 @@ static int run_ldg_streamed(int nq, double jx, double jy, LdgPhys ph, int s, con
           ldg_rows_streamed_general<P>(tab, s, tL, tR, tD, tU, U, tLT, tLQ, tRT, tRQ, tDT, tDQ, tUT, tUQ,
                                        out_streamed + (size_t)n * CD);
         }
+  // entry 82: the progressive form (the order-3 march loop), all-interior
+  ldg_cell_rows<P>(tab, s, T_SAME, T_SAME, T_SAME, T_SAME, U, UL, UR, UD, UU, out_general + (size_t)n * CD);
+  auto du = [&](int ix, double& dT, double& dQ, double& uT, double& uQ) {
+    dT = tDT[ix]; dQ = tDQ[ix]; uT = tUT[ix]; uQ = tUQ[ix];
+  };
+  auto tr = [&](double* rT, double* rQ) {
+    for (int q = 0; q < N1; ++q) { rT[q] = tRT[q]; rQ[q] = tRQ[q]; }
+  };
+  double* op = out_streamed + (size_t)n * CD;
+  auto emit = [&](int jx, const double* rows) {
+    for (int q = 0; q < 3 * N1; ++q) op[3 * N1 * jx + q] = rows[q];
+  };
+  if (s == 0) ldg_rows_progressive<P, 0>(tab, U, tLT, tLQ, du, tr, emit);
+  else ldg_rows_progressive<P, 1>(tab, U, tLT, tLQ, du, tr, emit);
   return 0;
 }
 

@@ -272,7 +272,8 @@ def test_ldg_streamed_rows_equal_general_rows(hostcheck, order, s):
     rng = np.random.default_rng(order * 10 + s)
     cd = 3 * (order + 1) ** 2
     x9 = rng.uniform(-1, 1, 9 * cd)
-    g, st = np.zeros(82 * cd), np.zeros(82 * cd)  # T_SAME everywhere, then all 81 face-type combinations
+    # T_SAME everywhere, then all 81 face-type combinations, then the progressive form (order-3 march loop)
+    g, st = np.zeros(83 * cd), np.zeros(83 * cd)
     d = ctypes.c_double
     dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))  # noqa: E731
     rc = hostcheck.hostcheck_ldg_streamed(order, order + 1, d(0.013), d(0.021), d(1.0), d(2.0), d(0.7), d(0.3), d(1.1),

@@ -470,3 +470,84 @@ def test_ip_convergence_csv_reproduced_from_the_gpu(cuda):
             err, _ = op.l2_error(torch.from_numpy(sol).cuda(), uex)
             tol = 1e-10 if n <= 9 else 5e-9
             assert abs(err - want) / want < tol, (n, order, err, want)
+
+
+@pytest.mark.parametrize("order,preconditioner", [(1, "block_jacobi"), (2, "block_jacobi"), (3, "none")])
+def test_cg_across_two_slabs_equals_single_solve(cuda, order, preconditioner):
+    """stefan_ipdg_cg_solve_slab: two slab handles, each driven by its own host thread (standing in for
+    the two processes of a two-GPU run), the halo exchange and the all-reduce callbacks implemented with
+    copies between the slabs' vectors and a host barrier.  Same iteration as the one-handle solve: equal
+    iteration counts (to the check granularity) and solutions equal to the solver tolerance."""
+    import threading
+    import torch
+    from stefanproblem_b200 import cutcelldg as cc
+    from stefanproblem_b200.distributed import _wrap_device
+    nx, ny, cut, nq = 21, 17, 9, order + 1
+    basis = cc.LagrangeTensorProductBasis(2, order)
+    omesh = UniformMesh2D([0, 0], [1, 1], [nx, ny], basis.nf)
+    P = fast.circle_phase(omesh).reshape(nx, ny)
+    pen, lam, Tm = 10.0 * nx * (order + 1) ** 2, 1.0, 0.5
+    mk = lambda m, **kw: cc.IPOperator(m, order, nq, 1.0, 2.0, pen, lam, Tm, "current", ALL, **kw)  # noqa: E731
+    full = mk(cc.UniformMesh([0, 0], [1, 1], [nx, ny], basis, phase=P.ravel()))
+    ops = [mk(cc.UniformMesh([0, 0], [cut / nx, 1], [cut, ny], basis, phase=P[:cut].ravel()), phase_hi=P[cut]),
+           mk(cc.UniformMesh([cut / nx, 0], [1 - cut / nx, 1], [nx - cut, ny], basis, phase=P[cut:].ravel()),
+              phase_lo=P[cut - 1])]
+    col = ny * basis.nf
+    b = torch.from_numpy(np.random.default_rng(3).uniform(-1, 1, full.ndofs)).cuda()
+    xref, iref = full.solve(b, tol=1e-11, maxiter=4000, preconditioner=preconditioner, check_every=5)
+    assert iref["converged"]
+    bs = [b[:cut * col].clone(), b[cut * col:].clone()]
+    # halos[r] is what rank r RECEIVES: rank 0 its x_hi (rank 1's first column), rank 1 its x_lo
+    halos = [torch.zeros(col, dtype=torch.float64, device="cuda") for _ in range(2)]
+    bar = threading.Barrier(2, timeout=120)
+    shared, results, failures = {}, [None, None], []
+
+    def run(r):
+        other = 1 - r
+
+        def exchange(v_ptr, st):
+            ext = torch.cuda.ExternalStream(st)
+            ext.synchronize()  # v is final
+            shared["v", r] = v_ptr
+            bar.wait()
+            ov = _wrap_device(shared["v", other], ops[other].ndofs)
+            with torch.cuda.stream(ext):
+                halos[r].copy_(ov[:col] if r == 0 else ov[-col:])
+            ext.synchronize()
+            bar.wait()  # the neighbour has copied: v may change
+
+        def allreduce(d_ptr, count, st):
+            ext = torch.cuda.ExternalStream(st)
+            t = _wrap_device(d_ptr, count)
+            with torch.cuda.stream(ext):
+                shared["s", r] = t.cpu()
+            bar.wait()
+            tot = shared["s", 0] + shared["s", 1]  # the same order on both sides
+            with torch.cuda.stream(ext):
+                t.copy_(tot.cuda())
+            ext.synchronize()
+            bar.wait()
+
+        try:
+            torch.cuda.set_device(0)
+            results[r] = ops[r].solve_slab(bs[r], halos[1] if r == 1 else None, halos[0] if r == 0 else None,
+                                           exchange, allreduce, tol=1e-11, maxiter=4000,
+                                           preconditioner=preconditioner, check_every=5)
+        except Exception as e:  # noqa: BLE001
+            failures.append(e)
+            bar.abort()
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(300)
+    assert not failures, failures
+    (x0, i0), (x1, i1) = results
+    assert i0["converged"] and i1["converged"] and i0["iterations"] == i1["iterations"]
+    assert abs(i0["iterations"] - iref["iterations"]) <= 5
+    assert abs(i0["residual_norm"] - i1["residual_norm"]) == 0.0
+    x = torch.cat([x0, x1])
+    assert float((x - xref).norm() / xref.norm()) <= 1e-8
+    r = b - full.apply(x, algo=1)
+    assert float(r.norm() / b.norm()) <= 1e-9
