@@ -346,6 +346,30 @@ function Base.:\(A::IPOperator, b::CuVector{Float64}; tol = 1e-12, maxiter = 100
     x
 end
 
+"""
+The same solve across column slabs, one process per GPU (stefan_ipdg_cg_solve_slab).  `exchange(v, stream)` must fill
+`halo_lo` / `halo_hi` with the neighbours' edge columns of the slab vector at device pointer `v` (e.g. CUDA-aware
+`MPI.Sendrecv!`), `allreduce(dev, count, stream)` must sum `count` device doubles over the ranks in place
+(`MPI.Allreduce!`); both are ordered on the raw stream they receive and return nothing.
+"""
+function solve_slab(A::IPOperator, b::CuVector{Float64}, halo_lo, halo_hi, exchange, allreduce;
+                    tol = 1e-12, maxiter = 10000)
+    x = CUDA.zeros(Float64, length(b))
+    res = Ref(CgResult(0, 0.0, 0.0, 0))
+    ex(ctx, v, st) = (exchange(v, st); Cint(0))
+    ar(ctx, d, n, st) = (allreduce(d, n, st); Cint(0))
+    cex = @cfunction($ex, Cint, (Ptr{Cvoid}, CuPtr{Float64}, Ptr{Cvoid}))
+    car = @cfunction($ar, Cint, (Ptr{Cvoid}, CuPtr{Float64}, Int32, Ptr{Cvoid}))
+    lo = halo_lo === nothing ? CU_NULL : pointer(halo_lo)
+    hi = halo_hi === nothing ? CU_NULL : pointer(halo_hi)
+    GC.@preserve cex car check(ccall((:stefan_ipdg_cg_solve_slab, lib), Cint,
+                (Ptr{Cvoid}, CuPtr{Float64}, CuPtr{Float64}, Ref{CgParams}, Ref{CgResult}, CuPtr{Float64}, CuPtr{Float64},
+                 Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                A.handle, b, x, Ref(CgParams(maxiter, tol, 1, 10)), res, lo, hi, cex, car, C_NULL, CUDA.stream().handle))
+    res[].converged == 1 || @warn "CG did not converge" res[]
+    x
+end
+
 "(||u_h - u_ex||, ||u_ex||) in L2 with the cell quadrature (`mesh_L2_error`, useful_routines.jl:95-133);
 `uex_qp` = exact solution at the cell quadrature points, [ncells][numqp^2]."
 function l2_error(A::IPOperator, u::CuVector{Float64}, uex_qp::CuVector{Float64})
