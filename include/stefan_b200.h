@@ -390,6 +390,38 @@ int stefan_blocks_cg_solve(stefan_blocks* h, const double* b, double* x, const s
 int stefan_blocks_interface_l2_error(stefan_blocks* h, const stefan_blocks_data* data, const int8_t* slot_select,
                                      const double* u, const double* uex_fq, double* out2_dev, void* stream);
 
+/* ------------------------------------------ local DG on element blocks (cut cells; SURVEY 8(a) LDG interface drivers)
+ * The local-DG twin of stefan_blocks_*: `assemble_LDG_linear_system!` (LDG_assembly.jl:1-91) for arbitrary per-cell /
+ * per-face quadratures in the same `stefan_blocks_data` layout -- divergence_operator (LDG_div_operator.jl:1-11),
+ * mass_matrix (LDG_mass_operator.jl:1-25), gradient_operator (LDG_gradient_operator.jl:1-11) from the volume points;
+ * assemble_face_scalar_flux_operator! (LDG_scalar_flux_operator.jl:25-107) and assemble_face_vector_flux_operator!
+ * (LDG_vector_flux_operator.jl:47-154) on every neighbour slot, which is what the interelement drivers (:111-237,
+ * :158-300) AND the cut-cell interface drivers (LDG_scalar_flux_operator.jl:241-309,
+ * LDG_vector_flux_operator.jl:318-386) call; assemble_boundary_face_vector_flux_operator! (:391-439) on boundary
+ * slots.  3 dofs per node, interleaved (T, q_x, q_y): ndofs = ncells * 3 NF, blocks are 3 NF x 3 NF.
+ * `slot_pen` is the slot's penalty (interior / interface penalty; on a boundary slot negboundarypenalty or
+ * posboundarypenalty, selected by the producer from sign(V0 . n) as the reference does); `slot_lambda` is ignored.
+ * (V0x, V0y): the unit vector V0 (edge switch of the scalar flux; n . V0 in the vector flux). */
+typedef struct stefan_ldgblocks stefan_ldgblocks;
+int stefan_ldgblocks_create(const stefan_blocks_dims* dims, stefan_ldgblocks** out);
+int stefan_ldgblocks_destroy(stefan_ldgblocks* h);
+int64_t stefan_ldgblocks_ndofs(const stefan_ldgblocks* h);
+int stefan_ldgblocks_assemble(stefan_ldgblocks* h, const stefan_blocks_data* data, double V0x, double V0y, void* stream);
+int stefan_ldgblocks_apply(stefan_ldgblocks* h, const double* x, double* y, void* stream);
+/* assemble_LDG_rhs! (LDG_assembly.jl:93-131) for the same data: T rows sum V f detjac w (LDG_source_term.jl:1-60); on
+ * boundary slots q rows sum n V g w (:64-198) and T rows + slot_pen sum V g w (:203-321).  f_qp [ncells][nqv] or NULL,
+ * g_qp [ncells][nslots][nqf] or NULL; rhs [ncells * 3 NF]. */
+int stefan_ldgblocks_rhs(stefan_ldgblocks* h, const stefan_blocks_data* data, const double* f_qp, const double* g_qp,
+                         double* rhs, void* stream);
+int64_t stefan_ldgblocks_coo_size(const stefan_ldgblocks* h);
+int stefan_ldgblocks_assemble_coo(stefan_ldgblocks* h, int64_t* rows, int64_t* cols, double* vals, int64_t capacity,
+                                  int32_t index_base, int64_t* nnz_out, void* stream);
+/* `matrix \ rhs` (cylindrical_bc_tests/LDG_test_cylindrical_bc_convergence.jl:157-159) on the device: q is eliminated
+ * through every solution cell's own mass block (inverted at assemble time) and BiCGStab runs on the Schur complement
+ * in T, as stefan_ldg_solve does on uniform meshes.  result as for stefan_ldg_solve. */
+int stefan_ldgblocks_solve(stefan_ldgblocks* h, const double* rhs, double* sol, const stefan_cg_params* params,
+                           stefan_cg_result* result, void* stream);
+
 /* ------------------------------------------------- point evaluation and front velocity
  * InteriorPenalty.interpolate_at_reference_points (IP_postprocess.jl:30-52) and gradient_at_reference_points
  * (:1-28) as device gathers: nodalvalues holds NF = (order + 1)^2 dofs per (solution) cell, refpoints [numpts][2]

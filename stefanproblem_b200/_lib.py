@@ -145,6 +145,18 @@ _SIGNATURES = {
     "stefan_blocks_l2_error": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(BlocksData)] + [ctypes.c_void_p] * 4),
     "stefan_blocks_cg_solve": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                               ctypes.POINTER(CgParams), ctypes.POINTER(CgResult), ctypes.c_void_p]),
+    "stefan_ldgblocks_create": (ctypes.c_int, [ctypes.POINTER(BlocksDims), ctypes.POINTER(ctypes.c_void_p)]),
+    "stefan_ldgblocks_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "stefan_ldgblocks_ndofs": (ctypes.c_int64, [ctypes.c_void_p]),
+    "stefan_ldgblocks_assemble": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(BlocksData), ctypes.c_double,
+                                                 ctypes.c_double, ctypes.c_void_p]),
+    "stefan_ldgblocks_apply": (ctypes.c_int, [ctypes.c_void_p] * 4),
+    "stefan_ldgblocks_rhs": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(BlocksData)] + [ctypes.c_void_p] * 4),
+    "stefan_ldgblocks_coo_size": (ctypes.c_int64, [ctypes.c_void_p]),
+    "stefan_ldgblocks_assemble_coo": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                     ctypes.c_int64, ctypes.c_int32, c_int64_p, ctypes.c_void_p]),
+    "stefan_ldgblocks_solve": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                              ctypes.POINTER(CgParams), ctypes.POINTER(CgResult), ctypes.c_void_p]),
     "stefan_blocks_interface_l2_error": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(BlocksData)] + [ctypes.c_void_p] * 5),
     "stefan_interpolate_at_reference_points": (ctypes.c_int, [ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
                                                               ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,

@@ -135,6 +135,110 @@ class BlockSystem:
         return rows, cols, vals
 
 
+class LDGBlockSystem:
+    """Local-DG element blocks on one GPU (`stefan_ldgblocks_*`): the cut-cell form of
+    `assemble_LDG_linear_system!` / `assemble_LDG_rhs!`.  3 dofs per node, interleaved (T, q_x, q_y).
+    `data["slot_pen"]` carries the penalty of every slot (see `ldg_slot_penalties`)."""
+
+    def __init__(self, ncells, order, nqv, nslots, nqf):
+        import torch
+        if not torch.cuda.is_available():
+            raise _lib.StefanError(-1, "no CUDA device: stefanproblem_b200 has no CPU fallback")
+        self.dims = _lib.BlocksDims(int(ncells), int(order), int(nqv), int(nslots), int(nqf))
+        h = ctypes.c_void_p()
+        _lib.check(_lib.lib().stefan_ldgblocks_create(ctypes.byref(self.dims), ctypes.byref(h)))
+        self._h = h
+        self.ndofs = int(_lib.lib().stefan_ldgblocks_ndofs(h))
+        self.shape = (self.ndofs, self.ndofs)
+        self._norms = None
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h and _lib is not None:
+            _lib.lib().stefan_ldgblocks_destroy(h)
+            self._h = None
+
+    _dev = BlockSystem._dev
+
+    def assemble(self, data, V0, stream=None):
+        import torch
+        dev = {}
+        for name in _FIELDS:
+            a = data[name]
+            if not isinstance(a, torch.Tensor):
+                a = torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32 if name == "slot_nbr" else np.float64))
+            dev[name] = a.cuda().contiguous()
+        self._data = dev
+        self._host_data = data
+        self._bd = _lib.BlocksData(*[dev[n].data_ptr() for n in _FIELDS])
+        _lib.check(_lib.lib().stefan_ldgblocks_assemble(self._h, ctypes.byref(self._bd), float(V0[0]), float(V0[1]),
+                                                        _stream_ptr(stream)))
+        return self
+
+    def apply(self, x, out=None, stream=None):
+        import torch
+        assert x.is_cuda and x.dtype == torch.float64 and x.is_contiguous() and x.numel() == self.ndofs
+        if out is None:
+            out = torch.empty_like(x)
+        _lib.check(_lib.lib().stefan_ldgblocks_apply(self._h, _ptr(x), _ptr(out), _stream_ptr(stream)))
+        return out
+
+    def __matmul__(self, x):
+        return self.apply(x)
+
+    def rhs(self, f_qp=None, g_qp=None, stream=None):
+        import torch
+        f, g = self._dev(f_qp), self._dev(g_qp)
+        out = torch.empty(self.ndofs, dtype=torch.float64, device="cuda")
+        _lib.check(_lib.lib().stefan_ldgblocks_rhs(self._h, ctypes.byref(self._bd), _ptr(f), _ptr(g), _ptr(out),
+                                                   _stream_ptr(stream)))
+        return out
+
+    def solve(self, b, tol=1e-12, maxiter=20000, check_every=10):
+        """`matrix \\ rhs` on the device: Schur complement on T + BiCGStab (stefan_ldgblocks_solve)."""
+        import torch
+        x = torch.zeros_like(b)
+        prm = _lib.CgParams(int(maxiter), float(tol), 0, int(check_every))
+        res = _lib.CgResult()
+        _lib.check(_lib.lib().stefan_ldgblocks_solve(self._h, _ptr(b), _ptr(x), ctypes.byref(prm), ctypes.byref(res),
+                                                     _stream_ptr()))
+        return x, {"iterations": res.iterations, "residual_norm": res.residual_norm, "rhs_norm": res.rhs_norm,
+                   "converged": bool(res.converged)}
+
+    def to_coo(self, index_base=0):
+        import torch
+        n = int(_lib.lib().stefan_ldgblocks_coo_size(self._h))
+        rows = torch.empty(n, dtype=torch.int64, device="cuda")
+        cols = torch.empty(n, dtype=torch.int64, device="cuda")
+        vals = torch.empty(n, dtype=torch.float64, device="cuda")
+        nnz = ctypes.c_int64()
+        _lib.check(_lib.lib().stefan_ldgblocks_assemble_coo(self._h, _ptr(rows), _ptr(cols), _ptr(vals), n, index_base,
+                                                            ctypes.byref(nnz), _stream_ptr()))
+        return rows, cols, vals
+
+    def l2_error(self, sol, uex_qp, component):
+        """mesh_L2_error of one component of the solution (0: T, 1 / 2: the flux variable) against samples at the
+        volume points, through the scalar block norm kernel (stefan_blocks_l2_error) on the same quadrature data."""
+        if self._norms is None:
+            d = self.dims
+            self._norms = BlockSystem(d.ncells, d.order, d.nqv, d.nslots, d.nqf).assemble(self._data)
+        return self._norms.l2_error(sol[component::3].contiguous(), uex_qp)
+
+
+def ldg_slot_penalties(data, V0, interiorpenalty, interfacepenalty, negboundarypenalty, posboundarypenalty,
+                       slot_is_interface=None):
+    """`slot_pen` of local-DG block data: interior / interface penalty on neighbour slots; on boundary slots the
+    penalty the reference selects from sign(V0 . n) (LDG_vector_flux_operator.jl:391-439, LDG_source_term.jl:203-321)."""
+    nbr = np.asarray(data["slot_nbr"])
+    pen = np.zeros(nbr.shape)
+    pen[nbr >= 0] = interiorpenalty
+    if slot_is_interface is not None:
+        pen[(nbr >= 0) & np.asarray(slot_is_interface, bool)] = interfacepenalty
+    v0n = np.asarray(data["face_normals"])[:, :, 0, :] @ np.asarray(V0, float)
+    pen[nbr == -1] = np.where(v0n < 0, negboundarypenalty, posboundarypenalty)[nbr == -1]
+    return pen
+
+
 def uniform_mesh_block_data(nx, ny, hx, hy, numqp, phase, k1, k2, penalty, lam=0.0, aligned_interface=True):
     """`stefan_blocks_data` arrays (NumPy) of an uncut uniform nx x ny mesh of two phases.
 

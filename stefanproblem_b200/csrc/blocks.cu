@@ -232,22 +232,6 @@ blocks_apply_kernel(int ncells, int nslots, const double* __restrict__ blocks, c
   }
 }
 
-__global__ void blocks_coo_kernel(int ncells, int nslots, int nf, const double* __restrict__ blocks,
-                                  const int32_t* __restrict__ slot_nbr, int64_t index_base, int64_t* __restrict__ rows,
-                                  int64_t* __restrict__ cols, double* __restrict__ vals) {
-  const int nb = 1 + nslots;
-  const int64_t n = (int64_t)ncells * nb * nf * nf;
-  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
-    const int b = (int)(e % nf), a = (int)((e / nf) % nf);
-    const int s = (int)((e / ((int64_t)nf * nf)) % nb);
-    const int cell = (int)(e / ((int64_t)nf * nf * nb));
-    const int nbr = s == 0 ? cell : slot_nbr[(size_t)cell * nslots + (s - 1)];
-    rows[e] = (int64_t)cell * nf + a + index_base;
-    cols[e] = (nbr >= 0 ? (int64_t)nbr * nf + b : (int64_t)cell * nf + b) + index_base;  // empty slots: explicit zeros
-    vals[e] = nbr >= 0 ? blocks[e] : 0.0;
-  }
-}
-
 }  // namespace stefan
 
 using namespace stefan;

@@ -343,7 +343,7 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, siz
 template <int P, int MODE>
 static int launch_march(IpdgHandle* h, const IpTab<P>& tab, const ApplyArgs& args0, cudaStream_t st) {
   using C = MarchCfg<P>;
-  const SegCache& sc = h->plan.segments(args0.cbeg, args0.cend, sm_count() * C::MINB);
+  const SegCache& sc = h->plan.segments(args0.cbeg, args0.cend, sm_count() * march_minb<P, MODE>());
   const SegTab& segs = sc.tab;
   const int grid = sc.n;
   if (grid <= 0) return fail(ST_UNSUPPORTED, "stefan_ipdg_apply: more than %d strip groups (ny too large)", kMaxMarchCtas);

@@ -95,6 +95,21 @@ struct MarchCfg<3> {
   static constexpr bool TENSOR = true;
 };
 
+// CTAs per SM of the kernel <P, MODE>.  The fused step (MODE 1) of order 2 needs more than the 128 registers
+// that two 8-warp CTAs leave per thread (138 B of spills in every column): one CTA of 192 registers per SM.
+// Measured (100 M dofs, us per step; profiles/r2_p2_step_variants.log): b per cell / staged, 2 CTAs: 597 / 660;
+// 1 CTA: 588 / 569.
+#ifndef MARCH_MINB2_STEP
+#define MARCH_MINB2_STEP 1
+#endif
+#ifndef MARCH_BSTAGE2
+#define MARCH_BSTAGE2 1
+#endif
+template <int P, int MODE>
+constexpr int march_minb() {
+  return (P == 2 && MODE == 1) ? MARCH_MINB2_STEP : MarchCfg<P>::MINB;
+}
+
 // SegTab (ipdg_handle.h): one entry per CTA, {strip group, first column, one past the last
 // column, -}, built by the host so that every CTA gets the same COST rather than the same
 // column count (columns where a strip mixes phases run both phase bodies).
@@ -102,7 +117,7 @@ template <int P, int MODE = 0>
 struct MarchSmem {
   using C = MarchCfg<P>;
   // P = 2 fused step: one strip of b (30 cells x 72 B), loaded coalesced and read back per cell
-  static constexpr int BBUF = (P == 2 && MODE == 1) ? 30 * 72 + 16 : 0;
+  static constexpr int BBUF = (P == 2 && MODE == 1 && MARCH_BSTAGE2) ? 30 * 72 + 16 : 0;
   static constexpr int WARP = C::NST * C::STAGE + 2 * C::OUTB + BBUF;
   // rings (1024-byte aligned for the swizzled tiles) + mbarriers + alignment slack
   static constexpr int TOTAL = C::WARPS * WARP + C::WARPS * C::NST * 8 + 1024;
@@ -197,7 +212,7 @@ struct MarchMath {
 // MODE 0: y = A x.  MODE 1: the fused explicit step y = x + dt Minv (b - A x) (SURVEY 2.4 K9:
 // 24 B per dof -- x and b read once, y written once -- instead of the 48 B of apply + update).
 template <int P, int MODE>
-__global__ void __launch_bounds__(MarchCfg<P>::WARPS * 32, MarchCfg<P>::MINB)
+__global__ void __launch_bounds__(MarchCfg<P>::WARPS * 32, march_minb<P, MODE>())
 ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const int4* __restrict__ runs,
                  const int* __restrict__ run_ofs, const __grid_constant__ CUtensorMap tmx,
                  const __grid_constant__ SegTab segs) {
@@ -430,7 +445,7 @@ ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const 
     // instructions (measured: the fused step at 62 % of the roofline against 79 % for the apply).  The warp
     // reads the strip's 270 doubles of b COALESCED instead (lane + 32 r), one column ahead, parks them in shared
     // memory at the top of the column and every lane picks up its own cell for the epilogue.
-    constexpr bool BSTAGE = (P == 2 && MODE == 1);
+    constexpr bool BSTAGE = (P == 2 && MODE == 1 && MARCH_BSTAGE2);
     constexpr int BR = BSTAGE ? (kStripCells * NF + 31) / 32 : 1;  // rounds of 32 doubles
     [[maybe_unused]] double Bnext[BR];
     [[maybe_unused]] const double* bchunk = a.b + (size_t)c0 * ycol + (size_t)j0 * NF;
@@ -465,8 +480,13 @@ ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const 
         if (c + 1 < c1) load_b_chunk();  // in flight behind the whole column
       } else if constexpr (MODE == 1) {
         if (bp_valid) {
+          if constexpr (P == 2) {
 #pragma unroll
-          for (int q = 0; q < NF; q += 4) ld_global_nc_v4(bp + q, Bc + q);
+            for (int q = 0; q < NF; ++q) Bc[q] = __ldg(bp + q);
+          } else {
+#pragma unroll
+            for (int q = 0; q < NF; q += 4) ld_global_nc_v4(bp + q, Bc + q);
+          }
         } else {
 #pragma unroll
           for (int q = 0; q < NF; ++q) Bc[q] = 0.0;

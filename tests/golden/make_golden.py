@@ -19,6 +19,7 @@ def main():
     robin = rows("StefanRobinIC/DG1D/robin-interface-tests/robin-convergence.csv")
     cyl = rows("StefanDG/InteriorPenalty/cylindrical_bc_tests/IP_convergence.csv")
     cylr = rows("StefanDG/InteriorPenalty/robin_cylindrical_bc_tests/IP_convergence.csv")
+    ldgcyl = rows("StefanDG/LocalDG/cylindrical_bc_tests/LDG_convergence.csv")
     gold = {
         "ip_uncut": [[int(r[0]), r[1], r[2]] for r in ip_rows],
         "ldg_uncut": [[int(r[0])] + r[1:] for r in ldg_rows],
@@ -27,7 +28,10 @@ def main():
         # cut-cell studies: NElmts, linear, quadratic (relative L2 errors); parity at discretisation level only
         "ip_cylinder": [[int(r[0]), r[1], r[2]] for r in cyl],
         "ip_cylinder_robin": [[int(r[0]), r[1], r[3]] for r in cylr],
+        # NElmts, then errT, errG1, errG2 (relative L2) for the linear and the quadratic basis
+        "ldg_cylinder": [[int(r[0])] + r[1:] for r in ldgcyl],
         "sources": {
+            "ldg_cylinder": "StefanDG/LocalDG/cylindrical_bc_tests/LDG_convergence.csv",
             "ip_cylinder": "StefanDG/InteriorPenalty/cylindrical_bc_tests/IP_convergence.csv",
             "ip_cylinder_robin": "StefanDG/InteriorPenalty/robin_cylindrical_bc_tests/IP_convergence.csv",
             "ip_uncut": "StefanDG/InteriorPenalty/uncut_mesh_tests/IP_convergence.csv",

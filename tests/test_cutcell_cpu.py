@@ -148,3 +148,96 @@ def test_distance_functions_restated():
         k = m.data["vol_wts"][sol] != 0
         dd = geo.circle_distance_function(m.vol_xy[sol][k].T, [0.0, 0.0], 0.5)
         assert np.all(dd * m.sol_phase[sol] > 0)
+
+
+# ----------------------------------------------------------------- local DG on element blocks (oracle/ldg_blocks.py)
+@pytest.mark.parametrize("order", [1, 2, 3])
+@pytest.mark.parametrize("interfacepenalty", [None, 0.7])
+def test_ldg_block_oracle_equals_the_uniform_ldg_oracle(order, interfacepenalty):
+    """Pins oracle/ldg_blocks.py: on uniform-mesh block data its matrix and right-hand side are those of the
+    golden-pinned uniform LDG oracle (oracle/fast.ldg_matrix / ldg_rhs), with and without the mesh-aligned interface
+    coupling."""
+    from oracle import fast, ldg_blocks as olb
+    from oracle.mesh import UniformMesh2D
+    from stefanproblem_b200.blocks import ldg_slot_penalties, uniform_mesh_block_data
+    nx, ny, nq = 4, 3, order + 1
+    nf = (order + 1) ** 2
+    mesh = UniformMesh2D([0, 0], [1.0, 0.9], [nx, ny], nf)
+    ph = fast.circle_phase(mesh, radius=0.33)
+    assert set(np.unique(ph)) == {-1, 1}
+    mesh.cellsign = ph
+    V0 = (np.cos(0.6), np.sin(0.6))
+    A = fast.ldg_matrix(mesh, order, nq, 1.0, 2.0, 0.5, 0.2, 1.3, V0, interfacepenalty=interfacepenalty).toarray()
+    data = uniform_mesh_block_data(nx, ny, 1.0 / nx, 0.9 / ny, nq, ph, 1.0, 2.0, 0.0, 0.0,
+                                   aligned_interface=interfacepenalty is not None)
+    nbr = data["slot_nbr"]
+    phc = ph.reshape(-1)
+    isif = (nbr >= 0) & (phc[np.maximum(nbr, 0)] != phc[:, None])
+    data["slot_pen"] = ldg_slot_penalties(data, V0, 0.5, interfacepenalty or 0.0, 0.2, 1.3, isif)
+    assert np.array_equal(data["slot_pen"], olb.boundary_penalties(data, V0, 0.2, 1.3, 0.5, interfacepenalty, isif))
+    B = olb.dense_matrix(olb.assemble_blocks(order, data, V0), nbr)
+    assert np.abs(A - B).max() <= 1e-14 * np.abs(A).max()
+    f = fast.sample_cell_quadrature(mesh, nq, lambda x, y: 1.0 + x * y)
+    g = fast.sample_face_quadrature(mesh, nq, lambda x, y: np.sin(x) - y)
+    b_ref = fast.ldg_rhs(mesh, order, nq, 0.2, 1.3, V0, f, g)
+    b = olb.assemble_rhs(order, data, f, np.transpose(g, (1, 0, 2)))
+    assert np.abs(b - b_ref).max() <= 1e-14 * np.abs(b_ref).max()
+
+
+def _ldg_cylinder(n, order, merge=0.25, exact=None, k2=2.0, q=(1.0, 2.0), numqp=None):
+    from oracle import ldg_blocks as olb
+    from stefanproblem_b200.blocks import ldg_slot_penalties
+    V0 = (np.cos(np.pi / 4), np.sin(np.pi / 4))
+    sol = CylindricalSolver(q[0], 1.0, q[1], k2, 0.5, 1.5, 1.0)
+    m = CircleCutMesh([0, 0], [1, 1], [n, n], [0, 0], 0.5, numqp or order + 3, 1.0, k2, 0.0, 0.0, merge_fraction=merge)
+    data = dict(m.data)
+    data["slot_pen"] = ldg_slot_penalties(data, V0, 0.0, 0.0, 0.0, 1.0, m.slot_is_interface)
+    A = sp.csc_matrix(olb.dense_matrix(olb.assemble_blocks(order, data, V0), data["slot_nbr"]))
+    if exact is None:
+        T = sol.at
+
+        def grad(x, y):
+            r = np.maximum(np.hypot(x, y), 1e-300)
+            tr = sol.radial_derivative(r)
+            return tr * x / r, tr * y / r
+    else:
+        T, grad = exact
+    f = m.sample_source(lambda x, y: q[0] + 0 * x, lambda x, y: q[1] + 0 * x)
+    u = spla.spsolve(A, olb.assemble_rhs(order, data, f, m.sample_boundary(T)))
+    out = []
+    for comp, ex in ((0, T), (1, lambda x, y: grad(x, y)[0]), (2, lambda x, y: grad(x, y)[1])):
+        e, den = ob.l2_error(order, data, u[comp::3], m.sample_exact(ex))
+        out.append((e, den))
+    return out
+
+
+def test_ldg_cylinder_study_small_meshes_against_the_reference_csv():
+    """n = 3, 5, 9 of cylindrical_bc_tests/LDG_test_cylindrical_bc_convergence.jl with the oracle's local-DG block
+    assembly on the generator's data, against the stored LDG_convergence.csv (relative L2 errors of T and of the two
+    flux components).  Observed ratio this / CSV: p = 1 0.99 ... 1.01 in all three columns; p = 2 temperature 0.97 / 0.99
+    at n = 5 / 9 (0.41 at n = 3); p = 2 flux components 0.14 ... 0.84 -- the exact circle beats the CSV's Q2-interpolated
+    interface there."""
+    for row in GOLD["ldg_cylinder"][:3]:
+        n = row[0]
+        for order in (1, 2):
+            got = [e / den for e, den in _ldg_cylinder(n, order)]
+            want = row[1 + 3 * (order - 1):4 + 3 * (order - 1)]
+            if order == 1:
+                for gv, wv in zip(got, want):
+                    assert 0.95 * wv < gv < 1.05 * wv, (n, order, got, want)
+            else:
+                assert (0.9 if n >= 5 else 0.3) * want[0] < got[0] < 1.1 * want[0], (n, got, want)
+                assert got[1] < 1.05 * want[1] and got[2] < 1.05 * want[2], (n, got, want)
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_ldg_cut_cell_patch_test(order):
+    """The reference's linear-solution studies (plane_interface_tests/linear_solution_LDG_convergence.csv: errors
+    ~1e-16): with k1 = k2 and no source a linear temperature is reproduced to rounding on the CUT mesh once the
+    generator's Gauss rules on the circular pieces are accurate enough to be consistent with each other (volume rule
+    against face + arc rules; 12 points: 1e-13 ... 1e-15, the study's p + 3 points: 1e-6 ... 1e-8, spectral in between).
+    A wrong sign, normal or neighbour frame in any cut-cell term gives O(1)."""
+    T = lambda x, y: 1.0 + 2.0 * x - 0.5 * y  # noqa: E731
+    grad = lambda x, y: (2.0 + 0 * x, -0.5 + 0 * x)  # noqa: E731
+    for e, den in _ldg_cylinder(5, order, exact=(T, grad), k2=1.0, q=(0.0, 0.0), numqp=12):
+        assert e <= 1e-10 * den, (e, den)
