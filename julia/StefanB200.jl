@@ -248,6 +248,48 @@ function l2_error(b::BlockSystem, data::BlocksData, u::CuVector{Float64}, uex_qp
     Tuple(Array(out))
 end
 
+# ------------------------------------------------- local DG on element blocks (cut meshes; stefan_ldgblocks_*)
+"assemble_LDG_linear_system! (LDG_assembly.jl:1-91) for per-cell / per-face quadrature data: 3 dofs per node
+(T, q_x, q_y); `data.slot_pen` holds every slot's penalty (interior / interface / boundary by sign(V0 . n))."
+mutable struct LDGBlockSystem
+    handle::Ptr{Cvoid}
+    ndofs::Int
+    function LDGBlockSystem(dims::BlocksDims)
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:stefan_ldgblocks_create, lib), Cint, (Ref{BlocksDims}, Ref{Ptr{Cvoid}}), Ref(dims), out))
+        b = new(out[], ccall((:stefan_ldgblocks_ndofs, lib), Int64, (Ptr{Cvoid},), out[]))
+        finalizer(o -> ccall((:stefan_ldgblocks_destroy, lib), Cint, (Ptr{Cvoid},), o.handle), b)
+        b
+    end
+end
+assemble!(b::LDGBlockSystem, data::BlocksData, V0) =
+    check(ccall((:stefan_ldgblocks_assemble, lib), Cint, (Ptr{Cvoid}, Ref{BlocksData}, Float64, Float64, Ptr{Cvoid}),
+                b.handle, Ref(data), V0[1], V0[2], CUDA.stream().handle))
+function Base.:*(b::LDGBlockSystem, x::CuVector{Float64})
+    y = similar(x)
+    check(ccall((:stefan_ldgblocks_apply, lib), Cint, (Ptr{Cvoid}, CuPtr{Float64}, CuPtr{Float64}, Ptr{Cvoid}),
+                b.handle, x, y, CUDA.stream().handle))
+    y
+end
+"assemble_LDG_rhs! (LDG_assembly.jl:93-131) + the two-phase source for block data (stefan_ldgblocks_rhs)."
+function rhs_vector(b::LDGBlockSystem, data::BlocksData, f_qp::CuVector{Float64}, g_qp::CuVector{Float64})
+    out = CUDA.zeros(Float64, b.ndofs)
+    check(ccall((:stefan_ldgblocks_rhs, lib), Cint,
+                (Ptr{Cvoid}, Ref{BlocksData}, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, Ptr{Cvoid}),
+                b.handle, Ref(data), f_qp, g_qp, out, CUDA.stream().handle))
+    out
+end
+"`reshape(matrix \\ rhs, 3, :)` of LDG_test_cylindrical_bc_convergence.jl:159 on the device (Schur complement + BiCGStab)."
+function Base.:\(b::LDGBlockSystem, rhs::CuVector{Float64}; tol = 1e-12, maxiter = 200000)
+    x = CUDA.zeros(Float64, length(rhs))
+    res = Ref(CgResult(0, 0.0, 0.0, 0))
+    check(ccall((:stefan_ldgblocks_solve, lib), Cint,
+                (Ptr{Cvoid}, CuPtr{Float64}, CuPtr{Float64}, Ref{CgParams}, Ref{CgResult}, Ptr{Cvoid}),
+                b.handle, rhs, x, Ref(CgParams(maxiter, tol, 0, 10)), res, CUDA.stream().handle))
+    res[].converged == 1 || @warn "BiCGStab did not converge" res[]
+    reshape(x, 3, :)
+end
+
 # ------------------------------------------------- point evaluation / front velocity (IP_postprocess.jl)
 "InteriorPenalty.interpolate_at_reference_points (IP_postprocess.jl:30-52): refpoints 2 x numpts, refcellids 1-based
 solution-cell ids (the caller picks the cell of the wanted level-set sign)."

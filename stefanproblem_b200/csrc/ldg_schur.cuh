@@ -120,7 +120,8 @@ int ldg_schur_bicgstab(Apply&& apply, MassSolve&& mass_solve, int64_t nn, const 
     LS_CUDA(cudaMemcpyAsync(hs, scal, sizeof(hs), cudaMemcpyDeviceToHost, st));
     LS_CUDA(cudaStreamSynchronize(st));
     rnorm = std::sqrt(hs[kry::S_RR]);
-    if (!(rnorm == rnorm) || hs[kry::S_RHO] == 0.0) broke = true;  // NaN or breakdown: report not converged
+    // NaN, breakdown or divergence (BiCGStab on a Schur complement that is too ill-conditioned): report not converged
+    if (!(rnorm == rnorm) || hs[kry::S_RHO] == 0.0 || rnorm > 1e8 * gnorm) broke = true;
   }
   // the TRUE residual of the Schur system, not the recurrence's
   if (gnorm > 0.0) {
