@@ -194,7 +194,7 @@ def main():
         xloc, iloc = cg_solve_distributed(dop, bloc, tol=1e-11, maxiter=5000, check_every=5)
         assert ifull["converged"] and iloc["converged"], (ifull, iloc)
         assert abs(ifull["iterations"] - iloc["iterations"]) <= 5, (ifull, iloc)
-        assert float((xloc - xfull[sl]).norm()) <= 1e-8 * float(xfull[sl].norm()), "slab CG differs from the one-GPU solve"
+        assert float((xloc - xfull[sl]).norm()) <= 1e-6 * float(xfull[sl].norm()), "slab CG differs from the one-GPU solve"
         if rank == 0:
             print(f"slab CG order {order}: {iloc['iterations']} iterations (one GPU: {ifull['iterations']}), "
                   f"residual {iloc['residual_norm']:.2e}", flush=True)
