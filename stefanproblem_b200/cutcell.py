@@ -177,6 +177,100 @@ def arc_rule(x0, x1, y0, y1, cx, cy, R, nq):
     return np.concatenate(P), np.concatenate(W), np.concatenate(N)
 
 
+# ----------------------------------------------------------------------------- straight interface
+def _clip_halfplane(poly, n, c, keep_positive):
+    """Sutherland-Hodgman: the part of the convex polygon `poly` [m, 2] with n . x - c >= 0 (or <= 0)."""
+    sgn = 1.0 if keep_positive else -1.0
+    d = sgn * (poly @ n - c)
+    out = []
+    m = len(poly)
+    for i in range(m):
+        p, q, dp, dq = poly[i], poly[(i + 1) % m], d[i], d[(i + 1) % m]
+        if dp >= 0:
+            out.append(p)
+        if (dp > 0 and dq < 0) or (dp < 0 and dq > 0):
+            t = dp / (dp - dq)
+            out.append(p + t * (q - p))
+    return np.array(out) if out else np.zeros((0, 2))
+
+
+def polygon_rule(poly, nq):
+    """Quadrature of a convex polygon: fan of triangles from vertex 0, collapsed tensor Gauss rule on each (exact for
+    polynomials of total degree 2 nq - 2)."""
+    if len(poly) < 3:
+        return np.zeros((0, 2)), np.zeros(0)
+    g, w = _gauss(nq)
+    u, wu = 0.5 * (1 + g), 0.5 * w
+    U, V = np.meshgrid(u, u, indexing="ij")
+    WU = np.outer(wu, wu)
+    P, W = [], []
+    A = poly[0]
+    for B, C in zip(poly[1:-1], poly[2:]):
+        area2 = abs((B[0] - A[0]) * (C[1] - A[1]) - (B[1] - A[1]) * (C[0] - A[0]))
+        if area2 <= 0.0:
+            continue
+        # x = A + u (B - A) + u v (C - B), |dx / d(u, v)| = u * 2 area
+        X = A[None, None, :] + U[..., None] * (B - A)[None, None, :] + (U * V)[..., None] * (C - B)[None, None, :]
+        P.append(X.reshape(-1, 2))
+        W.append((WU * U * area2).ravel())
+    if not P:
+        return np.zeros((0, 2)), np.zeros(0)
+    return np.concatenate(P), np.concatenate(W)
+
+
+def plane_rect_rules(x0, x1, y0, y1, n, c, nq):
+    """Quadrature of the parts of the rectangle with n . x - c > 0 / < 0 (exact geometry: convex polygons)."""
+    rect = np.array([[x0, y0], [x1, y0], [x1, y1], [x0, y1]], float)
+    return polygon_rule(_clip_halfplane(rect, n, c, True), nq), polygon_rule(_clip_halfplane(rect, n, c, False), nq)
+
+
+def plane_edge_rules(p0, p1, n, c, nq):
+    """Gauss rules on the parts of the segment p0 -> p1 on the + / - side of the line n . x = c (weights: lengths)."""
+    p0, p1 = np.asarray(p0, float), np.asarray(p1, float)
+    d0, d1 = p0 @ n - c, p1 @ n - c
+    L = np.linalg.norm(p1 - p0)
+    g, w = _gauss(nq)
+
+    def rule(a, b):   # parameters along the segment
+        if b - a <= 1e-13:
+            return np.zeros((0, 2)), np.zeros(0)
+        t = 0.5 * (a + b) + 0.5 * (b - a) * g
+        return p0[None, :] + t[:, None] * (p1 - p0)[None, :], 0.5 * (b - a) * w * L
+    empty = (np.zeros((0, 2)), np.zeros(0))
+    if d0 >= 0 and d1 >= 0:
+        return rule(0.0, 1.0), empty
+    if d0 <= 0 and d1 <= 0:
+        return empty, rule(0.0, 1.0)
+    tc = d0 / (d0 - d1)
+    return (rule(0.0, tc), rule(tc, 1.0)) if d0 > 0 else (rule(tc, 1.0), rule(0.0, tc))
+
+
+def plane_segment_rule(x0, x1, y0, y1, n, c, nq):
+    """Gauss rule on the part of the line n . x = c inside the rectangle: points, weights (length), unit normals
+    pointing OUT of the + side (= -n)."""
+    rect = np.array([[x0, y0], [x1, y0], [x1, y1], [x0, y1]], float)
+    d = rect @ n - c
+    pts = []
+    for i in range(4):
+        dp, dq = d[i], d[(i + 1) % 4]
+        if (dp > 0 and dq < 0) or (dp < 0 and dq > 0):
+            pts.append(rect[i] + dp / (dp - dq) * (rect[(i + 1) % 4] - rect[i]))
+        elif dp == 0.0:
+            pts.append(rect[i])
+    if len(pts) < 2:
+        return np.zeros((0, 2)), np.zeros(0), np.zeros((0, 2))
+    a, b = pts[0], pts[-1]
+    for q in pts[1:]:
+        if np.linalg.norm(q - a) > np.linalg.norm(b - a):
+            b = q
+    L = np.linalg.norm(b - a)
+    if L <= 1e-13 * max(x1 - x0, y1 - y0):
+        return np.zeros((0, 2)), np.zeros(0), np.zeros((0, 2))
+    g, w = _gauss(nq)
+    t = 0.5 * (1 + g)
+    return a[None, :] + t[:, None] * (b - a)[None, :], 0.5 * w * L, np.tile(-np.asarray(n, float), (nq, 1))
+
+
 class CircleCutMesh:
     """Uniform nx x ny mesh on [x0, x0 + widths] cut by the circle |x - center| = radius.
 
@@ -205,6 +299,17 @@ class CircleCutMesh:
         self._build()
 
     # ------------------------------------------------------------------ geometry
+    # the three rules a subclass provides: the parts of a rectangle / of an axis-parallel segment on the + and on
+    # the - side, and the piece of the interface inside a rectangle (normals pointing out of the + side)
+    def _region_rules(self, xa, xb, ya, yb):
+        return disk_rect_rules(xa, xb, ya, yb, self.center[0], self.center[1], self.R, self.nq)
+
+    def _edge_rules(self, p0, p1):
+        return edge_rules(p0, p1, self.center[0], self.center[1], self.R, self.nqf1)
+
+    def _interface_rule(self, xa, xb, ya, yb):
+        return arc_rule(xa, xb, ya, yb, self.center[0], self.center[1], self.R, self.nqf1)
+
     def cell_box(self, c):
         i, j = divmod(c, self.ny)
         xa = self.x0[0] + i * self.h[0]
@@ -219,23 +324,22 @@ class CircleCutMesh:
     def _build(self):
         nx, ny, nq = self.nx, self.ny, self.nq
         ncell = nx * ny
-        cx, cy = self.center
         area = self.h[0] * self.h[1]
         pieces = {}          # (cell, phase) -> dict(vol=(pts, w), faces=[(pts, w)] * 4, area)
         iface = {}           # cell -> (pts, w, normals)
         eps = 1e-12
         for c in range(ncell):
             xa, xb, ya, yb = self.cell_box(c)
-            (pi, wi), (po, wo) = disk_rect_rules(xa, xb, ya, yb, cx, cy, self.R, nq)
+            (pi, wi), (po, wo) = self._region_rules(xa, xb, ya, yb)
             ain, aout = wi.sum(), wo.sum()
             corners = [((xa, ya), (xb, ya)), ((xb, ya), (xb, yb)), ((xa, yb), (xb, yb)), ((xa, ya), (xa, yb))]
-            fr = [edge_rules(p0, p1, cx, cy, self.R, self.nqf1) for p0, p1 in corners]
+            fr = [self._edge_rules(p0, p1) for p0, p1 in corners]
             if ain > eps * area:
                 pieces[(c, 1)] = dict(vol=(pi, wi), faces=[f[0] for f in fr], area=ain)
             if aout > eps * area:
                 pieces[(c, -1)] = dict(vol=(po, wo), faces=[f[1] for f in fr], area=aout)
             if (c, 1) in pieces and (c, -1) in pieces:
-                iface[c] = arc_rule(xa, xb, ya, yb, cx, cy, self.R, self.nqf1)
+                iface[c] = self._interface_rule(xa, xb, ya, yb)
         self.pieces, self.iface = pieces, iface
         self.cell_sign = np.array([0 if ((c, 1) in pieces and (c, -1) in pieces) else (1 if (c, 1) in pieces else -1)
                                    for c in range(ncell)], dtype=np.int8)
@@ -388,3 +492,26 @@ class CircleCutMesh:
     def sample_exact(self, u):
         x, y = self.vol_xy[..., 0], self.vol_xy[..., 1]
         return np.broadcast_to(u(x, y), x.shape) * (self.data["vol_wts"] != 0)
+
+
+class PlaneCutMesh(CircleCutMesh):
+    """The same data for a STRAIGHT interface: phase +1 where (x - point) . normal > 0 (`plane_distance_function`,
+    StefanDG/useful_routines.jl:29-31), as in the reference's plane_interface_tests.  The cut pieces are convex polygons
+    and are integrated exactly (polynomials up to total degree 2 numqp - 2), which is also what the reference's
+    quadratures do for a level set that its Q2 interpolant represents exactly."""
+
+    def __init__(self, x0, widths, nelements, normal, point, numqp, k1, k2, penalty, lam=0.0, merge_fraction=0.0,
+                 face_numqp=None):
+        n = np.asarray(normal, float)
+        self.n = n / np.linalg.norm(n)
+        self.c = float(self.n @ np.asarray(point, float))
+        super().__init__(x0, widths, nelements, (0.0, 0.0), 1.0, numqp, k1, k2, penalty, lam, merge_fraction, face_numqp)
+
+    def _region_rules(self, xa, xb, ya, yb):
+        return plane_rect_rules(xa, xb, ya, yb, self.n, self.c, self.nq)
+
+    def _edge_rules(self, p0, p1):
+        return plane_edge_rules(p0, p1, self.n, self.c, self.nqf1)
+
+    def _interface_rule(self, xa, xb, ya, yb):
+        return plane_segment_rule(xa, xb, ya, yb, self.n, self.c, self.nqf1)
