@@ -1,0 +1,119 @@
+"""The reference's cut-cell convergence studies with a manufactured solution, end to end on the GPU.
+
+Mirrors, for the interior-penalty and the local-DG discretisation,
+    StefanDG/InteriorPenalty/plane_interface_tests/test_plane_interface_IP_convergence.jl
+    StefanDG/InteriorPenalty/curved_interface_tests/test_curved_interface_IP_convergence.jl
+    StefanDG/LocalDG/plane_interface_tests/test_plane_interface_LDG_convergence.jl
+    StefanDG/LocalDG/curved_interface_tests/test_curved_interface_LDG_convergence.jl
+: T = cos(2 pi x) sin(2 pi y) on the unit square, k1 = k2 = 1, Dirichlet data on the whole boundary, the square cut by
+the straight line through (0.8, 0) with normal at 60 degrees ("plane") or by the circle of radius 0.5 around (1, 1)
+("curved").  IP: penalty = 1e3 / h, numqp = required_quadrature_order(p) + 2, ABSOLUTE L2 error.  LDG: all penalties 0
+except posboundarypenalty = 1, V0 at 45 degrees, numqp = required_quadrature_order(p) (p = 1) / + 2 (p = 2), relative L2
+error of T and absolute L2 errors of the two flux components.
+
+The geometry comes from stefanproblem_b200.cutcell (PlaneCutMesh: exact polygons; CircleCutMesh: exact circle), tiny
+pieces merged below 0.2 of a cell (the ratio that reproduces CutCellDG.MergedMesh!'s results).  For the straight
+interface both this generator and the reference integrate the polynomial integrands exactly, so the stored CSVs are
+reproduced almost digit for digit where the quadrature is exact (IP: within 0.2 % at every n; LDG p = 2: within 0.06 %);
+LDG p = 1 uses a 2-point rule that is NOT exact on cut pieces, there the two rule constructions differ (15-30 %).
+
+    python examples/cut_interface_convergence.py [plane|curved] [ip|ldg]
+"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+MERGE = 0.2
+
+
+def exact(x, y):
+    return np.cos(2 * np.pi * x) * np.sin(2 * np.pi * y)
+
+
+def source(x, y):
+    return 8 * np.pi ** 2 * np.cos(2 * np.pi * x) * np.sin(2 * np.pi * y)
+
+
+def grad_x(x, y):
+    return -2 * np.pi * np.sin(2 * np.pi * x) * np.sin(2 * np.pi * y)
+
+
+def grad_y(x, y):
+    return 2 * np.pi * np.cos(2 * np.pi * x) * np.cos(2 * np.pi * y)
+
+
+def make_mesh(kind, nelmts, numqp, penalty):
+    from stefanproblem_b200.cutcell import CircleCutMesh, PlaneCutMesh
+    if kind == "plane":
+        normal = (np.cos(np.radians(60.0)), np.sin(np.radians(60.0)))
+        return PlaneCutMesh([0.0, 0.0], [1.0, 1.0], [nelmts, nelmts], normal, [0.8, 0.0], numqp, 1.0, 1.0, penalty, 0.0,
+                            merge_fraction=MERGE)
+    return CircleCutMesh([0.0, 0.0], [1.0, 1.0], [nelmts, nelmts], [1.0, 1.0], 0.5, numqp, 1.0, 1.0, penalty, 0.0,
+                         merge_fraction=MERGE)
+
+
+def _host_solve(system, rhs):
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    import torch
+    r, c, v = (t.cpu().numpy() for t in system.to_coo())
+    M = sp.coo_matrix((v, (r, c)), shape=system.shape).tocsc()
+    return torch.from_numpy(spla.spsolve(M, rhs.cpu().numpy())).cuda()
+
+
+def measure_ip(kind, nelmts, order):
+    """[absolute L2 error], solver iterations"""
+    from stefanproblem_b200 import blocks as B
+    mesh = make_mesh(kind, nelmts, order + 3, 1e3 * nelmts)
+    system = B.BlockSystem(mesh.nsol, order, mesh.nqv, mesh.nslots, mesh.nqf).assemble(mesh.data)
+    rhs = system.rhs(mesh.sample_source(source, source), mesh.sample_boundary(exact), 0.0)
+    sol, info = system.solve(rhs, tol=1e-13, maxiter=200000)
+    if not info["converged"]:
+        sol = _host_solve(system, rhs)
+    err, _ = system.l2_error(sol, mesh.sample_exact(exact))
+    return [err], info["iterations"], mesh
+
+
+def measure_ldg(kind, nelmts, order):
+    """[relative L2 error of T, absolute L2 errors of the flux components], solver iterations"""
+    from stefanproblem_b200 import blocks as B
+    V0 = (np.cos(np.radians(45.0)), np.sin(np.radians(45.0)))
+    mesh = make_mesh(kind, nelmts, 2 if order == 1 else order + 3, 0.0)
+    data = dict(mesh.data)
+    data["slot_pen"] = B.ldg_slot_penalties(data, V0, 0.0, 0.0, 0.0, 1.0, mesh.slot_is_interface)
+    system = B.LDGBlockSystem(mesh.nsol, order, mesh.nqv, mesh.nslots, mesh.nqf).assemble(data, V0)
+    rhs = system.rhs(mesh.sample_source(source, source), mesh.sample_boundary(exact))
+    sol, info = system.solve(rhs, tol=1e-12, maxiter=100000)
+    if not info["residual_norm"] <= 1e-9 * info["rhs_norm"]:
+        sol = _host_solve(system, rhs)   # (the reference's own step: triplets + sparse direct solve)
+    eT, nT = system.l2_error(sol, mesh.sample_exact(exact), 0)
+    e1, _ = system.l2_error(sol, mesh.sample_exact(grad_x), 1)
+    e2, _ = system.l2_error(sol, mesh.sample_exact(grad_y), 2)
+    return [eT / nT, e1, e2], info["iterations"], mesh
+
+
+def main(kind="plane", method="ip", powers=(1, 2, 3, 4, 5)):
+    nelmts = [2 ** p + 1 for p in powers]
+    measure = measure_ip if method == "ip" else measure_ldg
+    table = {}
+    for order in (1, 2):
+        out = [measure(kind, n, order) for n in nelmts]
+        err = np.array([e for e, _, _ in out])
+        rate = np.diff(np.log(err), axis=0) / np.diff(np.log(1.0 / np.array(nelmts)))[:, None]
+        table[order] = (err, rate)
+        for n, (e, it, m), r in zip(nelmts, out, [[np.nan] * err.shape[1]] + list(rate)):
+            print(f"{kind} {method} p={order} nelmts {n:3d}  solution cells {m.nsol:5d}  errors "
+                  + " ".join(f"{v:.6e}" for v in e) + "  rates " + " ".join(f"{v:5.2f}" for v in r) + f"  iterations {it}")
+    return nelmts, table
+
+
+if __name__ == "__main__":
+    a = sys.argv[1:]
+    kinds = [k for k in ("plane", "curved") if k in a] or ["plane", "curved"]
+    methods = [m for m in ("ip", "ldg") if m in a] or ["ip", "ldg"]
+    for k in kinds:
+        for m in methods:
+            main(k, m)

@@ -51,7 +51,7 @@ def exact_solution(prm):
     return u
 
 
-def measure_error(nelmts, solverorder, prm, penaltyfactor=1e3, merge_fraction=0.25, solver="cg"):
+def measure_error(nelmts, solverorder, prm, penaltyfactor=1e3, merge_fraction=0.2, solver="cg"):
     import torch
     from stefanproblem_b200 import blocks as B
     from stefanproblem_b200.cutcell import CircleCutMesh

@@ -48,7 +48,7 @@ def exact_solution(prm):
     return u, grad
 
 
-def measure_error(nelmts, solverorder, prm=PRM, merge_fraction=0.25, solver="schur"):
+def measure_error(nelmts, solverorder, prm=PRM, merge_fraction=0.2, solver="schur"):
     import torch
     from stefanproblem_b200 import blocks as B
     from stefanproblem_b200.cutcell import CircleCutMesh

@@ -93,7 +93,7 @@ def test_cut_mesh_geometry_is_consistent(merge):
         assert m.nsol < len(m.pieces) and (area > 0.2 * (1.0 / n) ** 2).all()   # no tiny solution cell is left
 
 
-def _study(n, order, prm, merge=0.25):
+def _study(n, order, prm, merge=0.2):
     sol = (RobinCylindricalSolver(prm["q1"], prm["k1"], prm["q2"], prm["k2"], prm["lam"], prm["R"], prm["b"], prm["Tw"], prm["Tm"])
            if prm["lam"] else CylindricalSolver(prm["q1"], prm["k1"], prm["q2"], prm["k2"], prm["R"], prm["b"], prm["Tw"]))
     m = CircleCutMesh([0, 0], [1, 1], [n, n], [0, 0], prm["R"], prm["numqp"][order], prm["k1"], prm["k2"], 1e3 * n, prm["lam"],
@@ -184,7 +184,7 @@ def test_ldg_block_oracle_equals_the_uniform_ldg_oracle(order, interfacepenalty)
     assert np.abs(b - b_ref).max() <= 1e-14 * np.abs(b_ref).max()
 
 
-def _ldg_cylinder(n, order, merge=0.25, exact=None, k2=2.0, q=(1.0, 2.0), numqp=None):
+def _ldg_cylinder(n, order, merge=0.2, exact=None, k2=2.0, q=(1.0, 2.0), numqp=None):
     from oracle import ldg_blocks as olb
     from stefanproblem_b200.blocks import ldg_slot_penalties
     V0 = (np.cos(np.pi / 4), np.sin(np.pi / 4))
@@ -241,3 +241,119 @@ def test_ldg_cut_cell_patch_test(order):
     grad = lambda x, y: (2.0 + 0 * x, -0.5 + 0 * x)  # noqa: E731
     for e, den in _ldg_cylinder(5, order, exact=(T, grad), k2=1.0, q=(0.0, 0.0), numqp=12):
         assert e <= 1e-10 * den, (e, den)
+
+
+# ------------------------------------------- manufactured-solution studies: straight and circular interface, IP and LDG
+def _manufactured(kind, method, n, order):
+    """examples/cut_interface_convergence.py with the ORACLE's block assembly and a sparse direct solve."""
+    import importlib.util
+    from oracle import ldg_blocks as olb
+    from stefanproblem_b200.blocks import ldg_slot_penalties
+    spec = importlib.util.spec_from_file_location(
+        "cut_ex", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples",
+                               "cut_interface_convergence.py"))
+    ex = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ex)
+    if method == "ip":
+        m = ex.make_mesh(kind, n, order + 3, 1e3 * n)
+        A = sp.csc_matrix(ob.dense_matrix(ob.assemble_blocks(order, m.data), m.data["slot_nbr"]))
+        assert abs(A - A.T).max() <= 1e-12 * abs(A).max()
+        u = spla.spsolve(A, ob.assemble_rhs(order, m.data, m.sample_source(ex.source, ex.source),
+                                            m.sample_boundary(ex.exact), 0.0))
+        return [ob.l2_error(order, m.data, u, m.sample_exact(ex.exact))[0]]
+    V0 = (np.cos(np.pi / 4), np.sin(np.pi / 4))
+    m = ex.make_mesh(kind, n, 2 if order == 1 else order + 3, 0.0)
+    data = dict(m.data)
+    data["slot_pen"] = ldg_slot_penalties(data, V0, 0.0, 0.0, 0.0, 1.0, m.slot_is_interface)
+    A = sp.csc_matrix(olb.dense_matrix(olb.assemble_blocks(order, data, V0), data["slot_nbr"]))
+    u = spla.spsolve(A, olb.assemble_rhs(order, data, m.sample_source(ex.source, ex.source), m.sample_boundary(ex.exact)))
+    eT, nT = ob.l2_error(order, data, u[0::3], m.sample_exact(ex.exact))
+    return [eT / nT, ob.l2_error(order, data, u[1::3], m.sample_exact(ex.grad_x))[0],
+            ob.l2_error(order, data, u[2::3], m.sample_exact(ex.grad_y))[0]]
+
+
+# |this / CSV - 1| allowed per (kind, method, order); observed over n = 3 ... 17 in the comment
+CUT_STUDY_TOL = {
+    ("plane", "ip", 1): 0.006, ("plane", "ip", 2): 0.002,        # 0.9958 ... 1.0018, 0.9996 ... 1.0008
+    ("plane", "ldg", 2): 0.001,                                   # 0.9994 ... 1.0002 in all three columns
+    ("curved", "ip", 1): 0.04, ("curved", "ip", 2): 0.015,      # 1.004 ... 1.032, 0.989 ... 1.004
+    ("curved", "ldg", 2): 0.005,                                  # 0.9962 ... 1.0008
+}
+
+
+@pytest.mark.parametrize("kind", ["plane", "curved"])
+@pytest.mark.parametrize("method", ["ip", "ldg"])
+def test_cut_interface_studies_small_meshes_against_the_reference_csvs(kind, method):
+    """n = 3, 5, 9 of the reference's plane_interface_tests / curved_interface_tests studies (IP and local DG) with the
+    oracle's block assembly on the generator's data against the stored CSVs.  Where the quadrature is exact for the
+    polynomial integrands (everything but LDG p = 1, which the reference runs with a 2-point rule) the CSVs are
+    reproduced to 3-4 digits -- the straight interface is represented exactly by both geometries, and at these
+    resolutions the circle nearly so.  LDG p = 1: the 2-point rules on the cut pieces are construction dependent
+    (observed 0.87 ... 2.2 of the CSV); only its order of magnitude is asserted."""
+    nc = 1 if method == "ip" else 3
+    for row in GOLD[f"{method}_{kind}"][:3]:
+        n = row[0]
+        for order in (1, 2):
+            got = _manufactured(kind, method, n, order)
+            want = row[1 + nc * (order - 1):1 + nc * order]
+            tol = CUT_STUDY_TOL.get((kind, method, order))
+            for gv, wv in zip(got, want):
+                if tol is None:
+                    assert 0.5 * wv < gv < 3.0 * wv, (kind, method, n, order, got, want)
+                else:
+                    assert abs(gv / wv - 1.0) <= tol, (kind, method, n, order, got, want)
+
+
+@pytest.mark.parametrize("method", ["ip", "ldg"])
+def test_plane_interface_linear_solution_is_reproduced_to_rounding(method):
+    """plane_interface_tests/linear_solution_{IP,LDG}_convergence.csv (errors 1e-16): T = 3 x + 4 y, no source.  The
+    polygon rules are exact, so the cut mesh reproduces it to rounding for both discretisations."""
+    from oracle import ldg_blocks as olb
+    from stefanproblem_b200.blocks import ldg_slot_penalties
+    from stefanproblem_b200.cutcell import PlaneCutMesh
+    T = lambda x, y: 3.0 * x + 4.0 * y  # noqa: E731
+    zero = lambda x, y: 0.0 * x  # noqa: E731
+    nrm = (np.cos(np.pi / 3), np.sin(np.pi / 3))
+    for order in (1, 2):
+        m = PlaneCutMesh([0, 0], [1, 1], [5, 5], nrm, [0.8, 0.0], order + 1 if method == "ldg" and order == 1 else order + 3,
+                         1.0, 1.0, 1e3 * 5, 0.0, merge_fraction=0.2)
+        if method == "ip":
+            A = sp.csc_matrix(ob.dense_matrix(ob.assemble_blocks(order, m.data), m.data["slot_nbr"]))
+            u = spla.spsolve(A, ob.assemble_rhs(order, m.data, m.sample_source(zero, zero), m.sample_boundary(T), 0.0))
+            e, den = ob.l2_error(order, m.data, u, m.sample_exact(T))
+            assert e <= 1e-9 * den, (order, e, den)      # (penalty 5e3: the system's conditioning, not the scheme)
+        else:
+            V0 = (np.cos(np.pi / 4), np.sin(np.pi / 4))
+            data = dict(m.data)
+            data["slot_pen"] = ldg_slot_penalties(data, V0, 0.0, 0.0, 0.0, 1.0, m.slot_is_interface)
+            A = sp.csc_matrix(olb.dense_matrix(olb.assemble_blocks(order, data, V0), data["slot_nbr"]))
+            u = spla.spsolve(A, olb.assemble_rhs(order, data, m.sample_source(zero, zero), m.sample_boundary(T)))
+            for comp, ex in ((0, T), (1, lambda x, y: 3.0 + 0 * x), (2, lambda x, y: 4.0 + 0 * x)):
+                e, den = ob.l2_error(order, data, u[comp::3], m.sample_exact(ex))
+                assert e <= 1e-11 * den, (order, comp, e, den)
+
+
+def test_polygon_rules_are_exact():
+    from stefanproblem_b200.cutcell import plane_edge_rules, plane_rect_rules, plane_segment_rule, polygon_rule
+    poly = np.array([[0, 0], [1, 0], [1.2, 0.7], [0.4, 1.1], [-0.2, 0.5]], float)
+    P, W = polygon_rule(poly, 4)
+    P2, W2 = polygon_rule(poly, 12)
+    x, y = poly[:, 0], poly[:, 1]
+    assert abs(W.sum() - 0.5 * abs(np.dot(x, np.roll(y, -1)) - np.dot(y, np.roll(x, -1)))) < 1e-14
+    f = lambda p: p[:, 0] ** 3 * p[:, 1] ** 3 + p[:, 0] ** 6  # noqa: E731   (total degree 6 = 2 nq - 2)
+    assert abs((W * f(P)).sum() - (W2 * f(P2)).sum()) < 1e-13
+    n, c = np.array([np.cos(1.0), np.sin(1.0)]), 0.45
+    (pp, wp), (pm, wm) = plane_rect_rules(0.1, 0.6, 0.2, 0.9, n, c, 3)
+    assert abs(wp.sum() + wm.sum() - 0.5 * 0.7) < 1e-14 and (pp @ n - c > 0).all() and (pm @ n - c < 0).all()
+    (ep, ewp), (em, ewm) = plane_edge_rules((0.1, 0.2), (0.6, 0.2), n, c, 3)
+    assert abs(ewp.sum() + ewm.sum() - 0.5) < 1e-14
+    sp_, sw, sn = plane_segment_rule(0.1, 0.6, 0.2, 0.9, n, c, 3)
+    assert np.abs(sp_ @ n - c).max() < 1e-14 and np.allclose(sn, -n)
+    # divergence theorem on the + piece: integral of div(x, y) = 2 |piece| = boundary integral of (x, y) . normal
+    faces = [((0.1, 0.2), (0.6, 0.2), (0, -1)), ((0.6, 0.2), (0.6, 0.9), (1, 0)), ((0.1, 0.9), (0.6, 0.9), (0, 1)),
+             ((0.1, 0.2), (0.1, 0.9), (-1, 0))]
+    flux = (sw * (sp_ @ (-n))).sum()
+    for p0, p1, nn in faces:
+        (q, wq), _ = plane_edge_rules(p0, p1, n, c, 3)
+        flux += (wq * (q @ np.array(nn, float))).sum()
+    assert abs(flux - 2 * wp.sum()) < 1e-13

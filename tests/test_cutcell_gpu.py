@@ -177,3 +177,31 @@ def test_ldg_cylinder_convergence_study_on_the_gpu(cuda):
         assert e2[1] < 1.15 * g[5] and e2[2] < 1.15 * g[6], (2, g[0], e2, g)   # (observed: 0.14 ... 1.08)
     assert np.mean(rate1[1:, 0]) > 1.7 and np.mean(rate1[1:, 1:]) > 1.2   # CSV: 1.8 (T), 1.3 (flux)
     assert np.mean(rate2[1:, 0]) > 2.6 and np.mean(rate2[1:, 1:]) > 2.0   # CSV: 2.8 (T), 2.4 (flux)
+
+
+@pytest.mark.parametrize("kind", ["plane", "curved"])
+@pytest.mark.parametrize("method", ["ip", "ldg"])
+def test_cut_interface_convergence_studies_on_the_gpu(cuda, kind, method):
+    """plane_interface_tests / curved_interface_tests of the reference (IP and local DG, p = 1, 2, n = 3 ... 33) end to
+    end on the device against the stored CSVs.  Tolerances as in tests/test_cutcell_cpu.py (3-4 digits wherever the
+    quadrature is exact; the finest circular meshes a little looser: IP curved n = 33)."""
+    spec = importlib.util.spec_from_file_location("cut_ex", os.path.join(ROOT, "examples", "cut_interface_convergence.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    nelmts, table = mod.main(kind, method)
+    gold = GOLD[f"{method}_{kind}"]
+    assert [g[0] for g in gold] == nelmts
+    tol = {("plane", "ip", 1): 0.006, ("plane", "ip", 2): 0.003, ("plane", "ldg", 2): 0.001,
+           ("curved", "ip", 1): 0.04, ("curved", "ip", 2): 0.015, ("curved", "ldg", 2): 0.005}
+    nc = 1 if method == "ip" else 3
+    for order in (1, 2):
+        err, rate = table[order]
+        for e, g in zip(err, gold):
+            want = g[1 + nc * (order - 1):1 + nc * order]
+            t = tol.get((kind, method, order))
+            for ev, wv in zip(e, want):
+                if t is None:
+                    assert 0.4 * wv < ev < 3.0 * wv, (kind, method, order, g[0], e, want)
+                else:
+                    assert abs(ev / wv - 1.0) <= t, (kind, method, order, g[0], e, want)
+        assert np.mean(rate[1:, 0]) > (1.8 if order == 1 else 2.8), (kind, method, order, rate)
