@@ -335,7 +335,9 @@ ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const 
           h ^= hi32(v[q]);
         }
         if (chunk_is_array_end(k) && j == a.ny - 1 && src != nullptr) {
-          // (sh + nbytes) was 8 mod 16: the copy stopped 8 bytes short of the array end
+          // (sh + nbytes) was 8 mod 16: the copy stopped 8 bytes short of the array end.  A halo column may be peer
+          // memory: this plain load is ordered after lane 0's flag acquire through the mbarrier this lane waited on
+          // (acquire -> bulk copy issued -> complete_tx -> this lane's try_wait), it never runs ahead of the copy.
           if ((sh + nbytes) & 8u) v[NF - 1] = *reinterpret_cast<const double*>(src + nbytes - 8);
         }
       } else {
