@@ -126,6 +126,9 @@ __device__ __forceinline__ void st_global_v4f(double* p, const double* v) {
   asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
 }
 
+#ifndef FD_PREFETCH
+#define FD_PREFETCH 1
+#endif
 template <int MODE>
 __global__ void __launch_bounds__(256)
 fd_apply_vec(const double* __restrict__ u, const double* __restrict__ u_lo, const double* __restrict__ u_hi,
@@ -140,16 +143,33 @@ fd_apply_vec(const double* __restrict__ u, const double* __restrict__ u_lo, cons
     if (g >= n && g < n + 3 && u_hi != nullptr) return u_hi[g - n];
     return 0.0;
   };
-  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec_w;
-       v += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t g0 = 4 * v;
-    double w[10];  // u[g0-3 .. g0+6]
-    if (g0 + 3 < n) {
-      ld_global_v4(u + g0, w + 3);
+  // the thread's own 4 nodes and row kinds of vector vv
+  auto load_own = [&](int64_t vv, double* o, unsigned& kk) {
+    const int64_t gg = 4 * vv;
+    if (gg + 3 < n) {
+      ld_global_v4(u + gg, o);
     } else {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) w[3 + k] = node(g0 + k);
+      for (int k = 0; k < 4; ++k) o[k] = node(gg + k);
     }
+    kk = vv < nvec ? *reinterpret_cast<const unsigned*>(kind + gg) : 0u;
+  };
+  // One iteration ahead: the loads of the next vector are issued before this one is worked on, so a thread always
+  // has a request in flight (round 2; without it the kernel sat at 73-80 % of the HBM peak with 64 KB of loads per
+  // SM in flight only at the instant every thread had just issued).
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double cur[4];
+  unsigned kcur = 0;
+  if (v < nvec_w) load_own(v, cur, kcur);
+  for (; v < nvec_w; v += stride) {
+    const int64_t g0 = 4 * v;
+    double nxt[4] = {0.0, 0.0, 0.0, 0.0};
+    unsigned knext = 0;
+    if (FD_PREFETCH && v + stride < nvec_w) load_own(v + stride, nxt, knext);
+    double w[10];  // u[g0-3 .. g0+6]
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w[3 + k] = cur[k];
     w[0] = __shfl_up_sync(0xffffffffu, w[4], 1);
     w[1] = __shfl_up_sync(0xffffffffu, w[5], 1);
     w[2] = __shfl_up_sync(0xffffffffu, w[6], 1);
@@ -164,43 +184,48 @@ fd_apply_vec(const double* __restrict__ u, const double* __restrict__ u_lo, cons
 #pragma unroll
       for (int k = 0; k < 3; ++k) w[7 + k] = node(g0 + 4 + k);
     }
-    if (v >= nvec) continue;
-    const unsigned kinds = *reinterpret_cast<const unsigned*>(kind + g0);
-    const bool any_cont = (kinds & (0x01010101u * FD_CONTINUITY)) != 0u;
-    double r[4];
+    if (v < nvec) {
+      const unsigned kinds = kcur;
+      const bool any_cont = (kinds & (0x01010101u * FD_CONTINUITY)) != 0u;
+      double r[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const double* c = w + 3 + k;
-      const unsigned kd = (kinds >> (8 * k)) & 0xffu;
-      const unsigned row = kd & 7u;
-      double t = 0.0;
-      if (row == FD_CENTRAL) t = (c[-1] - 2.0 * c[0] + c[1]) * inv_h2;
-      else if (row == FD_BACKWARD) t = (-c[-3] + 4.0 * c[-2] - 5.0 * c[-1] + 2.0 * c[0]) * inv_h2;
-      else if (row == FD_FORWARD) t = (2.0 * c[0] - 5.0 * c[1] + 4.0 * c[2] - c[3]) * inv_h2;
-      else if (row == FD_IDENTITY) t = c[0];
-      // interface rows are a handful per mesh: one test of the packed word keeps the loop off the common path
-      if (any_cont && (kd & FD_CONTINUITY)) {
-        for (int q = 0; q < ncont; ++q)
-          if (cont[q].node == g0 + k) {
-            const double rr = cont[q].r, ss = cont[q].s;
-            t += rr * c[-2] - 4.0 * rr * c[-1] + (1.0 + 3.0 * rr) * c[0] - (1.0 + 3.0 * ss) * c[1] +
-                 4.0 * ss * c[2] - ss * c[3];
-          }
+      for (int k = 0; k < 4; ++k) {
+        const double* c = w + 3 + k;
+        const unsigned kd = (kinds >> (8 * k)) & 0xffu;
+        const unsigned row = kd & 7u;
+        double t = 0.0;
+        if (row == FD_CENTRAL) t = (c[-1] - 2.0 * c[0] + c[1]) * inv_h2;
+        else if (row == FD_BACKWARD) t = (-c[-3] + 4.0 * c[-2] - 5.0 * c[-1] + 2.0 * c[0]) * inv_h2;
+        else if (row == FD_FORWARD) t = (2.0 * c[0] - 5.0 * c[1] + 4.0 * c[2] - c[3]) * inv_h2;
+        else if (row == FD_IDENTITY) t = c[0];
+        // interface rows are a handful per mesh: one test of the packed word keeps the loop off the common path
+        if (any_cont && (kd & FD_CONTINUITY)) {
+          for (int q = 0; q < ncont; ++q)
+            if (cont[q].node == g0 + k) {
+              const double rr = cont[q].r, ss = cont[q].s;
+              t += rr * c[-2] - 4.0 * rr * c[-1] + (1.0 + 3.0 * rr) * c[0] - (1.0 + 3.0 * ss) * c[1] +
+                   4.0 * ss * c[2] - ss * c[3];
+            }
+        }
+        if (MODE == 0) {
+          r[k] = t;
+        } else {
+          const bool laplace = row == FD_CENTRAL || row == FD_BACKWARD || row == FD_FORWARD;
+          r[k] = laplace ? c[0] + ((kd & FD_PHASE2) ? dtk2 : dtk1) * t : c[0];
+        }
       }
-      if (MODE == 0) {
-        r[k] = t;
+      if (g0 + 3 < n) {
+        st_global_v4f(y + g0, r);
       } else {
-        const bool laplace = row == FD_CENTRAL || row == FD_BACKWARD || row == FD_FORWARD;
-        r[k] = laplace ? c[0] + ((kd & FD_PHASE2) ? dtk2 : dtk1) * t : c[0];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (g0 + k < n) y[g0 + k] = r[k];
       }
     }
-    if (g0 + 3 < n) {
-      st_global_v4f(y + g0, r);
-    } else {
+    if (!FD_PREFETCH && v + stride < nvec_w) load_own(v + stride, nxt, knext);
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (g0 + k < n) y[g0 + k] = r[k];
-    }
+    for (int k = 0; k < 4; ++k) cur[k] = nxt[k];
+    kcur = knext;
   }
 }
 
