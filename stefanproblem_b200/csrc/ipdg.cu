@@ -68,7 +68,6 @@ struct ApplyArgs {
   unsigned long long* dbg_times;             // development only: per-CTA {start, prologue, loop, end} globaltimer, or null
   // dynamic tail queue: [0] next fix-list index, [1] CTAs finished; both reset by the last CTA
   unsigned* tail_ctr;
-  int head_share;  // 1: every warp takes its static share of the exception cells behind its first copies (fixup_tail)
   // fused explicit step (MODE 1 of the kernels): y = x + step_scale * Minv (b - A x), Minv the
   // Kronecker square of the inverse 1-D reference mass matrix
   const double* b;
@@ -159,22 +158,12 @@ __device__ __forceinline__ void step_epilogue(const ApplyArgs& a, const double* 
 // operators of ipdg_tables.h become warp shuffles along the x- / y-lines of the cell, every
 // load and store is coalesced, and a cell costs ~150 instructions at ~40 registers instead of a
 // whole per-thread ip_cell_rows with run-time table indices (10-25 us per 32-cell chunk).
-// Round 2, later: HEAD share.  The same routine is also called once by every warp right after it has issued its
-// first column copies (HEAD = true): warp g of the grid takes the rounds g, g + W, g + 2 W, ... (W = warps of the grid,
-// at most BATCH of them) -- statically, no atomic -- and works on them while its own copies are in flight, i.e. in the
-// 1-2 us in which the memory pipeline of the kernel is still filling.  What used to be a 2 us (IP) to 8 us (LDG order 3)
-// epilogue of the whole kernel becomes a fraction of a microsecond on some warps' prologue.  The queue at the end of
-// the kernel starts behind the head's share (BATCH W rounds) and is empty unless the list is unusually long.
-template <int P, int MODE, bool HEAD = false>
+template <int P, int MODE>
 __device__ __forceinline__ void fixup_tail(const IpTab<P>& tab, const ApplyArgs& a) {
   constexpr int N1 = P + 1, NF = N1 * N1;
   constexpr int CW = 32 / NF;      // cells per warp and round
   constexpr int BATCH = 4;         // rounds per queue access; their loads are issued together
   if (a.nfix <= 0) return;
-  const int gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwarps = gridDim.x * (blockDim.x >> 5);
-  const unsigned head_total = a.head_share ? (unsigned)nwarps * (unsigned)(CW * BATCH) : 0u;  // cells the heads take
-  if (HEAD && (!a.head_share || gwarp * CW >= a.nfix)) return;
-  if (!HEAD && head_total >= (unsigned)a.nfix) return;
   const int lane = threadIdx.x & 31;
   const bool lane_live = lane < CW * NF;
   const int grp = lane_live ? lane / NF : 0;          // (idle lanes shadow group 0 and never store)
@@ -183,29 +172,19 @@ __device__ __forceinline__ void fixup_tail(const IpTab<P>& tab, const ApplyArgs&
   const int gbase = grp * NF;
   unsigned long long epoch = 0;   // the value the neighbours' flags must have reached
   if (a.sync_epoch != 0) epoch = peer_epoch(a.sync_epoch_dev, a.sync_epoch) - (unsigned long long)a.sync_chained;
-  for (int pass = 0;; ++pass) {
-    int t0s[BATCH];  // first record of each round of this batch
-    if (HEAD) {
-      if (pass > 0) break;
-#pragma unroll
-      for (int rd = 0; rd < BATCH; ++rd) t0s[rd] = (gwarp + rd * nwarps) * CW;
-    } else {
-      unsigned base = 0;
-      if (lane == 0) base = atomicAdd(a.tail_ctr, (unsigned)(CW * BATCH));
-      base = __shfl_sync(0xffffffffu, base, 0) + head_total;
-      if (base >= (unsigned)a.nfix) break;
-#pragma unroll
-      for (int rd = 0; rd < BATCH; ++rd) t0s[rd] = (int)base + rd * CW;
-    }
+  for (;;) {
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(a.tail_ctr, (unsigned)(CW * BATCH));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= (unsigned)a.nfix) break;
     // ---- all loads of the batch first (two dependent levels: record, then dofs) ----
     int2 rec[BATCH];
     double X[BATCH], XL[BATCH], XR[BATCH], XD[BATCH], XU[BATCH];
     [[maybe_unused]] double Bv[BATCH];
 #pragma unroll
-    for (int rd = 0; rd < BATCH; ++rd) rec[rd] = a.fix[min(t0s[rd] + grp, a.nfix - 1)];
+    for (int rd = 0; rd < BATCH; ++rd) rec[rd] = a.fix[min((int)base + rd * CW + grp, a.nfix - 1)];
 #pragma unroll
     for (int rd = 0; rd < BATCH; ++rd) {
-      if (t0s[rd] >= a.nfix) continue;  // (warp-uniform; the head's later rounds are usually empty)
       const int64_t cell = rec[rd].x;
       const int code = rec[rd].y;
       const int i = (int)(cell / a.ny), j = (int)(cell - (int64_t)i * a.ny);
@@ -228,7 +207,7 @@ __device__ __forceinline__ void fixup_tail(const IpTab<P>& tab, const ApplyArgs&
     // ---- the line operators of each cell, by shuffles along its x- / y-lines ----
 #pragma unroll
     for (int rd = 0; rd < BATCH; ++rd) {
-      const int t0 = t0s[rd];
+      const int t0 = (int)base + rd * CW;
       if (t0 < a.nfix) {  // (warp-uniform)
         const bool live = lane_live && (t0 + grp) < a.nfix;
         const int code = rec[rd].y;
@@ -431,8 +410,6 @@ static int launch_apply(IpdgHandle* h, const ApplyArgs& args0, int algo, cudaStr
   args.nfix = h->plan.fix_col_ofs[args.cend] - h->plan.fix_col_ofs[args.cbeg];
   static const bool skip_tail = getenv("STEFAN_DEV_SKIP_TAIL") != nullptr;  // timing experiments only (wrong results)
   if (skip_tail) args.nfix = 0;
-  static const bool head_share = [] { const char* e = getenv("STEFAN_HEAD_SHARE"); return e == nullptr || atoi(e) != 0; }();
-  args.head_share = head_share ? 1 : 0;
   // CTA = (group of adjacent strips, x segment); one wave of MINB CTAs per SM
   int rc = step ? launch_march<P, 1>(h, tab, args, st) : launch_march<P, 0>(h, tab, args, st);
   if (rc) return rc;

@@ -397,8 +397,6 @@ ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const 
     // prologue: columns c0-1 .. c0+NST-2 into slots 0 .. NST-1
 #pragma unroll
     for (int k = 0; k < NST; ++k) issue_general(c0 - 1 + k, ring + k * C::STAGE, bars + 8 * k);
-    // while they are in flight: this warp's static share of the exception cells (see fixup_tail)
-    fixup_tail<P, MODE, true>(tab, a);
     double X[NF], tL[N1], dL[N1];
     {
       double XLfull[NF];
@@ -703,7 +701,6 @@ ipdg_apply_march(const __grid_constant__ IpTab<P> tab, const ApplyArgs a, const 
     }
   }
   griddep_wait();  // (warps without a strip have not waited yet)
-  if (!(strip < nstrips && c0 < c1)) fixup_tail<P, MODE, true>(tab, a);  // (... nor taken their head share)
   fixup_tail<P, MODE>(tab, a);
   if (a.dbg_times != nullptr) {  // development: end of the tail
     __syncthreads();

@@ -251,11 +251,9 @@ static int ldg_launch_march_v(LdgHandle* h, const LdgArgs& a, cudaStream_t st) {
     STEFAN_CUDA(cudaMemset(h->tail_ctr_dev, 0, kLdgTailRing * 2 * sizeof(unsigned)));
   }
   LdgMarchArgs m{a.x, a.x_lo, a.x_hi, a.y, a.phase, a.nx, a.ny, h->plan.fix_dev, h->plan.nfix, 0u, nullptr,
-                 h->tail_ctr_dev + 2 * (h->launch_seq++ % kLdgTailRing), 0};
+                 h->tail_ctr_dev + 2 * (h->launch_seq++ % kLdgTailRing)};
   static const bool skip_tail = getenv("STEFAN_DEV_SKIP_TAIL") != nullptr;  // timing experiments only (wrong results)
   if (skip_tail) m.nfix = 0;
-  static const bool head_share = [] { const char* e = getenv("STEFAN_HEAD_SHARE"); return e == nullptr || atoi(e) != 0; }();
-  m.head_share = head_share ? 1 : 0;
   CUtensorMap tm;
   std::memset(&tm, 0, sizeof(tm));
   if (C::TENSOR) {

@@ -76,7 +76,6 @@ struct LdgMarchArgs {
   unsigned zero;  // 0 at run time, unknown at compile time (slot release, see ipdg_march.cuh)
   unsigned long long* dbg_times;  // development only: per-CTA {start, prologue end, loop end, end} globaltimer, or null
   unsigned* tail_ctr;  // dynamic tail queue: [0] next fix-list index, [1] CTAs finished (reset by the last CTA)
-  int head_share;      // 1: every warp takes its static share of the exception cells behind its first copies
 };
 __device__ __forceinline__ void ldg_griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void ldg_griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -98,47 +97,30 @@ __device__ __forceinline__ void ldg_dbg_stamp(const LdgMarchArgs& a, int slot) {
 // coalesced (24 contiguous bytes per lane), about 40 registers and ~200 instructions per cell
 // instead of one thread working through a whole cell with run-time table indices (measured in
 // round 1 / 2: 10-25 us per 32-cell chunk at orders 2, 3 -- the kernel's critical path).
-// HEAD = true: the static share every warp takes right behind its first column copies (rounds g, g + W, ... of warp g,
-// W = warps of the grid; see fixup_tail in ipdg.cu) -- the queue at the end then starts behind BATCH W rounds.
-template <int P, bool HEAD = false>
+template <int P>
 __device__ __forceinline__ void ldg_fixup_tail(const LdgTab<P>& tab, const LdgMarchArgs& a) {
   constexpr int N1 = P + 1, NF = N1 * N1, CD = 3 * NF;
   constexpr int CW = 32 / NF;      // cells per warp and round
   constexpr int BATCH = 4;         // rounds per queue access; their loads are issued together
   if (a.nfix <= 0) return;
-  const int gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwarps = gridDim.x * (blockDim.x >> 5);
-  const unsigned head_total = a.head_share ? (unsigned)nwarps * (unsigned)(CW * BATCH) : 0u;
-  if (HEAD && (!a.head_share || gwarp * CW >= a.nfix)) return;
-  if (!HEAD && head_total >= (unsigned)a.nfix) return;
   const int lane_t = threadIdx.x & 31;
   const bool lane_live = lane_t < CW * NF;
   const int grp = lane_live ? lane_t / NF : 0;          // (idle lanes shadow group 0 and never store)
   const int node = lane_live ? lane_t - grp * NF : 0;
   const int ix = node / N1, iy = node % N1;
   const int gbase = grp * NF;
-  for (int pass = 0;; ++pass) {
-    int t0s[BATCH];  // first record of each round of this batch
-    if (HEAD) {
-      if (pass > 0) break;
-#pragma unroll
-      for (int rd = 0; rd < BATCH; ++rd) t0s[rd] = (gwarp + rd * nwarps) * CW;
-    } else {
-      unsigned base = 0;
-      if (lane_t == 0) base = atomicAdd(a.tail_ctr, (unsigned)(CW * BATCH));
-      base = __shfl_sync(0xffffffffu, base, 0) + head_total;
-      if (base >= (unsigned)a.nfix) break;
-#pragma unroll
-      for (int rd = 0; rd < BATCH; ++rd) t0s[rd] = (int)base + rd * CW;
-    }
+  for (;;) {
+    unsigned base = 0;
+    if (lane_t == 0) base = atomicAdd(a.tail_ctr, (unsigned)(CW * BATCH));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= (unsigned)a.nfix) break;
     // ---- all loads of the batch first (two dependent levels: record, then dofs) ----
     int2 rec[BATCH];
     double T[BATCH], Qx[BATCH], Qy[BATCH], nxT[BATCH], nxQ[BATCH], nyT[BATCH], nyQ[BATCH];
 #pragma unroll
-    for (int rd = 0; rd < BATCH; ++rd) rec[rd] = a.fix[min(t0s[rd] + grp, a.nfix - 1)];
+    for (int rd = 0; rd < BATCH; ++rd) rec[rd] = a.fix[min((int)base + rd * CW + grp, a.nfix - 1)];
 #pragma unroll
     for (int rd = 0; rd < BATCH; ++rd) {
-      T[rd] = Qx[rd] = Qy[rd] = nxT[rd] = nxQ[rd] = nyT[rd] = nyQ[rd] = 0.0;
-      if (t0s[rd] >= a.nfix) continue;  // (warp-uniform; the head's later rounds are usually empty)
       const int64_t cell = rec[rd].x;
       const int code = rec[rd].y;
       const int i = (int)(cell / a.ny), j = (int)(cell - (int64_t)i * a.ny);
@@ -159,7 +141,7 @@ __device__ __forceinline__ void ldg_fixup_tail(const LdgTab<P>& tab, const LdgMa
     }
 #pragma unroll
     for (int rd = 0; rd < BATCH; ++rd) {
-      const int t0 = t0s[rd];
+      const int t0 = (int)base + rd * CW;
       if (t0 < a.nfix) {  // (warp-uniform)
         const bool live = lane_live && (t0 + grp) < a.nfix;
         const int code = rec[rd].y;
@@ -373,8 +355,6 @@ ldg_apply_march(const __grid_constant__ LdgTab<P> tab, const LdgMarchArgs a, con
     // prologue: columns c0-1 .. c0+NST-2 into slots 0 .. NST-1
 #pragma unroll
     for (int k = 0; k < NST; ++k) issue(c0 - 1 + k, ring + k * C::STAGE, bars + 8 * k);
-    // while they are in flight: this warp's static share of the exception cells
-    ldg_fixup_tail<P, true>(tab, a);
     double U[CD];
     double tLT[N1], tLQ[N1];  // left neighbour: T and q_x at its ix = P nodes
     {
@@ -529,7 +509,6 @@ ldg_apply_march(const __grid_constant__ LdgTab<P> tab, const LdgMarchArgs a, con
     ldg_dbg_stamp(a, 2);
   }
   ldg_griddep_wait();  // (warps without a strip have not waited yet)
-  if (!(strip < nstrips && c0 < c1)) ldg_fixup_tail<P, true>(tab, a);  // (... nor taken their head share)
   ldg_fixup_tail<P>(tab, a);
   if (a.dbg_times != nullptr) {
     __syncthreads();
