@@ -19,7 +19,14 @@ Pins (see `tests/test_oracle_golden.py`):
   * the reference's own `@test`s for DG1D (symmetry, rate > 1.95, p=2 error
     < 1e6 eps, Robin flux residual < 1e3 eps)
   * the FD known-answer matrix of `StefanFD/test-linear-heat-equation.jl`
-PARITY UNPINNED for: cut-cell / merged-cell configurations, the mesh-aligned 2-D
+  * the cut-cell studies the reference stores (`tests/test_cutcell_cpu.py`; block
+    oracles `oracle/blocks.py`, `oracle/ldg_blocks.py` on data from the product's
+    host-side generators): `plane_interface_tests` IP and LDG p = 2 to 3-4 digits
+    (both geometries exact), `curved_interface_tests` and the cylinder studies at
+    discretisation level (exact circle against a Q2-interpolated level set);
+    `oracle/ldg_blocks.py` itself is pinned on uniform meshes against `oracle/fast.py`
+PARITY UNPINNED for: digit-level cut-cell results on curved interfaces (the
+reference's geometry lives in un-vendored packages), the mesh-aligned 2-D
 two-phase extension (face-level functions are the reference's, the driver loop is
 ours), and time stepping (no reference implementation exists).
 """

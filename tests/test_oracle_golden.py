@@ -72,7 +72,7 @@ def test_ip_current_is_symmetric_and_reproduces_constants_and_linears(p):
     assert e < 1e-10
 
 
-def ldg_errors(n, p, nq, pens=(0.0, 0.0, 0.0, 1.0)):
+def ldg_errors(n, p, nq, pens=(0.0, 0.0, 0.0, 1.0), exact=exact, source=source, exact_grad=exact_grad):
     basis = LagrangeTensorProductBasis(2, p)
     mesh = UniformMesh2D([0, 0], [1, 1], [n, n], basis.nf)
     cq, fq = CellQuadratures(nq), FaceQuadratures(nq)
@@ -85,6 +85,17 @@ def ldg_errors(n, p, nq, pens=(0.0, 0.0, 0.0, 1.0)):
     eT = mesh_L2_error(sol[0:1], exact, basis, cq, mesh)[0]
     eG = mesh_L2_error(sol[1:3], exact_grad, basis, cq, mesh)
     return eT / integral_norm_on_mesh(exact, cq, mesh, 1)[0], eG[0], eG[1]
+
+
+@pytest.mark.parametrize("p,nq", [(1, 2), (2, 5)])
+def test_ldg_uncut_reproduces_constants_and_linears(p, nq):
+    """uncut_mesh_tests/constant_solution_LDG_convergence.csv and linear_solution_LDG_convergence.csv (errors at
+    round-off level, 2e-16 ... 9e-16 relative): T = 3 x + 4 y and T = 1 with their gradients."""
+    eT, g1, g2 = ldg_errors(5, p, nq, exact=lambda v: 3 * v[0] + 4 * v[1], source=lambda v: 0.0,
+                            exact_grad=lambda v: np.array([3.0, 4.0]))
+    assert eT < 1e-13 and g1 < 1e-12 and g2 < 1e-12
+    eT, g1, g2 = ldg_errors(5, p, nq, exact=lambda v: 1.0, source=lambda v: 0.0, exact_grad=lambda v: np.zeros(2))
+    assert eT < 1e-13 and g1 < 1e-12 and g2 < 1e-12
 
 
 @pytest.mark.parametrize("row", [0, 1, 2, 3, 4])
