@@ -11,11 +11,12 @@ the straight line through (0.8, 0) with normal at 60 degrees ("plane") or by the
 except posboundarypenalty = 1, V0 at 45 degrees, numqp = required_quadrature_order(p) (p = 1) / + 2 (p = 2), relative L2
 error of T and absolute L2 errors of the two flux components.
 
-The geometry comes from stefanproblem_b200.cutcell (PlaneCutMesh: exact polygons; CircleCutMesh: exact circle), tiny
-pieces merged below 0.2 of a cell (the ratio that reproduces CutCellDG.MergedMesh!'s results).  For the straight
-interface both this generator and the reference integrate the polynomial integrands exactly, so the stored CSVs are
-reproduced almost digit for digit where the quadrature is exact (IP: within 0.2 % at every n; LDG p = 2: within 0.06 %);
-LDG p = 1 uses a 2-point rule that is NOT exact on cut pieces, there the two rule constructions differ (15-30 %).
+The geometry comes from stefanproblem_b200.cutcell (PlaneCutMesh: exact half-planes; CircleCutMesh: exact circle;
+height-function Gauss rules as in the reference's quadrature package), tiny pieces merged below 0.2 of a cell (the ratio
+that reproduces CutCellDG.MergedMesh!'s results).  For the straight interface this generator and the reference describe
+the same geometry, so the stored CSVs are reproduced almost digit for digit (IP: within 0.4 % at every n; LDG p = 2:
+within 0.06 %, seven digits at n = 33; LDG p = 1, which the reference runs with a 2-point rule that is not exact on cut
+pieces: within 0.1 %, because the rule construction is the same).
 
     python examples/cut_interface_convergence.py [plane|curved] [ip|ldg]
 """

@@ -275,7 +275,7 @@ def _manufactured(kind, method, n, order):
 # |this / CSV - 1| allowed per (kind, method, order); observed over n = 3 ... 17 in the comment
 CUT_STUDY_TOL = {
     ("plane", "ip", 1): 0.006, ("plane", "ip", 2): 0.002,        # 0.9958 ... 1.0018, 0.9996 ... 1.0008
-    ("plane", "ldg", 2): 0.001,                                   # 0.9994 ... 1.0002 in all three columns
+    ("plane", "ldg", 1): 0.003, ("plane", "ldg", 2): 0.001,      # 0.9988 ... 1.0011 (2-point rule), 0.9994 ... 1.0002
     ("curved", "ip", 1): 0.04, ("curved", "ip", 2): 0.015,      # 1.004 ... 1.032, 0.989 ... 1.004
     ("curved", "ldg", 2): 0.005,                                  # 0.9962 ... 1.0008
 }
@@ -334,7 +334,8 @@ def test_plane_interface_linear_solution_is_reproduced_to_rounding(method):
 
 
 def test_polygon_rules_are_exact():
-    from stefanproblem_b200.cutcell import plane_edge_rules, plane_rect_rules, plane_segment_rule, polygon_rule
+    from stefanproblem_b200.cutcell import (plane_edge_rules, plane_rect_rules, plane_rect_rules_polygon,
+                                           plane_segment_rule, polygon_rule)
     poly = np.array([[0, 0], [1, 0], [1.2, 0.7], [0.4, 1.1], [-0.2, 0.5]], float)
     P, W = polygon_rule(poly, 4)
     P2, W2 = polygon_rule(poly, 12)
@@ -345,6 +346,10 @@ def test_polygon_rules_are_exact():
     n, c = np.array([np.cos(1.0), np.sin(1.0)]), 0.45
     (pp, wp), (pm, wm) = plane_rect_rules(0.1, 0.6, 0.2, 0.9, n, c, 3)
     assert abs(wp.sum() + wm.sum() - 0.5 * 0.7) < 1e-14 and (pp @ n - c > 0).all() and (pm @ n - c < 0).all()
+    # the height-function rule against the triangulated polygons: same integrals of a polynomial both integrate exactly
+    (qp, vp), (qm, vm) = plane_rect_rules_polygon(0.1, 0.6, 0.2, 0.9, n, c, 4)
+    mono = lambda p: p[:, 0] ** 2 * p[:, 1] ** 2 + p[:, 0] ** 3  # noqa: E731
+    assert abs((wp * mono(pp)).sum() - (vp * mono(qp)).sum()) < 1e-14 and abs((wm * mono(pm)).sum() - (vm * mono(qm)).sum()) < 1e-14
     (ep, ewp), (em, ewm) = plane_edge_rules((0.1, 0.2), (0.6, 0.2), n, c, 3)
     assert abs(ewp.sum() + ewm.sum() - 0.5) < 1e-14
     sp_, sw, sn = plane_segment_rule(0.1, 0.6, 0.2, 0.9, n, c, 3)

@@ -191,7 +191,7 @@ def test_cut_interface_convergence_studies_on_the_gpu(cuda, kind, method):
     nelmts, table = mod.main(kind, method)
     gold = GOLD[f"{method}_{kind}"]
     assert [g[0] for g in gold] == nelmts
-    tol = {("plane", "ip", 1): 0.006, ("plane", "ip", 2): 0.003, ("plane", "ldg", 2): 0.001,
+    tol = {("plane", "ip", 1): 0.006, ("plane", "ip", 2): 0.003, ("plane", "ldg", 1): 0.003, ("plane", "ldg", 2): 0.001,
            ("curved", "ip", 1): 0.04, ("curved", "ip", 2): 0.015, ("curved", "ldg", 2): 0.005}
     nc = 1 if method == "ip" else 3
     for order in (1, 2):
