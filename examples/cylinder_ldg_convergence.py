@@ -5,7 +5,7 @@ r = 0.5 around the origin, phase +1 (k1, q1) inside, exact solution (cylinder-an
 on the whole boundary, penalties interior = interface = negboundary = 0, posboundary = 1, V0 at 45 degrees,
 numqp = required_quadrature_order(p) + 2.  What changes against the Julia script:
     CutCellDG.CutMesh / CellQuadratures / FaceQuadratures / InterfaceQuadratures / MergedMesh!
-                                    ->  stefanproblem_b200.cutcell.CircleCutMesh
+                                    ->  stefanproblem_b200.cutcell.LevelSetCutMesh
     LocalDG.assemble_LDG_linear_system!   ->  stefan_ldgblocks_assemble (element-local assembly on the device)
     LocalDG.assemble_LDG_rhs! + assemble_two_phase_source!  ->  stefan_ldgblocks_rhs
     matrix \\ rhs                     ->  stefan_ldgblocks_solve (Schur complement on T, BiCGStab on the device), or with
@@ -13,9 +13,9 @@ numqp = required_quadrature_order(p) + 2.  What changes against the Julia script
                                         (the reference's own step)
     mesh_L2_error / integral_norm_on_mesh -> stefan_blocks_l2_error per component (T against the exact solution, the
                                         flux variable against its gradient, as :163-171 does)
-The stored CSV comes from a Q2-interpolated level set; this generator cuts with the exact circle: the p = 1 columns
-agree to about 1 %, the p = 2 temperature to a few percent from n = 5 on, the p = 2 gradient errors here are SMALLER
-(0.4 ... 0.85 of the CSV: the interpolated interface limits the reference's gradient accuracy).
+Geometry: stefanproblem_b200.cutcell.LevelSetCutMesh, the Q2 interpolant of circle_distance_function with
+height-function Gauss rules (the reference's construction).  The stored CSV is reproduced to 6 digits in all six
+columns at n = 3, 9, 17, 33 and to 1e-3 at n = 5 (one merging decision).
 
     python examples/cylinder_ldg_convergence.py [coo]
 """
@@ -51,11 +51,12 @@ def exact_solution(prm):
 def measure_error(nelmts, solverorder, prm=PRM, merge_fraction=0.2, solver="schur"):
     import torch
     from stefanproblem_b200 import blocks as B
-    from stefanproblem_b200.cutcell import CircleCutMesh
+    from stefanproblem_b200.cutcell import LevelSetCutMesh
     numqp = solverorder + 1 + 2
     V0 = (np.cos(np.radians(prm["theta"])), np.sin(np.radians(prm["theta"])))
-    mesh = CircleCutMesh([0.0, 0.0], [1.0, 1.0], [nelmts, nelmts], [0.0, 0.0], prm["R"], numqp, prm["k1"], prm["k2"],
-                         0.0, 0.0, merge_fraction=merge_fraction)
+    # the reference's geometry: Q2 interpolant of circle_distance_function (levelsetorder = 2)
+    mesh = LevelSetCutMesh([0.0, 0.0], [1.0, 1.0], [nelmts, nelmts], lambda x, y: prm["R"] - np.hypot(x, y), 2, numqp,
+                           prm["k1"], prm["k2"], 0.0, 0.0, merge_fraction=merge_fraction)
     data = dict(mesh.data)
     data["slot_pen"] = B.ldg_slot_penalties(data, V0, prm["interiorpenalty"], prm["interfacepenalty"],
                                             prm["negboundarypenalty"], prm["posboundarypenalty"], mesh.slot_is_interface)

@@ -359,6 +359,11 @@ typedef struct stefan_blocks stefan_blocks;
 int stefan_blocks_create(const stefan_blocks_dims* dims, stefan_blocks** out);
 int stefan_blocks_destroy(stefan_blocks* h);
 int64_t stefan_blocks_ndofs(const stefan_blocks* h);
+/* Boundary form used by stefan_blocks_assemble / stefan_blocks_rhs: 0 = current (boundary block -(M + M') + pen P,
+ * rhs pen sum V g w - sum k (G.n) g w; IP_flux_operator.jl:330-357, IP_source_term.jl:131-159), 1 = the legacy
+ * boundary form (-M' + pen P, rhs pen sum V g w) that the reference's stored cut-cell CSVs of the interior-penalty
+ * method were produced with (as stefan_ipdg_params.variant).  Call before stefan_blocks_assemble. */
+int stefan_blocks_set_variant(stefan_blocks* h, int32_t variant);
 /* fills the blocks [ncells][1 + nslots][NF][NF] (diag, then one per slot) */
 int stefan_blocks_assemble(stefan_blocks* h, const stefan_blocks_data* data, void* stream);
 /* y = A x with the assembled blocks; 16 + 8 (1 + nslots) NF bytes of HBM traffic per dof */

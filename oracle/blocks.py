@@ -11,7 +11,7 @@ from . import ip
 from .basis import LagrangeTensorProductBasis
 
 
-def assemble_blocks(order, data):
+def assemble_blocks(order, data, variant="current"):
     """data: dict of NumPy arrays shaped like stefan_blocks_data.  Returns blocks
     [ncells][1 + nslots][NF][NF] (diag, then one per slot; zeros for empty slots)."""
     basis = LagrangeTensorProductBasis(2, order)
@@ -36,7 +36,8 @@ def assemble_blocks(order, data):
             P11 = ip.mass_operator(basis, q1, q1, ones)
             if nbr == -1:
                 M = ip.flux_operator(basis, q1, q1, normals, k1, jac1, ones)
-                out[c, 0] += -(M + M.T) + pen * P11
+                # (`legacy_boundary`: -M' only, oracle/ip.assemble_boundary_face_flux_operator)
+                out[c, 0] += (-(M + M.T) if variant == "current" else -M.T) + pen * P11
                 continue
             q2 = list(zip(data["face_nbr_pts"][c, s][keep], w))
             jac2, k2 = data["cell_jac"][nbr], data["cell_k"][nbr]
@@ -61,7 +62,7 @@ def dense_matrix(blocks, slot_nbr):
     return A
 
 
-def assemble_rhs(order, data, f_qp, g_qp, Tm=0.0):
+def assemble_rhs(order, data, f_qp, g_qp, Tm=0.0, variant="current"):
     """Right-hand side for block data, from the reference's linear forms applied per solution cell:
     volume source `linear_form` (IP_source_term.jl:97-107), boundary slots `R1 - R2` =
     pen * linear_form - flux_linear_form (IP_source_term.jl:109-159), slots with a Robin coefficient
@@ -88,7 +89,8 @@ def assemble_rhs(order, data, f_qp, g_qp, Tm=0.0):
                     q1 = [(p, wq)]
                     g = lambda _p, gq=gq: gq  # noqa: E731
                     rhs[c] += pen * ip.linear_form(g, basis, q1, ident, 1.0)
-                    rhs[c] -= ip.flux_linear_form(g, basis, q1, n, k, ident, jac, 1.0)
+                    if variant == "current":   # (`legacy_boundary`: R1 only, oracle/ip.assemble_boundary_face_source)
+                        rhs[c] -= ip.flux_linear_form(g, basis, q1, n, k, ident, jac, 1.0)
             elif nbr >= 0 and data["slot_lambda"][c, s] != 0.0:
                 quad = list(zip(pts, w))
                 rhs[c] += 0.5 * data["slot_lambda"][c, s] * Tm * ip.robin_interface_linear_form(

@@ -135,6 +135,7 @@ _SIGNATURES = {
     "stefan_blocks_create": (ctypes.c_int, [ctypes.POINTER(BlocksDims), ctypes.POINTER(ctypes.c_void_p)]),
     "stefan_blocks_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "stefan_blocks_ndofs": (ctypes.c_int64, [ctypes.c_void_p]),
+    "stefan_blocks_set_variant": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
     "stefan_blocks_assemble": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(BlocksData), ctypes.c_void_p]),
     "stefan_blocks_apply": (ctypes.c_int, [ctypes.c_void_p] * 4),
     "stefan_blocks_coo_size": (ctypes.c_int64, [ctypes.c_void_p]),

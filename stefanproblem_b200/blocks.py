@@ -20,7 +20,8 @@ _FIELDS = ("vol_pts", "vol_wts", "cell_jac", "cell_k", "slot_nbr", "face_pts", "
 class BlockSystem:
     """Assembled dense element blocks on one GPU: `assemble(data)`, `A @ x`, `to_coo()`."""
 
-    def __init__(self, ncells, order, nqv, nslots, nqf):
+    def __init__(self, ncells, order, nqv, nslots, nqf, variant="current"):
+        """variant: "current" or "legacy_boundary" (the boundary form of the reference's stored cut-cell CSVs)."""
         import torch
         if not torch.cuda.is_available():
             raise _lib.StefanError(-1, "no CUDA device: stefanproblem_b200 has no CPU fallback")
@@ -30,6 +31,7 @@ class BlockSystem:
         self._h = h
         self.ndofs = int(_lib.lib().stefan_blocks_ndofs(h))
         self.shape = (self.ndofs, self.ndofs)
+        _lib.check(_lib.lib().stefan_blocks_set_variant(h, {"current": 0, "legacy_boundary": 1}[variant]))
 
     def __del__(self):
         h = getattr(self, "_h", None)

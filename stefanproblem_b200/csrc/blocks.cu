@@ -51,7 +51,7 @@ struct AsmSmem {
 
 template <int P>
 __global__ void __launch_bounds__(kAsmWarps * 32)
-blocks_assemble_kernel(const stefan_blocks_dims d, const stefan_blocks_data in, double* __restrict__ blocks) {
+blocks_assemble_kernel(const stefan_blocks_dims d, const stefan_blocks_data in, int legacy, double* __restrict__ blocks) {
   constexpr int NF = (P + 1) * (P + 1);
   constexpr int MAXQ = AsmSmem<P>::MAXQ;
   extern __shared__ double asm_smem[];
@@ -142,8 +142,8 @@ blocks_assemble_kernel(const stefan_blocks_dims d, const stefan_blocks_data in, 
                   const double v2b = T2[q * NF + b], gn2b = T3[q * NF + b];
                   osum += (0.5 * k1 * gn1a * v2b - 0.5 * k2 * gn2b * v1a + (lam4 - pen) * v1a * v2b) * wq;
                 } else {
-                  // boundary: -(M + M') + pen P, M[a][b] = k1 gn1a v1b
-                  dsum += (-k1 * (gn1a * v1b + gn1b * v1a) + pen * v1a * v1b) * wq;
+                  // boundary: -(M + M') + pen P, M[a][b] = k1 gn1a v1b; legacy boundary form: -M' + pen P
+                  dsum += (-k1 * ((legacy ? 0.0 : gn1a * v1b) + gn1b * v1a) + pen * v1a * v1b) * wq;
                 }
               }
               acc[e] += dsum;
@@ -249,6 +249,7 @@ int stefan_blocks_create(const stefan_blocks_dims* dims, stefan_blocks** out) {
   h->blocks = nullptr;
   h->slot_nbr = nullptr;
   h->assembled = false;
+  h->variant = 0;
   const size_t nbytes = (size_t)dims->ncells * (1 + dims->nslots) * h->nf * h->nf * sizeof(double);
   cudaError_t e = cudaMalloc(&h->blocks, nbytes);
   if (e == cudaSuccess) e = cudaMalloc(&h->slot_nbr, (size_t)dims->ncells * dims->nslots * sizeof(int32_t));
@@ -270,6 +271,15 @@ int stefan_blocks_destroy(stefan_blocks* hv) {
   return ST_OK;
 }
 
+int stefan_blocks_set_variant(stefan_blocks* hv, int32_t variant) {
+  BlocksHandle* h = reinterpret_cast<BlocksHandle*>(hv);
+  STEFAN_REQUIRE(h, "stefan_blocks_set_variant: null handle");
+  STEFAN_REQUIRE(variant == 0 || variant == 1, "stefan_blocks_set_variant: variant must be 0 (current) or 1 (legacy_boundary)");
+  h->variant = variant;
+  h->assembled = false;
+  return ST_OK;
+}
+
 int64_t stefan_blocks_ndofs(const stefan_blocks* hv) {
   const BlocksHandle* h = reinterpret_cast<const BlocksHandle*>(hv);
   return h ? (int64_t)h->d.ncells * h->nf : -1;
@@ -288,21 +298,21 @@ int stefan_blocks_assemble(stefan_blocks* hv, const stefan_blocks_data* in, void
   switch (h->d.order) {
     case 1: {
       constexpr int smem = kAsmWarps * AsmSmem<1>::WARP_DOUBLES * 8;
-      blocks_assemble_kernel<1><<<blocks, kAsmWarps * 32, smem, st>>>(h->d, *in, h->blocks);
+      blocks_assemble_kernel<1><<<blocks, kAsmWarps * 32, smem, st>>>(h->d, *in, h->variant, h->blocks);
       break;
     }
     case 2: {
       constexpr int smem = kAsmWarps * AsmSmem<2>::WARP_DOUBLES * 8;
       static PerDeviceFlag set2;
       if (!set2.here()) { STEFAN_CUDA(cudaFuncSetAttribute(blocks_assemble_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set2.here() = true; }
-      blocks_assemble_kernel<2><<<blocks, kAsmWarps * 32, smem, st>>>(h->d, *in, h->blocks);
+      blocks_assemble_kernel<2><<<blocks, kAsmWarps * 32, smem, st>>>(h->d, *in, h->variant, h->blocks);
       break;
     }
     case 3: {
       constexpr int smem = kAsmWarps * AsmSmem<3>::WARP_DOUBLES * 8;
       static PerDeviceFlag set3;
       if (!set3.here()) { STEFAN_CUDA(cudaFuncSetAttribute(blocks_assemble_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set3.here() = true; }
-      blocks_assemble_kernel<3><<<blocks, kAsmWarps * 32, smem, st>>>(h->d, *in, h->blocks);
+      blocks_assemble_kernel<3><<<blocks, kAsmWarps * 32, smem, st>>>(h->d, *in, h->variant, h->blocks);
       break;
     }
   }

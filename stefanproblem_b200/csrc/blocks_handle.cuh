@@ -14,6 +14,7 @@ struct BlocksHandle {
   double* blocks;       // [ncells][1 + nslots][nf][nf], row-major (row = test function)
   int32_t* slot_nbr;    // [ncells][nslots] copy of the adjacency (apply needs it)
   bool assembled;
+  int variant;          // 0 current, 1 legacy boundary form (stefan_blocks_set_variant)
 };
 
 // 1-D Lagrange basis on order+1 equispaced nodes of [-1, 1]: value and derivative of N_i at x

@@ -22,7 +22,7 @@ namespace stefan {
 template <int P>
 __global__ void __launch_bounds__(128)
 blocks_rhs_kernel(const stefan_blocks_dims d, const stefan_blocks_data in, const double* __restrict__ f_qp,
-                  const double* __restrict__ g_qp, double Tm, double* __restrict__ rhs) {
+                  const double* __restrict__ g_qp, double Tm, int legacy, double* __restrict__ rhs) {
   constexpr int NF = (P + 1) * (P + 1);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   for (int cell = blockIdx.x * wpb + warp; cell < d.ncells; cell += gridDim.x * wpb) {
@@ -51,7 +51,7 @@ blocks_rhs_kernel(const stefan_blocks_dims d, const stefan_blocks_data in, const
             double v, gx, gy;
             basis_vg<P>(a, in.face_pts[2 * fq], in.face_pts[2 * fq + 1], jx, jy, v, gx, gy);
             const double gn = gx * in.face_normals[2 * fq] + gy * in.face_normals[2 * fq + 1];
-            acc += (pen * v - k * gn) * g_qp[fq] * w;   // R1 - R2 (IP_source_term.jl:131-159)
+            acc += (pen * v - (legacy ? 0.0 : k * gn)) * g_qp[fq] * w;   // R1 - R2 (IP_source_term.jl:131-159); legacy: R1
           }
         } else if (nbr >= 0 && lam != 0.0 && Tm != 0.0) {
           for (int q = 0; q < d.nqf; ++q) {
@@ -183,9 +183,9 @@ int stefan_blocks_rhs(stefan_blocks* hv, const stefan_blocks_data* in, const dou
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int blocks = (int)std::min<int64_t>(((int64_t)h->d.ncells + 3) / 4, (int64_t)sm_count() * 16);
   switch (h->d.order) {
-    case 1: blocks_rhs_kernel<1><<<blocks, 128, 0, st>>>(h->d, *in, f_qp, g_qp, Tm, rhs); break;
-    case 2: blocks_rhs_kernel<2><<<blocks, 128, 0, st>>>(h->d, *in, f_qp, g_qp, Tm, rhs); break;
-    case 3: blocks_rhs_kernel<3><<<blocks, 128, 0, st>>>(h->d, *in, f_qp, g_qp, Tm, rhs); break;
+    case 1: blocks_rhs_kernel<1><<<blocks, 128, 0, st>>>(h->d, *in, f_qp, g_qp, Tm, h->variant, rhs); break;
+    case 2: blocks_rhs_kernel<2><<<blocks, 128, 0, st>>>(h->d, *in, f_qp, g_qp, Tm, h->variant, rhs); break;
+    case 3: blocks_rhs_kernel<3><<<blocks, 128, 0, st>>>(h->d, *in, f_qp, g_qp, Tm, h->variant, rhs); break;
   }
   STEFAN_CUDA(cudaGetLastError());
   return ST_OK;

@@ -403,6 +403,8 @@ class CircleCutMesh:
                     nb = (ii * ny + jj, s)
                     if nb not in pieces or pieces[nb]["area"] < self.merge_fraction * area:
                         continue
+                    # (across the longest shared face: of all single-piece alternatives this is the choice that
+                    # reproduces the reference's stored results, e.g. plane_interface_tests n = 5)
                     ln = pc["faces"][f][1].sum()
                     if ln > best_len:
                         best, best_len = (nb, f), ln
@@ -559,3 +561,191 @@ class PlaneCutMesh(CircleCutMesh):
 
     def _interface_rule(self, xa, xb, ya, yb):
         return plane_segment_rule(xa, xb, ya, yb, self.n, self.c, self.nqf1)
+
+
+# ------------------------------------------------------------------- interpolated level set (the reference's geometry)
+def _real_roots_in(coeffs_low_to_high, lo=-1.0, hi=1.0, tol=1e-12):
+    """Real roots in (lo, hi) of the polynomial sum c_i t^i (degree <= 4 here)."""
+    c = np.array(coeffs_low_to_high, float)
+    scale = np.abs(c).max()
+    if scale == 0.0:
+        return []
+    c = c / scale
+    while len(c) > 1 and abs(c[-1]) < 1e-14:
+        c = c[:-1]
+    if len(c) <= 1:
+        return []
+    r = np.roots(c[::-1])
+    out = sorted(float(z.real) for z in r if abs(z.imag) < 1e-10 and lo + tol < z.real < hi - tol)
+    dedup = []
+    for z in out:
+        if not dedup or z - dedup[-1] > tol:
+            dedup.append(z)
+    return dedup
+
+
+class LevelSetCutMesh(CircleCutMesh):
+    """The same data for an INTERPOLATED level set: phi_h = the continuous piecewise-Q_m nodal interpolant (m =
+    `levelset_order`, the reference uses 2) of `distance_function(x, y)` on the mesh of the cells, exactly what
+    `CutCellDG.LevelSet(distancefunction, cgmesh, levelsetbasis)` is in the reference's drivers.  Phase +1 where
+    phi_h > 0.  In a cell phi_h is a polynomial, so every geometric quantity is in closed form: along a line of the
+    height direction (the coordinate with the larger |d phi_h| at the cell centre) phi_h is a polynomial of degree m
+    whose roots split the line into + and - pieces; the outer Gauss rule is split where a root enters / leaves through
+    the cell's faces or two roots merge.  Interface points: the roots at the outer Gauss points, weights = arc length
+    elements, normals = -grad phi_h / |grad phi_h| (out of the + side)."""
+
+    def __init__(self, x0, widths, nelements, distance_function, levelset_order, numqp, k1, k2, penalty, lam=0.0,
+                 merge_fraction=0.0, face_numqp=None):
+        m = int(levelset_order)
+        nx, ny = int(nelements[0]), int(nelements[1])
+        xs = np.asarray(x0, float)[0] + np.asarray(widths, float)[0] * np.arange(m * nx + 1) / (m * nx)
+        ys = np.asarray(x0, float)[1] + np.asarray(widths, float)[1] * np.arange(m * ny + 1) / (m * ny)
+        X, Y = np.meshgrid(xs, ys, indexing="ij")
+        self.m = m
+        self.phi_nodes = np.asarray(distance_function(X, Y), float)
+        nodes = -1.0 + 2.0 * np.arange(m + 1) / m
+        self._to_monomial = np.linalg.inv(np.vander(nodes, increasing=True))   # nodal values -> monomial coefficients
+        super().__init__(x0, widths, nelements, (0.0, 0.0), 1.0, numqp, k1, k2, penalty, lam, merge_fraction, face_numqp)
+
+    # monomial coefficients P[i][j] of xi^i eta^j of phi_h in cell (i, j)
+    def _poly(self, ci, cj):
+        m = self.m
+        C = self.phi_nodes[m * ci:m * ci + m + 1, m * cj:m * cj + m + 1]
+        return self._to_monomial @ C @ self._to_monomial.T
+
+    def _cell_index(self, x, y):
+        ci = int(np.clip(np.floor((x - self.x0[0]) / self.h[0]), 0, self.nx - 1))
+        cj = int(np.clip(np.floor((y - self.x0[1]) / self.h[1]), 0, self.ny - 1))
+        return ci, cj
+
+    @staticmethod
+    def _eval(P, t, s):
+        m1 = P.shape[0]
+        return float((t ** np.arange(m1)) @ P @ (s ** np.arange(m1)))
+
+    def _oriented(self, xa, xb, ya, yb):
+        """(P with the height variable second, swapped?, half widths (outer, height), centre (outer, height))"""
+        ci, cj = self._cell_index(0.5 * (xa + xb), 0.5 * (ya + yb))
+        P = self._poly(ci, cj)
+        gx = P[1, 0] * 2.0 / self.h[0]      # d phi / dx and d phi / dy at the cell centre
+        gy = P[0, 1] * 2.0 / self.h[1]
+        swap = abs(gx) > abs(gy)            # height direction x: exchange the roles
+        if swap:
+            return P.T.copy(), True, (0.5 * self.h[1], 0.5 * self.h[0]), (0.5 * (ya + yb), 0.5 * (xa + xb))
+        return P, False, (0.5 * self.h[0], 0.5 * self.h[1]), (0.5 * (xa + xb), 0.5 * (ya + yb))
+
+    @staticmethod
+    def _line_poly(P, t):
+        """coefficients (low to high) in s of phi(t, s)"""
+        return (t ** np.arange(P.shape[0])) @ P
+
+    def _breakpoints(self, P):
+        """outer values in (-1, 1) where the root structure along the height lines changes"""
+        m1 = P.shape[0]
+        cuts = [-1.0, 1.0]
+        for s in (-1.0, 1.0):
+            cuts += _real_roots_in(P @ (s ** np.arange(m1)))          # a root passes through the bottom / top face
+        if m1 == 3:
+            # two roots merge where the discriminant q1^2 - 4 q2 q0 of the quadratic in s vanishes (degree 4 in t)
+            q0, q1, q2 = P[:, 0], P[:, 1], P[:, 2]
+            disc = np.polynomial.polynomial.polysub(np.polynomial.polynomial.polymul(q1, q1),
+                                                    4.0 * np.polynomial.polynomial.polymul(q2, q0))
+            cuts += _real_roots_in(disc)
+        return sorted(set(cuts))
+
+    def _region_rules(self, xa, xb, ya, yb):
+        P, swap, (ht, hs), (ct, cs) = self._oriented(xa, xb, ya, yb)
+        g, w = _gauss(self.nq)
+        lists = {True: ([], []), False: ([], [])}
+        cuts = self._breakpoints(P)
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            if b - a <= 1e-12:
+                continue
+            for t, wt in zip(0.5 * (a + b) + 0.5 * (b - a) * g, 0.5 * (b - a) * w):
+                q = self._line_poly(P, t)
+                ends = [-1.0] + _real_roots_in(q) + [1.0]
+                for sa, sb in zip(ends[:-1], ends[1:]):
+                    if sb - sa <= 1e-13:
+                        continue
+                    plus = np.polynomial.polynomial.polyval(0.5 * (sa + sb), q) > 0
+                    sq = 0.5 * (sa + sb) + 0.5 * (sb - sa) * g
+                    pts = np.stack([np.full(self.nq, ct + ht * t), cs + hs * sq], 1)
+                    lists[plus][0].append(pts[:, ::-1] if swap else pts)
+                    lists[plus][1].append(0.5 * (sb - sa) * w * wt * ht * hs)
+
+        def pack(lp, lw):
+            if not lp:
+                return np.zeros((0, 2)), np.zeros(0)
+            return np.concatenate(lp), np.concatenate(lw)
+        return pack(*lists[True]), pack(*lists[False])
+
+    def _edge_rules(self, p0, p1):
+        p0, p1 = np.asarray(p0, float), np.asarray(p1, float)
+        mid = 0.5 * (p0 + p1)
+        horizontal = abs(p1[1] - p0[1]) < abs(p1[0] - p0[0])
+        # a cell that has the edge on its boundary (phi_h is continuous: either neighbour gives the same restriction)
+        eps = 1e-9 * self.h
+        ci, cj = self._cell_index(mid[0] + (0.0 if horizontal else -eps[0]), mid[1] + (-eps[1] if horizontal else 0.0))
+        if (not horizontal and mid[0] - eps[0] < self.x0[0]) or (horizontal and mid[1] - eps[1] < self.x0[1]):
+            ci, cj = self._cell_index(mid[0], mid[1])
+        P = self._poly(ci, cj)
+        m1 = P.shape[0]
+        xc = self.x0[0] + (ci + 0.5) * self.h[0]
+        yc = self.x0[1] + (cj + 0.5) * self.h[1]
+        if horizontal:
+            eta = (mid[1] - yc) / (0.5 * self.h[1])
+            q = P @ (eta ** np.arange(m1))              # polynomial in xi
+            lo, hi = sorted(((p0[0] - xc) / (0.5 * self.h[0]), (p1[0] - xc) / (0.5 * self.h[0])))
+            half = 0.5 * self.h[0]
+        else:
+            xi = (mid[0] - xc) / (0.5 * self.h[0])
+            q = (xi ** np.arange(m1)) @ P               # polynomial in eta
+            lo, hi = sorted(((p0[1] - yc) / (0.5 * self.h[1]), (p1[1] - yc) / (0.5 * self.h[1])))
+            half = 0.5 * self.h[1]
+        g, w = _gauss(self.nqf1)
+        ends = [lo] + _real_roots_in(q, lo, hi) + [hi]
+        lists = {True: ([], []), False: ([], [])}
+        for a, b in zip(ends[:-1], ends[1:]):
+            if b - a <= 1e-13:
+                continue
+            plus = np.polynomial.polynomial.polyval(0.5 * (a + b), q) > 0
+            r = 0.5 * (a + b) + 0.5 * (b - a) * g
+            if horizontal:
+                pts = np.stack([xc + half * r, np.full(self.nqf1, mid[1])], 1)
+            else:
+                pts = np.stack([np.full(self.nqf1, mid[0]), yc + half * r], 1)
+            lists[plus][0].append(pts)
+            lists[plus][1].append(0.5 * (b - a) * w * half)
+
+        def pack(lp, lw):
+            if not lp:
+                return np.zeros((0, 2)), np.zeros(0)
+            return np.concatenate(lp), np.concatenate(lw)
+        return pack(*lists[True]), pack(*lists[False])
+
+    def _interface_rule(self, xa, xb, ya, yb):
+        P, swap, (ht, hs), (ct, cs) = self._oriented(xa, xb, ya, yb)
+        m1 = P.shape[0]
+        g, w = _gauss(self.nqf1)
+        pw = np.arange(m1)
+        PT, WT, NT = [], [], []
+        cuts = self._breakpoints(P)
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            if b - a <= 1e-12:
+                continue
+            for t, wt in zip(0.5 * (a + b) + 0.5 * (b - a) * g, 0.5 * (b - a) * w):
+                for s in _real_roots_in(self._line_poly(P, t)):
+                    tp, sp_ = t ** pw, s ** pw
+                    dt = float((pw[1:] * t ** pw[:-1]) @ P[1:, :] @ sp_) / ht      # d phi / d(physical outer)
+                    ds = float(tp @ P[:, 1:] @ (pw[1:] * s ** pw[:-1])) / hs      # d phi / d(physical height)
+                    if ds == 0.0:
+                        continue
+                    nrm = np.hypot(dt, ds)
+                    pt = np.array([ct + ht * t, cs + hs * s])
+                    nv = -np.array([dt, ds]) / nrm
+                    PT.append(pt[::-1] if swap else pt)
+                    NT.append(nv[::-1] if swap else nv)
+                    WT.append(wt * ht * nrm / abs(ds))     # arc length element: |grad phi| / |d phi / d height| d(outer)
+        if not PT:
+            return np.zeros((0, 2)), np.zeros(0), np.zeros((0, 2))
+        return np.array(PT), np.array(WT), np.array(NT)

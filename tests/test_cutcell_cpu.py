@@ -11,7 +11,7 @@ import scipy.sparse.linalg as spla
 
 from oracle import blocks as ob
 from oracle.analytical import CylindricalSolver, RobinCylindricalSolver
-from stefanproblem_b200.cutcell import CircleCutMesh, arc_rule, disk_rect_rules, edge_rules
+from stefanproblem_b200.cutcell import CircleCutMesh, LevelSetCutMesh, arc_rule, disk_rect_rules, edge_rules
 
 GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_csv.json")))
 
@@ -93,35 +93,50 @@ def test_cut_mesh_geometry_is_consistent(merge):
         assert m.nsol < len(m.pieces) and (area > 0.2 * (1.0 / n) ** 2).all()   # no tiny solution cell is left
 
 
-def _study(n, order, prm, merge=0.2):
+def _study(n, order, prm, merge=0.2, geometry="levelset"):
     sol = (RobinCylindricalSolver(prm["q1"], prm["k1"], prm["q2"], prm["k2"], prm["lam"], prm["R"], prm["b"], prm["Tw"], prm["Tm"])
            if prm["lam"] else CylindricalSolver(prm["q1"], prm["k1"], prm["q2"], prm["k2"], prm["R"], prm["b"], prm["Tw"]))
-    m = CircleCutMesh([0, 0], [1, 1], [n, n], [0, 0], prm["R"], prm["numqp"][order], prm["k1"], prm["k2"], 1e3 * n, prm["lam"],
-                      merge_fraction=merge)
-    A = sp.csr_matrix(ob.dense_matrix(ob.assemble_blocks(order, m.data), m.data["slot_nbr"]))
-    assert abs(A - A.T).max() <= 1e-12 * abs(A).max()          # `@assert issymmetric(matrix)` of the drivers
+    if geometry == "exact":
+        m = CircleCutMesh([0, 0], [1, 1], [n, n], [0, 0], prm["R"], prm["numqp"][order], prm["k1"], prm["k2"], 1e3 * n,
+                          prm["lam"], merge_fraction=merge)
+    else:
+        m = LevelSetCutMesh([0, 0], [1, 1], [n, n], lambda x, y: prm["R"] - np.hypot(x, y), 2, prm["numqp"][order],
+                            prm["k1"], prm["k2"], 1e3 * n, prm["lam"], merge_fraction=merge)
+    variant = prm.get("variant", "current")
+    A = sp.csr_matrix(ob.dense_matrix(ob.assemble_blocks(order, m.data, variant), m.data["slot_nbr"]))
+    if variant == "current":
+        assert abs(A - A.T).max() <= 1e-12 * abs(A).max()          # `@assert issymmetric(matrix)` of the drivers
     rhs = ob.assemble_rhs(order, m.data, m.sample_source(lambda x, y: prm["q1"] + 0 * x, lambda x, y: prm["q2"] + 0 * x),
-                          m.sample_boundary(sol.at), prm["Tm"])
+                          m.sample_boundary(sol.at), prm["Tm"], variant)
     u = spla.spsolve(A.tocsc(), rhs)
     e, den = ob.l2_error(order, m.data, u, m.sample_exact(sol.at))
     return e / den
 
 
-PLAIN = dict(k1=1.0, k2=2.0, q1=1.0, q2=2.0, lam=0.0, Tm=0.0, R=0.5, b=1.5, Tw=1.0, numqp={1: 2, 2: 5})
+# (the stored plain-cylinder file was produced with the legacy boundary form -- SURVEY N4 --, the Robin one with the
+# current form)
+PLAIN = dict(k1=1.0, k2=2.0, q1=1.0, q2=2.0, lam=0.0, Tm=0.0, R=0.5, b=1.5, Tw=1.0, numqp={1: 2, 2: 5},
+             variant="legacy_boundary")
 ROBIN = dict(k1=1.0, k2=2.0, q1=2.0, q2=1.0, lam=1.0, Tm=0.5, R=0.7, b=1.5, Tw=1.0, numqp={1: 4, 2: 5})
+# |this / CSV - 1| allowed per (study, order); observed over n = 3 ... 17 in the comment
+CYL_TOL = {("ip_cylinder", 1): 0.02, ("ip_cylinder", 2): 1e-5,               # 2.4e-3 ... 1.3e-2 (2-point rule), 1e-8 ... 2e-6
+           ("ip_cylinder_robin", 1): 1e-7, ("ip_cylinder_robin", 2): 1e-6}   # 2e-11 ... 2e-9, 8e-10 ... 1.4e-7
 
 
 @pytest.mark.parametrize("name,prm", [("ip_cylinder", PLAIN), ("ip_cylinder_robin", ROBIN)])
 def test_cylinder_study_small_meshes_against_the_reference_csv(name, prm):
-    """n = 3, 5, 9 of the reference's cut-cell cylinder studies with the oracle's block assembly on the generator's
-    data.  Discretisation-level parity: the stored CSVs come from a Q2-interpolated level set and other quadrature
-    rules, this generator from the exact circle.  Observed ratio this / CSV over all 20 entries of the two studies
-    (n = 3 ... 33, p = 1, 2): 0.73 ... 1.08, within 4 % from n = 9 on except Robin p = 2 (0.91); asserted 0.7 ... 1.12."""
+    """n = 3, 5, 9 of the reference's cut-cell cylinder studies with the oracle's block assembly on the data of
+    `LevelSetCutMesh` -- the Q2 interpolant of circle_distance_function with height-function Gauss rules, i.e. the
+    reference's own geometry restated.  Wherever the quadrature is exact for the integrands the stored CSVs come back
+    to 6-10 digits; plain p = 1 runs with a 2-point rule that is not exact on cut cells (within 1.3 %).  With the
+    analytic circle instead (`geometry="exact"`) every entry is within 0.73 ... 1.08 of the CSV."""
     for row in GOLD[name][:3]:
         n = row[0]
         for order, want in ((1, row[1]), (2, row[2])):
             got = _study(n, order, prm)
-            assert 0.7 * want < got < 1.12 * want, (name, n, order, got, want)
+            assert abs(got / want - 1.0) <= CYL_TOL[name, order], (name, n, order, got, want)
+    got = _study(5, 2, dict(prm, variant="current"), geometry="exact")
+    assert 0.7 * GOLD[name][1][2] < got < 1.12 * GOLD[name][1][2]
 
 
 def test_distance_functions_restated():
@@ -189,7 +204,8 @@ def _ldg_cylinder(n, order, merge=0.2, exact=None, k2=2.0, q=(1.0, 2.0), numqp=N
     from stefanproblem_b200.blocks import ldg_slot_penalties
     V0 = (np.cos(np.pi / 4), np.sin(np.pi / 4))
     sol = CylindricalSolver(q[0], 1.0, q[1], k2, 0.5, 1.5, 1.0)
-    m = CircleCutMesh([0, 0], [1, 1], [n, n], [0, 0], 0.5, numqp or order + 3, 1.0, k2, 0.0, 0.0, merge_fraction=merge)
+    m = LevelSetCutMesh([0, 0], [1, 1], [n, n], lambda x, y: 0.5 - np.hypot(x, y), 2, numqp or order + 3, 1.0, k2, 0.0, 0.0,
+                        merge_fraction=merge)
     data = dict(m.data)
     data["slot_pen"] = ldg_slot_penalties(data, V0, 0.0, 0.0, 0.0, 1.0, m.slot_is_interface)
     A = sp.csc_matrix(olb.dense_matrix(olb.assemble_blocks(order, data, V0), data["slot_nbr"]))
@@ -213,21 +229,16 @@ def _ldg_cylinder(n, order, merge=0.2, exact=None, k2=2.0, q=(1.0, 2.0), numqp=N
 
 def test_ldg_cylinder_study_small_meshes_against_the_reference_csv():
     """n = 3, 5, 9 of cylindrical_bc_tests/LDG_test_cylindrical_bc_convergence.jl with the oracle's local-DG block
-    assembly on the generator's data, against the stored LDG_convergence.csv (relative L2 errors of T and of the two
-    flux components).  Observed ratio this / CSV: p = 1 0.99 ... 1.01 in all three columns; p = 2 temperature 0.97 / 0.99
-    at n = 5 / 9 (0.41 at n = 3); p = 2 flux components 0.14 ... 0.84 -- the exact circle beats the CSV's Q2-interpolated
-    interface there."""
+    assembly on `LevelSetCutMesh` data, against the stored LDG_convergence.csv (relative L2 errors of T and of the two
+    flux components): all six columns to 1e-6 at n = 3 and n = 9 (observed 1e-9 ... 9e-7; n = 17, 33 likewise), to 2e-3
+    at n = 5 (observed 3e-5 ... 1.3e-3: one merging decision at that size differs from CutCellDG's)."""
     for row in GOLD["ldg_cylinder"][:3]:
         n = row[0]
         for order in (1, 2):
             got = [e / den for e, den in _ldg_cylinder(n, order)]
             want = row[1 + 3 * (order - 1):4 + 3 * (order - 1)]
-            if order == 1:
-                for gv, wv in zip(got, want):
-                    assert 0.95 * wv < gv < 1.05 * wv, (n, order, got, want)
-            else:
-                assert (0.9 if n >= 5 else 0.3) * want[0] < got[0] < 1.1 * want[0], (n, got, want)
-                assert got[1] < 1.05 * want[1] and got[2] < 1.05 * want[2], (n, got, want)
+            for gv, wv in zip(got, want):
+                assert abs(gv / wv - 1.0) <= (2e-3 if n == 5 else 2e-6), (n, order, got, want)
 
 
 @pytest.mark.parametrize("order", [1, 2])
@@ -256,10 +267,12 @@ def _manufactured(kind, method, n, order):
     spec.loader.exec_module(ex)
     if method == "ip":
         m = ex.make_mesh(kind, n, order + 3, 1e3 * n)
-        A = sp.csc_matrix(ob.dense_matrix(ob.assemble_blocks(order, m.data), m.data["slot_nbr"]))
-        assert abs(A - A.T).max() <= 1e-12 * abs(A).max()
+        var = ex.IP_VARIANT[kind]
+        A = sp.csc_matrix(ob.dense_matrix(ob.assemble_blocks(order, m.data, var), m.data["slot_nbr"]))
+        if var == "current":
+            assert abs(A - A.T).max() <= 1e-12 * abs(A).max()
         u = spla.spsolve(A, ob.assemble_rhs(order, m.data, m.sample_source(ex.source, ex.source),
-                                            m.sample_boundary(ex.exact), 0.0))
+                                            m.sample_boundary(ex.exact), 0.0, var))
         return [ob.l2_error(order, m.data, u, m.sample_exact(ex.exact))[0]]
     V0 = (np.cos(np.pi / 4), np.sin(np.pi / 4))
     m = ex.make_mesh(kind, n, 2 if order == 1 else order + 3, 0.0)
@@ -272,12 +285,13 @@ def _manufactured(kind, method, n, order):
             ob.l2_error(order, data, u[2::3], m.sample_exact(ex.grad_y))[0]]
 
 
-# |this / CSV - 1| allowed per (kind, method, order); observed over n = 3 ... 17 in the comment
+# |this / CSV - 1| allowed per (kind, method, order) at n = 3, 9 (and 17, 33) / at n = 5, where one merging decision of
+# CutCellDG's is not reproduced; observed values in the comments.  None: only the order of magnitude is asserted.
 CUT_STUDY_TOL = {
-    ("plane", "ip", 1): 0.006, ("plane", "ip", 2): 0.002,        # 0.9958 ... 1.0018, 0.9996 ... 1.0008
-    ("plane", "ldg", 1): 0.003, ("plane", "ldg", 2): 0.001,      # 0.9988 ... 1.0011 (2-point rule), 0.9994 ... 1.0002
-    ("curved", "ip", 1): 0.04, ("curved", "ip", 2): 0.015,      # 1.004 ... 1.032, 0.989 ... 1.004
-    ("curved", "ldg", 2): 0.005,                                  # 0.9962 ... 1.0008
+    ("plane", "ip", 1): (1e-7, 6e-3), ("plane", "ip", 2): (1e-7, 2e-4),      # 7e-15, 1.3e-8 / 4.7e-3; 3e-13, 6e-9 / 1.1e-4
+    ("plane", "ldg", 1): (2e-3, 2e-3), ("plane", "ldg", 2): (1e-7, 5e-4),    # 3e-15, 1.3e-3 (2-point rule) / 1.1e-3; 2e-14, 2e-9 / 2.9e-4
+    ("curved", "ip", 1): (0.02, 0.04), ("curved", "ip", 2): (5e-3, 0.015),  # 1.1e-2, 3.8e-3 / 3.5e-2; 3.3e-3, 3.1e-3 / 1.1e-2
+    ("curved", "ldg", 1): None, ("curved", "ldg", 2): (1e-5, 1e-5),          # (2-point rule on curved pieces); 6e-6, 9e-9 / 1e-6
 }
 
 
@@ -285,23 +299,24 @@ CUT_STUDY_TOL = {
 @pytest.mark.parametrize("method", ["ip", "ldg"])
 def test_cut_interface_studies_small_meshes_against_the_reference_csvs(kind, method):
     """n = 3, 5, 9 of the reference's plane_interface_tests / curved_interface_tests studies (IP and local DG) with the
-    oracle's block assembly on the generator's data against the stored CSVs.  Where the quadrature is exact for the
-    polynomial integrands (everything but LDG p = 1, which the reference runs with a 2-point rule) the CSVs are
-    reproduced to 3-4 digits -- the straight interface is represented exactly by both geometries, and at these
-    resolutions the circle nearly so.  LDG p = 1: the 2-point rules on the cut pieces are construction dependent
-    (observed 0.87 ... 2.2 of the CSV); only its order of magnitude is asserted."""
+    oracle's block assembly on the generators' data (PlaneCutMesh; LevelSetCutMesh = the reference's Q2 level set)
+    against the stored CSVs.  Wherever the quadrature is exact for the polynomial integrands the CSVs come back to 8-15
+    digits (IP plane with the legacy boundary form it was produced with; LDG p = 2 for both interfaces); LDG p = 1 plane
+    runs with a 2-point rule that is not exact on cut pieces and still agrees to 1e-3 because the rule construction is
+    the reference's.  Not pinned that closely: IP curved (1-3 %: the stored file predates the current code in a way
+    neither boundary form recovers) and LDG p = 1 curved (2-point rule on curved pieces: 0.86 ... 1.8 of the CSV)."""
     nc = 1 if method == "ip" else 3
     for row in GOLD[f"{method}_{kind}"][:3]:
         n = row[0]
         for order in (1, 2):
             got = _manufactured(kind, method, n, order)
             want = row[1 + nc * (order - 1):1 + nc * order]
-            tol = CUT_STUDY_TOL.get((kind, method, order))
+            tol = CUT_STUDY_TOL[kind, method, order]
             for gv, wv in zip(got, want):
                 if tol is None:
                     assert 0.5 * wv < gv < 3.0 * wv, (kind, method, n, order, got, want)
                 else:
-                    assert abs(gv / wv - 1.0) <= tol, (kind, method, n, order, got, want)
+                    assert abs(gv / wv - 1.0) <= tol[1 if n == 5 else 0], (kind, method, n, order, got, want)
 
 
 @pytest.mark.parametrize("method", ["ip", "ldg"])
@@ -362,3 +377,40 @@ def test_polygon_rules_are_exact():
         (q, wq), _ = plane_edge_rules(p0, p1, n, c, 3)
         flux += (wq * (q @ np.array(nn, float))).sum()
     assert abs(flux - 2 * wp.sum()) < 1e-13
+
+
+def test_level_set_generator_on_a_plane_equals_the_plane_generator():
+    """LevelSetCutMesh (Q2 interpolant, roots of the cell polynomials) fed plane_distance_function must produce the data
+    of PlaneCutMesh (closed-form half-planes): same solution cells, adjacency, volume rules and face weights / normals
+    (the points of a face slot may come in the opposite order)."""
+    from stefanproblem_b200.cutcell import PlaneCutMesh
+    nrm = np.array([np.cos(np.pi / 3), np.sin(np.pi / 3)])
+    for n in (3, 5):
+        a = PlaneCutMesh([0, 0], [1, 1], [n, n], nrm, [0.8, 0.0], 4, 1.0, 1.0, 1e3 * n, 0.0, merge_fraction=0.2)
+        b = LevelSetCutMesh([0, 0], [1, 1], [n, n], lambda x, y: (x - 0.8) * nrm[0] + y * nrm[1], 2, 4, 1.0, 1.0, 1e3 * n,
+                            0.0, merge_fraction=0.2)
+        assert (a.nsol, a.nslots, a.nqv, a.nqf) == (b.nsol, b.nslots, b.nqv, b.nqf)
+        assert np.array_equal(a.data["slot_nbr"], b.data["slot_nbr"])
+        for key in ("vol_pts", "vol_wts", "face_normals"):
+            assert np.abs(a.data[key] - b.data[key]).max() < 1e-13, key
+        assert np.abs(np.sort(a.data["face_wts"], axis=-1) - np.sort(b.data["face_wts"], axis=-1)).max() < 1e-14
+
+
+def test_level_set_generator_circle_geometry():
+    """Area, interface length and the divergence theorem on the + region for the Q2-interpolated circle (the
+    interpolation error of the geometry is 3e-8 relative at n = 9)."""
+    m = LevelSetCutMesh([0, 0], [1, 1], [9, 9], lambda x, y: 0.5 - np.hypot(x, y), 2, 5, 1.0, 2.0, 9e3, 0.0, merge_fraction=0.2)
+    detj = 0.25 * m.h[0] * m.h[1]
+    inside = (m.data["vol_wts"][m.sol_phase == 1] * detj).sum()
+    assert abs(inside - np.pi * 0.25 / 4) < 1e-7
+    assert abs(m.data["face_wts"][m.slot_is_interface].sum() / 2 - np.pi * 0.5 / 2) < 1e-5
+    # sum over the + solution cells of the boundary integrals of x . n: interior faces cancel, what is left is
+    # 2 |region| = domain boundary part + interface part
+    flux = 0.0
+    for sol in np.nonzero(m.sol_phase == 1)[0]:
+        for s in range(m.nslots):
+            if m.data["slot_nbr"][sol, s] < -1:
+                continue
+            w = m.data["face_wts"][sol, s]
+            flux += (w * np.einsum("qd,qd->q", m.face_xy[sol, s], m.data["face_normals"][sol, s])).sum()
+    assert abs(flux - 2 * inside) < 1e-7

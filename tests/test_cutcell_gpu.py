@@ -61,12 +61,43 @@ def test_cut_cell_blocks_rhs_and_norm_match_oracle(cuda, order, numqp, lam, merg
         assert np.linalg.norm(x.cpu().numpy() - x_ref) <= 1e-7 * np.linalg.norm(x_ref)
 
 
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_blocks_legacy_boundary_variant_matches_oracle(cuda, order):
+    """stefan_blocks_set_variant(1): boundary blocks -M' + pen P and boundary right-hand side pen sum V g w (the form the
+    reference's stored cut-cell IP files were produced with), on interpolated-level-set data, against the oracle."""
+    from stefanproblem_b200 import blocks as B
+    from stefanproblem_b200.cutcell import LevelSetCutMesh
+    n = 5
+    m = LevelSetCutMesh([0, 0], [1, 1], [n, n], lambda x, y: 0.55 - np.hypot(x, y), 2, order + 3, 1.0, 2.0, 1e3 * n, 0.0,
+                        merge_fraction=0.2)
+    ref = ob.assemble_blocks(order, m.data, "legacy_boundary")
+    system = B.BlockSystem(m.nsol, order, m.nqv, m.nslots, m.nqf, variant="legacy_boundary").assemble(m.data)
+    nf = (order + 1) ** 2
+    got = system.to_coo()[2].cpu().numpy().reshape(m.nsol, 1 + m.nslots, nf, nf)
+    live = np.concatenate([np.ones((m.nsol, 1), bool), m.data["slot_nbr"] >= 0], axis=1)
+    assert np.abs(got[live] - ref[live]).max() <= 1e-12 * np.abs(ref).max()
+    assert np.abs(ref - ob.assemble_blocks(order, m.data)).max() > 1e-3 * np.abs(ref).max()   # (the variants differ)
+    f = m.sample_source(lambda x, y: 1.0 + x * y, lambda x, y: 2.0 - x + 0 * y)
+    g = m.sample_boundary(lambda x, y: np.cos(x) + y)
+    b_ref = ob.assemble_rhs(order, m.data, f, g, 0.0, "legacy_boundary")
+    assert np.linalg.norm(system.rhs(f, g, 0.0).cpu().numpy() - b_ref) <= 1e-12 * np.linalg.norm(b_ref)
+
+
+def _gpu_tol(tight, n, loose_n5=6e-3):
+    """GPU studies end with an iterative solve (or a host solve of device-assembled triplets): the digit-level pins live
+    in tests/test_cutcell_cpu.py; here the same numbers to 2e-4 (n = 5: one merging decision differs, n = 33: solver
+    accuracy against discretisation errors of 1e-8)."""
+    if tight is None:
+        return None
+    return max(tight, loose_n5 if n == 5 else (2e-3 if n == 33 else 2e-4))
+
+
 @pytest.mark.parametrize("robin", [False, True])
 def test_cylinder_convergence_study_on_the_gpu(cuda, robin):
     """IP_test_cylindrical_bc_convergence.jl / IP_test_cylndrical_robin_bc_convergence.jl, n = 3 ... 33, p = 1, 2,
-    end to end on the device (cut-cell data -> blocks -> rhs -> CG -> L2 error).  Acceptance as in the reference's
-    test_IP_convergence.jl:125,156 (mean rate > 1.8 / > 2.8) and errors within 0.7 ... 1.12 of the stored CSV
-    (discretisation-level parity, see tests/test_cutcell_cpu.py)."""
+    end to end on the device (cut-cell data of the reference's Q2 level set -> blocks -> rhs -> CG or triplets + host
+    solve -> L2 error).  Acceptance as in the reference's test_IP_convergence.jl:125,156 (mean rate > 1.8 / > 2.8) and
+    the stored CSVs: Robin study and plain p = 2 to 2e-4 (CPU oracle: 1e-6 ... 1e-10), plain p = 1 (2-point rule) to 2 %."""
     mod = _example()
     nelmts, table = mod.main(robin=robin)
     gold = GOLD["ip_cylinder_robin" if robin else "ip_cylinder"]
@@ -75,7 +106,8 @@ def test_cylinder_convergence_study_on_the_gpu(cuda, robin):
         err, rate = table[order]
         assert np.mean(rate[1:]) > bar, (order, rate)
         for e, g in zip(err, gold):
-            assert 0.7 * g[col] < e < 1.12 * g[col], (order, g[0], e, g[col])
+            tol = 0.02 if (not robin and order == 1) else _gpu_tol(1e-6, g[0])
+            assert abs(e / g[col] - 1.0) <= tol, (order, g[0], e, g[col])
 
 
 # ----------------------------------------------------------------- local DG on element blocks (stefan_ldgblocks_*)
@@ -158,10 +190,9 @@ def test_ldg_blocks_on_a_uniform_mesh_equal_the_matrix_free_ldg_operator(cuda):
 
 def test_ldg_cylinder_convergence_study_on_the_gpu(cuda):
     """cylindrical_bc_tests/LDG_test_cylindrical_bc_convergence.jl, n = 3 ... 33, p = 1, 2, end to end on the device
-    (cut-cell data -> local-DG blocks -> rhs -> Schur BiCGStab -> component L2 errors) against the stored
-    LDG_convergence.csv: p = 1 within 5 % in all three columns, p = 2 temperature within 10 % from n = 5 on, p = 2 flux
-    errors at or below the CSV's up to n = 17 (the exact circle against its Q2 level set) and within 8 % at n = 33, rates
-    as the CSV's."""
+    (cut-cell data of the reference's Q2 level set -> local-DG blocks -> rhs -> Schur BiCGStab -> component L2 errors)
+    against the stored LDG_convergence.csv: all six columns to 2e-4 (n = 5: 6e-3, n = 33: 2e-3; the CPU oracle pins the
+    same numbers to 2e-6), rates as the CSV's."""
     spec = importlib.util.spec_from_file_location("cyl_ldg", os.path.join(ROOT, "examples", "cylinder_ldg_convergence.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
@@ -172,33 +203,32 @@ def test_ldg_cylinder_convergence_study_on_the_gpu(cuda):
     err2, rate2 = table[2]
     for e1, e2, g in zip(err1, err2, gold):
         for col in range(3):
-            assert 0.95 * g[1 + col] < e1[col] < 1.05 * g[1 + col], (1, g[0], col, e1, g)
-        assert (0.9 if g[0] >= 5 else 0.3) * g[4] < e2[0] < 1.1 * g[4], (2, g[0], e2, g)
-        assert e2[1] < 1.15 * g[5] and e2[2] < 1.15 * g[6], (2, g[0], e2, g)   # (observed: 0.14 ... 1.08)
-    assert np.mean(rate1[1:, 0]) > 1.7 and np.mean(rate1[1:, 1:]) > 1.2   # CSV: 1.8 (T), 1.3 (flux)
-    assert np.mean(rate2[1:, 0]) > 2.6 and np.mean(rate2[1:, 1:]) > 2.0   # CSV: 2.8 (T), 2.4 (flux)
+            assert abs(e1[col] / g[1 + col] - 1.0) <= _gpu_tol(2e-6, g[0]), (1, g[0], col, e1, g)
+            assert abs(e2[col] / g[4 + col] - 1.0) <= _gpu_tol(2e-6, g[0]), (2, g[0], col, e2, g)
+    assert np.mean(rate1[1:, 0]) > 1.7 and np.mean(rate1[1:, 1:]) > 1.2   # CSV: 1.95 (T), 1.45 (flux)
+    assert np.mean(rate2[1:, 0]) > 2.6 and np.mean(rate2[1:, 1:]) > 2.0   # CSV: 2.98 (T), 2.66 (flux)
 
 
 @pytest.mark.parametrize("kind", ["plane", "curved"])
 @pytest.mark.parametrize("method", ["ip", "ldg"])
 def test_cut_interface_convergence_studies_on_the_gpu(cuda, kind, method):
     """plane_interface_tests / curved_interface_tests of the reference (IP and local DG, p = 1, 2, n = 3 ... 33) end to
-    end on the device against the stored CSVs.  Tolerances as in tests/test_cutcell_cpu.py (3-4 digits wherever the
-    quadrature is exact; the finest circular meshes a little looser: IP curved n = 33)."""
+    end on the device against the stored CSVs: 2e-4 wherever tests/test_cutcell_cpu.py pins the same numbers to 1e-7
+    (IP plane, LDG p = 2 plane and curved), percent level for IP curved and LDG p = 1 (see there)."""
     spec = importlib.util.spec_from_file_location("cut_ex", os.path.join(ROOT, "examples", "cut_interface_convergence.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     nelmts, table = mod.main(kind, method)
     gold = GOLD[f"{method}_{kind}"]
     assert [g[0] for g in gold] == nelmts
-    tol = {("plane", "ip", 1): 0.006, ("plane", "ip", 2): 0.003, ("plane", "ldg", 1): 0.003, ("plane", "ldg", 2): 0.001,
-           ("curved", "ip", 1): 0.04, ("curved", "ip", 2): 0.015, ("curved", "ldg", 2): 0.005}
+    tight = {("plane", "ip", 1): 1e-7, ("plane", "ip", 2): 1e-7, ("plane", "ldg", 1): 2e-3, ("plane", "ldg", 2): 1e-7,
+             ("curved", "ip", 1): 0.04, ("curved", "ip", 2): 0.015, ("curved", "ldg", 1): None, ("curved", "ldg", 2): 1e-5}
     nc = 1 if method == "ip" else 3
     for order in (1, 2):
         err, rate = table[order]
         for e, g in zip(err, gold):
             want = g[1 + nc * (order - 1):1 + nc * order]
-            t = tol.get((kind, method, order))
+            t = _gpu_tol(tight[kind, method, order], g[0])
             for ev, wv in zip(e, want):
                 if t is None:
                     assert 0.4 * wv < ev < 3.0 * wv, (kind, method, order, g[0], e, want)
