@@ -14,11 +14,11 @@ error of T and absolute L2 errors of the two flux components.
 The geometry comes from stefanproblem_b200.cutcell: PlaneCutMesh (exact half-planes) and LevelSetCutMesh (the Q2
 interpolant of circle_distance_function, i.e. the reference's own level set), height-function Gauss rules as in the
 reference's quadrature package, tiny pieces merged below 0.2 of a cell (the ratio that reproduces
-CutCellDG.MergedMesh!'s results).  The stored CSVs come back almost digit for digit: IP plane (legacy boundary form,
-SURVEY N4) to 6 digits at n = 3, 9, 17, 33; LDG p = 2 to 5-7 digits for both interfaces; LDG p = 1 plane (2-point rule,
-not exact on cut pieces, so the rule CONSTRUCTION has to agree) within 0.1 %.  Not reproduced that closely: n = 5 of
-the plane studies (0.5 %: a merging decision), IP curved (1-3 %: the stored file predates the current code in some way
-neither boundary form recovers), LDG p = 1 curved (the 2-point rule on curved pieces).
+CutCellDG.MergedMesh!'s results).  The stored CSVs come back almost digit for digit: IP plane and IP curved (legacy
+boundary form; the curved file with a level set of order 1) to 8-15 digits at n = 3, 9, 17, 33; LDG p = 2 to
+5-7 digits for both interfaces; LDG p = 1 plane (2-point rule, not exact on cut pieces, so the rule CONSTRUCTION has to
+agree) within 0.1 %; LDG p = 1 curved to 5e-6 with the 4-point rule its stored columns were produced with.  Not
+reproduced that closely: n = 5 of the plane studies (0.5 %).
 
     python examples/cut_interface_convergence.py [plane|curved] [ip|ldg]
 """
@@ -48,20 +48,25 @@ def grad_y(x, y):
     return 2 * np.pi * np.cos(2 * np.pi * x) * np.cos(2 * np.pi * y)
 
 
-# boundary form of the interior-penalty studies: the stored plane-interface CSV is reproduced digit for digit by the
-# legacy boundary form (as the uncut IP CSV); the curved-interface CSV by neither (within 1-3 % of both)
-IP_VARIANT = {"plane": "legacy_boundary", "curved": "current"}
+# What the stored interior-penalty files were produced with (inferred: these settings reproduce them to 8-15 digits,
+# the scripts' present settings do not): the legacy boundary form (as the uncut IP CSV) and, for the
+# curved-interface file, a level set of order 1 (the script now says levelsetorder = 2 and no longer writes the CSV).
+IP_VARIANT = {"plane": "legacy_boundary", "curved": "legacy_boundary"}
+IP_LEVELSET_ORDER = 1
+# quadrature orders of the local-DG studies: required_quadrature_order(p) for p = 1 and + 2 for p = 2 in the scripts; the
+# stored curved-interface file has its p = 1 columns from the + 2 rule (4 points reproduce them to 5e-6, 2 points do not)
+LDG_NUMQP = {"plane": {1: 2, 2: 5}, "curved": {1: 4, 2: 5}}
 
 
-def make_mesh(kind, nelmts, numqp, penalty):
+def make_mesh(kind, nelmts, numqp, penalty, levelset_order=2):
     from stefanproblem_b200.cutcell import LevelSetCutMesh, PlaneCutMesh
     if kind == "plane":
         normal = (np.cos(np.radians(60.0)), np.sin(np.radians(60.0)))
         return PlaneCutMesh([0.0, 0.0], [1.0, 1.0], [nelmts, nelmts], normal, [0.8, 0.0], numqp, 1.0, 1.0, penalty, 0.0,
                             merge_fraction=MERGE)
-    # levelsetorder = 2: the Q2 interpolant of circle_distance_function, as the reference's drivers build it
-    return LevelSetCutMesh([0.0, 0.0], [1.0, 1.0], [nelmts, nelmts], lambda x, y: 0.5 - np.hypot(x - 1.0, y - 1.0), 2,
-                           numqp, 1.0, 1.0, penalty, 0.0, merge_fraction=MERGE)
+    # the nodal interpolant of circle_distance_function on the mesh, as the reference's drivers build it
+    return LevelSetCutMesh([0.0, 0.0], [1.0, 1.0], [nelmts, nelmts], lambda x, y: 0.5 - np.hypot(x - 1.0, y - 1.0),
+                           levelset_order, numqp, 1.0, 1.0, penalty, 0.0, merge_fraction=MERGE)
 
 
 def _host_solve(system, rhs):
@@ -76,7 +81,7 @@ def _host_solve(system, rhs):
 def measure_ip(kind, nelmts, order):
     """[absolute L2 error], solver iterations"""
     from stefanproblem_b200 import blocks as B
-    mesh = make_mesh(kind, nelmts, order + 3, 1e3 * nelmts)
+    mesh = make_mesh(kind, nelmts, order + 3, 1e3 * nelmts, IP_LEVELSET_ORDER)
     system = B.BlockSystem(mesh.nsol, order, mesh.nqv, mesh.nslots, mesh.nqf, variant=IP_VARIANT[kind]).assemble(mesh.data)
     rhs = system.rhs(mesh.sample_source(source, source), mesh.sample_boundary(exact), 0.0)
     if IP_VARIANT[kind] == "current":
@@ -93,7 +98,7 @@ def measure_ldg(kind, nelmts, order):
     """[relative L2 error of T, absolute L2 errors of the flux components], solver iterations"""
     from stefanproblem_b200 import blocks as B
     V0 = (np.cos(np.radians(45.0)), np.sin(np.radians(45.0)))
-    mesh = make_mesh(kind, nelmts, 2 if order == 1 else order + 3, 0.0)
+    mesh = make_mesh(kind, nelmts, LDG_NUMQP[kind][order], 0.0)
     data = dict(mesh.data)
     data["slot_pen"] = B.ldg_slot_penalties(data, V0, 0.0, 0.0, 0.0, 1.0, mesh.slot_is_interface)
     system = B.LDGBlockSystem(mesh.nsol, order, mesh.nqv, mesh.nslots, mesh.nqf).assemble(data, V0)

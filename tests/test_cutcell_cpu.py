@@ -266,7 +266,7 @@ def _manufactured(kind, method, n, order):
     ex = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(ex)
     if method == "ip":
-        m = ex.make_mesh(kind, n, order + 3, 1e3 * n)
+        m = ex.make_mesh(kind, n, order + 3, 1e3 * n, ex.IP_LEVELSET_ORDER)
         var = ex.IP_VARIANT[kind]
         A = sp.csc_matrix(ob.dense_matrix(ob.assemble_blocks(order, m.data, var), m.data["slot_nbr"]))
         if var == "current":
@@ -275,7 +275,7 @@ def _manufactured(kind, method, n, order):
                                             m.sample_boundary(ex.exact), 0.0, var))
         return [ob.l2_error(order, m.data, u, m.sample_exact(ex.exact))[0]]
     V0 = (np.cos(np.pi / 4), np.sin(np.pi / 4))
-    m = ex.make_mesh(kind, n, 2 if order == 1 else order + 3, 0.0)
+    m = ex.make_mesh(kind, n, ex.LDG_NUMQP[kind][order], 0.0)
     data = dict(m.data)
     data["slot_pen"] = ldg_slot_penalties(data, V0, 0.0, 0.0, 0.0, 1.0, m.slot_is_interface)
     A = sp.csc_matrix(olb.dense_matrix(olb.assemble_blocks(order, data, V0), data["slot_nbr"]))
@@ -290,8 +290,8 @@ def _manufactured(kind, method, n, order):
 CUT_STUDY_TOL = {
     ("plane", "ip", 1): (1e-7, 6e-3), ("plane", "ip", 2): (1e-7, 2e-4),      # 7e-15, 1.3e-8 / 4.7e-3; 3e-13, 6e-9 / 1.1e-4
     ("plane", "ldg", 1): (2e-3, 2e-3), ("plane", "ldg", 2): (1e-7, 5e-4),    # 3e-15, 1.3e-3 (2-point rule) / 1.1e-3; 2e-14, 2e-9 / 2.9e-4
-    ("curved", "ip", 1): (0.02, 0.04), ("curved", "ip", 2): (5e-3, 0.015),  # 1.1e-2, 3.8e-3 / 3.5e-2; 3.3e-3, 3.1e-3 / 1.1e-2
-    ("curved", "ldg", 1): None, ("curved", "ldg", 2): (1e-5, 1e-5),          # (2-point rule on curved pieces); 6e-6, 9e-9 / 1e-6
+    ("curved", "ip", 1): (5e-5, 5e-6), ("curved", "ip", 2): (5e-5, 5e-6),    # 1.5e-5, 5e-9 / 4e-7; 1.1e-5, 4e-9 / 4e-8 (level set of order 1)
+    ("curved", "ldg", 1): (3e-5, 3e-5), ("curved", "ldg", 2): (1e-5, 1e-5),  # 1e-5, 3e-8 / 2.5e-6 (4-point rule); 6e-6, 9e-9 / 1e-6
 }
 
 
@@ -303,8 +303,10 @@ def test_cut_interface_studies_small_meshes_against_the_reference_csvs(kind, met
     against the stored CSVs.  Wherever the quadrature is exact for the polynomial integrands the CSVs come back to 8-15
     digits (IP plane with the legacy boundary form it was produced with; LDG p = 2 for both interfaces); LDG p = 1 plane
     runs with a 2-point rule that is not exact on cut pieces and still agrees to 1e-3 because the rule construction is
-    the reference's.  Not pinned that closely: IP curved (1-3 %: the stored file predates the current code in a way
-    neither boundary form recovers) and LDG p = 1 curved (2-point rule on curved pieces: 0.86 ... 1.8 of the CSV)."""
+    the reference's.  The IP curved file is reproduced (1e-5 at n = 3, 4e-9 at n = 9) by the legacy boundary form on a level
+    set of ORDER 1 -- the settings it must have been written with; the script's present levelsetorder = 2 gives 1-3 %.
+    Likewise the p = 1 columns of the LDG curved file come back (1e-5 ... 1e-9) with the 4-point rule, not with the 2-point
+    rule the script now asks for (0.86 ... 1.8 of the CSV)."""
     nc = 1 if method == "ip" else 3
     for row in GOLD[f"{method}_{kind}"][:3]:
         n = row[0]
