@@ -15,7 +15,7 @@ numqp = required_quadrature_order(p) + 2.  What changes against the Julia script
                                         flux variable against its gradient, as :163-171 does)
 Geometry: stefanproblem_b200.cutcell.LevelSetCutMesh, the Q2 interpolant of circle_distance_function with
 height-function Gauss rules (the reference's construction).  The stored CSV is reproduced to 6 digits in all six
-columns at n = 3, 9, 17, 33 and to 1e-3 at n = 5 (where the circle passes exactly through level-set nodes).
+columns at n = 3, 9, 17, 33 and to 1e-3 at n = 5.
 
     python examples/cylinder_ldg_convergence.py [coo]
 """
