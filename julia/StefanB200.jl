@@ -211,6 +211,10 @@ mutable struct BlockSystem
         b
     end
 end
+"Boundary form of the block path: 0 = current, 1 = legacy_boundary (what the reference's stored cut-cell IP files were
+produced with; stefan_blocks_set_variant).  Call before `assemble!`."
+set_variant!(b::BlockSystem, variant::Integer) =
+    check(ccall((:stefan_blocks_set_variant, lib), Cint, (Ptr{Cvoid}, Int32), b.handle, variant))
 assemble!(b::BlockSystem, data::BlocksData) =
     check(ccall((:stefan_blocks_assemble, lib), Cint, (Ptr{Cvoid}, Ref{BlocksData}, Ptr{Cvoid}),
                 b.handle, Ref(data), CUDA.stream().handle))
