@@ -60,6 +60,13 @@ constexpr int kFdTile = kFdThreads * kFdPerThread;
 constexpr int kFdHalo = 4;  // 3 needed; 4 keeps the tile loads 32-byte aligned
 
 // MODE 0: y = K u.  MODE 1: y = u + dt * kappa(phase) * (K u) on Laplace rows, u elsewhere.
+// the central row and the explicit update, with the roundings spelled out: the fast path, the general path of the vector
+// kernel and the scalar kernel must give the same bits (a slab split moves nodes from one path to the other; tests compare with torch.equal)
+__device__ __forceinline__ double fd_central(const double* c, double inv_h2) {
+  return __dmul_rn(__dadd_rn(__fma_rn(-2.0, c[0], c[-1]), c[1]), inv_h2);
+}
+__device__ __forceinline__ double fd_update(double c0, double coef, double t) { return __fma_rn(coef, t, c0); }
+
 template <int MODE>
 __global__ void __launch_bounds__(kFdThreads)
 fd_apply_kernel(const double* __restrict__ u, const double* __restrict__ u_lo,
@@ -90,7 +97,7 @@ fd_apply_kernel(const double* __restrict__ u, const double* __restrict__ u_lo,
     const uint8_t kd = kind[g];
     double r = 0.0;
     switch (kd & 7) {
-      case FD_CENTRAL: r = (c[-1] - 2.0 * c[0] + c[1]) * inv_h2; break;
+      case FD_CENTRAL: r = fd_central(c, inv_h2); break;
       case FD_BACKWARD: r = (-c[-3] + 4.0 * c[-2] - 5.0 * c[-1] + 2.0 * c[0]) * inv_h2; break;
       case FD_FORWARD: r = (2.0 * c[0] - 5.0 * c[1] + 4.0 * c[2] - c[3]) * inv_h2; break;
       case FD_IDENTITY: r = c[0]; break;
@@ -109,7 +116,7 @@ fd_apply_kernel(const double* __restrict__ u, const double* __restrict__ u_lo,
     } else {
       const int row = kd & 7;
       const bool laplace = row == FD_CENTRAL || row == FD_BACKWARD || row == FD_FORWARD;
-      y[g] = laplace ? c[0] + ((kd & FD_PHASE2) ? dtk2 : dtk1) * r : c[0];
+      y[g] = laplace ? fd_update(c[0], (kd & FD_PHASE2) ? dtk2 : dtk1, r) : c[0];
     }
   }
 }
@@ -188,13 +195,24 @@ fd_apply_vec(const double* __restrict__ u, const double* __restrict__ u_lo, cons
       const unsigned kinds = kcur;
       const bool any_cont = (kinds & (0x01010101u * FD_CONTINUITY)) != 0u;
       double r[4];
+      // fast path: four central rows without continuity terms (all but a handful of vectors of a mesh) -- straight-line
+      // code instead of the per-node row dispatch (ncu: the dispatch kept the issue slots 62 % busy)
+      if ((kinds & (0x01010101u * (7u | FD_CONTINUITY))) == 0x01010101u * FD_CENTRAL) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const double* c = w + 3 + k;
+          const double t = fd_central(c, inv_h2);
+          if (MODE == 0) r[k] = t;
+          else r[k] = fd_update(c[0], ((kinds >> (8 * k)) & FD_PHASE2) ? dtk2 : dtk1, t);
+        }
+      } else
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const double* c = w + 3 + k;
         const unsigned kd = (kinds >> (8 * k)) & 0xffu;
         const unsigned row = kd & 7u;
         double t = 0.0;
-        if (row == FD_CENTRAL) t = (c[-1] - 2.0 * c[0] + c[1]) * inv_h2;
+        if (row == FD_CENTRAL) t = fd_central(c, inv_h2);
         else if (row == FD_BACKWARD) t = (-c[-3] + 4.0 * c[-2] - 5.0 * c[-1] + 2.0 * c[0]) * inv_h2;
         else if (row == FD_FORWARD) t = (2.0 * c[0] - 5.0 * c[1] + 4.0 * c[2] - c[3]) * inv_h2;
         else if (row == FD_IDENTITY) t = c[0];
@@ -211,7 +229,7 @@ fd_apply_vec(const double* __restrict__ u, const double* __restrict__ u_lo, cons
           r[k] = t;
         } else {
           const bool laplace = row == FD_CENTRAL || row == FD_BACKWARD || row == FD_FORWARD;
-          r[k] = laplace ? c[0] + ((kd & FD_PHASE2) ? dtk2 : dtk1) * t : c[0];
+          r[k] = laplace ? fd_update(c[0], (kd & FD_PHASE2) ? dtk2 : dtk1, t) : c[0];
         }
       }
       if (g0 + 3 < n) {
