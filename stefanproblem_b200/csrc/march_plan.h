@@ -42,6 +42,7 @@ struct SegCache {
 struct MarchPlan {
   int nx = 0, ny = 0, nstrips = 0, ngroups = 0, group_warps = 0;
   std::vector<int> mixed_cum;    // [nstrips][nx+1] running count of phase-mixing columns
+  std::vector<int> p2_cum;       // [nstrips][nx+1] running count of columns whose stored cells are (mostly) phase 2
   std::vector<int> fix_col_ofs;  // the fix list is sorted by column: [nx+1] offsets
   std::vector<SegCache> seg_cache;
   int4* runs_dev = nullptr;
@@ -110,6 +111,7 @@ struct MarchPlan {
       }
     }
     mixed_cum.assign((size_t)nstrips * (nx + 1), 0);
+    p2_cum.assign((size_t)nstrips * (nx + 1), 0);
     for (int sidx = 0; sidx < nstrips; ++sidx) {
       run_ofs[sidx] = (int)runs.size();
       const uint32_t* sm = smask.data() + (size_t)sidx * nx;
@@ -130,6 +132,8 @@ struct MarchPlan {
       for (int k = 0; k < 3; ++k) runs.push_back(make_int4(INT_MAX, 0, 0, 0));  // sentinels
       int* cum = mixed_cum.data() + (size_t)sidx * (nx + 1);
       for (int i = 0; i < nx; ++i) cum[i + 1] = cum[i] + ((sm[i] != 0 && pm[i] != 0 && pm[i] != sm[i]) ? 1 : 0);
+      int* c2 = p2_cum.data() + (size_t)sidx * (nx + 1);
+      for (int i = 0; i < nx; ++i) c2[i + 1] = c2[i] + (2 * __builtin_popcount(pm[i]) > __builtin_popcount(sm[i]) ? 1 : 0);
     }
     run_ofs[nstrips] = (int)runs.size();
     nfix = (int)fix.size();
@@ -233,6 +237,34 @@ struct MarchPlan {
     // CTA order: segment-major = CTAs with neighbouring block indices work on neighbouring
     // strips of the same columns
     std::stable_sort(tiles.begin(), tiles.end(), [](const int4& a, const int4& b) { return a.w < b.w; });
+    // Experiment (STEFAN_TILE_PAIRING, default 0 = off): the two phase bodies of the order-2 / order-3 kernels together
+    // exceed the instruction cache, and an SM that hosts one CTA of each phase thrashes it.  Order the tiles so that
+    // the CTAs that share an SM work on the same phase: 1 = blocks b and b + n/2 are partners, 2 = blocks 2b, 2b + 1.
+    static const int pairing = [] { const char* e = getenv("STEFAN_TILE_PAIRING"); return e ? atoi(e) : 0; }();
+    if (pairing != 0 && tiles.size() >= 4) {
+      auto phase2_share = [&](const int4& t) {
+        int64_t p2 = 0, all = 0;
+        for (int sidx = t.x * gw; sidx < std::min(nstrips, (t.x + 1) * gw); ++sidx) {
+          const int* c2 = p2_cum.data() + (size_t)sidx * (nx + 1);
+          p2 += c2[t.z] - c2[t.y];
+          all += t.z - t.y;
+        }
+        return all ? (double)p2 / (double)all : 0.0;
+      };
+      std::vector<std::pair<double, int>> key(tiles.size());
+      for (size_t k = 0; k < tiles.size(); ++k) key[k] = {phase2_share(tiles[k]), (int)k};
+      std::stable_sort(key.begin(), key.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+      std::vector<int4> out(tiles.size());
+      const size_t half = (tiles.size() + 1) / 2;
+      for (size_t k = 0; k < tiles.size(); ++k) {
+        const size_t dst = pairing == 1 ? (k % 2 == 0 ? k / 2 : half + k / 2) : k;
+        out[std::min(dst, tiles.size() - 1)] = tiles[key[k].second];
+      }
+      if (pairing == 1 && tiles.size() % 2 == 1) {   // (odd count: the simple interleave above leaves a hole; fall back)
+        for (size_t k = 0; k < tiles.size(); ++k) out[k] = tiles[key[k].second];
+      }
+      tiles.swap(out);
+    }
     SegCache c;
     c.cbeg = cbeg;
     c.cend = cend;
