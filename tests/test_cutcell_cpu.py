@@ -62,18 +62,27 @@ def test_disk_rect_rules_integrate_polynomials(box, circle):
 
 
 @pytest.mark.parametrize("merge", [0.0, 0.25])
-def test_cut_mesh_geometry_is_consistent(merge):
+@pytest.mark.parametrize("generator", ["circle", "levelset2", "levelset1"])
+def test_cut_mesh_geometry_is_consistent(merge, generator):
     n, R = 9, 0.5
-    m = CircleCutMesh([0, 0], [1, 1], [n, n], [0, 0], R, 3, 1.0, 2.0, 1e3 * n, 1.0, merge_fraction=merge)
+    if generator == "circle":
+        m = CircleCutMesh([0, 0], [1, 1], [n, n], [0, 0], R, 3, 1.0, 2.0, 1e3 * n, 1.0, merge_fraction=merge)
+        tol_area, tol_len = 1e-6, 1e-12    # exact boundary; 3-point Gauss of the chord length
+    else:
+        order = 2 if generator == "levelset2" else 1
+        m = LevelSetCutMesh([0, 0], [1, 1], [n, n], lambda x, y: R - np.hypot(x, y), order, 3, 1.0, 2.0, 1e3 * n, 1.0,
+                            merge_fraction=merge)
+        tol_area, tol_len = (1e-6, 1e-5) if order == 2 else (2e-3, 4e-3)   # geometry of the Q2 / Q1 interpolant
     d = m.data
     detj = d["cell_jac"][:, 0] * d["cell_jac"][:, 1]
     area = (d["vol_wts"] * detj[:, None]).sum(axis=1)
     plus = m.sol_phase == 1
     assert abs(area.sum() - 1.0) < 1e-12                                # the pieces tile the square
-    assert abs(area[plus].sum() - np.pi * R * R / 4) < 1e-6             # quarter disk (exact boundary; 3-point Gauss of the chord length)
+    assert abs(area[plus].sum() - np.pi * R * R / 4) < tol_area         # quarter disk
     iface = m.slot_is_interface & (d["slot_nbr"] >= 0)
-    assert abs(d["face_wts"][iface & plus[:, None]].sum() - np.pi * R / 2) < 1e-12     # quarter circumference, once per side
-    assert abs(d["face_wts"][iface & ~plus[:, None]].sum() - np.pi * R / 2) < 1e-12
+    assert abs(d["face_wts"][iface & plus[:, None]].sum() - np.pi * R / 2) < tol_len     # quarter circumference, once per side
+    assert abs(d["face_wts"][iface & ~plus[:, None]].sum() - np.pi * R / 2) < tol_len
+    assert abs(d["face_wts"][iface & plus[:, None]].sum() - d["face_wts"][iface & ~plus[:, None]].sum()) < 1e-13
     bd = d["slot_nbr"] == -1
     assert abs(d["face_wts"][bd].sum() - 4.0) < 1e-12                   # the boundary of the square
     # every coupled slot has a partner slot on the neighbour with the same weights and opposite normals
